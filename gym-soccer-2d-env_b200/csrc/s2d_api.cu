@@ -1,0 +1,369 @@
+// s2d_api.cu - the C ABI of libsoccer2d.so (include/soccer2d.h) and the kernel launches behind it.
+//
+// Host side of the drop-in boundary for Soccer2DEnv.step/reset (soccer_2d_env.py:179-269): a handle holds
+// parameters and launch geometry only; every device buffer belongs to the caller.  Nothing here runs the
+// simulation on the CPU: without a CUDA device s2d_create fails with S2D_ERR_NO_DEVICE.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "s2d_reachball.cuh"
+
+using namespace s2d;
+
+struct S2DSim {
+  S2DConfig cfg;
+  S2DBuffers buf;
+  KernelParams kp;
+  float* d_dirs = nullptr;
+  bool bound = false;
+  int grid = 0;
+  uint64_t env_steps = 0;
+  char err[512];
+};
+
+static thread_local char g_create_err[512] = "";
+
+static int fail(S2DSim* h, int code, const char* fmt, ...) {
+  char* dst = h ? h->err : g_create_err;
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(dst, 512, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define S2D_CUDA(h, expr)                                                                              \
+  do {                                                                                                 \
+    cudaError_t err__ = (expr);                                                                        \
+    if (err__ != cudaSuccess)                                                                          \
+      return fail(h, S2D_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(err__), __FILE__, \
+                  __LINE__);                                                                           \
+  } while (0)
+
+// RAII: run on the handle's device without changing the caller's current device
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+};
+
+extern "C" {
+
+int s2d_abi_version(void) { return S2D_ABI_VERSION; }
+
+const char* s2d_error_string(int code) {
+  switch (code) {
+    case S2D_OK: return "ok";
+    case S2D_ERR_INVALID: return "invalid argument or configuration";
+    case S2D_ERR_UNBOUND: return "buffers not bound (s2d_bind) or a required buffer is NULL";
+    case S2D_ERR_CUDA: return "CUDA runtime error";
+    case S2D_ERR_NO_DEVICE: return "no usable CUDA device (there is no CPU fallback)";
+    default: return "unknown error code";
+  }
+}
+
+const char* s2d_last_error(S2DHandle h) { return h ? h->err : g_create_err; }
+
+int s2d_default_server_param(S2DServerParam* sp) {
+  if (!sp) return S2D_ERR_INVALID;
+  memset(sp, 0, sizeof(*sp));
+  // rcssserver defaults; names as in proto ServerParam / PlayerType (idl/service.proto:1435-1732)
+  sp->pitch_half_length = 52.5f; sp->pitch_half_width = 34.0f; sp->goal_width = 14.02f; sp->goal_post_radius = 0.06f;
+  sp->ball_size = 0.085f; sp->ball_decay = 0.94f; sp->ball_rand = 0.05f; sp->ball_speed_max = 3.0f; sp->ball_accel_max = 2.7f;
+  sp->player_size = 0.3f; sp->player_decay = 0.4f; sp->player_rand = 0.1f; sp->player_speed_max = 1.05f; sp->player_accel_max = 1.0f;
+  sp->dash_power_rate = 0.006f; sp->inertia_moment = 5.0f;
+  sp->min_dash_power = 0.0f; sp->max_dash_power = 100.0f; sp->min_dash_angle = -180.0f; sp->max_dash_angle = 180.0f;
+  sp->dash_angle_step = 1.0f; sp->side_dash_rate = 0.4f; sp->back_dash_rate = 0.7f;
+  sp->min_power = -100.0f; sp->max_power = 100.0f; sp->min_moment = -180.0f; sp->max_moment = 180.0f;
+  sp->kick_power_rate = 0.027f; sp->kickable_margin = 0.7f; sp->kick_rand = 0.1f;
+  sp->stamina_max = 8000.0f; sp->stamina_inc_max = 45.0f; sp->extra_stamina = 50.0f; sp->stamina_capacity = 130600.0f;
+  sp->recover_init = 1.0f; sp->recover_min = 0.5f; sp->recover_dec = 0.002f; sp->recover_dec_thr = 0.3f;
+  sp->effort_init = 1.0f; sp->effort_max = 1.0f; sp->effort_min = 0.6f; sp->effort_dec = 0.005f; sp->effort_dec_thr = 0.3f;
+  sp->effort_inc = 0.01f; sp->effort_inc_thr = 0.6f;
+  sp->slowness_on_top_for_left_team = 1.0f; sp->slowness_on_top_for_right_team = 1.0f;
+  return S2D_OK;
+}
+
+int s2d_default_config(S2DConfig* c, int scenario) {
+  if (!c) return S2D_ERR_INVALID;
+  memset(c, 0, sizeof(*c));
+  c->struct_size = static_cast<int32_t>(sizeof(S2DConfig));
+  c->scenario = scenario;
+  c->num_envs = 1;
+  c->action_mode = S2D_ACT_CONTINUOUS;  // reach_ball_env.py:34 use_continuous_action=True
+  c->action_space_size = 16;            // :35
+  c->max_steps = 200;                   // :33
+  c->auto_reset = 1;
+  c->change_ball_position = 1;          // :26
+  c->change_ball_velocity = 0;          // :27
+  c->players_per_side = scenario == S2D_SCENARIO_FULLGAME ? 11 : 1;
+  c->half_time_cycles = 3000;
+  c->min_distance_to_ball = 5.0f;       // :32
+  c->goto_dist_thr = 0.5f;
+  return s2d_default_server_param(&c->sp);
+}
+
+static bool config_ok(const S2DConfig* c, char* why, size_t n) {
+  if (!c) { snprintf(why, n, "config is NULL"); return false; }
+  if (c->struct_size != static_cast<int32_t>(sizeof(S2DConfig))) {
+    snprintf(why, n, "S2DConfig.struct_size %d != %zu (ABI mismatch)", c->struct_size, sizeof(S2DConfig));
+    return false;
+  }
+  if (c->num_envs < 1) { snprintf(why, n, "num_envs must be >= 1"); return false; }
+  if (c->scenario != S2D_SCENARIO_REACHBALL) { snprintf(why, n, "scenario %d is not available in this build", c->scenario); return false; }
+  if (c->action_mode < S2D_ACT_DISCRETE || c->action_mode > S2D_ACT_TURNING) {
+    snprintf(why, n, "action_mode %d is not valid for this scenario", c->action_mode);
+    return false;
+  }
+  if (c->action_mode == S2D_ACT_DISCRETE && (c->action_space_size < 1 || c->action_space_size > 256)) {
+    snprintf(why, n, "action_space_size must be in 1..256");
+    return false;
+  }
+  if (c->max_steps < 0) { snprintf(why, n, "max_steps must be >= 0"); return false; }
+  return true;
+}
+
+static size_t action_elem_bytes(const S2DConfig* c) {
+  switch (c->action_mode) {
+    case S2D_ACT_DISCRETE: return 1;
+    case S2D_ACT_CONTINUOUS: return 4;
+    case S2D_ACT_TURNING: return 16;
+    default: return 16 * static_cast<size_t>(s2d_num_players(c));
+  }
+}
+
+size_t s2d_state_bytes(const S2DConfig* c) { return c ? static_cast<size_t>(c->num_envs) * kStateBytesPerEnv : 0; }
+size_t s2d_action_bytes(const S2DConfig* c) { return c ? static_cast<size_t>(c->num_envs) * action_elem_bytes(c) : 0; }
+size_t s2d_stats_bytes(const S2DConfig* c) { return c ? sizeof(unsigned long long) * kStatSlots * kStatWords : 0; }
+int s2d_obs_dim(const S2DConfig* c) { return c ? kObsDim : 0; }
+int s2d_num_players(const S2DConfig* c) {
+  if (!c) return 0;
+  return c->scenario == S2D_SCENARIO_FULLGAME ? 2 * c->players_per_side : 1;
+}
+
+int s2d_create(const S2DConfig* cfg, S2DHandle* out) {
+  if (!out) return fail(nullptr, S2D_ERR_INVALID, "out handle pointer is NULL");
+  *out = nullptr;
+  char why[256];
+  if (!config_ok(cfg, why, sizeof(why))) return fail(nullptr, S2D_ERR_INVALID, "%s", why);
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
+    cudaGetLastError();
+    return fail(nullptr, S2D_ERR_NO_DEVICE, "no CUDA device is visible; libsoccer2d has no CPU path");
+  }
+  if (cfg->device < 0 || cfg->device >= ndev)
+    return fail(nullptr, S2D_ERR_INVALID, "device %d out of range (0..%d)", cfg->device, ndev - 1);
+  S2DSim* h = new (std::nothrow) S2DSim();
+  if (!h) return fail(nullptr, S2D_ERR_INVALID, "out of host memory");
+  h->cfg = *cfg;
+  h->err[0] = 0;
+  memset(&h->buf, 0, sizeof(h->buf));
+  DeviceGuard guard(cfg->device);
+
+  KernelParams& kp = h->kp;
+  memset(&kp, 0, sizeof(kp));
+  kp.sp = cfg->sp;
+  kp.num_envs = cfg->num_envs;
+  kp.env_id_offset = cfg->env_id_offset;
+  kp.seed = cfg->seed;
+  kp.scenario = cfg->scenario;
+  kp.action_mode = cfg->action_mode;
+  kp.action_space_size = cfg->action_space_size;
+  kp.max_steps = cfg->max_steps;
+  kp.auto_reset = cfg->auto_reset;
+  kp.change_ball_position = cfg->change_ball_position;
+  kp.change_ball_velocity = cfg->change_ball_velocity;
+  kp.noise = cfg->noise;
+  kp.min_distance_to_ball = cfg->min_distance_to_ball;
+  kp.ball_position_x = cfg->ball_position_x;
+  kp.ball_position_y = cfg->ball_position_y;
+  kp.ball_speed = cfg->ball_speed;
+  kp.ball_direction = cfg->ball_direction;
+  kp.goto_dist_thr = cfg->goto_dist_thr;
+  // reach_ball_env.py:207 - the reference uses 0.96 here, not the server's ball_decay
+  kp.travel_factor = static_cast<float>((1.0 - pow(0.96, static_cast<double>(cfg->max_steps))) / (1.0 - 0.96));
+
+  // Discrete(n) -> Dash direction, reach_ball_env.py:84, evaluated as the reference does (double, then the
+  // proto float)
+  float dirs[256];
+  const int n = cfg->action_space_size;
+  for (int a = 0; a < 256; ++a)
+    dirs[a] = n > 0 ? static_cast<float>(fmod(static_cast<double>(a) * 360.0 / static_cast<double>(n), 360.0) - 180.0) : 0.0f;
+  cudaError_t e = cudaMalloc(&h->d_dirs, sizeof(dirs));
+  if (e == cudaSuccess) e = cudaMemcpy(h->d_dirs, dirs, sizeof(dirs), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    fail(nullptr, S2D_ERR_CUDA, "allocating the action table failed: %s", cudaGetErrorString(e));
+    if (h->d_dirs) cudaFree(h->d_dirs);
+    delete h;
+    return S2D_ERR_CUDA;
+  }
+  kp.dash_dirs = h->d_dirs;
+  h->grid = static_cast<int>((cfg->num_envs + kBlock - 1) / kBlock);
+  *out = h;
+  return S2D_OK;
+}
+
+int s2d_destroy(S2DHandle h) {
+  if (!h) return S2D_OK;
+  {
+    DeviceGuard guard(h->cfg.device);
+    if (h->d_dirs) cudaFree(h->d_dirs);
+  }
+  delete h;
+  return S2D_OK;
+}
+
+int s2d_bind(S2DHandle h, const S2DBuffers* b) {
+  if (!h) return S2D_ERR_INVALID;
+  if (!b) return fail(h, S2D_ERR_INVALID, "buffers pointer is NULL");
+  if (!b->state || !b->actions || !b->obs || !b->reward || !b->done || !b->result || !b->stats)
+    return fail(h, S2D_ERR_UNBOUND, "state, actions, obs, reward, done, result and stats are required");
+  if ((reinterpret_cast<uintptr_t>(b->state) & 255) || (reinterpret_cast<uintptr_t>(b->actions) & 15) ||
+      (reinterpret_cast<uintptr_t>(b->obs) & 15) || (b->terminal_obs && (reinterpret_cast<uintptr_t>(b->terminal_obs) & 15)))
+    return fail(h, S2D_ERR_INVALID, "state must be 256-byte aligned; actions / obs / terminal_obs 16-byte aligned");
+  h->buf = *b;
+  h->kp.state = b->state;
+  h->kp.actions = b->actions;
+  h->kp.obs = b->obs;
+  h->kp.reward = b->reward;
+  h->kp.done = b->done;
+  h->kp.result = b->result;
+  h->kp.terminal_obs = b->terminal_obs;
+  h->kp.stats = static_cast<unsigned long long*>(b->stats);
+  h->bound = true;
+  return S2D_OK;
+}
+
+int s2d_reset(S2DHandle h, const uint8_t* device_mask_or_null, void* stream) {
+  if (!h) return S2D_ERR_INVALID;
+  if (!h->bound) return fail(h, S2D_ERR_UNBOUND, "s2d_bind has not been called");
+  DeviceGuard guard(h->cfg.device);
+  reachball_reset_kernel<<<h->grid, kBlock, 0, static_cast<cudaStream_t>(stream)>>>(h->kp, device_mask_or_null);
+  S2D_CUDA(h, cudaGetLastError());
+  return S2D_OK;
+}
+
+int s2d_step(S2DHandle h, int k_substeps, void* stream) {
+  if (!h) return S2D_ERR_INVALID;
+  if (!h->bound) return fail(h, S2D_ERR_UNBOUND, "s2d_bind has not been called");
+  if (k_substeps < 1) return fail(h, S2D_ERR_INVALID, "k_substeps must be >= 1");
+  DeviceGuard guard(h->cfg.device);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  switch (h->cfg.action_mode) {
+    case S2D_ACT_DISCRETE: reachball_step_kernel<S2D_ACT_DISCRETE><<<h->grid, kBlock, 0, s>>>(h->kp, k_substeps); break;
+    case S2D_ACT_CONTINUOUS: reachball_step_kernel<S2D_ACT_CONTINUOUS><<<h->grid, kBlock, 0, s>>>(h->kp, k_substeps); break;
+    default: reachball_step_kernel<S2D_ACT_TURNING><<<h->grid, kBlock, 0, s>>>(h->kp, k_substeps); break;
+  }
+  S2D_CUDA(h, cudaGetLastError());
+  h->env_steps += static_cast<uint64_t>(h->cfg.num_envs) * static_cast<uint64_t>(k_substeps);
+  return S2D_OK;
+}
+
+int s2d_step_host(S2DHandle h, int k_substeps, const void* h_actions, float* h_obs, float* h_reward, uint8_t* h_done,
+                  uint8_t* h_result, void* stream) {
+  if (!h) return S2D_ERR_INVALID;
+  if (!h->bound) return fail(h, S2D_ERR_UNBOUND, "s2d_bind has not been called");
+  if (!h_actions) return fail(h, S2D_ERR_INVALID, "h_actions is NULL");
+  if (k_substeps < 1) return fail(h, S2D_ERR_INVALID, "k_substeps must be >= 1");
+  DeviceGuard guard(h->cfg.device);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t n = static_cast<size_t>(h->cfg.num_envs);
+  S2D_CUDA(h, cudaMemcpyAsync(h->buf.actions, h_actions, s2d_action_bytes(&h->cfg) * k_substeps, cudaMemcpyHostToDevice, s));
+  const int rc = s2d_step(h, k_substeps, stream);
+  if (rc != S2D_OK) return rc;
+  if (h_obs) S2D_CUDA(h, cudaMemcpyAsync(h_obs, h->buf.obs, n * kObsDim * sizeof(float), cudaMemcpyDeviceToHost, s));
+  if (h_reward) S2D_CUDA(h, cudaMemcpyAsync(h_reward, h->buf.reward, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+  if (h_done) S2D_CUDA(h, cudaMemcpyAsync(h_done, h->buf.done, n, cudaMemcpyDeviceToHost, s));
+  if (h_result) S2D_CUDA(h, cudaMemcpyAsync(h_result, h->buf.result, n, cudaMemcpyDeviceToHost, s));
+  return S2D_OK;
+}
+
+int s2d_stats(S2DHandle h, S2DStats* out, void* stream) {
+  if (!h || !out) return S2D_ERR_INVALID;
+  if (!h->bound) return fail(h, S2D_ERR_UNBOUND, "s2d_bind has not been called");
+  DeviceGuard guard(h->cfg.device);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  std::vector<unsigned long long> host(kStatSlots * kStatWords);
+  S2D_CUDA(h, cudaMemcpyAsync(host.data(), h->buf.stats, host.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+  S2D_CUDA(h, cudaStreamSynchronize(s));
+  memset(out, 0, sizeof(*out));
+  for (int k = 0; k < kStatSlots; ++k) {
+    const unsigned long long* slot = host.data() + static_cast<size_t>(k) * kStatWords;
+    out->episodes += slot[ST_EPISODES];
+    out->goals += slot[ST_GOALS];
+    out->outs += slot[ST_OUTS];
+    out->timeouts += slot[ST_TIMEOUTS];
+    out->episode_steps += slot[ST_EP_STEPS];
+    double r;
+    memcpy(&r, slot + ST_RETURN, sizeof(r));
+    out->return_sum += r;
+  }
+  out->env_steps = h->env_steps;
+  return S2D_OK;
+}
+
+int s2d_stats_reset(S2DHandle h, void* stream) {
+  if (!h) return S2D_ERR_INVALID;
+  if (!h->bound) return fail(h, S2D_ERR_UNBOUND, "s2d_bind has not been called");
+  DeviceGuard guard(h->cfg.device);
+  S2D_CUDA(h, cudaMemsetAsync(h->buf.stats, 0, s2d_stats_bytes(&h->cfg), static_cast<cudaStream_t>(stream)));
+  h->env_steps = 0;
+  return S2D_OK;
+}
+
+int s2d_export_env(S2DHandle h, int64_t i, S2DEnvSnapshot* out, void* stream) {
+  if (!h || !out) return S2D_ERR_INVALID;
+  if (!h->bound) return fail(h, S2D_ERR_UNBOUND, "s2d_bind has not been called");
+  if (i < 0 || i >= h->cfg.num_envs) return fail(h, S2D_ERR_INVALID, "env index %lld out of range", static_cast<long long>(i));
+  DeviceGuard guard(h->cfg.device);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  float4 f[4];
+  uint4 u;
+  const char* base = static_cast<const char*>(h->buf.state);
+  const size_t n = static_cast<size_t>(h->cfg.num_envs);
+  for (int p = 0; p < 4; ++p)
+    S2D_CUDA(h, cudaMemcpyAsync(&f[p], base + (p * n + static_cast<size_t>(i)) * 16, 16, cudaMemcpyDeviceToHost, s));
+  S2D_CUDA(h, cudaMemcpyAsync(&u, base + (4 * n + static_cast<size_t>(i)) * 16, 16, cudaMemcpyDeviceToHost, s));
+  S2D_CUDA(h, cudaStreamSynchronize(s));
+  memset(out, 0, sizeof(*out));
+  out->cycle = static_cast<int32_t>(u.y);
+  out->game_mode_type = S2D_PM_PLAY_ON;  // the trainer forces PlayOn every cycle (soccer_2d_env.py:242)
+  out->game_mode_side = S2D_SIDE_LEFT;
+  out->step_number = static_cast<int32_t>(u.x);
+  out->episode = static_cast<int32_t>(u.z);
+  out->flags = static_cast<int32_t>(u.w);
+  out->ball_x = f[2].x; out->ball_y = f[2].y; out->ball_vx = f[2].z; out->ball_vy = f[2].w;
+  out->mem_distance_to_ball = f[3].x;
+  out->mem_body_ball_angle_diff = f[3].y;
+  out->episode_return = f[3].w;
+  out->ball_collided = (u.w & S2D_FLAG_BALL_COLLIDED) ? 1 : 0;
+  out->num_players = 1;
+  S2DPlayerSnapshot& p = out->players[0];
+  p.x = f[0].x; p.y = f[0].y; p.vx = f[0].z; p.vy = f[0].w;
+  p.body_direction = f[1].x; p.stamina = f[1].y; p.effort = f[1].z; p.recovery = f[1].w;
+  p.stamina_capacity = f[3].z;
+  p.side = S2D_SIDE_LEFT;
+  p.uniform_number = 1;  // DoMovePlayer(our_side=True, uniform_number=1), reach_ball_env.py:190-194
+  p.collided = (u.w & S2D_FLAG_PLAYER_COLLIDED) ? 1 : 0;
+  p.kicked = (u.w & S2D_FLAG_KICKED) ? 1 : 0;
+  return S2D_OK;
+}
+
+int s2d_launch_info(S2DHandle h, int* grid, int* block, int* kernels_per_step) {
+  if (!h) return S2D_ERR_INVALID;
+  if (grid) *grid = h->grid;
+  if (block) *block = kBlock;
+  if (kernels_per_step) *kernels_per_step = 1;
+  return S2D_OK;
+}
+
+}  // extern "C"

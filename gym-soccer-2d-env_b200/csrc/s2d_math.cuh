@@ -1,0 +1,156 @@
+// s2d_math.cuh - device math of the lockstep soccer simulator (sm_100a).
+//
+// fp32 SPEC.  Every value the simulator produces is defined by a fixed sequence of IEEE-754 binary32
+// operations: +, -, *, /, sqrt (all round-to-nearest: nvcc's default -prec-div/-prec-sqrt), rint, and
+// fused multiply-adds ONLY where this file writes __fmaf_rn.  The translation unit is compiled with
+// --fmad=false, so ptxas never contracts a*b+c on its own.  That makes results independent of compiler
+// scheduling and reproducible on any IEEE machine (the test oracle re-states the same sequence in C).
+//
+// Angles are DEGREES in [-180, 180] as in the proto fields (idl/service.proto:181-223) and in pyrusgeom's
+// AngleDeg (call sites sample_environments/reach_ball_env.py:89-96, :119-124).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace s2d {
+
+__device__ __forceinline__ float fmin_(float a, float b) { return a < b ? a : b; }
+__device__ __forceinline__ float fmax_(float a, float b) { return a > b ? a : b; }
+__device__ __forceinline__ float clampf(float lo, float x, float hi) { return fmax_(lo, fmin_(x, hi)); }
+
+__device__ __forceinline__ float hypot2(float x, float y) { return sqrtf(x * x + y * y); }
+
+// AngleDeg normalisation: fmod only beyond +-360, then one wrap.  Both ends of [-180, 180] are kept.
+__device__ __forceinline__ float norm_deg(float d) {
+  if (d < -360.0f || 360.0f < d) d = fmodf(d, 360.0f);
+  if (d < -180.0f) d += 360.0f;
+  if (d > 180.0f) d -= 360.0f;
+  return d;
+}
+
+// sin and cos of x degrees.  Quadrant reduction is exact in degrees (q*90 is exact, the fma has a single
+// rounding of an exactly representable result); the kernels are the classic single-precision minimax
+// polynomials for sin and cos on [-pi/4, pi/4].
+__device__ __forceinline__ void sincos_deg(float x, float& s, float& c) {
+  const float q = rintf(x * 0.011111111f);
+  const float r = __fmaf_rn(q, -90.0f, x);
+  const float t = r * 0.017453292f;
+  const float z = t * t;
+  float u = __fmaf_rn(z, -1.9515295891e-4f, 8.3321608736e-3f);
+  u = __fmaf_rn(z, u, -1.6666654611e-1f);
+  const float sp = __fmaf_rn(t * z, u, t);
+  float v = __fmaf_rn(z, 2.443315711809948e-5f, -1.388731625493765e-3f);
+  v = __fmaf_rn(z, v, 4.166664568298827e-2f);
+  const float cp = __fmaf_rn(z * z, v, __fmaf_rn(z, -0.5f, 1.0f));
+  const int n = static_cast<int>(q) & 3;
+  float ss = (n & 1) ? cp : sp;
+  float cc = (n & 1) ? sp : cp;
+  if (n == 1 || n == 2) cc = -cc;
+  if (n >= 2) ss = -ss;
+  s = ss;
+  c = cc;
+}
+
+// Vector2D::th() in degrees: octant reduction, ONE division, odd minimax polynomial; 0 for the zero vector.
+__device__ __forceinline__ float atan2_deg(float y, float x) {
+  const float ax = fabsf(x), ay = fabsf(y);
+  if (ax == 0.0f && ay == 0.0f) return 0.0f;
+  const bool swap = ay > ax;
+  const float mx = swap ? ay : ax, mn = swap ? ax : ay;
+  float num = mn, den = mx, off = 0.0f;
+  if (mn > 0.41421356f * mx) {
+    num = mn - mx;
+    den = mn + mx;
+    off = 45.0f;
+  }
+  const float a = num / den;
+  const float z = a * a;
+  float p = __fmaf_rn(z, 8.05374449538e-2f, -1.38776856032e-1f);
+  p = __fmaf_rn(z, p, 1.99777106478e-1f);
+  p = __fmaf_rn(z, p, -3.33329491539e-1f);
+  p = __fmaf_rn(p * z, a, a);
+  float r = __fmaf_rn(p, 57.29577951f, off);
+  if (swap) r = 90.0f - r;
+  if (x < 0.0f) r = 180.0f - r;
+  if (y < 0.0f) r = -r;
+  return r;
+}
+
+// e^x, |x| <= 88: Cody-Waite reduction by ln2 and a degree-6 polynomial, exponent patched in.
+__device__ __forceinline__ float exp_poly(float x) {
+  const float k = rintf(x * 1.44269504f);
+  float r = __fmaf_rn(k, -0.693359375f, x);
+  r = __fmaf_rn(k, 2.12194440e-4f, r);
+  float p = __fmaf_rn(r, 1.9875691500e-4f, 1.3981999507e-3f);
+  p = __fmaf_rn(r, p, 8.3334519073e-3f);
+  p = __fmaf_rn(r, p, 4.1665795894e-2f);
+  p = __fmaf_rn(r, p, 1.6666665459e-1f);
+  p = __fmaf_rn(r, p, 5.0000001201e-1f);
+  p = __fmaf_rn(p, r * r, r) + 1.0f;
+  return __int_as_float(__float_as_int(p) + (static_cast<int>(k) << 23));
+}
+
+// softmax([a, b])[0] = e^a / (e^a + e^b), written with one exponential
+__device__ __forceinline__ float softmax_first(float a, float b) { return 1.0f / (1.0f + exp_poly(b - a)); }
+
+// ------------------------------------------------------------------------------------------------------
+// Counter-based RNG: Philox4x32-10 (Salmon, Moraes, Dror, Shaw: "Parallel random numbers: as easy as
+// 1, 2, 3", SC'11).  key = the 64-bit seed; counter = (global env id lo, hi, index, purpose<<24 | sub).
+// `index` is the episode number for reset draws and the server cycle for per-step draws, so a stream never
+// depends on how envs are sharded over GPUs or how many substeps a launch fuses.
+// ------------------------------------------------------------------------------------------------------
+enum RngPurpose : uint32_t { RNG_RESET = 0, RNG_BALLVEL = 1, RNG_ACTION = 2, RNG_NOISE = 3 };
+
+__device__ __forceinline__ uint4 philox4x32_10(uint64_t seed, uint64_t env, uint32_t index, uint32_t purpose,
+                                               uint32_t sub) {
+  uint32_t c0 = static_cast<uint32_t>(env), c1 = static_cast<uint32_t>(env >> 32), c2 = index,
+           c3 = (purpose << 24) | sub;
+  uint32_t k0 = static_cast<uint32_t>(seed), k1 = static_cast<uint32_t>(seed >> 32);
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+    const uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+    c0 = h1 ^ c1 ^ k0;
+    c1 = l1;
+    c2 = h0 ^ c3 ^ k1;
+    c3 = l0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+
+// uniform integer in [lo, hi] (multiply-shift) - the role of random.randint at reach_ball_env.py:173-178
+__device__ __forceinline__ int u32_to_int(uint32_t u, int lo, int hi) {
+  return lo + static_cast<int>(__umulhi(u, static_cast<uint32_t>(hi - lo + 1)));
+}
+// uniform in [0, 1), 24 bits - the role of random.random at reach_ball_env.py:205
+__device__ __forceinline__ float u32_to_unit(uint32_t u) { return static_cast<float>(u >> 8) * (1.0f / 16777216.0f); }
+
+// 128-bit streaming accesses: state planes are touched exactly once per launch, so do not allocate in L1.
+__device__ __forceinline__ float4 ld_stream(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
+}
+__device__ __forceinline__ uint4 ld_stream(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void st_stream(float4* p, const float4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ void st_stream(uint4* p, const uint4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
+               "r"(v.w)
+               : "memory");
+}
+
+}  // namespace s2d

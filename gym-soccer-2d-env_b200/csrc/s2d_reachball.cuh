@@ -1,0 +1,351 @@
+// s2d_reachball.cuh - the ReachBall scenario fused into the lockstep kernels.
+//
+// Replaces, per env and per cycle, the whole of Soccer2DEnv.step (soccer_2d_env.py:226-269):
+//   decode_action      ReachBallEnv.action_to_rpc_actions      sample_environments/reach_ball_env.py:53-85
+//   simulate_cycle     the rcssserver cycle behind the gRPC round trip (server.py:49-103)
+//   check_episode      ReachBallEnv.check_trainer_observation  reach_ball_env.py:113-161
+//   write_obs          ReachBallEnv.state_to_observation       reach_ball_env.py:87-111
+//   reset_episode      Soccer2DEnv.env_reset + ReachBallEnv.abs_reset / trainer_reset_actions /
+//                      get_ball_velocity                       soccer_2d_env.py:179-224, reach_ball_env.py:163-218
+#pragma once
+#include "s2d_one_player.cuh"
+
+namespace s2d {
+
+constexpr int kObsDim = 10;       // reach_ball_env.py:48
+constexpr int kBallVelTries = 64; // bound on the rejection loop of reach_ball_env.py:204-212
+
+// Everything a kernel needs, passed by value as a __grid_constant__ (lives in the constant bank).
+struct KernelParams {
+  S2DServerParam sp;
+  int64_t num_envs;
+  int64_t env_id_offset;
+  uint64_t seed;
+  int32_t scenario, action_mode, action_space_size, max_steps;
+  int32_t auto_reset, change_ball_position, change_ball_velocity, noise;
+  float min_distance_to_ball, ball_position_x, ball_position_y, ball_speed, ball_direction;
+  float travel_factor;  // (1 - 0.96^max_steps) / (1 - 0.96), reach_ball_env.py:207
+  float goto_dist_thr;
+  // device buffers (caller-owned, see S2DBuffers)
+  void* state;
+  const void* actions;
+  float* obs;
+  float* reward;
+  uint8_t* done;
+  uint8_t* result;
+  float* terminal_obs;
+  unsigned long long* stats;  // [kStatSlots][kStatWords]
+  const float* dash_dirs;     // [256] Discrete(n) -> relative direction, built on the host at create
+};
+
+// episode statistics: slots spread the atomics over L2 lines; s2d_stats sums them
+constexpr int kStatSlots = 256;
+constexpr int kStatWords = 8;  // episodes, goals, outs, timeouts, episode_steps, return (double bits), pad, pad
+enum { ST_EPISODES = 0, ST_GOALS = 1, ST_OUTS = 2, ST_TIMEOUTS = 3, ST_EP_STEPS = 4, ST_RETURN = 5 };
+
+struct Tally {
+  uint32_t episodes = 0, goals = 0, outs = 0, timeouts = 0, ep_steps = 0;
+  float ret = 0.0f;
+};
+
+// reach_ball_env.py:113-161.  Rewards accumulate and later endings overwrite `result`, in the reference's
+// order Goal -> Out -> Timeout; leaving the pitch ADDS 10 (`reward -= -10.0`, :144).
+__device__ __forceinline__ bool check_episode(Episode& e, const KernelParams& P, float& reward, int& result) {
+  const float dx = e.bx - e.px, dy = e.by - e.py;
+  const float dist = hypot2(dx, dy);
+  const float diff = norm_deg(norm_deg(atan2_deg(dy, dx)) - norm_deg(e.body));
+  bool done = false;
+  result = S2D_RESULT_NONE;
+  reward = 0.0f;
+  reward += e.mem_dist - dist;
+  reward += (fabsf(norm_deg(e.mem_ang)) - fabsf(diff)) * static_cast<float>(1.0 / 180.0);
+  if (dist < P.min_distance_to_ball) {
+    done = true;
+    reward += 10.0f;
+    result = S2D_RESULT_GOAL;
+  }
+  if (fabsf(e.px) > 52.5f || fabsf(e.py) > 34.0f) {
+    done = true;
+    reward -= -10.0f;
+    result = S2D_RESULT_OUT;
+  }
+  if (e.step_number > P.max_steps) {
+    done = true;
+    reward -= 5.0f;
+    result = S2D_RESULT_TIMEOUT;
+  }
+  e.mem_dist = dist;
+  e.mem_ang = diff;
+  return done;
+}
+
+// reach_ball_env.py:87-111.  Must follow a check_episode on the same state: obs[0] is exactly the
+// body-to-ball angle that check just stored in mem_ang, so the atan2 is not repeated.
+__device__ __forceinline__ void build_obs(const Episode& e, float* o) {
+  const float speed = hypot2(e.bvx, e.bvy);
+  const float bdir = norm_deg(atan2_deg(e.bvy, e.bvx));
+  o[0] = e.mem_ang * static_cast<float>(1.0 / 180.0);
+  o[1] = norm_deg(e.body) * static_cast<float>(1.0 / 180.0);
+  o[2] = e.px * static_cast<float>(1.0 / 52.5);
+  o[3] = e.py * static_cast<float>(1.0 / 34.0);
+  o[4] = e.bx * static_cast<float>(1.0 / 52.5);
+  o[5] = e.by * static_cast<float>(1.0 / 34.0);
+  o[6] = speed * static_cast<float>(1.0 / 3.0);
+  o[7] = bdir * static_cast<float>(1.0 / 360.0);
+  o[8] = e.bvx * static_cast<float>(1.0 / 3.0);
+  o[9] = e.bvy * static_cast<float>(1.0 / 3.0);
+}
+
+// New episode: trainer_reset_actions' draws (integers: x in [-50,50], y in [-30,30], body in [0,360]; ball
+// velocity by bounded rejection), DoMoveBall / DoMovePlayer (vel = 0) / DoRecover, then ONE idle server cycle
+// (the reference's reset observes the state one cycle after placement) and the priming call of
+// check_trainer_observation whose reward is discarded (reach_ball_env.py:166).
+__device__ __noinline__ void reset_episode(Episode& e, const KernelParams& P, uint64_t gid) {
+  const uint4 w = philox4x32_10(P.seed, gid, e.episode, RNG_RESET, 0);
+  const float px = static_cast<float>(u32_to_int(w.x, -50, 50));
+  const float py = static_cast<float>(u32_to_int(w.y, -30, 30));
+  const float body = static_cast<float>(u32_to_int(w.z, 0, 360));
+  float bx, by;
+  if (P.change_ball_position) {
+    const uint4 w2 = philox4x32_10(P.seed, gid, e.episode, RNG_RESET, 1);
+    bx = static_cast<float>(u32_to_int(w.w, -50, 50));
+    by = static_cast<float>(u32_to_int(w2.x, -30, 30));
+  } else {
+    bx = P.ball_position_x;
+    by = P.ball_position_y;
+  }
+  float speed = 0.0f, d = 0.0f;
+  if (P.change_ball_velocity) {
+    uint4 wv = make_uint4(0, 0, 0, 0);
+#pragma unroll 1
+    for (int t = 0; t < kBallVelTries; ++t) {
+      if ((t & 1) == 0) wv = philox4x32_10(P.seed, gid, e.episode, RNG_BALLVEL, static_cast<uint32_t>(t >> 1));
+      const float s_try = u32_to_unit((t & 1) ? wv.z : wv.x) * 3.0f;
+      const float d_try = static_cast<float>(u32_to_int((t & 1) ? wv.w : wv.y, 0, 360));
+      const float travel = s_try * P.travel_factor;
+      float sn, cs;
+      sincos_deg(d_try, sn, cs);
+      if (fabsf(bx + travel * cs) <= 52.5f && fabsf(by + travel * sn) <= 34.0f) {
+        speed = s_try;
+        d = d_try;
+        break;
+      }
+    }
+  } else {
+    speed = P.ball_speed;
+    d = P.ball_direction;
+  }
+  float sn, cs;
+  sincos_deg(d, sn, cs);
+  e.episode += 1u;
+  e.step_number = 0;
+  e.ep_return = 0.0f;
+  e.bx = bx; e.by = by; e.bvx = speed * cs; e.bvy = speed * sn;
+  e.px = px; e.py = py; e.vx = 0.0f; e.vy = 0.0f;
+  e.body = norm_deg(body);
+  e.flags = 0u;
+  recover(e, P.sp);
+  simulate_cycle(e, S2D_CMD_NONE, 0.0f, 0.0f, P.sp);
+  float rw;
+  int rs;
+  check_episode(e, P, rw, rs);
+}
+
+// Coalesced write of one warp's observations: each lane parks its row in shared memory, then the warp
+// streams the 32 x 10 floats out as 80 float4 (512 contiguous bytes per store instruction).
+__device__ __forceinline__ void warp_store_obs(float* __restrict__ dst, int64_t warp_first_env, int64_t n,
+                                               const float* row, bool lane_valid, float* stage /* [320] */) {
+  const int lane = threadIdx.x & 31;
+  if (lane_valid) {
+#pragma unroll
+    for (int j = 0; j < kObsDim; ++j) stage[lane * kObsDim + j] = row[j];
+  }
+  __syncwarp();
+  const int64_t rows = (n - warp_first_env) < 32 ? (n - warp_first_env) : 32;
+  const int nvec = static_cast<int>(rows) * kObsDim / 4;  // full float4s
+  float4* out4 = reinterpret_cast<float4*>(dst + warp_first_env * kObsDim);  // 32*10*4 B = 1280 B: 16-B aligned
+  const float4* st4 = reinterpret_cast<const float4*>(stage);
+  for (int v = lane; v < nvec; v += 32) st_stream(out4 + v, st4[v]);
+  const int tail = static_cast<int>(rows) * kObsDim - nvec * 4;  // only in the last, ragged warp
+  if (lane < tail) dst[warp_first_env * kObsDim + nvec * 4 + lane] = stage[nvec * 4 + lane];
+  __syncwarp();
+}
+
+// Same idea for rows that only SOME lanes own (terminal observations): a masked, per-lane row store.
+__device__ __forceinline__ void lane_store_row(float* __restrict__ dst, int64_t env, const float* row) {
+  float2* o = reinterpret_cast<float2*>(dst + env * kObsDim);  // 40 B rows: 8-B aligned
+#pragma unroll
+  for (int j = 0; j < kObsDim / 2; ++j) o[j] = make_float2(row[2 * j], row[2 * j + 1]);
+}
+
+__device__ __forceinline__ void flush_tally(const Tally& t, unsigned long long* stats) {
+  const unsigned full = 0xffffffffu;
+  if (!__any_sync(full, t.episodes != 0)) return;
+  const uint32_t ep = __reduce_add_sync(full, t.episodes), g = __reduce_add_sync(full, t.goals),
+                 o = __reduce_add_sync(full, t.outs), to = __reduce_add_sync(full, t.timeouts),
+                 st = __reduce_add_sync(full, t.ep_steps);
+  double r = static_cast<double>(t.ret);
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) r += __shfl_xor_sync(full, r, s);
+  if ((threadIdx.x & 31) == 0) {
+    const unsigned warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    unsigned long long* slot = stats + static_cast<size_t>(warp_global % kStatSlots) * kStatWords;
+    atomicAdd(slot + ST_EPISODES, static_cast<unsigned long long>(ep));
+    if (g) atomicAdd(slot + ST_GOALS, static_cast<unsigned long long>(g));
+    if (o) atomicAdd(slot + ST_OUTS, static_cast<unsigned long long>(o));
+    if (to) atomicAdd(slot + ST_TIMEOUTS, static_cast<unsigned long long>(to));
+    atomicAdd(slot + ST_EP_STEPS, static_cast<unsigned long long>(st));
+    atomicAdd(reinterpret_cast<double*>(slot + ST_RETURN), r);
+  }
+}
+
+// ---- action fetch ---------------------------------------------------------------------------------
+// actions[N][K] (uint8 / float) or [N][K][4] (float).  A lane's K actions are contiguous; with K a multiple
+// of 16 (uint8) or 4 (float) they come in as 128-bit words, otherwise through the read-only path one by one.
+
+template <int ACT>
+struct ActionReader;
+
+template <>
+struct ActionReader<S2D_ACT_DISCRETE> {
+  const uint8_t* base;
+  bool vec;
+  uint4 w;
+  __device__ __forceinline__ ActionReader(const void* actions, int64_t i, int K)
+      : base(static_cast<const uint8_t*>(actions) + i * K), vec((K & 15) == 0), w(make_uint4(0, 0, 0, 0)) {}
+  __device__ __forceinline__ uint32_t get(int k) {
+    if (!vec) return __ldg(base + k);
+    if ((k & 15) == 0) w = __ldg(reinterpret_cast<const uint4*>(base + k));
+    const int j = k & 15;
+    const uint32_t word = (j < 4) ? w.x : (j < 8) ? w.y : (j < 12) ? w.z : w.w;
+    return (word >> ((j & 3) * 8)) & 0xffu;
+  }
+};
+
+template <>
+struct ActionReader<S2D_ACT_CONTINUOUS> {
+  const float* base;
+  bool vec;
+  float4 w;
+  __device__ __forceinline__ ActionReader(const void* actions, int64_t i, int K)
+      : base(static_cast<const float*>(actions) + i * K), vec((K & 3) == 0), w(make_float4(0, 0, 0, 0)) {}
+  __device__ __forceinline__ float get(int k) {
+    if (!vec) return __ldg(base + k);
+    if ((k & 3) == 0) w = __ldg(reinterpret_cast<const float4*>(base + k));
+    const int j = k & 3;
+    return j == 0 ? w.x : j == 1 ? w.y : j == 2 ? w.z : w.w;
+  }
+};
+
+template <>
+struct ActionReader<S2D_ACT_TURNING> {
+  const float4* base;
+  __device__ __forceinline__ ActionReader(const void* actions, int64_t i, int K)
+      : base(static_cast<const float4*>(actions) + i * K) {}
+  __device__ __forceinline__ float4 get(int k) { return __ldg(base + k); }
+};
+
+// ---- kernels --------------------------------------------------------------------------------------
+
+constexpr int kBlock = 256;
+
+// K lockstep cycles of every env in one launch; state stays in registers in between.
+template <int ACT>
+__global__ void __launch_bounds__(kBlock) reachball_step_kernel(const __grid_constant__ KernelParams P, const int K) {
+  __shared__ float s_dirs[256];
+  __shared__ __align__(16) float s_stage[kBlock / 32][32 * kObsDim];
+  if constexpr (ACT == S2D_ACT_DISCRETE) {
+    for (int a = threadIdx.x; a < 256; a += kBlock) s_dirs[a] = P.dash_dirs[a];
+    __syncthreads();
+  }
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * kBlock + threadIdx.x;
+  const int64_t n = P.num_envs;
+  const bool valid = i < n;
+  const uint64_t gid = static_cast<uint64_t>(P.env_id_offset + i);
+  float* stage = s_stage[threadIdx.x >> 5];
+  const int64_t warp_first = i - (threadIdx.x & 31);
+
+  Episode e;
+  Tally tally;
+  float reward_sum = 0.0f;
+  uint32_t any_done = 0, last_result = 0;
+  float obs_row[kObsDim];
+
+  if (valid) {
+    load_episode(P.state, n, i, e);
+    ActionReader<ACT> reader(P.actions, i, K);
+#pragma unroll 1
+    for (int k = 0; k < K; ++k) {
+      // ---- action decode (reach_ball_env.py:53-85): step_number counts calls
+      e.step_number += 1;
+      int cmd = S2D_CMD_DASH;
+      float power = 100.0f, dir;
+      if constexpr (ACT == S2D_ACT_DISCRETE) {
+        dir = s_dirs[reader.get(k)];
+      } else if constexpr (ACT == S2D_ACT_CONTINUOUS) {
+        dir = reader.get(k) * 180.0f;
+      } else {
+        const float4 a = reader.get(k);  // [turn_prob, turn_angle, dash_prob, dash_angle], :65-68
+        const float tp = clampf(-1.0f, a.x, 1.0f), ta = clampf(-1.0f, a.y, 1.0f);
+        const float dp = clampf(-1.0f, a.z, 1.0f), da = clampf(-1.0f, a.w, 1.0f);
+        const float u = u32_to_unit(philox4x32_10(P.seed, gid, e.cycle, RNG_ACTION, 0).x);
+        if (u < softmax_first(dp, tp)) {  // :69-72: tested against the DASH logit's weight, as the reference does
+          cmd = S2D_CMD_TURN;
+          power = 0.0f;
+          dir = ta * 180.0f;
+        } else {
+          dir = da * 180.0f;
+        }
+      }
+      simulate_cycle(e, cmd, power, dir, P.sp);
+      float rw;
+      int rs;
+      const bool done = check_episode(e, P, rw, rs);
+      reward_sum += rw;
+      e.ep_return += rw;
+      if (done) {
+        any_done = 1;
+        last_result = static_cast<uint32_t>(rs);
+        tally.episodes += 1;
+        tally.ep_steps += static_cast<uint32_t>(e.step_number);
+        tally.ret += e.ep_return;
+        tally.goals += rs == S2D_RESULT_GOAL;
+        tally.outs += rs == S2D_RESULT_OUT;
+        tally.timeouts += rs == S2D_RESULT_TIMEOUT;
+        if (P.terminal_obs) {
+          build_obs(e, obs_row);
+          lane_store_row(P.terminal_obs, i, obs_row);
+        }
+        if (P.auto_reset) reset_episode(e, P, gid);
+        else e.flags |= S2D_FLAG_DONE;
+      }
+    }
+    store_episode(P.state, n, i, e);
+    build_obs(e, obs_row);
+    P.reward[i] = reward_sum;
+    P.done[i] = static_cast<uint8_t>(any_done);
+    P.result[i] = static_cast<uint8_t>(last_result);
+  }
+  warp_store_obs(P.obs, warp_first, n, obs_row, valid, stage);
+  flush_tally(tally, P.stats);
+}
+
+// Soccer2DEnv.reset for every env (mask == nullptr) or the envs with a non-zero mask byte.
+__global__ void __launch_bounds__(kBlock) reachball_reset_kernel(const __grid_constant__ KernelParams P,
+                                                                 const uint8_t* __restrict__ mask) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * kBlock + threadIdx.x;
+  if (i >= P.num_envs) return;
+  if (mask && !mask[i]) return;
+  Episode e;
+  load_episode(P.state, P.num_envs, i, e);
+  reset_episode(e, P, static_cast<uint64_t>(P.env_id_offset + i));
+  store_episode(P.state, P.num_envs, i, e);
+  float row[kObsDim];
+  build_obs(e, row);
+  lane_store_row(P.obs, i, row);
+  P.reward[i] = 0.0f;
+  P.done[i] = 0;
+  P.result[i] = 0;
+}
+
+}  // namespace s2d

@@ -1,0 +1,312 @@
+"""Soccer2DVecEnv - N lockstep episodes held in GPU memory, stepped by libsoccer2d.so.
+
+Vectorised face of the reference's `Soccer2DEnv.step/reset` (soccer_2d_env.py:179-269) for the scenario
+classes of sample_environments/: instead of one env whose every step is a gRPC + UDP round trip to an
+external rcssserver, `num_envs` independent episodes advance together in one CUDA kernel launch.  The obs,
+reward, done and result tensors are persistent CUDA tensors that the kernel writes directly (zero copy).
+
+Duck-types stable_baselines3.common.vec_env.VecEnv (num_envs, observation_space, action_space, reset,
+step_async, step_wait, step, close, get_attr, set_attr, env_method, env_is_wrapped, seed) with auto-reset,
+`infos[i]['terminal_observation']` and `infos[i]['result']` (what utils/info_collector_callback.py:17-53
+tallies).  The torch-native calls (`reset_torch`, `step_torch`) return device tensors and build no infos.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _abi
+from .spaces import Box, Discrete
+
+# kwargs of ReachBallEnv.__init__ (sample_environments/reach_ball_env.py:26-36) with the reference defaults
+REACHBALL_DEFAULTS = dict(
+    change_ball_position=True, change_ball_velocity=False, ball_position_x=0, ball_position_y=0, ball_speed=0,
+    ball_direction=0, min_distance_to_ball=5.0, max_steps=200, use_continuous_action=True, action_space_size=16,
+    use_turning=False)
+
+_SCENARIOS = {"reachball": _abi.SCENARIO_REACHBALL}
+
+
+def _stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+class Soccer2DVecEnv:
+    """`num_envs` ReachBall episodes on one GPU.
+
+    num_envs       episodes held by THIS process (its shard)
+    scenario       "reachball" (case-insensitive, as environment_factory.py:25)
+    device         CUDA device; there is no CPU mode
+    seed           Philox key; with `env_id_offset` (global id of local env 0) it fixes every episode,
+                   independent of how envs are sharded over GPUs
+    substeps       K cycles fused per launch; actions then carry a K axis: [N, K(, A)]
+    auto_reset     finished episodes restart inside the kernel (VecEnv convention)
+    terminal_obs   also keep the last observation of finished episodes (needed for SB3 infos)
+    server_param   dict of overrides for the physics constants (proto ServerParam names)
+    **kwargs       the ReachBallEnv kwargs, same names and defaults as the reference
+    """
+
+    metadata = {"render.modes": ["human"]}  # soccer_2d_env.py:28
+
+    def __init__(self, num_envs: int, scenario: str = "reachball", device="cuda", seed: int = 0, substeps: int = 1,
+                 env_id_offset: int = 0, auto_reset: bool = True, terminal_obs: bool = False,
+                 server_param: dict | None = None, **kwargs):
+        if scenario.lower() not in _SCENARIOS:
+            raise ValueError(f"Environment {scenario} not found.")  # environment_factory.py:28
+        unknown = set(kwargs) - set(REACHBALL_DEFAULTS)
+        if unknown:
+            raise TypeError(f"unknown ReachBall kwargs: {sorted(unknown)}")
+        self.lib = _abi.load()
+        if not torch.cuda.is_available():
+            raise _abi.Soccer2DError(_abi.S2D_ERR_NO_DEVICE, "no CUDA device: soccer2d_b200 has no CPU fallback")
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise ValueError("Soccer2DVecEnv runs on CUDA devices only")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.num_envs = int(num_envs)
+        self.substeps = int(substeps)
+        self.kw = dict(REACHBALL_DEFAULTS, **kwargs)
+        for k, v in self.kw.items():
+            setattr(self, k, v)
+        self.seed_value = int(seed)
+        self.env_id_offset = int(env_id_offset)
+        self.auto_reset = bool(auto_reset)
+
+        cfg = _abi.Config()
+        _abi.check(self.lib.s2d_default_config(C.byref(cfg), _SCENARIOS[scenario.lower()]))
+        cfg.num_envs = self.num_envs
+        cfg.env_id_offset = self.env_id_offset
+        cfg.seed = self.seed_value & 0xFFFFFFFFFFFFFFFF
+        cfg.device = self.device.index
+        if self.kw["use_continuous_action"]:
+            cfg.action_mode = _abi.ACT_TURNING if self.kw["use_turning"] else _abi.ACT_CONTINUOUS
+        else:
+            cfg.action_mode = _abi.ACT_DISCRETE
+        cfg.action_space_size = int(self.kw["action_space_size"])
+        cfg.max_steps = int(self.kw["max_steps"])
+        cfg.auto_reset = int(self.auto_reset)
+        cfg.change_ball_position = int(bool(self.kw["change_ball_position"]))
+        cfg.change_ball_velocity = int(bool(self.kw["change_ball_velocity"]))
+        cfg.min_distance_to_ball = float(self.kw["min_distance_to_ball"])
+        cfg.ball_position_x = float(self.kw["ball_position_x"])
+        cfg.ball_position_y = float(self.kw["ball_position_y"])
+        cfg.ball_speed = float(self.kw["ball_speed"])
+        cfg.ball_direction = float(self.kw["ball_direction"])
+        for k, v in (server_param or {}).items():
+            if k not in _abi._SP_FIELDS:
+                raise KeyError(f"unknown ServerParam field {k!r}")
+            setattr(cfg.sp, k, float(v))
+        self.cfg = cfg
+        self.action_mode = cfg.action_mode
+
+        # spaces exactly as reach_ball_env.py:39-48
+        if cfg.action_mode == _abi.ACT_TURNING:
+            self.action_space = Box(low=np.array([-1, -1, -1, -1], dtype=np.float32),
+                                    high=np.array([1, 1, 1, 1], dtype=np.float32), dtype=np.float32)
+        elif cfg.action_mode == _abi.ACT_CONTINUOUS:
+            self.action_space = Box(low=-1, high=1, shape=(1,), dtype=np.float32)
+        else:
+            self.action_space = Discrete(cfg.action_space_size)
+        self.observation_space = Box(low=-1, high=1, shape=(10,), dtype=np.float32)
+
+        self.handle = C.c_void_p()
+        _abi.check(self.lib.s2d_create(C.byref(cfg), C.byref(self.handle)))
+
+        # ---- device buffers: owned here (PyTorch), bound into the handle ---------------------------
+        n, k, dev = self.num_envs, self.substeps, self.device
+        self.obs_dim = self.lib.s2d_obs_dim(C.byref(cfg))
+        self.state = torch.zeros(self.lib.s2d_state_bytes(C.byref(cfg)), dtype=torch.uint8, device=dev)
+        if cfg.action_mode == _abi.ACT_DISCRETE:
+            self.actions = torch.zeros((n, k), dtype=torch.uint8, device=dev)
+        elif cfg.action_mode == _abi.ACT_CONTINUOUS:
+            self.actions = torch.zeros((n, k), dtype=torch.float32, device=dev)
+        else:
+            self.actions = torch.zeros((n, k, 4), dtype=torch.float32, device=dev)
+        assert self.actions.numel() * self.actions.element_size() == self.lib.s2d_action_bytes(C.byref(cfg)) * k
+        self.obs = torch.zeros((n, self.obs_dim), dtype=torch.float32, device=dev)
+        self.reward = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.done_u8 = torch.zeros(n, dtype=torch.uint8, device=dev)
+        self.done = self.done_u8.view(torch.bool)
+        self.result = torch.zeros(n, dtype=torch.uint8, device=dev)
+        self.terminal_obs = torch.zeros((n, self.obs_dim), dtype=torch.float32, device=dev) if terminal_obs else None
+        self.stats_buf = torch.zeros(self.lib.s2d_stats_bytes(C.byref(cfg)), dtype=torch.uint8, device=dev)
+        self._bufs = bufs = _abi.Buffers(
+            state=self.state.data_ptr(), actions=self.actions.data_ptr(), obs=self.obs.data_ptr(),
+            reward=self.reward.data_ptr(), done=self.done_u8.data_ptr(), result=self.result.data_ptr(),
+            terminal_obs=self.terminal_obs.data_ptr() if terminal_obs else None, stats=self.stats_buf.data_ptr())
+        _abi.check(self.lib.s2d_bind(self.handle, C.byref(bufs)), self.handle)
+        self._pinned = None
+        self._pending = None
+        self._closed = False
+
+    # ---- torch-native API: device tensors in, device tensors out, no host sync ------------------------
+    def reset_torch(self, mask: torch.Tensor | None = None) -> torch.Tensor:
+        """New episode in every env, or in the envs where `mask` (bool/uint8 [N], on the device) is set."""
+        ptr = None
+        if mask is not None:
+            mask = mask.to(device=self.device).view(-1)
+            mask = mask.view(torch.uint8) if mask.dtype == torch.bool else mask.to(torch.uint8)
+            mask = mask.contiguous()
+            assert mask.numel() == self.num_envs
+            ptr = mask.data_ptr()
+        _abi.check(self.lib.s2d_reset(self.handle, ptr, _stream_ptr(self.device)), self.handle)
+        return self.obs
+
+    def step_torch(self, actions: torch.Tensor | None = None):
+        """One launch = `substeps` cycles of every env.  `actions=None` uses what is already in
+        `self.actions` (a policy may write there directly).  Returns (obs, reward, done, result): views of
+        the persistent tensors, valid until the next step."""
+        if actions is not None:
+            self.actions.copy_(actions.to(self.device).reshape(self.actions.shape), non_blocking=True)
+        _abi.check(self.lib.s2d_step(self.handle, self.substeps, _stream_ptr(self.device)), self.handle)
+        return self.obs, self.reward, self.done, self.result
+
+    def bind_actions(self, actions: torch.Tensor) -> None:
+        """Point the kernels at another device tensor of the same shape/dtype (no copy): lets a policy, or a
+        pool of pre-generated action blocks, feed the step without a device-to-device copy."""
+        assert actions.is_cuda and actions.device == self.device and actions.is_contiguous()
+        assert actions.shape == self.actions.shape and actions.dtype == self.actions.dtype
+        self.actions = actions
+        self._bufs.actions = actions.data_ptr()
+        _abi.check(self.lib.s2d_bind(self.handle, C.byref(self._bufs)), self.handle)
+
+    # ---- host API: host buffers in / host buffers out (the reference-facing call) --------------------
+    def host_buffers(self) -> dict:
+        """Pinned host staging tensors: 'actions' (fill it in place for zero-copy submission) and the
+        outputs 'obs', 'reward', 'done', 'result' that step_host fills."""
+        if self._pinned is None:
+            pin = lambda t: torch.empty(t.shape, dtype=t.dtype, pin_memory=True)  # noqa: E731
+            self._pinned = dict(actions=pin(self.actions), obs=pin(self.obs), reward=pin(self.reward),
+                                done=pin(self.done_u8), result=pin(self.result))
+        return self._pinned
+
+    def step_host(self, actions=None):
+        """Host actions in, host results out: H2D of the actions, the step launch and D2H of
+        obs/reward/done/result are enqueued by ONE C-ABI call (s2d_step_host), then the stream is drained.
+        `actions`: numpy array / CPU tensor of the action shape (pinned memory makes the copy asynchronous),
+        or None to submit host_buffers()['actions'].  Returns numpy views of the pinned output buffers."""
+        p = self.host_buffers()
+        if actions is None:
+            src = p["actions"]
+        elif isinstance(actions, torch.Tensor):
+            src = actions.to(dtype=self.actions.dtype).reshape(self.actions.shape).contiguous()
+            assert not src.is_cuda
+        else:
+            src = torch.from_numpy(np.ascontiguousarray(
+                np.asarray(actions).reshape(tuple(self.actions.shape)), dtype=p["actions"].numpy().dtype))
+        _abi.check(self.lib.s2d_step_host(self.handle, self.substeps, src.data_ptr(), p["obs"].data_ptr(),
+                                          p["reward"].data_ptr(), p["done"].data_ptr(), p["result"].data_ptr(),
+                                          _stream_ptr(self.device)), self.handle)
+        torch.cuda.current_stream(self.device).synchronize()
+        return p["obs"].numpy(), p["reward"].numpy(), p["done"].numpy().view(np.bool_), p["result"].numpy()
+
+    # ---- SB3 VecEnv surface ---------------------------------------------------------------------------
+    def reset(self) -> np.ndarray:
+        return self.reset_torch().cpu().numpy()
+
+    def step_async(self, actions) -> None:
+        self._pending = actions
+
+    def step_wait(self):
+        obs, reward, done, result = self.step_host(self._pending)
+        self._pending = None
+        infos = [{"result": None} for _ in range(self.num_envs)]
+        idx = np.nonzero(done)[0]
+        if idx.size:
+            term = self.terminal_obs.cpu().numpy() if self.terminal_obs is not None else None
+            for i in idx:
+                infos[i]["result"] = _abi.RESULT_NAMES[int(result[i])]
+                if term is not None:
+                    infos[i]["terminal_observation"] = term[i].copy()
+        return obs.copy(), reward.copy(), done.copy(), infos
+
+    def step(self, actions):
+        self.step_async(actions)
+        return self.step_wait()
+
+    def close(self) -> None:
+        if not self._closed:
+            self._closed = True
+            if self.handle:
+                self.lib.s2d_destroy(self.handle)
+                self.handle = C.c_void_p()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    def seed(self, seed=None):
+        return [None] * self.num_envs  # the Philox key is fixed at construction
+
+    def get_attr(self, attr_name, indices=None):
+        return [getattr(self, attr_name)] * len(self._indices(indices))
+
+    def set_attr(self, attr_name, value, indices=None):
+        raise AttributeError("episode parameters are fixed at construction (they are kernel constants)")
+
+    def env_method(self, method_name, *args, indices=None, **kwargs):
+        raise AttributeError(f"{method_name}: per-env Python methods do not exist on the GPU path")
+
+    def env_is_wrapped(self, wrapper_class, indices=None):
+        return [False] * len(self._indices(indices))
+
+    def render(self, mode="human"):
+        return None
+
+    def _indices(self, indices):
+        if indices is None:
+            return range(self.num_envs)
+        return [indices] if isinstance(indices, int) else indices
+
+    # ---- statistics, export, checkpoint ---------------------------------------------------------------
+    def stats(self) -> dict:
+        """Totals since construction / reset_stats(): what InfoCollectorCallback counts per 100 episodes
+        (utils/info_collector_callback.py:37-53), plus episode length and return sums."""
+        st = _abi.Stats()
+        _abi.check(self.lib.s2d_stats(self.handle, C.byref(st), _stream_ptr(self.device)), self.handle)
+        return {k: getattr(st, k) for k in
+                ("episodes", "goals", "outs", "timeouts", "episode_steps", "env_steps", "return_sum")}
+
+    def reset_stats(self) -> None:
+        _abi.check(self.lib.s2d_stats_reset(self.handle, _stream_ptr(self.device)), self.handle)
+
+    def allreduce_stats(self, group=None) -> dict:
+        """Sum of stats() over all ranks (one small all-reduce; NCCL when the process group is NCCL)."""
+        import torch.distributed as dist
+
+        st = self.stats()
+        keys = list(st)
+        if not (dist.is_available() and dist.is_initialized()):
+            return st
+        on_gpu = dist.get_backend(group) == "nccl"
+        t = torch.tensor([float(st[k]) for k in keys], dtype=torch.float64, device=self.device if on_gpu else "cpu")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        vals = t.cpu().tolist()
+        return {k: (v if k == "return_sum" else int(round(v))) for k, v in zip(keys, vals)}
+
+    def export_env(self, i: int) -> _abi.EnvSnapshot:
+        """Host snapshot of env `i`: the WorldModel fields the reference path reads (idl/service.proto:306-349)."""
+        snap = _abi.EnvSnapshot()
+        _abi.check(self.lib.s2d_export_env(self.handle, int(i), C.byref(snap), _stream_ptr(self.device)), self.handle)
+        return snap
+
+    def state_planes(self):
+        """Views of the SoA planes: (float32 [4, N, 4], int32 [N, 4]) - layout in DESIGN.md."""
+        n = self.num_envs
+        f = self.state[: 4 * n * 16].view(torch.float32).view(4, n, 4)
+        u = self.state[4 * n * 16:].view(torch.int32).view(n, 4)
+        return f, u
+
+    def state_dict(self) -> dict:
+        return {"state": self.state.clone(), "stats": self.stats_buf.clone(), "seed": self.seed_value,
+                "env_id_offset": self.env_id_offset, "num_envs": self.num_envs}
+
+    def load_state_dict(self, sd: dict) -> None:
+        assert sd["num_envs"] == self.num_envs and sd["seed"] == self.seed_value and sd["env_id_offset"] == self.env_id_offset
+        self.state.copy_(sd["state"])
+        self.stats_buf.copy_(sd["stats"])

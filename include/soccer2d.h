@@ -1,0 +1,212 @@
+/*
+ * soccer2d.h - C ABI of libsoccer2d.so: the batched lockstep 2D-soccer simulator (sm_100a).
+ *
+ * This is the drop-in boundary for ONE path of CLSFramework/gym-soccer-2d-env: Soccer2DEnv.step/reset.
+ * The reference has no FFI for this path - it crosses three process boundaries instead
+ * (multiprocessing.Queue x4, gRPC, rcssserver UDP).  Each entry point below names the reference
+ * interface it replaces (paths relative to the reference root):
+ *
+ *   s2d_create / s2d_destroy   Soccer2DEnv.__init__ / close        soccer_2d_env.py:30-95, :280-299
+ *                              (spawn gRPC server + rcssserver + proxy, _wait_for_agents)
+ *   s2d_reset                  Soccer2DEnv.reset -> env_reset      soccer_2d_env.py:179-224
+ *                              + ReachBallEnv.abs_reset /          sample_environments/reach_ball_env.py:163-197
+ *                                trainer_reset_actions (DoMoveBall, DoMovePlayer, DoRecover)
+ *   s2d_step / s2d_step_host   Soccer2DEnv.step                    soccer_2d_env.py:226-269
+ *                              = action_to_rpc_actions             reach_ball_env.py:53-85
+ *                              + GrpcAgent.GetPlayerActions /      server.py:49-67, :85-103
+ *                                GetTrainerActions round trip
+ *                              + one rcssserver cycle (external)   soccer_2d_env.py:356-383
+ *                              + state_to_observation              reach_ball_env.py:87-111
+ *                              + check_trainer_observation         reach_ball_env.py:113-161
+ *   s2d_stats                  InfoCollectorCallback tallies       utils/info_collector_callback.py:17-53
+ *   s2d_export_env             proto State/WorldModel of one env   idl/service.proto:306-359
+ *   S2DServerParam             proto ServerParam / PlayerType      idl/service.proto:1435-1732
+ *   S2D_PM_*, S2D_SIDE_*       proto GameModeType / Side           idl/service.proto:267-301, :88-92
+ *   S2D_CMD_*                  proto PlayerAction oneof            idl/service.proto:1291-1308
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 or a negative S2D_ERR_* code and
+ * never throws; s2d_last_error() gives the message.  All device buffers are owned by the caller (PyTorch
+ * tensors in the Python host); a handle owns only parameters and launch configuration.  A handle is bound
+ * to one CUDA device and is not thread-safe.  All work is enqueued on the caller's stream
+ * (`stream` = cudaStream_t as void*); nothing synchronises except s2d_stats and s2d_export_env.
+ */
+#ifndef SOCCER2D_H_
+#define SOCCER2D_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define S2D_ABI_VERSION 3
+
+/* error codes */
+#define S2D_OK 0
+#define S2D_ERR_INVALID (-1)   /* bad argument / config */
+#define S2D_ERR_UNBOUND (-2)   /* s2d_bind has not been called or a required buffer is NULL */
+#define S2D_ERR_CUDA (-3)      /* CUDA runtime error (message in s2d_last_error) */
+#define S2D_ERR_NO_DEVICE (-4) /* no usable CUDA device: there is NO CPU fallback */
+
+/* scenarios */
+#define S2D_SCENARIO_REACHBALL 0 /* sample_environments/reach_ball_env.py: 1 player + ball */
+#define S2D_SCENARIO_SHOOT 1     /* 1v0 shoot-on-goal: kick model + goal / ball-out detection */
+#define S2D_SCENARIO_FULLGAME 2  /* 11 v 11: dash/turn/kick, stamina, collisions, play modes */
+
+/* action encodings (reach_ball_env.py:39-47, :53-85) */
+#define S2D_ACT_DISCRETE 0   /* uint8  [N][K]      Discrete(n): Dash(100, (a*360/n)%360-180)      */
+#define S2D_ACT_CONTINUOUS 1 /* float  [N][K][1]   Box(-1,1,(1,)): Dash(100, a*180)               */
+#define S2D_ACT_TURNING 2    /* float  [N][K][4]   [turn_prob, turn_angle, dash_prob, dash_angle] */
+#define S2D_ACT_COMMAND 3    /* float4 [N][K][P]   {cmd, a, b, c} per player: see S2D_CMD_*       */
+
+/* S2D_ACT_COMMAND: cmd stored as a float; arguments as in the proto messages */
+#define S2D_CMD_NONE 0 /* no body command this cycle                                  */
+#define S2D_CMD_DASH 1 /* a = power, b = relative_direction   (service.proto:380-383) */
+#define S2D_CMD_TURN 2 /* a = relative_direction              (service.proto:390-392) */
+#define S2D_CMD_KICK 3 /* a = power, b = relative_direction   (service.proto:394-397) */
+#define S2D_CMD_GOTO 4 /* a,b = target x,y, c = max_dash_power; distance_threshold = S2DConfig.goto_dist_thr (:684-688) */
+
+/* episode results: info['result'] of reach_ball_env.py:126,140,145,150 */
+#define S2D_RESULT_NONE 0
+#define S2D_RESULT_GOAL 1
+#define S2D_RESULT_OUT 2
+#define S2D_RESULT_TIMEOUT 3
+
+/* play modes / sides (values = proto enums) */
+#define S2D_PM_BEFORE_KICK_OFF 0
+#define S2D_PM_TIME_OVER 1
+#define S2D_PM_PLAY_ON 2
+#define S2D_PM_KICK_OFF 3
+#define S2D_PM_KICK_IN 4
+#define S2D_PM_FREE_KICK 5
+#define S2D_PM_CORNER_KICK 6
+#define S2D_PM_GOAL_KICK 7
+#define S2D_PM_AFTER_GOAL 8
+#define S2D_SIDE_UNKNOWN 0
+#define S2D_SIDE_LEFT 1
+#define S2D_SIDE_RIGHT 2
+
+/* flag bits of the per-env `flags` word (state plane 4, .z) */
+#define S2D_FLAG_BALL_COLLIDED 0x1u   /* ball collided in the last simulated cycle   */
+#define S2D_FLAG_PLAYER_COLLIDED 0x2u /* player collided in the last simulated cycle */
+#define S2D_FLAG_KICKED 0x4u          /* a kick was applied in the last cycle        */
+#define S2D_FLAG_DONE 0x8u            /* episode ended and auto_reset is off         */
+
+/* Physics constants.  Field names = proto ServerParam / PlayerType; defaults = rcssserver's
+ * (s2d_default_server_param).  All float: the kernels compute in fp32. */
+typedef struct S2DServerParam {
+  float pitch_half_length, pitch_half_width, goal_width, goal_post_radius;
+  float ball_size, ball_decay, ball_rand, ball_speed_max, ball_accel_max;
+  float player_size, player_decay, player_rand, player_speed_max, player_accel_max;
+  float dash_power_rate, inertia_moment;
+  float min_dash_power, max_dash_power, min_dash_angle, max_dash_angle, dash_angle_step;
+  float side_dash_rate, back_dash_rate;
+  float min_power, max_power, min_moment, max_moment;
+  float kick_power_rate, kickable_margin, kick_rand;
+  float stamina_max, stamina_inc_max, extra_stamina, stamina_capacity;
+  float recover_init, recover_min, recover_dec, recover_dec_thr;
+  float effort_init, effort_max, effort_min, effort_dec, effort_dec_thr, effort_inc, effort_inc_thr;
+  float slowness_on_top_for_left_team, slowness_on_top_for_right_team;
+  float reserved[5];
+} S2DServerParam;
+
+typedef struct S2DConfig {
+  int32_t struct_size; /* sizeof(S2DConfig): checked by s2d_create */
+  int32_t scenario;    /* S2D_SCENARIO_* */
+  int64_t num_envs;    /* envs held by THIS handle (this rank's shard) */
+  int64_t env_id_offset; /* global id of local env 0: RNG is keyed on the global id, so shards reproduce */
+  uint64_t seed;
+  int32_t device;      /* CUDA device ordinal */
+  int32_t action_mode; /* S2D_ACT_* */
+  int32_t action_space_size; /* Discrete(n), n <= 256 */
+  int32_t max_steps;   /* reach_ball_env.py:33 */
+  int32_t auto_reset;  /* 1: a finished episode is re-drawn inside the step kernel (VecEnv convention) */
+  int32_t change_ball_position, change_ball_velocity; /* reach_ball_env.py:26-27 */
+  int32_t noise;       /* 0 = noise off (player_rand = ball_rand = kick_rand = 0) */
+  int32_t players_per_side; /* FULLGAME: 1..11 */
+  int32_t half_time_cycles; /* FULLGAME: cycles per half (rcssserver: 3000) */
+  float min_distance_to_ball; /* reach_ball_env.py:32 */
+  float ball_position_x, ball_position_y, ball_speed, ball_direction; /* reach_ball_env.py:28-31 */
+  float goto_dist_thr; /* Body_GoToPoint.distance_threshold for S2D_CMD_GOTO */
+  float reserved_f[3];
+  S2DServerParam sp;
+} S2DConfig;
+
+/* Device buffers, owned by the caller.  Sizes come from the s2d_*_bytes helpers. */
+typedef struct S2DBuffers {
+  void* state;         /* s2d_state_bytes(cfg), 256-B aligned; plane-major SoA (layout in DESIGN.md) */
+  void* actions;       /* k_max * s2d_action_bytes(cfg) */
+  float* obs;          /* [num_envs][s2d_obs_dim(cfg)] row-major fp32 */
+  float* reward;       /* [num_envs] (sum over the K substeps of one launch) */
+  uint8_t* done;       /* [num_envs] 1 if an episode ended during the launch */
+  uint8_t* result;     /* [num_envs] S2D_RESULT_* of the episode that ended (else 0) */
+  float* terminal_obs; /* optional [num_envs][obs_dim]: last observation of an episode that ended; may be NULL */
+  void* stats;         /* s2d_stats_bytes(cfg): per-warp partial accumulators */
+} S2DBuffers;
+
+/* Totals since create (or the last s2d_stats_reset): what InfoCollectorCallback tallies. */
+typedef struct S2DStats {
+  uint64_t episodes, goals, outs, timeouts;
+  uint64_t episode_steps; /* sum of episode lengths */
+  uint64_t env_steps;     /* env-steps simulated (incl. the extra reset cycles NOT counted) */
+  double return_sum;      /* sum of episode returns */
+  double reserved;
+} S2DStats;
+
+/* One env on the host: the fields of proto WorldModel the path consumes (idl/service.proto:306-349). */
+typedef struct S2DPlayerSnapshot {
+  float x, y, vx, vy, body_direction, stamina, effort, recovery, stamina_capacity;
+  int32_t side, uniform_number, collided, kicked;
+} S2DPlayerSnapshot;
+typedef struct S2DEnvSnapshot {
+  int32_t cycle, stoped_cycle, game_mode_type, game_mode_side;
+  int32_t step_number, episode, left_score, right_score;
+  float ball_x, ball_y, ball_vx, ball_vy;
+  float mem_distance_to_ball, mem_body_ball_angle_diff, episode_return;
+  int32_t ball_collided, num_players, flags;
+  S2DPlayerSnapshot players[22];
+} S2DEnvSnapshot;
+
+typedef struct S2DSim* S2DHandle;
+
+int s2d_abi_version(void);
+const char* s2d_error_string(int code);
+const char* s2d_last_error(S2DHandle h); /* h may be NULL: last create error */
+
+int s2d_default_server_param(S2DServerParam* out);
+int s2d_default_config(S2DConfig* out, int scenario);
+
+size_t s2d_state_bytes(const S2DConfig* cfg);
+size_t s2d_action_bytes(const S2DConfig* cfg); /* bytes of ONE substep's actions for all envs */
+size_t s2d_stats_bytes(const S2DConfig* cfg);
+int s2d_obs_dim(const S2DConfig* cfg);
+int s2d_num_players(const S2DConfig* cfg);
+
+int s2d_create(const S2DConfig* cfg, S2DHandle* out);
+int s2d_destroy(S2DHandle h);
+int s2d_bind(S2DHandle h, const S2DBuffers* buffers);
+
+/* Start a new episode in every env (mask == NULL) or in the envs whose device mask byte is non-zero;
+ * writes obs.  Equivalent of Soccer2DEnv.reset (placement, recover, one idle cycle, reward priming). */
+int s2d_reset(S2DHandle h, const uint8_t* device_mask_or_null, void* stream);
+
+/* Advance every env by k_substeps cycles in ONE kernel launch, reading actions[N][k] from buffers.actions. */
+int s2d_step(S2DHandle h, int k_substeps, void* stream);
+
+/* Same, with HOST buffers: copies actions host->device, steps, copies obs/reward/done/result back, all
+ * asynchronously on `stream` (use pinned memory).  Any of the h_* outputs may be NULL to skip that copy. */
+int s2d_step_host(S2DHandle h, int k_substeps, const void* h_actions, float* h_obs, float* h_reward,
+                  uint8_t* h_done, uint8_t* h_result, void* stream);
+
+int s2d_stats(S2DHandle h, S2DStats* host_out, void* stream);   /* reduces the partials; synchronises */
+int s2d_stats_reset(S2DHandle h, void* stream);
+int s2d_export_env(S2DHandle h, int64_t local_env, S2DEnvSnapshot* host_out, void* stream); /* synchronises */
+
+/* Launch geometry actually used (for bench.py's gpu_launches / DESIGN.md): blocks, threads, kernels per step call */
+int s2d_launch_info(S2DHandle h, int* grid, int* block, int* kernels_per_step);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SOCCER2D_H_ */

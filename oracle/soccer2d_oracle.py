@@ -95,6 +95,14 @@ class ServerParam:
     slowness_on_top_for_right_team: float = 1.0
     noise: bool = False  # "noise off" = player_rand = ball_rand = kick_rand = 0 (north_star)
 
+    def as_f32(self) -> "ServerParam":
+        """The same constants rounded to float32 - what a proto ServerParam message (all `float` fields,
+        idl/service.proto:1435-1662) and the C ABI's S2DServerParam carry."""
+        out = ServerParam()
+        for k, v in self.__dict__.items():
+            setattr(out, k, f32(v) if isinstance(v, float) else v)
+        return out
+
 
 # play-mode codes = proto GameModeType (idl/service.proto:267-301); sides = proto Side (:88-92)
 PM_BeforeKickOff, PM_TimeOver, PM_PlayOn, PM_KickOff, PM_KickIn, PM_FreeKick, PM_CornerKick, PM_GoalKick, PM_AfterGoal = range(9)

@@ -1,0 +1,73 @@
+"""Shared helpers for the parity tests."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "gym-soccer-2d-env_b200")
+for p in (ROOT, PKG, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+from soccer2d_b200 import _abi  # noqa: E402
+
+MODES = {"discrete": _abi.ACT_DISCRETE, "continuous": _abi.ACT_CONTINUOUS, "turning": _abi.ACT_TURNING}
+# obs columns that are angles / 180 or / 360: -1 and +1 (or -0.5 / +0.5) are the same direction
+OBS_ANGLE_PERIOD = {0: 2.0, 1: 2.0, 7: 1.0}
+# relative tolerance of the north star (1e-5) against the natural scale of each quantity
+TOL = 1.0e-5
+
+
+def make_config(num_envs, mode="discrete", **kw):
+    """S2DConfig with the reference defaults (s2d_default_config) and overrides; kwargs named like the
+    struct fields, plus `sp={...}` for ServerParam overrides."""
+    lib = _abi.load()
+    cfg = _abi.Config()
+    assert lib.s2d_default_config(C.byref(cfg), _abi.SCENARIO_REACHBALL) == 0
+    cfg.num_envs = num_envs
+    cfg.action_mode = MODES[mode] if isinstance(mode, str) else mode
+    sp = kw.pop("sp", {})
+    for k, v in kw.items():
+        assert hasattr(cfg, k), k
+        setattr(cfg, k, v)
+    for k, v in sp.items():
+        assert hasattr(cfg.sp, k), k
+        setattr(cfg.sp, k, v)
+    return cfg
+
+
+def random_actions(rng, mode, n, k=1, n_actions=16):
+    mode = MODES[mode] if isinstance(mode, str) else mode
+    if mode == _abi.ACT_DISCRETE:
+        return rng.integers(0, n_actions, size=(n, k)).astype(np.uint8)
+    if mode == _abi.ACT_CONTINUOUS:
+        return rng.uniform(-1, 1, size=(n, k)).astype(np.float32)
+    return rng.uniform(-1.25, 1.25, size=(n, k, 4)).astype(np.float32)
+
+
+def obs_close(a, b, tol=TOL):
+    """|a - b| <= tol per column, angles compared on the circle.  Obs columns are already normalised to O(1)."""
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    d = np.abs(a - b)
+    for col, period in OBS_ANGLE_PERIOD.items():
+        d[..., col] = np.minimum(d[..., col], np.abs(period - d[..., col]))
+    return d.max() if d.size else 0.0
+
+
+# natural scales for the 16 float state fields of oracle_lib.STATE_FIELDS (positions: pitch half length,
+# velocities: speed max, body / mem_ang: 180 deg, stamina: stamina_max, capacity: stamina_capacity, ...)
+STATE_SCALE = np.array([52.5, 34.0, 1.05, 1.05, 180.0, 8000.0, 1.0, 1.0, 130600.0, 52.5, 34.0, 3.0, 3.0,
+                        100.0, 180.0, 100.0])
+
+
+def state_err(a, b):
+    """max over envs of |a-b| / scale for the 16 float fields (angles on the circle)."""
+    a = np.asarray(a, np.float64)[..., :16]
+    b = np.asarray(b, np.float64)[..., :16]
+    d = np.abs(a - b)
+    for col in (4, 14):
+        d[..., col] = np.minimum(d[..., col], np.abs(360.0 - d[..., col]))
+    return (d / STATE_SCALE).max()

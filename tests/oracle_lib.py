@@ -1,0 +1,111 @@
+"""ctypes access to the C oracle (oracle/s2d_oracle.c -> oracle/_build/liboracle_{f64,f32}.so).  Test-side only."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+
+STATE_FIELDS = ("px py vx vy body stamina effort recovery capacity bx by bvx bvy mem_dist mem_ang ep_return "
+                "step_number cycle episode flags").split()
+
+
+def build():
+    subprocess.run(["make", "-s", "-C", ORACLE_DIR], check=True, capture_output=True)
+
+
+_libs = {}
+
+
+def lib(kind: str):
+    if kind not in _libs:
+        path = os.path.join(ORACLE_DIR, "_build", f"liboracle_{kind}.so")
+        src = os.path.join(ORACLE_DIR, "s2d_oracle.c")
+        if not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(src):
+            build()
+        L = C.CDLL(path)
+        L.s2do_create.restype = C.c_int
+        L.s2do_create.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+        L.s2do_destroy.argtypes = [C.c_void_p]
+        L.s2do_reset.argtypes = [C.c_void_p, C.c_void_p]
+        L.s2do_reset_masked.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.s2do_step.argtypes = [C.c_void_p] + [C.c_void_p, C.c_int] + [C.c_void_p] * 5
+        L.s2do_stats.argtypes = [C.c_void_p, C.c_void_p]
+        L.s2do_get_state.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
+        L.s2do_set_state.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
+        L.s2do_probe_sincos_deg.argtypes = [C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.s2do_probe_atan2_deg.restype = C.c_double
+        L.s2do_probe_atan2_deg.argtypes = [C.c_double, C.c_double]
+        L.s2do_probe_softmax_first.restype = C.c_double
+        L.s2do_probe_softmax_first.argtypes = [C.c_double, C.c_double]
+        L.s2do_probe_philox.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
+        _libs[kind] = L
+    return _libs[kind]
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class OracleSim:
+    """N ReachBall episodes stepped on the CPU by the C oracle.  kind = "f64" (truth) or "f32" (the bit-exact
+    mirror of the CUDA arithmetic).  `cfg` is a soccer2d_b200._abi.Config (same struct as S2DConfig)."""
+
+    def __init__(self, cfg, kind="f64"):
+        self.L = lib(kind)
+        self.kind = kind
+        self.real = np.float64 if kind == "f64" else np.float32
+        assert self.L.s2do_is_f32() == (kind == "f32")
+        self.cfg = cfg
+        self.n = int(cfg.num_envs)
+        self.h = C.c_void_p()
+        rc = self.L.s2do_create(C.byref(cfg), C.byref(self.h))
+        if rc != 0:
+            raise ValueError("oracle rejected the config")
+        self.obs = np.zeros((self.n, 10), self.real)
+        self.term_obs = np.zeros((self.n, 10), self.real)
+        self.reward = np.zeros(self.n, self.real)
+        self.done = np.zeros(self.n, np.uint8)
+        self.result = np.zeros(self.n, np.uint8)
+
+    def close(self):
+        if self.h is not None:
+            self.L.s2do_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # interpreter shutdown
+            pass
+
+    def reset(self, mask=None):
+        if mask is None:
+            self.L.s2do_reset(self.h, _ptr(self.obs))
+        else:
+            m = np.ascontiguousarray(mask, dtype=np.uint8)
+            self.L.s2do_reset_masked(self.h, _ptr(m), _ptr(self.obs))
+        return self.obs
+
+    def step(self, actions, k=1):
+        a = np.ascontiguousarray(actions)
+        self.L.s2do_step(self.h, _ptr(a), int(k), _ptr(self.obs), _ptr(self.reward), _ptr(self.done),
+                         _ptr(self.result), _ptr(self.term_obs))
+        return self.obs, self.reward, self.done, self.result
+
+    def stats(self, stats_struct):
+        self.L.s2do_stats(self.h, C.byref(stats_struct))
+        return stats_struct
+
+    def get_state(self, i=None):
+        if i is None:
+            return np.stack([self.get_state(j) for j in range(self.n)])
+        out = np.zeros(20, np.float64)
+        self.L.s2do_get_state(self.h, int(i), _ptr(out))
+        return out
+
+    def set_state(self, i, vec20):
+        v = np.ascontiguousarray(vec20, dtype=np.float64)
+        self.L.s2do_set_state(self.h, int(i), _ptr(v))

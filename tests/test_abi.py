@@ -1,0 +1,112 @@
+"""CPU-only checks of the drop-in boundary: the shared library loads, exports every symbol include/soccer2d.h
+declares, agrees with the header on struct sizes and defaults, and FAILS LOUDLY without a GPU (no CPU path)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+import helpers as H
+from soccer2d_b200 import _abi
+
+HEADER = os.path.join(H.ROOT, "include", "soccer2d.h")
+
+
+def _declared_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(s2d_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    names = _declared_functions()
+    assert len(names) >= 20
+    lib = C.CDLL(_abi.LIB_PATH)
+    for n in names:
+        assert hasattr(lib, n), f"{n} is declared in include/soccer2d.h but not exported"
+    assert sorted(_abi.SIGNATURES) == names  # the Python binding covers exactly the declared surface
+
+
+def test_abi_version_and_struct_sizes_match_the_header(tmp_path):
+    lib = _abi.load()
+    assert lib.s2d_abi_version() == _abi.ABI_VERSION
+    # ask the C compiler for the truth
+    prog = tmp_path / "sizes.c"
+    prog.write_text('#include <stdio.h>\n#include "soccer2d.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %d\\n",'
+                    "sizeof(S2DServerParam),sizeof(S2DConfig),sizeof(S2DBuffers),sizeof(S2DStats),"
+                    "sizeof(S2DPlayerSnapshot),sizeof(S2DEnvSnapshot),S2D_ABI_VERSION);return 0;}\n")
+    exe = tmp_path / "sizes"
+    subprocess.run(["gcc", "-I", os.path.dirname(HEADER), str(prog), "-o", str(exe)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    want = [C.sizeof(t) for t in (_abi.ServerParam, _abi.Config, _abi.Buffers, _abi.Stats, _abi.PlayerSnapshot,
+                                  _abi.EnvSnapshot)] + [_abi.ABI_VERSION]
+    assert got == want
+
+
+def test_defaults_are_the_reference_defaults(golden):
+    lib = _abi.load()
+    cfg = _abi.Config()
+    assert lib.s2d_default_config(C.byref(cfg), _abi.SCENARIO_REACHBALL) == 0
+    d = golden["spaces"]["envs"][0]["defaults"]  # produced by the reference's ReachBallEnv.__init__
+    assert cfg.max_steps == d["max_steps"] and cfg.action_space_size == d["action_space_size"]
+    assert cfg.min_distance_to_ball == d["min_distance_to_ball"]
+    assert bool(cfg.change_ball_position) == d["change_ball_position"]
+    assert bool(cfg.change_ball_velocity) == d["change_ball_velocity"]
+    assert (cfg.action_mode == _abi.ACT_CONTINUOUS) == (d["use_continuous_action"] and not d["use_turning"])
+    assert cfg.struct_size == C.sizeof(_abi.Config)
+    assert lib.s2d_obs_dim(C.byref(cfg)) == golden["spaces"]["envs"][0]["observation_space"]["shape"][0]
+    assert lib.s2d_num_players(C.byref(cfg)) == 1
+    cfg.num_envs = 1000
+    assert lib.s2d_state_bytes(C.byref(cfg)) == 80 * 1000
+    assert lib.s2d_action_bytes(C.byref(cfg)) == 4 * 1000
+    # rcssserver defaults, names = proto ServerParam
+    sp = cfg.sp
+    assert (sp.player_decay, sp.ball_decay, sp.dash_power_rate) == pytest.approx((0.4, 0.94, 0.006))
+    assert (sp.stamina_max, sp.stamina_inc_max, sp.kickable_margin) == pytest.approx((8000, 45, 0.7))
+
+
+def test_invalid_configs_are_rejected_with_a_message():
+    lib = _abi.load()
+    h = C.c_void_p()
+    cfg = H.make_config(4)
+    cfg.struct_size = 12
+    assert lib.s2d_create(C.byref(cfg), C.byref(h)) == _abi.S2D_ERR_INVALID
+    assert b"struct_size" in lib.s2d_last_error(None)
+    cfg = H.make_config(0)
+    assert lib.s2d_create(C.byref(cfg), C.byref(h)) == _abi.S2D_ERR_INVALID
+    cfg = H.make_config(4, action_space_size=300)
+    assert lib.s2d_create(C.byref(cfg), C.byref(h)) == _abi.S2D_ERR_INVALID
+    assert lib.s2d_create(None, C.byref(h)) == _abi.S2D_ERR_INVALID
+    assert lib.s2d_step(None, 1, None) == _abi.S2D_ERR_INVALID
+    assert lib.s2d_error_string(_abi.S2D_ERR_NO_DEVICE).startswith(b"no usable CUDA device")
+
+
+def test_no_gpu_means_error_not_fallback():
+    """In a container without a CUDA device the product path must refuse to run."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    lib = _abi.load()
+    h = C.c_void_p()
+    cfg = H.make_config(4)
+    assert lib.s2d_create(C.byref(cfg), C.byref(h)) == _abi.S2D_ERR_NO_DEVICE
+    assert not h.value
+    from soccer2d_b200 import Soccer2DError, Soccer2DVecEnv
+    with pytest.raises(Soccer2DError):
+        Soccer2DVecEnv(4)
+    from sample_environments.environment_factory import EnvironmentFactory
+    with pytest.raises(Soccer2DError):
+        EnvironmentFactory().create("ReachBall", None, None, "/tmp")
+    with pytest.raises(ValueError, match="Environment ReachCenter not found."):
+        EnvironmentFactory().create("ReachCenter", None, None, "/tmp")
+
+
+def test_product_never_imports_the_oracle():
+    pkg = H.PKG
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(root, f)).read()
+                assert "oracle" not in text.lower() or f == "s2d_math.cuh", f  # s2d_math.cuh mentions the test oracle in a comment
+                assert "import oracle" not in text and "from oracle" not in text and "liboracle" not in text

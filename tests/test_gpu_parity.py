@@ -1,0 +1,414 @@
+"""GPU parity tests (run on the B200 box with -m gpu).  Everything goes through the C ABI of libsoccer2d.so
+(via the Python host) and is checked against the CPU oracle on identical seeded inputs:
+
+  * bit-exact against the oracle's fp32 build (same operation order as the kernels): obs, reward, done,
+    result, terminal observations, full state, collision flags, statistics;
+  * against the oracle's f64 build (the "truth", rcssserver computes in double): flags bit-exact, floats
+    within 1e-5 relative to each quantity's scale over 1 000 cycles (the north-star tolerance);
+  * against the golden vectors produced by the reference's own reach_ball_env.py.
+"""
+import numpy as np
+import pytest
+import torch
+
+import helpers as H
+import oracle_lib as OL
+from soccer2d_b200 import Soccer2DVecEnv, _abi
+
+pytestmark = pytest.mark.gpu
+
+MODE_KW = {
+    "discrete": dict(use_continuous_action=False),
+    "continuous": dict(use_continuous_action=True, use_turning=False),
+    "turning": dict(use_continuous_action=True, use_turning=True),
+}
+
+
+def make_env(n, mode, **kw):
+    args = dict(MODE_KW[mode])
+    args.update(kw)
+    return Soccer2DVecEnv(n, device="cuda:0", **args)
+
+
+def gpu_state(env):
+    """[N, 20] float64 in the order of oracle_lib.STATE_FIELDS."""
+    f, u = env.state_planes()
+    f = f.cpu().numpy().astype(np.float64)
+    u = u.cpu().numpy().astype(np.int64)
+    out = np.zeros((env.num_envs, 20))
+    out[:, 0:4] = f[0]
+    out[:, 4:8] = f[1]
+    out[:, 8] = f[3][:, 2]
+    out[:, 9:13] = f[2]
+    out[:, 13:15] = f[3][:, 0:2]
+    out[:, 15] = f[3][:, 3]
+    out[:, 16:20] = u
+    return out
+
+
+def set_gpu_state(env, i, v):
+    f, u = env.state_planes()
+    v = [float(x) for x in v]
+    f[0, i] = torch.tensor(v[0:4], device=f.device)
+    f[1, i] = torch.tensor(v[4:8], device=f.device)
+    f[2, i] = torch.tensor(v[9:13], device=f.device)
+    f[3, i] = torch.tensor([v[13], v[14], v[8], v[15]], device=f.device)
+    u[i, :3] = torch.tensor([int(v[16]), int(v[17]), int(v[18])], dtype=torch.int32, device=u.device)
+
+
+def assert_same_step(env, sim, exact=True):
+    obs, rew = env.obs.cpu().numpy(), env.reward.cpu().numpy()
+    done, res = env.done_u8.cpu().numpy(), env.result.cpu().numpy()
+    assert np.array_equal(done, sim.done) and np.array_equal(res, sim.result)
+    if exact:
+        assert np.array_equal(obs, sim.obs)
+        assert np.array_equal(rew, sim.reward)
+        if env.terminal_obs is not None:
+            d = done.astype(bool)
+            assert np.array_equal(env.terminal_obs.cpu().numpy()[d], sim.term_obs[d])
+    else:
+        assert H.obs_close(obs, sim.obs) < H.TOL
+        assert np.abs(rew - sim.reward).max() < H.TOL * 100.0
+    return int(done.sum())
+
+
+@pytest.mark.parametrize("mode", ["discrete", "continuous", "turning"])
+def test_bit_exact_against_fp32_oracle_1000_cycles(mode):
+    n = 1000  # ragged: not a multiple of the warp or the block
+    env = make_env(n, mode, seed=7, change_ball_velocity=True, terminal_obs=True)
+    sim = OL.OracleSim(env.cfg, "f32")
+    assert np.array_equal(env.reset(), sim.reset())
+    assert np.array_equal(gpu_state(env), sim.get_state())
+    rng = np.random.default_rng(0)
+    episodes = 0
+    for t in range(1000):
+        act = H.random_actions(rng, mode, n)
+        env.step_torch(torch.from_numpy(act))
+        sim.step(act)
+        episodes += assert_same_step(env, sim)
+        if t % 100 == 99:
+            assert np.array_equal(gpu_state(env), sim.get_state())
+    assert episodes > 2 * n
+    st, so = env.stats(), sim.stats(_abi.Stats())
+    for k in ("episodes", "goals", "outs", "timeouts", "episode_steps", "env_steps"):
+        assert st[k] == getattr(so, k), k
+    assert st["return_sum"] == pytest.approx(so.return_sum, rel=1e-9)
+    assert st["episodes"] == st["goals"] + st["outs"] + st["timeouts"] == episodes
+    env.close()
+
+
+@pytest.mark.parametrize("mode", ["discrete", "continuous", "turning"])
+def test_against_f64_truth_1000_cycles(mode):
+    """north star: flags bit-exact, floats within 1e-5 relative over 1 000 cycles against the double oracle."""
+    n = 192
+    env = make_env(n, mode, seed=2024, change_ball_velocity=True)
+    sim = OL.OracleSim(env.cfg, "f64")
+    assert H.obs_close(env.reset(), sim.reset()) < H.TOL
+    rng = np.random.default_rng(5)
+    episodes = 0
+    for _ in range(1000):
+        act = H.random_actions(rng, mode, n)
+        env.step_torch(torch.from_numpy(act))
+        sim.step(act)
+        episodes += assert_same_step(env, sim, exact=False)
+    assert episodes > n
+    g, o = gpu_state(env), sim.get_state()
+    assert np.array_equal(g[:, 16:], o[:, 16:])  # step_number, cycle, episode, collision flags
+    assert H.state_err(g, o) < H.TOL
+    env.close()
+
+
+@pytest.mark.parametrize("mode,k", [("discrete", 16), ("discrete", 5), ("continuous", 8), ("continuous", 3), ("turning", 4)])
+def test_fused_substeps_equal_oracle_and_single_steps(mode, k):
+    n = 777
+    kw = dict(seed=3, change_ball_velocity=True, max_steps=40, terminal_obs=True)
+    env = make_env(n, mode, substeps=k, **kw)
+    one = make_env(n, mode, substeps=1, **kw)
+    sim = OL.OracleSim(env.cfg, "f32")
+    env.reset_torch()
+    one.reset_torch()
+    sim.reset()
+    rng = np.random.default_rng(9)
+    for _ in range(25):
+        act = H.random_actions(rng, mode, n, k)
+        env.step_torch(torch.from_numpy(act))
+        sim.step(act, k)
+        assert_same_step(env, sim)
+        for j in range(k):
+            one.step_torch(torch.from_numpy(np.ascontiguousarray(act[:, j:j + 1])))
+        assert torch.equal(env.obs, one.obs) and torch.equal(env.state, one.state)
+    assert np.array_equal(gpu_state(env), sim.get_state())
+    assert env.stats() == one.stats()
+    env.close()
+    one.close()
+
+
+def test_shards_reproduce_the_global_run():
+    """RNG is keyed on the GLOBAL env id: 3 shards (as 3 ranks would hold) == one big env."""
+    n, k = 3000, 4
+    kw = dict(seed=99, change_ball_velocity=True, max_steps=30, substeps=k)
+    whole = make_env(n, "discrete", **kw)
+    bounds = [0, 1000, 1900, 3000]
+    parts = [make_env(b - a, "discrete", env_id_offset=a, **kw) for a, b in zip(bounds[:-1], bounds[1:])]
+    whole.reset_torch()
+    for p in parts:
+        p.reset_torch()
+    rng = np.random.default_rng(2)
+    for _ in range(20):
+        act = H.random_actions(rng, "discrete", n, k)
+        whole.step_torch(torch.from_numpy(act))
+        for p, a, b in zip(parts, bounds[:-1], bounds[1:]):
+            p.step_torch(torch.from_numpy(act[a:b]))
+    assert torch.equal(whole.obs, torch.cat([p.obs for p in parts]))
+    assert torch.equal(whole.reward, torch.cat([p.reward for p in parts]))
+    assert np.array_equal(gpu_state(whole), np.concatenate([gpu_state(p) for p in parts]))
+    tot = {k_: sum(p.stats()[k_] for p in parts) for k_ in ("episodes", "goals", "outs", "timeouts", "episode_steps")}
+    assert all(whole.stats()[k_] == v for k_, v in tot.items())
+
+
+def test_masked_reset_and_no_auto_reset():
+    n = 300
+    env = make_env(n, "discrete", seed=4, auto_reset=False, max_steps=10, change_ball_velocity=True)
+    sim = OL.OracleSim(env.cfg, "f32")
+    env.reset_torch()
+    sim.reset()
+    rng = np.random.default_rng(1)
+    finished = np.zeros(n, bool)
+    for t in range(40):
+        act = H.random_actions(rng, "discrete", n)
+        env.step_torch(torch.from_numpy(act))
+        sim.step(act)
+        assert_same_step(env, sim)
+        g = gpu_state(env)
+        assert np.array_equal(g, sim.get_state())
+        # an env that finished keeps its DONE flag until it is reset (the reference keeps simulating too)
+        finished |= env.done.cpu().numpy()
+        assert np.array_equal((g[:, 19].astype(int) & _abi.FLAG_DONE) != 0, finished)
+        if t % 7 == 6:
+            mask = env.done.clone()
+            finished &= ~mask.cpu().numpy()
+            before = env.obs.clone()
+            env.reset_torch(mask)
+            sim.reset(mask.cpu().numpy())
+            assert np.array_equal(env.obs.cpu().numpy(), sim.obs)
+            keep = ~mask
+            assert torch.equal(env.obs[keep], before[keep])
+            assert np.array_equal(gpu_state(env), sim.get_state())
+
+
+@pytest.mark.parametrize("n", [1, 31, 33, 257])
+def test_ragged_sizes(n):
+    env = make_env(n, "continuous", seed=n, terminal_obs=True, max_steps=7)
+    sim = OL.OracleSim(env.cfg, "f32")
+    canary = env.obs.clone()
+    assert np.array_equal(env.reset(), sim.reset())
+    rng = np.random.default_rng(n)
+    for _ in range(30):
+        act = H.random_actions(rng, "continuous", n)
+        env.step_torch(torch.from_numpy(act))
+        sim.step(act)
+        assert_same_step(env, sim)
+    assert canary.shape == env.obs.shape
+
+
+def test_collisions_stamina_and_boundaries_match_oracle():
+    """Hand-placed states: ball inside the player (moving and at rest, centres coincident), player at the
+    pitch edge, exhausted stamina (effort / recovery decay), capacity nearly used up."""
+    cases = [
+        # px py vx vy body stamina effort recovery capacity | bx by bvx bvy | mem_dist mem_ang ep_ret | step cycle episode
+        [0, 0, 0.3, 0.1, 10, 8000, 1, 1, 130600, 0.2, 0.1, -1.0, 0.2, 1, 5, 0, 3, 3, 1],
+        [5, 5, 0, 0, 90, 8000, 1, 1, 130600, 5.1, 5.0, 0, 0, 1, 5, 0, 3, 3, 1],
+        [5, 5, 0, 0, 90, 8000, 1, 1, 130600, 5.0, 5.0, 0, 0, 1, 5, 0, 3, 3, 1],
+        [-7, 3, 0.5, 0.5, -120, 8000, 1, 1, 130600, -6.8, 3.3, 2.5, -1.0, 1, 5, 0, 3, 3, 1],
+        [52.3, 0, 0.6, 0, 0, 8000, 1, 1, 130600, 0, 0, 0, 0, 52, 0, 0, 3, 3, 1],
+        [0, -33.9, 0, -0.6, -90, 8000, 1, 1, 130600, 20, 0, 0, 0, 40, 0, 0, 3, 3, 1],
+        [10, 10, 0, 0, 0, 30, 0.7, 0.6, 130600, -20, 0, 0, 0, 30, 0, 0, 3, 3, 1],
+        [10, 10, 0, 0, 0, 0, 0.6, 0.5, 20, -20, 0, 0, 0, 30, 0, 0, 3, 3, 1],
+        [10, -10, 0, 0, 45, 2400, 1, 1, 130600, -20, 0, 3.0, 0, 30, 0, 0, 3, 3, 1],
+        [10, -10, 0, 0, 45, 4800, 0.9, 1, 0, -20, 0, 3.0, 0, 30, 0, 0, 3, 3, 1],
+    ]
+    n = len(cases)
+    env = make_env(n, "continuous", seed=1, min_distance_to_ball=0.05, max_steps=100000, terminal_obs=True)
+    sim = OL.OracleSim(env.cfg, "f32")
+    env.reset_torch()
+    sim.reset()
+    for i, c in enumerate(cases):
+        set_gpu_state(env, i, c + [0])
+        sim.set_state(i, np.array(c + [0], dtype=np.float64))
+    rng = np.random.default_rng(4)
+    seen_flags = 0
+    for _ in range(60):
+        act = H.random_actions(rng, "continuous", n)
+        act[6:8] = 0.0  # straight ahead: burns stamina as fast as possible
+        env.step_torch(torch.from_numpy(act))
+        sim.step(act)
+        assert_same_step(env, sim)
+        g = gpu_state(env)
+        assert np.array_equal(g, sim.get_state())
+        seen_flags |= int(np.bitwise_or.reduce(g[:, 19].astype(int)))
+    assert seen_flags & _abi.FLAG_BALL_COLLIDED and seen_flags & _abi.FLAG_PLAYER_COLLIDED
+    st = env.stats()
+    assert st["outs"] >= 2  # the two edge cases left the pitch
+
+
+def test_golden_obs_and_reward_from_the_reference_code(golden):
+    """The reference's own state_to_observation / check_trainer_observation outputs (tests/golden) against
+    the GPU.  A step is made the identity on the golden state: the ball starts one velocity behind with
+    ball_decay = 1, and dash_power_rate = 0 keeps the player in place."""
+    sp = dict(ball_decay=1.0, dash_power_rate=0.0, player_size=0.0, ball_size=0.0)  # sizes 0: no collisions
+    # --- observations
+    rows = golden["obs"]
+    n = len(rows)
+    env = make_env(n, "continuous", seed=0, server_param=sp, max_steps=10**6, min_distance_to_ball=0.0,
+                   auto_reset=False)
+    env.reset_torch()
+    for i, r in enumerate(rows):
+        bx, by, bvx, bvy, px, py, body = r["state"]
+        v = [px, py, 0, 0, body, 8000, 1, 1, 130600, np.float32(bx) - np.float32(bvx), np.float32(by) - np.float32(bvy),
+             bvx, bvy, 0, 0, 0, 0, 1, 1, 0]
+        set_gpu_state(env, i, v)
+    env.step_torch(torch.zeros((n, 1)))
+    got = env.obs.cpu().numpy()
+    want = np.array([r["obs"] for r in rows])
+    assert H.obs_close(got, want) < 2.0e-6
+    # --- reward / done / info chains (incl. the +10 on Out quirk and the 201st-step Timeout)
+    for chain in golden["reward"]:
+        steps = chain["steps"]
+        kw = chain["kwargs"]
+        env = make_env(1, "continuous", seed=0, server_param=sp, max_steps=kw["max_steps"],
+                       min_distance_to_ball=kw["min_distance_to_ball"], auto_reset=False)
+        env.reset_torch()
+        mem_d, mem_a = 0.0, 0.0
+        for s in steps:
+            bx, by, _, _, px, py, body = s["state"]
+            set_gpu_state(env, 0, [px, py, 0, 0, body, 8000, 1, 1, 130600, bx, by, 0, 0, mem_d, mem_a, 0,
+                                   s["step_number"] - 1, 1, 1, 0])
+            env.step_torch(torch.zeros((1, 1)))
+            assert bool(env.done[0]) == s["done"]
+            assert _abi.RESULT_NAMES[int(env.result[0])] == s["result"]
+            assert float(env.reward[0]) == pytest.approx(s["reward"], abs=2e-4)  # distances ~100 m in fp32
+            mem_d, mem_a = s["mem_dist"], s["mem_ang"]
+            snap = env.export_env(0)
+            assert snap.mem_distance_to_ball == pytest.approx(mem_d, rel=1e-6, abs=1e-5)
+            d = abs(snap.mem_body_ball_angle_diff - mem_a)
+            assert min(d, 360 - d) < 2e-4 or s["mem_dist"] < 1e-3
+        env.close()
+
+
+def test_decode_table_matches_reference_golden(golden):
+    """Discrete(n) -> Dash direction (reach_ball_env.py:84) for n in {16, 8, 36, 7}: one dash from rest moves
+    the player along body + rint(direction)."""
+    for n_act in (16, 8, 36, 7):
+        rows = [r for r in golden["decode"]["discrete"] if r["n"] == n_act]
+        env = make_env(n_act, "discrete", action_space_size=n_act, seed=1, max_steps=10**6, min_distance_to_ball=0.0)
+        env.reset_torch()
+        for a in range(n_act):
+            set_gpu_state(env, a, [0, 0, 0, 0, 0, 8000, 1, 1, 130600, 30, 30, 0, 0, 0, 0, 0, 0, 1, 1, 0])
+        env.step_torch(torch.arange(n_act, dtype=torch.uint8).view(-1, 1))
+        g = gpu_state(env)
+        for a in range(n_act):
+            want = np.rint(np.float32(rows[a]["dir"]))  # dash_angle_step = 1 snaps to whole degrees
+            got = np.degrees(np.arctan2(g[a, 1], g[a, 0]))
+            d = abs(got - want)
+            assert min(d, 360 - d) < 1e-3, (n_act, a)
+        env.close()
+
+
+def test_step_host_and_gym_api_match_torch_path():
+    from sample_environments.environment_factory import EnvironmentFactory
+
+    n = 513
+    a = make_env(n, "discrete", seed=8, change_ball_velocity=True, max_steps=25, terminal_obs=True)
+    b = make_env(n, "discrete", seed=8, change_ball_velocity=True, max_steps=25, terminal_obs=True)
+    assert np.array_equal(a.reset(), b.reset())
+    rng = np.random.default_rng(3)
+    dones = 0
+    for _ in range(60):
+        act = H.random_actions(rng, "discrete", n)
+        a.step_torch(torch.from_numpy(act))
+        obs, rew, done, infos = b.step(act[:, 0])
+        assert np.array_equal(obs, a.obs.cpu().numpy()) and np.array_equal(rew, a.reward.cpu().numpy())
+        assert np.array_equal(done, a.done.cpu().numpy())
+        for i in np.nonzero(done)[0]:
+            assert infos[i]["result"] in ("Goal", "Out", "Timeout")
+            assert np.array_equal(infos[i]["terminal_observation"], a.terminal_obs[i].cpu().numpy())
+            dones += 1
+        assert all(infos[i]["result"] is None for i in np.nonzero(~done)[0])
+    assert dones > n
+
+    # single-env gym API (old 4-tuple), against the fp32 oracle with auto_reset off
+    kwargs = dict(use_continuous_action=False, action_space_size=16, max_steps=30, change_ball_velocity=True)
+    env = EnvironmentFactory().create("ReachBall", None, None, "/tmp", seed=21, **kwargs)
+    assert env.action_space.n == 16 and env.observation_space.shape == (10,)
+    sim = OL.OracleSim(env._vec.cfg, "f32")
+    for episode in range(3):
+        obs = env.reset()
+        assert obs.shape == (10,) and np.array_equal(obs, sim.reset(np.ones(1, np.uint8))[0])
+        done = False
+        steps = 0
+        while not done:
+            act = int(rng.integers(16))
+            obs, reward, done, info = env.step(act)
+            sim.step(np.array([[act]], np.uint8))
+            assert np.array_equal(obs, sim.obs[0]) and reward == float(sim.reward[0]) and done == bool(sim.done[0])
+            assert info == {"result": _abi.RESULT_NAMES[int(sim.result[0])]}
+            steps += 1
+        assert info["result"] in ("Goal", "Out", "Timeout") and steps <= 31
+    env.close()
+    env.close()  # idempotent, the reference scripts call it twice (dqn_stable_baselines3.py:73,86)
+
+
+def test_unbound_and_bad_arguments_fail_loudly():
+    import ctypes as C
+    lib = _abi.load()
+    h = C.c_void_p()
+    cfg = H.make_config(64)
+    assert lib.s2d_create(C.byref(cfg), C.byref(h)) == 0
+    assert lib.s2d_step(h, 1, None) == _abi.S2D_ERR_UNBOUND
+    assert lib.s2d_reset(h, None, None) == _abi.S2D_ERR_UNBOUND
+    bufs = _abi.Buffers()
+    assert lib.s2d_bind(h, C.byref(bufs)) == _abi.S2D_ERR_UNBOUND
+    assert b"required" in lib.s2d_last_error(h)
+    assert lib.s2d_destroy(h) == 0
+    env = make_env(64, "discrete")
+    assert lib.s2d_step(env.handle, 0, None) == _abi.S2D_ERR_INVALID
+    cfg = H.make_config(64, device=99)
+    assert lib.s2d_create(C.byref(cfg), C.byref(h)) == _abi.S2D_ERR_INVALID
+
+
+def test_full_size_properties_1m_envs():
+    """BASELINE configs[1] size (2^20 envs, K = 16): size-independent properties instead of the oracle."""
+    n, k = 1 << 20, 16
+    kw = dict(seed=0, change_ball_velocity=True, substeps=k)
+    a = make_env(n, "discrete", **kw)
+    b = make_env(n, "discrete", substeps=1, seed=0, change_ball_velocity=True)
+    a.reset_torch()
+    b.reset_torch()
+    assert torch.equal(a.obs, b.obs)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    total_done = 0
+    for _ in range(14):  # 224 cycles: every env passes its 200-step timeout at least once
+        act = torch.randint(0, 16, (n, k), dtype=torch.uint8, device="cuda", generator=g)
+        a.step_torch(act)
+        for j in range(k):
+            b.step_torch(act[:, j:j + 1])
+        total_done += int(a.done.sum())
+    # determinism + fusion: 16 fused substeps == 16 single-step launches, bit for bit, on all 2^20 envs
+    assert torch.equal(a.state, b.state) and torch.equal(a.obs, b.obs)
+    f, u = a.state_planes()
+    sp = a.cfg.sp
+    speed = torch.hypot(f[0, :, 2], f[0, :, 3])
+    assert float(speed.max()) <= sp.player_speed_max * sp.player_decay * (1 + 1e-6)
+    assert float(torch.hypot(f[2, :, 2], f[2, :, 3]).max()) <= 3.0
+    assert float(f[1, :, 1].min()) >= 0.0 and float(f[1, :, 1].max()) <= sp.stamina_max
+    assert float(f[1, :, 2].min()) >= sp.effort_min and float(f[1, :, 2].max()) <= sp.effort_max
+    assert float(f[1, :, 0].abs().max()) <= 180.0
+    assert int(u[:, 0].max()) <= 200 and int(u[:, 0].min()) >= 0          # step_number
+    assert int(u[:, 1].min()) >= 224                                       # cycle counts the reset cycles too
+    assert bool(torch.isfinite(a.obs).all()) and float(a.obs[:, 0:2].abs().max()) <= 1.0
+    st = a.stats()
+    assert st["episodes"] == st["goals"] + st["outs"] + st["timeouts"] >= n
+    assert st["env_steps"] == n * k * 14 and st == b.stats() | {"return_sum": st["return_sum"]}
+    assert st["return_sum"] == pytest.approx(b.stats()["return_sum"], rel=1e-9)
+    assert int((u[:, 2] - 1).sum()) == st["episodes"]                      # episode counters add up
+    assert total_done > 0

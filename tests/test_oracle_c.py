@@ -1,0 +1,159 @@
+"""CPU-only: pins the C oracle (oracle/s2d_oracle.c) against the Python oracle (oracle/soccer2d_oracle.py, itself
+pinned to the reference by tests/test_oracle_contract.py), and bounds the fp32 spec against the f64 truth."""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+
+import helpers as H
+import oracle_lib as OL
+from oracle import soccer2d_oracle as O
+from soccer2d_b200 import _abi
+
+
+def test_philox_c_matches_known_answers():
+    L = OL.lib("f64")
+    out = (C.c_uint32 * 4)()
+    # counter = (env_lo, env_hi, index, purpose<<24|sub), key = seed -> Random123 known answers
+    L.s2do_probe_philox(0, 0, 0, 0, 0, out)
+    assert tuple(out) == (0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8)
+    L.s2do_probe_philox(0xFFFFFFFFFFFFFFFF, 0xFFFFFFFFFFFFFFFF, 0xFFFFFFFF, 0xFF, 0xFFFFFF, out)
+    assert tuple(out) == (0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD)
+    L.s2do_probe_philox(0x299F31D0A4093822, 0x85A308D3243F6A88, 0x13198A2E, 0x03, 0x707344, out)
+    assert tuple(out) == (0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1)
+    for seed, env, idx, purpose, sub in [(7, 123456789012, 55, 2, 0), (2**63 + 5, 3, 9, 1, 31)]:
+        L.s2do_probe_philox(seed, env, idx, purpose, sub, out)
+        assert tuple(out) == O.rng_block(seed, env, idx, purpose, sub)
+
+
+def test_fp32_math_spec_close_to_libm():
+    L = OL.lib("f32")
+    s, c = C.c_double(), C.c_double()
+    rng = np.random.default_rng(0)
+    xs = np.concatenate([np.arange(-720, 721, 0.5), rng.uniform(-400, 400, 4000)]).astype(np.float32)
+    worst = 0.0
+    for x in xs:
+        L.s2do_probe_sincos_deg(float(x), C.byref(s), C.byref(c))
+        r = math.radians(float(x))
+        worst = max(worst, abs(s.value - math.sin(r)), abs(c.value - math.cos(r)))
+    assert worst < 2.5e-7
+    # exact at the multiples of 90 degrees (what integer body directions and Discrete(16) actions hit)
+    for d, (es, ec) in {0: (0, 1), 90: (1, 0), 180: (0, -1), -90: (-1, 0), 270: (-1, 0), 360: (0, 1), -180: (0, -1)}.items():
+        L.s2do_probe_sincos_deg(float(d), C.byref(s), C.byref(c))
+        assert (s.value, c.value) == (es, ec)
+    worst = 0.0
+    pts = rng.uniform(-60, 60, (6000, 2)).astype(np.float32)
+    pts[:50, 0] = 0.0
+    pts[50:100, 1] = 0.0
+    for y, x in pts:
+        got = L.s2do_probe_atan2_deg(float(y), float(x))
+        want = O.atan2_deg(float(y), float(x))
+        d = abs(got - want)
+        worst = max(worst, min(d, 360 - d))
+    assert worst < 3.0e-5  # degrees; the f32 ulp at 180 is 1.5e-5
+    assert L.s2do_probe_atan2_deg(0.0, 0.0) == 0.0
+    worst = 0.0
+    for a, b in rng.uniform(-1, 1, (2000, 2)):
+        want = math.exp(a) / (math.exp(a) + math.exp(b))
+        worst = max(worst, abs(L.s2do_probe_softmax_first(float(np.float32(a)), float(np.float32(b))) - want))
+    assert worst < 2.0e-7
+
+
+def _py_oracles(cfg, kw, n):
+    pc = O.ReachBallConfig(seed=int(cfg.seed), sp=O.ServerParam().as_f32(), **kw)  # S2DServerParam is float
+    return [O.ReachBallOracle(pc, env_id=int(cfg.env_id_offset) + i, auto_reset=bool(cfg.auto_reset)) for i in range(n)]
+
+
+@pytest.mark.parametrize("mode", ["discrete", "continuous", "turning"])
+def test_c_f64_equals_python_oracle(mode):
+    """Same algorithm, two restatements (C and Python): trajectories must agree to rounding noise."""
+    n, steps = 6, 450
+    kw = dict(change_ball_position=True, change_ball_velocity=True, use_continuous_action=mode != "discrete",
+              use_turning=mode == "turning", max_steps=60, min_distance_to_ball=3.0)
+    cfg = H.make_config(n, mode, seed=11, env_id_offset=1000, change_ball_velocity=1, max_steps=60,
+                        min_distance_to_ball=3.0)
+    sim = OL.OracleSim(cfg, "f64")
+    py = _py_oracles(cfg, kw, n)
+    obs = sim.reset().copy()
+    for i, o in enumerate(py):
+        assert np.allclose(o.reset(), obs[i], rtol=0, atol=1e-12)
+    rng = np.random.default_rng(3)
+    results = set()
+    for _ in range(steps):
+        act = H.random_actions(rng, mode, n)
+        obs, rew, done, res = sim.step(act)
+        for i, o in enumerate(py):
+            a = act[i, 0]
+            po, pr, pd, pres, _ = o.step(a if mode != "continuous" else [a])
+            assert pd == bool(done[i]) and pres == int(res[i])
+            assert pr == pytest.approx(float(rew[i]), rel=1e-11, abs=1e-11)
+            assert H.obs_close(po, obs[i], 0) < 1e-11
+            results.add(pres)
+    assert results == {0, 1, 2, 3} or mode != "discrete" or results >= {0, 1, 3}
+    st = sim.stats(_abi.Stats())
+    assert st.episodes > 0 and st.env_steps == n * steps
+    assert st.episodes == st.goals + st.outs + st.timeouts
+
+
+def test_c_f64_k_substeps_equals_single_steps():
+    n, k, launches = 16, 8, 40
+    cfg = H.make_config(n, "discrete", seed=2, change_ball_velocity=1, max_steps=50)
+    a, b = OL.OracleSim(cfg, "f64"), OL.OracleSim(cfg, "f64")
+    a.reset()
+    b.reset()
+    rng = np.random.default_rng(0)
+    for _ in range(launches):
+        act = H.random_actions(rng, "discrete", n, k)
+        oa, ra, da, _ = a.step(act, k)
+        rsum = np.zeros(n)
+        dany = np.zeros(n, np.uint8)
+        for j in range(k):
+            ob, rb, db, _ = b.step(np.ascontiguousarray(act[:, j:j + 1]), 1)
+            rsum += rb
+            dany |= db
+        assert np.array_equal(oa, ob) and np.array_equal(da, dany)
+        assert np.allclose(ra, rsum, rtol=0, atol=1e-9)
+    assert np.array_equal(a.get_state(), b.get_state())
+
+
+@pytest.mark.parametrize("mode", ["discrete", "continuous", "turning"])
+def test_fp32_spec_tracks_f64_truth_1000_cycles(mode):
+    """The fp32 arithmetic the GPU uses (C f32 build) against the double-precision truth over 1 000 cycles:
+    flags bit-exact, floats within the north-star tolerance (1e-5 relative to each quantity's scale)."""
+    n = 192
+    cfg = H.make_config(n, mode, seed=2024, change_ball_velocity=1)
+    t, s = OL.OracleSim(cfg, "f64"), OL.OracleSim(cfg, "f32")
+    assert H.obs_close(t.reset(), s.reset()) < H.TOL
+    rng = np.random.default_rng(5)
+    episodes = 0
+    for _ in range(1000):
+        act = H.random_actions(rng, mode, n)
+        ot, rt, dt, rest = t.step(act)
+        os_, rs, ds, ress = s.step(act)
+        assert np.array_equal(dt, ds) and np.array_equal(rest, ress)
+        assert H.obs_close(ot, os_) < H.TOL
+        assert np.abs(rt - rs).max() < H.TOL * 100.0  # rewards are differences of distances (scale 100 m)
+        episodes += int(dt.sum())
+    assert episodes > n  # every env went through several resets on the way
+    st, ss = t.get_state(), s.get_state()
+    assert np.array_equal(st[:, 16:], ss[:, 16:])  # step_number, cycle, episode, collision flags
+    assert H.state_err(st, ss) < H.TOL
+
+
+def test_fp32_flag_flips_are_rare_and_near_thresholds():
+    """On a big batch a threshold test (dist < min_distance, |x| > 52.5) can land within fp32 rounding of
+    its threshold; count how often the fp32 spec and the f64 truth disagree on `done`."""
+    n = 4096
+    cfg = H.make_config(n, "continuous", seed=5, change_ball_velocity=1)
+    t, s = OL.OracleSim(cfg, "f64"), OL.OracleSim(cfg, "f32")
+    t.reset()
+    s.reset()
+    rng = np.random.default_rng(1)
+    alive = np.ones(n, bool)
+    for _ in range(400):
+        act = H.random_actions(rng, "continuous", n)
+        _, _, dt, _ = t.step(act)
+        _, _, ds, _ = s.step(act)
+        alive &= dt == ds
+    assert (~alive).sum() <= 4  # <= 1e-3 of the envs, ~2.5e-6 per env-step

@@ -170,34 +170,8 @@ int s2d_create(const S2DConfig* cfg, S2DHandle* out) {
   DeviceGuard guard(cfg->device);
 
   KernelParams& kp = h->kp;
-  memset(&kp, 0, sizeof(kp));
-  kp.sp = cfg->sp;
-  kp.num_envs = cfg->num_envs;
-  kp.env_id_offset = cfg->env_id_offset;
-  kp.seed = cfg->seed;
-  kp.scenario = cfg->scenario;
-  kp.action_mode = cfg->action_mode;
-  kp.action_space_size = cfg->action_space_size;
-  kp.max_steps = cfg->max_steps;
-  kp.auto_reset = cfg->auto_reset;
-  kp.change_ball_position = cfg->change_ball_position;
-  kp.change_ball_velocity = cfg->change_ball_velocity;
-  kp.noise = cfg->noise;
-  kp.min_distance_to_ball = cfg->min_distance_to_ball;
-  kp.ball_position_x = cfg->ball_position_x;
-  kp.ball_position_y = cfg->ball_position_y;
-  kp.ball_speed = cfg->ball_speed;
-  kp.ball_direction = cfg->ball_direction;
-  kp.goto_dist_thr = cfg->goto_dist_thr;
-  // reach_ball_env.py:207 - the reference uses 0.96 here, not the server's ball_decay
-  kp.travel_factor = static_cast<float>((1.0 - pow(0.96, static_cast<double>(cfg->max_steps))) / (1.0 - 0.96));
-
-  // Discrete(n) -> Dash direction, reach_ball_env.py:84, evaluated as the reference does (double, then the
-  // proto float)
   float dirs[256];
-  const int n = cfg->action_space_size;
-  for (int a = 0; a < 256; ++a)
-    dirs[a] = n > 0 ? static_cast<float>(fmod(static_cast<double>(a) * 360.0 / static_cast<double>(n), 360.0) - 180.0) : 0.0f;
+  make_kernel_params(*cfg, kp, dirs);
   cudaError_t e = cudaMalloc(&h->d_dirs, sizeof(dirs));
   if (e == cudaSuccess) e = cudaMemcpy(h->d_dirs, dirs, sizeof(dirs), cudaMemcpyHostToDevice);
   if (e != cudaSuccess) {

@@ -4,27 +4,44 @@
 // operations: +, -, *, /, sqrt (all round-to-nearest: nvcc's default -prec-div/-prec-sqrt), rint, and
 // fused multiply-adds ONLY where this file writes __fmaf_rn.  The translation unit is compiled with
 // --fmad=false, so ptxas never contracts a*b+c on its own.  That makes results independent of compiler
-// scheduling and reproducible on any IEEE machine (the test oracle re-states the same sequence in C).
+// scheduling and reproducible on any IEEE machine (the test suite re-states the same sequence in C).
 //
 // Angles are DEGREES in [-180, 180] as in the proto fields (idl/service.proto:181-223) and in pyrusgeom's
 // AngleDeg (call sites sample_environments/reach_ball_env.py:89-96, :119-124).
+//
+// S2D_HOST_EMU: tests/emu compiles the __device__ functions of csrc/ for the host (with a shim header for
+// the few CUDA built-ins) to check them bit for bit on a machine without a GPU.  The product library never
+// defines it.
 #pragma once
+#ifndef S2D_HOST_EMU
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 
 namespace s2d {
 
-__device__ __forceinline__ float fmin_(float a, float b) { return a < b ? a : b; }
-__device__ __forceinline__ float fmax_(float a, float b) { return a > b ? a : b; }
-__device__ __forceinline__ float clampf(float lo, float x, float hi) { return fmax_(lo, fmin_(x, hi)); }
+// min / max: FMNMX.  (NaN never occurs on valid states; the sign of a zero result is not significant.)
+__device__ __forceinline__ float fmin_(float a, float b) { return fminf(a, b); }
+__device__ __forceinline__ float fmax_(float a, float b) { return fmaxf(a, b); }
+__device__ __forceinline__ float clampf(float lo, float x, float hi) { return fmaxf(lo, fminf(x, hi)); }
 
 __device__ __forceinline__ float hypot2(float x, float y) { return sqrtf(x * x + y * y); }
 
+// cold paths kept out of line: they are (almost) never taken, and inlining them costs registers and I-cache
+__device__ __noinline__ float cold_fmod360(float d) { return fmodf(d, 360.0f); }
+__device__ __noinline__ float cold_div(float a, float b) { return a / b; }
+
 // AngleDeg normalisation: fmod only beyond +-360, then one wrap.  Both ends of [-180, 180] are kept.
 __device__ __forceinline__ float norm_deg(float d) {
-  if (d < -360.0f || 360.0f < d) d = fmodf(d, 360.0f);
+  if (d < -360.0f || 360.0f < d) d = cold_fmod360(d);
   if (d < -180.0f) d += 360.0f;
   if (d > 180.0f) d -= 360.0f;
+  return d;
+}
+// the same for |d| <= 360 (sum or difference of two normalised angles): the fmod is never reached
+__device__ __forceinline__ float norm_deg_360(float d) {
+  d = d < -180.0f ? d + 360.0f : d;
+  d = d > 180.0f ? d - 360.0f : d;
   return d;
 }
 
@@ -54,15 +71,14 @@ __device__ __forceinline__ void sincos_deg(float x, float& s, float& c) {
 // Vector2D::th() in degrees: octant reduction, ONE division, odd minimax polynomial; 0 for the zero vector.
 __device__ __forceinline__ float atan2_deg(float y, float x) {
   const float ax = fabsf(x), ay = fabsf(y);
-  if (ax == 0.0f && ay == 0.0f) return 0.0f;
   const bool swap = ay > ax;
   const float mx = swap ? ay : ax, mn = swap ? ax : ay;
-  float num = mn, den = mx, off = 0.0f;
-  if (mn > 0.41421356f * mx) {
-    num = mn - mx;
-    den = mn + mx;
-    off = 45.0f;
-  }
+  const bool upper = mn > 0.41421356f * mx;
+  const float num = upper ? mn - mx : mn;
+  float den = upper ? mn + mx : mx;
+  const float off = upper ? 45.0f : 0.0f;
+  const bool zero = mx == 0.0f;  // both components are zero
+  den = zero ? 1.0f : den;       // 0 / 1 = 0 -> polynomial gives 0 -> result 0 (or +-180 / +-0 folded below)
   const float a = num / den;
   const float z = a * a;
   float p = __fmaf_rn(z, 8.05374449538e-2f, -1.38776856032e-1f);
@@ -70,10 +86,10 @@ __device__ __forceinline__ float atan2_deg(float y, float x) {
   p = __fmaf_rn(z, p, -3.33329491539e-1f);
   p = __fmaf_rn(p * z, a, a);
   float r = __fmaf_rn(p, 57.29577951f, off);
-  if (swap) r = 90.0f - r;
-  if (x < 0.0f) r = 180.0f - r;
-  if (y < 0.0f) r = -r;
-  return r;
+  r = swap ? 90.0f - r : r;
+  r = x < 0.0f ? 180.0f - r : r;
+  r = y < 0.0f ? -r : r;
+  return zero ? 0.0f : r;
 }
 
 // e^x, |x| <= 88: Cody-Waite reduction by ln2 and a degree-6 polynomial, exponent patched in.
@@ -127,6 +143,7 @@ __device__ __forceinline__ int u32_to_int(uint32_t u, int lo, int hi) {
 // uniform in [0, 1), 24 bits - the role of random.random at reach_ball_env.py:205
 __device__ __forceinline__ float u32_to_unit(uint32_t u) { return static_cast<float>(u >> 8) * (1.0f / 16777216.0f); }
 
+#ifndef S2D_HOST_EMU
 // 128-bit streaming accesses: state planes are touched exactly once per launch, so do not allocate in L1.
 __device__ __forceinline__ float4 ld_stream(const float4* p) {
   float4 v;
@@ -152,5 +169,11 @@ __device__ __forceinline__ void st_stream(uint4* p, const uint4& v) {
                "r"(v.w)
                : "memory");
 }
+#else
+__device__ __forceinline__ float4 ld_stream(const float4* p) { return *p; }
+__device__ __forceinline__ uint4 ld_stream(const uint4* p) { return *p; }
+__device__ __forceinline__ void st_stream(float4* p, const float4& v) { *p = v; }
+__device__ __forceinline__ void st_stream(uint4* p, const uint4& v) { *p = v; }
+#endif
 
 }  // namespace s2d

@@ -35,6 +35,36 @@ struct Episode {
   uint32_t cycle, episode, flags;
 };
 
+// Physics constants in the form the cycle uses them: the proto ServerParam values plus products and
+// reciprocals that are the same for every env.  Built once per handle on the host (make_cycle_consts), in
+// float arithmetic, so device and host agree on every bit.
+struct CycleConsts {
+  S2DServerParam sp;
+  float inv_dash_angle_step;                 // 1 / dash_angle_step (0 when the step is disabled)
+  float player_accel_max2, player_speed_max2;  // squares: the clamps compare squared lengths
+  float ball_accel_max2, ball_speed_max2;
+  float collide_r, collide_r2;               // player_size + ball_size, and its square
+  float recover_dec_stamina, effort_dec_stamina, effort_inc_stamina;  // thresholds * stamina_max
+  float kickable_area;                       // player_size + ball_size + kickable_margin
+};
+
+inline CycleConsts make_cycle_consts(const S2DServerParam& sp) {
+  CycleConsts c;
+  c.sp = sp;
+  c.inv_dash_angle_step = sp.dash_angle_step > 1.0e-10f ? static_cast<float>(1.0 / static_cast<double>(sp.dash_angle_step)) : 0.0f;
+  c.player_accel_max2 = sp.player_accel_max * sp.player_accel_max;
+  c.player_speed_max2 = sp.player_speed_max * sp.player_speed_max;
+  c.ball_accel_max2 = sp.ball_accel_max * sp.ball_accel_max;
+  c.ball_speed_max2 = sp.ball_speed_max * sp.ball_speed_max;
+  c.collide_r = sp.player_size + sp.ball_size;
+  c.collide_r2 = c.collide_r * c.collide_r;
+  c.recover_dec_stamina = sp.recover_dec_thr * sp.stamina_max;
+  c.effort_dec_stamina = sp.effort_dec_thr * sp.stamina_max;
+  c.effort_inc_stamina = sp.effort_inc_thr * sp.stamina_max;
+  c.kickable_area = sp.player_size + sp.ball_size + sp.kickable_margin;
+  return c;
+}
+
 __device__ __forceinline__ void load_episode(const void* state, int64_t n, int64_t i, Episode& e) {
   const float4* f = reinterpret_cast<const float4*>(state);
   const float4 a = ld_stream(f + i), b = ld_stream(f + n + i), c = ld_stream(f + 2 * n + i),
@@ -68,30 +98,27 @@ __device__ __forceinline__ void recover(Episode& e, const S2DServerParam& sp) {
 
 // (dash power dir): stamina is charged first, then the effective power is scaled by effort, the
 // direction-dependent rate (forward 1, sideways side_dash_rate, backwards back_dash_rate) and
-// dash_power_rate.  Returns the acceleration it adds.
-__device__ __forceinline__ void dash(Episode& e, float power, float dir, const S2DServerParam& sp, float& ax,
-                                     float& ay) {
+// dash_power_rate.  Adds to the player's acceleration.
+__device__ __forceinline__ void dash(Episode& e, float power, float dir, const CycleConsts& C, float& ax, float& ay) {
+  const S2DServerParam& sp = C.sp;
   power = clampf(sp.min_dash_power, power, sp.max_dash_power);
   dir = clampf(sp.min_dash_angle, dir, sp.max_dash_angle);
-  if (sp.dash_angle_step > 1.0e-10f) dir = sp.dash_angle_step * rintf(dir / sp.dash_angle_step);
+  if (sp.dash_angle_step > 1.0e-10f) dir = sp.dash_angle_step * rintf(dir * C.inv_dash_angle_step);
   const bool back = power < 0.0f;
   float need = back ? power * -2.0f : power;
   need = fmin_(need, e.stamina + sp.extra_stamina);
   e.stamina = fmax_(0.0f, e.stamina - need);
-  power = back ? need / -2.0f : need;
+  power = back ? need * -0.5f : need;
   const float ad = fabsf(dir);
-  float rate;
-  if (ad > 90.0f)
-    rate = sp.back_dash_rate - ((sp.back_dash_rate - sp.side_dash_rate) * (1.0f - (ad - 90.0f) / 90.0f));
-  else
-    rate = sp.side_dash_rate + ((1.0f - sp.side_dash_rate) * (1.0f - ad / 90.0f));
-  rate = clampf(0.0f, rate, 1.0f);
+  const float over = (ad - 90.0f) * static_cast<float>(1.0 / 90.0);
+  const float under = ad * static_cast<float>(1.0 / 90.0);
+  const float rate_back = sp.back_dash_rate - ((sp.back_dash_rate - sp.side_dash_rate) * (1.0f - over));
+  const float rate_fwd = sp.side_dash_rate + ((1.0f - sp.side_dash_rate) * (1.0f - under));
+  const float rate = clampf(0.0f, ad > 90.0f ? rate_back : rate_fwd, 1.0f);
   float eff = fabsf(e.effort * power * rate * sp.dash_power_rate);
-  if (e.py < 0.0f) {
-    const float slow = sp.slowness_on_top_for_left_team;  // the single player is on the left team
-    if (slow != 1.0f) eff /= slow;
-  }
-  if (back) dir += 180.0f;
+  const float slow = sp.slowness_on_top_for_left_team;  // the single player is on the left team
+  if (slow != 1.0f && e.py < 0.0f) eff = cold_div(eff, slow);
+  dir = back ? dir + 180.0f : dir;
   float s, c;
   sincos_deg(e.body + dir, s, c);
   ax += eff * c;
@@ -99,25 +126,25 @@ __device__ __forceinline__ void dash(Episode& e, float power, float dir, const S
 }
 
 // (turn moment): the faster the player moves, the less it turns (inertia_moment)
-__device__ __forceinline__ void turn(Episode& e, float moment, const S2DServerParam& sp) {
-  moment = clampf(sp.min_moment, moment, sp.max_moment);
+__device__ __forceinline__ void turn(Episode& e, float moment, const CycleConsts& C) {
+  moment = clampf(C.sp.min_moment, moment, C.sp.max_moment);
   const float speed = hypot2(e.vx, e.vy);
-  e.body = norm_deg(e.body + moment / (1.0f + sp.inertia_moment * speed));
+  e.body = norm_deg(e.body + moment / (1.0f + C.sp.inertia_moment * speed));
 }
 
 // (kick power dir): only inside the kickable area; power falls off by up to 25 % with the angle between
 // body and ball and by up to 25 % with the distance.  Adds to the ball's acceleration.
-__device__ __forceinline__ bool kick(Episode& e, float power, float dir, const S2DServerParam& sp, float& bax,
-                                     float& bay) {
+__device__ __forceinline__ bool kick(Episode& e, float power, float dir, const CycleConsts& C, float& bax, float& bay) {
+  const S2DServerParam& sp = C.sp;
   power = clampf(0.0f, power, sp.max_power);
   dir = clampf(sp.min_moment, dir, sp.max_moment);
   const float dx = e.bx - e.px, dy = e.by - e.py;
   const float dist = hypot2(dx, dy);
-  if (dist > sp.player_size + sp.ball_size + sp.kickable_margin) return false;
-  const float dir_diff = fabsf(norm_deg(atan2_deg(dy, dx) - e.body));
+  if (dist > C.kickable_area) return false;
+  const float dir_diff = fabsf(norm_deg_360(atan2_deg(dy, dx) - e.body));
   const float dist_ball = dist - sp.player_size - sp.ball_size;
-  const float eff =
-      power * sp.kick_power_rate * (1.0f - 0.25f * dir_diff / 180.0f - 0.25f * dist_ball / sp.kickable_margin);
+  const float eff = power * sp.kick_power_rate *
+                    (1.0f - 0.25f * dir_diff * static_cast<float>(1.0 / 180.0) - 0.25f * dist_ball / sp.kickable_margin);
   float s, c;
   sincos_deg(e.body + dir, s, c);
   bax += eff * c;
@@ -127,20 +154,22 @@ __device__ __forceinline__ bool kick(Episode& e, float power, float dir, const S
 
 // ---- one cycle ------------------------------------------------------------------------------------
 
+// MPObject::_inc.  The two clamps compare SQUARED lengths (no square root unless a clamp applies).
 __device__ __forceinline__ void move_object(float& x, float& y, float& vx, float& vy, float ax, float ay,
-                                            float accel_max, float speed_max, float decay) {
+                                            float accel_max, float accel_max2, float speed_max, float speed_max2,
+                                            float decay) {
   if (ax != 0.0f || ay != 0.0f) {
-    const float a = hypot2(ax, ay);
-    if (a > accel_max) {
-      const float k = accel_max / a;
+    const float a2 = ax * ax + ay * ay;
+    if (a2 > accel_max2) {
+      const float k = cold_div(accel_max, sqrtf(a2));
       ax *= k;
       ay *= k;
     }
     vx += ax;
     vy += ay;
-    const float v = hypot2(vx, vy);
-    if (v > speed_max) {
-      const float k = speed_max / v;
+    const float v2 = vx * vx + vy * vy;
+    if (v2 > speed_max2) {
+      const float k = cold_div(speed_max, sqrtf(v2));
       vx *= k;
       vy *= k;
     }
@@ -153,29 +182,28 @@ __device__ __forceinline__ void move_object(float& x, float& y, float& vx, float
 
 constexpr float kCollideEps = 1.0e-6f;
 
-// Ball overlapping the player: the ball goes back along its own velocity until the two just touch; if it
-// is not moving (or the line misses), it is pushed out radially.  The player keeps its place.  Up to ten
+// Ball overlapping the player (rare): the ball goes back along its own velocity until the two just touch; if
+// it is not moving (or the line misses), it is pushed out radially.  The player keeps its place.  Up to ten
 // relaxation rounds as in the server, then both objects that collided get vel *= -0.1.
-__device__ __forceinline__ void collide_ball_player(Episode& e, const S2DServerParam& sp) {
-  uint32_t hit = 0;
-  const float r = sp.player_size + sp.ball_size;
+__device__ __noinline__ float2 resolve_ball_player_overlap(float px, float py, float bx, float by, float bvx, float bvy,
+                                                           float r) {
+  const float r2 = r * r;
+  const float rr = r + kCollideEps;
 #pragma unroll 1
   for (int round = 0; round < 10; ++round) {
-    const float dx = e.bx - e.px, dy = e.by - e.py;
-    if (!(dx * dx + dy * dy < r * r)) break;
-    hit = S2D_FLAG_BALL_COLLIDED | S2D_FLAG_PLAYER_COLLIDED;
-    const float rr = r + kCollideEps;
-    const float v = hypot2(e.bvx, e.bvy);
+    const float dx = bx - px, dy = by - py;
+    if (!(dx * dx + dy * dy < r2)) break;
+    const float v = hypot2(bvx, bvy);
     bool placed = false;
     if (v > 1.0e-10f) {
-      const float ux = e.bvx / v, uy = e.bvy / v;
+      const float ux = bvx / v, uy = bvy / v;
       const float du = dx * ux + dy * uy;
       const float disc = du * du - (dx * dx + dy * dy - rr * rr);
       if (disc >= 0.0f) {
         const float t = du + sqrtf(disc);
         if (t >= 0.0f) {
-          e.bx = e.bx - t * ux;
-          e.by = e.by - t * uy;
+          bx = bx - t * ux;
+          by = by - t * uy;
           placed = true;
         }
       }
@@ -183,15 +211,25 @@ __device__ __forceinline__ void collide_ball_player(Episode& e, const S2DServerP
     if (!placed) {
       const float d = hypot2(dx, dy);
       if (d < 1.0e-10f) {
-        e.bx = e.px + rr;
-        e.by = e.py;
+        bx = px + rr;
+        by = py;
       } else {
-        e.bx = e.px + dx / d * rr;
-        e.by = e.py + dy / d * rr;
+        bx = px + dx / d * rr;
+        by = py + dy / d * rr;
       }
     }
   }
-  if (hit) {
+  return make_float2(bx, by);
+}
+
+__device__ __forceinline__ void collide_ball_player(Episode& e, const CycleConsts& C) {
+  const float dx = e.bx - e.px, dy = e.by - e.py;
+  uint32_t hit = 0;
+  if (dx * dx + dy * dy < C.collide_r2) {
+    hit = S2D_FLAG_BALL_COLLIDED | S2D_FLAG_PLAYER_COLLIDED;
+    const float2 b = resolve_ball_player_overlap(e.px, e.py, e.bx, e.by, e.bvx, e.bvy, C.collide_r);
+    e.bx = b.x;
+    e.by = b.y;
     e.bvx *= -0.1f;
     e.bvy *= -0.1f;
     e.vx *= -0.1f;
@@ -200,46 +238,52 @@ __device__ __forceinline__ void collide_ball_player(Episode& e, const S2DServerP
   e.flags = (e.flags & ~(S2D_FLAG_BALL_COLLIDED | S2D_FLAG_PLAYER_COLLIDED)) | hit;
 }
 
-__device__ __forceinline__ void update_stamina(Episode& e, const S2DServerParam& sp) {
-  if (e.stamina <= sp.recover_dec_thr * sp.stamina_max) {
-    if (e.recovery > sp.recover_min) e.recovery -= sp.recover_dec;
-    if (e.recovery < sp.recover_min) e.recovery = sp.recover_min;
+// Player::updateStamina, written with selects instead of nested branches.
+__device__ __forceinline__ void update_stamina(Episode& e, const CycleConsts& C) {
+  const S2DServerParam& sp = C.sp;
+  {  // recovery decays below recover_dec_thr * stamina_max
+    float r = e.recovery > sp.recover_min ? e.recovery - sp.recover_dec : e.recovery;
+    r = r < sp.recover_min ? sp.recover_min : r;
+    e.recovery = e.stamina <= C.recover_dec_stamina ? r : e.recovery;
   }
-  if (e.stamina <= sp.effort_dec_thr * sp.stamina_max) {
-    if (e.effort > sp.effort_min) e.effort -= sp.effort_dec;
-    if (e.effort < sp.effort_min) e.effort = sp.effort_min;
+  {  // effort decays below effort_dec_thr * stamina_max ...
+    float f = e.effort > sp.effort_min ? e.effort - sp.effort_dec : e.effort;
+    f = f < sp.effort_min ? sp.effort_min : f;
+    e.effort = e.stamina <= C.effort_dec_stamina ? f : e.effort;
   }
-  if (e.stamina >= sp.effort_inc_thr * sp.stamina_max) {
-    if (e.effort < sp.effort_max) {
-      e.effort += sp.effort_inc;
-      if (e.effort > sp.effort_max) e.effort = sp.effort_max;
-    }
+  {  // ... and comes back above effort_inc_thr * stamina_max
+    float f = e.effort + sp.effort_inc;
+    f = f > sp.effort_max ? sp.effort_max : f;
+    e.effort = (e.stamina >= C.effort_inc_stamina && e.effort < sp.effort_max) ? f : e.effort;
   }
   float inc = fmin_(e.recovery * sp.stamina_inc_max, sp.stamina_max - e.stamina);
-  if (sp.stamina_capacity >= 0.0f) {
-    if (inc > e.capacity) inc = e.capacity;
-  }
+  const bool capped = sp.stamina_capacity >= 0.0f;
+  inc = (capped && inc > e.capacity) ? e.capacity : inc;
   e.stamina += inc;
-  if (sp.stamina_capacity >= 0.0f) e.capacity = fmax_(0.0f, e.capacity - inc);
+  e.capacity = capped ? fmax_(0.0f, e.capacity - inc) : e.capacity;
 }
 
 // One server cycle with at most one body command.  Order as in rcssserver's Stadium::step: commands were
 // applied on receipt, then every object moves, then collisions, then stamina, then the clock.
-__device__ __forceinline__ void simulate_cycle(Episode& e, int cmd, float power, float dir,
-                                               const S2DServerParam& sp) {
+// TURNS / KICKS say whether the caller can issue those commands at all (compile-time pruning).
+template <bool TURNS, bool KICKS>
+__device__ __forceinline__ void simulate_cycle(Episode& e, int cmd, float power, float dir, const CycleConsts& C) {
+  const S2DServerParam& sp = C.sp;
   float ax = 0.0f, ay = 0.0f, bax = 0.0f, bay = 0.0f;
-  e.flags &= ~S2D_FLAG_KICKED;
+  if (KICKS) e.flags &= ~S2D_FLAG_KICKED;
   if (cmd == S2D_CMD_DASH) {
-    dash(e, power, dir, sp, ax, ay);
-  } else if (cmd == S2D_CMD_TURN) {
-    turn(e, dir, sp);
-  } else if (cmd == S2D_CMD_KICK) {
-    if (kick(e, power, dir, sp, bax, bay)) e.flags |= S2D_FLAG_KICKED;
+    dash(e, power, dir, C, ax, ay);
+  } else if (TURNS && cmd == S2D_CMD_TURN) {
+    turn(e, dir, C);
+  } else if (KICKS && cmd == S2D_CMD_KICK) {
+    if (kick(e, power, dir, C, bax, bay)) e.flags |= S2D_FLAG_KICKED;
   }
-  move_object(e.px, e.py, e.vx, e.vy, ax, ay, sp.player_accel_max, sp.player_speed_max, sp.player_decay);
-  move_object(e.bx, e.by, e.bvx, e.bvy, bax, bay, sp.ball_accel_max, sp.ball_speed_max, sp.ball_decay);
-  collide_ball_player(e, sp);
-  update_stamina(e, sp);
+  move_object(e.px, e.py, e.vx, e.vy, ax, ay, sp.player_accel_max, C.player_accel_max2, sp.player_speed_max,
+              C.player_speed_max2, sp.player_decay);
+  move_object(e.bx, e.by, e.bvx, e.bvy, bax, bay, sp.ball_accel_max, C.ball_accel_max2, sp.ball_speed_max,
+              C.ball_speed_max2, sp.ball_decay);
+  collide_ball_player(e, C);
+  update_stamina(e, C);
   e.cycle += 1u;
 }
 

@@ -1,23 +1,26 @@
 // s2d_reachball.cuh - the ReachBall scenario fused into the lockstep kernels.
 //
 // Replaces, per env and per cycle, the whole of Soccer2DEnv.step (soccer_2d_env.py:226-269):
-//   decode_action      ReachBallEnv.action_to_rpc_actions      sample_environments/reach_ball_env.py:53-85
-//   simulate_cycle     the rcssserver cycle behind the gRPC round trip (server.py:49-103)
-//   check_episode      ReachBallEnv.check_trainer_observation  reach_ball_env.py:113-161
-//   write_obs          ReachBallEnv.state_to_observation       reach_ball_env.py:87-111
-//   reset_episode      Soccer2DEnv.env_reset + ReachBallEnv.abs_reset / trainer_reset_actions /
-//                      get_ball_velocity                       soccer_2d_env.py:179-224, reach_ball_env.py:163-218
+//   decode (in substep)  ReachBallEnv.action_to_rpc_actions      sample_environments/reach_ball_env.py:53-85
+//   simulate_cycle       the rcssserver cycle behind the gRPC round trip (server.py:49-103)
+//   check_episode        ReachBallEnv.check_trainer_observation  reach_ball_env.py:113-161
+//   build_obs            ReachBallEnv.state_to_observation       reach_ball_env.py:87-111
+//   place_new_episode    Soccer2DEnv.env_reset + ReachBallEnv.abs_reset / trainer_reset_actions /
+//                        get_ball_velocity                       soccer_2d_env.py:179-224, reach_ball_env.py:163-218
 #pragma once
+#include <math.h>
+#include <string.h>
+
 #include "s2d_one_player.cuh"
 
 namespace s2d {
 
-constexpr int kObsDim = 10;       // reach_ball_env.py:48
-constexpr int kBallVelTries = 64; // bound on the rejection loop of reach_ball_env.py:204-212
+constexpr int kObsDim = 10;        // reach_ball_env.py:48
+constexpr int kBallVelTries = 64;  // bound on the rejection loop of reach_ball_env.py:204-212
 
 // Everything a kernel needs, passed by value as a __grid_constant__ (lives in the constant bank).
 struct KernelParams {
-  S2DServerParam sp;
+  CycleConsts cc;
   int64_t num_envs;
   int64_t env_id_offset;
   uint64_t seed;
@@ -38,54 +41,77 @@ struct KernelParams {
   const float* dash_dirs;     // [256] Discrete(n) -> relative direction, built on the host at create
 };
 
+// Fills everything but the buffer pointers from a config.  `dirs` receives the Discrete(n) -> Dash direction
+// table of reach_ball_env.py:84, evaluated as the reference does (double, then the proto float).
+inline void make_kernel_params(const S2DConfig& cfg, KernelParams& kp, float dirs[256]) {
+  memset(&kp, 0, sizeof(kp));
+  kp.cc = make_cycle_consts(cfg.sp);
+  kp.num_envs = cfg.num_envs;
+  kp.env_id_offset = cfg.env_id_offset;
+  kp.seed = cfg.seed;
+  kp.scenario = cfg.scenario;
+  kp.action_mode = cfg.action_mode;
+  kp.action_space_size = cfg.action_space_size;
+  kp.max_steps = cfg.max_steps;
+  kp.auto_reset = cfg.auto_reset;
+  kp.change_ball_position = cfg.change_ball_position;
+  kp.change_ball_velocity = cfg.change_ball_velocity;
+  kp.noise = cfg.noise;
+  kp.min_distance_to_ball = cfg.min_distance_to_ball;
+  kp.ball_position_x = cfg.ball_position_x;
+  kp.ball_position_y = cfg.ball_position_y;
+  kp.ball_speed = cfg.ball_speed;
+  kp.ball_direction = cfg.ball_direction;
+  kp.goto_dist_thr = cfg.goto_dist_thr;
+  // reach_ball_env.py:207 - the reference uses 0.96 here, not the server's ball_decay
+  kp.travel_factor = static_cast<float>((1.0 - pow(0.96, static_cast<double>(cfg.max_steps))) / (1.0 - 0.96));
+  const int n = cfg.action_space_size;
+  for (int a = 0; a < 256; ++a)
+    dirs[a] = n > 0 ? static_cast<float>(fmod(static_cast<double>(a) * 360.0 / static_cast<double>(n), 360.0) - 180.0) : 0.0f;
+}
+
 // episode statistics: slots spread the atomics over L2 lines; s2d_stats sums them
 constexpr int kStatSlots = 256;
 constexpr int kStatWords = 8;  // episodes, goals, outs, timeouts, episode_steps, return (double bits), pad, pad
 enum { ST_EPISODES = 0, ST_GOALS = 1, ST_OUTS = 2, ST_TIMEOUTS = 3, ST_EP_STEPS = 4, ST_RETURN = 5 };
 
-struct Tally {
+// what one launch accumulates per env
+struct LaunchOut {
+  float reward_sum = 0.0f;
+  uint32_t any_done = 0, last_result = 0;
   uint32_t episodes = 0, goals = 0, outs = 0, timeouts = 0, ep_steps = 0;
-  float ret = 0.0f;
+  double ret = 0.0;
 };
 
 // reach_ball_env.py:113-161.  Rewards accumulate and later endings overwrite `result`, in the reference's
 // order Goal -> Out -> Timeout; leaving the pitch ADDS 10 (`reward -= -10.0`, :144).
+// body, mem_ang and atan2's result are already in [-180, 180], so AngleDeg's re-normalisations are identities.
 __device__ __forceinline__ bool check_episode(Episode& e, const KernelParams& P, float& reward, int& result) {
   const float dx = e.bx - e.px, dy = e.by - e.py;
   const float dist = hypot2(dx, dy);
-  const float diff = norm_deg(norm_deg(atan2_deg(dy, dx)) - norm_deg(e.body));
-  bool done = false;
-  result = S2D_RESULT_NONE;
-  reward = 0.0f;
-  reward += e.mem_dist - dist;
-  reward += (fabsf(norm_deg(e.mem_ang)) - fabsf(diff)) * static_cast<float>(1.0 / 180.0);
-  if (dist < P.min_distance_to_ball) {
-    done = true;
-    reward += 10.0f;
-    result = S2D_RESULT_GOAL;
-  }
-  if (fabsf(e.px) > 52.5f || fabsf(e.py) > 34.0f) {
-    done = true;
-    reward -= -10.0f;
-    result = S2D_RESULT_OUT;
-  }
-  if (e.step_number > P.max_steps) {
-    done = true;
-    reward -= 5.0f;
-    result = S2D_RESULT_TIMEOUT;
-  }
+  const float diff = norm_deg_360(atan2_deg(dy, dx) - e.body);
+  float rw = 0.0f + (e.mem_dist - dist);
+  rw += (fabsf(e.mem_ang) - fabsf(diff)) * static_cast<float>(1.0 / 180.0);
+  const bool goal = dist < P.min_distance_to_ball;
+  const bool out = fabsf(e.px) > 52.5f || fabsf(e.py) > 34.0f;
+  const bool timeout = e.step_number > P.max_steps;
+  rw = goal ? rw + 10.0f : rw;
+  rw = out ? rw - -10.0f : rw;
+  rw = timeout ? rw - 5.0f : rw;
+  result = timeout ? S2D_RESULT_TIMEOUT : out ? S2D_RESULT_OUT : goal ? S2D_RESULT_GOAL : S2D_RESULT_NONE;
+  reward = rw;
   e.mem_dist = dist;
   e.mem_ang = diff;
-  return done;
+  return goal || out || timeout;
 }
 
 // reach_ball_env.py:87-111.  Must follow a check_episode on the same state: obs[0] is exactly the
 // body-to-ball angle that check just stored in mem_ang, so the atan2 is not repeated.
 __device__ __forceinline__ void build_obs(const Episode& e, float* o) {
   const float speed = hypot2(e.bvx, e.bvy);
-  const float bdir = norm_deg(atan2_deg(e.bvy, e.bvx));
+  const float bdir = atan2_deg(e.bvy, e.bvx);
   o[0] = e.mem_ang * static_cast<float>(1.0 / 180.0);
-  o[1] = norm_deg(e.body) * static_cast<float>(1.0 / 180.0);
+  o[1] = e.body * static_cast<float>(1.0 / 180.0);
   o[2] = e.px * static_cast<float>(1.0 / 52.5);
   o[3] = e.py * static_cast<float>(1.0 / 34.0);
   o[4] = e.bx * static_cast<float>(1.0 / 52.5);
@@ -96,26 +122,25 @@ __device__ __forceinline__ void build_obs(const Episode& e, float* o) {
   o[9] = e.bvy * static_cast<float>(1.0 / 3.0);
 }
 
-// New episode: trainer_reset_actions' draws (integers: x in [-50,50], y in [-30,30], body in [0,360]; ball
-// velocity by bounded rejection), DoMoveBall / DoMovePlayer (vel = 0) / DoRecover, then ONE idle server cycle
-// (the reference's reset observes the state one cycle after placement) and the priming call of
-// check_trainer_observation whose reward is discarded (reach_ball_env.py:166).
-__device__ __noinline__ void reset_episode(Episode& e, const KernelParams& P, uint64_t gid) {
+// trainer_reset_actions' draws (integers: x in [-50,50], y in [-30,30], body in [0,360]; ball velocity by
+// bounded rejection: the ball must stay on the pitch for max_steps cycles), then DoMoveBall / DoMovePlayer
+// (vel = 0) / DoRecover.  The caller still owes the episode ONE idle server cycle and the priming check
+// (the reference's reset observes the state one cycle after placement, reach_ball_env.py:163-168).
+__device__ __forceinline__ void place_new_episode(Episode& e, const KernelParams& P, uint64_t gid) {
   const uint4 w = philox4x32_10(P.seed, gid, e.episode, RNG_RESET, 0);
   const float px = static_cast<float>(u32_to_int(w.x, -50, 50));
   const float py = static_cast<float>(u32_to_int(w.y, -30, 30));
   const float body = static_cast<float>(u32_to_int(w.z, 0, 360));
-  float bx, by;
+  float bx = P.ball_position_x, by = P.ball_position_y;
   if (P.change_ball_position) {
     const uint4 w2 = philox4x32_10(P.seed, gid, e.episode, RNG_RESET, 1);
     bx = static_cast<float>(u32_to_int(w.w, -50, 50));
     by = static_cast<float>(u32_to_int(w2.x, -30, 30));
-  } else {
-    bx = P.ball_position_x;
-    by = P.ball_position_y;
   }
-  float speed = 0.0f, d = 0.0f;
+  float speed = P.ball_speed, d = P.ball_direction;
   if (P.change_ball_velocity) {
+    speed = 0.0f;
+    d = 0.0f;
     uint4 wv = make_uint4(0, 0, 0, 0);
 #pragma unroll 1
     for (int t = 0; t < kBallVelTries; ++t) {
@@ -131,9 +156,6 @@ __device__ __noinline__ void reset_episode(Episode& e, const KernelParams& P, ui
         break;
       }
     }
-  } else {
-    speed = P.ball_speed;
-    d = P.ball_direction;
   }
   float sn, cs;
   sincos_deg(d, sn, cs);
@@ -144,13 +166,85 @@ __device__ __noinline__ void reset_episode(Episode& e, const KernelParams& P, ui
   e.px = px; e.py = py; e.vx = 0.0f; e.vy = 0.0f;
   e.body = norm_deg(body);
   e.flags = 0u;
-  recover(e, P.sp);
-  simulate_cycle(e, S2D_CMD_NONE, 0.0f, 0.0f, P.sp);
+  recover(e, P.cc.sp);
+}
+
+// per-lane row store (terminal observations, reset kernel): 40-byte rows are 8-byte aligned
+__device__ __forceinline__ void lane_store_row(float* __restrict__ dst, int64_t env, const float* row) {
+  float2* o = reinterpret_cast<float2*>(dst + env * kObsDim);
+#pragma unroll
+  for (int j = 0; j < kObsDim / 2; ++j) o[j] = make_float2(row[2 * j], row[2 * j + 1]);
+}
+
+// ONE env-step = what Soccer2DEnv.step does: decode the action, run the server cycle, score it; when the
+// episode ends, record it and (auto_reset) start the next one, which costs a second, idle pass through the
+// same cycle + check code (placement, one cycle, priming check whose reward is discarded).
+//   a0..a3: the action - discrete: a0 = dash direction from the table; continuous: a0 in [-1,1];
+//           turning: [turn_prob, turn_angle, dash_prob, dash_angle] (reach_ball_env.py:65-68)
+template <int ACT>
+__device__ __forceinline__ void substep(Episode& e, const KernelParams& P, uint64_t gid, int64_t i, float a0, float a1,
+                                        float a2, float a3, LaunchOut& out) {
+  constexpr bool kTurns = ACT == S2D_ACT_TURNING;
+  e.step_number += 1;  // reach_ball_env.py:55
+  int cmd = S2D_CMD_DASH;
+  float power = 100.0f, dir;
+  if (ACT == S2D_ACT_DISCRETE) {
+    dir = a0;
+  } else if (ACT == S2D_ACT_CONTINUOUS) {
+    dir = a0 * 180.0f;
+  } else {
+    const float tp = clampf(-1.0f, a0, 1.0f), ta = clampf(-1.0f, a1, 1.0f);
+    const float dp = clampf(-1.0f, a2, 1.0f), da = clampf(-1.0f, a3, 1.0f);
+    const float u = u32_to_unit(philox4x32_10(P.seed, gid, e.cycle, RNG_ACTION, 0).x);
+    const bool turn_selected = u < softmax_first(dp, tp);  // :69-72: tested against the DASH logit's weight
+    cmd = turn_selected ? S2D_CMD_TURN : S2D_CMD_DASH;
+    power = turn_selected ? 0.0f : 100.0f;
+    dir = (turn_selected ? ta : da) * 180.0f;
+  }
+  bool priming = false;
+#pragma unroll 1
+  for (;;) {
+    simulate_cycle<kTurns, false>(e, cmd, power, dir, P.cc);
+    float rw;
+    int rs;
+    const bool done = check_episode(e, P, rw, rs);
+    if (priming) break;  // reach_ball_env.py:166: the first check after a reset only primes the memory
+    out.reward_sum += rw;
+    e.ep_return += rw;
+    if (!done) break;
+    out.any_done = 1;
+    out.last_result = static_cast<uint32_t>(rs);
+    out.episodes += 1;
+    out.ep_steps += static_cast<uint32_t>(e.step_number);
+    out.ret += static_cast<double>(e.ep_return);
+    out.goals += rs == S2D_RESULT_GOAL;
+    out.outs += rs == S2D_RESULT_OUT;
+    out.timeouts += rs == S2D_RESULT_TIMEOUT;
+    if (P.terminal_obs) {
+      float row[kObsDim];
+      build_obs(e, row);
+      lane_store_row(P.terminal_obs, i, row);
+    }
+    if (!P.auto_reset) {
+      e.flags |= S2D_FLAG_DONE;
+      break;
+    }
+    place_new_episode(e, P, gid);
+    cmd = S2D_CMD_NONE;
+    priming = true;
+  }
+}
+
+// Soccer2DEnv.reset for one env: placement, the idle cycle, the priming check.
+__device__ __forceinline__ void reset_episode(Episode& e, const KernelParams& P, uint64_t gid) {
+  place_new_episode(e, P, gid);
+  simulate_cycle<false, false>(e, S2D_CMD_NONE, 0.0f, 0.0f, P.cc);
   float rw;
   int rs;
   check_episode(e, P, rw, rs);
 }
 
+#ifndef S2D_HOST_EMU
 // Coalesced write of one warp's observations: each lane parks its row in shared memory, then the warp
 // streams the 32 x 10 floats out as 80 float4 (512 contiguous bytes per store instruction).
 __device__ __forceinline__ void warp_store_obs(float* __restrict__ dst, int64_t warp_first_env, int64_t n,
@@ -171,20 +265,14 @@ __device__ __forceinline__ void warp_store_obs(float* __restrict__ dst, int64_t 
   __syncwarp();
 }
 
-// Same idea for rows that only SOME lanes own (terminal observations): a masked, per-lane row store.
-__device__ __forceinline__ void lane_store_row(float* __restrict__ dst, int64_t env, const float* row) {
-  float2* o = reinterpret_cast<float2*>(dst + env * kObsDim);  // 40 B rows: 8-B aligned
-#pragma unroll
-  for (int j = 0; j < kObsDim / 2; ++j) o[j] = make_float2(row[2 * j], row[2 * j + 1]);
-}
-
-__device__ __forceinline__ void flush_tally(const Tally& t, unsigned long long* stats) {
+// warp-level sum of the launch's episode statistics, then one lane adds them to a stats slot
+__device__ __forceinline__ void flush_tally(const LaunchOut& t, unsigned long long* stats) {
   const unsigned full = 0xffffffffu;
   if (!__any_sync(full, t.episodes != 0)) return;
   const uint32_t ep = __reduce_add_sync(full, t.episodes), g = __reduce_add_sync(full, t.goals),
                  o = __reduce_add_sync(full, t.outs), to = __reduce_add_sync(full, t.timeouts),
                  st = __reduce_add_sync(full, t.ep_steps);
-  double r = static_cast<double>(t.ret);
+  double r = t.ret;
 #pragma unroll
   for (int s = 16; s > 0; s >>= 1) r += __shfl_xor_sync(full, r, s);
   if ((threadIdx.x & 31) == 0) {
@@ -199,62 +287,25 @@ __device__ __forceinline__ void flush_tally(const Tally& t, unsigned long long* 
   }
 }
 
-// ---- action fetch ---------------------------------------------------------------------------------
-// actions[N][K] (uint8 / float) or [N][K][4] (float).  A lane's K actions are contiguous; with K a multiple
-// of 16 (uint8) or 4 (float) they come in as 128-bit words, otherwise through the read-only path one by one.
-
-template <int ACT>
-struct ActionReader;
-
-template <>
-struct ActionReader<S2D_ACT_DISCRETE> {
-  const uint8_t* base;
-  bool vec;
-  uint4 w;
-  __device__ __forceinline__ ActionReader(const void* actions, int64_t i, int K)
-      : base(static_cast<const uint8_t*>(actions) + i * K), vec((K & 15) == 0), w(make_uint4(0, 0, 0, 0)) {}
-  __device__ __forceinline__ uint32_t get(int k) {
-    if (!vec) return __ldg(base + k);
-    if ((k & 15) == 0) w = __ldg(reinterpret_cast<const uint4*>(base + k));
-    const int j = k & 15;
-    const uint32_t word = (j < 4) ? w.x : (j < 8) ? w.y : (j < 12) ? w.z : w.w;
-    return (word >> ((j & 3) * 8)) & 0xffu;
-  }
-};
-
-template <>
-struct ActionReader<S2D_ACT_CONTINUOUS> {
-  const float* base;
-  bool vec;
-  float4 w;
-  __device__ __forceinline__ ActionReader(const void* actions, int64_t i, int K)
-      : base(static_cast<const float*>(actions) + i * K), vec((K & 3) == 0), w(make_float4(0, 0, 0, 0)) {}
-  __device__ __forceinline__ float get(int k) {
-    if (!vec) return __ldg(base + k);
-    if ((k & 3) == 0) w = __ldg(reinterpret_cast<const float4*>(base + k));
-    const int j = k & 3;
-    return j == 0 ? w.x : j == 1 ? w.y : j == 2 ? w.z : w.w;
-  }
-};
-
-template <>
-struct ActionReader<S2D_ACT_TURNING> {
-  const float4* base;
-  __device__ __forceinline__ ActionReader(const void* actions, int64_t i, int K)
-      : base(static_cast<const float4*>(actions) + i * K) {}
-  __device__ __forceinline__ float4 get(int k) { return __ldg(base + k); }
-};
-
 // ---- kernels --------------------------------------------------------------------------------------
 
-constexpr int kBlock = 256;
+#ifndef S2D_BLOCK
+#define S2D_BLOCK 256
+#endif
+constexpr int kBlock = S2D_BLOCK;
+#ifndef S2D_MIN_BLOCKS
+#define S2D_MIN_BLOCKS 4  // resident blocks per SM the step kernel is compiled for (register budget)
+#endif
 
 // K lockstep cycles of every env in one launch; state stays in registers in between.
+// actions[N][K] (uint8 / float) or [N][K][4] (float): a lane's K actions are contiguous; with K a multiple of
+// 16 (uint8) or 4 (float) they come in as 128-bit words, otherwise one by one through the read-only path.
 template <int ACT>
-__global__ void __launch_bounds__(kBlock) reachball_step_kernel(const __grid_constant__ KernelParams P, const int K) {
+__global__ void __launch_bounds__(kBlock, S2D_MIN_BLOCKS) reachball_step_kernel(const __grid_constant__ KernelParams P,
+                                                                               const int K) {
   __shared__ float s_dirs[256];
   __shared__ __align__(16) float s_stage[kBlock / 32][32 * kObsDim];
-  if constexpr (ACT == S2D_ACT_DISCRETE) {
+  if (ACT == S2D_ACT_DISCRETE) {
     for (int a = threadIdx.x; a < 256; a += kBlock) s_dirs[a] = P.dash_dirs[a];
     __syncthreads();
   }
@@ -266,68 +317,54 @@ __global__ void __launch_bounds__(kBlock) reachball_step_kernel(const __grid_con
   const int64_t warp_first = i - (threadIdx.x & 31);
 
   Episode e;
-  Tally tally;
-  float reward_sum = 0.0f;
-  uint32_t any_done = 0, last_result = 0;
+  LaunchOut out;
   float obs_row[kObsDim];
 
   if (valid) {
     load_episode(P.state, n, i, e);
-    ActionReader<ACT> reader(P.actions, i, K);
+    if (ACT == S2D_ACT_DISCRETE) {
+      const uint8_t* base = static_cast<const uint8_t*>(P.actions) + i * K;
+      const bool vec = (K & 15) == 0;  // 16 actions per 128-bit load, peeled off byte by byte
+      uint4 w = make_uint4(0, 0, 0, 0);
+      uint32_t cur = 0;
 #pragma unroll 1
-    for (int k = 0; k < K; ++k) {
-      // ---- action decode (reach_ball_env.py:53-85): step_number counts calls
-      e.step_number += 1;
-      int cmd = S2D_CMD_DASH;
-      float power = 100.0f, dir;
-      if constexpr (ACT == S2D_ACT_DISCRETE) {
-        dir = s_dirs[reader.get(k)];
-      } else if constexpr (ACT == S2D_ACT_CONTINUOUS) {
-        dir = reader.get(k) * 180.0f;
-      } else {
-        const float4 a = reader.get(k);  // [turn_prob, turn_angle, dash_prob, dash_angle], :65-68
-        const float tp = clampf(-1.0f, a.x, 1.0f), ta = clampf(-1.0f, a.y, 1.0f);
-        const float dp = clampf(-1.0f, a.z, 1.0f), da = clampf(-1.0f, a.w, 1.0f);
-        const float u = u32_to_unit(philox4x32_10(P.seed, gid, e.cycle, RNG_ACTION, 0).x);
-        if (u < softmax_first(dp, tp)) {  // :69-72: tested against the DASH logit's weight, as the reference does
-          cmd = S2D_CMD_TURN;
-          power = 0.0f;
-          dir = ta * 180.0f;
+      for (int k = 0; k < K; ++k) {
+        uint32_t a;
+        if (vec) {
+          if ((k & 15) == 0) w = __ldg(reinterpret_cast<const uint4*>(base + k));
+          if ((k & 3) == 0) {
+            cur = w.x;
+            w.x = w.y;
+            w.y = w.z;
+            w.z = w.w;
+          }
+          a = cur & 0xffu;
+          cur >>= 8;
         } else {
-          dir = da * 180.0f;
+          a = __ldg(base + k);
         }
+        substep<ACT>(e, P, gid, i, s_dirs[a], 0.f, 0.f, 0.f, out);
       }
-      simulate_cycle(e, cmd, power, dir, P.sp);
-      float rw;
-      int rs;
-      const bool done = check_episode(e, P, rw, rs);
-      reward_sum += rw;
-      e.ep_return += rw;
-      if (done) {
-        any_done = 1;
-        last_result = static_cast<uint32_t>(rs);
-        tally.episodes += 1;
-        tally.ep_steps += static_cast<uint32_t>(e.step_number);
-        tally.ret += e.ep_return;
-        tally.goals += rs == S2D_RESULT_GOAL;
-        tally.outs += rs == S2D_RESULT_OUT;
-        tally.timeouts += rs == S2D_RESULT_TIMEOUT;
-        if (P.terminal_obs) {
-          build_obs(e, obs_row);
-          lane_store_row(P.terminal_obs, i, obs_row);
-        }
-        if (P.auto_reset) reset_episode(e, P, gid);
-        else e.flags |= S2D_FLAG_DONE;
+    } else if (ACT == S2D_ACT_CONTINUOUS) {
+      const float* base = static_cast<const float*>(P.actions) + i * K;
+#pragma unroll 1
+      for (int k = 0; k < K; ++k) substep<ACT>(e, P, gid, i, __ldg(base + k), 0.f, 0.f, 0.f, out);
+    } else {
+      const float4* base = static_cast<const float4*>(P.actions) + i * K;
+#pragma unroll 1
+      for (int k = 0; k < K; ++k) {
+        const float4 a = __ldg(base + k);
+        substep<ACT>(e, P, gid, i, a.x, a.y, a.z, a.w, out);
       }
     }
     store_episode(P.state, n, i, e);
     build_obs(e, obs_row);
-    P.reward[i] = reward_sum;
-    P.done[i] = static_cast<uint8_t>(any_done);
-    P.result[i] = static_cast<uint8_t>(last_result);
+    P.reward[i] = out.reward_sum;
+    P.done[i] = static_cast<uint8_t>(out.any_done);
+    P.result[i] = static_cast<uint8_t>(out.last_result);
   }
   warp_store_obs(P.obs, warp_first, n, obs_row, valid, stage);
-  flush_tally(tally, P.stats);
+  flush_tally(out, P.stats);
 }
 
 // Soccer2DEnv.reset for every env (mask == nullptr) or the envs with a non-zero mask byte.
@@ -347,5 +384,6 @@ __global__ void __launch_bounds__(kBlock) reachball_reset_kernel(const __grid_co
   P.done[i] = 0;
   P.result[i] = 0;
 }
+#endif  // !S2D_HOST_EMU
 
 }  // namespace s2d

@@ -109,7 +109,8 @@ SIGNATURES = {
     "s2d_launch_info": (C.c_int, [_H, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
 }
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libsoccer2d.so")
+# S2D_LIB: alternative build of the same library (kernel tuning experiments); default = the in-tree build
+LIB_PATH = os.environ.get("S2D_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libsoccer2d.so")
 
 
 class Soccer2DError(RuntimeError):

@@ -1,0 +1,27 @@
+// cuda_shim.h - TEST-ONLY stand-ins for the handful of CUDA built-ins that the __device__ functions of
+// gym-soccer-2d-env_b200/csrc use, so that the very same source can be compiled with g++ and checked bit for
+// bit against the fp32 oracle on a machine without a GPU (tests/test_kernel_source_on_host.py).
+// This is not a CPU backend: the product library is built by nvcc without S2D_HOST_EMU and contains no host path.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#define __device__
+#define __host__
+#define __forceinline__ inline __attribute__((always_inline))
+#define __noinline__ __attribute__((noinline))
+#define __restrict__ __restrict
+
+struct float2 { float x, y; };
+struct float4 { float x, y, z, w; };
+struct uint4 { uint32_t x, y, z, w; };
+static inline float2 make_float2(float x, float y) { return float2{x, y}; }
+static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return uint4{x, y, z, w}; }
+
+static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }  // glibc / FMA3: single rounding
+static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32); }
+static inline int __float_as_int(float f) { int i; memcpy(&i, &f, 4); return i; }
+static inline float __int_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }
+template <class T> static inline T __ldg(const T* p) { return *p; }

@@ -1,0 +1,81 @@
+"""CPU-only: the __device__ functions of csrc/*.cuh (the kernel SOURCE), compiled for the host by tests/emu, must
+reproduce the fp32 oracle bit for bit.  This catches arithmetic / logic divergences before any GPU time is spent;
+the -m gpu tests then check the real kernels, memory layout and launch plumbing on the B200."""
+import numpy as np
+import pytest
+
+import emu_lib as EL
+import helpers as H
+import oracle_lib as OL
+from test_gpu_parity_cases import HAND_PLACED_STATES
+
+
+@pytest.mark.parametrize("mode,k", [("discrete", 1), ("discrete", 16), ("continuous", 1), ("continuous", 4), ("turning", 1), ("turning", 3)])
+def test_kernel_source_bit_exact(mode, k):
+    n = 257
+    cfg = H.make_config(n, mode, seed=7, change_ball_velocity=1, max_steps=60 if k == 1 else 200)
+    emu, sim = EL.EmuSim(cfg), OL.OracleSim(cfg, "f32")
+    assert np.array_equal(emu.reset(), sim.reset())
+    assert np.array_equal(emu.get_state(), sim.get_state())
+    rng = np.random.default_rng(0)
+    episodes = 0
+    for t in range(600 // k):
+        act = H.random_actions(rng, mode, n, k)
+        emu.step(act, k)
+        sim.step(act, k)
+        assert np.array_equal(emu.done, sim.done) and np.array_equal(emu.result, sim.result)
+        assert np.array_equal(emu.obs, sim.obs) and np.array_equal(emu.reward, sim.reward)
+        d = emu.done.astype(bool)
+        assert np.array_equal(emu.term_obs[d], sim.term_obs[d])
+        episodes += int(d.sum())
+    assert np.array_equal(emu.get_state(), sim.get_state())
+    assert episodes > n
+    from soccer2d_b200 import _abi
+    st = sim.stats(_abi.Stats())
+    assert [st.episodes, st.goals, st.outs, st.timeouts, st.episode_steps] == [int(x) for x in emu.stats6[:5]]
+    assert st.return_sum == pytest.approx(emu.stats6[5], rel=1e-12)
+
+
+def test_kernel_source_hand_placed_states():
+    cases = HAND_PLACED_STATES
+    n = len(cases)
+    cfg = H.make_config(n, "continuous", seed=1, min_distance_to_ball=0.05, max_steps=100000)
+    emu, sim = EL.EmuSim(cfg), OL.OracleSim(cfg, "f32")
+    emu.reset()
+    sim.reset()
+    for i, c in enumerate(cases):
+        emu.set_state(i, c + [0])
+        sim.set_state(i, np.array(c + [0], dtype=np.float64))
+    rng = np.random.default_rng(4)
+    flags = 0
+    for _ in range(60):
+        act = H.random_actions(rng, "continuous", n)
+        act[6:8] = 0.0
+        emu.step(act)
+        sim.step(act)
+        assert np.array_equal(emu.obs, sim.obs) and np.array_equal(emu.reward, sim.reward)
+        assert np.array_equal(emu.done, sim.done)
+        g = emu.get_state()
+        assert np.array_equal(g, sim.get_state())
+        flags |= int(np.bitwise_or.reduce(g[:, 19].astype(int)))
+    assert flags & 1 and flags & 2
+
+
+def test_kernel_source_masked_reset_no_auto_reset():
+    n = 64
+    cfg = H.make_config(n, "discrete", seed=4, auto_reset=0, max_steps=10, change_ball_velocity=1)
+    emu, sim = EL.EmuSim(cfg), OL.OracleSim(cfg, "f32")
+    emu.reset()
+    sim.reset()
+    rng = np.random.default_rng(1)
+    for t in range(40):
+        act = H.random_actions(rng, "discrete", n)
+        emu.step(act)
+        sim.step(act)
+        assert np.array_equal(emu.get_state(), sim.get_state())
+        if t % 7 == 6:
+            mask = emu.done.copy()
+            emu.reset(mask)
+            sim.reset(mask)
+            assert np.array_equal(emu.obs[mask.astype(bool)], sim.obs[mask.astype(bool)])
+            assert np.array_equal(emu.get_state(), sim.get_state())

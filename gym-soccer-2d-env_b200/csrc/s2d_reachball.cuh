@@ -290,11 +290,11 @@ __device__ __forceinline__ void flush_tally(const LaunchOut& t, unsigned long lo
 // ---- kernels --------------------------------------------------------------------------------------
 
 #ifndef S2D_BLOCK
-#define S2D_BLOCK 256
+#define S2D_BLOCK 128
 #endif
 constexpr int kBlock = S2D_BLOCK;
 #ifndef S2D_MIN_BLOCKS
-#define S2D_MIN_BLOCKS 4  // resident blocks per SM the step kernel is compiled for (register budget)
+#define S2D_MIN_BLOCKS 8  // resident blocks per SM the step kernel is compiled for (register budget)
 #endif
 
 // K lockstep cycles of every env in one launch; state stays in registers in between.

@@ -56,6 +56,16 @@ def workload_config(n_gpus, envs, k, extra=None):
     return cfg
 
 
+def load_traffic(key, envs):
+    """DRAM bytes per launch of the step kernel from the committed ncu capture (profiles/traffic.json); None if
+    the capture was taken at another size."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f)[f"{key}_envs_{envs}"]["traffic_bytes"]
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def load_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -293,12 +303,14 @@ def run_b200(args, rank, local_rank, world):
                 "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3,
                 "path": "Soccer2DVecEnv.step_host -> s2d_step_host (pinned host actions in, obs/reward/done/result out)"},
         "gpu_launches": args.steps,
-        "roofline": {"bound": "hbm", "achieved": ach16, "peak": peak, "unit": "GB/s", "frac": ach16 / peak, "traffic": None,
+        "roofline": {"bound": "hbm", "achieved": ach16, "peak": peak, "unit": "GB/s", "frac": ach16 / peak,
+                     "traffic": load_traffic(f"k{k}", n),
                      "kernel": "reachball_step_kernel<DISCRETE>", "launch_ms": launch_ms,
                      "algorithmic_bytes_per_launch": bytes16, "peak_source": peak_src,
                      "note": "K=16 keeps 16 cycles in registers: HBM traffic is 222 B per 16 env-steps by construction, "
                              "this regime is instruction-issue bound; see roofline_k1 for the HBM-bound regime"},
-        "roofline_k1": {"bound": "hbm", "achieved": ach1, "peak": peak, "unit": "GB/s", "frac": ach1 / peak, "traffic": None,
+        "roofline_k1": {"bound": "hbm", "achieved": ach1, "peak": peak, "unit": "GB/s", "frac": ach1 / peak,
+                        "traffic": load_traffic("k1", n1),
                         "kernel": "reachball_step_kernel<DISCRETE>", "launch_ms": k1_launch_ms, "envs_per_gpu": n1,
                         "substeps": 1, "algorithmic_bytes_per_launch": bytes1, "env_steps_per_sec": k1_value,
                         "peak_source": peak_src},

@@ -277,17 +277,8 @@ class Soccer2DVecEnv:
 
     def allreduce_stats(self, group=None) -> dict:
         """Sum of stats() over all ranks (one small all-reduce; NCCL when the process group is NCCL)."""
-        import torch.distributed as dist
-
-        st = self.stats()
-        keys = list(st)
-        if not (dist.is_available() and dist.is_initialized()):
-            return st
-        on_gpu = dist.get_backend(group) == "nccl"
-        t = torch.tensor([float(st[k]) for k in keys], dtype=torch.float64, device=self.device if on_gpu else "cpu")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
-        vals = t.cpu().tolist()
-        return {k: (v if k == "return_sum" else int(round(v))) for k, v in zip(keys, vals)}
+        from .sharding import allreduce_stats
+        return allreduce_stats(self.stats(), device=self.device, group=group)
 
     def export_env(self, i: int) -> _abi.EnvSnapshot:
         """Host snapshot of env `i`: the WorldModel fields the reference path reads (idl/service.proto:306-349)."""

@@ -18,7 +18,8 @@ struct S2DSim {
   S2DConfig cfg;
   S2DBuffers buf;
   KernelParams kp;
-  float* d_dirs = nullptr;
+  float2* d_table = nullptr;
+  bool default_sp = false;  // cfg.sp == rcssserver defaults: use the constant-folded kernels
   bool bound = false;
   int grid = 0;
   uint64_t env_steps = 0;
@@ -75,24 +76,9 @@ const char* s2d_last_error(S2DHandle h) { return h ? h->err : g_create_err; }
 
 int s2d_default_server_param(S2DServerParam* sp) {
   if (!sp) return S2D_ERR_INVALID;
-  memset(sp, 0, sizeof(*sp));
-  // rcssserver defaults; names as in proto ServerParam / PlayerType (idl/service.proto:1435-1732)
-  sp->pitch_half_length = 52.5f; sp->pitch_half_width = 34.0f; sp->goal_width = 14.02f; sp->goal_post_radius = 0.06f;
-  sp->ball_size = 0.085f; sp->ball_decay = 0.94f; sp->ball_rand = 0.05f; sp->ball_speed_max = 3.0f; sp->ball_accel_max = 2.7f;
-  sp->player_size = 0.3f; sp->player_decay = 0.4f; sp->player_rand = 0.1f; sp->player_speed_max = 1.05f; sp->player_accel_max = 1.0f;
-  sp->dash_power_rate = 0.006f; sp->inertia_moment = 5.0f;
-  sp->min_dash_power = 0.0f; sp->max_dash_power = 100.0f; sp->min_dash_angle = -180.0f; sp->max_dash_angle = 180.0f;
-  sp->dash_angle_step = 1.0f; sp->side_dash_rate = 0.4f; sp->back_dash_rate = 0.7f;
-  sp->min_power = -100.0f; sp->max_power = 100.0f; sp->min_moment = -180.0f; sp->max_moment = 180.0f;
-  sp->kick_power_rate = 0.027f; sp->kickable_margin = 0.7f; sp->kick_rand = 0.1f;
-  sp->stamina_max = 8000.0f; sp->stamina_inc_max = 45.0f; sp->extra_stamina = 50.0f; sp->stamina_capacity = 130600.0f;
-  sp->recover_init = 1.0f; sp->recover_min = 0.5f; sp->recover_dec = 0.002f; sp->recover_dec_thr = 0.3f;
-  sp->effort_init = 1.0f; sp->effort_max = 1.0f; sp->effort_min = 0.6f; sp->effort_dec = 0.005f; sp->effort_dec_thr = 0.3f;
-  sp->effort_inc = 0.01f; sp->effort_inc_thr = 0.6f;
-  sp->slowness_on_top_for_left_team = 1.0f; sp->slowness_on_top_for_right_team = 1.0f;
+  default_server_param(*sp);  // rcssserver defaults (s2d_params.h)
   return S2D_OK;
 }
-
 int s2d_default_config(S2DConfig* c, int scenario) {
   if (!c) return S2D_ERR_INVALID;
   memset(c, 0, sizeof(*c));
@@ -170,17 +156,18 @@ int s2d_create(const S2DConfig* cfg, S2DHandle* out) {
   DeviceGuard guard(cfg->device);
 
   KernelParams& kp = h->kp;
-  float dirs[256];
-  make_kernel_params(*cfg, kp, dirs);
-  cudaError_t e = cudaMalloc(&h->d_dirs, sizeof(dirs));
-  if (e == cudaSuccess) e = cudaMemcpy(h->d_dirs, dirs, sizeof(dirs), cudaMemcpyHostToDevice);
+  float2 table[256];
+  make_kernel_params(*cfg, kp, table);
+  h->default_sp = is_default_server_param(cfg->sp);
+  cudaError_t e = cudaMalloc(&h->d_table, sizeof(table));
+  if (e == cudaSuccess) e = cudaMemcpy(h->d_table, table, sizeof(table), cudaMemcpyHostToDevice);
   if (e != cudaSuccess) {
     fail(nullptr, S2D_ERR_CUDA, "allocating the action table failed: %s", cudaGetErrorString(e));
-    if (h->d_dirs) cudaFree(h->d_dirs);
+    if (h->d_table) cudaFree(h->d_table);
     delete h;
     return S2D_ERR_CUDA;
   }
-  kp.dash_dirs = h->d_dirs;
+  kp.dash_table = h->d_table;
   h->grid = static_cast<int>((cfg->num_envs + kBlock - 1) / kBlock);
   *out = h;
   return S2D_OK;
@@ -190,7 +177,7 @@ int s2d_destroy(S2DHandle h) {
   if (!h) return S2D_OK;
   {
     DeviceGuard guard(h->cfg.device);
-    if (h->d_dirs) cudaFree(h->d_dirs);
+    if (h->d_table) cudaFree(h->d_table);
   }
   delete h;
   return S2D_OK;
@@ -229,14 +216,21 @@ int s2d_reset(S2DHandle h, const uint8_t* device_mask_or_null, void* stream) {
 int s2d_step(S2DHandle h, int k_substeps, void* stream) {
   if (!h) return S2D_ERR_INVALID;
   if (!h->bound) return fail(h, S2D_ERR_UNBOUND, "s2d_bind has not been called");
-  if (k_substeps < 1) return fail(h, S2D_ERR_INVALID, "k_substeps must be >= 1");
+  if (k_substeps < 1 || k_substeps > kMaxSubsteps)
+    return fail(h, S2D_ERR_INVALID, "k_substeps must be in 1..%d", kMaxSubsteps);
   DeviceGuard guard(h->cfg.device);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+#define S2D_LAUNCH(ACT)                                                                              \
+  do {                                                                                               \
+    if (h->default_sp) reachball_step_kernel<ACT, true><<<h->grid, kBlock, 0, s>>>(h->kp, k_substeps); \
+    else reachball_step_kernel<ACT, false><<<h->grid, kBlock, 0, s>>>(h->kp, k_substeps);            \
+  } while (0)
   switch (h->cfg.action_mode) {
-    case S2D_ACT_DISCRETE: reachball_step_kernel<S2D_ACT_DISCRETE><<<h->grid, kBlock, 0, s>>>(h->kp, k_substeps); break;
-    case S2D_ACT_CONTINUOUS: reachball_step_kernel<S2D_ACT_CONTINUOUS><<<h->grid, kBlock, 0, s>>>(h->kp, k_substeps); break;
-    default: reachball_step_kernel<S2D_ACT_TURNING><<<h->grid, kBlock, 0, s>>>(h->kp, k_substeps); break;
+    case S2D_ACT_DISCRETE: S2D_LAUNCH(S2D_ACT_DISCRETE); break;
+    case S2D_ACT_CONTINUOUS: S2D_LAUNCH(S2D_ACT_CONTINUOUS); break;
+    default: S2D_LAUNCH(S2D_ACT_TURNING); break;
   }
+#undef S2D_LAUNCH
   S2D_CUDA(h, cudaGetLastError());
   h->env_steps += static_cast<uint64_t>(h->cfg.num_envs) * static_cast<uint64_t>(k_substeps);
   return S2D_OK;
@@ -247,7 +241,8 @@ int s2d_step_host(S2DHandle h, int k_substeps, const void* h_actions, float* h_o
   if (!h) return S2D_ERR_INVALID;
   if (!h->bound) return fail(h, S2D_ERR_UNBOUND, "s2d_bind has not been called");
   if (!h_actions) return fail(h, S2D_ERR_INVALID, "h_actions is NULL");
-  if (k_substeps < 1) return fail(h, S2D_ERR_INVALID, "k_substeps must be >= 1");
+  if (k_substeps < 1 || k_substeps > kMaxSubsteps)
+    return fail(h, S2D_ERR_INVALID, "k_substeps must be in 1..%d", kMaxSubsteps);
   DeviceGuard guard(h->cfg.device);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const size_t n = static_cast<size_t>(h->cfg.num_envs);

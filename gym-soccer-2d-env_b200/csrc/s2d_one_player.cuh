@@ -2,7 +2,8 @@
 // (ReachBall: sample_environments/reach_ball_env.py; Shoot: 1v0 with the kick model).
 //
 // One thread owns one episode; everything below lives in registers between the state load and the state
-// store of a launch.  The arithmetic follows the fp32 SPEC of s2d_math.cuh (no implicit fma).
+// store of a launch.  The arithmetic follows the fp32 SPEC of s2d_math.cuh (no implicit fma).  Every function
+// takes the constants through an accessor type SP (RuntimeSP or DefaultSP, s2d_params.h).
 //
 // What each function stands in for (the reference only *launches* these; soccer_2d_env.py:356-398):
 //   dash / turn / kick        rcssserver Player::dash, Player::turn, Player::kick
@@ -11,8 +12,8 @@
 //   update_stamina            rcssserver Player::updateStamina
 //   recover                   trainer (recover) = proto DoRecover (idl/service.proto:1407)
 #pragma once
-#include "../../include/soccer2d.h"
 #include "s2d_math.cuh"
+#include "s2d_params.h"
 
 namespace s2d {
 
@@ -34,36 +35,6 @@ struct Episode {
   int step_number;
   uint32_t cycle, episode, flags;
 };
-
-// Physics constants in the form the cycle uses them: the proto ServerParam values plus products and
-// reciprocals that are the same for every env.  Built once per handle on the host (make_cycle_consts), in
-// float arithmetic, so device and host agree on every bit.
-struct CycleConsts {
-  S2DServerParam sp;
-  float inv_dash_angle_step;                 // 1 / dash_angle_step (0 when the step is disabled)
-  float player_accel_max2, player_speed_max2;  // squares: the clamps compare squared lengths
-  float ball_accel_max2, ball_speed_max2;
-  float collide_r, collide_r2;               // player_size + ball_size, and its square
-  float recover_dec_stamina, effort_dec_stamina, effort_inc_stamina;  // thresholds * stamina_max
-  float kickable_area;                       // player_size + ball_size + kickable_margin
-};
-
-inline CycleConsts make_cycle_consts(const S2DServerParam& sp) {
-  CycleConsts c;
-  c.sp = sp;
-  c.inv_dash_angle_step = sp.dash_angle_step > 1.0e-10f ? static_cast<float>(1.0 / static_cast<double>(sp.dash_angle_step)) : 0.0f;
-  c.player_accel_max2 = sp.player_accel_max * sp.player_accel_max;
-  c.player_speed_max2 = sp.player_speed_max * sp.player_speed_max;
-  c.ball_accel_max2 = sp.ball_accel_max * sp.ball_accel_max;
-  c.ball_speed_max2 = sp.ball_speed_max * sp.ball_speed_max;
-  c.collide_r = sp.player_size + sp.ball_size;
-  c.collide_r2 = c.collide_r * c.collide_r;
-  c.recover_dec_stamina = sp.recover_dec_thr * sp.stamina_max;
-  c.effort_dec_stamina = sp.effort_dec_thr * sp.stamina_max;
-  c.effort_inc_stamina = sp.effort_inc_thr * sp.stamina_max;
-  c.kickable_area = sp.player_size + sp.ball_size + sp.kickable_margin;
-  return c;
-}
 
 __device__ __forceinline__ void load_episode(const void* state, int64_t n, int64_t i, Episode& e) {
   const float4* f = reinterpret_cast<const float4*>(state);
@@ -89,34 +60,43 @@ __device__ __forceinline__ void store_episode(void* state, int64_t n, int64_t i,
 
 // ---- commands -------------------------------------------------------------------------------------
 
-__device__ __forceinline__ void recover(Episode& e, const S2DServerParam& sp) {
-  e.stamina = sp.stamina_max;
-  e.recovery = sp.recover_init;
-  e.effort = sp.effort_max;
-  e.capacity = sp.stamina_capacity;
+template <class SP>
+__device__ __forceinline__ void recover(Episode& e, const SP& sp) {
+  e.stamina = sp.stamina_max();
+  e.recovery = sp.recover_init();
+  e.effort = sp.effort_max();
+  e.capacity = sp.stamina_capacity();
 }
 
-// (dash power dir): stamina is charged first, then the effective power is scaled by effort, the
-// direction-dependent rate (forward 1, sideways side_dash_rate, backwards back_dash_rate) and
-// dash_power_rate.  Adds to the player's acceleration.
-__device__ __forceinline__ void dash(Episode& e, float power, float dir, const CycleConsts& C, float& ax, float& ay) {
-  const S2DServerParam& sp = C.sp;
-  power = clampf(sp.min_dash_power, power, sp.max_dash_power);
-  dir = clampf(sp.min_dash_angle, dir, sp.max_dash_angle);
-  if (sp.dash_angle_step > 1.0e-10f) dir = sp.dash_angle_step * rintf(dir * C.inv_dash_angle_step);
-  const bool back = power < 0.0f;
-  float need = back ? power * -2.0f : power;
-  need = fmin_(need, e.stamina + sp.extra_stamina);
-  e.stamina = fmax_(0.0f, e.stamina - need);
-  power = back ? need * -0.5f : need;
+// The direction half of (dash power dir): clamp, snap to dash_angle_step, and the direction-dependent rate
+// (forward 1, sideways side_dash_rate, backwards back_dash_rate).  It depends on the command only, not on
+// the episode, so Discrete(n) actions get it from a table built with this very function on the host.
+template <class SP>
+S2D_HD void dash_direction(float dir, const SP& sp, float& snapped, float& rate) {
+  dir = fmaxf(sp.min_dash_angle(), fminf(dir, sp.max_dash_angle()));
+  if (sp.dash_angle_step() > 1.0e-10f) dir = sp.dash_angle_step() * rintf(dir * sp.inv_dash_angle_step());
   const float ad = fabsf(dir);
   const float over = (ad - 90.0f) * static_cast<float>(1.0 / 90.0);
   const float under = ad * static_cast<float>(1.0 / 90.0);
-  const float rate_back = sp.back_dash_rate - ((sp.back_dash_rate - sp.side_dash_rate) * (1.0f - over));
-  const float rate_fwd = sp.side_dash_rate + ((1.0f - sp.side_dash_rate) * (1.0f - under));
-  const float rate = clampf(0.0f, ad > 90.0f ? rate_back : rate_fwd, 1.0f);
-  float eff = fabsf(e.effort * power * rate * sp.dash_power_rate);
-  const float slow = sp.slowness_on_top_for_left_team;  // the single player is on the left team
+  const float rate_back = sp.back_dash_rate() - ((sp.back_dash_rate() - sp.side_dash_rate()) * (1.0f - over));
+  const float rate_fwd = sp.side_dash_rate() + ((1.0f - sp.side_dash_rate()) * (1.0f - under));
+  rate = fmaxf(0.0f, fminf(ad > 90.0f ? rate_back : rate_fwd, 1.0f));
+  snapped = dir;
+}
+
+// The episode half: stamina is charged first, then the effective power is scaled by effort, the rate and
+// dash_power_rate.  Adds to the player's acceleration.
+template <class SP>
+__device__ __forceinline__ void dash_apply(Episode& e, float power, float dir, float rate, const SP& sp, float& ax,
+                                           float& ay) {
+  power = clampf(sp.min_dash_power(), power, sp.max_dash_power());
+  const bool back = power < 0.0f;
+  float need = back ? power * -2.0f : power;
+  need = fmin_(need, e.stamina + sp.extra_stamina());
+  e.stamina = fmax_(0.0f, e.stamina - need);
+  power = back ? need * -0.5f : need;
+  float eff = fabsf(e.effort * power * rate * sp.dash_power_rate());
+  const float slow = sp.slowness_on_top_for_left_team();  // the single player is on the left team
   if (slow != 1.0f && e.py < 0.0f) eff = cold_div(eff, slow);
   dir = back ? dir + 180.0f : dir;
   float s, c;
@@ -126,25 +106,26 @@ __device__ __forceinline__ void dash(Episode& e, float power, float dir, const C
 }
 
 // (turn moment): the faster the player moves, the less it turns (inertia_moment)
-__device__ __forceinline__ void turn(Episode& e, float moment, const CycleConsts& C) {
-  moment = clampf(C.sp.min_moment, moment, C.sp.max_moment);
+template <class SP>
+__device__ __forceinline__ void turn(Episode& e, float moment, const SP& sp) {
+  moment = clampf(sp.min_moment(), moment, sp.max_moment());
   const float speed = hypot2(e.vx, e.vy);
-  e.body = norm_deg(e.body + moment / (1.0f + C.sp.inertia_moment * speed));
+  e.body = norm_deg(e.body + moment / (1.0f + sp.inertia_moment() * speed));
 }
 
 // (kick power dir): only inside the kickable area; power falls off by up to 25 % with the angle between
 // body and ball and by up to 25 % with the distance.  Adds to the ball's acceleration.
-__device__ __forceinline__ bool kick(Episode& e, float power, float dir, const CycleConsts& C, float& bax, float& bay) {
-  const S2DServerParam& sp = C.sp;
-  power = clampf(0.0f, power, sp.max_power);
-  dir = clampf(sp.min_moment, dir, sp.max_moment);
+template <class SP>
+__device__ __forceinline__ bool kick(Episode& e, float power, float dir, const SP& sp, float& bax, float& bay) {
+  power = clampf(0.0f, power, sp.max_power());
+  dir = clampf(sp.min_moment(), dir, sp.max_moment());
   const float dx = e.bx - e.px, dy = e.by - e.py;
   const float dist = hypot2(dx, dy);
-  if (dist > C.kickable_area) return false;
+  if (dist > sp.kickable_area()) return false;
   const float dir_diff = fabsf(norm_deg_360(atan2_deg(dy, dx) - e.body));
-  const float dist_ball = dist - sp.player_size - sp.ball_size;
-  const float eff = power * sp.kick_power_rate *
-                    (1.0f - 0.25f * dir_diff * static_cast<float>(1.0 / 180.0) - 0.25f * dist_ball / sp.kickable_margin);
+  const float dist_ball = dist - sp.player_size() - sp.ball_size();
+  const float eff = power * sp.kick_power_rate() *
+                    (1.0f - 0.25f * dir_diff * static_cast<float>(1.0 / 180.0) - 0.25f * dist_ball / sp.kickable_margin());
   float s, c;
   sincos_deg(e.body + dir, s, c);
   bax += eff * c;
@@ -222,12 +203,13 @@ __device__ __noinline__ float2 resolve_ball_player_overlap(float px, float py, f
   return make_float2(bx, by);
 }
 
-__device__ __forceinline__ void collide_ball_player(Episode& e, const CycleConsts& C) {
+template <class SP>
+__device__ __forceinline__ void collide_ball_player(Episode& e, const SP& sp) {
   const float dx = e.bx - e.px, dy = e.by - e.py;
   uint32_t hit = 0;
-  if (dx * dx + dy * dy < C.collide_r2) {
+  if (dx * dx + dy * dy < sp.collide_r2()) {
     hit = S2D_FLAG_BALL_COLLIDED | S2D_FLAG_PLAYER_COLLIDED;
-    const float2 b = resolve_ball_player_overlap(e.px, e.py, e.bx, e.by, e.bvx, e.bvy, C.collide_r);
+    const float2 b = resolve_ball_player_overlap(e.px, e.py, e.bx, e.by, e.bvx, e.bvy, sp.collide_r());
     e.bx = b.x;
     e.by = b.y;
     e.bvx *= -0.1f;
@@ -239,25 +221,25 @@ __device__ __forceinline__ void collide_ball_player(Episode& e, const CycleConst
 }
 
 // Player::updateStamina, written with selects instead of nested branches.
-__device__ __forceinline__ void update_stamina(Episode& e, const CycleConsts& C) {
-  const S2DServerParam& sp = C.sp;
+template <class SP>
+__device__ __forceinline__ void update_stamina(Episode& e, const SP& sp) {
   {  // recovery decays below recover_dec_thr * stamina_max
-    float r = e.recovery > sp.recover_min ? e.recovery - sp.recover_dec : e.recovery;
-    r = r < sp.recover_min ? sp.recover_min : r;
-    e.recovery = e.stamina <= C.recover_dec_stamina ? r : e.recovery;
+    float r = e.recovery > sp.recover_min() ? e.recovery - sp.recover_dec() : e.recovery;
+    r = r < sp.recover_min() ? sp.recover_min() : r;
+    e.recovery = e.stamina <= sp.recover_dec_stamina() ? r : e.recovery;
   }
   {  // effort decays below effort_dec_thr * stamina_max ...
-    float f = e.effort > sp.effort_min ? e.effort - sp.effort_dec : e.effort;
-    f = f < sp.effort_min ? sp.effort_min : f;
-    e.effort = e.stamina <= C.effort_dec_stamina ? f : e.effort;
+    float f = e.effort > sp.effort_min() ? e.effort - sp.effort_dec() : e.effort;
+    f = f < sp.effort_min() ? sp.effort_min() : f;
+    e.effort = e.stamina <= sp.effort_dec_stamina() ? f : e.effort;
   }
   {  // ... and comes back above effort_inc_thr * stamina_max
-    float f = e.effort + sp.effort_inc;
-    f = f > sp.effort_max ? sp.effort_max : f;
-    e.effort = (e.stamina >= C.effort_inc_stamina && e.effort < sp.effort_max) ? f : e.effort;
+    float f = e.effort + sp.effort_inc();
+    f = f > sp.effort_max() ? sp.effort_max() : f;
+    e.effort = (e.stamina >= sp.effort_inc_stamina() && e.effort < sp.effort_max()) ? f : e.effort;
   }
-  float inc = fmin_(e.recovery * sp.stamina_inc_max, sp.stamina_max - e.stamina);
-  const bool capped = sp.stamina_capacity >= 0.0f;
+  float inc = fmin_(e.recovery * sp.stamina_inc_max(), sp.stamina_max() - e.stamina);
+  const bool capped = sp.stamina_capacity() >= 0.0f;
   inc = (capped && inc > e.capacity) ? e.capacity : inc;
   e.stamina += inc;
   e.capacity = capped ? fmax_(0.0f, e.capacity - inc) : e.capacity;
@@ -265,25 +247,25 @@ __device__ __forceinline__ void update_stamina(Episode& e, const CycleConsts& C)
 
 // One server cycle with at most one body command.  Order as in rcssserver's Stadium::step: commands were
 // applied on receipt, then every object moves, then collisions, then stamina, then the clock.
-// TURNS / KICKS say whether the caller can issue those commands at all (compile-time pruning).
-template <bool TURNS, bool KICKS>
-__device__ __forceinline__ void simulate_cycle(Episode& e, int cmd, float power, float dir, const CycleConsts& C) {
-  const S2DServerParam& sp = C.sp;
+// For S2D_CMD_DASH, (dir, rate) come from dash_direction.  TURNS / KICKS say whether the caller can issue those
+// commands at all (compile-time pruning).
+template <bool TURNS, bool KICKS, class SP>
+__device__ __forceinline__ void simulate_cycle(Episode& e, int cmd, float power, float dir, float rate, const SP& sp) {
   float ax = 0.0f, ay = 0.0f, bax = 0.0f, bay = 0.0f;
   if (KICKS) e.flags &= ~S2D_FLAG_KICKED;
   if (cmd == S2D_CMD_DASH) {
-    dash(e, power, dir, C, ax, ay);
+    dash_apply(e, power, dir, rate, sp, ax, ay);
   } else if (TURNS && cmd == S2D_CMD_TURN) {
-    turn(e, dir, C);
+    turn(e, dir, sp);
   } else if (KICKS && cmd == S2D_CMD_KICK) {
-    if (kick(e, power, dir, C, bax, bay)) e.flags |= S2D_FLAG_KICKED;
+    if (kick(e, power, dir, sp, bax, bay)) e.flags |= S2D_FLAG_KICKED;
   }
-  move_object(e.px, e.py, e.vx, e.vy, ax, ay, sp.player_accel_max, C.player_accel_max2, sp.player_speed_max,
-              C.player_speed_max2, sp.player_decay);
-  move_object(e.bx, e.by, e.bvx, e.bvy, bax, bay, sp.ball_accel_max, C.ball_accel_max2, sp.ball_speed_max,
-              C.ball_speed_max2, sp.ball_decay);
-  collide_ball_player(e, C);
-  update_stamina(e, C);
+  move_object(e.px, e.py, e.vx, e.vy, ax, ay, sp.player_accel_max(), sp.player_accel_max2(), sp.player_speed_max(),
+              sp.player_speed_max2(), sp.player_decay());
+  move_object(e.bx, e.by, e.bvx, e.bvy, bax, bay, sp.ball_accel_max(), sp.ball_accel_max2(), sp.ball_speed_max(),
+              sp.ball_speed_max2(), sp.ball_decay());
+  collide_ball_player(e, sp);
+  update_stamina(e, sp);
   e.cycle += 1u;
 }
 

@@ -11,6 +11,8 @@
 #include <math.h>
 #include <string.h>
 
+#include <type_traits>
+
 #include "s2d_one_player.cuh"
 
 namespace s2d {
@@ -38,12 +40,14 @@ struct KernelParams {
   uint8_t* result;
   float* terminal_obs;
   unsigned long long* stats;  // [kStatSlots][kStatWords]
-  const float* dash_dirs;     // [256] Discrete(n) -> relative direction, built on the host at create
+  const float2* dash_table;   // [256] Discrete(n) -> {snapped dash direction, direction rate}, built on the host
 };
 
-// Fills everything but the buffer pointers from a config.  `dirs` receives the Discrete(n) -> Dash direction
-// table of reach_ball_env.py:84, evaluated as the reference does (double, then the proto float).
-inline void make_kernel_params(const S2DConfig& cfg, KernelParams& kp, float dirs[256]) {
+// Fills everything but the buffer pointers from a config.  `table` receives, per Discrete(n) action, the Dash
+// direction of reach_ball_env.py:84 (evaluated as the reference does: double, then the proto float) already
+// lowered by dash_direction (clamp, dash_angle_step snap, direction rate) - the part of Player::dash that does
+// not depend on the episode.
+inline void make_kernel_params(const S2DConfig& cfg, KernelParams& kp, float2 table[256]) {
   memset(&kp, 0, sizeof(kp));
   kp.cc = make_cycle_consts(cfg.sp);
   kp.num_envs = cfg.num_envs;
@@ -66,8 +70,11 @@ inline void make_kernel_params(const S2DConfig& cfg, KernelParams& kp, float dir
   // reach_ball_env.py:207 - the reference uses 0.96 here, not the server's ball_decay
   kp.travel_factor = static_cast<float>((1.0 - pow(0.96, static_cast<double>(cfg.max_steps))) / (1.0 - 0.96));
   const int n = cfg.action_space_size;
-  for (int a = 0; a < 256; ++a)
-    dirs[a] = n > 0 ? static_cast<float>(fmod(static_cast<double>(a) * 360.0 / static_cast<double>(n), 360.0) - 180.0) : 0.0f;
+  const RuntimeSP sp(kp.cc);
+  for (int a = 0; a < 256; ++a) {
+    const float dir = n > 0 ? static_cast<float>(fmod(static_cast<double>(a) * 360.0 / static_cast<double>(n), 360.0) - 180.0) : 0.0f;
+    dash_direction(dir, sp, table[a].x, table[a].y);
+  }
 }
 
 // episode statistics: slots spread the atomics over L2 lines; s2d_stats sums them
@@ -75,12 +82,20 @@ constexpr int kStatSlots = 256;
 constexpr int kStatWords = 8;  // episodes, goals, outs, timeouts, episode_steps, return (double bits), pad, pad
 enum { ST_EPISODES = 0, ST_GOALS = 1, ST_OUTS = 2, ST_TIMEOUTS = 3, ST_EP_STEPS = 4, ST_RETURN = 5 };
 
-// what one launch accumulates per env
+// what one launch accumulates per env.  `ended` packs three 10-bit counters (episodes that ended as Goal / Out /
+// Timeout during the launch: K <= kMaxSubsteps) and, in the top two bits, the result of the last one.
+constexpr int kMaxSubsteps = 1023;
 struct LaunchOut {
   float reward_sum = 0.0f;
-  uint32_t any_done = 0, last_result = 0;
-  uint32_t episodes = 0, goals = 0, outs = 0, timeouts = 0, ep_steps = 0;
+  uint32_t ended = 0;
+  uint32_t ep_steps = 0;
   double ret = 0.0;
+  __device__ __forceinline__ void count(int result) { ended = ((ended & 0x3fffffffu) + (1u << (10 * (result - 1)))) | (static_cast<uint32_t>(result) << 30); }
+  __device__ __forceinline__ uint32_t goals() const { return ended & 0x3ffu; }
+  __device__ __forceinline__ uint32_t outs() const { return (ended >> 10) & 0x3ffu; }
+  __device__ __forceinline__ uint32_t timeouts() const { return (ended >> 20) & 0x3ffu; }
+  __device__ __forceinline__ uint32_t episodes() const { return goals() + outs() + timeouts(); }
+  __device__ __forceinline__ uint32_t last_result() const { return ended >> 30; }
 };
 
 // reach_ball_env.py:113-161.  Rewards accumulate and later endings overwrite `result`, in the reference's
@@ -126,7 +141,8 @@ __device__ __forceinline__ void build_obs(const Episode& e, float* o) {
 // bounded rejection: the ball must stay on the pitch for max_steps cycles), then DoMoveBall / DoMovePlayer
 // (vel = 0) / DoRecover.  The caller still owes the episode ONE idle server cycle and the priming check
 // (the reference's reset observes the state one cycle after placement, reach_ball_env.py:163-168).
-__device__ __forceinline__ void place_new_episode(Episode& e, const KernelParams& P, uint64_t gid) {
+template <class SP>
+__device__ __forceinline__ void place_new_episode(Episode& e, const KernelParams& P, const SP& sp, uint64_t gid) {
   const uint4 w = philox4x32_10(P.seed, gid, e.episode, RNG_RESET, 0);
   const float px = static_cast<float>(u32_to_int(w.x, -50, 50));
   const float py = static_cast<float>(u32_to_int(w.y, -30, 30));
@@ -166,7 +182,7 @@ __device__ __forceinline__ void place_new_episode(Episode& e, const KernelParams
   e.px = px; e.py = py; e.vx = 0.0f; e.vy = 0.0f;
   e.body = norm_deg(body);
   e.flags = 0u;
-  recover(e, P.cc.sp);
+  recover(e, sp);
 }
 
 // per-lane row store (terminal observations, reset kernel): 40-byte rows are 8-byte aligned
@@ -179,19 +195,21 @@ __device__ __forceinline__ void lane_store_row(float* __restrict__ dst, int64_t 
 // ONE env-step = what Soccer2DEnv.step does: decode the action, run the server cycle, score it; when the
 // episode ends, record it and (auto_reset) start the next one, which costs a second, idle pass through the
 // same cycle + check code (placement, one cycle, priming check whose reward is discarded).
-//   a0..a3: the action - discrete: a0 = dash direction from the table; continuous: a0 in [-1,1];
-//           turning: [turn_prob, turn_angle, dash_prob, dash_angle] (reach_ball_env.py:65-68)
-template <int ACT>
-__device__ __forceinline__ void substep(Episode& e, const KernelParams& P, uint64_t gid, int64_t i, float a0, float a1,
-                                        float a2, float a3, LaunchOut& out) {
+//   discrete:   a0 = snapped dash direction, a1 = its direction rate (both from the action table)
+//   continuous: a0 in [-1, 1]
+//   turning:    [turn_prob, turn_angle, dash_prob, dash_angle] (reach_ball_env.py:65-68)
+template <int ACT, class SP>
+__device__ __forceinline__ void substep(Episode& e, const KernelParams& P, const SP& sp, uint64_t gid, int64_t i, float a0,
+                                        float a1, float a2, float a3, LaunchOut& out) {
   constexpr bool kTurns = ACT == S2D_ACT_TURNING;
   e.step_number += 1;  // reach_ball_env.py:55
   int cmd = S2D_CMD_DASH;
-  float power = 100.0f, dir;
+  float power = 100.0f, dir, rate;
   if (ACT == S2D_ACT_DISCRETE) {
     dir = a0;
+    rate = a1;
   } else if (ACT == S2D_ACT_CONTINUOUS) {
-    dir = a0 * 180.0f;
+    dash_direction(a0 * 180.0f, sp, dir, rate);
   } else {
     const float tp = clampf(-1.0f, a0, 1.0f), ta = clampf(-1.0f, a1, 1.0f);
     const float dp = clampf(-1.0f, a2, 1.0f), da = clampf(-1.0f, a3, 1.0f);
@@ -199,12 +217,13 @@ __device__ __forceinline__ void substep(Episode& e, const KernelParams& P, uint6
     const bool turn_selected = u < softmax_first(dp, tp);  // :69-72: tested against the DASH logit's weight
     cmd = turn_selected ? S2D_CMD_TURN : S2D_CMD_DASH;
     power = turn_selected ? 0.0f : 100.0f;
-    dir = (turn_selected ? ta : da) * 180.0f;
+    dash_direction(da * 180.0f, sp, dir, rate);
+    dir = turn_selected ? ta * 180.0f : dir;
   }
   bool priming = false;
 #pragma unroll 1
   for (;;) {
-    simulate_cycle<kTurns, false>(e, cmd, power, dir, P.cc);
+    simulate_cycle<kTurns, false>(e, cmd, power, dir, rate, sp);
     float rw;
     int rs;
     const bool done = check_episode(e, P, rw, rs);
@@ -212,14 +231,9 @@ __device__ __forceinline__ void substep(Episode& e, const KernelParams& P, uint6
     out.reward_sum += rw;
     e.ep_return += rw;
     if (!done) break;
-    out.any_done = 1;
-    out.last_result = static_cast<uint32_t>(rs);
-    out.episodes += 1;
+    out.count(rs);
     out.ep_steps += static_cast<uint32_t>(e.step_number);
     out.ret += static_cast<double>(e.ep_return);
-    out.goals += rs == S2D_RESULT_GOAL;
-    out.outs += rs == S2D_RESULT_OUT;
-    out.timeouts += rs == S2D_RESULT_TIMEOUT;
     if (P.terminal_obs) {
       float row[kObsDim];
       build_obs(e, row);
@@ -229,16 +243,17 @@ __device__ __forceinline__ void substep(Episode& e, const KernelParams& P, uint6
       e.flags |= S2D_FLAG_DONE;
       break;
     }
-    place_new_episode(e, P, gid);
+    place_new_episode(e, P, sp, gid);
     cmd = S2D_CMD_NONE;
     priming = true;
   }
 }
 
 // Soccer2DEnv.reset for one env: placement, the idle cycle, the priming check.
-__device__ __forceinline__ void reset_episode(Episode& e, const KernelParams& P, uint64_t gid) {
-  place_new_episode(e, P, gid);
-  simulate_cycle<false, false>(e, S2D_CMD_NONE, 0.0f, 0.0f, P.cc);
+template <class SP>
+__device__ __forceinline__ void reset_episode(Episode& e, const KernelParams& P, const SP& sp, uint64_t gid) {
+  place_new_episode(e, P, sp, gid);
+  simulate_cycle<false, false>(e, S2D_CMD_NONE, 0.0f, 0.0f, 0.0f, sp);
   float rw;
   int rs;
   check_episode(e, P, rw, rs);
@@ -268,17 +283,16 @@ __device__ __forceinline__ void warp_store_obs(float* __restrict__ dst, int64_t 
 // warp-level sum of the launch's episode statistics, then one lane adds them to a stats slot
 __device__ __forceinline__ void flush_tally(const LaunchOut& t, unsigned long long* stats) {
   const unsigned full = 0xffffffffu;
-  if (!__any_sync(full, t.episodes != 0)) return;
-  const uint32_t ep = __reduce_add_sync(full, t.episodes), g = __reduce_add_sync(full, t.goals),
-                 o = __reduce_add_sync(full, t.outs), to = __reduce_add_sync(full, t.timeouts),
-                 st = __reduce_add_sync(full, t.ep_steps);
+  if (!__any_sync(full, t.ended != 0)) return;
+  const uint32_t g = __reduce_add_sync(full, t.goals()), o = __reduce_add_sync(full, t.outs()),
+                 to = __reduce_add_sync(full, t.timeouts()), st = __reduce_add_sync(full, t.ep_steps);
   double r = t.ret;
 #pragma unroll
   for (int s = 16; s > 0; s >>= 1) r += __shfl_xor_sync(full, r, s);
   if ((threadIdx.x & 31) == 0) {
     const unsigned warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     unsigned long long* slot = stats + static_cast<size_t>(warp_global % kStatSlots) * kStatWords;
-    atomicAdd(slot + ST_EPISODES, static_cast<unsigned long long>(ep));
+    atomicAdd(slot + ST_EPISODES, static_cast<unsigned long long>(g + o + to));
     if (g) atomicAdd(slot + ST_GOALS, static_cast<unsigned long long>(g));
     if (o) atomicAdd(slot + ST_OUTS, static_cast<unsigned long long>(o));
     if (to) atomicAdd(slot + ST_TIMEOUTS, static_cast<unsigned long long>(to));
@@ -298,15 +312,18 @@ constexpr int kBlock = S2D_BLOCK;
 #endif
 
 // K lockstep cycles of every env in one launch; state stays in registers in between.
-// actions[N][K] (uint8 / float) or [N][K][4] (float): a lane's K actions are contiguous; with K a multiple of
-// 16 (uint8) or 4 (float) they come in as 128-bit words, otherwise one by one through the read-only path.
-template <int ACT>
+// actions[N][K] (uint8 / float) or [N][K][4] (float): a lane's K actions are contiguous in memory; the first
+// access pulls the lane's sector(s) into L1 and the following cycles hit there (ld.global.nc).
+// DEF: the constants are the default ServerParam, folded at compile time (DefaultSP).
+template <int ACT, bool DEF>
 __global__ void __launch_bounds__(kBlock, S2D_MIN_BLOCKS) reachball_step_kernel(const __grid_constant__ KernelParams P,
                                                                                const int K) {
-  __shared__ float s_dirs[256];
+  using SP = typename std::conditional<DEF, DefaultSP, RuntimeSP>::type;
+  const SP sp(P.cc);
+  __shared__ float2 s_table[256];
   __shared__ __align__(16) float s_stage[kBlock / 32][32 * kObsDim];
   if (ACT == S2D_ACT_DISCRETE) {
-    for (int a = threadIdx.x; a < 256; a += kBlock) s_dirs[a] = P.dash_dirs[a];
+    for (int a = threadIdx.x; a < P.action_space_size; a += kBlock) s_table[a] = P.dash_table[a];
     __syncthreads();
   }
   const int64_t i = static_cast<int64_t>(blockIdx.x) * kBlock + threadIdx.x;
@@ -323,45 +340,29 @@ __global__ void __launch_bounds__(kBlock, S2D_MIN_BLOCKS) reachball_step_kernel(
   if (valid) {
     load_episode(P.state, n, i, e);
     if (ACT == S2D_ACT_DISCRETE) {
-      const uint8_t* base = static_cast<const uint8_t*>(P.actions) + i * K;
-      const bool vec = (K & 15) == 0;  // 16 actions per 128-bit load, peeled off byte by byte
-      uint4 w = make_uint4(0, 0, 0, 0);
-      uint32_t cur = 0;
+      const uint8_t* act = static_cast<const uint8_t*>(P.actions) + i * K;
 #pragma unroll 1
       for (int k = 0; k < K; ++k) {
-        uint32_t a;
-        if (vec) {
-          if ((k & 15) == 0) w = __ldg(reinterpret_cast<const uint4*>(base + k));
-          if ((k & 3) == 0) {
-            cur = w.x;
-            w.x = w.y;
-            w.y = w.z;
-            w.z = w.w;
-          }
-          a = cur & 0xffu;
-          cur >>= 8;
-        } else {
-          a = __ldg(base + k);
-        }
-        substep<ACT>(e, P, gid, i, s_dirs[a], 0.f, 0.f, 0.f, out);
+        const float2 t = s_table[__ldg(act + k)];
+        substep<ACT>(e, P, sp, gid, i, t.x, t.y, 0.f, 0.f, out);
       }
     } else if (ACT == S2D_ACT_CONTINUOUS) {
-      const float* base = static_cast<const float*>(P.actions) + i * K;
+      const float* act = static_cast<const float*>(P.actions) + i * K;
 #pragma unroll 1
-      for (int k = 0; k < K; ++k) substep<ACT>(e, P, gid, i, __ldg(base + k), 0.f, 0.f, 0.f, out);
+      for (int k = 0; k < K; ++k) substep<ACT>(e, P, sp, gid, i, __ldg(act + k), 0.f, 0.f, 0.f, out);
     } else {
-      const float4* base = static_cast<const float4*>(P.actions) + i * K;
+      const float4* act = static_cast<const float4*>(P.actions) + i * K;
 #pragma unroll 1
       for (int k = 0; k < K; ++k) {
-        const float4 a = __ldg(base + k);
-        substep<ACT>(e, P, gid, i, a.x, a.y, a.z, a.w, out);
+        const float4 a = __ldg(act + k);
+        substep<ACT>(e, P, sp, gid, i, a.x, a.y, a.z, a.w, out);
       }
     }
     store_episode(P.state, n, i, e);
     build_obs(e, obs_row);
     P.reward[i] = out.reward_sum;
-    P.done[i] = static_cast<uint8_t>(out.any_done);
-    P.result[i] = static_cast<uint8_t>(out.last_result);
+    P.done[i] = static_cast<uint8_t>(out.ended != 0);
+    P.result[i] = static_cast<uint8_t>(out.last_result());
   }
   warp_store_obs(P.obs, warp_first, n, obs_row, valid, stage);
   flush_tally(out, P.stats);
@@ -373,9 +374,10 @@ __global__ void __launch_bounds__(kBlock) reachball_reset_kernel(const __grid_co
   const int64_t i = static_cast<int64_t>(blockIdx.x) * kBlock + threadIdx.x;
   if (i >= P.num_envs) return;
   if (mask && !mask[i]) return;
+  const RuntimeSP sp(P.cc);
   Episode e;
   load_episode(P.state, P.num_envs, i, e);
-  reset_episode(e, P, static_cast<uint64_t>(P.env_id_offset + i));
+  reset_episode(e, P, sp, static_cast<uint64_t>(P.env_id_offset + i));
   store_episode(P.state, P.num_envs, i, e);
   float row[kObsDim];
   build_obs(e, row);

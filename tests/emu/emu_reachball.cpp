@@ -11,14 +11,16 @@ using namespace s2d;
 
 struct Emu {
   KernelParams kp;
-  float dirs[256];
+  float2 table[256];
+  bool default_sp;  // same dispatch as s2d_create: constant-folded accessors for the default ServerParam
   std::vector<unsigned char> state;
 };
 
-template <int ACT>
+template <int ACT, class SP>
 static void step_all(Emu* h, const void* actions, int K, float* obs, float* reward, uint8_t* done, uint8_t* result,
                      double* stats) {
   const KernelParams& P = h->kp;
+  const SP sp(P.cc);
   const int64_t n = P.num_envs;
   for (int64_t i = 0; i < n; ++i) {
     Episode e;
@@ -27,20 +29,21 @@ static void step_all(Emu* h, const void* actions, int K, float* obs, float* rewa
     const uint64_t gid = (uint64_t)(P.env_id_offset + i);
     for (int k = 0; k < K; ++k) {
       if (ACT == S2D_ACT_DISCRETE) {
-        substep<ACT>(e, P, gid, i, h->dirs[((const uint8_t*)actions)[i * K + k]], 0.f, 0.f, 0.f, out);
+        const float2 t = h->table[((const uint8_t*)actions)[i * K + k]];
+        substep<ACT>(e, P, sp, gid, i, t.x, t.y, 0.f, 0.f, out);
       } else if (ACT == S2D_ACT_CONTINUOUS) {
-        substep<ACT>(e, P, gid, i, ((const float*)actions)[i * K + k], 0.f, 0.f, 0.f, out);
+        substep<ACT>(e, P, sp, gid, i, ((const float*)actions)[i * K + k], 0.f, 0.f, 0.f, out);
       } else {
         const float* a = (const float*)actions + (i * K + k) * 4;
-        substep<ACT>(e, P, gid, i, a[0], a[1], a[2], a[3], out);
+        substep<ACT>(e, P, sp, gid, i, a[0], a[1], a[2], a[3], out);
       }
     }
     store_episode(P.state, n, i, e);
     build_obs(e, obs + i * kObsDim);
     reward[i] = out.reward_sum;
-    done[i] = (uint8_t)out.any_done;
-    result[i] = (uint8_t)out.last_result;
-    stats[0] += out.episodes; stats[1] += out.goals; stats[2] += out.outs; stats[3] += out.timeouts;
+    done[i] = (uint8_t)(out.ended != 0);
+    result[i] = (uint8_t)out.last_result();
+    stats[0] += out.episodes(); stats[1] += out.goals(); stats[2] += out.outs(); stats[3] += out.timeouts();
     stats[4] += out.ep_steps; stats[5] += out.ret;
   }
 }
@@ -49,10 +52,11 @@ extern "C" {
 
 void* emu_create(const S2DConfig* cfg) {
   Emu* h = new Emu();
-  make_kernel_params(*cfg, h->kp, h->dirs);
+  make_kernel_params(*cfg, h->kp, h->table);
+  h->default_sp = is_default_server_param(cfg->sp);
   h->state.assign((size_t)cfg->num_envs * kStateBytesPerEnv, 0);
   h->kp.state = h->state.data();
-  h->kp.dash_dirs = h->dirs;
+  h->kp.dash_table = h->table;
   return h;
 }
 void emu_destroy(void* p) { delete (Emu*)p; }
@@ -65,7 +69,7 @@ void emu_reset(void* p, const uint8_t* mask, float* obs) {
     if (mask && !mask[i]) continue;
     Episode e;
     load_episode(P.state, P.num_envs, i, e);
-    reset_episode(e, P, (uint64_t)(P.env_id_offset + i));
+    reset_episode(e, P, RuntimeSP(P.cc), (uint64_t)(P.env_id_offset + i));
     store_episode(P.state, P.num_envs, i, e);
     build_obs(e, obs + i * kObsDim);
   }
@@ -75,11 +79,38 @@ void emu_step(void* p, const void* actions, int K, float* obs, float* reward, ui
               float* terminal_obs, double* stats6) {
   Emu* h = (Emu*)p;
   h->kp.terminal_obs = terminal_obs;
+#define EMU_STEP(ACT)                                                                            \
+  do {                                                                                           \
+    if (h->default_sp) step_all<ACT, DefaultSP>(h, actions, K, obs, reward, done, result, stats6); \
+    else step_all<ACT, RuntimeSP>(h, actions, K, obs, reward, done, result, stats6);             \
+  } while (0)
   switch (h->kp.action_mode) {
-    case S2D_ACT_DISCRETE: step_all<S2D_ACT_DISCRETE>(h, actions, K, obs, reward, done, result, stats6); break;
-    case S2D_ACT_CONTINUOUS: step_all<S2D_ACT_CONTINUOUS>(h, actions, K, obs, reward, done, result, stats6); break;
-    default: step_all<S2D_ACT_TURNING>(h, actions, K, obs, reward, done, result, stats6); break;
+    case S2D_ACT_DISCRETE: EMU_STEP(S2D_ACT_DISCRETE); break;
+    case S2D_ACT_CONTINUOUS: EMU_STEP(S2D_ACT_CONTINUOUS); break;
+    default: EMU_STEP(S2D_ACT_TURNING); break;
   }
 }
+
+// DefaultSP (compile-time constants) must equal make_cycle_consts(defaults) bit for bit; returns the mismatches
+int emu_check_default_consts(void) {
+  S2DServerParam sp;
+  default_server_param(sp);
+  const CycleConsts c = make_cycle_consts(sp);
+  const RuntimeSP r(c);
+  const DefaultSP d(c);
+  int bad = 0;
+#define X(name, def) bad += memcmp(&(const float&)r.name(), &(const float&)d.name(), 4) != 0;
+#define CHK(name) { float a = r.name(), b = d.name(); bad += memcmp(&a, &b, 4) != 0; }
+#undef X
+#define X(name, def) CHK(name)
+  S2D_SERVER_PARAMS(X)
+#undef X
+#define Y(name, expr) CHK(name)
+  S2D_DERIVED_PARAMS(Y)
+#undef Y
+  return bad;
+}
+
+int emu_uses_default_sp(void* p) { return ((Emu*)p)->default_sp ? 1 : 0; }
 
 }  // extern "C"

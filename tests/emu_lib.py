@@ -28,6 +28,7 @@ def lib():
         L.emu_state.argtypes = [C.c_void_p]
         L.emu_reset.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.emu_step.argtypes = [C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 6
+        L.emu_uses_default_sp.argtypes = [C.c_void_p]
         _lib = L
     return _lib
 

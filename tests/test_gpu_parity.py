@@ -99,6 +99,28 @@ def test_bit_exact_against_fp32_oracle_1000_cycles(mode):
 
 
 @pytest.mark.parametrize("mode", ["discrete", "continuous", "turning"])
+def test_non_default_server_param_kernels_bit_exact(mode):
+    """A non-default ServerParam selects the kernels that read their constants from the constant bank (the default
+    one uses compile-time constants): 45-degree dash_angle_step, slowness on top, other decays / rates."""
+    n = 600
+    sp = dict(dash_angle_step=45.0, slowness_on_top_for_left_team=1.25, player_decay=0.5, ball_decay=0.9,
+              side_dash_rate=0.5, back_dash_rate=0.6, stamina_inc_max=30.0, player_speed_max=0.8, inertia_moment=3.0)
+    env = make_env(n, mode, seed=11, change_ball_velocity=True, terminal_obs=True, max_steps=80, server_param=sp)
+    sim = OL.OracleSim(env.cfg, "f32")
+    assert np.array_equal(env.reset(), sim.reset())
+    rng = np.random.default_rng(0)
+    episodes = 0
+    for t in range(400):
+        act = H.random_actions(rng, mode, n)
+        env.step_torch(torch.from_numpy(act))
+        sim.step(act)
+        episodes += assert_same_step(env, sim)
+    assert np.array_equal(gpu_state(env), sim.get_state())
+    assert episodes > n
+    env.close()
+
+
+@pytest.mark.parametrize("mode", ["discrete", "continuous", "turning"])
 def test_against_f64_truth_1000_cycles(mode):
     """north star: flags bit-exact, floats within 1e-5 relative over 1 000 cycles against the double oracle."""
     n = 192

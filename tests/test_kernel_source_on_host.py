@@ -36,6 +36,32 @@ def test_kernel_source_bit_exact(mode, k):
     assert st.return_sum == pytest.approx(emu.stats6[5], rel=1e-12)
 
 
+def test_default_constants_fold_to_the_same_bits():
+    """DefaultSP (immediates in the constant-folded kernels) == make_cycle_consts(default ServerParam)."""
+    assert EL.lib().emu_check_default_consts() == 0
+
+
+@pytest.mark.parametrize("mode", ["discrete", "continuous", "turning"])
+def test_kernel_source_runtime_params_path(mode):
+    """Non-default ServerParam -> the RuntimeSP kernels (constants from the constant bank), incl. back dashes
+    (min_dash_power < 0 is irrelevant at power 100, so exercise slowness, a 45-degree dash_angle_step, other decays)."""
+    n = 129
+    sp = dict(dash_angle_step=45.0, slowness_on_top_for_left_team=1.25, player_decay=0.5, ball_decay=0.9,
+              side_dash_rate=0.5, back_dash_rate=0.6, stamina_inc_max=30.0, player_speed_max=0.8, inertia_moment=3.0)
+    cfg = H.make_config(n, mode, seed=3, change_ball_velocity=1, max_steps=80, sp=sp)
+    emu, sim = EL.EmuSim(cfg), OL.OracleSim(cfg, "f32")
+    assert EL.lib().emu_uses_default_sp(emu.h) == 0
+    assert np.array_equal(emu.reset(), sim.reset())
+    rng = np.random.default_rng(0)
+    for t in range(300):
+        act = H.random_actions(rng, mode, n)
+        emu.step(act)
+        sim.step(act)
+        assert np.array_equal(emu.done, sim.done) and np.array_equal(emu.result, sim.result)
+        assert np.array_equal(emu.obs, sim.obs) and np.array_equal(emu.reward, sim.reward)
+    assert np.array_equal(emu.get_state(), sim.get_state())
+
+
 def test_kernel_source_hand_placed_states():
     cases = HAND_PLACED_STATES
     n = len(cases)

@@ -119,6 +119,8 @@ class ClockSampler(threading.Thread):
 
 def time_cpu_oracle(envs, k, min_seconds, max_launches=10**9, warmup=1, fixed_launches=None):
     """env-steps/s of the C oracle (f64 build, OpenMP over all host cores) on `envs` episodes x k cycles per call."""
+    # torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm is meant to use every host thread it can
+    os.environ["OMP_NUM_THREADS"] = str(host_threads())
     import numpy as np
 
     import helpers as H

@@ -85,7 +85,7 @@ S2D_HD void dash_direction(float dir, const SP& sp, float& snapped, float& rate)
 }
 
 // The episode half: stamina is charged first, then the effective power is scaled by effort, the rate and
-// dash_power_rate.  Adds to the player's acceleration.
+// dash_power_rate.  Gives the player's acceleration (it is the only contribution in a cycle).
 template <class SP>
 __device__ __forceinline__ void dash_apply(Episode& e, float power, float dir, float rate, const SP& sp, float& ax,
                                            float& ay) {
@@ -101,8 +101,8 @@ __device__ __forceinline__ void dash_apply(Episode& e, float power, float dir, f
   dir = back ? dir + 180.0f : dir;
   float s, c;
   sincos_deg(e.body + dir, s, c);
-  ax += eff * c;
-  ay += eff * s;
+  ax = eff * c;
+  ay = eff * s;
 }
 
 // (turn moment): the faster the player moves, the less it turns (inertia_moment)
@@ -203,11 +203,12 @@ __device__ __noinline__ float2 resolve_ball_player_overlap(float px, float py, f
   return make_float2(bx, by);
 }
 
+// (dx, dy) = ball - player and d2 = dx*dx + dy*dy come from the caller, which re-uses them for the reward when
+// nothing collided (the common case).  Returns true when the ball was moved.
 template <class SP>
-__device__ __forceinline__ void collide_ball_player(Episode& e, const SP& sp) {
-  const float dx = e.bx - e.px, dy = e.by - e.py;
+__device__ __forceinline__ bool collide_ball_player(Episode& e, float d2, const SP& sp) {
   uint32_t hit = 0;
-  if (dx * dx + dy * dy < sp.collide_r2()) {
+  if (d2 < sp.collide_r2()) {
     hit = S2D_FLAG_BALL_COLLIDED | S2D_FLAG_PLAYER_COLLIDED;
     const float2 b = resolve_ball_player_overlap(e.px, e.py, e.bx, e.by, e.bvx, e.bvy, sp.collide_r());
     e.bx = b.x;
@@ -218,6 +219,7 @@ __device__ __forceinline__ void collide_ball_player(Episode& e, const SP& sp) {
     e.vy *= -0.1f;
   }
   e.flags = (e.flags & ~(S2D_FLAG_BALL_COLLIDED | S2D_FLAG_PLAYER_COLLIDED)) | hit;
+  return hit != 0;
 }
 
 // Player::updateStamina, written with selects instead of nested branches.
@@ -249,8 +251,10 @@ __device__ __forceinline__ void update_stamina(Episode& e, const SP& sp) {
 // applied on receipt, then every object moves, then collisions, then stamina, then the clock.
 // For S2D_CMD_DASH, (dir, rate) come from dash_direction.  TURNS / KICKS say whether the caller can issue those
 // commands at all (compile-time pruning).
+// Outputs (dx, dy) = ball - player after the cycle and d2 = dx*dx + dy*dy, which the scenario's scoring re-uses.
 template <bool TURNS, bool KICKS, class SP>
-__device__ __forceinline__ void simulate_cycle(Episode& e, int cmd, float power, float dir, float rate, const SP& sp) {
+__device__ __forceinline__ void simulate_cycle(Episode& e, int cmd, float power, float dir, float rate, const SP& sp,
+                                               float& dx, float& dy, float& d2) {
   float ax = 0.0f, ay = 0.0f, bax = 0.0f, bay = 0.0f;
   if (KICKS) e.flags &= ~S2D_FLAG_KICKED;
   if (cmd == S2D_CMD_DASH) {
@@ -264,7 +268,14 @@ __device__ __forceinline__ void simulate_cycle(Episode& e, int cmd, float power,
               sp.player_speed_max2(), sp.player_decay());
   move_object(e.bx, e.by, e.bvx, e.bvy, bax, bay, sp.ball_accel_max(), sp.ball_accel_max2(), sp.ball_speed_max(),
               sp.ball_speed_max2(), sp.ball_decay());
-  collide_ball_player(e, sp);
+  dx = e.bx - e.px;
+  dy = e.by - e.py;
+  d2 = dx * dx + dy * dy;
+  if (collide_ball_player(e, d2, sp)) {
+    dx = e.bx - e.px;
+    dy = e.by - e.py;
+    d2 = dx * dx + dy * dy;
+  }
   update_stamina(e, sp);
   e.cycle += 1u;
 }

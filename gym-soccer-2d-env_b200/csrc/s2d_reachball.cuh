@@ -101,11 +101,12 @@ struct LaunchOut {
 // reach_ball_env.py:113-161.  Rewards accumulate and later endings overwrite `result`, in the reference's
 // order Goal -> Out -> Timeout; leaving the pitch ADDS 10 (`reward -= -10.0`, :144).
 // body, mem_ang and atan2's result are already in [-180, 180], so AngleDeg's re-normalisations are identities.
-__device__ __forceinline__ bool check_episode(Episode& e, const KernelParams& P, float& reward, int& result) {
-  const float dx = e.bx - e.px, dy = e.by - e.py;
-  const float dist = hypot2(dx, dy);
+// (dx, dy) = ball - player and d2 = dx*dx + dy*dy as left by simulate_cycle.
+__device__ __forceinline__ bool check_episode(Episode& e, const KernelParams& P, float dx, float dy, float d2,
+                                              float& reward, int& result) {
+  const float dist = sqrtf(d2);
   const float diff = norm_deg_360(atan2_deg(dy, dx) - e.body);
-  float rw = 0.0f + (e.mem_dist - dist);
+  float rw = e.mem_dist - dist;
   rw += (fabsf(e.mem_ang) - fabsf(diff)) * static_cast<float>(1.0 / 180.0);
   const bool goal = dist < P.min_distance_to_ball;
   const bool out = fabsf(e.px) > 52.5f || fabsf(e.py) > 34.0f;
@@ -192,9 +193,18 @@ __device__ __forceinline__ void lane_store_row(float* __restrict__ dst, int64_t 
   for (int j = 0; j < kObsDim / 2; ++j) o[j] = make_float2(row[2 * j], row[2 * j + 1]);
 }
 
+// Soccer2DEnv.reset for one env: placement, the idle cycle, the priming check.
+template <class SP>
+__device__ __forceinline__ void reset_episode(Episode& e, const KernelParams& P, const SP& sp, uint64_t gid) {
+  place_new_episode(e, P, sp, gid);
+  float dx, dy, d2, rw;
+  int rs;
+  simulate_cycle<false, false>(e, S2D_CMD_NONE, 0.0f, 0.0f, 0.0f, sp, dx, dy, d2);
+  check_episode(e, P, dx, dy, d2, rw, rs);  // reach_ball_env.py:166: primes the memory, reward discarded
+}
+
 // ONE env-step = what Soccer2DEnv.step does: decode the action, run the server cycle, score it; when the
-// episode ends, record it and (auto_reset) start the next one, which costs a second, idle pass through the
-// same cycle + check code (placement, one cycle, priming check whose reward is discarded).
+// episode ends, record it and (auto_reset) start the next one (placement, idle cycle, priming check).
 //   discrete:   a0 = snapped dash direction, a1 = its direction rate (both from the action table)
 //   continuous: a0 in [-1, 1]
 //   turning:    [turn_prob, turn_angle, dash_prob, dash_angle] (reach_ball_env.py:65-68)
@@ -220,17 +230,13 @@ __device__ __forceinline__ void substep(Episode& e, const KernelParams& P, const
     dash_direction(da * 180.0f, sp, dir, rate);
     dir = turn_selected ? ta * 180.0f : dir;
   }
-  bool priming = false;
-#pragma unroll 1
-  for (;;) {
-    simulate_cycle<kTurns, false>(e, cmd, power, dir, rate, sp);
-    float rw;
-    int rs;
-    const bool done = check_episode(e, P, rw, rs);
-    if (priming) break;  // reach_ball_env.py:166: the first check after a reset only primes the memory
-    out.reward_sum += rw;
-    e.ep_return += rw;
-    if (!done) break;
+  float dx, dy, d2, rw;
+  int rs;
+  simulate_cycle<kTurns, false>(e, cmd, power, dir, rate, sp, dx, dy, d2);
+  const bool done = check_episode(e, P, dx, dy, d2, rw, rs);
+  out.reward_sum += rw;
+  e.ep_return += rw;
+  if (done) {
     out.count(rs);
     out.ep_steps += static_cast<uint32_t>(e.step_number);
     out.ret += static_cast<double>(e.ep_return);
@@ -239,24 +245,12 @@ __device__ __forceinline__ void substep(Episode& e, const KernelParams& P, const
       build_obs(e, row);
       lane_store_row(P.terminal_obs, i, row);
     }
-    if (!P.auto_reset) {
+    if (P.auto_reset) {
+      reset_episode(e, P, sp, gid);
+    } else {
       e.flags |= S2D_FLAG_DONE;
-      break;
     }
-    place_new_episode(e, P, sp, gid);
-    cmd = S2D_CMD_NONE;
-    priming = true;
   }
-}
-
-// Soccer2DEnv.reset for one env: placement, the idle cycle, the priming check.
-template <class SP>
-__device__ __forceinline__ void reset_episode(Episode& e, const KernelParams& P, const SP& sp, uint64_t gid) {
-  place_new_episode(e, P, sp, gid);
-  simulate_cycle<false, false>(e, S2D_CMD_NONE, 0.0f, 0.0f, 0.0f, sp);
-  float rw;
-  int rs;
-  check_episode(e, P, rw, rs);
 }
 
 #ifndef S2D_HOST_EMU
@@ -320,12 +314,7 @@ __global__ void __launch_bounds__(kBlock, S2D_MIN_BLOCKS) reachball_step_kernel(
                                                                                const int K) {
   using SP = typename std::conditional<DEF, DefaultSP, RuntimeSP>::type;
   const SP sp(P.cc);
-  __shared__ float2 s_table[256];
   __shared__ __align__(16) float s_stage[kBlock / 32][32 * kObsDim];
-  if (ACT == S2D_ACT_DISCRETE) {
-    for (int a = threadIdx.x; a < P.action_space_size; a += kBlock) s_table[a] = P.dash_table[a];
-    __syncthreads();
-  }
   const int64_t i = static_cast<int64_t>(blockIdx.x) * kBlock + threadIdx.x;
   const int64_t n = P.num_envs;
   const bool valid = i < n;
@@ -340,10 +329,12 @@ __global__ void __launch_bounds__(kBlock, S2D_MIN_BLOCKS) reachball_step_kernel(
   if (valid) {
     load_episode(P.state, n, i, e);
     if (ACT == S2D_ACT_DISCRETE) {
+      // the 2 KB action table stays in L1 (read-only path); `act` walks the lane's K action bytes
       const uint8_t* act = static_cast<const uint8_t*>(P.actions) + i * K;
+      const uint8_t* const end = act + K;
 #pragma unroll 1
-      for (int k = 0; k < K; ++k) {
-        const float2 t = s_table[__ldg(act + k)];
+      for (; act != end; ++act) {
+        const float2 t = __ldg(P.dash_table + __ldg(act));
         substep<ACT>(e, P, sp, gid, i, t.x, t.y, 0.f, 0.f, out);
       }
     } else if (ACT == S2D_ACT_CONTINUOUS) {

@@ -129,6 +129,7 @@ def time_cpu_oracle(envs, k, min_seconds, max_launches=10**9, warmup=1, fixed_la
                         min_distance_to_ball=SCENARIO_KW["min_distance_to_ball"],
                         action_space_size=SCENARIO_KW["action_space_size"])
     sim = OL.OracleSim(cfg, "f64")
+    OL.lib("f64").s2do_set_threads(host_threads())
     sim.reset()
     rng = np.random.default_rng(0)
     pool = [H.random_actions(rng, "discrete", envs, k) for _ in range(4)]
@@ -276,6 +277,19 @@ def run_b200(args, rank, local_rank, world):
     k1_launch_ms = sum(ms1) / len(ms1)
     k1_value = world * n1 * k1_steps / (k1_total_ms * 1e-3)
     env1.close()
+    del env1, pool1
+
+    # ---- closed-loop policy rollout (configs[4]): obs -> 64-64 MLP -> argmax -> step, all on the device ----
+    from soccer2d_b200.rollout import QNetwork, measure_rollout
+    rollout = {}
+    for nr in (1 << 16, 1 << 20):
+        envr = Soccer2DVecEnv(nr, device=dev, seed=0, substeps=1, env_id_offset=rank * nr, **SCENARIO_KW)
+        envr.reset_torch()
+        torch.manual_seed(0)
+        qnet = QNetwork(envr.obs_dim, 16).to(dev)
+        rollout[str(nr)] = measure_rollout(envr, qnet, steps=max(10, min(args.steps, 50)))
+        envr.close()
+        del envr
     clocks = sampler.summary()
 
     if rank != 0:
@@ -316,6 +330,9 @@ def run_b200(args, rank, local_rank, world):
                         "kernel": "reachball_step_kernel<DISCRETE>", "launch_ms": k1_launch_ms, "envs_per_gpu": n1,
                         "substeps": 1, "algorithmic_bytes_per_launch": bytes1, "env_steps_per_sec": k1_value,
                         "peak_source": peak_src},
+        "rollout_dqn": {"unit": UNIT + " per GPU", "policy": "64-64 ReLU MLP (SB3 DQN MlpPolicy shape), greedy, K=1, zero-copy "
+                        "obs/action tensors (torch fp32 matmuls for the policy, not part of the step path)",
+                        "envs_to_value": rollout},
         "clocks": clocks,
         "episode_stats": stats,
     }

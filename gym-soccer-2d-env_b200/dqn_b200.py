@@ -1,0 +1,45 @@
+#!/usr/bin/env python
+"""DQN on ReachBall with the lockstep GPU simulator - the counterpart of the reference's
+dqn_stable_baselines3.py (:17-31 env kwargs, :36-41 train loop, :44-62 test), with the rollout, the replay
+buffer and the learner all on the device (soccer2d_b200.rollout).
+
+    python gym-soccer-2d-env_b200/dqn_b200.py --envs 4096 --steps 3000
+"""
+import argparse
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
+from soccer2d_b200 import Soccer2DVecEnv  # noqa: E402
+from soccer2d_b200.rollout import DeviceDQN, DQNConfig  # noqa: E402
+
+# dqn_stable_baselines3.py:17-31
+KWARGS = dict(change_ball_position=True, change_ball_velocity=True, ball_position_x=0, ball_position_y=0, ball_speed=0,
+              ball_direction=0, min_distance_to_ball=5.0, max_steps=200, use_continuous_action=False, action_space_size=16,
+              use_turning=False)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--envs", type=int, default=4096)
+    ap.add_argument("--steps", type=int, default=3000, help="lockstep steps (x envs transitions)")
+    ap.add_argument("--test-steps", type=int, default=400)
+    ap.add_argument("--report-every", type=int, default=250)
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--device", default="cuda:0")
+    args = ap.parse_args()
+
+    env = Soccer2DVecEnv(args.envs, device=args.device, seed=args.seed, terminal_obs=True, **KWARGS)
+    agent = DeviceDQN(env, DQNConfig(seed=args.seed, learning_starts=min(1 << 16, 16 * args.envs)))
+    baseline = agent.evaluate(0)  # noqa: F841
+    for rep in agent.learn(args.steps, report_every=args.report_every):
+        print(json.dumps(rep), flush=True)
+    print(json.dumps({"test": agent.evaluate(args.test_steps)}), flush=True)
+    env.close()
+    env.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,204 @@
+"""Device-resident DQN rollout on Soccer2DVecEnv - the caller side of the step path (BASELINE configs[4]).
+
+The reference trains with Stable-Baselines3 (`DQN("MlpPolicy", env)`, dqn_stable_baselines3.py:36-41): one env,
+numpy observations, a numpy replay buffer and Python `infos` dicts per step.  With 10^4..10^6 lockstep envs that
+plumbing is the bottleneck, so this module keeps the whole loop on the GPU:
+
+  obs (the tensor the step kernel writes) -> Q-network -> epsilon-greedy argmax written straight into the env's
+  action tensor -> s2d_step -> (reward, done, terminal obs) -> ring replay buffer in HBM -> TD update.
+
+No host copies, no per-env Python objects; episode outcomes (Goal / Out / Timeout, what InfoCollectorCallback
+tallies, utils/info_collector_callback.py:37-53) come from the kernel's statistics counters.
+SB3 is not installed in this image; the network shape (64-64 ReLU MLP), the Huber TD loss, the target network
+and the epsilon schedule follow SB3's DQN defaults.
+"""
+from __future__ import annotations
+
+import time
+from dataclasses import dataclass, field
+
+import torch
+from torch import nn
+
+
+class QNetwork(nn.Module):
+    """SB3 DQN "MlpPolicy": obs -> 64 -> 64 -> n_actions, ReLU."""
+
+    def __init__(self, obs_dim: int, n_actions: int, hidden: int = 64):
+        super().__init__()
+        self.net = nn.Sequential(nn.Linear(obs_dim, hidden), nn.ReLU(), nn.Linear(hidden, hidden), nn.ReLU(),
+                                 nn.Linear(hidden, n_actions))
+
+    def forward(self, obs: torch.Tensor) -> torch.Tensor:
+        return self.net(obs)
+
+
+class DeviceReplayBuffer:
+    """Ring buffer of transitions in GPU memory; whole batches of N envs are appended per step."""
+
+    def __init__(self, capacity: int, obs_dim: int, device):
+        self.capacity, self.device = int(capacity), device
+        self.obs = torch.empty((capacity, obs_dim), dtype=torch.float32, device=device)
+        self.next_obs = torch.empty((capacity, obs_dim), dtype=torch.float32, device=device)
+        self.action = torch.empty(capacity, dtype=torch.uint8, device=device)
+        self.reward = torch.empty(capacity, dtype=torch.float32, device=device)
+        self.done = torch.empty(capacity, dtype=torch.bool, device=device)
+        self.pos, self.size = 0, 0
+
+    def add_batch(self, obs, action, reward, next_obs, done):
+        n = obs.shape[0]
+        if n >= self.capacity:  # keep the newest `capacity` rows
+            sl = slice(n - self.capacity, n)
+            self.obs.copy_(obs[sl]); self.next_obs.copy_(next_obs[sl]); self.action.copy_(action[sl])
+            self.reward.copy_(reward[sl]); self.done.copy_(done[sl])
+            self.pos, self.size = 0, self.capacity
+            return
+        first = min(n, self.capacity - self.pos)
+        for dst, src in ((self.obs, obs), (self.next_obs, next_obs), (self.action, action), (self.reward, reward),
+                         (self.done, done)):
+            dst[self.pos:self.pos + first].copy_(src[:first])
+            if first < n:
+                dst[:n - first].copy_(src[first:])
+        self.pos = (self.pos + n) % self.capacity
+        self.size = min(self.capacity, self.size + n)
+
+    def sample(self, batch: int, generator=None):
+        idx = torch.randint(0, self.size, (batch,), device=self.device, generator=generator)
+        return self.obs[idx], self.action[idx].long(), self.reward[idx], self.next_obs[idx], self.done[idx]
+
+
+@dataclass
+class DQNConfig:
+    gamma: float = 0.99
+    lr: float = 1e-4                 # SB3 DQN default
+    batch_size: int = 4096
+    buffer_size: int = 1 << 21
+    learning_starts: int = 1 << 16   # transitions
+    train_every: int = 1             # env steps (of all N envs) between gradient steps
+    gradient_steps: int = 1
+    target_update_every: int = 250   # gradient steps
+    eps_start: float = 1.0
+    eps_end: float = 0.05
+    eps_fraction: float = 0.3        # of total steps (SB3: exploration_fraction... 0.1; larger for short runs)
+    seed: int = 0
+    log: list = field(default_factory=list)
+
+
+class DeviceDQN:
+    """DQN whose rollout never leaves the GPU.  `env` must be a Discrete-action Soccer2DVecEnv with substeps=1,
+    auto_reset=True and terminal_obs=True."""
+
+    def __init__(self, env, cfg: DQNConfig | None = None):
+        assert env.substeps == 1 and env.auto_reset and env.terminal_obs is not None
+        assert env.actions.dtype == torch.uint8, "Discrete action space required"
+        self.env, self.cfg, self.device = env, cfg or DQNConfig(), env.device
+        torch.manual_seed(self.cfg.seed)
+        self.n_actions = env.action_space.n
+        self.q = QNetwork(env.obs_dim, self.n_actions).to(self.device)
+        self.q_target = QNetwork(env.obs_dim, self.n_actions).to(self.device)
+        self.q_target.load_state_dict(self.q.state_dict())
+        self.opt = torch.optim.Adam(self.q.parameters(), lr=self.cfg.lr)
+        self.buffer = DeviceReplayBuffer(self.cfg.buffer_size, env.obs_dim, self.device)
+        self.gen = torch.Generator(device=self.device).manual_seed(self.cfg.seed)
+        self.env_steps = 0       # lockstep steps taken (each = num_envs transitions)
+        self.grad_steps = 0
+        self._obs = env.reset_torch().clone()
+
+    # -- acting ----------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def act(self, obs: torch.Tensor, epsilon: float) -> torch.Tensor:
+        greedy = self.q(obs).argmax(dim=1)
+        if epsilon <= 0.0:
+            return greedy.to(torch.uint8)
+        n = obs.shape[0]
+        explore = torch.rand(n, device=self.device, generator=self.gen) < epsilon
+        rand_a = torch.randint(0, self.n_actions, (n,), device=self.device, generator=self.gen)
+        return torch.where(explore, rand_a, greedy).to(torch.uint8)
+
+    @torch.no_grad()
+    def rollout_step(self, epsilon: float, store: bool = True):
+        """One lockstep step of all envs; the action tensor is written in place (zero copy)."""
+        env = self.env
+        a = self.act(self._obs, epsilon)
+        env.actions.view(-1).copy_(a)
+        obs, reward, done, _ = env.step_torch()
+        if store:
+            next_obs = torch.where(done.unsqueeze(1), env.terminal_obs, obs)  # finished envs already show their new episode
+            self.buffer.add_batch(self._obs, a, reward, next_obs, done)
+        self._obs.copy_(obs)
+        self.env_steps += 1
+
+    # -- learning --------------------------------------------------------------------------------------
+    def train_step(self):
+        c = self.cfg
+        obs, act, rew, nxt, done = self.buffer.sample(c.batch_size, self.gen)
+        with torch.no_grad():
+            target = rew + c.gamma * (~done).float() * self.q_target(nxt).max(dim=1).values
+        qsa = self.q(obs).gather(1, act.unsqueeze(1)).squeeze(1)
+        loss = nn.functional.smooth_l1_loss(qsa, target)
+        self.opt.zero_grad(set_to_none=True)
+        loss.backward()
+        nn.utils.clip_grad_norm_(self.q.parameters(), 10.0)  # SB3 max_grad_norm
+        self.opt.step()
+        self.grad_steps += 1
+        if self.grad_steps % c.target_update_every == 0:
+            self.q_target.load_state_dict(self.q.state_dict())
+        return loss
+
+    def epsilon(self, total_steps: int) -> float:
+        c = self.cfg
+        frac = min(1.0, self.env_steps / max(1.0, c.eps_fraction * total_steps))
+        return c.eps_start + frac * (c.eps_end - c.eps_start)
+
+    def learn(self, total_steps: int, report_every: int = 0):
+        """`total_steps` lockstep steps (x num_envs transitions).  Returns the list of report dicts: per interval
+        the outcome counts of the finished episodes, like InfoCollectorCallback's per-100-episodes print."""
+        c, env = self.cfg, self.env
+        last = env.stats()
+        t0 = time.perf_counter()
+        for step in range(1, total_steps + 1):
+            self.rollout_step(self.epsilon(total_steps))
+            if self.buffer.size >= c.learning_starts and step % c.train_every == 0:
+                for _ in range(c.gradient_steps):
+                    self.train_step()
+            if report_every and step % report_every == 0:
+                now = env.stats()
+                d = {k: now[k] - last[k] for k in ("episodes", "goals", "outs", "timeouts", "episode_steps", "return_sum")}
+                last = now
+                ep = max(1, d["episodes"])
+                rep = {"step": step, "transitions": step * env.num_envs, "epsilon": round(self.epsilon(total_steps), 3),
+                       "episodes": d["episodes"], "goal_rate": d["goals"] / ep, "out_rate": d["outs"] / ep,
+                       "timeout_rate": d["timeouts"] / ep, "mean_return": d["return_sum"] / ep,
+                       "mean_length": d["episode_steps"] / ep, "wall_s": round(time.perf_counter() - t0, 2)}
+                c.log.append(rep)
+        return c.log
+
+    @torch.no_grad()
+    def evaluate(self, steps: int) -> dict:
+        """Greedy rollout (the reference's `test()`, dqn_ddpg_stable_baselines3.py:56-75): outcome rates."""
+        before = self.env.stats()
+        for _ in range(steps):
+            self.rollout_step(0.0, store=False)
+        after = self.env.stats()
+        d = {k: after[k] - before[k] for k in ("episodes", "goals", "outs", "timeouts", "return_sum")}
+        ep = max(1, d["episodes"])
+        return {"episodes": d["episodes"], "goal_rate": d["goals"] / ep, "out_rate": d["outs"] / ep,
+                "timeout_rate": d["timeouts"] / ep, "mean_return": d["return_sum"] / ep}
+
+
+@torch.no_grad()
+def measure_rollout(env, qnet: nn.Module, steps: int, warmup: int = 5) -> float:
+    """env-steps/s of the closed loop obs -> Q-net -> argmax -> step (no learning), timed with CUDA events."""
+    def one():
+        a = qnet(env.obs).argmax(dim=1).to(torch.uint8)
+        env.actions.view(-1).copy_(a)
+        env.step_torch()
+    for _ in range(warmup):
+        one()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(steps):
+        one()
+    e.record()
+    torch.cuda.synchronize()
+    return env.num_envs * steps / (s.elapsed_time(e) * 1e-3)

@@ -29,6 +29,8 @@ def lib(kind: str):
         L.s2do_create.restype = C.c_int
         L.s2do_create.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
         L.s2do_destroy.argtypes = [C.c_void_p]
+        L.s2do_set_threads.restype = C.c_int
+        L.s2do_set_threads.argtypes = [C.c_int]
         L.s2do_reset.argtypes = [C.c_void_p, C.c_void_p]
         L.s2do_reset_masked.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.s2do_step.argtypes = [C.c_void_p] + [C.c_void_p, C.c_int] + [C.c_void_p] * 5

@@ -18,7 +18,7 @@ struct S2DSim {
   S2DConfig cfg;
   S2DBuffers buf;
   KernelParams kp;
-  float2* d_table = nullptr;
+  float4* d_table = nullptr;
   bool default_sp = false;  // cfg.sp == rcssserver defaults: use the constant-folded kernels
   bool bound = false;
   int grid = 0;
@@ -93,6 +93,11 @@ int s2d_default_config(S2DConfig* c, int scenario) {
   c->change_ball_velocity = 0;          // :27
   c->players_per_side = scenario == S2D_SCENARIO_FULLGAME ? 11 : 1;
   c->half_time_cycles = 3000;
+  if (scenario == S2D_SCENARIO_SHOOT) {  // Discrete(24) = 16 dashes + 8 kicks
+    c->action_mode = S2D_ACT_DISCRETE;
+    c->action_space_size = 24;
+    c->kick_actions = 8;
+  }
   c->min_distance_to_ball = 5.0f;       // :32
   c->goto_dist_thr = 0.5f;
   return s2d_default_server_param(&c->sp);
@@ -105,13 +110,24 @@ static bool config_ok(const S2DConfig* c, char* why, size_t n) {
     return false;
   }
   if (c->num_envs < 1) { snprintf(why, n, "num_envs must be >= 1"); return false; }
-  if (c->scenario != S2D_SCENARIO_REACHBALL) { snprintf(why, n, "scenario %d is not available in this build", c->scenario); return false; }
-  if (c->action_mode < S2D_ACT_DISCRETE || c->action_mode > S2D_ACT_TURNING) {
-    snprintf(why, n, "action_mode %d is not valid for this scenario", c->action_mode);
+  if (c->scenario != S2D_SCENARIO_REACHBALL && c->scenario != S2D_SCENARIO_SHOOT) {
+    snprintf(why, n, "scenario %d is not available in this build", c->scenario);
+    return false;
+  }
+  const bool mode_ok = c->scenario == S2D_SCENARIO_SHOOT
+                           ? (c->action_mode == S2D_ACT_DISCRETE || c->action_mode == S2D_ACT_COMMAND)
+                           : (c->action_mode >= S2D_ACT_DISCRETE && c->action_mode <= S2D_ACT_COMMAND);
+  if (!mode_ok) {
+    snprintf(why, n, "action_mode %d is not valid for scenario %d", c->action_mode, c->scenario);
     return false;
   }
   if (c->action_mode == S2D_ACT_DISCRETE && (c->action_space_size < 1 || c->action_space_size > 256)) {
     snprintf(why, n, "action_space_size must be in 1..256");
+    return false;
+  }
+  if (c->scenario == S2D_SCENARIO_SHOOT && c->action_mode == S2D_ACT_DISCRETE &&
+      (c->kick_actions < 1 || c->kick_actions >= c->action_space_size)) {
+    snprintf(why, n, "SHOOT Discrete(n) needs 1 <= kick_actions < action_space_size");
     return false;
   }
   if (c->max_steps < 0) { snprintf(why, n, "max_steps must be >= 0"); return false; }
@@ -156,7 +172,7 @@ int s2d_create(const S2DConfig* cfg, S2DHandle* out) {
   DeviceGuard guard(cfg->device);
 
   KernelParams& kp = h->kp;
-  float2 table[256];
+  float4 table[256];
   make_kernel_params(*cfg, kp, table);
   h->default_sp = is_default_server_param(cfg->sp);
   cudaError_t e = cudaMalloc(&h->d_table, sizeof(table));
@@ -167,7 +183,7 @@ int s2d_create(const S2DConfig* cfg, S2DHandle* out) {
     delete h;
     return S2D_ERR_CUDA;
   }
-  kp.dash_table = h->d_table;
+  kp.action_table = h->d_table;
   h->grid = static_cast<int>((cfg->num_envs + kBlock - 1) / kBlock);
   *out = h;
   return S2D_OK;
@@ -208,7 +224,10 @@ int s2d_reset(S2DHandle h, const uint8_t* device_mask_or_null, void* stream) {
   if (!h) return S2D_ERR_INVALID;
   if (!h->bound) return fail(h, S2D_ERR_UNBOUND, "s2d_bind has not been called");
   DeviceGuard guard(h->cfg.device);
-  reachball_reset_kernel<<<h->grid, kBlock, 0, static_cast<cudaStream_t>(stream)>>>(h->kp, device_mask_or_null);
+  if (h->cfg.scenario == S2D_SCENARIO_SHOOT)
+    reset_kernel<S2D_SCENARIO_SHOOT><<<h->grid, kBlock, 0, static_cast<cudaStream_t>(stream)>>>(h->kp, device_mask_or_null);
+  else
+    reset_kernel<S2D_SCENARIO_REACHBALL><<<h->grid, kBlock, 0, static_cast<cudaStream_t>(stream)>>>(h->kp, device_mask_or_null);
   S2D_CUDA(h, cudaGetLastError());
   return S2D_OK;
 }
@@ -220,15 +239,21 @@ int s2d_step(S2DHandle h, int k_substeps, void* stream) {
     return fail(h, S2D_ERR_INVALID, "k_substeps must be in 1..%d", kMaxSubsteps);
   DeviceGuard guard(h->cfg.device);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-#define S2D_LAUNCH(ACT)                                                                              \
-  do {                                                                                               \
-    if (h->default_sp) reachball_step_kernel<ACT, true><<<h->grid, kBlock, 0, s>>>(h->kp, k_substeps); \
-    else reachball_step_kernel<ACT, false><<<h->grid, kBlock, 0, s>>>(h->kp, k_substeps);            \
+#define S2D_LAUNCH(SCN, ACT)                                                                        \
+  do {                                                                                              \
+    if (h->default_sp) step_kernel<SCN, ACT, true><<<h->grid, kBlock, 0, s>>>(h->kp, k_substeps);   \
+    else step_kernel<SCN, ACT, false><<<h->grid, kBlock, 0, s>>>(h->kp, k_substeps);                \
   } while (0)
-  switch (h->cfg.action_mode) {
-    case S2D_ACT_DISCRETE: S2D_LAUNCH(S2D_ACT_DISCRETE); break;
-    case S2D_ACT_CONTINUOUS: S2D_LAUNCH(S2D_ACT_CONTINUOUS); break;
-    default: S2D_LAUNCH(S2D_ACT_TURNING); break;
+  if (h->cfg.scenario == S2D_SCENARIO_SHOOT) {
+    if (h->cfg.action_mode == S2D_ACT_DISCRETE) S2D_LAUNCH(S2D_SCENARIO_SHOOT, S2D_ACT_DISCRETE);
+    else S2D_LAUNCH(S2D_SCENARIO_SHOOT, S2D_ACT_COMMAND);
+  } else {
+    switch (h->cfg.action_mode) {
+      case S2D_ACT_DISCRETE: S2D_LAUNCH(S2D_SCENARIO_REACHBALL, S2D_ACT_DISCRETE); break;
+      case S2D_ACT_CONTINUOUS: S2D_LAUNCH(S2D_SCENARIO_REACHBALL, S2D_ACT_CONTINUOUS); break;
+      case S2D_ACT_TURNING: S2D_LAUNCH(S2D_SCENARIO_REACHBALL, S2D_ACT_TURNING); break;
+      default: S2D_LAUNCH(S2D_SCENARIO_REACHBALL, S2D_ACT_COMMAND); break;
+    }
   }
 #undef S2D_LAUNCH
   S2D_CUDA(h, cudaGetLastError());

@@ -133,6 +133,58 @@ __device__ __forceinline__ bool kick(Episode& e, float power, float dir, const S
   return true;
 }
 
+// Body_GoToPoint (idl/service.proto:684-688) as the proxy lowers it to ONE server command (simplified librcsc
+// rule): inside dist_thr -> nothing; facing error above max(15 deg, asin(dist_thr / dist)) -> turn towards the
+// target, compensating inertia; else dash straight with the power that reaches the target this cycle.
+template <class SP>
+__device__ __forceinline__ void lower_goto(const Episode& e, float tx, float ty, float dist_thr, float max_power,
+                                           const SP& sp, int& cmd, float& power, float& dir) {
+  const float dx = tx - e.px, dy = ty - e.py;
+  const float dist = hypot2(dx, dy);
+  cmd = S2D_CMD_NONE;
+  power = 0.0f;
+  dir = 0.0f;
+  if (dist < dist_thr) return;
+  const float ang = norm_deg_360(atan2_deg(dy, dx) - e.body);
+  const float ratio = dist_thr / dist;
+  const float athr = fmax_(15.0f, atan2_deg(ratio, sqrtf(fmax_(0.0f, 1.0f - ratio * ratio))));
+  if (fabsf(ang) > athr) {
+    const float speed = hypot2(e.vx, e.vy);
+    cmd = S2D_CMD_TURN;
+    dir = clampf(sp.min_moment(), ang * (1.0f + sp.inertia_moment() * speed), sp.max_moment());
+    return;
+  }
+  float sn, cs;
+  sincos_deg(e.body, sn, cs);
+  const float v_along = e.vx * cs + e.vy * sn;
+  const float need = (dist - v_along) / (e.effort * sp.dash_power_rate());
+  cmd = S2D_CMD_DASH;
+  power = clampf(0.0f, need, max_power);
+}
+
+// S2D_ACT_COMMAND: {cmd, a, b, c} = proto PlayerAction dash / turn / kick / body_go_to_point (S2D_CMD_*).
+// Dashes come out with the direction already lowered by dash_direction.
+template <class SP>
+__device__ __forceinline__ void decode_command(const Episode& e, float4 a, float goto_dist_thr, const SP& sp, int& cmd,
+                                               float& power, float& dir, float& rate) {
+  const int c = static_cast<int>(a.x);
+  cmd = S2D_CMD_NONE;
+  power = 0.0f;
+  dir = 0.0f;
+  rate = 0.0f;
+  if (c == S2D_CMD_DASH || c == S2D_CMD_KICK) {
+    cmd = c;
+    power = a.y;
+    dir = a.z;
+  } else if (c == S2D_CMD_TURN) {
+    cmd = c;
+    dir = a.y;
+  } else if (c == S2D_CMD_GOTO) {
+    lower_goto(e, a.y, a.z, goto_dist_thr, a.w, sp, cmd, power, dir);
+  }
+  if (cmd == S2D_CMD_DASH) dash_direction(dir, sp, dir, rate);
+}
+
 // ---- one cycle ------------------------------------------------------------------------------------
 
 // MPObject::_inc.  The two clamps compare SQUARED lengths (no square root unless a clamp applies).

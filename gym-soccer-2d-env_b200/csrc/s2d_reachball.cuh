@@ -40,14 +40,15 @@ struct KernelParams {
   uint8_t* result;
   float* terminal_obs;
   unsigned long long* stats;  // [kStatSlots][kStatWords]
-  const float2* dash_table;   // [256] Discrete(n) -> {snapped dash direction, direction rate}, built on the host
+  int32_t kick_actions;       // SHOOT Discrete(n): the last kick_actions actions are kicks
+  const float4* action_table; // [256] Discrete(n) -> {cmd, power, lowered direction, dash direction rate}, built on the host
 };
 
-// Fills everything but the buffer pointers from a config.  `table` receives, per Discrete(n) action, the Dash
-// direction of reach_ball_env.py:84 (evaluated as the reference does: double, then the proto float) already
-// lowered by dash_direction (clamp, dash_angle_step snap, direction rate) - the part of Player::dash that does
-// not depend on the episode.
-inline void make_kernel_params(const S2DConfig& cfg, KernelParams& kp, float2 table[256]) {
+// Fills everything but the buffer pointers from a config.  `table` receives, per Discrete(n) action, the command
+// it stands for: Dash(100, dir) with the direction of reach_ball_env.py:84 (evaluated as the reference does: double,
+// then the proto float) already lowered by dash_direction (clamp, dash_angle_step snap, direction rate - the part
+// of Player::dash that does not depend on the episode); in SHOOT the last kick_actions entries are Kick(100, dir).
+inline void make_kernel_params(const S2DConfig& cfg, KernelParams& kp, float4 table[256]) {
   memset(&kp, 0, sizeof(kp));
   kp.cc = make_cycle_consts(cfg.sp);
   kp.num_envs = cfg.num_envs;
@@ -69,11 +70,20 @@ inline void make_kernel_params(const S2DConfig& cfg, KernelParams& kp, float2 ta
   kp.goto_dist_thr = cfg.goto_dist_thr;
   // reach_ball_env.py:207 - the reference uses 0.96 here, not the server's ball_decay
   kp.travel_factor = static_cast<float>((1.0 - pow(0.96, static_cast<double>(cfg.max_steps))) / (1.0 - 0.96));
-  const int n = cfg.action_space_size;
+  kp.kick_actions = cfg.scenario == S2D_SCENARIO_SHOOT ? cfg.kick_actions : 0;
+  const int n_dash = cfg.action_space_size - kp.kick_actions;
   const RuntimeSP sp(kp.cc);
+  auto direction = [](int a, int n) {
+    return n > 0 ? static_cast<float>(fmod(static_cast<double>(a) * 360.0 / static_cast<double>(n), 360.0) - 180.0) : 0.0f;
+  };
   for (int a = 0; a < 256; ++a) {
-    const float dir = n > 0 ? static_cast<float>(fmod(static_cast<double>(a) * 360.0 / static_cast<double>(n), 360.0) - 180.0) : 0.0f;
-    dash_direction(dir, sp, table[a].x, table[a].y);
+    if (a < n_dash || kp.kick_actions == 0) {
+      table[a].x = static_cast<float>(S2D_CMD_DASH);
+      table[a].y = 100.0f;
+      dash_direction(direction(a, n_dash), sp, table[a].z, table[a].w);
+    } else {
+      table[a] = make_float4(static_cast<float>(S2D_CMD_KICK), 100.0f, direction(a - n_dash, kp.kick_actions), 0.0f);
+    }
   }
 }
 
@@ -138,6 +148,54 @@ __device__ __forceinline__ void build_obs(const Episode& e, float* o) {
   o[9] = e.bvy * static_cast<float>(1.0 / 3.0);
 }
 
+// ---- SHOOT (spec: include/soccer2d.h) ---------------------------------------------------------------
+// (pbx, pby) = ball position before this cycle's move.  The reward memory holds the player-ball distance
+// (mem_dist) and the ball-goal distance (mem_ang slot).
+template <class SP>
+__device__ __forceinline__ bool check_shoot(Episode& e, const KernelParams& P, const SP& sp, float d2, float pbx,
+                                            float pby, float& reward, int& result) {
+  const float d_pb = sqrtf(d2);
+  const float d_bg = hypot2(sp.pitch_half_length() - e.bx, 0.0f - e.by);
+  float rw = (e.mem_dist - d_pb) * 0.2f + (e.mem_ang - d_bg);
+  const float line = sp.pitch_half_length() + sp.ball_size();
+  const float post = sp.goal_width() * 0.5f + sp.goal_post_radius();
+  bool goal = false;
+  if (e.bx > line && !(pbx > line)) {
+    const float yc = pby + (e.by - pby) * ((line - pbx) / (e.bx - pbx));
+    goal = fabsf(yc) <= post;
+  }
+  const bool out = !goal && (fabsf(e.bx) > line || fabsf(e.by) > sp.pitch_half_width() + sp.ball_size());
+  const bool timeout = !goal && !out && e.step_number > P.max_steps;
+  rw = goal ? rw + 10.0f : rw;
+  rw = out ? rw - 10.0f : rw;
+  rw = timeout ? rw - 5.0f : rw;
+  result = goal ? S2D_RESULT_GOAL : out ? S2D_RESULT_OUT : timeout ? S2D_RESULT_TIMEOUT : S2D_RESULT_NONE;
+  reward = rw;
+  e.mem_dist = d_pb;
+  e.mem_ang = d_bg;
+  return goal || out || timeout;
+}
+
+// same 10 values as ReachBall; the body-to-ball angle is computed here (the memory slot holds a distance)
+__device__ __forceinline__ void build_obs_shoot(const Episode& e, float* o) {
+  Episode t = e;
+  t.mem_ang = norm_deg_360(atan2_deg(e.by - e.py, e.bx - e.px) - e.body);
+  build_obs(t, o);
+}
+
+template <int SCN>
+__device__ __forceinline__ void scenario_obs(const Episode& e, float* o) {
+  if (SCN == S2D_SCENARIO_SHOOT) build_obs_shoot(e, o);
+  else build_obs(e, o);
+}
+
+template <int SCN, class SP>
+__device__ __forceinline__ bool scenario_check(Episode& e, const KernelParams& P, const SP& sp, float dx, float dy,
+                                               float d2, float pbx, float pby, float& reward, int& result) {
+  if (SCN == S2D_SCENARIO_SHOOT) return check_shoot(e, P, sp, d2, pbx, pby, reward, result);
+  return check_episode(e, P, dx, dy, d2, reward, result);
+}
+
 // trainer_reset_actions' draws (integers: x in [-50,50], y in [-30,30], body in [0,360]; ball velocity by
 // bounded rejection: the ball must stay on the pitch for max_steps cycles), then DoMoveBall / DoMovePlayer
 // (vel = 0) / DoRecover.  The caller still owes the episode ONE idle server cycle and the priming check
@@ -194,33 +252,40 @@ __device__ __forceinline__ void lane_store_row(float* __restrict__ dst, int64_t 
 }
 
 // Soccer2DEnv.reset for one env: placement, the idle cycle, the priming check.
-template <class SP>
+template <int SCN, class SP>
 __device__ __forceinline__ void reset_episode(Episode& e, const KernelParams& P, const SP& sp, uint64_t gid) {
   place_new_episode(e, P, sp, gid);
   float dx, dy, d2, rw;
   int rs;
+  const float pbx = e.bx, pby = e.by;
   simulate_cycle<false, false>(e, S2D_CMD_NONE, 0.0f, 0.0f, 0.0f, sp, dx, dy, d2);
-  check_episode(e, P, dx, dy, d2, rw, rs);  // reach_ball_env.py:166: primes the memory, reward discarded
+  scenario_check<SCN>(e, P, sp, dx, dy, d2, pbx, pby, rw, rs);  // reach_ball_env.py:166: primes the memory, reward discarded
 }
 
 // ONE env-step = what Soccer2DEnv.step does: decode the action, run the server cycle, score it; when the
 // episode ends, record it and (auto_reset) start the next one (placement, idle cycle, priming check).
-//   discrete:   a0 = snapped dash direction, a1 = its direction rate (both from the action table)
-//   continuous: a0 in [-1, 1]
-//   turning:    [turn_prob, turn_angle, dash_prob, dash_angle] (reach_ball_env.py:65-68)
-template <int ACT, class SP>
+//   discrete:   (a0..a3) = the action's table entry {cmd, power, lowered direction, dash rate}
+//   continuous: a0 in [-1, 1]                                                    (ReachBall)
+//   turning:    [turn_prob, turn_angle, dash_prob, dash_angle], :65-68           (ReachBall)
+//   command:    {cmd, a, b, c} = proto PlayerAction dash / turn / kick / body_go_to_point
+template <int SCN, int ACT, class SP>
 __device__ __forceinline__ void substep(Episode& e, const KernelParams& P, const SP& sp, uint64_t gid, int64_t i, float a0,
                                         float a1, float a2, float a3, LaunchOut& out) {
-  constexpr bool kTurns = ACT == S2D_ACT_TURNING;
+  constexpr bool kTurns = ACT == S2D_ACT_TURNING || ACT == S2D_ACT_COMMAND;
+  constexpr bool kKicks = ACT == S2D_ACT_COMMAND || SCN == S2D_SCENARIO_SHOOT;
   e.step_number += 1;  // reach_ball_env.py:55
   int cmd = S2D_CMD_DASH;
   float power = 100.0f, dir, rate;
   if (ACT == S2D_ACT_DISCRETE) {
-    dir = a0;
-    rate = a1;
+    if (SCN == S2D_SCENARIO_SHOOT) {
+      cmd = static_cast<int>(a0);
+      power = a1;
+    }
+    dir = a2;
+    rate = a3;
   } else if (ACT == S2D_ACT_CONTINUOUS) {
     dash_direction(a0 * 180.0f, sp, dir, rate);
-  } else {
+  } else if (ACT == S2D_ACT_TURNING) {
     const float tp = clampf(-1.0f, a0, 1.0f), ta = clampf(-1.0f, a1, 1.0f);
     const float dp = clampf(-1.0f, a2, 1.0f), da = clampf(-1.0f, a3, 1.0f);
     const float u = u32_to_unit(philox4x32_10(P.seed, gid, e.cycle, RNG_ACTION, 0).x);
@@ -229,11 +294,14 @@ __device__ __forceinline__ void substep(Episode& e, const KernelParams& P, const
     power = turn_selected ? 0.0f : 100.0f;
     dash_direction(da * 180.0f, sp, dir, rate);
     dir = turn_selected ? ta * 180.0f : dir;
+  } else {
+    decode_command(e, make_float4(a0, a1, a2, a3), P.goto_dist_thr, sp, cmd, power, dir, rate);
   }
   float dx, dy, d2, rw;
   int rs;
-  simulate_cycle<kTurns, false>(e, cmd, power, dir, rate, sp, dx, dy, d2);
-  const bool done = check_episode(e, P, dx, dy, d2, rw, rs);
+  const float pbx = e.bx, pby = e.by;
+  simulate_cycle<kTurns, kKicks>(e, cmd, power, dir, rate, sp, dx, dy, d2);
+  const bool done = scenario_check<SCN>(e, P, sp, dx, dy, d2, pbx, pby, rw, rs);
   out.reward_sum += rw;
   e.ep_return += rw;
   if (done) {
@@ -242,11 +310,11 @@ __device__ __forceinline__ void substep(Episode& e, const KernelParams& P, const
     out.ret += static_cast<double>(e.ep_return);
     if (P.terminal_obs) {
       float row[kObsDim];
-      build_obs(e, row);
+      scenario_obs<SCN>(e, row);
       lane_store_row(P.terminal_obs, i, row);
     }
     if (P.auto_reset) {
-      reset_episode(e, P, sp, gid);
+      reset_episode<SCN>(e, P, sp, gid);
     } else {
       e.flags |= S2D_FLAG_DONE;
     }
@@ -308,10 +376,9 @@ constexpr int kBlock = S2D_BLOCK;
 // K lockstep cycles of every env in one launch; state stays in registers in between.
 // actions[N][K] (uint8 / float) or [N][K][4] (float): a lane's K actions are contiguous in memory; the first
 // access pulls the lane's sector(s) into L1 and the following cycles hit there (ld.global.nc).
-// DEF: the constants are the default ServerParam, folded at compile time (DefaultSP).
-template <int ACT, bool DEF>
-__global__ void __launch_bounds__(kBlock, S2D_MIN_BLOCKS) reachball_step_kernel(const __grid_constant__ KernelParams P,
-                                                                               const int K) {
+// SCN: scenario; ACT: action encoding; DEF: the constants are the default ServerParam, folded at compile time.
+template <int SCN, int ACT, bool DEF>
+__global__ void __launch_bounds__(kBlock, S2D_MIN_BLOCKS) step_kernel(const __grid_constant__ KernelParams P, const int K) {
   using SP = typename std::conditional<DEF, DefaultSP, RuntimeSP>::type;
   const SP sp(P.cc);
   __shared__ __align__(16) float s_stage[kBlock / 32][32 * kObsDim];
@@ -329,28 +396,33 @@ __global__ void __launch_bounds__(kBlock, S2D_MIN_BLOCKS) reachball_step_kernel(
   if (valid) {
     load_episode(P.state, n, i, e);
     if (ACT == S2D_ACT_DISCRETE) {
-      // the 2 KB action table stays in L1 (read-only path); `act` walks the lane's K action bytes
+      // the 4 KB action table stays in L1 (read-only path); `act` walks the lane's K action bytes
       const uint8_t* act = static_cast<const uint8_t*>(P.actions) + i * K;
       const uint8_t* const end = act + K;
 #pragma unroll 1
       for (; act != end; ++act) {
-        const float2 t = __ldg(P.dash_table + __ldg(act));
-        substep<ACT>(e, P, sp, gid, i, t.x, t.y, 0.f, 0.f, out);
+        if (SCN == S2D_SCENARIO_SHOOT) {
+          const float4 t = __ldg(P.action_table + __ldg(act));
+          substep<SCN, ACT>(e, P, sp, gid, i, t.x, t.y, t.z, t.w, out);
+        } else {  // ReachBall: always Dash(100, .): only the lowered direction and its rate are needed
+          const float2 t = __ldg(reinterpret_cast<const float2*>(P.action_table + __ldg(act)) + 1);
+          substep<SCN, ACT>(e, P, sp, gid, i, 0.f, 0.f, t.x, t.y, out);
+        }
       }
     } else if (ACT == S2D_ACT_CONTINUOUS) {
       const float* act = static_cast<const float*>(P.actions) + i * K;
 #pragma unroll 1
-      for (int k = 0; k < K; ++k) substep<ACT>(e, P, sp, gid, i, __ldg(act + k), 0.f, 0.f, 0.f, out);
+      for (int k = 0; k < K; ++k) substep<SCN, ACT>(e, P, sp, gid, i, __ldg(act + k), 0.f, 0.f, 0.f, out);
     } else {
       const float4* act = static_cast<const float4*>(P.actions) + i * K;
 #pragma unroll 1
       for (int k = 0; k < K; ++k) {
         const float4 a = __ldg(act + k);
-        substep<ACT>(e, P, sp, gid, i, a.x, a.y, a.z, a.w, out);
+        substep<SCN, ACT>(e, P, sp, gid, i, a.x, a.y, a.z, a.w, out);
       }
     }
     store_episode(P.state, n, i, e);
-    build_obs(e, obs_row);
+    scenario_obs<SCN>(e, obs_row);
     P.reward[i] = out.reward_sum;
     P.done[i] = static_cast<uint8_t>(out.ended != 0);
     P.result[i] = static_cast<uint8_t>(out.last_result());
@@ -360,18 +432,19 @@ __global__ void __launch_bounds__(kBlock, S2D_MIN_BLOCKS) reachball_step_kernel(
 }
 
 // Soccer2DEnv.reset for every env (mask == nullptr) or the envs with a non-zero mask byte.
-__global__ void __launch_bounds__(kBlock) reachball_reset_kernel(const __grid_constant__ KernelParams P,
-                                                                 const uint8_t* __restrict__ mask) {
+template <int SCN>
+__global__ void __launch_bounds__(kBlock) reset_kernel(const __grid_constant__ KernelParams P,
+                                                       const uint8_t* __restrict__ mask) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * kBlock + threadIdx.x;
   if (i >= P.num_envs) return;
   if (mask && !mask[i]) return;
   const RuntimeSP sp(P.cc);
   Episode e;
   load_episode(P.state, P.num_envs, i, e);
-  reset_episode(e, P, sp, static_cast<uint64_t>(P.env_id_offset + i));
+  reset_episode<SCN>(e, P, sp, static_cast<uint64_t>(P.env_id_offset + i));
   store_episode(P.state, P.num_envs, i, e);
   float row[kObsDim];
-  build_obs(e, row);
+  scenario_obs<SCN>(e, row);
   lane_store_row(P.obs, i, row);
   P.reward[i] = 0.0f;
   P.done[i] = 0;

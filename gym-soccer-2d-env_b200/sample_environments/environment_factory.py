@@ -4,6 +4,7 @@ vectorised entry point (N lockstep episodes on one GPU)."""
 from __future__ import annotations
 
 from sample_environments.reach_ball_env import ReachBallEnv
+from sample_environments.shoot_env import ShootEnv
 from soccer_2d_env import Soccer2DEnv
 from soccer2d_b200.vec_env import Soccer2DVecEnv
 
@@ -12,9 +13,11 @@ class EnvironmentFactory:
     def create(self, env_name: str, render_mode: str, logger, log_dir: str, **kwargs) -> Soccer2DEnv:
         if env_name.lower() == "reachball":
             return ReachBallEnv(render_mode=render_mode, logger=logger, log_dir=log_dir, **kwargs)
+        if env_name.lower() == "shoot":  # new scenario, not in the reference
+            return ShootEnv(render_mode=render_mode, logger=logger, log_dir=log_dir, **kwargs)
         raise ValueError(f"Environment {env_name} not found.")
 
     def create_vec(self, env_name: str, num_envs: int, **kwargs) -> Soccer2DVecEnv:
-        if env_name.lower() == "reachball":
-            return Soccer2DVecEnv(num_envs, scenario="reachball", **kwargs)
+        if env_name.lower() in ("reachball", "shoot"):
+            return Soccer2DVecEnv(num_envs, scenario=env_name.lower(), **kwargs)
         raise ValueError(f"Environment {env_name} not found.")

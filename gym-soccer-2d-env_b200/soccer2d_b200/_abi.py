@@ -8,7 +8,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 # ---- constants (mirror include/soccer2d.h) ----------------------------------------------------------
 S2D_OK, S2D_ERR_INVALID, S2D_ERR_UNBOUND, S2D_ERR_CUDA, S2D_ERR_NO_DEVICE = 0, -1, -2, -3, -4
@@ -47,6 +47,7 @@ class Config(C.Structure):
         ("max_steps", C.c_int32), ("auto_reset", C.c_int32),
         ("change_ball_position", C.c_int32), ("change_ball_velocity", C.c_int32), ("noise", C.c_int32),
         ("players_per_side", C.c_int32), ("half_time_cycles", C.c_int32),
+        ("kick_actions", C.c_int32), ("reserved_i", C.c_int32 * 3),
         ("min_distance_to_ball", C.c_float),
         ("ball_position_x", C.c_float), ("ball_position_y", C.c_float),
         ("ball_speed", C.c_float), ("ball_direction", C.c_float),

@@ -26,7 +26,13 @@ REACHBALL_DEFAULTS = dict(
     ball_direction=0, min_distance_to_ball=5.0, max_steps=200, use_continuous_action=True, action_space_size=16,
     use_turning=False)
 
-_SCENARIOS = {"reachball": _abi.SCENARIO_REACHBALL}
+# 1v0 shoot-on-goal (BASELINE configs[2]; spec in include/soccer2d.h): Discrete(24) = 16 dashes + 8 kicks by default
+SHOOT_DEFAULTS = dict(
+    change_ball_position=True, change_ball_velocity=False, ball_position_x=0, ball_position_y=0, ball_speed=0,
+    ball_direction=0, max_steps=200, action_space_size=24, kick_actions=8)
+
+_SCENARIOS = {"reachball": _abi.SCENARIO_REACHBALL, "shoot": _abi.SCENARIO_SHOOT}
+_DEFAULTS = {"reachball": REACHBALL_DEFAULTS, "shoot": SHOOT_DEFAULTS}
 
 
 def _stream_ptr(device) -> int:
@@ -45,19 +51,25 @@ class Soccer2DVecEnv:
     auto_reset     finished episodes restart inside the kernel (VecEnv convention)
     terminal_obs   also keep the last observation of finished episodes (needed for SB3 infos)
     server_param   dict of overrides for the physics constants (proto ServerParam names)
-    **kwargs       the ReachBallEnv kwargs, same names and defaults as the reference
+    use_command_action   actions are proto-style commands {cmd, a, b, c} (S2D_CMD_*: dash / turn / kick /
+                   body_go_to_point) instead of the scenario's own action space; shape [N, K, 4] float32
+    goto_dist_thr  Body_GoToPoint.distance_threshold for CMD_GOTO
+    **kwargs       the scenario kwargs: ReachBallEnv's (same names and defaults as the reference) or SHOOT_DEFAULTS
     """
 
     metadata = {"render.modes": ["human"]}  # soccer_2d_env.py:28
 
     def __init__(self, num_envs: int, scenario: str = "reachball", device="cuda", seed: int = 0, substeps: int = 1,
                  env_id_offset: int = 0, auto_reset: bool = True, terminal_obs: bool = False,
-                 server_param: dict | None = None, **kwargs):
+                 server_param: dict | None = None, use_command_action: bool = False, goto_dist_thr: float = 0.5,
+                 **kwargs):
         if scenario.lower() not in _SCENARIOS:
             raise ValueError(f"Environment {scenario} not found.")  # environment_factory.py:28
-        unknown = set(kwargs) - set(REACHBALL_DEFAULTS)
+        self.scenario = scenario.lower()
+        defaults = _DEFAULTS[self.scenario]
+        unknown = set(kwargs) - set(defaults)
         if unknown:
-            raise TypeError(f"unknown ReachBall kwargs: {sorted(unknown)}")
+            raise TypeError(f"unknown {self.scenario} kwargs: {sorted(unknown)}")
         self.lib = _abi.load()
         if not torch.cuda.is_available():
             raise _abi.Soccer2DError(_abi.S2D_ERR_NO_DEVICE, "no CUDA device: soccer2d_b200 has no CPU fallback")
@@ -68,7 +80,7 @@ class Soccer2DVecEnv:
             self.device = torch.device("cuda", torch.cuda.current_device())
         self.num_envs = int(num_envs)
         self.substeps = int(substeps)
-        self.kw = dict(REACHBALL_DEFAULTS, **kwargs)
+        self.kw = dict(defaults, **kwargs)
         for k, v in self.kw.items():
             setattr(self, k, v)
         self.seed_value = int(seed)
@@ -81,16 +93,20 @@ class Soccer2DVecEnv:
         cfg.env_id_offset = self.env_id_offset
         cfg.seed = self.seed_value & 0xFFFFFFFFFFFFFFFF
         cfg.device = self.device.index
-        if self.kw["use_continuous_action"]:
+        if use_command_action:
+            cfg.action_mode = _abi.ACT_COMMAND
+        elif self.kw.get("use_continuous_action", False):
             cfg.action_mode = _abi.ACT_TURNING if self.kw["use_turning"] else _abi.ACT_CONTINUOUS
         else:
             cfg.action_mode = _abi.ACT_DISCRETE
         cfg.action_space_size = int(self.kw["action_space_size"])
+        cfg.kick_actions = int(self.kw.get("kick_actions", 0))
+        cfg.goto_dist_thr = float(goto_dist_thr)
         cfg.max_steps = int(self.kw["max_steps"])
         cfg.auto_reset = int(self.auto_reset)
         cfg.change_ball_position = int(bool(self.kw["change_ball_position"]))
         cfg.change_ball_velocity = int(bool(self.kw["change_ball_velocity"]))
-        cfg.min_distance_to_ball = float(self.kw["min_distance_to_ball"])
+        cfg.min_distance_to_ball = float(self.kw.get("min_distance_to_ball", 5.0))
         cfg.ball_position_x = float(self.kw["ball_position_x"])
         cfg.ball_position_y = float(self.kw["ball_position_y"])
         cfg.ball_speed = float(self.kw["ball_speed"])
@@ -103,7 +119,10 @@ class Soccer2DVecEnv:
         self.action_mode = cfg.action_mode
 
         # spaces exactly as reach_ball_env.py:39-48
-        if cfg.action_mode == _abi.ACT_TURNING:
+        if cfg.action_mode == _abi.ACT_COMMAND:  # {cmd, a, b, c}: cmd in 0..4, arguments in metres / degrees / power
+            self.action_space = Box(low=np.array([0, -180, -180, -180], dtype=np.float32),
+                                    high=np.array([4, 180, 180, 180], dtype=np.float32), dtype=np.float32)
+        elif cfg.action_mode == _abi.ACT_TURNING:
             self.action_space = Box(low=np.array([-1, -1, -1, -1], dtype=np.float32),
                                     high=np.array([1, 1, 1, 1], dtype=np.float32), dtype=np.float32)
         elif cfg.action_mode == _abi.ACT_CONTINUOUS:

@@ -30,7 +30,8 @@ class Soccer2DEnv(Env):
 
     def __init__(self, render_mode: str = None, run_grpc_server: bool = True, run_rcssserver: bool = True,
                  run_trainer_player: bool = True, logger: logging.Logger = None, log_dir: str = None,
-                 *, device="cuda", seed: int = 0, server_param: dict | None = None, **scenario_kwargs):
+                 *, device="cuda", seed: int = 0, server_param: dict | None = None, use_command_action: bool = False,
+                 **scenario_kwargs):
         self.log_dir = log_dir
         self.logger = logger
         if self.logger is None:
@@ -44,7 +45,8 @@ class Soccer2DEnv(Env):
         self.action_space = Discrete(4)
         self.observation_space = Box(low=-1, high=1, shape=(2,), dtype=np.float32)
         self._vec = Soccer2DVecEnv(1, scenario=self.scenario, device=device, seed=seed, substeps=1, auto_reset=False,
-                                   server_param=server_param, **scenario_kwargs)
+                                   server_param=server_param, use_command_action=use_command_action,
+                                   **scenario_kwargs)
         self.action_space = self._vec.action_space
         self.observation_space = self._vec.observation_space
         self.step_number = 0
@@ -89,10 +91,10 @@ class Soccer2DEnv(Env):
                 raise ValueError(f"discrete action {a} outside Discrete({n})")
             return np.array([[a]], dtype=np.uint8)
         a = np.asarray(action, dtype=np.float32).reshape(-1)
-        want = 4 if mode == _abi.ACT_TURNING else 1
+        want = 4 if mode in (_abi.ACT_TURNING, _abi.ACT_COMMAND) else 1
         if a.size != want:
             raise ValueError(f"expected an action with {want} value(s), got shape {np.asarray(action).shape}")
-        return a.reshape((1, 1, 4) if mode == _abi.ACT_TURNING else (1, 1))
+        return a.reshape((1, 1, 4) if want == 4 else (1, 1))
 
     @property
     def distance_to_ball(self) -> float:

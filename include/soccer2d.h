@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define S2D_ABI_VERSION 3
+#define S2D_ABI_VERSION 4
 
 /* error codes */
 #define S2D_OK 0
@@ -51,14 +51,27 @@ extern "C" {
 
 /* scenarios */
 #define S2D_SCENARIO_REACHBALL 0 /* sample_environments/reach_ball_env.py: 1 player + ball */
-#define S2D_SCENARIO_SHOOT 1     /* 1v0 shoot-on-goal: kick model + goal / ball-out detection */
+#define S2D_SCENARIO_SHOOT 1     /* 1v0 shoot-on-goal: kick model + goal / ball-out detection (spec below) */
 #define S2D_SCENARIO_FULLGAME 2  /* 11 v 11: dash/turn/kick, stamina, collisions, play modes */
 
+/* SHOOT scenario (BASELINE configs[2]; not in the reference, which has ReachBall only - this is the spec):
+ *   one player (left team) + ball, reset distribution and observation as ReachBall;
+ *   goal   = the ball is beyond x = +(pitch_half_length + ball_size) this cycle, was not the cycle before, and the
+ *            segment between the two positions meets that line at |y| <= goal_width/2 + goal_post_radius
+ *            (rcssserver's referee rule)                                   -> done, result GOAL,    reward +10
+ *   out    = otherwise |x| > pitch_half_length + ball_size or |y| > pitch_half_width + ball_size (own goal
+ *            included)                                                     -> done, result OUT,     reward -10
+ *   else step_number > max_steps                                           -> done, result TIMEOUT, reward -5
+ *   shaping every step: 0.2 * (d_player_ball[t-1] - d_player_ball[t]) + (d_ball_goal[t-1] - d_ball_goal[t]),
+ *            d_ball_goal measured to the centre of the right goal (pitch_half_length, 0).
+ *   Discrete(n): the first n - kick_actions actions are Dash(100, (a*360/n_dash)%360-180) as in ReachBall, the last
+ *            kick_actions are Kick(100, (j*360/kick_actions)%360-180). */
+
 /* action encodings (reach_ball_env.py:39-47, :53-85) */
-#define S2D_ACT_DISCRETE 0   /* uint8  [N][K]      Discrete(n): Dash(100, (a*360/n)%360-180)      */
-#define S2D_ACT_CONTINUOUS 1 /* float  [N][K][1]   Box(-1,1,(1,)): Dash(100, a*180)               */
-#define S2D_ACT_TURNING 2    /* float  [N][K][4]   [turn_prob, turn_angle, dash_prob, dash_angle] */
-#define S2D_ACT_COMMAND 3    /* float4 [N][K][P]   {cmd, a, b, c} per player: see S2D_CMD_*       */
+#define S2D_ACT_DISCRETE 0   /* uint8  [N][K]      Discrete(n): Dash(100, (a*360/n)%360-180) (+ kicks in SHOOT)  */
+#define S2D_ACT_CONTINUOUS 1 /* float  [N][K][1]   Box(-1,1,(1,)): Dash(100, a*180)               (REACHBALL)   */
+#define S2D_ACT_TURNING 2    /* float  [N][K][4]   [turn_prob, turn_angle, dash_prob, dash_angle] (REACHBALL)   */
+#define S2D_ACT_COMMAND 3    /* float4 [N][K][P]   {cmd, a, b, c} per player: see S2D_CMD_* (proto PlayerAction) */
 
 /* S2D_ACT_COMMAND: cmd stored as a float; arguments as in the proto messages */
 #define S2D_CMD_NONE 0 /* no body command this cycle                                  */
@@ -126,6 +139,8 @@ typedef struct S2DConfig {
   int32_t noise;       /* 0 = noise off (player_rand = ball_rand = kick_rand = 0) */
   int32_t players_per_side; /* FULLGAME: 1..11 */
   int32_t half_time_cycles; /* FULLGAME: cycles per half (rcssserver: 3000) */
+  int32_t kick_actions;     /* SHOOT + S2D_ACT_DISCRETE: how many of the action_space_size actions are kicks */
+  int32_t reserved_i[3];
   float min_distance_to_ball; /* reach_ball_env.py:32 */
   float ball_position_x, ball_position_y, ball_speed, ball_direction; /* reach_ball_env.py:28-31 */
   float goto_dist_thr; /* Body_GoToPoint.distance_threshold for S2D_CMD_GOTO */

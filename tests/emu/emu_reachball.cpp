@@ -11,12 +11,12 @@ using namespace s2d;
 
 struct Emu {
   KernelParams kp;
-  float2 table[256];
+  float4 table[256];
   bool default_sp;  // same dispatch as s2d_create: constant-folded accessors for the default ServerParam
   std::vector<unsigned char> state;
 };
 
-template <int ACT, class SP>
+template <int SCN, int ACT, class SP>
 static void step_all(Emu* h, const void* actions, int K, float* obs, float* reward, uint8_t* done, uint8_t* result,
                      double* stats) {
   const KernelParams& P = h->kp;
@@ -29,17 +29,17 @@ static void step_all(Emu* h, const void* actions, int K, float* obs, float* rewa
     const uint64_t gid = (uint64_t)(P.env_id_offset + i);
     for (int k = 0; k < K; ++k) {
       if (ACT == S2D_ACT_DISCRETE) {
-        const float2 t = h->table[((const uint8_t*)actions)[i * K + k]];
-        substep<ACT>(e, P, sp, gid, i, t.x, t.y, 0.f, 0.f, out);
+        const float4 t = h->table[((const uint8_t*)actions)[i * K + k]];
+        substep<SCN, ACT>(e, P, sp, gid, i, t.x, t.y, t.z, t.w, out);
       } else if (ACT == S2D_ACT_CONTINUOUS) {
-        substep<ACT>(e, P, sp, gid, i, ((const float*)actions)[i * K + k], 0.f, 0.f, 0.f, out);
+        substep<SCN, ACT>(e, P, sp, gid, i, ((const float*)actions)[i * K + k], 0.f, 0.f, 0.f, out);
       } else {
         const float* a = (const float*)actions + (i * K + k) * 4;
-        substep<ACT>(e, P, sp, gid, i, a[0], a[1], a[2], a[3], out);
+        substep<SCN, ACT>(e, P, sp, gid, i, a[0], a[1], a[2], a[3], out);
       }
     }
     store_episode(P.state, n, i, e);
-    build_obs(e, obs + i * kObsDim);
+    scenario_obs<SCN>(e, obs + i * kObsDim);
     reward[i] = out.reward_sum;
     done[i] = (uint8_t)(out.ended != 0);
     result[i] = (uint8_t)out.last_result();
@@ -56,7 +56,7 @@ void* emu_create(const S2DConfig* cfg) {
   h->default_sp = is_default_server_param(cfg->sp);
   h->state.assign((size_t)cfg->num_envs * kStateBytesPerEnv, 0);
   h->kp.state = h->state.data();
-  h->kp.dash_table = h->table;
+  h->kp.action_table = h->table;
   return h;
 }
 void emu_destroy(void* p) { delete (Emu*)p; }
@@ -69,9 +69,14 @@ void emu_reset(void* p, const uint8_t* mask, float* obs) {
     if (mask && !mask[i]) continue;
     Episode e;
     load_episode(P.state, P.num_envs, i, e);
-    reset_episode(e, P, RuntimeSP(P.cc), (uint64_t)(P.env_id_offset + i));
+    if (P.scenario == S2D_SCENARIO_SHOOT) {
+      reset_episode<S2D_SCENARIO_SHOOT>(e, P, RuntimeSP(P.cc), (uint64_t)(P.env_id_offset + i));
+      scenario_obs<S2D_SCENARIO_SHOOT>(e, obs + i * kObsDim);
+    } else {
+      reset_episode<S2D_SCENARIO_REACHBALL>(e, P, RuntimeSP(P.cc), (uint64_t)(P.env_id_offset + i));
+      scenario_obs<S2D_SCENARIO_REACHBALL>(e, obs + i * kObsDim);
+    }
     store_episode(P.state, P.num_envs, i, e);
-    build_obs(e, obs + i * kObsDim);
   }
 }
 
@@ -79,15 +84,21 @@ void emu_step(void* p, const void* actions, int K, float* obs, float* reward, ui
               float* terminal_obs, double* stats6) {
   Emu* h = (Emu*)p;
   h->kp.terminal_obs = terminal_obs;
-#define EMU_STEP(ACT)                                                                            \
-  do {                                                                                           \
-    if (h->default_sp) step_all<ACT, DefaultSP>(h, actions, K, obs, reward, done, result, stats6); \
-    else step_all<ACT, RuntimeSP>(h, actions, K, obs, reward, done, result, stats6);             \
+#define EMU_STEP(SCN, ACT)                                                                            \
+  do {                                                                                                \
+    if (h->default_sp) step_all<SCN, ACT, DefaultSP>(h, actions, K, obs, reward, done, result, stats6); \
+    else step_all<SCN, ACT, RuntimeSP>(h, actions, K, obs, reward, done, result, stats6);             \
   } while (0)
-  switch (h->kp.action_mode) {
-    case S2D_ACT_DISCRETE: EMU_STEP(S2D_ACT_DISCRETE); break;
-    case S2D_ACT_CONTINUOUS: EMU_STEP(S2D_ACT_CONTINUOUS); break;
-    default: EMU_STEP(S2D_ACT_TURNING); break;
+  if (h->kp.scenario == S2D_SCENARIO_SHOOT) {
+    if (h->kp.action_mode == S2D_ACT_DISCRETE) EMU_STEP(S2D_SCENARIO_SHOOT, S2D_ACT_DISCRETE);
+    else EMU_STEP(S2D_SCENARIO_SHOOT, S2D_ACT_COMMAND);
+  } else {
+    switch (h->kp.action_mode) {
+      case S2D_ACT_DISCRETE: EMU_STEP(S2D_SCENARIO_REACHBALL, S2D_ACT_DISCRETE); break;
+      case S2D_ACT_CONTINUOUS: EMU_STEP(S2D_SCENARIO_REACHBALL, S2D_ACT_CONTINUOUS); break;
+      case S2D_ACT_TURNING: EMU_STEP(S2D_SCENARIO_REACHBALL, S2D_ACT_TURNING); break;
+      default: EMU_STEP(S2D_SCENARIO_REACHBALL, S2D_ACT_COMMAND); break;
+    }
   }
 }
 

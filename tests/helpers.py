@@ -20,12 +20,15 @@ OBS_ANGLE_PERIOD = {0: 2.0, 1: 2.0, 7: 1.0}
 TOL = 1.0e-5
 
 
-def make_config(num_envs, mode="discrete", **kw):
+MODES["command"] = _abi.ACT_COMMAND
+
+
+def make_config(num_envs, mode="discrete", scenario=_abi.SCENARIO_REACHBALL, **kw):
     """S2DConfig with the reference defaults (s2d_default_config) and overrides; kwargs named like the
     struct fields, plus `sp={...}` for ServerParam overrides."""
     lib = _abi.load()
     cfg = _abi.Config()
-    assert lib.s2d_default_config(C.byref(cfg), _abi.SCENARIO_REACHBALL) == 0
+    assert lib.s2d_default_config(C.byref(cfg), scenario) == 0
     cfg.num_envs = num_envs
     cfg.action_mode = MODES[mode] if isinstance(mode, str) else mode
     sp = kw.pop("sp", {})
@@ -44,7 +47,47 @@ def random_actions(rng, mode, n, k=1, n_actions=16):
         return rng.integers(0, n_actions, size=(n, k)).astype(np.uint8)
     if mode == _abi.ACT_CONTINUOUS:
         return rng.uniform(-1, 1, size=(n, k)).astype(np.float32)
+    if mode == _abi.ACT_COMMAND:
+        return random_commands(rng, n, k)
     return rng.uniform(-1.25, 1.25, size=(n, k, 4)).astype(np.float32)
+
+
+def random_commands(rng, n, k=1):
+    """[n, k, 4] float32 {cmd, a, b, c}: a mix of none / dash / turn / kick / go-to-point with out-of-range
+    arguments now and then (the clamps are part of the contract)."""
+    a = np.zeros((n, k, 4), np.float32)
+    cmd = rng.choice([0, 1, 1, 1, 2, 3, 3, 4, 4], size=(n, k))
+    a[..., 0] = cmd
+    dash, turn, kick, goto = cmd == 1, cmd == 2, cmd == 3, cmd == 4
+    a[..., 1] = np.where(dash | kick, rng.uniform(-30, 130, (n, k)), a[..., 1])
+    a[..., 2] = np.where(dash | kick, rng.uniform(-200, 200, (n, k)), a[..., 2])
+    a[..., 1] = np.where(turn, rng.uniform(-200, 200, (n, k)), a[..., 1])
+    a[..., 1] = np.where(goto, rng.uniform(-55, 55, (n, k)), a[..., 1])
+    a[..., 2] = np.where(goto, rng.uniform(-36, 36, (n, k)), a[..., 2])
+    a[..., 3] = np.where(goto, rng.uniform(20, 120, (n, k)), a[..., 3])
+    return a
+
+
+def chase_and_shoot(obs, rng=None, kick_prob=1.0):
+    """Scripted 1v0 policy from a [n, 10] observation (ReachBall layout): go to the ball, kick it towards the
+    centre of the right goal when it is close.  Returns [n, 1, 4] float32 commands."""
+    obs = np.asarray(obs, np.float64)
+    n = obs.shape[0]
+    px, py, bx, by = obs[:, 2] * 52.5, obs[:, 3] * 34.0, obs[:, 4] * 52.5, obs[:, 5] * 34.0
+    body = obs[:, 1] * 180.0
+    dist = np.hypot(bx - px, by - py)
+    a = np.zeros((n, 1, 4), np.float32)
+    near = dist < 1.0
+    goal_dir = np.degrees(np.arctan2(0.0 - by, 52.5 - bx)) - body
+    goal_dir = (goal_dir + 180.0) % 360.0 - 180.0
+    a[:, 0, 0] = np.where(near, 3, 4)
+    a[:, 0, 1] = np.where(near, 100.0, bx)
+    a[:, 0, 2] = np.where(near, goal_dir, by)
+    a[:, 0, 3] = np.where(near, 0.0, 100.0)
+    if rng is not None and kick_prob < 1.0:
+        skip = near & (rng.uniform(size=n) > kick_prob)
+        a[skip, 0, 0] = 0
+    return a
 
 
 def obs_close(a, b, tol=TOL):

@@ -425,3 +425,128 @@ def test_full_size_properties_1m_envs():
     assert st["return_sum"] == pytest.approx(b.stats()["return_sum"], rel=1e-9)
     assert int((u[:, 2] - 1).sum()) == st["episodes"]                      # episode counters add up
     assert total_done > 0
+
+
+# ---- command actions (proto PlayerAction vocabulary) and the SHOOT scenario (BASELINE configs[2]) -------------
+
+def test_command_mode_reachball_bit_exact():
+    n = 700
+    env = Soccer2DVecEnv(n, device="cuda:0", seed=9, use_command_action=True, goto_dist_thr=0.4, terminal_obs=True,
+                         change_ball_velocity=True, max_steps=120, min_distance_to_ball=0.3)
+    sim = OL.OracleSim(env.cfg, "f32")
+    assert np.array_equal(env.reset(), sim.reset())
+    rng = np.random.default_rng(0)
+    flags = 0
+    for t in range(500):
+        act = H.random_commands(rng, n)
+        if t % 2:
+            act = np.where(rng.uniform(size=(n, 1, 1)) < 0.7, H.chase_and_shoot(sim.obs), act).astype(np.float32)
+        env.step_torch(torch.from_numpy(act))
+        sim.step(act)
+        assert_same_step(env, sim)
+        if t % 50 == 49:
+            g = gpu_state(env)
+            assert np.array_equal(g, sim.get_state())
+            flags |= int(np.bitwise_or.reduce(g[:, 19].astype(int)))
+    assert env.stats()["episodes"] > n
+
+
+@pytest.mark.parametrize("mode,k", [("discrete", 1), ("discrete", 16), ("command", 1), ("command", 4)])
+def test_shoot_bit_exact_against_fp32_oracle(mode, k):
+    n = 900
+    env = Soccer2DVecEnv(n, scenario="shoot", device="cuda:0", seed=21, substeps=k, terminal_obs=True, max_steps=150,
+                         use_command_action=mode == "command")
+    sim = OL.OracleSim(env.cfg, "f32")
+    assert env.action_space.shape == ((4,) if mode == "command" else ()) and env.obs.shape == (n, 10)
+    assert np.array_equal(env.reset(), sim.reset())
+    rng = np.random.default_rng(1)
+    for t in range(640 // k):
+        if mode == "discrete":
+            act = rng.integers(0, 24, size=(n, k)).astype(np.uint8)
+        else:
+            act = np.repeat(H.chase_and_shoot(sim.obs, rng, kick_prob=0.9), k, axis=1)
+            rnd = H.random_commands(rng, n, k)
+            act = np.where(rng.uniform(size=(n, k, 1)) < 0.1, rnd, act).astype(np.float32)
+        env.step_torch(torch.from_numpy(act))
+        sim.step(act, k)
+        assert_same_step(env, sim)
+    assert np.array_equal(gpu_state(env), sim.get_state())
+    st, so = env.stats(), sim.stats(_abi.Stats())
+    assert (st["episodes"], st["goals"], st["outs"], st["timeouts"]) == (so.episodes, so.goals, so.outs, so.timeouts)
+    assert st["episodes"] > 0
+    if mode == "command":
+        assert st["goals"] > 50 and st["outs"] > 0
+
+
+def test_shoot_against_f64_truth():
+    """scripted chase-and-shoot policy, 600 cycles: flags bit-exact, floats within 1e-5 of the double oracle"""
+    n = 128
+    env = Soccer2DVecEnv(n, scenario="shoot", device="cuda:0", seed=77, use_command_action=True, max_steps=150)
+    sim = OL.OracleSim(env.cfg, "f64")
+    assert H.obs_close(env.reset(), sim.reset()) < H.TOL
+    goals = 0
+    for t in range(600):
+        act = H.chase_and_shoot(sim.obs.astype(np.float32))
+        env.step_torch(torch.from_numpy(act))
+        sim.step(act)
+        assert_same_step(env, sim, exact=False)
+        goals += int((sim.result == 1).sum())
+    assert goals > 30
+    g, o = gpu_state(env), sim.get_state()
+    assert np.array_equal(g[:, 16:], o[:, 16:])
+    assert H.state_err(g, o) < H.TOL
+
+
+def test_shoot_goal_line_and_kickable_edge_cases():
+    line = 52.5 + 0.085
+    base = [0, 0, 0, 0, 0, 8000, 1, 1, 130600]
+    cases = [
+        base + [line - 0.5, 6.9, 1.0, 0.1, 50, 1, 0, 3, 3, 1],
+        base + [line - 0.5, 7.0, 1.0, 0.2, 50, 1, 0, 3, 3, 1],
+        base + [line - 0.5, 0.0, 0.4, 0.0, 50, 1, 0, 3, 3, 1],
+        base + [-line + 0.5, 0.0, -1.0, 0.0, 50, 104, 0, 3, 3, 1],
+        base + [10, 33.9, 0.0, 0.5, 40, 45, 0, 3, 3, 1],
+        [20, 10, 0, 0, 30, 8000, 1, 1, 130600, 20 + 1.08, 10, 0, 0, 1.08, 34, 0, 3, 3, 1],
+        [20, 10, 0, 0, 30, 8000, 1, 1, 130600, 20 + 1.09, 10, 0, 0, 1.09, 34, 0, 3, 3, 1],
+        [51, 0, 0, 0, 0, 8000, 1, 1, 130600, 51.5, 0, 0, 0, 0.5, 1, 0, 3, 3, 1],
+    ]
+    n = len(cases)
+    env = Soccer2DVecEnv(n, scenario="shoot", device="cuda:0", seed=2, use_command_action=True, max_steps=50)
+    sim = OL.OracleSim(env.cfg, "f32")
+    env.reset_torch()
+    sim.reset()
+    for i, c in enumerate(cases):
+        set_gpu_state(env, i, c + [0])
+        sim.set_state(i, np.array(c + [0], dtype=np.float64))
+    act = np.zeros((n, 1, 4), np.float32)
+    act[5:, 0, :3] = [3, 100, 0]
+    env.step_torch(torch.from_numpy(act))
+    sim.step(act)
+    assert_same_step(env, sim)
+    assert env.result.cpu().tolist()[:5] == [1, 2, 0, 2, 2]  # Goal, Out (outside the post), -, Out (own goal), Out (side)
+    g = gpu_state(env)
+    assert np.array_equal(g, sim.get_state())
+    assert int(g[5, 19]) & _abi.FLAG_KICKED and not int(g[6, 19]) & _abi.FLAG_KICKED
+    snap = env.export_env(5)
+    assert snap.players[0].kicked == 1 and snap.num_players == 1
+
+
+def test_shoot_gym_api_and_factory():
+    from sample_environments.environment_factory import EnvironmentFactory
+    env = EnvironmentFactory().create("Shoot", None, None, "/tmp", seed=3, max_steps=40)
+    assert env.action_space.n == 24 and env.observation_space.shape == (10,)
+    sim = OL.OracleSim(env._vec.cfg, "f32")
+    rng = np.random.default_rng(0)
+    obs = env.reset()
+    assert np.array_equal(obs, sim.reset(np.ones(1, np.uint8))[0])
+    done = False
+    while not done:
+        a = int(rng.integers(24))
+        obs, reward, done, info = env.step(a)
+        sim.step(np.array([[a]], np.uint8))
+        assert np.array_equal(obs, sim.obs[0]) and reward == float(sim.reward[0])
+    assert info["result"] in ("Goal", "Out", "Timeout")
+    env.close()
+    vec = EnvironmentFactory().create_vec("shoot", 64, device="cuda:0", use_command_action=True)
+    assert vec.actions.shape == (64, 1, 4)
+    vec.close()

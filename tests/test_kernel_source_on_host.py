@@ -105,3 +105,104 @@ def test_kernel_source_masked_reset_no_auto_reset():
             sim.reset(mask)
             assert np.array_equal(emu.obs[mask.astype(bool)], sim.obs[mask.astype(bool)])
             assert np.array_equal(emu.get_state(), sim.get_state())
+
+
+# ---- command mode (proto PlayerAction vocabulary) and the SHOOT scenario ---------------------------------
+
+def _same(emu, sim):
+    assert np.array_equal(emu.done, sim.done) and np.array_equal(emu.result, sim.result)
+    assert np.array_equal(emu.obs, sim.obs) and np.array_equal(emu.reward, sim.reward)
+    d = emu.done.astype(bool)
+    assert np.array_equal(emu.term_obs[d], sim.term_obs[d])
+
+
+@pytest.mark.parametrize("default_sp", [True, False])
+def test_kernel_source_command_mode_reachball(default_sp):
+    """none / dash / turn / kick / go-to-point with out-of-range arguments, ReachBall scoring.  min_distance 0.3 so
+    that episodes get close enough for kicks and collisions to happen."""
+    n = 193
+    sp = {} if default_sp else dict(inertia_moment=4.0, kick_power_rate=0.03, kickable_margin=0.9, dash_angle_step=0.0)
+    cfg = H.make_config(n, "command", seed=9, change_ball_velocity=1, max_steps=120, min_distance_to_ball=0.3,
+                        goto_dist_thr=0.4, sp=sp)
+    emu, sim = EL.EmuSim(cfg), OL.OracleSim(cfg, "f32")
+    assert EL.lib().emu_uses_default_sp(emu.h) == int(default_sp)
+    assert np.array_equal(emu.reset(), sim.reset())
+    rng = np.random.default_rng(0)
+    flags = 0
+    for t in range(500):
+        act = H.random_commands(rng, n)
+        if t % 2:  # every other step chase the ball so that kicks find it kickable
+            act = np.where(rng.uniform(size=(n, 1, 1)) < 0.7, H.chase_and_shoot(sim.obs), act).astype(np.float32)
+        emu.step(act)
+        sim.step(act)
+        _same(emu, sim)
+        g = emu.get_state()
+        assert np.array_equal(g, sim.get_state())
+        flags |= int(np.bitwise_or.reduce(g[:, 19].astype(int)))
+    assert flags & 4, "no kick was ever applied"
+
+
+@pytest.mark.parametrize("mode", ["discrete", "command"])
+def test_kernel_source_shoot(mode):
+    from soccer2d_b200 import _abi
+    n = 160
+    cfg = H.make_config(n, mode, scenario=_abi.SCENARIO_SHOOT, seed=21, change_ball_velocity=0, max_steps=150)
+    emu, sim = EL.EmuSim(cfg), OL.OracleSim(cfg, "f32")
+    assert np.array_equal(emu.reset(), sim.reset())
+    rng = np.random.default_rng(1)
+    for t in range(700):
+        if mode == "discrete":
+            act = rng.integers(0, 24, size=(n, 1)).astype(np.uint8)
+        else:
+            act = H.chase_and_shoot(sim.obs, rng, kick_prob=0.9)
+            rnd = H.random_commands(rng, n)
+            act = np.where(rng.uniform(size=(n, 1, 1)) < 0.1, rnd, act).astype(np.float32)
+        emu.step(act)
+        sim.step(act)
+        _same(emu, sim)
+    assert np.array_equal(emu.get_state(), sim.get_state())
+    st = sim.stats(_abi.Stats())
+    assert st.episodes > 0
+    if mode == "command":  # the scripted policy scores, misses and runs out of time
+        assert st.goals > 20 and st.outs > 0 and st.timeouts >= 0
+
+
+def test_kernel_source_shoot_goal_line_cases():
+    """Hand-placed balls about to cross the goal line: inside the post, outside it, own goal, side line; and a
+    kick from the edge of the kickable area."""
+    from soccer2d_b200 import _abi
+    line = 52.5 + 0.085
+    # px py vx vy body stamina effort recovery capacity | bx by bvx bvy | mem_pb mem_bg ep_ret | step cycle episode
+    base = [0, 0, 0, 0, 0, 8000, 1, 1, 130600]
+    cases = [
+        base + [line - 0.5, 6.9, 1.0, 0.1, 50, 1, 0, 3, 3, 1],      # crosses inside the post -> Goal
+        base + [line - 0.5, 7.0, 1.0, 0.2, 50, 1, 0, 3, 3, 1],      # crosses just outside -> Out
+        base + [line - 0.5, 0.0, 0.4, 0.0, 50, 1, 0, 3, 3, 1],      # does not reach the line this cycle
+        base + [-line + 0.5, 0.0, -1.0, 0.0, 50, 104, 0, 3, 3, 1],  # own goal -> Out
+        base + [10, 33.9, 0.0, 0.5, 40, 45, 0, 3, 3, 1],            # over the side line -> Out
+        [20, 10, 0, 0, 30, 8000, 1, 1, 130600, 20 + 1.08, 10, 0, 0, 1.08, 34, 0, 3, 3, 1],   # kickable (edge)
+        [20, 10, 0, 0, 30, 8000, 1, 1, 130600, 20 + 1.09, 10, 0, 0, 1.09, 34, 0, 3, 3, 1],   # just not kickable
+        [51, 0, 0, 0, 0, 8000, 1, 1, 130600, 51.5, 0, 0, 0, 0.5, 1, 0, 3, 3, 1],             # kick straight in
+    ]
+    n = len(cases)
+    cfg = H.make_config(n, "command", scenario=_abi.SCENARIO_SHOOT, seed=2, max_steps=50)
+    emu, sim = EL.EmuSim(cfg), OL.OracleSim(cfg, "f32")
+    emu.reset()
+    sim.reset()
+    for i, c in enumerate(cases):
+        emu.set_state(i, c + [0])
+        sim.set_state(i, np.array(c + [0], dtype=np.float64))
+    act = np.zeros((n, 1, 4), np.float32)
+    act[5:, 0, :3] = [3, 100, 0]  # Kick(100, 0)
+    emu.step(act)
+    sim.step(act)
+    _same(emu, sim)
+    assert np.array_equal(emu.get_state(), sim.get_state())
+    assert list(sim.result[:5]) == [1, 2, 0, 2, 2]
+    st = sim.get_state()
+    assert int(st[5, 19]) & 4 and not int(st[6, 19]) & 4  # kicked flag: edge of the kickable area
+    for _ in range(3):
+        emu.step(act)
+        sim.step(act)
+        _same(emu, sim)
+    assert sim.stats(_abi.Stats()).goals >= 2  # case 0 and the straight kick

@@ -68,6 +68,20 @@ def random_commands(rng, n, k=1):
     return a
 
 
+def dash_and_shoot(obs):
+    """Like chase_and_shoot, but moves with explicit Dash(100, direction to the ball) commands: no turn-or-dash
+    decision inside the simulator, so an fp32 and an f64 run cannot split on that threshold."""
+    a = chase_and_shoot(obs)
+    obs = np.asarray(obs, np.float64)
+    far = a[:, 0, 0] == 4
+    rel = obs[:, 0] * 180.0  # body-to-ball angle
+    a[far, 0, 0] = 1
+    a[far, 0, 1] = 100.0
+    a[far, 0, 2] = np.rint(rel[far])
+    a[far, 0, 3] = 0.0
+    return a
+
+
 def chase_and_shoot(obs, rng=None, kick_prob=1.0):
     """Scripted 1v0 policy from a [n, 10] observation (ReachBall layout): go to the ball, kick it towards the
     centre of the right goal when it is close.  Returns [n, 1, 4] float32 commands."""
@@ -90,13 +104,15 @@ def chase_and_shoot(obs, rng=None, kick_prob=1.0):
     return a
 
 
-def obs_close(a, b, tol=TOL):
-    """|a - b| <= tol per column, angles compared on the circle.  Obs columns are already normalised to O(1)."""
+def obs_close(a, b, tol=TOL, angle_scale=1.0):
+    """max |a - b| over the columns, angles compared on the circle.  Obs columns are already normalised to O(1).
+    `angle_scale` < 1 down-weights the angle columns: the direction of a short vector (player next to the ball, slow
+    ball) is ill-conditioned - an absolute position error eps moves it by eps / length."""
     a = np.asarray(a, np.float64)
     b = np.asarray(b, np.float64)
     d = np.abs(a - b)
     for col, period in OBS_ANGLE_PERIOD.items():
-        d[..., col] = np.minimum(d[..., col], np.abs(period - d[..., col]))
+        d[..., col] = np.minimum(d[..., col], np.abs(period - d[..., col])) * angle_scale
     return d.max() if d.size else 0.0
 
 

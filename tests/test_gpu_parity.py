@@ -57,7 +57,7 @@ def set_gpu_state(env, i, v):
     u[i, :3] = torch.tensor([int(v[16]), int(v[17]), int(v[18])], dtype=torch.int32, device=u.device)
 
 
-def assert_same_step(env, sim, exact=True):
+def assert_same_step(env, sim, exact=True, angle_scale=1.0):
     obs, rew = env.obs.cpu().numpy(), env.reward.cpu().numpy()
     done, res = env.done_u8.cpu().numpy(), env.result.cpu().numpy()
     assert np.array_equal(done, sim.done) and np.array_equal(res, sim.result)
@@ -68,7 +68,7 @@ def assert_same_step(env, sim, exact=True):
             d = done.astype(bool)
             assert np.array_equal(env.terminal_obs.cpu().numpy()[d], sim.term_obs[d])
     else:
-        assert H.obs_close(obs, sim.obs) < H.TOL
+        assert H.obs_close(obs, sim.obs, angle_scale=angle_scale) < H.TOL
         assert np.abs(rew - sim.reward).max() < H.TOL * 100.0
     return int(done.sum())
 
@@ -479,22 +479,31 @@ def test_shoot_bit_exact_against_fp32_oracle(mode, k):
 
 
 def test_shoot_against_f64_truth():
-    """scripted chase-and-shoot policy, 600 cycles: flags bit-exact, floats within 1e-5 of the double oracle"""
+    """Against the double oracle, cycle by cycle: flags bit-exact, floats within 1e-5.
+    Dribbling is chaotic - every kick multiplies a position error by about the ball's travel (x16) - so over many
+    kicks NO fixed tolerance can hold between an fp32 and an f64 run.  The double oracle is therefore re-synchronised
+    to the GPU state before every cycle and the two are compared one cycle ahead, for every state the policy visits
+    (kicks, collisions, goals, resets included)."""
     n = 128
     env = Soccer2DVecEnv(n, scenario="shoot", device="cuda:0", seed=77, use_command_action=True, max_steps=150)
     sim = OL.OracleSim(env.cfg, "f64")
     assert H.obs_close(env.reset(), sim.reset()) < H.TOL
-    goals = 0
-    for t in range(600):
-        act = H.chase_and_shoot(sim.obs.astype(np.float32))
+    goals = kicks = 0
+    for t in range(400):
+        g = gpu_state(env)
+        for i in range(n):
+            sim.set_state(i, g[i])
+        act = H.chase_and_shoot(env.obs.cpu().numpy())
         env.step_torch(torch.from_numpy(act))
         sim.step(act)
-        assert_same_step(env, sim, exact=False)
+        # next to the ball the direction to it is ill-conditioned (position error / distance): scale those columns
+        assert_same_step(env, sim, exact=False, angle_scale=0.02)
         goals += int((sim.result == 1).sum())
-    assert goals > 30
-    g, o = gpu_state(env), sim.get_state()
-    assert np.array_equal(g[:, 16:], o[:, 16:])
-    assert H.state_err(g, o) < H.TOL
+        g2, o2 = gpu_state(env), sim.get_state()
+        kicks += int(((g2[:, 19].astype(int) & _abi.FLAG_KICKED) != 0).sum())
+        assert np.array_equal(g2[:, 16:], o2[:, 16:])  # step_number, cycle, episode, collision / kick flags
+        assert H.state_err(g2, o2) < H.TOL
+    assert goals > 20 and kicks > 200
 
 
 def test_shoot_goal_line_and_kickable_edge_cases():

@@ -10,7 +10,7 @@
 #include <new>
 #include <vector>
 
-#include "s2d_reachball.cuh"
+#include "s2d_fullgame.cuh"
 
 using namespace s2d;
 
@@ -98,6 +98,7 @@ int s2d_default_config(S2DConfig* c, int scenario) {
     c->action_space_size = 24;
     c->kick_actions = 8;
   }
+  if (scenario == S2D_SCENARIO_FULLGAME) c->action_mode = S2D_ACT_COMMAND;
   c->min_distance_to_ball = 5.0f;       // :32
   c->goto_dist_thr = 0.5f;
   return s2d_default_server_param(&c->sp);
@@ -110,13 +111,19 @@ static bool config_ok(const S2DConfig* c, char* why, size_t n) {
     return false;
   }
   if (c->num_envs < 1) { snprintf(why, n, "num_envs must be >= 1"); return false; }
-  if (c->scenario != S2D_SCENARIO_REACHBALL && c->scenario != S2D_SCENARIO_SHOOT) {
-    snprintf(why, n, "scenario %d is not available in this build", c->scenario);
+  if (c->scenario < S2D_SCENARIO_REACHBALL || c->scenario > S2D_SCENARIO_FULLGAME) {
+    snprintf(why, n, "scenario %d does not exist", c->scenario);
     return false;
   }
-  const bool mode_ok = c->scenario == S2D_SCENARIO_SHOOT
-                           ? (c->action_mode == S2D_ACT_DISCRETE || c->action_mode == S2D_ACT_COMMAND)
-                           : (c->action_mode >= S2D_ACT_DISCRETE && c->action_mode <= S2D_ACT_COMMAND);
+  if (c->scenario == S2D_SCENARIO_FULLGAME) {
+    if (c->players_per_side < 1 || c->players_per_side > 11) { snprintf(why, n, "players_per_side must be in 1..11"); return false; }
+    if (c->half_time_cycles < 1) { snprintf(why, n, "half_time_cycles must be >= 1"); return false; }
+  }
+  const bool mode_ok = c->scenario == S2D_SCENARIO_FULLGAME
+                           ? c->action_mode == S2D_ACT_COMMAND
+                           : c->scenario == S2D_SCENARIO_SHOOT
+                                 ? (c->action_mode == S2D_ACT_DISCRETE || c->action_mode == S2D_ACT_COMMAND)
+                                 : (c->action_mode >= S2D_ACT_DISCRETE && c->action_mode <= S2D_ACT_COMMAND);
   if (!mode_ok) {
     snprintf(why, n, "action_mode %d is not valid for scenario %d", c->action_mode, c->scenario);
     return false;
@@ -143,10 +150,14 @@ static size_t action_elem_bytes(const S2DConfig* c) {
   }
 }
 
-size_t s2d_state_bytes(const S2DConfig* c) { return c ? static_cast<size_t>(c->num_envs) * kStateBytesPerEnv : 0; }
+size_t s2d_state_bytes(const S2DConfig* c) {
+  if (!c) return 0;
+  if (c->scenario == S2D_SCENARIO_FULLGAME) return FgLayout{c->num_envs, 2 * c->players_per_side}.bytes();
+  return static_cast<size_t>(c->num_envs) * kStateBytesPerEnv;
+}
 size_t s2d_action_bytes(const S2DConfig* c) { return c ? static_cast<size_t>(c->num_envs) * action_elem_bytes(c) : 0; }
 size_t s2d_stats_bytes(const S2DConfig* c) { return c ? sizeof(unsigned long long) * kStatSlots * kStatWords : 0; }
-int s2d_obs_dim(const S2DConfig* c) { return c ? kObsDim : 0; }
+int s2d_obs_dim(const S2DConfig* c) { return !c ? 0 : c->scenario == S2D_SCENARIO_FULLGAME ? kFgObsDim : kObsDim; }
 int s2d_num_players(const S2DConfig* c) {
   if (!c) return 0;
   return c->scenario == S2D_SCENARIO_FULLGAME ? 2 * c->players_per_side : 1;
@@ -184,7 +195,9 @@ int s2d_create(const S2DConfig* cfg, S2DHandle* out) {
     return S2D_ERR_CUDA;
   }
   kp.action_table = h->d_table;
-  h->grid = static_cast<int>((cfg->num_envs + kBlock - 1) / kBlock);
+  h->grid = cfg->scenario == S2D_SCENARIO_FULLGAME
+                ? static_cast<int>((cfg->num_envs + (kFgBlock / 32) - 1) / (kFgBlock / 32))
+                : static_cast<int>((cfg->num_envs + kBlock - 1) / kBlock);
   *out = h;
   return S2D_OK;
 }
@@ -224,7 +237,10 @@ int s2d_reset(S2DHandle h, const uint8_t* device_mask_or_null, void* stream) {
   if (!h) return S2D_ERR_INVALID;
   if (!h->bound) return fail(h, S2D_ERR_UNBOUND, "s2d_bind has not been called");
   DeviceGuard guard(h->cfg.device);
-  if (h->cfg.scenario == S2D_SCENARIO_SHOOT)
+  if (h->cfg.scenario == S2D_SCENARIO_FULLGAME)
+    fullgame_reset_kernel<<<h->grid, kFgBlock, 0, static_cast<cudaStream_t>(stream)>>>(
+        h->kp, device_mask_or_null, 2 * h->cfg.players_per_side, h->cfg.half_time_cycles);
+  else if (h->cfg.scenario == S2D_SCENARIO_SHOOT)
     reset_kernel<S2D_SCENARIO_SHOOT><<<h->grid, kBlock, 0, static_cast<cudaStream_t>(stream)>>>(h->kp, device_mask_or_null);
   else
     reset_kernel<S2D_SCENARIO_REACHBALL><<<h->grid, kBlock, 0, static_cast<cudaStream_t>(stream)>>>(h->kp, device_mask_or_null);
@@ -244,7 +260,11 @@ int s2d_step(S2DHandle h, int k_substeps, void* stream) {
     if (h->default_sp) step_kernel<SCN, ACT, true><<<h->grid, kBlock, 0, s>>>(h->kp, k_substeps);   \
     else step_kernel<SCN, ACT, false><<<h->grid, kBlock, 0, s>>>(h->kp, k_substeps);                \
   } while (0)
-  if (h->cfg.scenario == S2D_SCENARIO_SHOOT) {
+  if (h->cfg.scenario == S2D_SCENARIO_FULLGAME) {
+    const int np = 2 * h->cfg.players_per_side, ht = h->cfg.half_time_cycles;
+    if (h->default_sp) fullgame_step_kernel<true><<<h->grid, kFgBlock, 0, s>>>(h->kp, k_substeps, np, ht);
+    else fullgame_step_kernel<false><<<h->grid, kFgBlock, 0, s>>>(h->kp, k_substeps, np, ht);
+  } else if (h->cfg.scenario == S2D_SCENARIO_SHOOT) {
     if (h->cfg.action_mode == S2D_ACT_DISCRETE) S2D_LAUNCH(S2D_SCENARIO_SHOOT, S2D_ACT_DISCRETE);
     else S2D_LAUNCH(S2D_SCENARIO_SHOOT, S2D_ACT_COMMAND);
   } else {
@@ -274,7 +294,7 @@ int s2d_step_host(S2DHandle h, int k_substeps, const void* h_actions, float* h_o
   S2D_CUDA(h, cudaMemcpyAsync(h->buf.actions, h_actions, s2d_action_bytes(&h->cfg) * k_substeps, cudaMemcpyHostToDevice, s));
   const int rc = s2d_step(h, k_substeps, stream);
   if (rc != S2D_OK) return rc;
-  if (h_obs) S2D_CUDA(h, cudaMemcpyAsync(h_obs, h->buf.obs, n * kObsDim * sizeof(float), cudaMemcpyDeviceToHost, s));
+  if (h_obs) S2D_CUDA(h, cudaMemcpyAsync(h_obs, h->buf.obs, n * s2d_obs_dim(&h->cfg) * sizeof(float), cudaMemcpyDeviceToHost, s));
   if (h_reward) S2D_CUDA(h, cudaMemcpyAsync(h_reward, h->buf.reward, n * sizeof(float), cudaMemcpyDeviceToHost, s));
   if (h_done) S2D_CUDA(h, cudaMemcpyAsync(h_done, h->buf.done, n, cudaMemcpyDeviceToHost, s));
   if (h_result) S2D_CUDA(h, cudaMemcpyAsync(h_result, h->buf.result, n, cudaMemcpyDeviceToHost, s));
@@ -320,10 +340,51 @@ int s2d_export_env(S2DHandle h, int64_t i, S2DEnvSnapshot* out, void* stream) {
   if (i < 0 || i >= h->cfg.num_envs) return fail(h, S2D_ERR_INVALID, "env index %lld out of range", static_cast<long long>(i));
   DeviceGuard guard(h->cfg.device);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  float4 f[4];
-  uint4 u;
   const char* base = static_cast<const char*>(h->buf.state);
   const size_t n = static_cast<size_t>(h->cfg.num_envs);
+  if (h->cfg.scenario == S2D_SCENARIO_FULLGAME) {
+    const int np = 2 * h->cfg.players_per_side, pps = h->cfg.players_per_side;
+    const FgLayout L{h->cfg.num_envs, np};
+    float4 pa[kFgMaxPlayers], pb[kFgMaxPlayers], ball, ef;
+    float pc[kFgMaxPlayers];
+    uint4 ei, ej;
+    const size_t first = static_cast<size_t>(i) * np;
+    S2D_CUDA(h, cudaMemcpyAsync(pa, base + L.pa() + first * 16, static_cast<size_t>(np) * 16, cudaMemcpyDeviceToHost, s));
+    S2D_CUDA(h, cudaMemcpyAsync(pb, base + L.pb() + first * 16, static_cast<size_t>(np) * 16, cudaMemcpyDeviceToHost, s));
+    S2D_CUDA(h, cudaMemcpyAsync(pc, base + L.pc() + first * 4, static_cast<size_t>(np) * 4, cudaMemcpyDeviceToHost, s));
+    S2D_CUDA(h, cudaMemcpyAsync(&ball, base + L.eb() + static_cast<size_t>(i) * 16, 16, cudaMemcpyDeviceToHost, s));
+    S2D_CUDA(h, cudaMemcpyAsync(&ef, base + L.ef() + static_cast<size_t>(i) * 16, 16, cudaMemcpyDeviceToHost, s));
+    S2D_CUDA(h, cudaMemcpyAsync(&ei, base + L.ei() + static_cast<size_t>(i) * 16, 16, cudaMemcpyDeviceToHost, s));
+    S2D_CUDA(h, cudaMemcpyAsync(&ej, base + L.ej() + static_cast<size_t>(i) * 16, 16, cudaMemcpyDeviceToHost, s));
+    S2D_CUDA(h, cudaStreamSynchronize(s));
+    memset(out, 0, sizeof(*out));
+    out->step_number = static_cast<int32_t>(ei.x);
+    out->cycle = static_cast<int32_t>(ei.y);
+    out->episode = static_cast<int32_t>(ei.z);
+    out->game_mode_type = static_cast<int32_t>(ei.w & 0xff);
+    out->game_mode_side = static_cast<int32_t>((ei.w >> 8) & 3);
+    out->stoped_cycle = static_cast<int32_t>((ei.w >> 12) & 0xff);  // cycles the current dead ball has waited
+    out->ball_collided = static_cast<int32_t>((ei.w >> 20) & 1);
+    out->flags = static_cast<int32_t>(((ei.w >> 21) & 1) ? S2D_FLAG_DONE : 0) | (out->ball_collided ? S2D_FLAG_BALL_COLLIDED : 0);
+    out->left_score = static_cast<int32_t>(ej.x);
+    out->right_score = static_cast<int32_t>(ej.y);
+    out->ball_x = ball.x; out->ball_y = ball.y; out->ball_vx = ball.z; out->ball_vy = ball.w;
+    out->episode_return = ef.x;
+    out->num_players = np;
+    for (int j = 0; j < np; ++j) {
+      S2DPlayerSnapshot& q = out->players[j];
+      q.x = pa[j].x; q.y = pa[j].y; q.vx = pa[j].z; q.vy = pa[j].w;
+      q.body_direction = pb[j].x; q.stamina = pb[j].y; q.effort = pb[j].z; q.recovery = pb[j].w;
+      q.stamina_capacity = pc[j];
+      q.side = j < pps ? S2D_SIDE_LEFT : S2D_SIDE_RIGHT;
+      q.uniform_number = (j < pps ? j : j - pps) + 1;
+      q.collided = (ej.z >> j) & 1;
+      q.kicked = (ej.w >> j) & 1;
+    }
+    return S2D_OK;
+  }
+  float4 f[4];
+  uint4 u;
   for (int p = 0; p < 4; ++p)
     S2D_CUDA(h, cudaMemcpyAsync(&f[p], base + (p * n + static_cast<size_t>(i)) * 16, 16, cudaMemcpyDeviceToHost, s));
   S2D_CUDA(h, cudaMemcpyAsync(&u, base + (4 * n + static_cast<size_t>(i)) * 16, 16, cudaMemcpyDeviceToHost, s));
@@ -357,6 +418,7 @@ int s2d_launch_info(S2DHandle h, int* grid, int* block, int* kernels_per_step) {
   if (grid) *grid = h->grid;
   if (block) *block = kBlock;
   if (kernels_per_step) *kernels_per_step = 1;
+  if (block && h->cfg.scenario == S2D_SCENARIO_FULLGAME) *block = kFgBlock;
   return S2D_OK;
 }
 

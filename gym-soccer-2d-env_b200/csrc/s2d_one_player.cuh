@@ -88,7 +88,7 @@ S2D_HD void dash_direction(float dir, const SP& sp, float& snapped, float& rate)
 // dash_power_rate.  Gives the player's acceleration (it is the only contribution in a cycle).
 template <class SP>
 __device__ __forceinline__ void dash_apply(Episode& e, float power, float dir, float rate, const SP& sp, float& ax,
-                                           float& ay) {
+                                           float& ay, bool left_team = true) {
   power = clampf(sp.min_dash_power(), power, sp.max_dash_power());
   const bool back = power < 0.0f;
   float need = back ? power * -2.0f : power;
@@ -96,7 +96,7 @@ __device__ __forceinline__ void dash_apply(Episode& e, float power, float dir, f
   e.stamina = fmax_(0.0f, e.stamina - need);
   power = back ? need * -0.5f : need;
   float eff = fabsf(e.effort * power * rate * sp.dash_power_rate());
-  const float slow = sp.slowness_on_top_for_left_team();  // the single player is on the left team
+  const float slow = left_team ? sp.slowness_on_top_for_left_team() : sp.slowness_on_top_for_right_team();
   if (slow != 1.0f && e.py < 0.0f) eff = cold_div(eff, slow);
   dir = back ? dir + 180.0f : dir;
   float s, c;
@@ -215,9 +215,27 @@ __device__ __forceinline__ void move_object(float& x, float& y, float& vx, float
 
 constexpr float kCollideEps = 1.0e-6f;
 
-// Ball overlapping the player (rare): the ball goes back along its own velocity until the two just touch; if
-// it is not moving (or the line misses), it is pushed out radially.  The player keeps its place.  Up to ten
-// relaxation rounds as in the server, then both objects that collided get vel *= -0.1.
+// Where the ball goes when it overlaps a player: back along its own velocity until the two are `rr` apart; if it is
+// not moving (or that line misses), straight out along the line of centres.
+__device__ __forceinline__ float2 ball_back_trace(float px, float py, float bx, float by, float bvx, float bvy, float rr) {
+  const float dx = bx - px, dy = by - py;
+  const float v = hypot2(bvx, bvy);
+  if (v > 1.0e-10f) {
+    const float ux = bvx / v, uy = bvy / v;
+    const float du = dx * ux + dy * uy;
+    const float disc = du * du - (dx * dx + dy * dy - rr * rr);
+    if (disc >= 0.0f) {
+      const float t = du + sqrtf(disc);
+      if (t >= 0.0f) return make_float2(bx - t * ux, by - t * uy);
+    }
+  }
+  const float d = hypot2(dx, dy);
+  if (d < 1.0e-10f) return make_float2(px + rr, py);
+  return make_float2(px + dx / d * rr, py + dy / d * rr);
+}
+
+// Ball overlapping the single player (rare): up to ten relaxation rounds as in the server; the player keeps its
+// place (the average of its proposals is its own position).  The caller applies vel *= -0.1 to both.
 __device__ __noinline__ float2 resolve_ball_player_overlap(float px, float py, float bx, float by, float bvx, float bvy,
                                                            float r) {
   const float r2 = r * r;
@@ -226,38 +244,16 @@ __device__ __noinline__ float2 resolve_ball_player_overlap(float px, float py, f
   for (int round = 0; round < 10; ++round) {
     const float dx = bx - px, dy = by - py;
     if (!(dx * dx + dy * dy < r2)) break;
-    const float v = hypot2(bvx, bvy);
-    bool placed = false;
-    if (v > 1.0e-10f) {
-      const float ux = bvx / v, uy = bvy / v;
-      const float du = dx * ux + dy * uy;
-      const float disc = du * du - (dx * dx + dy * dy - rr * rr);
-      if (disc >= 0.0f) {
-        const float t = du + sqrtf(disc);
-        if (t >= 0.0f) {
-          bx = bx - t * ux;
-          by = by - t * uy;
-          placed = true;
-        }
-      }
-    }
-    if (!placed) {
-      const float d = hypot2(dx, dy);
-      if (d < 1.0e-10f) {
-        bx = px + rr;
-        by = py;
-      } else {
-        bx = px + dx / d * rr;
-        by = py + dy / d * rr;
-      }
-    }
+    const float2 b = ball_back_trace(px, py, bx, by, bvx, bvy, rr);
+    bx = b.x;
+    by = b.y;
   }
   return make_float2(bx, by);
 }
 
+template <class SP>
 // (dx, dy) = ball - player and d2 = dx*dx + dy*dy come from the caller, which re-uses them for the reward when
 // nothing collided (the common case).  Returns true when the ball was moved.
-template <class SP>
 __device__ __forceinline__ bool collide_ball_player(Episode& e, float d2, const SP& sp) {
   uint32_t hit = 0;
   if (d2 < sp.collide_r2()) {

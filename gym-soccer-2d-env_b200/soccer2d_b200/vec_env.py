@@ -31,8 +31,11 @@ SHOOT_DEFAULTS = dict(
     change_ball_position=True, change_ball_velocity=False, ball_position_x=0, ball_position_y=0, ball_speed=0,
     ball_direction=0, max_steps=200, action_space_size=24, kick_actions=8)
 
-_SCENARIOS = {"reachball": _abi.SCENARIO_REACHBALL, "shoot": _abi.SCENARIO_SHOOT}
-_DEFAULTS = {"reachball": REACHBALL_DEFAULTS, "shoot": SHOOT_DEFAULTS}
+# full match, up to 11 v 11 (BASELINE configs[3]; spec in include/soccer2d.h): command actions for every player
+FULLGAME_DEFAULTS = dict(players_per_side=11, half_time_cycles=3000)
+
+_SCENARIOS = {"reachball": _abi.SCENARIO_REACHBALL, "shoot": _abi.SCENARIO_SHOOT, "fullgame": _abi.SCENARIO_FULLGAME}
+_DEFAULTS = {"reachball": REACHBALL_DEFAULTS, "shoot": SHOOT_DEFAULTS, "fullgame": FULLGAME_DEFAULTS}
 
 
 def _stream_ptr(device) -> int:
@@ -93,24 +96,30 @@ class Soccer2DVecEnv:
         cfg.env_id_offset = self.env_id_offset
         cfg.seed = self.seed_value & 0xFFFFFFFFFFFFFFFF
         cfg.device = self.device.index
+        self.num_players = 1
+        if self.scenario == "fullgame":
+            use_command_action = True
+            cfg.players_per_side = int(self.kw["players_per_side"])
+            cfg.half_time_cycles = int(self.kw["half_time_cycles"])
+            self.num_players = 2 * cfg.players_per_side
         if use_command_action:
             cfg.action_mode = _abi.ACT_COMMAND
         elif self.kw.get("use_continuous_action", False):
             cfg.action_mode = _abi.ACT_TURNING if self.kw["use_turning"] else _abi.ACT_CONTINUOUS
         else:
             cfg.action_mode = _abi.ACT_DISCRETE
-        cfg.action_space_size = int(self.kw["action_space_size"])
+        cfg.action_space_size = int(self.kw.get("action_space_size", 16))
         cfg.kick_actions = int(self.kw.get("kick_actions", 0))
         cfg.goto_dist_thr = float(goto_dist_thr)
-        cfg.max_steps = int(self.kw["max_steps"])
+        cfg.max_steps = int(self.kw.get("max_steps", 200))
         cfg.auto_reset = int(self.auto_reset)
-        cfg.change_ball_position = int(bool(self.kw["change_ball_position"]))
-        cfg.change_ball_velocity = int(bool(self.kw["change_ball_velocity"]))
+        cfg.change_ball_position = int(bool(self.kw.get("change_ball_position", True)))
+        cfg.change_ball_velocity = int(bool(self.kw.get("change_ball_velocity", False)))
         cfg.min_distance_to_ball = float(self.kw.get("min_distance_to_ball", 5.0))
-        cfg.ball_position_x = float(self.kw["ball_position_x"])
-        cfg.ball_position_y = float(self.kw["ball_position_y"])
-        cfg.ball_speed = float(self.kw["ball_speed"])
-        cfg.ball_direction = float(self.kw["ball_direction"])
+        cfg.ball_position_x = float(self.kw.get("ball_position_x", 0))
+        cfg.ball_position_y = float(self.kw.get("ball_position_y", 0))
+        cfg.ball_speed = float(self.kw.get("ball_speed", 0))
+        cfg.ball_direction = float(self.kw.get("ball_direction", 0))
         for k, v in (server_param or {}).items():
             if k not in _abi._SP_FIELDS:
                 raise KeyError(f"unknown ServerParam field {k!r}")
@@ -119,7 +128,11 @@ class Soccer2DVecEnv:
         self.action_mode = cfg.action_mode
 
         # spaces exactly as reach_ball_env.py:39-48
-        if cfg.action_mode == _abi.ACT_COMMAND:  # {cmd, a, b, c}: cmd in 0..4, arguments in metres / degrees / power
+        if self.scenario == "fullgame":  # one command per player
+            lo = np.tile(np.array([0, -180, -180, -180], dtype=np.float32), (self.num_players, 1))
+            hi = np.tile(np.array([4, 180, 180, 180], dtype=np.float32), (self.num_players, 1))
+            self.action_space = Box(low=lo, high=hi, dtype=np.float32)
+        elif cfg.action_mode == _abi.ACT_COMMAND:  # {cmd, a, b, c}: cmd in 0..4, arguments in metres / degrees / power
             self.action_space = Box(low=np.array([0, -180, -180, -180], dtype=np.float32),
                                     high=np.array([4, 180, 180, 180], dtype=np.float32), dtype=np.float32)
         elif cfg.action_mode == _abi.ACT_TURNING:
@@ -129,7 +142,7 @@ class Soccer2DVecEnv:
             self.action_space = Box(low=-1, high=1, shape=(1,), dtype=np.float32)
         else:
             self.action_space = Discrete(cfg.action_space_size)
-        self.observation_space = Box(low=-1, high=1, shape=(10,), dtype=np.float32)
+        self.observation_space = Box(low=-1, high=1, shape=(self.lib.s2d_obs_dim(C.byref(cfg)),), dtype=np.float32)
 
         self.handle = C.c_void_p()
         _abi.check(self.lib.s2d_create(C.byref(cfg), C.byref(self.handle)))
@@ -142,6 +155,8 @@ class Soccer2DVecEnv:
             self.actions = torch.zeros((n, k), dtype=torch.uint8, device=dev)
         elif cfg.action_mode == _abi.ACT_CONTINUOUS:
             self.actions = torch.zeros((n, k), dtype=torch.float32, device=dev)
+        elif self.scenario == "fullgame":
+            self.actions = torch.zeros((n, k, self.num_players, 4), dtype=torch.float32, device=dev)
         else:
             self.actions = torch.zeros((n, k, 4), dtype=torch.float32, device=dev)
         assert self.actions.numel() * self.actions.element_size() == self.lib.s2d_action_bytes(C.byref(cfg)) * k
@@ -306,11 +321,29 @@ class Soccer2DVecEnv:
         return snap
 
     def state_planes(self):
-        """Views of the SoA planes: (float32 [4, N, 4], int32 [N, 4]) - layout in DESIGN.md."""
+        """One-player scenarios: views of the SoA planes (float32 [4, N, 4], int32 [N, 4]) - layout in DESIGN.md."""
+        assert self.scenario != "fullgame", "use export_env / fullgame_planes for the match layout"
         n = self.num_envs
         f = self.state[: 4 * n * 16].view(torch.float32).view(4, n, 4)
         u = self.state[4 * n * 16:].view(torch.int32).view(n, 4)
         return f, u
+
+    def fullgame_planes(self) -> dict:
+        """FULLGAME: views of the planes (layout: csrc/s2d_fullgame.cuh FgLayout)."""
+        assert self.scenario == "fullgame"
+        n, p = self.num_envs, self.num_players
+        off = 0
+        out = {}
+        for name, rows, width, dt in (("pa", n * p, 4, torch.float32), ("pb", n * p, 4, torch.float32)):
+            out[name] = self.state[off:off + rows * width * 4].view(dt).view(n, p, width)
+            off += rows * width * 4
+        out["pc"] = self.state[off:off + n * p * 4].view(torch.float32).view(n, p)
+        off += (n * p * 4 + 15) // 16 * 16
+        for name, dt in (("ball", torch.float32), ("ef", torch.float32), ("ei", torch.int32), ("ej", torch.int32)):
+            out[name] = self.state[off:off + n * 16].view(dt).view(n, 4)
+            off += n * 16
+        assert off == self.state.numel()
+        return out
 
     def state_dict(self) -> dict:
         return {"state": self.state.clone(), "stats": self.stats_buf.clone(), "seed": self.seed_value,

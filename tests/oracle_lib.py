@@ -37,6 +37,10 @@ def lib(kind: str):
         L.s2do_stats.argtypes = [C.c_void_p, C.c_void_p]
         L.s2do_get_state.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
         L.s2do_set_state.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
+        L.s2do_obs_dim.argtypes = [C.c_void_p]
+        L.s2do_get_state_fg.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
+        L.s2do_set_ball_fg.argtypes = [C.c_void_p, C.c_int64] + [C.c_double] * 4 + [C.c_int] * 3
+        L.s2do_set_player_fg.argtypes = [C.c_void_p, C.c_int64, C.c_int] + [C.c_double] * 5
         L.s2do_probe_sincos_deg.argtypes = [C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.s2do_probe_atan2_deg.restype = C.c_double
         L.s2do_probe_atan2_deg.argtypes = [C.c_double, C.c_double]
@@ -66,8 +70,9 @@ class OracleSim:
         rc = self.L.s2do_create(C.byref(cfg), C.byref(self.h))
         if rc != 0:
             raise ValueError("oracle rejected the config")
-        self.obs = np.zeros((self.n, 10), self.real)
-        self.term_obs = np.zeros((self.n, 10), self.real)
+        self.obs_dim = int(self.L.s2do_obs_dim(self.h))
+        self.obs = np.zeros((self.n, self.obs_dim), self.real)
+        self.term_obs = np.zeros((self.n, self.obs_dim), self.real)
         self.reward = np.zeros(self.n, self.real)
         self.done = np.zeros(self.n, np.uint8)
         self.result = np.zeros(self.n, np.uint8)
@@ -106,6 +111,15 @@ class OracleSim:
             return np.stack([self.get_state(j) for j in range(self.n)])
         out = np.zeros(20, np.float64)
         self.L.s2do_get_state(self.h, int(i), _ptr(out))
+        return out
+
+    def get_state_fg(self, i=None):
+        """FULLGAME: [np*12 + 5 + 11] doubles per env (layout: s2do_get_state_fg)."""
+        if i is None:
+            return np.stack([self.get_state_fg(j) for j in range(self.n)])
+        np_ = 2 * int(self.cfg.players_per_side)
+        out = np.zeros(np_ * 12 + 16, np.float64)
+        assert self.L.s2do_get_state_fg(self.h, int(i), _ptr(out)) == out.size
         return out
 
     def set_state(self, i, vec20):

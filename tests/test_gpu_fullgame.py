@@ -1,0 +1,230 @@
+"""GPU: the FULLGAME scenario (BASELINE configs[3], up to 11 v 11, one warp per match) against the CPU oracle:
+bit for bit against its fp32 build, cycle by cycle against its f64 build."""
+import numpy as np
+import pytest
+import torch
+
+import helpers as H
+import oracle_lib as OL
+from soccer2d_b200 import Soccer2DVecEnv, _abi
+
+pytestmark = pytest.mark.gpu
+
+
+def swarm_policy(obs, np_players, rng=None, random_frac=0.0):
+    """every player runs to the ball (Body_GoToPoint) and kicks it towards the opponents' goal when within 1 m"""
+    obs = np.asarray(obs, np.float64)
+    n = obs.shape[0]
+    pps = np_players // 2
+    a = np.zeros((n, 1, np_players, 4), np.float32)
+    bx, by = obs[:, 0] * 52.5, obs[:, 1] * 34.0
+    P = obs[:, 4:4 + 5 * np_players].reshape(n, np_players, 5)
+    px, py, body = P[:, :, 0] * 52.5, P[:, :, 1] * 34.0, P[:, :, 4] * 180.0
+    d = np.hypot(bx[:, None] - px, by[:, None] - py)
+    gx = np.where(np.arange(np_players) < pps, 52.5, -52.5)[None, :]
+    gd = np.degrees(np.arctan2(0.0 - by[:, None], gx - bx[:, None])) - body
+    gd = (gd + 180.0) % 360.0 - 180.0
+    near = d < 1.0
+    a[:, 0, :, 0] = np.where(near, 3, 4)
+    a[:, 0, :, 1] = np.where(near, 100.0, bx[:, None])
+    a[:, 0, :, 2] = np.where(near, gd, by[:, None])
+    a[:, 0, :, 3] = np.where(near, 0.0, 100.0)
+    if rng is not None and random_frac > 0:
+        rnd = H.random_commands(rng, n * np_players).reshape(n, 1, np_players, 4)
+        a = np.where(rng.uniform(size=(n, 1, np_players, 1)) < random_frac, rnd, a).astype(np.float32)
+    return a
+
+
+def gpu_state_fg(env):
+    """[N, np*12 + 16] float64 in the layout of s2do_get_state_fg"""
+    pl = {k: v.cpu().numpy() for k, v in env.fullgame_planes().items()}
+    n, p = env.num_envs, env.num_players
+    pps = p // 2
+    out = np.zeros((n, p * 12 + 16))
+    players = out[:, :p * 12].reshape(n, p, 12)
+    players[:, :, 0:4] = pl["pa"]
+    players[:, :, 4:8] = pl["pb"]
+    players[:, :, 8] = pl["pc"]
+    ei, ej = pl["ei"].astype(np.int64) & 0xFFFFFFFF, pl["ej"].astype(np.int64) & 0xFFFFFFFF
+    for j in range(p):
+        players[:, j, 9] = (ej[:, 2] >> j) & 1
+        players[:, j, 10] = (ej[:, 3] >> j) & 1
+        players[:, j, 11] = 1 if j < pps else 2
+    k = p * 12
+    out[:, k:k + 4] = pl["ball"]
+    out[:, k + 4] = (ei[:, 3] >> 20) & 1
+    out[:, k + 5] = pl["ei"][:, 0]
+    out[:, k + 6] = ei[:, 1]
+    out[:, k + 7] = ei[:, 2]
+    out[:, k + 8] = ei[:, 3] & 0xff
+    out[:, k + 9] = (ei[:, 3] >> 8) & 3
+    out[:, k + 10] = (ei[:, 3] >> 12) & 0xff
+    out[:, k + 11] = ej[:, 0]
+    out[:, k + 12] = ej[:, 1]
+    out[:, k + 13] = (ei[:, 3] >> 10) & 3
+    out[:, k + 14] = pl["ef"][:, 0]
+    out[:, k + 15] = (ei[:, 3] >> 21) & 1
+    return out
+
+
+def same_step(env, sim):
+    assert np.array_equal(env.done_u8.cpu().numpy(), sim.done) and np.array_equal(env.result.cpu().numpy(), sim.result)
+    assert np.array_equal(env.obs.cpu().numpy(), sim.obs)
+    assert np.array_equal(env.reward.cpu().numpy(), sim.reward)
+    d = sim.done.astype(bool)
+    if env.terminal_obs is not None and d.any():
+        assert np.array_equal(env.terminal_obs.cpu().numpy()[d], sim.term_obs[d])
+
+
+@pytest.mark.parametrize("pps,k,default_sp", [(11, 1, True), (11, 4, True), (3, 1, True), (11, 1, False)])
+def test_fullgame_bit_exact_against_fp32_oracle(pps, k, default_sp):
+    n = 131
+    sp = None if default_sp else dict(player_decay=0.45, kickable_margin=0.8, slowness_on_top_for_right_team=1.1,
+                                     ball_decay=0.95, kick_power_rate=0.03)
+    env = Soccer2DVecEnv(n, scenario="fullgame", device="cuda:0", seed=5, substeps=k, terminal_obs=True,
+                         players_per_side=pps, half_time_cycles=120, server_param=sp)
+    p = 2 * pps
+    assert env.obs.shape == (n, 120) and env.actions.shape == (n, k, p, 4)
+    sim = OL.OracleSim(env.cfg, "f32")
+    assert np.array_equal(env.reset(), sim.reset())
+    assert np.array_equal(gpu_state_fg(env), sim.get_state_fg())
+    rng = np.random.default_rng(0)
+    modes = set()
+    for t in range(600 // k):
+        act = np.repeat(swarm_policy(sim.obs, p, rng, random_frac=0.15), k, axis=1)
+        env.step_torch(torch.from_numpy(act))
+        sim.step(act.reshape(n, -1), k)
+        same_step(env, sim)
+        modes |= set(sim.obs[:, 114].astype(int).tolist())
+        if t % 25 == 24:
+            assert np.array_equal(gpu_state_fg(env), sim.get_state_fg())
+    assert np.array_equal(gpu_state_fg(env), sim.get_state_fg())
+    st, so = env.stats(), sim.stats(_abi.Stats())
+    for key in ("episodes", "goals", "outs", "timeouts", "episode_steps", "env_steps"):
+        assert st[key] == getattr(so, key), key
+    assert st["return_sum"] == pytest.approx(so.return_sum, rel=1e-9)
+    assert st["episodes"] == 2 * n if k == 1 else st["episodes"] >= n
+    assert _abi.RESULT_NAMES and {2, 3} <= modes  # PlayOn and KickOff at least
+    total_goals = int(sim.get_state_fg()[:, p * 12 + 11:p * 12 + 13].sum())
+    assert total_goals >= 0
+
+
+def test_fullgame_referee_and_collision_cases():
+    """Hand-placed balls and players: kick-in, corner kick, goal kick, goals at both ends, dead-ball rules (the
+    other side's kick is ignored, the awarded side's kick resumes play, drop ball after 100 cycles), two players
+    on the same spot, a pile-up around the ball."""
+    line = 52.5 + 0.085
+    #        ball x, y, vx, vy, play_mode, mode_side, last_touch
+    cases = [
+        (10.0, 34.0, 0.0, 0.5, 2, 0, 1),      # 0 over the side line, last touched by left -> KickIn right
+        (-5.0, -34.0, 0.2, -0.5, 2, 0, 2),    # 1 other side line, last touched by right -> KickIn left
+        (line - 0.2, 20.0, 1.0, 0.0, 2, 0, 2),  # 2 over the right goal line, defender (right) touched -> corner for left
+        (line - 0.2, -20.0, 1.0, 0.0, 2, 0, 1),  # 3 attacker (left) touched -> goal kick for right
+        (line - 0.2, 3.0, 1.0, 0.1, 2, 0, 1),   # 4 into the right goal -> left scores, kick-off for right
+        (-line + 0.2, -3.0, -1.0, 0.0, 2, 0, 2),  # 5 into the left goal -> right scores
+        (0.0, 0.0, 0.0, 0.0, 4, 1, 0),          # 6 kick-in for left: right player's kick is ignored, left's resumes
+        (0.0, 0.0, 0.0, 0.0, 5, 2, 0),          # 7 free kick for right, nobody kicks -> drop ball after 100 cycles
+        (20.0, 10.0, 0.0, 0.0, 2, 0, 0),        # 8 two players on the same spot + a third overlapping
+        (-20.0, -10.0, 1.5, 0.5, 2, 0, 0),      # 9 pile-up: four players overlapping the moving ball
+    ]
+    n = len(cases)
+    env = Soccer2DVecEnv(n, scenario="fullgame", device="cuda:0", seed=9, half_time_cycles=1000, terminal_obs=True)
+    sim = OL.OracleSim(env.cfg, "f32")
+    env.reset_torch()
+    sim.reset()
+    pl = env.fullgame_planes()
+
+    def put_ball(i, x, y, vx, vy, mode, side, touch):
+        sim.L.s2do_set_ball_fg(sim.h, i, x, y, vx, vy, mode, side, touch)
+        pl["ball"][i] = torch.tensor([x, y, vx, vy], device="cuda")
+        pl["ei"][i, 3] = mode | (side << 8) | (touch << 10)
+
+    def put_player(i, j, x, y, vx, vy, body):
+        sim.L.s2do_set_player_fg(sim.h, i, j, x, y, vx, vy, body)
+        pl["pa"][i, j] = torch.tensor([x, y, vx, vy], device="cuda")
+        pl["pb"][i, j, 0] = body
+
+    for i, c in enumerate(cases):
+        put_ball(i, *c)
+    put_player(6, 12, 0.5, 0.0, 0, 0, 180.0)   # right player next to the dead ball
+    put_player(6, 3, -0.5, 0.0, 0, 0, 0.0)     # left player next to it
+    put_player(8, 1, 20.0, 10.0, 0.3, 0, 0)
+    put_player(8, 13, 20.0, 10.0, -0.3, 0, 180.0)
+    put_player(8, 2, 20.3, 10.1, 0, 0.1, 90.0)
+    for j, (dx, dy) in zip((4, 5, 15, 16), ((0.2, 0.0), (-0.2, 0.1), (0.0, -0.25), (0.1, 0.2))):
+        put_player(9, j, -20.0 + dx, -10.0 + dy, 0.1, -0.1, 45.0)
+    assert np.array_equal(gpu_state_fg(env), sim.get_state_fg())
+
+    act = np.zeros((n, 1, 22, 4), np.float32)
+    act[6, 0, 12, :3] = [3, 100, 0]  # the right player kicks during the left team's kick-in: ignored
+    env.step_torch(torch.from_numpy(act))
+    sim.step(act.reshape(n, -1))
+    same_step(env, sim)
+    g = gpu_state_fg(env)
+    assert np.array_equal(g, sim.get_state_fg())
+    k = 22 * 12
+    mode, side, sl, sr = g[:, k + 8], g[:, k + 9], g[:, k + 11], g[:, k + 12]
+    assert (mode[0], side[0]) == (_abi_pm("KICK_IN"), 2) and (mode[1], side[1]) == (_abi_pm("KICK_IN"), 1)
+    assert (mode[2], side[2]) == (_abi_pm("CORNER_KICK"), 1) and (mode[3], side[3]) == (_abi_pm("GOAL_KICK"), 2)
+    assert (mode[4], side[4], sl[4], sr[4]) == (_abi_pm("KICK_OFF"), 2, 1, 0)
+    assert (mode[5], side[5], sl[5], sr[5]) == (_abi_pm("KICK_OFF"), 1, 0, 1)
+    assert mode[6] == _abi_pm("KICK_IN") and not g[6, 12 * 12 + 10]  # still a dead ball, no kick registered
+    assert g[8, 1 * 12 + 9] and g[8, 13 * 12 + 9] and g[8, 2 * 12 + 9]  # collided flags
+    assert g[9, k + 4] == 1  # ball collided
+    assert float(env.reward[4]) > 9.9 and float(env.reward[5]) < -9.9
+
+    act[:] = 0
+    act[6, 0, 3, :3] = [3, 60, 0]    # now the left player kicks: play on
+    for t in range(110):
+        env.step_torch(torch.from_numpy(act))
+        sim.step(act.reshape(n, -1))
+        same_step(env, sim)
+        if t == 0:
+            g = gpu_state_fg(env)
+            assert g[6, k + 8] == _abi_pm("PLAY_ON") and g[6, 3 * 12 + 10] == 1
+            assert g[7, k + 8] == 5
+        act[6] = 0
+    g = gpu_state_fg(env)
+    assert np.array_equal(g, sim.get_state_fg())
+    assert g[7, k + 8] == _abi_pm("PLAY_ON")  # dropped after 100 cycles
+    snap = env.export_env(4)
+    assert (snap.left_score, snap.right_score, snap.num_players) == (1, 0, 22)
+    assert snap.players[11].side == 2 and snap.players[11].uniform_number == 1
+
+
+def _abi_pm(name):
+    return {"BEFORE_KICK_OFF": 0, "TIME_OVER": 1, "PLAY_ON": 2, "KICK_OFF": 3, "KICK_IN": 4, "FREE_KICK": 5,
+            "CORNER_KICK": 6, "GOAL_KICK": 7, "AFTER_GOAL": 8}[name]
+
+
+def test_fullgame_against_f64_truth_cycle_by_cycle():
+    """22 players chasing one ball is chaotic (collisions, kicks), so - as for Shoot - the double oracle is compared one
+    cycle ahead from the GPU's state... which it cannot be set to wholesale; instead both run freely for the first 60
+    cycles of a match (before the first contacts amplify rounding) and must agree to 1e-5."""
+    n = 64
+    env = Soccer2DVecEnv(n, scenario="fullgame", device="cuda:0", seed=3, half_time_cycles=500)
+    sim = OL.OracleSim(env.cfg, "f64")
+    assert H.obs_close(env.reset(), sim.reset(), angle_scale=0.0) < H.TOL
+    for t in range(60):
+        act = swarm_policy(sim.obs, 22)
+        env.step_torch(torch.from_numpy(act))
+        sim.step(act.reshape(n, -1))
+        assert np.array_equal(env.done_u8.cpu().numpy(), sim.done)
+        o, w = env.obs.cpu().numpy().astype(np.float64), sim.obs
+        assert np.array_equal(o[:, 114:118], w[:, 114:118])  # play mode, side, scores
+        assert np.abs(o[:, :114] - w[:, :114]).max() < 5 * H.TOL
+        assert np.abs(env.reward.cpu().numpy() - sim.reward).max() < 1e-4
+
+
+def test_fullgame_gym_api():
+    from sample_environments.environment_factory import EnvironmentFactory
+    env = EnvironmentFactory().create("FullGame", None, None, "/tmp", seed=1, players_per_side=5, half_time_cycles=20)
+    assert env.action_space.shape == (10, 4) and env.observation_space.shape == (120,)
+    obs = env.reset()
+    done, steps = False, 0
+    while not done:
+        act = swarm_policy(obs[None], 10)[0, 0]
+        obs, reward, done, info = env.step(act)
+        steps += 1
+    assert steps == 40 and info["result"] in ("Goal", "Out", "Timeout")
+    env.close()

@@ -39,6 +39,7 @@ def lib(kind: str):
         L.s2do_set_state.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
         L.s2do_obs_dim.argtypes = [C.c_void_p]
         L.s2do_get_state_fg.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
+        L.s2do_set_state_fg.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
         L.s2do_set_ball_fg.argtypes = [C.c_void_p, C.c_int64] + [C.c_double] * 4 + [C.c_int] * 3
         L.s2do_set_player_fg.argtypes = [C.c_void_p, C.c_int64, C.c_int] + [C.c_double] * 5
         L.s2do_probe_sincos_deg.argtypes = [C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
@@ -121,6 +122,12 @@ class OracleSim:
         out = np.zeros(np_ * 12 + 16, np.float64)
         assert self.L.s2do_get_state_fg(self.h, int(i), _ptr(out)) == out.size
         return out
+
+    def set_state_fg(self, states):
+        """FULLGAME: overwrite every env's state from an [N, np*12+16] array (layout of get_state_fg)."""
+        st = np.ascontiguousarray(states, dtype=np.float64)
+        for i in range(self.n):
+            self.L.s2do_set_state_fg(self.h, i, _ptr(st[i]))
 
     def set_state(self, i, vec20):
         v = np.ascontiguousarray(vec20, dtype=np.float64)

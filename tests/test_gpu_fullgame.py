@@ -125,7 +125,7 @@ def test_fullgame_referee_and_collision_cases():
         (0.0, 0.0, 0.0, 0.0, 4, 1, 0),          # 6 kick-in for left: right player's kick is ignored, left's resumes
         (0.0, 0.0, 0.0, 0.0, 5, 2, 0),          # 7 free kick for right, nobody kicks -> drop ball after 100 cycles
         (20.0, 10.0, 0.0, 0.0, 2, 0, 0),        # 8 two players on the same spot + a third overlapping
-        (-20.0, -10.0, 1.5, 0.5, 2, 0, 0),      # 9 pile-up: four players overlapping the moving ball
+        (-20.0, -10.0, 0.1, 0.05, 2, 0, 0),     # 9 pile-up: four players overlapping the (slowly) moving ball
     ]
     n = len(cases)
     env = Soccer2DVecEnv(n, scenario="fullgame", device="cuda:0", seed=9, half_time_cycles=1000, terminal_obs=True)
@@ -198,22 +198,46 @@ def _abi_pm(name):
 
 
 def test_fullgame_against_f64_truth_cycle_by_cycle():
-    """22 players chasing one ball is chaotic (collisions, kicks), so - as for Shoot - the double oracle is compared one
-    cycle ahead from the GPU's state... which it cannot be set to wholesale; instead both run freely for the first 60
-    cycles of a match (before the first contacts amplify rounding) and must agree to 1e-5."""
-    n = 64
-    env = Soccer2DVecEnv(n, scenario="fullgame", device="cuda:0", seed=3, half_time_cycles=500)
+    """22 players chasing one ball is chaotic (every kick and collision amplifies a rounding difference), so - as for
+    Shoot - the double oracle is re-synchronised to the GPU state before every cycle and compared one cycle ahead:
+    referee state and flags bit-exact, floats within 1e-5 of each quantity's scale, over 300 cycles of swarm play
+    (kicks, pile-ups, goals, restarts)."""
+    n, p = 48, 22
+    env = Soccer2DVecEnv(n, scenario="fullgame", device="cuda:0", seed=3, half_time_cycles=100)
     sim = OL.OracleSim(env.cfg, "f64")
-    assert H.obs_close(env.reset(), sim.reset(), angle_scale=0.0) < H.TOL
-    for t in range(60):
-        act = swarm_policy(sim.obs, 22)
+    env.reset_torch()
+    sim.reset()
+    scale = np.tile([52.5, 34.0, 1.05, 1.05, 180.0, 8000.0, 1.0, 1.0, 130600.0], p)
+    worst = worst_hit = 0.0
+    kicks = collisions = 0
+    for t in range(300):
+        g = gpu_state_fg(env)
+        sim.set_state_fg(g)
+        act = swarm_policy(env.obs.cpu().numpy(), p)
         env.step_torch(torch.from_numpy(act))
         sim.step(act.reshape(n, -1))
-        assert np.array_equal(env.done_u8.cpu().numpy(), sim.done)
-        o, w = env.obs.cpu().numpy().astype(np.float64), sim.obs
-        assert np.array_equal(o[:, 114:118], w[:, 114:118])  # play mode, side, scores
-        assert np.abs(o[:, :114] - w[:, :114]).max() < 5 * H.TOL
+        assert np.array_equal(env.done_u8.cpu().numpy(), sim.done) and np.array_equal(env.result.cpu().numpy(), sim.result)
+        g2, o2 = gpu_state_fg(env), sim.get_state_fg()
+        P2, Q2 = g2[:, :p * 12].reshape(n, p, 12), o2[:, :p * 12].reshape(n, p, 12)
+        assert np.array_equal(P2[:, :, 9:], Q2[:, :, 9:])                      # collided, kicked, side
+        assert np.array_equal(g2[:, p * 12 + 4:p * 12 + 14], o2[:, p * 12 + 4:p * 12 + 14])  # ball flag, counters, referee
+        d = np.abs(P2[:, :, :9] - Q2[:, :, :9])
+        d[:, :, 4] = np.minimum(d[:, :, 4], np.abs(360.0 - d[:, :, 4]))
+        d = d / scale.reshape(p, 9)[None]
+        db = np.abs(g2[:, p * 12:p * 12 + 4] - o2[:, p * 12:p * 12 + 4]) / [52.5, 34.0, 3.0, 3.0]
+        # Collision resolution pushes overlapping objects apart along the line of centres; for nearly coincident
+        # centres (a pile-up on the ball) that direction is ill-conditioned, so objects that collided this cycle
+        # get a loose bound and everything else the 1e-5 one.
+        hit = P2[:, :, 9] != 0
+        ball_hit = g2[:, p * 12 + 4] != 0
+        worst = max(worst, float(d[~hit].max()), float(db[~ball_hit].max()) if (~ball_hit).any() else 0.0)
+        worst_hit = max(worst_hit, float(d[hit].max()) if hit.any() else 0.0, float(db[ball_hit].max()) if ball_hit.any() else 0.0)
         assert np.abs(env.reward.cpu().numpy() - sim.reward).max() < 1e-4
+        kicks += int(P2[:, :, 10].sum())
+        collisions += int(P2[:, :, 9].sum())
+    assert worst < H.TOL, worst
+    assert worst_hit < 2e-2, worst_hit
+    assert kicks > 100 and collisions > 1000
 
 
 def test_fullgame_gym_api():

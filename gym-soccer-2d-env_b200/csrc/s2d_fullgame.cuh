@@ -88,6 +88,25 @@ __device__ __forceinline__ int fg_collisions(Episode& p, bool active, int lane, 
   const float h = r2 / 2.0f + kCollideEps;
 #pragma unroll 1
   for (int round = 0; round < 10; ++round) {
+    // Broad phase: does anything overlap at all?  Lane i tests the ball and the partners (i + d) mod np for
+    // d = 1..np/2, which covers every unordered pair in half the iterations of the ordered loop below.  The
+    // predicates are the very same expressions, so skipping the narrow phase changes nothing when they are all false.
+    {
+      bool overlap = false;
+      if (active && !ball_fixed) {
+        const float dx = p.bx - p.px, dy = p.by - p.py;
+        overlap = dx * dx + dy * dy < r * r;
+      }
+#pragma unroll 1
+      for (int d = 1; d <= (np >> 1); ++d) {
+        int j = lane + d;
+        j = j >= np ? j - np : j;
+        const float xj = __shfl_sync(full, p.px, j & 31), yj = __shfl_sync(full, p.py, j & 31);
+        const float ex = p.px - xj, ey = p.py - yj;
+        overlap = overlap || (active && ex * ex + ey * ey < r2 * r2);
+      }
+      if (!__any_sync(full, overlap)) break;
+    }
     bool col = false;
     int cnt = 0;
     float sx = 0.0f, sy = 0.0f, bpx = 0.0f, bpy = 0.0f;
@@ -380,11 +399,14 @@ __device__ __forceinline__ void fg_store(const KernelParams& P, const FgLayout& 
   }
 }
 
+#ifndef S2D_FG_MIN_BLOCKS
+#define S2D_FG_MIN_BLOCKS 8
+#endif
 constexpr int kFgBlock = 128;  // 4 matches per block
 
 // K lockstep cycles of every match; actions float4 [N][K][np].
 template <bool DEF>
-__global__ void __launch_bounds__(kFgBlock) fullgame_step_kernel(const __grid_constant__ KernelParams P, const int K,
+__global__ void __launch_bounds__(kFgBlock, S2D_FG_MIN_BLOCKS) fullgame_step_kernel(const __grid_constant__ KernelParams P, const int K,
                                                                  const int np, const int half_time) {
   using SP = typename std::conditional<DEF, DefaultSP, RuntimeSP>::type;
   const SP sp(P.cc);

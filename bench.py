@@ -239,10 +239,13 @@ def run_b200(args, rank, local_rank, world):
     value = world * n * k * args.steps / (total_ms * 1e-3)
     launch_ms = sum(ms) / len(ms)
 
-    # ---- e2e: host buffers through s2d_step_host ----------------------------------------------------
+    # ---- e2e: host buffers, every step's actions H2D and results D2H inside the timed region --------------
     hb = env.host_buffers()
     host_pool = [p.cpu().pin_memory() for p in pool[:2]]
     e2e_steps = max(3, min(args.steps, 30))
+    h2d = pool[0].numel() * pool[0].element_size()
+    d2h = sum(hb[x].numel() * hb[x].element_size() for x in ("obs", "reward", "done", "result"))
+    # (a) synchronous call: s2d_step_host, one step at a time (H2D -> kernel -> D2H -> host reads the reward)
     for i in range(3):
         env.step_host(host_pool[i % 2])
     barrier()
@@ -250,13 +253,30 @@ def run_b200(args, rank, local_rank, world):
     checksum = 0.0
     for i in range(e2e_steps):
         _, reward, _, _ = env.step_host(host_pool[i % 2])
-        checksum += float(reward[0])  # the host reads the step's result
+        checksum += float(reward[0])
+    torch.cuda.synchronize()
+    e2e_sync_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    # (b) pipelined call: s2d_submit_host / s2d_wait_host, two steps in flight - the copies of one step overlap
+    #     the kernel and the copies of the next; the host still reads every step's result
+    env.enable_pipeline()
+    t = env.submit_host(host_pool[0])
+    env.wait_host(t)
+    barrier()
+    t0 = time.perf_counter()
+    ticket = env.submit_host(host_pool[0])
+    for i in range(1, e2e_steps):
+        nxt = env.submit_host(host_pool[i % 2])
+        _, reward, _, _ = env.wait_host(ticket)
+        checksum += float(reward[0])
+        ticket = nxt
+    _, reward, _, _ = env.wait_host(ticket)
+    checksum += float(reward[0])
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     barrier()
     e2e_value = world * n * k * e2e_steps / e2e_s
-    h2d = pool[0].numel() * pool[0].element_size()
-    d2h = sum(hb[x].numel() * hb[x].element_size() for x in ("obs", "reward", "done", "result"))
+    e2e_sync_value = world * n * k * e2e_steps / e2e_sync_s
 
     stats = env.allreduce_stats()  # NCCL all-reduce of the episode statistics (the only collective)
     env.close()
@@ -317,7 +337,10 @@ def run_b200(args, rank, local_rank, world):
             "timing": "sum of per-launch CUDA-event durations on the launching stream, max over ranks"}),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3,
-                "path": "Soccer2DVecEnv.step_host -> s2d_step_host (pinned host actions in, obs/reward/done/result out)"},
+                "path": "Soccer2DVecEnv.submit_host / wait_host -> s2d_submit_host / s2d_wait_host: pinned host actions in, "
+                        "obs/reward/done/result out, two steps in flight (copies overlap the kernel)",
+                "synchronous": {"value": e2e_sync_value, "ms_per_step": e2e_sync_s / e2e_steps * 1e3,
+                                "path": "Soccer2DVecEnv.step_host -> s2d_step_host, one step at a time"}},
         "gpu_launches": args.steps,
         "roofline": {"bound": "hbm", "achieved": ach16, "peak": peak, "unit": "GB/s", "frac": ach16 / peak,
                      "traffic": load_traffic(f"k{k}", n),

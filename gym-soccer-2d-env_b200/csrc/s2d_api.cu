@@ -21,6 +21,13 @@ struct S2DSim {
   float4* d_table = nullptr;
   bool default_sp = false;  // cfg.sp == rcssserver defaults: use the constant-folded kernels
   bool bound = false;
+  // host-buffer pipeline (s2d_bind_pipeline / s2d_submit_host / s2d_wait_host): two slots of actions + outputs
+  bool piped = false;
+  S2DBuffers pbuf[2];
+  KernelParams pkp[2];
+  cudaStream_t st_in = nullptr, st_compute = nullptr, st_out = nullptr;
+  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_kernel[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+  bool used[2] = {false, false};
   int grid = 0;
   uint64_t env_steps = 0;
   char err[512];
@@ -207,6 +214,19 @@ int s2d_destroy(S2DHandle h) {
   {
     DeviceGuard guard(h->cfg.device);
     if (h->d_table) cudaFree(h->d_table);
+    if (h->st_in) {
+      cudaStreamSynchronize(h->st_in);
+      cudaStreamSynchronize(h->st_compute);
+      cudaStreamSynchronize(h->st_out);
+      for (int k = 0; k < 2; ++k) {
+        cudaEventDestroy(h->ev_in[k]);
+        cudaEventDestroy(h->ev_kernel[k]);
+        cudaEventDestroy(h->ev_out[k]);
+      }
+      cudaStreamDestroy(h->st_in);
+      cudaStreamDestroy(h->st_compute);
+      cudaStreamDestroy(h->st_out);
+    }
   }
   delete h;
   return S2D_OK;
@@ -248,22 +268,17 @@ int s2d_reset(S2DHandle h, const uint8_t* device_mask_or_null, void* stream) {
   return S2D_OK;
 }
 
-int s2d_step(S2DHandle h, int k_substeps, void* stream) {
-  if (!h) return S2D_ERR_INVALID;
-  if (!h->bound) return fail(h, S2D_ERR_UNBOUND, "s2d_bind has not been called");
-  if (k_substeps < 1 || k_substeps > kMaxSubsteps)
-    return fail(h, S2D_ERR_INVALID, "k_substeps must be in 1..%d", kMaxSubsteps);
-  DeviceGuard guard(h->cfg.device);
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-#define S2D_LAUNCH(SCN, ACT)                                                                        \
-  do {                                                                                              \
-    if (h->default_sp) step_kernel<SCN, ACT, true><<<h->grid, kBlock, 0, s>>>(h->kp, k_substeps);   \
-    else step_kernel<SCN, ACT, false><<<h->grid, kBlock, 0, s>>>(h->kp, k_substeps);                \
+// one launch of the scenario's step kernel with the given parameter block
+static cudaError_t launch_step(S2DSim* h, const KernelParams& kp, int k_substeps, cudaStream_t s) {
+#define S2D_LAUNCH(SCN, ACT)                                                                   \
+  do {                                                                                         \
+    if (h->default_sp) step_kernel<SCN, ACT, true><<<h->grid, kBlock, 0, s>>>(kp, k_substeps); \
+    else step_kernel<SCN, ACT, false><<<h->grid, kBlock, 0, s>>>(kp, k_substeps);              \
   } while (0)
   if (h->cfg.scenario == S2D_SCENARIO_FULLGAME) {
     const int np = 2 * h->cfg.players_per_side, ht = h->cfg.half_time_cycles;
-    if (h->default_sp) fullgame_step_kernel<true><<<h->grid, kFgBlock, 0, s>>>(h->kp, k_substeps, np, ht);
-    else fullgame_step_kernel<false><<<h->grid, kFgBlock, 0, s>>>(h->kp, k_substeps, np, ht);
+    if (h->default_sp) fullgame_step_kernel<true><<<h->grid, kFgBlock, 0, s>>>(kp, k_substeps, np, ht);
+    else fullgame_step_kernel<false><<<h->grid, kFgBlock, 0, s>>>(kp, k_substeps, np, ht);
   } else if (h->cfg.scenario == S2D_SCENARIO_SHOOT) {
     if (h->cfg.action_mode == S2D_ACT_DISCRETE) S2D_LAUNCH(S2D_SCENARIO_SHOOT, S2D_ACT_DISCRETE);
     else S2D_LAUNCH(S2D_SCENARIO_SHOOT, S2D_ACT_COMMAND);
@@ -276,8 +291,103 @@ int s2d_step(S2DHandle h, int k_substeps, void* stream) {
     }
   }
 #undef S2D_LAUNCH
-  S2D_CUDA(h, cudaGetLastError());
+  return cudaGetLastError();
+}
+
+int s2d_step(S2DHandle h, int k_substeps, void* stream) {
+  if (!h) return S2D_ERR_INVALID;
+  if (!h->bound) return fail(h, S2D_ERR_UNBOUND, "s2d_bind has not been called");
+  if (k_substeps < 1 || k_substeps > kMaxSubsteps)
+    return fail(h, S2D_ERR_INVALID, "k_substeps must be in 1..%d", kMaxSubsteps);
+  DeviceGuard guard(h->cfg.device);
+  S2D_CUDA(h, launch_step(h, h->kp, k_substeps, static_cast<cudaStream_t>(stream)));
   h->env_steps += static_cast<uint64_t>(h->cfg.num_envs) * static_cast<uint64_t>(k_substeps);
+  return S2D_OK;
+}
+
+// ---- pipelined host-buffer stepping ----------------------------------------------------------------------
+// Slot s owns a device actions buffer and device output buffers (slot 0 = the buffers of s2d_bind, slot 1 = the ones
+// given here).  s2d_submit_host enqueues, on three internal streams, H2D(actions) -> step kernel -> D2H(outputs) for
+// one slot; consecutive submissions alternate slots, so the copies of step i overlap the kernel and the copies of
+// step i+1.  The step kernels themselves stay in submission order (they share the state).
+
+int s2d_bind_pipeline(S2DHandle h, const S2DBuffers* second) {
+  if (!h) return S2D_ERR_INVALID;
+  if (!h->bound) return fail(h, S2D_ERR_UNBOUND, "s2d_bind must come first");
+  if (!second || !second->actions || !second->obs || !second->reward || !second->done || !second->result)
+    return fail(h, S2D_ERR_UNBOUND, "the second slot needs actions, obs, reward, done and result buffers");
+  if ((reinterpret_cast<uintptr_t>(second->actions) & 15) || (reinterpret_cast<uintptr_t>(second->obs) & 15))
+    return fail(h, S2D_ERR_INVALID, "actions / obs must be 16-byte aligned");
+  DeviceGuard guard(h->cfg.device);
+  if (!h->st_in) {
+    S2D_CUDA(h, cudaStreamCreateWithFlags(&h->st_in, cudaStreamNonBlocking));
+    S2D_CUDA(h, cudaStreamCreateWithFlags(&h->st_compute, cudaStreamNonBlocking));
+    S2D_CUDA(h, cudaStreamCreateWithFlags(&h->st_out, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; ++k) {
+      S2D_CUDA(h, cudaEventCreateWithFlags(&h->ev_in[k], cudaEventDisableTiming));
+      S2D_CUDA(h, cudaEventCreateWithFlags(&h->ev_kernel[k], cudaEventDisableTiming));
+      S2D_CUDA(h, cudaEventCreateWithFlags(&h->ev_out[k], cudaEventDisableTiming));
+    }
+  }
+  h->pbuf[0] = h->buf;
+  h->pbuf[1] = h->buf;  // state and stats are shared
+  h->pbuf[1].actions = second->actions;
+  h->pbuf[1].obs = second->obs;
+  h->pbuf[1].reward = second->reward;
+  h->pbuf[1].done = second->done;
+  h->pbuf[1].result = second->result;
+  h->pbuf[1].terminal_obs = second->terminal_obs;
+  for (int k = 0; k < 2; ++k) {
+    h->pkp[k] = h->kp;
+    h->pkp[k].actions = h->pbuf[k].actions;
+    h->pkp[k].obs = h->pbuf[k].obs;
+    h->pkp[k].reward = h->pbuf[k].reward;
+    h->pkp[k].done = h->pbuf[k].done;
+    h->pkp[k].result = h->pbuf[k].result;
+    h->pkp[k].terminal_obs = h->pbuf[k].terminal_obs;
+    h->used[k] = false;
+  }
+  h->piped = true;
+  return S2D_OK;
+}
+
+int s2d_submit_host(S2DHandle h, int k_substeps, int slot, const void* h_actions, float* h_obs, float* h_reward,
+                    uint8_t* h_done, uint8_t* h_result) {
+  if (!h) return S2D_ERR_INVALID;
+  if (!h->piped) return fail(h, S2D_ERR_UNBOUND, "s2d_bind_pipeline has not been called");
+  if (slot < 0 || slot > 1) return fail(h, S2D_ERR_INVALID, "slot must be 0 or 1");
+  if (!h_actions) return fail(h, S2D_ERR_INVALID, "h_actions is NULL");
+  if (k_substeps < 1 || k_substeps > kMaxSubsteps)
+    return fail(h, S2D_ERR_INVALID, "k_substeps must be in 1..%d", kMaxSubsteps);
+  DeviceGuard guard(h->cfg.device);
+  const size_t n = static_cast<size_t>(h->cfg.num_envs);
+  const S2DBuffers& b = h->pbuf[slot];
+  // actions[slot] may be overwritten once the kernel that read them is done; outputs[slot] once their D2H is done
+  if (h->used[slot]) S2D_CUDA(h, cudaStreamWaitEvent(h->st_in, h->ev_kernel[slot], 0));
+  S2D_CUDA(h, cudaMemcpyAsync(b.actions, h_actions, s2d_action_bytes(&h->cfg) * k_substeps, cudaMemcpyHostToDevice, h->st_in));
+  S2D_CUDA(h, cudaEventRecord(h->ev_in[slot], h->st_in));
+  S2D_CUDA(h, cudaStreamWaitEvent(h->st_compute, h->ev_in[slot], 0));
+  if (h->used[slot]) S2D_CUDA(h, cudaStreamWaitEvent(h->st_compute, h->ev_out[slot], 0));
+  S2D_CUDA(h, launch_step(h, h->pkp[slot], k_substeps, h->st_compute));
+  S2D_CUDA(h, cudaEventRecord(h->ev_kernel[slot], h->st_compute));
+  S2D_CUDA(h, cudaStreamWaitEvent(h->st_out, h->ev_kernel[slot], 0));
+  if (h_obs) S2D_CUDA(h, cudaMemcpyAsync(h_obs, b.obs, n * s2d_obs_dim(&h->cfg) * sizeof(float), cudaMemcpyDeviceToHost, h->st_out));
+  if (h_reward) S2D_CUDA(h, cudaMemcpyAsync(h_reward, b.reward, n * sizeof(float), cudaMemcpyDeviceToHost, h->st_out));
+  if (h_done) S2D_CUDA(h, cudaMemcpyAsync(h_done, b.done, n, cudaMemcpyDeviceToHost, h->st_out));
+  if (h_result) S2D_CUDA(h, cudaMemcpyAsync(h_result, b.result, n, cudaMemcpyDeviceToHost, h->st_out));
+  S2D_CUDA(h, cudaEventRecord(h->ev_out[slot], h->st_out));
+  h->used[slot] = true;
+  h->env_steps += static_cast<uint64_t>(h->cfg.num_envs) * static_cast<uint64_t>(k_substeps);
+  return S2D_OK;
+}
+
+int s2d_wait_host(S2DHandle h, int slot) {
+  if (!h) return S2D_ERR_INVALID;
+  if (!h->piped) return fail(h, S2D_ERR_UNBOUND, "s2d_bind_pipeline has not been called");
+  if (slot < 0 || slot > 1) return fail(h, S2D_ERR_INVALID, "slot must be 0 or 1");
+  if (!h->used[slot]) return S2D_OK;
+  DeviceGuard guard(h->cfg.device);
+  S2D_CUDA(h, cudaEventSynchronize(h->ev_out[slot]));
   return S2D_OK;
 }
 

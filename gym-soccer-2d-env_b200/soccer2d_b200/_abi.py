@@ -8,7 +8,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 # ---- constants (mirror include/soccer2d.h) ----------------------------------------------------------
 S2D_OK, S2D_ERR_INVALID, S2D_ERR_UNBOUND, S2D_ERR_CUDA, S2D_ERR_NO_DEVICE = 0, -1, -2, -3, -4
@@ -104,6 +104,9 @@ SIGNATURES = {
     "s2d_reset": (C.c_int, [_H, C.c_void_p, C.c_void_p]),
     "s2d_step": (C.c_int, [_H, C.c_int, C.c_void_p]),
     "s2d_step_host": (C.c_int, [_H, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "s2d_bind_pipeline": (C.c_int, [_H, C.POINTER(Buffers)]),
+    "s2d_submit_host": (C.c_int, [_H, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "s2d_wait_host": (C.c_int, [_H, C.c_int]),
     "s2d_stats": (C.c_int, [_H, C.POINTER(Stats), C.c_void_p]),
     "s2d_stats_reset": (C.c_int, [_H, C.c_void_p]),
     "s2d_export_env": (C.c_int, [_H, C.c_int64, C.POINTER(EnvSnapshot), C.c_void_p]),

@@ -173,6 +173,7 @@ class Soccer2DVecEnv:
             terminal_obs=self.terminal_obs.data_ptr() if terminal_obs else None, stats=self.stats_buf.data_ptr())
         _abi.check(self.lib.s2d_bind(self.handle, C.byref(bufs)), self.handle)
         self._pinned = None
+        self._pipe = None
         self._pending = None
         self._closed = False
 
@@ -236,6 +237,54 @@ class Soccer2DVecEnv:
                                           _stream_ptr(self.device)), self.handle)
         torch.cuda.current_stream(self.device).synchronize()
         return p["obs"].numpy(), p["reward"].numpy(), p["done"].numpy().view(np.bool_), p["result"].numpy()
+
+    # ---- pipelined host API: submit step i+1 while the results of step i are still coming back ---------
+    def enable_pipeline(self) -> None:
+        """Allocate the second slot (device actions + outputs, pinned host outputs) and bind it."""
+        if getattr(self, "_pipe", None) is not None:
+            return
+        dev = self.device
+        like = lambda t: torch.zeros_like(t, device=dev)  # noqa: E731
+        pin = lambda t: torch.empty(t.shape, dtype=t.dtype, pin_memory=True)  # noqa: E731
+        second = dict(actions=like(self.actions), obs=like(self.obs), reward=like(self.reward), done=like(self.done_u8),
+                      result=like(self.result),
+                      terminal_obs=like(self.terminal_obs) if self.terminal_obs is not None else None)
+        b = _abi.Buffers(state=self.state.data_ptr(), actions=second["actions"].data_ptr(), obs=second["obs"].data_ptr(),
+                         reward=second["reward"].data_ptr(), done=second["done"].data_ptr(),
+                         result=second["result"].data_ptr(),
+                         terminal_obs=second["terminal_obs"].data_ptr() if second["terminal_obs"] is not None else None,
+                         stats=self.stats_buf.data_ptr())
+        torch.cuda.current_stream(dev).synchronize()
+        _abi.check(self.lib.s2d_bind_pipeline(self.handle, C.byref(b)), self.handle)
+        host = [dict(obs=pin(self.obs), reward=pin(self.reward), done=pin(self.done_u8), result=pin(self.result))
+                for _ in range(2)]
+        self._pipe = dict(device=second, host=host, next_slot=0, keep=[None, None])
+
+    def submit_host(self, actions) -> int:
+        """Enqueue one step from host `actions` (pinned CPU tensor / numpy array of the action shape) and return
+        its ticket (the slot).  At most two steps can be in flight: wait_host() the older one first."""
+        self.enable_pipeline()
+        pipe = self._pipe
+        slot = pipe["next_slot"]
+        pipe["next_slot"] = 1 - slot
+        if isinstance(actions, torch.Tensor):
+            src = actions.to(dtype=self.actions.dtype).reshape(self.actions.shape).contiguous()
+        else:
+            src = torch.from_numpy(np.ascontiguousarray(np.asarray(actions).reshape(tuple(self.actions.shape))))
+            src = src.to(dtype=self.actions.dtype)
+        pipe["keep"][slot] = src  # keep the host source alive until the copy has happened
+        ho = pipe["host"][slot]
+        _abi.check(self.lib.s2d_submit_host(self.handle, self.substeps, slot, src.data_ptr(), ho["obs"].data_ptr(),
+                                            ho["reward"].data_ptr(), ho["done"].data_ptr(), ho["result"].data_ptr()),
+                   self.handle)
+        return slot
+
+    def wait_host(self, ticket: int):
+        """Block until the step submitted with `ticket` is on the host; returns numpy views of that slot's pinned
+        outputs (valid until the slot is submitted again)."""
+        _abi.check(self.lib.s2d_wait_host(self.handle, int(ticket)), self.handle)
+        ho = self._pipe["host"][ticket]
+        return ho["obs"].numpy(), ho["reward"].numpy(), ho["done"].numpy().view(np.bool_), ho["result"].numpy()
 
     # ---- SB3 VecEnv surface ---------------------------------------------------------------------------
     def reset(self) -> np.ndarray:

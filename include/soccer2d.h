@@ -18,6 +18,8 @@
  *                              + one rcssserver cycle (external)   soccer_2d_env.py:356-383
  *                              + state_to_observation              reach_ball_env.py:87-111
  *                              + check_trainer_observation         reach_ball_env.py:113-161
+ *   s2d_bind_pipeline /        the same step, submitted asynchronously from host buffers (copies overlap compute)
+ *   s2d_submit_host / s2d_wait_host
  *   s2d_stats                  InfoCollectorCallback tallies       utils/info_collector_callback.py:17-53
  *   s2d_export_env             proto State/WorldModel of one env   idl/service.proto:306-359
  *   S2DServerParam             proto ServerParam / PlayerType      idl/service.proto:1435-1732
@@ -40,7 +42,7 @@
 extern "C" {
 #endif
 
-#define S2D_ABI_VERSION 4
+#define S2D_ABI_VERSION 5
 
 /* error codes */
 #define S2D_OK 0
@@ -213,6 +215,18 @@ int s2d_step(S2DHandle h, int k_substeps, void* stream);
  * asynchronously on `stream` (use pinned memory).  Any of the h_* outputs may be NULL to skip that copy. */
 int s2d_step_host(S2DHandle h, int k_substeps, const void* h_actions, float* h_obs, float* h_reward,
                   uint8_t* h_done, uint8_t* h_result, void* stream);
+
+/* Pipelined host-buffer stepping: the copies of one step overlap the kernel and the copies of the next.
+ * s2d_bind_pipeline gives the handle a SECOND set of device actions / obs / reward / done / result (/ terminal_obs)
+ * buffers (slot 1; slot 0 = the buffers of s2d_bind; state and stats are shared).  s2d_submit_host enqueues
+ * H2D(actions) -> step kernel -> D2H(outputs) for one slot on three internal streams and returns at once; alternate
+ * the slots between consecutive submissions and call s2d_wait_host(slot) before reading that slot's host outputs (or
+ * re-using its host action buffer).  Host buffers should be pinned.  Do not mix with s2d_step / s2d_step_host on
+ * other streams without draining both slots first. */
+int s2d_bind_pipeline(S2DHandle h, const S2DBuffers* second_slot);
+int s2d_submit_host(S2DHandle h, int k_substeps, int slot, const void* h_actions, float* h_obs, float* h_reward,
+                    uint8_t* h_done, uint8_t* h_result);
+int s2d_wait_host(S2DHandle h, int slot); /* blocks the calling thread until the slot's outputs are on the host */
 
 int s2d_stats(S2DHandle h, S2DStats* host_out, void* stream);   /* reduces the partials; synchronises */
 int s2d_stats_reset(S2DHandle h, void* stream);

@@ -559,3 +559,31 @@ def test_shoot_gym_api_and_factory():
     vec = EnvironmentFactory().create_vec("shoot", 64, device="cuda:0", use_command_action=True)
     assert vec.actions.shape == (64, 1, 4)
     vec.close()
+
+
+def test_pipelined_host_steps_equal_synchronous_ones():
+    """s2d_bind_pipeline / s2d_submit_host / s2d_wait_host: two steps in flight, results identical to step_host."""
+    n, k = 5000, 4
+    kw = dict(device="cuda:0", seed=12, substeps=k, use_continuous_action=False, change_ball_velocity=True, max_steps=30)
+    a, b = Soccer2DVecEnv(n, **kw), Soccer2DVecEnv(n, **kw)
+    assert np.array_equal(a.reset(), b.reset())
+    rng = np.random.default_rng(0)
+    acts = [torch.from_numpy(H.random_actions(rng, "discrete", n, k)).pin_memory() for _ in range(12)]
+    want = []
+    for act in acts:
+        o, r, d, res = a.step_host(act)
+        want.append((o.copy(), r.copy(), d.copy(), res.copy()))
+    tickets = []
+    got = []
+    for i, act in enumerate(acts):
+        tickets.append(b.submit_host(act))
+        if i >= 1:
+            o, r, d, res = b.wait_host(tickets[i - 1])
+            got.append((o.copy(), r.copy(), d.copy(), res.copy()))
+    o, r, d, res = b.wait_host(tickets[-1])
+    got.append((o.copy(), r.copy(), d.copy(), res.copy()))
+    for w, g in zip(want, got):
+        for x, y in zip(w, g):
+            assert np.array_equal(x, y)
+    torch.cuda.synchronize()
+    assert torch.equal(a.state, b.state) and a.stats() == b.stats() | {"return_sum": a.stats()["return_sum"]}

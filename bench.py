@@ -344,13 +344,13 @@ def run_b200(args, rank, local_rank, world):
         "gpu_launches": args.steps,
         "roofline": {"bound": "hbm", "achieved": ach16, "peak": peak, "unit": "GB/s", "frac": ach16 / peak,
                      "traffic": load_traffic(f"k{k}", n),
-                     "kernel": "reachball_step_kernel<DISCRETE>", "launch_ms": launch_ms,
+                     "kernel": "s2d::step_kernel<REACHBALL, DISCRETE, default ServerParam>", "launch_ms": launch_ms,
                      "algorithmic_bytes_per_launch": bytes16, "peak_source": peak_src,
                      "note": "K=16 keeps 16 cycles in registers: HBM traffic is 222 B per 16 env-steps by construction, "
                              "this regime is instruction-issue bound; see roofline_k1 for the HBM-bound regime"},
         "roofline_k1": {"bound": "hbm", "achieved": ach1, "peak": peak, "unit": "GB/s", "frac": ach1 / peak,
                         "traffic": load_traffic("k1", n1),
-                        "kernel": "reachball_step_kernel<DISCRETE>", "launch_ms": k1_launch_ms, "envs_per_gpu": n1,
+                        "kernel": "s2d::step_kernel<REACHBALL, DISCRETE, default ServerParam>", "launch_ms": k1_launch_ms, "envs_per_gpu": n1,
                         "substeps": 1, "algorithmic_bytes_per_launch": bytes1, "env_steps_per_sec": k1_value,
                         "peak_source": peak_src},
         "rollout_dqn": {"unit": UNIT + " per GPU", "policy": "64-64 ReLU MLP (SB3 DQN MlpPolicy shape), greedy, K=1, zero-copy "

@@ -260,10 +260,13 @@ int s2d_reset(S2DHandle h, const uint8_t* device_mask_or_null, void* stream) {
   if (h->cfg.scenario == S2D_SCENARIO_FULLGAME)
     fullgame_reset_kernel<<<h->grid, kFgBlock, 0, static_cast<cudaStream_t>(stream)>>>(
         h->kp, device_mask_or_null, 2 * h->cfg.players_per_side, h->cfg.half_time_cycles);
-  else if (h->cfg.scenario == S2D_SCENARIO_SHOOT)
-    reset_kernel<S2D_SCENARIO_SHOOT><<<h->grid, kBlock, 0, static_cast<cudaStream_t>(stream)>>>(h->kp, device_mask_or_null);
-  else
-    reset_kernel<S2D_SCENARIO_REACHBALL><<<h->grid, kBlock, 0, static_cast<cudaStream_t>(stream)>>>(h->kp, device_mask_or_null);
+  else if (h->cfg.scenario == S2D_SCENARIO_SHOOT) {
+    if (h->cfg.noise) reset_kernel<S2D_SCENARIO_SHOOT, true><<<h->grid, kBlock, 0, static_cast<cudaStream_t>(stream)>>>(h->kp, device_mask_or_null);
+    else reset_kernel<S2D_SCENARIO_SHOOT, false><<<h->grid, kBlock, 0, static_cast<cudaStream_t>(stream)>>>(h->kp, device_mask_or_null);
+  } else {
+    if (h->cfg.noise) reset_kernel<S2D_SCENARIO_REACHBALL, true><<<h->grid, kBlock, 0, static_cast<cudaStream_t>(stream)>>>(h->kp, device_mask_or_null);
+    else reset_kernel<S2D_SCENARIO_REACHBALL, false><<<h->grid, kBlock, 0, static_cast<cudaStream_t>(stream)>>>(h->kp, device_mask_or_null);
+  }
   S2D_CUDA(h, cudaGetLastError());
   return S2D_OK;
 }
@@ -272,13 +275,15 @@ int s2d_reset(S2DHandle h, const uint8_t* device_mask_or_null, void* stream) {
 static cudaError_t launch_step(S2DSim* h, const KernelParams& kp, int k_substeps, cudaStream_t s) {
 #define S2D_LAUNCH(SCN, ACT)                                                                   \
   do {                                                                                         \
-    if (h->default_sp) step_kernel<SCN, ACT, true><<<h->grid, kBlock, 0, s>>>(kp, k_substeps); \
-    else step_kernel<SCN, ACT, false><<<h->grid, kBlock, 0, s>>>(kp, k_substeps);              \
+    if (h->cfg.noise) step_kernel<SCN, ACT, kVarNoisy><<<h->grid, kBlock, 0, s>>>(kp, k_substeps);             \
+    else if (h->default_sp) step_kernel<SCN, ACT, kVarDefault><<<h->grid, kBlock, 0, s>>>(kp, k_substeps);  \
+    else step_kernel<SCN, ACT, kVarRuntime><<<h->grid, kBlock, 0, s>>>(kp, k_substeps);                     \
   } while (0)
   if (h->cfg.scenario == S2D_SCENARIO_FULLGAME) {
     const int np = 2 * h->cfg.players_per_side, ht = h->cfg.half_time_cycles;
-    if (h->default_sp) fullgame_step_kernel<true><<<h->grid, kFgBlock, 0, s>>>(kp, k_substeps, np, ht);
-    else fullgame_step_kernel<false><<<h->grid, kFgBlock, 0, s>>>(kp, k_substeps, np, ht);
+    if (h->cfg.noise) fullgame_step_kernel<kVarNoisy><<<h->grid, kFgBlock, 0, s>>>(kp, k_substeps, np, ht);
+    else if (h->default_sp) fullgame_step_kernel<kVarDefault><<<h->grid, kFgBlock, 0, s>>>(kp, k_substeps, np, ht);
+    else fullgame_step_kernel<kVarRuntime><<<h->grid, kFgBlock, 0, s>>>(kp, k_substeps, np, ht);
   } else if (h->cfg.scenario == S2D_SCENARIO_SHOOT) {
     if (h->cfg.action_mode == S2D_ACT_DISCRETE) S2D_LAUNCH(S2D_SCENARIO_SHOOT, S2D_ACT_DISCRETE);
     else S2D_LAUNCH(S2D_SCENARIO_SHOOT, S2D_ACT_COMMAND);

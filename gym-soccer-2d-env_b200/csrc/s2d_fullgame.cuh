@@ -237,6 +237,7 @@ __device__ __forceinline__ bool fg_cycle(Episode& p, Match& m, const KernelParam
   // ---- commands ----
   float ax = 0.0f, ay = 0.0f, kax = 0.0f, kay = 0.0f;
   bool kicked = false;
+  const NoiseCtx nz{P.seed, gid, m.cycle};
   if (active) {
     int cmd;
     float power, dir, rate;
@@ -244,9 +245,9 @@ __device__ __forceinline__ bool fg_cycle(Episode& p, Match& m, const KernelParam
     if (cmd == S2D_CMD_DASH) {
       dash_apply(p, power, dir, rate, sp, ax, ay, left);
     } else if (cmd == S2D_CMD_TURN) {
-      turn(p, dir, sp);
+      turn(p, dir, sp, nz, static_cast<uint32_t>(lane));
     } else if (cmd == S2D_CMD_KICK && (!dead || my_side == m.side)) {
-      kicked = kick(p, power, dir, sp, kax, kay);
+      kicked = kick(p, power, dir, sp, kax, kay, nz, static_cast<uint32_t>(lane));
     }
   }
   const float bax = butterfly_sum(kax), bay = butterfly_sum(kay);
@@ -263,11 +264,12 @@ __device__ __forceinline__ bool fg_cycle(Episode& p, Match& m, const KernelParam
   // ---- move ----
   const float pbx = p.bx, pby = p.by;
   if (active)
-    move_object(p.px, p.py, p.vx, p.vy, ax, ay, sp.player_accel_max(), sp.player_accel_max2(), sp.player_speed_max(),
-                sp.player_speed_max2(), sp.player_decay());
+    move_object<SP::kNoise>(p.px, p.py, p.vx, p.vy, ax, ay, sp.player_accel_max(), sp.player_accel_max2(),
+                            sp.player_speed_max(), sp.player_speed_max2(), sp.player_decay(), sp.player_rand(), &nz,
+                            static_cast<uint32_t>(lane));
   if (!dead) {
-    move_object(p.bx, p.by, p.bvx, p.bvy, bax, bay, sp.ball_accel_max(), sp.ball_accel_max2(), sp.ball_speed_max(),
-                sp.ball_speed_max2(), sp.ball_decay());
+    move_object<SP::kNoise>(p.bx, p.by, p.bvx, p.bvy, bax, bay, sp.ball_accel_max(), sp.ball_accel_max2(),
+                            sp.ball_speed_max(), sp.ball_speed_max2(), sp.ball_decay(), sp.ball_rand(), &nz, kBallAgent);
   } else {
     p.bvx = 0.0f;
     p.bvy = 0.0f;
@@ -405,10 +407,10 @@ __device__ __forceinline__ void fg_store(const KernelParams& P, const FgLayout& 
 constexpr int kFgBlock = 128;  // 4 matches per block
 
 // K lockstep cycles of every match; actions float4 [N][K][np].
-template <bool DEF>
+template <int VAR>
 __global__ void __launch_bounds__(kFgBlock, S2D_FG_MIN_BLOCKS) fullgame_step_kernel(const __grid_constant__ KernelParams P, const int K,
                                                                  const int np, const int half_time) {
-  using SP = typename std::conditional<DEF, DefaultSP, RuntimeSP>::type;
+  using SP = typename VariantSP<VAR>::type;
   const SP sp(P.cc);
   __shared__ __align__(16) float s_stage[kFgBlock / 32][kFgObsDim];
   const int lane = threadIdx.x & 31;

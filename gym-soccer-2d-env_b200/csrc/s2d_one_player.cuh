@@ -58,6 +58,21 @@ __device__ __forceinline__ void store_episode(void* state, int64_t n, int64_t i,
             make_uint4(static_cast<uint32_t>(e.step_number), e.cycle, e.episode, e.flags));
 }
 
+// ---- noise ------------------------------------------------------------------------------------------
+// rcssserver's player_rand / ball_rand / kick_rand, drawn from the counter-based RNG: one Philox block per
+// (env, server cycle, agent) - agent = player index, kBallAgent = the ball - and a second block (32 + agent) for a
+// kicker's kick-noise direction.  Streams do not depend on sharding or on K; with noise off (SP::kNoise == false,
+// the comparison mode of the north star) none of this is compiled in.
+struct NoiseCtx {
+  uint64_t seed, gid;
+  uint32_t cycle;
+};
+constexpr uint32_t kBallAgent = 31;
+__device__ __forceinline__ float u11(uint32_t w) { return u32_to_unit(w) * 2.0f - 1.0f; }  // uniform in [-1, 1)
+__device__ __forceinline__ uint4 noise_block(const NoiseCtx& nz, uint32_t sub) {
+  return philox4x32_10(nz.seed, nz.gid, nz.cycle, RNG_NOISE, sub);
+}
+
 // ---- commands -------------------------------------------------------------------------------------
 
 template <class SP>
@@ -107,8 +122,9 @@ __device__ __forceinline__ void dash_apply(Episode& e, float power, float dir, f
 
 // (turn moment): the faster the player moves, the less it turns (inertia_moment)
 template <class SP>
-__device__ __forceinline__ void turn(Episode& e, float moment, const SP& sp) {
+__device__ __forceinline__ void turn(Episode& e, float moment, const SP& sp, const NoiseCtx& nz, uint32_t agent = 0) {
   moment = clampf(sp.min_moment(), moment, sp.max_moment());
+  if (SP::kNoise) moment = moment * (1.0f + sp.player_rand() * u11(noise_block(nz, agent).z));
   const float speed = hypot2(e.vx, e.vy);
   e.body = norm_deg(e.body + moment / (1.0f + sp.inertia_moment() * speed));
 }
@@ -116,7 +132,8 @@ __device__ __forceinline__ void turn(Episode& e, float moment, const SP& sp) {
 // (kick power dir): only inside the kickable area; power falls off by up to 25 % with the angle between
 // body and ball and by up to 25 % with the distance.  Adds to the ball's acceleration.
 template <class SP>
-__device__ __forceinline__ bool kick(Episode& e, float power, float dir, const SP& sp, float& bax, float& bay) {
+__device__ __forceinline__ bool kick(Episode& e, float power, float dir, const SP& sp, float& bax, float& bay,
+                                     const NoiseCtx& nz, uint32_t agent = 0) {
   power = clampf(0.0f, power, sp.max_power());
   dir = clampf(sp.min_moment(), dir, sp.max_moment());
   const float dx = e.bx - e.px, dy = e.by - e.py;
@@ -130,6 +147,17 @@ __device__ __forceinline__ bool kick(Episode& e, float power, float dir, const S
   sincos_deg(e.body + dir, s, c);
   bax += eff * c;
   bay += eff * s;
+  if (SP::kNoise) {  // a random push whose size grows with power, with the awkwardness of the kick and with ball speed
+    const uint4 w = noise_block(nz, agent), w2 = noise_block(nz, 32u + agent);
+    const float pos_rate = 0.5f + 0.25f * (dir_diff * static_cast<float>(1.0 / 180.0) + dist_ball / sp.kickable_margin());
+    const float speed_rate = 0.5f + 0.5f * (hypot2(e.bvx, e.bvy) / (sp.ball_speed_max() * sp.ball_decay()));
+    const float max_rand = sp.kick_rand() * (power / sp.max_power()) * (pos_rate + speed_rate);
+    const float mag = u32_to_unit(w.w) * max_rand;
+    float ns, nc;
+    sincos_deg(u11(w2.x) * 180.0f, ns, nc);
+    bax += mag * nc;
+    bay += mag * ns;
+  }
   return true;
 }
 
@@ -188,9 +216,12 @@ __device__ __forceinline__ void decode_command(const Episode& e, float4 a, float
 // ---- one cycle ------------------------------------------------------------------------------------
 
 // MPObject::_inc.  The two clamps compare SQUARED lengths (no square root unless a clamp applies).
+// NOISE: vel += (U(-m, m), U(-m, m)) with m = rnd * |vel|, drawn for `agent`.
+template <bool NOISE = false>
 __device__ __forceinline__ void move_object(float& x, float& y, float& vx, float& vy, float ax, float ay,
                                             float accel_max, float accel_max2, float speed_max, float speed_max2,
-                                            float decay) {
+                                            float decay, float rnd = 0.0f, const NoiseCtx* nz = nullptr,
+                                            uint32_t agent = 0) {
   if (ax != 0.0f || ay != 0.0f) {
     const float a2 = ax * ax + ay * ay;
     if (a2 > accel_max2) {
@@ -206,6 +237,12 @@ __device__ __forceinline__ void move_object(float& x, float& y, float& vx, float
       vx *= k;
       vy *= k;
     }
+  }
+  if (NOISE) {
+    const uint4 w = noise_block(*nz, agent);
+    const float m = rnd * hypot2(vx, vy);
+    vx += m * u11(w.x);
+    vy += m * u11(w.y);
   }
   x += vx;
   y += vy;
@@ -302,20 +339,21 @@ __device__ __forceinline__ void update_stamina(Episode& e, const SP& sp) {
 // Outputs (dx, dy) = ball - player after the cycle and d2 = dx*dx + dy*dy, which the scenario's scoring re-uses.
 template <bool TURNS, bool KICKS, class SP>
 __device__ __forceinline__ void simulate_cycle(Episode& e, int cmd, float power, float dir, float rate, const SP& sp,
-                                               float& dx, float& dy, float& d2) {
+                                               float& dx, float& dy, float& d2, uint64_t seed, uint64_t gid) {
   float ax = 0.0f, ay = 0.0f, bax = 0.0f, bay = 0.0f;
+  const NoiseCtx nz{seed, gid, e.cycle};
   if (KICKS) e.flags &= ~S2D_FLAG_KICKED;
   if (cmd == S2D_CMD_DASH) {
     dash_apply(e, power, dir, rate, sp, ax, ay);
   } else if (TURNS && cmd == S2D_CMD_TURN) {
-    turn(e, dir, sp);
+    turn(e, dir, sp, nz);
   } else if (KICKS && cmd == S2D_CMD_KICK) {
-    if (kick(e, power, dir, sp, bax, bay)) e.flags |= S2D_FLAG_KICKED;
+    if (kick(e, power, dir, sp, bax, bay, nz)) e.flags |= S2D_FLAG_KICKED;
   }
-  move_object(e.px, e.py, e.vx, e.vy, ax, ay, sp.player_accel_max(), sp.player_accel_max2(), sp.player_speed_max(),
-              sp.player_speed_max2(), sp.player_decay());
-  move_object(e.bx, e.by, e.bvx, e.bvy, bax, bay, sp.ball_accel_max(), sp.ball_accel_max2(), sp.ball_speed_max(),
-              sp.ball_speed_max2(), sp.ball_decay());
+  move_object<SP::kNoise>(e.px, e.py, e.vx, e.vy, ax, ay, sp.player_accel_max(), sp.player_accel_max2(),
+                          sp.player_speed_max(), sp.player_speed_max2(), sp.player_decay(), sp.player_rand(), &nz, 0u);
+  move_object<SP::kNoise>(e.bx, e.by, e.bvx, e.bvy, bax, bay, sp.ball_accel_max(), sp.ball_accel_max2(),
+                          sp.ball_speed_max(), sp.ball_speed_max2(), sp.ball_decay(), sp.ball_rand(), &nz, kBallAgent);
   dx = e.bx - e.px;
   dy = e.by - e.py;
   d2 = dx * dx + dy * dy;

@@ -5,6 +5,7 @@
 // defaults below are rcssserver's documented ones.
 //
 //   RuntimeSP   reads S2DServerParam (+ derived products) from the kernel's constant bank: any configuration
+//   NoisySP     RuntimeSP, and the physics functions add noise (S2DConfig.noise != 0)
 //   DefaultSP   the same accessors as compile-time constants for the default configuration: immediates, no
 //               constant loads, dead branches folded (back-dash, slowness, angle step ...).  s2d_create picks
 //               the DefaultSP kernels when cfg->sp equals s2d_default_server_param() bit for bit.
@@ -99,6 +100,7 @@ inline bool is_default_server_param(const S2DServerParam& sp) {
 
 // accessors over the kernel's constant bank
 struct RuntimeSP {
+  static constexpr bool kNoise = false;
   const CycleConsts& c;
   S2D_HD explicit RuntimeSP(const CycleConsts& c_) : c(c_) {}
 #define X(name, def) S2D_HD float name() const { return c.sp.name; }
@@ -109,6 +111,12 @@ struct RuntimeSP {
 #undef Y
 };
 
+// same constants, and the cycle adds rcssserver's noise (player_rand, ball_rand, kick_rand) from the counter RNG
+struct NoisySP : RuntimeSP {
+  static constexpr bool kNoise = true;
+  S2D_HD explicit NoisySP(const CycleConsts& c_) : RuntimeSP(c_) {}
+};
+
 // the default configuration as compile-time constants
 struct DefaultBase {
 #define X(name, def) S2D_HDC float name() { return def; }
@@ -116,6 +124,7 @@ struct DefaultBase {
 #undef X
 };
 struct DefaultSP : DefaultBase {
+  static constexpr bool kNoise = false;
   S2D_HD explicit DefaultSP(const CycleConsts&) {}
 #define Y(name, expr)                \
   S2D_HDC float name() {             \

@@ -258,7 +258,7 @@ __device__ __forceinline__ void reset_episode(Episode& e, const KernelParams& P,
   float dx, dy, d2, rw;
   int rs;
   const float pbx = e.bx, pby = e.by;
-  simulate_cycle<false, false>(e, S2D_CMD_NONE, 0.0f, 0.0f, 0.0f, sp, dx, dy, d2);
+  simulate_cycle<false, false>(e, S2D_CMD_NONE, 0.0f, 0.0f, 0.0f, sp, dx, dy, d2, P.seed, gid);
   scenario_check<SCN>(e, P, sp, dx, dy, d2, pbx, pby, rw, rs);  // reach_ball_env.py:166: primes the memory, reward discarded
 }
 
@@ -300,7 +300,7 @@ __device__ __forceinline__ void substep(Episode& e, const KernelParams& P, const
   float dx, dy, d2, rw;
   int rs;
   const float pbx = e.bx, pby = e.by;
-  simulate_cycle<kTurns, kKicks>(e, cmd, power, dir, rate, sp, dx, dy, d2);
+  simulate_cycle<kTurns, kKicks>(e, cmd, power, dir, rate, sp, dx, dy, d2, P.seed, gid);
   const bool done = scenario_check<SCN>(e, P, sp, dx, dy, d2, pbx, pby, rw, rs);
   out.reward_sum += rw;
   e.ep_return += rw;
@@ -376,10 +376,18 @@ constexpr int kBlock = S2D_BLOCK;
 // K lockstep cycles of every env in one launch; state stays in registers in between.
 // actions[N][K] (uint8 / float) or [N][K][4] (float): a lane's K actions are contiguous in memory; the first
 // access pulls the lane's sector(s) into L1 and the following cycles hit there (ld.global.nc).
-// SCN: scenario; ACT: action encoding; DEF: the constants are the default ServerParam, folded at compile time.
-template <int SCN, int ACT, bool DEF>
+// SCN: scenario; ACT: action encoding; VAR: how the constants come in (kVarRuntime: constant bank, kVarDefault: the
+// default ServerParam folded at compile time, kVarNoisy: constant bank + rcssserver noise).
+constexpr int kVarRuntime = 0, kVarDefault = 1, kVarNoisy = 2;
+template <int VAR>
+struct VariantSP {
+  using type = typename std::conditional<VAR == kVarDefault, DefaultSP,
+                                         typename std::conditional<VAR == kVarNoisy, NoisySP, RuntimeSP>::type>::type;
+};
+
+template <int SCN, int ACT, int VAR>
 __global__ void __launch_bounds__(kBlock, S2D_MIN_BLOCKS) step_kernel(const __grid_constant__ KernelParams P, const int K) {
-  using SP = typename std::conditional<DEF, DefaultSP, RuntimeSP>::type;
+  using SP = typename VariantSP<VAR>::type;
   const SP sp(P.cc);
   __shared__ __align__(16) float s_stage[kBlock / 32][32 * kObsDim];
   const int64_t i = static_cast<int64_t>(blockIdx.x) * kBlock + threadIdx.x;
@@ -432,13 +440,13 @@ __global__ void __launch_bounds__(kBlock, S2D_MIN_BLOCKS) step_kernel(const __gr
 }
 
 // Soccer2DEnv.reset for every env (mask == nullptr) or the envs with a non-zero mask byte.
-template <int SCN>
+template <int SCN, bool NOISY>
 __global__ void __launch_bounds__(kBlock) reset_kernel(const __grid_constant__ KernelParams P,
                                                        const uint8_t* __restrict__ mask) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * kBlock + threadIdx.x;
   if (i >= P.num_envs) return;
   if (mask && !mask[i]) return;
-  const RuntimeSP sp(P.cc);
+  const typename std::conditional<NOISY, NoisySP, RuntimeSP>::type sp(P.cc);
   Episode e;
   load_episode(P.state, P.num_envs, i, e);
   reset_episode<SCN>(e, P, sp, static_cast<uint64_t>(P.env_id_offset + i));

@@ -17,10 +17,10 @@ class FullGameEnv(Soccer2DEnv):
     scenario = "fullgame"
 
     def __init__(self, render_mode=None, logger=None, log_dir=None, *, device="cuda", seed: int = 0,
-                 server_param: dict | None = None, **kwargs):
+                 server_param: dict | None = None, noise: bool = False, **kwargs):
         known = {k: kwargs[k] for k in FULLGAME_DEFAULTS if k in kwargs}
         super().__init__(render_mode, logger=logger, log_dir=log_dir, device=device, seed=seed,
-                         server_param=server_param, **known)
+                         server_param=server_param, noise=noise, **known)
         for k, v in dict(FULLGAME_DEFAULTS, **known).items():
             setattr(self, k, v)
 

@@ -17,10 +17,11 @@ class ReachBallEnv(Soccer2DEnv):
     scenario = "reachball"
 
     def __init__(self, render_mode=None, logger=None, log_dir=None, *, device="cuda", seed: int = 0,
-                 server_param: dict | None = None, use_command_action: bool = False, **kwargs):
+                 server_param: dict | None = None, use_command_action: bool = False, noise: bool = False,
+                 **kwargs):
         # the reference reads kwargs with .get() and ignores unknown keys (:26-36)
         known = {k: kwargs[k] for k in REACHBALL_DEFAULTS if k in kwargs}
         super().__init__(render_mode, logger=logger, log_dir=log_dir, device=device, seed=seed,
-                         server_param=server_param, use_command_action=use_command_action, **known)
+                         server_param=server_param, use_command_action=use_command_action, noise=noise, **known)
         for k, v in dict(REACHBALL_DEFAULTS, **known).items():
             setattr(self, k, v)

@@ -57,6 +57,9 @@ class Soccer2DVecEnv:
     use_command_action   actions are proto-style commands {cmd, a, b, c} (S2D_CMD_*: dash / turn / kick /
                    body_go_to_point) instead of the scenario's own action space; shape [N, K, 4] float32
     goto_dist_thr  Body_GoToPoint.distance_threshold for CMD_GOTO
+    noise          rcssserver's player_rand / ball_rand / kick_rand noise from the counter-based RNG, keyed on
+                   (seed, global env id, server cycle, agent): reproducible, independent of sharding and of
+                   `substeps`.  Off by default (the mode in which runs are compared with the oracle's f64 truth)
     **kwargs       the scenario kwargs: ReachBallEnv's (same names and defaults as the reference) or SHOOT_DEFAULTS
     """
 
@@ -65,7 +68,7 @@ class Soccer2DVecEnv:
     def __init__(self, num_envs: int, scenario: str = "reachball", device="cuda", seed: int = 0, substeps: int = 1,
                  env_id_offset: int = 0, auto_reset: bool = True, terminal_obs: bool = False,
                  server_param: dict | None = None, use_command_action: bool = False, goto_dist_thr: float = 0.5,
-                 **kwargs):
+                 noise: bool = False, **kwargs):
         if scenario.lower() not in _SCENARIOS:
             raise ValueError(f"Environment {scenario} not found.")  # environment_factory.py:28
         self.scenario = scenario.lower()
@@ -111,6 +114,7 @@ class Soccer2DVecEnv:
         cfg.action_space_size = int(self.kw.get("action_space_size", 16))
         cfg.kick_actions = int(self.kw.get("kick_actions", 0))
         cfg.goto_dist_thr = float(goto_dist_thr)
+        cfg.noise = int(bool(noise))
         cfg.max_steps = int(self.kw.get("max_steps", 200))
         cfg.auto_reset = int(self.auto_reset)
         cfg.change_ball_position = int(bool(self.kw.get("change_ball_position", True)))

@@ -31,7 +31,7 @@ class Soccer2DEnv(Env):
     def __init__(self, render_mode: str = None, run_grpc_server: bool = True, run_rcssserver: bool = True,
                  run_trainer_player: bool = True, logger: logging.Logger = None, log_dir: str = None,
                  *, device="cuda", seed: int = 0, server_param: dict | None = None, use_command_action: bool = False,
-                 **scenario_kwargs):
+                 noise: bool = False, **scenario_kwargs):
         self.log_dir = log_dir
         self.logger = logger
         if self.logger is None:
@@ -46,7 +46,7 @@ class Soccer2DEnv(Env):
         self.observation_space = Box(low=-1, high=1, shape=(2,), dtype=np.float32)
         self._vec = Soccer2DVecEnv(1, scenario=self.scenario, device=device, seed=seed, substeps=1, auto_reset=False,
                                    server_param=server_param, use_command_action=use_command_action,
-                                   **scenario_kwargs)
+                                   noise=noise, **scenario_kwargs)
         self.action_space = self._vec.action_space
         self.observation_space = self._vec.observation_space
         self.step_number = 0

@@ -69,11 +69,14 @@ void emu_reset(void* p, const uint8_t* mask, float* obs) {
     if (mask && !mask[i]) continue;
     Episode e;
     load_episode(P.state, P.num_envs, i, e);
+    const uint64_t gid = (uint64_t)(P.env_id_offset + i);
     if (P.scenario == S2D_SCENARIO_SHOOT) {
-      reset_episode<S2D_SCENARIO_SHOOT>(e, P, RuntimeSP(P.cc), (uint64_t)(P.env_id_offset + i));
+      if (P.noise) reset_episode<S2D_SCENARIO_SHOOT>(e, P, NoisySP(P.cc), gid);
+      else reset_episode<S2D_SCENARIO_SHOOT>(e, P, RuntimeSP(P.cc), gid);
       scenario_obs<S2D_SCENARIO_SHOOT>(e, obs + i * kObsDim);
     } else {
-      reset_episode<S2D_SCENARIO_REACHBALL>(e, P, RuntimeSP(P.cc), (uint64_t)(P.env_id_offset + i));
+      if (P.noise) reset_episode<S2D_SCENARIO_REACHBALL>(e, P, NoisySP(P.cc), gid);
+      else reset_episode<S2D_SCENARIO_REACHBALL>(e, P, RuntimeSP(P.cc), gid);
       scenario_obs<S2D_SCENARIO_REACHBALL>(e, obs + i * kObsDim);
     }
     store_episode(P.state, P.num_envs, i, e);
@@ -86,7 +89,8 @@ void emu_step(void* p, const void* actions, int K, float* obs, float* reward, ui
   h->kp.terminal_obs = terminal_obs;
 #define EMU_STEP(SCN, ACT)                                                                            \
   do {                                                                                                \
-    if (h->default_sp) step_all<SCN, ACT, DefaultSP>(h, actions, K, obs, reward, done, result, stats6); \
+    if (h->kp.noise) step_all<SCN, ACT, NoisySP>(h, actions, K, obs, reward, done, result, stats6);     \
+    else if (h->default_sp) step_all<SCN, ACT, DefaultSP>(h, actions, K, obs, reward, done, result, stats6); \
     else step_all<SCN, ACT, RuntimeSP>(h, actions, K, obs, reward, done, result, stats6);             \
   } while (0)
   if (h->kp.scenario == S2D_SCENARIO_SHOOT) {

@@ -252,3 +252,18 @@ def test_fullgame_gym_api():
         steps += 1
     assert steps == 40 and info["result"] in ("Goal", "Out", "Timeout")
     env.close()
+
+
+def test_fullgame_with_noise_bit_exact():
+    n, p = 96, 22
+    env = Soccer2DVecEnv(n, scenario="fullgame", device="cuda:0", seed=6, noise=True, half_time_cycles=100, terminal_obs=True)
+    sim = OL.OracleSim(env.cfg, "f32")
+    assert np.array_equal(env.reset(), sim.reset())
+    rng = np.random.default_rng(3)
+    for t in range(300):
+        act = swarm_policy(sim.obs, p, rng, random_frac=0.15)
+        env.step_torch(torch.from_numpy(act))
+        sim.step(act.reshape(n, -1))
+        same_step(env, sim)
+    assert np.array_equal(gpu_state_fg(env), sim.get_state_fg())
+    assert env.stats()["episodes"] == n

@@ -587,3 +587,37 @@ def test_pipelined_host_steps_equal_synchronous_ones():
             assert np.array_equal(x, y)
     torch.cuda.synchronize()
     assert torch.equal(a.state, b.state) and a.stats() == b.stats() | {"return_sum": a.stats()["return_sum"]}
+
+
+@pytest.mark.parametrize("scenario,mode,k", [("reachball", "discrete", 1), ("reachball", "discrete", 16), ("reachball", "turning", 1),
+                                             ("shoot", "command", 1)])
+def test_noise_on_bit_exact_and_reproducible(scenario, mode, k):
+    """player_rand / ball_rand / kick_rand noise from Philox keyed on (seed, env, cycle, agent): the GPU equals the fp32
+    oracle bit for bit, K fused cycles equal K single ones, and a shard reproduces its slice of the global run."""
+    n = 640
+    kw = dict(device="cuda:0", seed=31, noise=True, terminal_obs=True, max_steps=100, substeps=k)
+    if scenario == "shoot":
+        env = Soccer2DVecEnv(n, scenario="shoot", use_command_action=True, **kw)
+        shard = Soccer2DVecEnv(200, scenario="shoot", use_command_action=True, env_id_offset=300, **kw)
+    else:
+        env = make_env(n, mode, change_ball_velocity=True, **kw)
+        shard = make_env(200, mode, change_ball_velocity=True, env_id_offset=300, **kw)
+    sim = OL.OracleSim(env.cfg, "f32")
+    assert np.array_equal(env.reset(), sim.reset())
+    shard.reset_torch()
+    rng = np.random.default_rng(0)
+    for t in range(320 // k):
+        if mode == "command":
+            act = H.chase_and_shoot(sim.obs, rng, kick_prob=0.9)
+            act = np.where(rng.uniform(size=(n, 1, 1)) < 0.15, H.random_commands(rng, n), act).astype(np.float32)
+        else:
+            act = H.random_actions(rng, mode, n, k)
+        env.step_torch(torch.from_numpy(act))
+        shard.step_torch(torch.from_numpy(np.ascontiguousarray(act[300:500])))
+        sim.step(act, k)
+        assert_same_step(env, sim)
+    assert np.array_equal(gpu_state(env), sim.get_state())
+    assert torch.equal(env.obs[300:500], shard.obs) and np.array_equal(gpu_state(env)[300:500], gpu_state(shard))
+    quiet = OL.OracleSim(H.make_config(n, mode, scenario=env.cfg.scenario, seed=31, change_ball_velocity=1, max_steps=100), "f32")
+    quiet.reset()
+    assert not np.array_equal(quiet.obs, sim.obs)

@@ -206,3 +206,64 @@ def test_kernel_source_shoot_goal_line_cases():
         sim.step(act)
         _same(emu, sim)
     assert sim.stats(_abi.Stats()).goals >= 2  # case 0 and the straight kick
+
+
+# ---- noise (player_rand / ball_rand / kick_rand from the counter-based RNG) ---------------------------------
+
+@pytest.mark.parametrize("scenario,mode", [("reachball", "discrete"), ("reachball", "turning"), ("reachball", "command"),
+                                           ("shoot", "command")])
+def test_kernel_source_with_noise_bit_exact(scenario, mode):
+    from soccer2d_b200 import _abi
+    n = 150
+    scn = _abi.SCENARIO_SHOOT if scenario == "shoot" else _abi.SCENARIO_REACHBALL
+    kw = dict(min_distance_to_ball=0.3, goto_dist_thr=0.4) if mode == "command" and scenario == "reachball" else {}
+    cfg = H.make_config(n, mode, scenario=scn, seed=31, noise=1, change_ball_velocity=1, max_steps=100, **kw)
+    emu, sim, quiet = EL.EmuSim(cfg), OL.OracleSim(cfg, "f32"), OL.OracleSim(H.make_config(
+        n, mode, scenario=scn, seed=31, noise=0, change_ball_velocity=1, max_steps=100, **kw), "f32")
+    assert np.array_equal(emu.reset(), sim.reset())
+    quiet.reset()
+    assert not np.array_equal(sim.obs, quiet.obs)  # the reset's idle cycle already moves the ball noisily
+    rng = np.random.default_rng(0)
+    flags = 0
+    for t in range(400):
+        if mode == "command":
+            act = H.chase_and_shoot(sim.obs, rng, kick_prob=0.9)
+            act = np.where(rng.uniform(size=(n, 1, 1)) < 0.15, H.random_commands(rng, n), act).astype(np.float32)
+        else:
+            act = H.random_actions(rng, mode, n)
+        emu.step(act)
+        sim.step(act)
+        _same(emu, sim)
+        if t % 40 == 39:
+            g = emu.get_state()
+            assert np.array_equal(g, sim.get_state())
+            flags |= int(np.bitwise_or.reduce(g[:, 19].astype(int)))
+    if mode == "command":
+        assert flags & 4  # kicks (and their noise) happened
+
+
+def test_noise_statistics_and_f64_agreement():
+    """fp32 spec vs f64 truth with noise on (the uniforms are identical integers, so the 1e-5 bound still holds over
+    a few hundred cycles), and the size of the velocity noise: |dv| <= rand * |v| per axis."""
+    n = 256
+    cfg = H.make_config(n, "discrete", seed=8, noise=1, change_ball_velocity=1)
+    t, s = OL.OracleSim(cfg, "f64"), OL.OracleSim(cfg, "f32")
+    t.reset()
+    s.reset()
+    rng = np.random.default_rng(2)
+    for _ in range(150):
+        act = H.random_actions(rng, "discrete", n)
+        t.step(act)
+        s.step(act)
+        assert np.array_equal(t.done, s.done)
+        assert H.obs_close(t.obs, s.obs) < H.TOL
+    # ball only: with noise off the ball decays along a straight line; with noise on its direction wanders a little
+    quiet = OL.OracleSim(H.make_config(n, "discrete", seed=8, noise=0, change_ball_velocity=1), "f64")
+    loud = OL.OracleSim(H.make_config(n, "discrete", seed=8, noise=1, change_ball_velocity=1), "f64")
+    quiet.reset()
+    loud.reset()
+    q, l = quiet.get_state(), loud.get_state()
+    vq, vl = np.hypot(q[:, 11], q[:, 12]), np.hypot(l[:, 11], l[:, 12])
+    moving = vq > 0.1
+    rel = np.abs(vl[moving] - vq[moving]) / vq[moving]
+    assert rel.max() <= 0.05 * np.sqrt(2) + 1e-6 and rel.mean() > 0.005  # ball_rand = 0.05 per axis

@@ -59,7 +59,7 @@ class Soccer2DVecEnv:
     goto_dist_thr  Body_GoToPoint.distance_threshold for CMD_GOTO
     noise          rcssserver's player_rand / ball_rand / kick_rand noise from the counter-based RNG, keyed on
                    (seed, global env id, server cycle, agent): reproducible, independent of sharding and of
-                   `substeps`.  Off by default (the mode in which runs are compared with the oracle's f64 truth)
+                   `substeps`.  Off by default (the mode in which runs are compared with the double-precision CPU truth)
     **kwargs       the scenario kwargs: ReachBallEnv's (same names and defaults as the reference) or SHOOT_DEFAULTS
     """
 

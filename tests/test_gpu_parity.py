@@ -595,10 +595,10 @@ def test_noise_on_bit_exact_and_reproducible(scenario, mode, k):
     """player_rand / ball_rand / kick_rand noise from Philox keyed on (seed, env, cycle, agent): the GPU equals the fp32
     oracle bit for bit, K fused cycles equal K single ones, and a shard reproduces its slice of the global run."""
     n = 640
-    kw = dict(device="cuda:0", seed=31, noise=True, terminal_obs=True, max_steps=100, substeps=k)
+    kw = dict(seed=31, noise=True, terminal_obs=True, max_steps=100, substeps=k)
     if scenario == "shoot":
-        env = Soccer2DVecEnv(n, scenario="shoot", use_command_action=True, **kw)
-        shard = Soccer2DVecEnv(200, scenario="shoot", use_command_action=True, env_id_offset=300, **kw)
+        env = Soccer2DVecEnv(n, scenario="shoot", device="cuda:0", use_command_action=True, **kw)
+        shard = Soccer2DVecEnv(200, scenario="shoot", device="cuda:0", use_command_action=True, env_id_offset=300, **kw)
     else:
         env = make_env(n, mode, change_ball_velocity=True, **kw)
         shard = make_env(200, mode, change_ball_velocity=True, env_id_offset=300, **kw)

@@ -373,6 +373,13 @@ class Soccer2DVecEnv:
         _abi.check(self.lib.s2d_export_env(self.handle, int(i), C.byref(snap), _stream_ptr(self.device)), self.handle)
         return snap
 
+    def export_state(self, i: int, unum: int = 1, side: int = 1) -> dict:
+        """proto `State` of env `i` as seen by player `unum` of `side`, as nested dicts keyed by the proto field names
+        (idl/service.proto:306-359); `json_format.ParseDict(d, service_pb2.State())` turns it into the message."""
+        from .proto_state import state_dict
+        return state_dict(self.export_env(i), unum=unum, side=side,
+                          kickable_area=self.cfg.sp.player_size + self.cfg.sp.ball_size + self.cfg.sp.kickable_margin)
+
     def state_planes(self):
         """One-player scenarios: views of the SoA planes (float32 [4, N, 4], int32 [N, 4]) - layout in DESIGN.md."""
         assert self.scenario != "fullgame", "use export_env / fullgame_planes for the match layout"

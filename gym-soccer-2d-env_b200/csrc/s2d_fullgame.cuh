@@ -88,24 +88,29 @@ __device__ __forceinline__ int fg_collisions(Episode& p, bool active, int lane, 
   const float h = r2 / 2.0f + kCollideEps;
 #pragma unroll 1
   for (int round = 0; round < 10; ++round) {
-    // Broad phase: does anything overlap at all?  Lane i tests the ball and the partners (i + d) mod np for
-    // d = 1..np/2, which covers every unordered pair in half the iterations of the ordered loop below.  The
-    // predicates are the very same expressions, so skipping the narrow phase changes nothing when they are all false.
+    // Broad phase: does anything overlap at all?  Players are hashed into square cells a bit wider than twice the
+    // collision distance, on four grids shifted by half a cell in x and / or y: two players closer than the collision
+    // distance share a cell on at least one of the four grids, so if no lane finds a partner with its key
+    // (__match_any_sync) - and no player touches the ball - nothing overlaps and the ordered narrow phase below,
+    // which would change nothing, is skipped.  (Conservative: a shared cell only means "look closer".)
     {
-      bool overlap = false;
+      bool maybe = false;
       if (active && !ball_fixed) {
         const float dx = p.bx - p.px, dy = p.by - p.py;
-        overlap = dx * dx + dy * dy < r * r;
+        maybe = dx * dx + dy * dy < r * r;
       }
-#pragma unroll 1
-      for (int d = 1; d <= (np >> 1); ++d) {
-        int j = lane + d;
-        j = j >= np ? j - np : j;
-        const float xj = __shfl_sync(full, p.px, j & 31), yj = __shfl_sync(full, p.py, j & 31);
-        const float ex = p.px - xj, ey = p.py - yj;
-        overlap = overlap || (active && ex * ex + ey * ey < r2 * r2);
+      const float inv_cell = 1.0f / (2.02f * r2), half = 0.5f;
+      const float gx = p.px * inv_cell, gy = p.py * inv_cell;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int cx = __float2int_rd(gx + ((g & 1) ? half : 0.0f)), cy = __float2int_rd(gy + ((g & 2) ? half : 0.0f));
+        // inactive lanes get a key no player can have
+        const unsigned key = active ? ((static_cast<unsigned>(cx) & 0xffffu) << 16) | (static_cast<unsigned>(cy) & 0xffffu)
+                                    : 0x80008000u + static_cast<unsigned>(lane);
+        const unsigned same = __match_any_sync(full, key);
+        maybe = maybe || (active && (same & (same - 1u)) != 0u);  // more than one lane in my cell
       }
-      if (!__any_sync(full, overlap)) break;
+      if (!__any_sync(full, maybe)) break;
     }
     bool col = false;
     int cnt = 0;
@@ -175,9 +180,12 @@ __device__ __forceinline__ int fg_collisions(Episode& p, bool active, int lane, 
 // 120-float observation of a match: ball, 22 x {x, y, vx, vy, body}, referee state.  Staged in shared memory and
 // written by lanes 0..29 as one float4 each (480 contiguous bytes).
 __device__ __forceinline__ void fg_write_obs(float* __restrict__ dst, int64_t env, const Episode& p, const Match& m,
-                                             bool active, int lane, int half_time, float* stage /* [120] */) {
-  for (int k = lane; k < kFgObsDim; k += 32) stage[k] = 0.0f;
-  __syncwarp();
+                                             bool active, int lane, int np, int half_time,
+                                             float* stage /* [120] */) {
+  if (np < kFgMaxPlayers) {  // fewer than 11 a side: the rows of the absent players are zero
+    for (int k = lane; k < kFgObsDim; k += 32) stage[k] = 0.0f;
+    __syncwarp();
+  }
   if (active) {
     float* o = stage + 4 + 5 * lane;
     o[0] = p.px * static_cast<float>(1.0 / 52.5);
@@ -196,6 +204,7 @@ __device__ __forceinline__ void fg_write_obs(float* __restrict__ dst, int64_t en
     stage[116] = static_cast<float>(m.score_l);
     stage[117] = static_cast<float>(m.score_r);
     stage[118] = static_cast<float>(m.step_number) / static_cast<float>(2 * half_time);
+    stage[119] = 0.0f;
   }
   __syncwarp();
   if (lane < kFgObsDim / 4)
@@ -448,7 +457,7 @@ __global__ void __launch_bounds__(kFgBlock, S2D_FG_MIN_BLOCKS) fullgame_step_ker
         atomicAdd(slot + ST_EP_STEPS, static_cast<unsigned long long>(m.step_number));
         atomicAdd(reinterpret_cast<double*>(slot + ST_RETURN), static_cast<double>(m.ep_return));
       }
-      if (P.terminal_obs) fg_write_obs(P.terminal_obs, env, p, m, active, lane, half_time, stage);
+      if (P.terminal_obs) fg_write_obs(P.terminal_obs, env, p, m, active, lane, np, half_time, stage);
       if (P.auto_reset) {
         fg_reset(p, m, P, sp, gid, lane, np >> 1);
         collided_mask = kicked_mask = 0;
@@ -459,7 +468,7 @@ __global__ void __launch_bounds__(kFgBlock, S2D_FG_MIN_BLOCKS) fullgame_step_ker
     }
   }
   fg_store(P, L, env, lane, active, p, m, collided_mask, kicked_mask, ball_collided);
-  fg_write_obs(P.obs, env, p, m, active, lane, half_time, stage);
+  fg_write_obs(P.obs, env, p, m, active, lane, np, half_time, stage);
   if (lane == 0) {
     P.reward[env] = reward_sum;
     P.done[env] = static_cast<uint8_t>(any_done);
@@ -483,7 +492,7 @@ __global__ void __launch_bounds__(kFgBlock) fullgame_reset_kernel(const __grid_c
   fg_load(P, L, env, lane, active, p, m);
   fg_reset(p, m, P, sp, static_cast<uint64_t>(P.env_id_offset + env), lane, np >> 1);
   fg_store(P, L, env, lane, active, p, m, 0u, 0u, false);
-  fg_write_obs(P.obs, env, p, m, active, lane, half_time, s_stage[threadIdx.x >> 5]);
+  fg_write_obs(P.obs, env, p, m, active, lane, np, half_time, s_stage[threadIdx.x >> 5]);
   if (lane == 0) {
     P.reward[env] = 0.0f;
     P.done[env] = 0;

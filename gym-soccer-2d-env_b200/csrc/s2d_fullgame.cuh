@@ -22,7 +22,7 @@ constexpr int kFgMaxPlayers = 22;
 // HBM layout of N matches with np players each (plane-major; every plane starts 16-byte aligned):
 //   PA float4 [N][np] {x, y, vx, vy}            PB float4 [N][np] {body, stamina, effort, recovery}
 //   PC float  [N][np] stamina_capacity (plane padded to 16 B)
-//   EB float4 [N] ball {x, y, vx, vy}           EF float4 [N] {episode return, -, -, -}
+//   EB float4 [N] ball {x, y, vx, vy}           EF float4 [N] {episode return, player separation bound, -, -}
 //   EI uint4  [N] {step_number, cycle, episode, mode | side<<8 | last_touch<<10 | timer<<12 | ball_collided<<20 | done<<21}
 //   EJ uint4  [N] {score_l, score_r, collided mask (bit = player), kicked mask}
 struct FgLayout {
@@ -46,6 +46,7 @@ struct Match {
   int mode, side, last_touch, timer;
   int score_l, score_r;
   float ep_return;
+  float sep;  // lower bound on the smallest player-player distance (see fg_collisions); 0 = unknown
   bool done_flag;
 };
 
@@ -78,40 +79,48 @@ __device__ __forceinline__ void fg_place_player(Episode& p, const KernelParams& 
 // Stadium::collisions for np players and the ball, one lane per player.  In a round every object collects the
 // positions proposed for it and moves to their average; afterwards whatever collided gets vel *= -0.1 once.
 // Returns this lane's bits: 1 = player collided, 2 = player touched the ball; ball_collided is warp-uniform.
+//
+// `sep` (kept in the match state) is a LOWER BOUND on the smallest distance between two players.  Every cycle it
+// shrinks by `shrink` = twice the largest distance a player can move in a cycle; only when it drops below the collision
+// distance is the exact minimum recomputed (the O(n^2 / 32) pair loop) - in open play every few cycles instead of
+// every cycle.  The ball is tested against every player every cycle.  If neither test finds an overlap, the ordered
+// relaxation rounds - which would change nothing - are skipped, so the results do not depend on this shortcut.
 template <class SP>
 __device__ __forceinline__ int fg_collisions(Episode& p, bool active, int lane, int np, bool ball_fixed, const SP& sp,
-                                             bool& ball_collided) {
+                                             bool& ball_collided, float& sep, float shrink) {
   const unsigned full = 0xffffffffu;
   bool collided = false, ballhit = false, ball_any = false;
   const float r = sp.player_size() + sp.ball_size();
   const float r2 = sp.player_size() + sp.player_size();
   const float h = r2 / 2.0f + kCollideEps;
+  ball_collided = false;
+
+  bool ball_overlap = false;
+  if (active && !ball_fixed) {
+    const float dx = p.bx - p.px, dy = p.by - p.py;
+    ball_overlap = dx * dx + dy * dy < r * r;
+  }
+  sep -= shrink;
+  bool pairs_close = false;
+  if (sep < r2) {  // uniform: the bound has run out, measure the true minimum (lane i looks at (i + d) mod np, d <= np/2)
+    float m2 = 3.0e38f;
+    int j = lane;
+#pragma unroll 1
+    for (int d = 1; d <= (np >> 1); ++d) {
+      j = j + 1 >= np ? j + 1 - np : j + 1;
+      const float xj = __shfl_sync(full, p.px, j), yj = __shfl_sync(full, p.py, j);
+      const float ex = p.px - xj, ey = p.py - yj;
+      m2 = fminf(m2, ex * ex + ey * ey);
+    }
+    m2 = active ? m2 : 3.0e38f;
+    m2 = __uint_as_float(__reduce_min_sync(full, __float_as_uint(m2)));  // non-negative floats order like their bits
+    pairs_close = m2 < r2 * r2;
+    sep = sqrtf(m2) * 0.999f;
+  }
+  if (!pairs_close && !__any_sync(full, ball_overlap)) return 0;
+
 #pragma unroll 1
   for (int round = 0; round < 10; ++round) {
-    // Broad phase: does anything overlap at all?  Players are hashed into square cells a bit wider than twice the
-    // collision distance, on four grids shifted by half a cell in x and / or y: two players closer than the collision
-    // distance share a cell on at least one of the four grids, so if no lane finds a partner with its key
-    // (__match_any_sync) - and no player touches the ball - nothing overlaps and the ordered narrow phase below,
-    // which would change nothing, is skipped.  (Conservative: a shared cell only means "look closer".)
-    {
-      bool maybe = false;
-      if (active && !ball_fixed) {
-        const float dx = p.bx - p.px, dy = p.by - p.py;
-        maybe = dx * dx + dy * dy < r * r;
-      }
-      const float inv_cell = 1.0f / (2.02f * r2), half = 0.5f;
-      const float gx = p.px * inv_cell, gy = p.py * inv_cell;
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const int cx = __float2int_rd(gx + ((g & 1) ? half : 0.0f)), cy = __float2int_rd(gy + ((g & 2) ? half : 0.0f));
-        // inactive lanes get a key no player can have
-        const unsigned key = active ? ((static_cast<unsigned>(cx) & 0xffffu) << 16) | (static_cast<unsigned>(cy) & 0xffffu)
-                                    : 0x80008000u + static_cast<unsigned>(lane);
-        const unsigned same = __match_any_sync(full, key);
-        maybe = maybe || (active && (same & (same - 1u)) != 0u);  // more than one lane in my cell
-      }
-      if (!__any_sync(full, maybe)) break;
-    }
     bool col = false;
     int cnt = 0;
     float sx = 0.0f, sy = 0.0f, bpx = 0.0f, bpy = 0.0f;
@@ -165,6 +174,7 @@ __device__ __forceinline__ int fg_collisions(Episode& p, bool active, int lane, 
     }
     if (!__any_sync(full, col)) break;
   }
+  sep = 0.0f;  // players were pushed around: measure again next cycle
   if (ball_any) {
     p.bvx *= -0.1f;
     p.bvy *= -0.1f;
@@ -224,6 +234,7 @@ __device__ __forceinline__ void fg_reset(Episode& p, Match& m, const KernelParam
   m.episode += 1u;
   m.step_number = 0;
   m.ep_return = 0.0f;
+  m.sep = 0.0f;
   m.done_flag = false;
   m.mode = S2D_PM_KICK_OFF;
   m.side = S2D_SIDE_LEFT;
@@ -285,7 +296,9 @@ __device__ __forceinline__ bool fg_cycle(Episode& p, Match& m, const KernelParam
   }
 
   // ---- collisions ----
-  const int hit = fg_collisions(p, active, lane, np, dead, sp, ball_collided);
+  // the farthest a player can move in a cycle: speed_max (the clamp) plus, with noise, up to rand * sqrt(2) of it
+  const float vmax = sp.player_speed_max() * (SP::kNoise ? 1.0f + 1.5f * sp.player_rand() : 1.0f) * 1.001f;
+  const int hit = fg_collisions(p, active, lane, np, dead, sp, ball_collided, m.sep, 2.0f * vmax);
   collided_mask = __ballot_sync(full, (hit & 1) != 0);
   {
     const unsigned touch = __ballot_sync(full, (hit & 2) != 0);
@@ -351,6 +364,7 @@ __device__ __forceinline__ bool fg_cycle(Episode& p, Match& m, const KernelParam
     }
   }
   if (kick_off) {
+    m.sep = 0.0f;
     if (active) fg_place_player(p, P, gid, m.episode, lane, pps, m.score_l + m.score_r);
     p.bx = p.by = p.bvx = p.bvy = 0.0f;
   }
@@ -381,6 +395,7 @@ __device__ __forceinline__ void fg_load(const KernelParams& P, const FgLayout& L
   const uint4 ej = *(reinterpret_cast<const uint4*>(base + L.ej()) + env);
   p.bx = ball.x; p.by = ball.y; p.bvx = ball.z; p.bvy = ball.w;
   m.ep_return = ef.x;
+  m.sep = ef.y;
   m.step_number = static_cast<int>(ei.x); m.cycle = ei.y; m.episode = ei.z;
   m.mode = ei.w & 0xff; m.side = (ei.w >> 8) & 3; m.last_touch = (ei.w >> 10) & 3; m.timer = (ei.w >> 12) & 0xff;
   m.done_flag = (ei.w >> 21) & 1;
@@ -399,7 +414,7 @@ __device__ __forceinline__ void fg_store(const KernelParams& P, const FgLayout& 
   }
   if (lane == 0) {
     *(reinterpret_cast<float4*>(base + L.eb()) + env) = make_float4(p.bx, p.by, p.bvx, p.bvy);
-    *(reinterpret_cast<float4*>(base + L.ef()) + env) = make_float4(m.ep_return, 0.0f, 0.0f, 0.0f);
+    *(reinterpret_cast<float4*>(base + L.ef()) + env) = make_float4(m.ep_return, m.sep, 0.0f, 0.0f);
     const uint32_t packed = static_cast<uint32_t>(m.mode) | (static_cast<uint32_t>(m.side) << 8) |
                             (static_cast<uint32_t>(m.last_touch) << 10) | (static_cast<uint32_t>(m.timer) << 12) |
                             (ball_collided ? 1u << 20 : 0u) | (m.done_flag ? 1u << 21 : 0u);

@@ -366,12 +366,125 @@ def run_b200(args, rank, local_rank, world):
         dist.destroy_process_group()
 
 
+def run_other_workload(args, rank, local_rank, world):
+    """--workload shoot | fullgame: BASELINE configs[2] (1v0 shoot, 4M envs in total) and configs[3] (11v11, 256K
+    matches in total), sharded over the ranks (strong scaling, shard_range), command actions resident in HBM.
+    Same timing rules as the main arm; prints one JSON line with value, roofline and the pipelined e2e."""
+    import torch
+    import torch.distributed as dist
+
+    from soccer2d_b200 import Soccer2DVecEnv, shard_range
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    k = args.substeps
+    gen = torch.Generator(device=dev).manual_seed(99 + rank)
+
+    def commands(shape):
+        a = torch.zeros(shape + (4,), device=dev)
+        cmd = torch.randint(0, 5, shape, device=dev, generator=gen)
+        u = lambda: torch.rand(shape, device=dev, generator=gen)  # noqa: E731
+        a[..., 0] = cmd.float()
+        a[..., 1] = torch.where(cmd == 4, u() * 100 - 50, u() * 100)
+        a[..., 2] = torch.where(cmd == 4, u() * 60 - 30, u() * 360 - 180)
+        a[..., 3] = 100.0
+        return a
+
+    if args.workload == "shoot":
+        total = args.envs if args.envs != ENVS_PER_GPU else 1 << 22
+        off, n = shard_range(rank, world, total)
+        env = Soccer2DVecEnv(n, scenario="shoot", device=dev, seed=0, substeps=k, env_id_offset=off, use_command_action=True)
+        pool = [commands((n, k)) for _ in range(2)]
+        per_env = 2 * STATE_BYTES + 16 * k + OBS_BYTES + OUT_BYTES
+        name = f"1v0 shoot-on-goal, {total} envs in total, proto-style command actions (dash/turn/kick/go-to-point), K={k}"
+        kernel = "s2d::step_kernel<SHOOT, COMMAND, default ServerParam>"
+    else:
+        total = args.envs if args.envs != ENVS_PER_GPU else 1 << 18
+        off, n = shard_range(rank, world, total)
+        env = Soccer2DVecEnv(n, scenario="fullgame", device=dev, seed=0, substeps=k, env_id_offset=off)
+        pool = [commands((n, k, 22)) for _ in range(2)]
+        per_env = 2 * (22 * 36 + 64) + 22 * 16 * k + 480 + OUT_BYTES
+        name = f"11v11 full game, {total} matches in total, one command per player per cycle, K={k}"
+        kernel = "s2d::fullgame_step_kernel<default ServerParam>"
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    env.reset_torch()
+    time_launches(env, pool, max(args.warmup, 3), flush)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    ms = time_launches(env, pool, args.steps, flush)
+    barrier()
+    total_ms = max_over_ranks(sum(ms))
+    value = total * k * args.steps / (total_ms * 1e-3)
+    launch_ms = sum(ms) / len(ms)
+    # e2e, pipelined host buffers
+    host_pool = [p.cpu().pin_memory() for p in pool]
+    e2e_steps = max(3, min(args.steps, 20))
+    env.enable_pipeline()
+    env.wait_host(env.submit_host(host_pool[0]))
+    barrier()
+    t0 = time.perf_counter()
+    ticket = env.submit_host(host_pool[0])
+    checksum = 0.0
+    for i in range(1, e2e_steps):
+        nxt = env.submit_host(host_pool[i % 2])
+        checksum += float(env.wait_host(ticket)[1][0])
+        ticket = nxt
+    checksum += float(env.wait_host(ticket)[1][0])
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    hb = env._pipe["host"][0]
+    h2d = pool[0].numel() * pool[0].element_size()
+    d2h = sum(hb[x].numel() * hb[x].element_size() for x in ("obs", "reward", "done", "result"))
+    stats = env.allreduce_stats()
+    clocks = sampler.summary()
+    env.close()
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        ach = per_env * n / (launch_ms * 1e-3) / 1e9
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": name, "envs_per_gpu": n, "substeps": k, "global_envs": total,
+                       "parallelism": f"episode-shard x{world}", "l2": "flushed between timed launches (256 MiB memset, not timed)"},
+            "e2e": {"value": total * k * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3,
+                    "path": "Soccer2DVecEnv.submit_host / wait_host (s2d_submit_host / s2d_wait_host), pinned host buffers"},
+            "gpu_launches": args.steps,
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                         "kernel": kernel, "launch_ms": launch_ms, "algorithmic_bytes_per_launch": per_env * n,
+                         "peak_source": peak_src},
+            "clocks": clocks, "episode_stats": stats}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="reachball", choices=["reachball", "shoot", "fullgame"],
+                    help="reachball = BASELINE configs[1] (the contract line); shoot / fullgame = configs[2] / [3]")
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="episodes per GPU (default 2^20, configs[1])")
     ap.add_argument("--substeps", type=int, default=SUBSTEPS)
     ap.add_argument("--envs-k1", type=int, default=1 << 23, help="episodes per GPU of the K=1 roofline run")
@@ -386,6 +499,11 @@ def main():
     if world != args.gpus and world == 1 and args.gpus > 1:
         raise SystemExit(f"--gpus {args.gpus} needs torchrun: python -m torch.distributed.run --nproc-per-node {args.gpus} "
                          f"--master-addr 127.0.0.1 bench.py --gpus {args.gpus} ...")
+    if args.workload != "reachball":
+        if args.substeps == SUBSTEPS:
+            args.substeps = 1
+        run_other_workload(args, rank, local_rank, world)
+        return
     run_b200(args, rank, local_rank, world)
 
 

@@ -645,3 +645,126 @@ class ReachBallOracle:
             term = obs
             obs = self.reset()
         return obs, reward, done, result, term
+
+
+# ----------------------------------------------------------------------------------------------
+# Shoot: 1v0 shoot-on-goal (BASELINE configs[2]).  NOT in the reference; the contract is specified in
+# include/soccer2d.h.  Second restatement (next to oracle/s2d_oracle.c) so that the two can be checked
+# against each other.
+# ----------------------------------------------------------------------------------------------
+
+
+@dataclass
+class ShootConfig:
+    change_ball_position: bool = True
+    change_ball_velocity: bool = False
+    ball_position_x: float = 0.0
+    ball_position_y: float = 0.0
+    ball_speed: float = 0.0
+    ball_direction: float = 0.0
+    max_steps: int = 200
+    action_space_size: int = 24
+    kick_actions: int = 8
+    goto_dist_thr: float = 0.5
+    seed: int = 0
+    sp: ServerParam = field(default_factory=ServerParam)
+    # ReachBallOracle.sample_reset reads these
+    min_distance_to_ball: float = 5.0
+
+
+def check_shoot(cfg, mem_pb, mem_bg, step_number, bx, by, px, py, prev_bx, prev_by):
+    """-> (done, reward, result, d_player_ball, d_ball_goal); all positions as the proto float32 holds them."""
+    sp = cfg.sp
+    d_pb = hypot2(bx - px, by - py)
+    d_bg = hypot2(sp.pitch_half_length - bx, 0.0 - by)
+    reward = (mem_pb - d_pb) * 0.2 + (mem_bg - d_bg)
+    line = sp.pitch_half_length + sp.ball_size
+    post = sp.goal_width / 2.0 + sp.goal_post_radius
+    goal = False
+    if bx > line and not prev_bx > line:
+        yc = prev_by + (by - prev_by) * ((line - prev_bx) / (bx - prev_bx))
+        goal = math.fabs(yc) <= post
+    out = (not goal) and (math.fabs(bx) > line or math.fabs(by) > sp.pitch_half_width + sp.ball_size)
+    done, result = False, RESULT_NONE
+    if goal:
+        done, reward, result = True, reward + 10.0, RESULT_GOAL
+    elif out:
+        done, reward, result = True, reward - 10.0, RESULT_OUT
+    elif step_number > cfg.max_steps:
+        done, reward, result = True, reward - 5.0, RESULT_TIMEOUT
+    return done, reward, result, d_pb, d_bg
+
+
+class ShootOracle(ReachBallOracle):
+    """One Shoot episode stream.  Actions: ('discrete', a) or a 4-tuple command (cmd, a, b, c)."""
+
+    def _dirs(self, a, n):
+        return f32((a * 360.0 / n) % 360.0 - 180.0)
+
+    def decode(self, action):
+        cfg = self.cfg
+        if isinstance(action, (int,)) or (hasattr(action, "dtype") and action.ndim == 0):
+            a = int(action)
+            n_dash = cfg.action_space_size - cfg.kick_actions
+            if a < n_dash:
+                return CMD_DASH, 100.0, self._dirs(a, n_dash)
+            return CMD_KICK, 100.0, self._dirs(a - n_dash, cfg.kick_actions)
+        c, a1, a2, a3 = (float(v) for v in action)
+        c = int(c)
+        if c in (CMD_DASH, CMD_KICK):
+            return c, a1, a2
+        if c == CMD_TURN:
+            return c, 0.0, a1
+        if c == CMD_GOTO:
+            return lower_goto(self.player, a1, a2, f32(cfg.goto_dist_thr), a3, self.sp)
+        return CMD_NONE, 0.0, 0.0
+
+    def _simulate_cycle(self, cmd, power, direction):
+        sp, p, b = self.sp, self.player, self.ball
+        p.kicked = False
+        if cmd == CMD_DASH:
+            cmd_dash(p, power, direction, sp)
+        elif cmd == CMD_TURN:
+            cmd_turn(p, direction, sp)
+        elif cmd == CMD_KICK:
+            cmd_kick(p, b, power, direction, sp)
+        obj_inc(p, sp.player_accel_max, sp.player_speed_max, sp.player_decay)
+        obj_inc(b, sp.ball_accel_max, sp.ball_speed_max, sp.ball_decay)
+        collisions(b, [p], sp)
+        update_stamina(p, sp)
+        self.cycle += 1
+
+    def _check(self):
+        bx, by, _, _, px, py, _ = self.quantised()
+        return check_shoot(self.cfg, self.mem_dist, self.mem_ang, self.step_number, bx, by, px, py,
+                           f32(self._prev_ball[0]), f32(self._prev_ball[1]))
+
+    def reset(self):
+        px, py, body, bx, by, bvx, bvy = self.sample_reset()
+        self.episode += 1
+        self.step_number = 0
+        self.ep_return = 0.0
+        b, p = self.ball, self.player
+        b.x, b.y, b.vx, b.vy, b.ax, b.ay = bx, by, bvx, bvy, 0.0, 0.0
+        p.x, p.y, p.vx, p.vy, p.ax, p.ay = px, py, 0.0, 0.0, 0.0, 0.0
+        p.body = norm_deg(body)
+        player_recover(p, self.sp)
+        self._prev_ball = (b.x, b.y)
+        self._simulate_cycle(CMD_NONE, 0.0, 0.0)
+        obs = self.observe()
+        _, _, _, self.mem_dist, self.mem_ang = self._check()
+        return obs
+
+    def step(self, action):
+        self.step_number += 1
+        cmd, power, direction = self.decode(action)
+        self._prev_ball = (self.ball.x, self.ball.y)
+        self._simulate_cycle(cmd, power, direction)
+        obs = self.observe()
+        done, reward, result, self.mem_dist, self.mem_ang = self._check()
+        self.ep_return += reward
+        term = None
+        if done and self.auto_reset:
+            term = obs
+            obs = self.reset()
+        return obs, reward, done, result, term

@@ -157,3 +157,36 @@ def test_fp32_flag_flips_are_rare_and_near_thresholds():
         _, _, ds, _ = s.step(act)
         alive &= dt == ds
     assert (~alive).sum() <= 4  # <= 1e-3 of the envs, ~2.5e-6 per env-step
+
+
+@pytest.mark.parametrize("mode", ["discrete", "command"])
+def test_shoot_c_f64_equals_python_oracle(mode):
+    """The Shoot scenario has no counterpart in the reference; its two restatements (C and Python) must agree."""
+    n, steps = 5, 500
+    cfg = H.make_config(n, mode, scenario=_abi.SCENARIO_SHOOT, seed=4, env_id_offset=50, max_steps=120, goto_dist_thr=0.5)
+    sim = OL.OracleSim(cfg, "f64")
+    pc = O.ShootConfig(seed=4, max_steps=120, sp=O.ServerParam().as_f32())
+    py = [O.ShootOracle(pc, env_id=50 + i) for i in range(n)]
+    obs = sim.reset().copy()
+    for i, o in enumerate(py):
+        assert np.allclose(o.reset(), obs[i], rtol=0, atol=1e-12)
+    rng = np.random.default_rng(6)
+    results = set()
+    kicks = 0
+    for _ in range(steps):
+        if mode == "discrete":
+            act = rng.integers(0, 24, size=(n, 1)).astype(np.uint8)
+        else:
+            act = H.chase_and_shoot(sim.obs, rng, kick_prob=0.9)
+            act = np.where(rng.uniform(size=(n, 1, 1)) < 0.1, H.random_commands(rng, n), act).astype(np.float32)
+        obs, rew, done, res = sim.step(act)
+        for i, o in enumerate(py):
+            a = int(act[i, 0]) if mode == "discrete" else act[i, 0]
+            po, pr, pd, pres, _ = o.step(a)
+            assert pd == bool(done[i]) and pres == int(res[i])
+            assert pr == pytest.approx(float(rew[i]), rel=1e-10, abs=1e-10)
+            assert H.obs_close(po, obs[i], 0) < 1e-10
+            results.add(pres)
+            kicks += o.player.kicked
+    if mode == "command":
+        assert {0, 1} <= results and kicks > 20

@@ -621,3 +621,48 @@ def test_noise_on_bit_exact_and_reproducible(scenario, mode, k):
     quiet = OL.OracleSim(H.make_config(n, mode, scenario=env.cfg.scenario, seed=31, change_ball_velocity=1, max_steps=100), "f32")
     quiet.reset()
     assert not np.array_equal(quiet.obs, sim.obs)
+
+
+@pytest.mark.parametrize("scenario,n", [("reachball", 33), ("reachball", 257), ("shoot", 130), ("fullgame", 7)])
+def test_kernels_stay_inside_their_buffers(scenario, n):
+    """compute-sanitizer is not available on this pool, so: every buffer is bound as the middle of a larger tensor
+    filled with a sentinel, ragged sizes, K > 1, terminal obs on - the guard bytes on both sides must survive."""
+    import ctypes as C
+    lib = _abi.load()
+    env = Soccer2DVecEnv(n, scenario=scenario, device="cuda:0", seed=1, substeps=3, terminal_obs=True,
+                         **({"use_continuous_action": False, "max_steps": 4, "change_ball_velocity": True} if scenario == "reachball"
+                            else {"max_steps": 4} if scenario == "shoot" else {"half_time_cycles": 3}))
+    guard = 4096
+    big = {}
+
+    def guarded(t):
+        nbytes = t.numel() * t.element_size()
+        buf = torch.full((nbytes + 2 * guard,), 0xA5, dtype=torch.uint8, device="cuda")
+        big[len(big)] = (buf, nbytes)
+        buf[guard:guard + nbytes] = 0
+        return buf[guard:guard + nbytes]
+
+    views = {k: guarded(getattr(env, k)) for k in ("state", "obs", "reward", "done_u8", "result", "terminal_obs", "stats_buf")}
+    actions = guarded(env.actions)
+    if env.actions.dtype == torch.uint8:
+        actions.copy_(torch.randint(0, 16, (actions.numel(),), dtype=torch.uint8, device="cuda"))
+    else:
+        a = torch.rand(env.actions.shape, device="cuda") * 100 - 50
+        a[..., 0] = torch.randint(0, 5, a.shape[:-1], device="cuda").float()
+        actions.copy_(a.view(-1).view(torch.uint8))
+    b = _abi.Buffers(state=views["state"].data_ptr(), actions=actions.data_ptr(), obs=views["obs"].data_ptr(),
+                     reward=views["reward"].data_ptr(), done=views["done_u8"].data_ptr(), result=views["result"].data_ptr(),
+                     terminal_obs=views["terminal_obs"].data_ptr(), stats=views["stats_buf"].data_ptr())
+    torch.cuda.synchronize()
+    _abi.check(lib.s2d_bind(env.handle, C.byref(b)), env.handle)
+    stream = torch.cuda.current_stream().cuda_stream
+    _abi.check(lib.s2d_reset(env.handle, None, stream), env.handle)
+    for _ in range(6):
+        _abi.check(lib.s2d_step(env.handle, 3, stream), env.handle)
+    mask = torch.ones(n, dtype=torch.uint8, device="cuda")
+    _abi.check(lib.s2d_reset(env.handle, mask.data_ptr(), stream), env.handle)
+    torch.cuda.synchronize()
+    for buf, nbytes in big.values():
+        assert bool((buf[:guard] == 0xA5).all()) and bool((buf[guard + nbytes:] == 0xA5).all())
+    assert float(views["obs"].view(torch.float32).abs().sum()) > 0  # the kernels did write
+    env.close()

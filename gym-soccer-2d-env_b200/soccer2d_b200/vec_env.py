@@ -38,11 +38,17 @@ _SCENARIOS = {"reachball": _abi.SCENARIO_REACHBALL, "shoot": _abi.SCENARIO_SHOOT
 _DEFAULTS = {"reachball": REACHBALL_DEFAULTS, "shoot": SHOOT_DEFAULTS, "fullgame": FULLGAME_DEFAULTS}
 
 
+try:  # when Stable-Baselines3 is installed, be a real VecEnv so that SB3 does not wrap us in a DummyVecEnv
+    from stable_baselines3.common.vec_env import VecEnv as _VecEnvBase  # type: ignore
+except Exception:  # noqa: BLE001 - SB3 is not part of this image
+    _VecEnvBase = object
+
+
 def _stream_ptr(device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
 
-class Soccer2DVecEnv:
+class Soccer2DVecEnv(_VecEnvBase):
     """`num_envs` ReachBall episodes on one GPU.
 
     num_envs       episodes held by THIS process (its shard)
@@ -179,6 +185,8 @@ class Soccer2DVecEnv:
         self._pinned = None
         self._pipe = None
         self._pending = None
+        if _VecEnvBase is not object:
+            _VecEnvBase.__init__(self, self.num_envs, self.observation_space, self.action_space)
         self._closed = False
 
     # ---- torch-native API: device tensors in, device tensors out, no host sync ------------------------

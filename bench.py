@@ -312,6 +312,29 @@ def run_b200(args, rank, local_rank, world):
         del envr
     clocks = sampler.summary()
 
+    # ---- configs[0]: ONE env behind the reference's gym API (reset / step -> 4-tuple), host round trip every step ----
+    single = None
+    if rank == 0 and world == 1:
+        from sample_environments.environment_factory import EnvironmentFactory
+        genv = EnvironmentFactory().create("ReachBall", None, None, None, device=dev, seed=0, **SCENARIO_KW)
+        import numpy as _np
+        arng = _np.random.default_rng(0)
+        acts = arng.integers(0, 16, size=4000)
+        genv.reset()
+        for a in acts[:200]:
+            if genv.step(int(a))[2]:
+                genv.reset()
+        t0 = time.perf_counter()
+        episodes = 0
+        for a in acts[200:]:
+            if genv.step(int(a))[2]:
+                genv.reset()
+                episodes += 1
+        dt = time.perf_counter() - t0
+        genv.close()
+        single = {"value": (len(acts) - 200) / dt, "unit": "env-steps/s", "steps": len(acts) - 200, "episodes": episodes,
+                  "path": "EnvironmentFactory().create('ReachBall').step(a): s2d_step_host on 1 env, stream sync, numpy 4-tuple"}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -356,6 +379,7 @@ def run_b200(args, rank, local_rank, world):
         "rollout_dqn": {"unit": UNIT + " per GPU", "policy": "64-64 ReLU MLP (SB3 DQN MlpPolicy shape), greedy, K=1, zero-copy "
                         "obs/action tensors (torch fp32 matmuls for the policy, not part of the step path)",
                         "envs_to_value": rollout},
+        "single_env_gym_api": single,
         "clocks": clocks,
         "episode_stats": stats,
     }

@@ -66,6 +66,9 @@ class Soccer2DVecEnv(_VecEnvBase):
     noise          rcssserver's player_rand / ball_rand / kick_rand noise from the counter-based RNG, keyed on
                    (seed, global env id, server cycle, agent): reproducible, independent of sharding and of
                    `substeps`.  Off by default (the mode in which runs are compared with the double-precision CPU truth)
+    host_mapped_io actions / obs / reward / done / result live in PINNED HOST memory that the kernel reads and writes
+                   directly over PCIe (unified addressing): no memcpy calls at all - the lowest-latency path for a
+                   handful of envs (the single-env gym API uses it); the state stays in HBM
     **kwargs       the scenario kwargs: ReachBallEnv's (same names and defaults as the reference) or SHOOT_DEFAULTS
     """
 
@@ -74,7 +77,7 @@ class Soccer2DVecEnv(_VecEnvBase):
     def __init__(self, num_envs: int, scenario: str = "reachball", device="cuda", seed: int = 0, substeps: int = 1,
                  env_id_offset: int = 0, auto_reset: bool = True, terminal_obs: bool = False,
                  server_param: dict | None = None, use_command_action: bool = False, goto_dist_thr: float = 0.5,
-                 noise: bool = False, **kwargs):
+                 noise: bool = False, host_mapped_io: bool = False, **kwargs):
         if scenario.lower() not in _SCENARIOS:
             raise ValueError(f"Environment {scenario} not found.")  # environment_factory.py:28
         self.scenario = scenario.lower()
@@ -159,23 +162,29 @@ class Soccer2DVecEnv(_VecEnvBase):
 
         # ---- device buffers: owned here (PyTorch), bound into the handle ---------------------------
         n, k, dev = self.num_envs, self.substeps, self.device
+        self.host_mapped_io = bool(host_mapped_io)
         self.obs_dim = self.lib.s2d_obs_dim(C.byref(cfg))
         self.state = torch.zeros(self.lib.s2d_state_bytes(C.byref(cfg)), dtype=torch.uint8, device=dev)
-        if cfg.action_mode == _abi.ACT_DISCRETE:
-            self.actions = torch.zeros((n, k), dtype=torch.uint8, device=dev)
-        elif cfg.action_mode == _abi.ACT_CONTINUOUS:
-            self.actions = torch.zeros((n, k), dtype=torch.float32, device=dev)
-        elif self.scenario == "fullgame":
-            self.actions = torch.zeros((n, k, self.num_players, 4), dtype=torch.float32, device=dev)
+        if self.host_mapped_io:
+            torch.cuda.init()
+            io = lambda shape, dt: torch.zeros(shape, dtype=dt).pin_memory()  # noqa: E731  device-visible host memory
         else:
-            self.actions = torch.zeros((n, k, 4), dtype=torch.float32, device=dev)
+            io = lambda shape, dt: torch.zeros(shape, dtype=dt, device=dev)  # noqa: E731
+        if cfg.action_mode == _abi.ACT_DISCRETE:
+            self.actions = io((n, k), torch.uint8)
+        elif cfg.action_mode == _abi.ACT_CONTINUOUS:
+            self.actions = io((n, k), torch.float32)
+        elif self.scenario == "fullgame":
+            self.actions = io((n, k, self.num_players, 4), torch.float32)
+        else:
+            self.actions = io((n, k, 4), torch.float32)
         assert self.actions.numel() * self.actions.element_size() == self.lib.s2d_action_bytes(C.byref(cfg)) * k
-        self.obs = torch.zeros((n, self.obs_dim), dtype=torch.float32, device=dev)
-        self.reward = torch.zeros(n, dtype=torch.float32, device=dev)
-        self.done_u8 = torch.zeros(n, dtype=torch.uint8, device=dev)
+        self.obs = io((n, self.obs_dim), torch.float32)
+        self.reward = io(n, torch.float32)
+        self.done_u8 = io(n, torch.uint8)
         self.done = self.done_u8.view(torch.bool)
-        self.result = torch.zeros(n, dtype=torch.uint8, device=dev)
-        self.terminal_obs = torch.zeros((n, self.obs_dim), dtype=torch.float32, device=dev) if terminal_obs else None
+        self.result = io(n, torch.uint8)
+        self.terminal_obs = io((n, self.obs_dim), torch.float32) if terminal_obs else None
         self.stats_buf = torch.zeros(self.lib.s2d_stats_bytes(C.byref(cfg)), dtype=torch.uint8, device=dev)
         self._bufs = bufs = _abi.Buffers(
             state=self.state.data_ptr(), actions=self.actions.data_ptr(), obs=self.obs.data_ptr(),
@@ -235,6 +244,12 @@ class Soccer2DVecEnv(_VecEnvBase):
         obs/reward/done/result are enqueued by ONE C-ABI call (s2d_step_host), then the stream is drained.
         `actions`: numpy array / CPU tensor of the action shape (pinned memory makes the copy asynchronous),
         or None to submit host_buffers()['actions'].  Returns numpy views of the pinned output buffers."""
+        if self.host_mapped_io:  # the kernel reads the actions from / writes the results to host memory itself
+            if actions is not None:
+                self.actions.numpy()[...] = np.asarray(actions).reshape(tuple(self.actions.shape))
+            _abi.check(self.lib.s2d_step(self.handle, self.substeps, _stream_ptr(self.device)), self.handle)
+            torch.cuda.current_stream(self.device).synchronize()
+            return self.obs.numpy(), self.reward.numpy(), self.done_u8.numpy().view(np.bool_), self.result.numpy()
         p = self.host_buffers()
         if actions is None:
             src = p["actions"]
@@ -300,7 +315,11 @@ class Soccer2DVecEnv(_VecEnvBase):
 
     # ---- SB3 VecEnv surface ---------------------------------------------------------------------------
     def reset(self) -> np.ndarray:
-        return self.reset_torch().cpu().numpy()
+        obs = self.reset_torch()
+        if self.host_mapped_io:
+            torch.cuda.current_stream(self.device).synchronize()
+            return obs.numpy().copy()
+        return obs.cpu().numpy()
 
     def step_async(self, actions) -> None:
         self._pending = actions

@@ -3,8 +3,8 @@ new internals.
 
 The reference's constructor spawns a gRPC server process, an rcssserver and a proxy, and every `step`
 blocks on four multiprocessing queues (soccer_2d_env.py:226-269).  Here the episode lives in GPU memory
-inside a one-env `Soccer2DVecEnv` and `step` is one C-ABI call (s2d_step_host): H2D of the action, one
-fused kernel (decode + server cycle + reward/done + observation), D2H of the results.
+inside a one-env `Soccer2DVecEnv` and `step` is one C-ABI call (s2d_step): one fused kernel (decode + server
+cycle + reward/done + observation) that reads the action from and writes the results to pinned host memory.
 
 Kept: constructor signature (`render_mode, run_grpc_server, run_rcssserver, run_trainer_player, logger,
 log_dir`; the three run_* flags are accepted and ignored - there is nothing to spawn), `metadata`,
@@ -46,7 +46,7 @@ class Soccer2DEnv(Env):
         self.observation_space = Box(low=-1, high=1, shape=(2,), dtype=np.float32)
         self._vec = Soccer2DVecEnv(1, scenario=self.scenario, device=device, seed=seed, substeps=1, auto_reset=False,
                                    server_param=server_param, use_command_action=use_command_action,
-                                   noise=noise, **scenario_kwargs)
+                                   noise=noise, host_mapped_io=True, **scenario_kwargs)
         self.action_space = self._vec.action_space
         self.observation_space = self._vec.observation_space
         self.step_number = 0

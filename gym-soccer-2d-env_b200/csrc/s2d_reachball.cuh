@@ -406,9 +406,8 @@ __global__ void __launch_bounds__(kBlock, S2D_MIN_BLOCKS) step_kernel(const __gr
     if (ACT == S2D_ACT_DISCRETE) {
       // the 4 KB action table stays in L1 (read-only path); `act` walks the lane's K action bytes
       const uint8_t* act = static_cast<const uint8_t*>(P.actions) + i * K;
-      const uint8_t* const end = act + K;
 #pragma unroll 1
-      for (; act != end; ++act) {
+      for (int k = K; k > 0; --k, ++act) {
         if (SCN == S2D_SCENARIO_SHOOT) {
           const float4 t = __ldg(P.action_table + __ldg(act));
           substep<SCN, ACT>(e, P, sp, gid, i, t.x, t.y, t.z, t.w, out);

@@ -270,8 +270,12 @@ __device__ __forceinline__ bool fg_cycle(Episode& p, Match& m, const KernelParam
       kicked = kick(p, power, dir, sp, kax, kay, nz, static_cast<uint32_t>(lane));
     }
   }
-  const float bax = butterfly_sum(kax), bay = butterfly_sum(kay);
   const unsigned kick_ballot = __ballot_sync(full, kicked);
+  float bax = 0.0f, bay = 0.0f;
+  if (kick_ballot) {  // uniform; without a kicker both sums are exactly zero
+    bax = butterfly_sum(kax);
+    bay = butterfly_sum(kay);
+  }
   const unsigned left_lanes = (1u << pps) - 1u;
   const bool kick_l = (kick_ballot & left_lanes) != 0, kick_r = (kick_ballot & ~left_lanes) != 0;
   if (kick_l != kick_r) m.last_touch = kick_l ? S2D_SIDE_LEFT : S2D_SIDE_RIGHT;

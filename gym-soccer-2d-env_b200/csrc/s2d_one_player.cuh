@@ -175,7 +175,8 @@ __device__ __forceinline__ void lower_goto(const Episode& e, float tx, float ty,
   if (dist < dist_thr) return;
   const float ang = norm_deg_360(atan2_deg(dy, dx) - e.body);
   const float ratio = dist_thr / dist;
-  const float athr = fmax_(15.0f, atan2_deg(ratio, sqrtf(fmax_(0.0f, 1.0f - ratio * ratio))));
+  // asin(ratio) exceeds 15 degrees only for ratio > sin(15 deg) = 0.2588: below 0.25 the threshold is exactly 15
+  const float athr = ratio > 0.25f ? fmax_(15.0f, atan2_deg(ratio, sqrtf(fmax_(0.0f, 1.0f - ratio * ratio)))) : 15.0f;
   if (fabsf(ang) > athr) {
     const float speed = hypot2(e.vx, e.vy);
     cmd = S2D_CMD_TURN;

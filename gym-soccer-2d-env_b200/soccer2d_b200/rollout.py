@@ -202,3 +202,143 @@ def measure_rollout(env, qnet: nn.Module, steps: int, warmup: int = 5) -> float:
     e.record()
     torch.cuda.synchronize()
     return env.num_envs * steps / (s.elapsed_time(e) * 1e-3)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# DDPG (continuous actions) - the counterpart of the reference's ddpg_stable_baselines3.py
+# ---------------------------------------------------------------------------------------------------------
+
+class Actor(nn.Module):
+    """obs -> action in [-1, 1]^A (tanh), 64-64 ReLU"""
+
+    def __init__(self, obs_dim: int, act_dim: int, hidden: int = 64):
+        super().__init__()
+        self.net = nn.Sequential(nn.Linear(obs_dim, hidden), nn.ReLU(), nn.Linear(hidden, hidden), nn.ReLU(),
+                                 nn.Linear(hidden, act_dim), nn.Tanh())
+
+    def forward(self, obs):
+        return self.net(obs)
+
+
+class Critic(nn.Module):
+    def __init__(self, obs_dim: int, act_dim: int, hidden: int = 64):
+        super().__init__()
+        self.net = nn.Sequential(nn.Linear(obs_dim + act_dim, hidden), nn.ReLU(), nn.Linear(hidden, hidden), nn.ReLU(),
+                                 nn.Linear(hidden, 1))
+
+    def forward(self, obs, act):
+        return self.net(torch.cat([obs, act], dim=1)).squeeze(1)
+
+
+@dataclass
+class DDPGConfig:
+    gamma: float = 0.99
+    lr: float = 1e-3                 # SB3 DDPG default
+    tau: float = 0.005
+    batch_size: int = 4096
+    buffer_size: int = 1 << 21
+    learning_starts: int = 1 << 16
+    action_noise: float = 0.2        # std of the Gaussian exploration noise (SB3: user-supplied NormalActionNoise)
+    seed: int = 0
+    log: list = field(default_factory=list)
+
+
+class DeviceDDPG:
+    """DDPG with the rollout, the replay buffer and the learner on the GPU.  `env`: a Box(-1, 1, (1,)) ReachBall
+    Soccer2DVecEnv (use_continuous_action=True, use_turning=False) with substeps=1, auto_reset and terminal_obs."""
+
+    def __init__(self, env, cfg: DDPGConfig | None = None):
+        assert env.substeps == 1 and env.auto_reset and env.terminal_obs is not None
+        assert env.actions.dtype == torch.float32 and env.actions.dim() == 2, "Box(-1, 1, (1,)) action space required"
+        self.env, self.cfg, self.device = env, cfg or DDPGConfig(), env.device
+        torch.manual_seed(self.cfg.seed)
+        od, ad = env.obs_dim, 1
+        self.actor, self.actor_t = Actor(od, ad).to(self.device), Actor(od, ad).to(self.device)
+        self.critic, self.critic_t = Critic(od, ad).to(self.device), Critic(od, ad).to(self.device)
+        self.actor_t.load_state_dict(self.actor.state_dict())
+        self.critic_t.load_state_dict(self.critic.state_dict())
+        self.opt_a = torch.optim.Adam(self.actor.parameters(), lr=self.cfg.lr)
+        self.opt_c = torch.optim.Adam(self.critic.parameters(), lr=self.cfg.lr)
+        n = self.cfg.buffer_size
+        dev = self.device
+        self.b_obs = torch.empty((n, od), device=dev)
+        self.b_next = torch.empty((n, od), device=dev)
+        self.b_act = torch.empty((n, ad), device=dev)
+        self.b_rew = torch.empty(n, device=dev)
+        self.b_done = torch.empty(n, dtype=torch.bool, device=dev)
+        self.pos = self.size = 0
+        self.gen = torch.Generator(device=dev).manual_seed(self.cfg.seed)
+        self.env_steps = 0
+        self._obs = env.reset_torch().clone()
+
+    def _store(self, obs, act, rew, nxt, done):
+        n, cap = obs.shape[0], self.cfg.buffer_size
+        idx = (torch.arange(n, device=self.device) + self.pos) % cap
+        self.b_obs[idx], self.b_act[idx], self.b_rew[idx], self.b_next[idx], self.b_done[idx] = obs, act, rew, nxt, done
+        self.pos = (self.pos + n) % cap
+        self.size = min(cap, self.size + n)
+
+    @torch.no_grad()
+    def rollout_step(self, noise_std: float, store: bool = True, random: bool = False):
+        env = self.env
+        if random:
+            a = torch.rand((env.num_envs, 1), device=self.device, generator=self.gen) * 2 - 1
+        else:
+            a = self.actor(self._obs)
+            if noise_std > 0:
+                a = (a + noise_std * torch.randn(a.shape, device=self.device, generator=self.gen)).clamp_(-1, 1)
+        env.actions.copy_(a)  # [N, 1] float32: written in place, zero copy
+        obs, reward, done, _ = env.step_torch()
+        if store:
+            nxt = torch.where(done.unsqueeze(1), env.terminal_obs, obs)
+            self._store(self._obs, a, reward, nxt, done)
+        self._obs.copy_(obs)
+        self.env_steps += 1
+
+    def train_step(self):
+        c = self.cfg
+        idx = torch.randint(0, self.size, (c.batch_size,), device=self.device, generator=self.gen)
+        obs, act, rew, nxt, done = self.b_obs[idx], self.b_act[idx], self.b_rew[idx], self.b_next[idx], self.b_done[idx]
+        with torch.no_grad():
+            target = rew + c.gamma * (~done).float() * self.critic_t(nxt, self.actor_t(nxt))
+        loss_c = nn.functional.mse_loss(self.critic(obs, act), target)
+        self.opt_c.zero_grad(set_to_none=True)
+        loss_c.backward()
+        self.opt_c.step()
+        loss_a = -self.critic(obs, self.actor(obs)).mean()
+        self.opt_a.zero_grad(set_to_none=True)
+        loss_a.backward()
+        self.opt_a.step()
+        with torch.no_grad():
+            for net, tgt in ((self.actor, self.actor_t), (self.critic, self.critic_t)):
+                for p, pt in zip(net.parameters(), tgt.parameters()):
+                    pt.lerp_(p, c.tau)
+
+    def learn(self, total_steps: int, report_every: int = 0):
+        c, env = self.cfg, self.env
+        last, t0 = env.stats(), time.perf_counter()
+        for step in range(1, total_steps + 1):
+            warm = self.size < c.learning_starts
+            self.rollout_step(c.action_noise, random=warm)
+            if not warm:
+                self.train_step()
+            if report_every and step % report_every == 0:
+                now = env.stats()
+                d = {k: now[k] - last[k] for k in ("episodes", "goals", "outs", "timeouts", "return_sum")}
+                last = now
+                ep = max(1, d["episodes"])
+                c.log.append({"step": step, "transitions": step * env.num_envs, "episodes": d["episodes"],
+                              "goal_rate": d["goals"] / ep, "out_rate": d["outs"] / ep, "timeout_rate": d["timeouts"] / ep,
+                              "mean_return": d["return_sum"] / ep, "wall_s": round(time.perf_counter() - t0, 2)})
+        return c.log
+
+    @torch.no_grad()
+    def evaluate(self, steps: int) -> dict:
+        before = self.env.stats()
+        for _ in range(steps):
+            self.rollout_step(0.0, store=False)
+        after = self.env.stats()
+        d = {k: after[k] - before[k] for k in ("episodes", "goals", "outs", "timeouts", "return_sum")}
+        ep = max(1, d["episodes"])
+        return {"episodes": d["episodes"], "goal_rate": d["goals"] / ep, "out_rate": d["outs"] / ep,
+                "timeout_rate": d["timeouts"] / ep, "mean_return": d["return_sum"] / ep}

@@ -71,3 +71,19 @@ def test_measure_rollout_runs():
     q = QNetwork(10, 16).to("cuda:0")
     rate = measure_rollout(env, q, steps=20)
     assert rate > 1e7
+
+
+def test_ddpg_learns_to_reach_the_ball():
+    """continuous Dash direction (ddpg_stable_baselines3.py's configuration): the trained actor beats the random policy"""
+    from soccer2d_b200.rollout import DDPGConfig, DeviceDDPG
+    kw = dict(change_ball_position=False, use_continuous_action=True, use_turning=False)
+    env = Soccer2DVecEnv(4096, device="cuda:0", seed=0, terminal_obs=True, **kw)
+    agent = DeviceDDPG(env, DDPGConfig(seed=0, learning_starts=1 << 15))
+    for _ in range(250):
+        agent.rollout_step(0.0, store=False, random=True)
+    st = env.stats()
+    random_goal_rate = st["goals"] / max(1, st["episodes"])
+    agent.learn(1500)
+    trained = agent.evaluate(400)
+    assert trained["episodes"] > 4096
+    assert trained["goal_rate"] > max(0.6, 2 * random_goal_rate), (trained, random_goal_rate)

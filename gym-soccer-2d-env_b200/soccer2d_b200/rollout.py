@@ -187,18 +187,38 @@ class DeviceDQN:
 
 
 @torch.no_grad()
-def measure_rollout(env, qnet: nn.Module, steps: int, warmup: int = 5) -> float:
-    """env-steps/s of the closed loop obs -> Q-net -> argmax -> step (no learning), timed with CUDA events."""
+def measure_rollout(env, qnet: nn.Module, steps: int, warmup: int = 5, use_graph: bool = True) -> float:
+    """env-steps/s of the closed loop obs -> Q-net -> argmax -> step (no learning), timed with CUDA events.
+    use_graph: the loop body (policy kernels + the step kernel, launched through the C ABI on the capturing stream)
+    is captured once into a CUDA graph and replayed - the launch-bound case of a few thousand envs."""
     def one():
         a = qnet(env.obs).argmax(dim=1).to(torch.uint8)
         env.actions.view(-1).copy_(a)
         env.step_torch()
+
+    run = one
+    if use_graph:
+        side = torch.cuda.Stream(device=env.device)
+        side.wait_stream(torch.cuda.current_stream(env.device))
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                one()
+        torch.cuda.current_stream(env.device).wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        steps_before = env.stats()["env_steps"]
+        with torch.cuda.graph(graph):
+            one()
+        graph.replay()
+        torch.cuda.synchronize()
+        # one capture (no execution) + one replay: the library's host-side step counter moved by 2, the device by 1
+        assert env.stats()["env_steps"] == steps_before + 2 * env.num_envs
+        run = graph.replay
     for _ in range(warmup):
-        one()
+        run()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()
     for _ in range(steps):
-        one()
+        run()
     e.record()
     torch.cuda.synchronize()
     return env.num_envs * steps / (s.elapsed_time(e) * 1e-3)

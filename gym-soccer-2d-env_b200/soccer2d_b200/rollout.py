@@ -205,14 +205,15 @@ def measure_rollout(env, qnet: nn.Module, steps: int, warmup: int = 5, use_graph
                 one()
         torch.cuda.current_stream(env.device).wait_stream(side)
         graph = torch.cuda.CUDAGraph()
-        steps_before = env.stats()["env_steps"]
+        cycle = env.state_planes()[1][0, 1]  # server cycle of env 0 (a view of the state the kernel updates)
+        before = int(cycle)
         with torch.cuda.graph(graph):
             one()
+        assert int(cycle) == before, "capture must not execute"
         graph.replay()
         torch.cuda.synchronize()
-        # one capture (no execution) + one replay: the library's host-side step counter moved by 2, the device by 1
-        assert env.stats()["env_steps"] == steps_before + 2 * env.num_envs
-        run = graph.replay
+        assert int(cycle) in (before + 1, before + 2), "the captured step kernel did not run"  # +2: an auto-reset cycle
+        run = graph.replay  # (the handle's host-side env_steps counter does not see replays)
     for _ in range(warmup):
         run()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

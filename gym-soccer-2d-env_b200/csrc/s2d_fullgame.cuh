@@ -11,7 +11,7 @@
 // kick-in / corner kick / goal kick, kick-off after a goal, time over.  NOT in the reference (which only ever runs
 // one player with the referee off, soccer_2d_env.py:363-369): the spec is include/soccer2d.h.
 #pragma once
-#include "s2d_reachball.cuh"
+#include "s2d_scenarios.cuh"
 
 namespace s2d {
 

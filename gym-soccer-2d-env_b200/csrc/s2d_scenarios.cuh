@@ -1,4 +1,4 @@
-// s2d_reachball.cuh - the ReachBall scenario fused into the lockstep kernels.
+// s2d_scenarios.cuh - the one-player scenarios (ReachBall, Shoot) fused into the lockstep step / reset kernels.
 //
 // Replaces, per env and per cycle, the whole of Soccer2DEnv.step (soccer_2d_env.py:226-269):
 //   decode (in substep)  ReachBallEnv.action_to_rpc_actions      sample_environments/reach_ball_env.py:53-85

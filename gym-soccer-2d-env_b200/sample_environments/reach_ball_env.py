@@ -4,7 +4,7 @@ one player has to get within `min_distance_to_ball` of the ball.
 Same constructor (`render_mode, logger, log_dir, **kwargs` with the 11 kwargs of :26-36 and their
 defaults), same spaces (:39-48), same step/reset results.  Action decode (:53-85), observation (:87-111),
 reward/done/info (:113-161) and the reset distribution (:170-218) are implemented in
-csrc/s2d_reachball.cuh and run on the GPU; the extra keyword-only arguments `device`, `seed` and
+csrc/s2d_scenarios.cuh and run on the GPU; the extra keyword-only arguments `device`, `seed` and
 `server_param` select where and how the episode is simulated.
 """
 from __future__ import annotations

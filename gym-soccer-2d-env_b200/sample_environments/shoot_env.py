@@ -2,7 +2,7 @@
 
 Not part of the reference (whose only scenario is ReachBall); it exists to exercise the kick model, the
 kickable-area test and goal / ball-out detection behind the same gym API.  The scenario contract (reset, reward,
-done, result names) is specified in include/soccer2d.h and implemented in csrc/s2d_reachball.cuh (check_shoot).
+done, result names) is specified in include/soccer2d.h and implemented in csrc/s2d_scenarios.cuh (check_shoot).
 Observation: the same 10 values as ReachBall.  Actions: Discrete(action_space_size) = dashes + `kick_actions` kicks,
 or proto-style commands with use_command_action=True (Dash / Turn / Kick / Body_GoToPoint).
 """

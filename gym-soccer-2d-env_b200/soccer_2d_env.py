@@ -107,13 +107,13 @@ class Soccer2DEnv(Env):
     # ---- the reference's scenario hooks (soccer_2d_env.py:317-354): names kept for subclasses that
     # ---- introspect them; the GPU path does not call them -------------------------------------------
     def action_to_rpc_actions(self, action, player_state=None):
-        raise NotImplementedError("action decode is fused into the step kernel (csrc/s2d_reachball.cuh)")
+        raise NotImplementedError("action decode is fused into the step kernel (csrc/s2d_scenarios.cuh)")
 
     def state_to_observation(self, state=None):
-        raise NotImplementedError("observation build is fused into the step kernel (csrc/s2d_reachball.cuh)")
+        raise NotImplementedError("observation build is fused into the step kernel (csrc/s2d_scenarios.cuh)")
 
     def check_trainer_observation(self, observation=None):
-        raise NotImplementedError("reward/done is fused into the step kernel (csrc/s2d_reachball.cuh)")
+        raise NotImplementedError("reward/done is fused into the step kernel (csrc/s2d_scenarios.cuh)")
 
     def trainer_reset_actions(self):
-        raise NotImplementedError("reset placement is drawn inside the reset kernel (csrc/s2d_reachball.cuh)")
+        raise NotImplementedError("reset placement is drawn inside the reset kernel (csrc/s2d_scenarios.cuh)")

@@ -1,9 +1,9 @@
-// emu_reachball.cpp - TEST-ONLY: runs the __device__ functions of csrc/s2d_reachball.cuh (substep, reset_episode,
+// emu_reachball.cpp - TEST-ONLY: runs the __device__ functions of csrc/s2d_scenarios.cuh (substep, reset_episode,
 // build_obs, load/store_episode) on the host, one "thread" after another, over a state buffer with the same
 // plane-major layout as the GPU's.  Lets the CPU test suite check the kernel source against the fp32 oracle.
 #define S2D_HOST_EMU 1
 #include "cuda_shim.h"
-#include "../../gym-soccer-2d-env_b200/csrc/s2d_reachball.cuh"
+#include "../../gym-soccer-2d-env_b200/csrc/s2d_scenarios.cuh"
 
 #include <vector>
 

@@ -666,3 +666,26 @@ def test_kernels_stay_inside_their_buffers(scenario, n):
         assert bool((buf[:guard] == 0xA5).all()) and bool((buf[guard + nbytes:] == 0xA5).all())
     assert float(views["obs"].view(torch.float32).abs().sum()) > 0  # the kernels did write
     env.close()
+
+
+def test_checkpoint_resume_is_exact():
+    """state_dict / load_state_dict: the SoA state (incl. RNG counters = episode / cycle) is the whole checkpoint."""
+    n, k = 2000, 4
+    env = make_env(n, "discrete", seed=5, substeps=k, noise=True, change_ball_velocity=True, max_steps=20)
+    env.reset_torch()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    acts = [torch.randint(0, 16, (n, k), dtype=torch.uint8, device="cuda", generator=g) for _ in range(20)]
+    for a in acts[:10]:
+        env.step_torch(a)
+    ckpt = env.state_dict()
+    outs = []
+    for a in acts[10:]:
+        env.step_torch(a)
+        outs.append((env.obs.clone(), env.reward.clone(), env.done.clone()))
+    final_stats = env.stats()
+    env.load_state_dict(ckpt)
+    for a, (o, r, d) in zip(acts[10:], outs):
+        env.step_torch(a)
+        assert torch.equal(env.obs, o) and torch.equal(env.reward, r) and torch.equal(env.done, d)
+    st = env.stats()
+    assert {k_: st[k_] for k_ in ("episodes", "goals", "outs", "timeouts")} == {k_: final_stats[k_] for k_ in ("episodes", "goals", "outs", "timeouts")}

@@ -69,6 +69,29 @@ extern "C" {
  *   Discrete(n): the first n - kick_actions actions are Dash(100, (a*360/n_dash)%360-180) as in ReachBall, the last
  *            kick_actions are Kick(100, (j*360/kick_actions)%360-180). */
 
+/* FULLGAME scenario (BASELINE configs[3]; not in the reference - this is the spec):
+ *   players_per_side v players_per_side (1..11); player index p < pps = left team, uniform number p+1; p >= pps = right
+ *   team.  Actions: S2D_ACT_COMMAND, one {cmd, a, b, c} per player and cycle.  Every player: dash / turn / kick /
+ *   Body_GoToPoint, stamina, player-player and ball-player collisions as in the one-player scenarios.
+ *   A match lasts 2 * half_time_cycles cycles, then done with result 1 = left wins, 2 = right wins, 3 = draw.
+ *   Reset / kick-off: 4-4-2 formation in the own half, each player jittered by +-2 m (Philox), left faces 0 deg, right
+ *   180 deg, ball at the centre, play mode KickOff for the left team (after a goal: for the conceding side, next cycle).
+ *   Referee subset (play modes = proto GameModeType, idl/service.proto:267-301):
+ *     goal       ball beyond x = +-(pitch_half_length + ball_size) having crossed the line between the posts
+ *                (|y| <= goal_width/2 + goal_post_radius at the crossing)      -> score, KickOff
+ *     goal line  crossed elsewhere: last touched by the defending side -> CornerKick for the attackers at
+ *                (+-(half_length - 1), +-(half_width - 1)); else GoalKick for the defenders at (+-(half_length - 5.5), +-9.16)
+ *     side line  |y| > pitch_half_width + ball_size -> KickIn for the side that did not touch it last, ball on the line
+ *     dead ball  (KickOff, KickIn, CornerKick, GoalKick): the ball rests and takes no part in collisions; only the awarded
+ *                side's kicks count, the first one resumes PlayOn; after 100 cycles without it play resumes anyway.
+ *     last touch = side of the last kicker(s) / of the player(s) the ball collided with (unchanged if both sides did).
+ *     Not modelled: 9.15 m clearance, AfterGoal pause, offside, fouls, tackle, catch, heterogeneous player types.
+ *   Reward (left team's view) per cycle: 10 * (goals by left - goals by right) + 0.01 * (ball x after physics - before).
+ *   Observation: 120 floats = ball {x/52.5, y/34, vx/3, vy/3}, then per player {x/52.5, y/34, vx, vy, body/180}
+ *   (absent players zero), then [114] play mode, [115] side awarded, [116] left score, [117] right score,
+ *   [118] step_number / (2 * half_time_cycles), [119] 0.
+ *   State buffer: s2d_state_bytes(cfg) = N * (np * 36 + 64) bytes (+ padding), plane-major (layout: DESIGN.md). */
+
 /* action encodings (reach_ball_env.py:39-47, :53-85) */
 #define S2D_ACT_DISCRETE 0   /* uint8  [N][K]      Discrete(n): Dash(100, (a*360/n)%360-180) (+ kicks in SHOOT)  */
 #define S2D_ACT_CONTINUOUS 1 /* float  [N][K][1]   Box(-1,1,(1,)): Dash(100, a*180)               (REACHBALL)   */

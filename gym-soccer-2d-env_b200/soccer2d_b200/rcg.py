@@ -1,0 +1,70 @@
+"""Game-log writer: one env's trajectory as an rcssserver game log (`.rcg`, text version 5) so that it can be replayed
+in the usual viewers (rcssmonitor / soccerwindow2) - SURVEY.md section 8(f), the debugging / visualisation side of
+the path.  Input: the `EnvSnapshot`s of `Soccer2DVecEnv.export_env(i)`, one per cycle.
+
+Layout of a cycle (rcssserver's logger, version 4/5 text format):
+    (playmode <t> <name>)                      when the mode changes
+    (team <t> <left> <right> <score_l> <score_r>)   when a score changes
+    (show <t> ((b) x y vx vy)
+              ((l 1) <type> <state> x y vx vy body neck (v h 180) (s stamina effort recovery capacity)
+                     (c kick dash turn catch move tneck view say tackle pointto attention)) ...)
+Written from the format's published description; no viewer is available offline to replay the files here.
+"""
+from __future__ import annotations
+
+PLAYMODE_NAMES = {0: "before_kick_off", 1: "time_over", 2: "play_on", 3: "kick_off", 4: "kick_in", 5: "free_kick",
+                  6: "corner_kick", 7: "goal_kick", 8: "after_goal"}
+STATE_STAND, STATE_KICK, STATE_GOALIE, STATE_BALL_COLLIDE, STATE_PLAYER_COLLIDE = 0x1, 0x2, 0x8, 0x400, 0x800
+
+
+def _f(v: float) -> str:
+    s = f"{float(v):.4f}".rstrip("0").rstrip(".")
+    return "0" if s in ("-0", "") else s
+
+
+class RcgWriter:
+    def __init__(self, path: str, left: str = "left", right: str = "right"):
+        self.f = open(path, "w")
+        self.left, self.right = left, right
+        self.last_mode = None
+        self.last_score = None
+        self.f.write("ULG5\n")
+
+    def _playmode_name(self, snap) -> str:
+        name = PLAYMODE_NAMES.get(int(snap.game_mode_type), "play_on")
+        if name in ("kick_off", "kick_in", "free_kick", "corner_kick", "goal_kick", "after_goal"):
+            name += "_l" if snap.game_mode_side == 1 else "_r"
+        return name
+
+    def write(self, snap) -> None:
+        """append one cycle (an _abi.EnvSnapshot)"""
+        t = int(snap.cycle)
+        mode = self._playmode_name(snap)
+        if mode != self.last_mode:
+            self.f.write(f"(playmode {t} {mode})\n")
+            self.last_mode = mode
+        score = (int(snap.left_score), int(snap.right_score))
+        if score != self.last_score:
+            self.f.write(f"(team {t} {self.left} {self.right} {score[0]} {score[1]})\n")
+            self.last_score = score
+        parts = [f"(show {t} ((b) {_f(snap.ball_x)} {_f(snap.ball_y)} {_f(snap.ball_vx)} {_f(snap.ball_vy)})"]
+        for j in range(int(snap.num_players)):
+            p = snap.players[j]
+            state = STATE_STAND | (STATE_KICK if p.kicked else 0) | (STATE_GOALIE if p.uniform_number == 1 else 0)
+            state |= STATE_PLAYER_COLLIDE if p.collided else 0
+            side = "l" if p.side == 1 else "r"
+            parts.append(f" (({side} {int(p.uniform_number)}) 0 {hex(state)} {_f(p.x)} {_f(p.y)} {_f(p.vx)} {_f(p.vy)} "
+                         f"{_f(p.body_direction)} 0 (v h 180) (s {_f(p.stamina)} {_f(p.effort)} {_f(p.recovery)} "
+                         f"{_f(p.stamina_capacity)}) (c 0 0 0 0 0 0 0 0 0 0 0))")
+        parts.append(")\n")
+        self.f.write("".join(parts))
+
+    def close(self) -> None:
+        if not self.f.closed:
+            self.f.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()

@@ -314,10 +314,12 @@ __device__ __forceinline__ bool fg_cycle(Episode& p, Match& m, const KernelParam
   int goal_l = 0, goal_r = 0;
   const float bx_phys = p.bx;
   bool kick_off = false;
-  if (!dead) {
+  const float line = sp.pitch_half_length() + sp.ball_size();
+  const float side_line = sp.pitch_half_width() + sp.ball_size();
+  if (!dead && !(fabsf(p.bx) > line || fabsf(p.by) > side_line)) {
+    // ball inside the field: every ruling below needs it beyond a line, so there is nothing to decide (the common case)
+  } else if (!dead) {
     const float bx = p.bx, by = p.by;
-    const float line = sp.pitch_half_length() + sp.ball_size();
-    const float side_line = sp.pitch_half_width() + sp.ball_size();
     const float post = sp.goal_width() * 0.5f + sp.goal_post_radius();
     if (bx > line && !(pbx > line)) {
       const float yc = pby + (by - pby) * ((line - pbx) / (bx - pbx));

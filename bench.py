@@ -56,12 +56,12 @@ def workload_config(n_gpus, envs, k, extra=None):
     return cfg
 
 
-def load_traffic(key, envs):
-    """DRAM bytes per launch of the step kernel from the committed ncu capture (profiles/traffic.json); None if
-    the capture was taken at another size."""
+def load_traffic(key, envs, field="traffic_bytes"):
+    """DRAM bytes per launch (or another recorded ncu figure) of the step kernel from the committed ncu capture
+    (profiles/traffic.json); None if the capture was taken at another size."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            return json.load(f)[f"{key}_envs_{envs}"]["traffic_bytes"]
+            return json.load(f)[f"{key}_envs_{envs}"][field]
     except Exception:  # noqa: BLE001
         return None
 
@@ -371,6 +371,8 @@ def run_b200(args, rank, local_rank, world):
         "gpu_launches": args.steps,
         "roofline": {"bound": "hbm", "achieved": ach16, "peak": peak, "unit": "GB/s", "frac": ach16 / peak,
                      "traffic": load_traffic(f"k{k}", n),
+                     "issue_slots_busy_pct_ncu": load_traffic(f"k{k}", n, "issue_active_pct"),
+                     "warp_instructions_per_env_step_ncu": load_traffic(f"k{k}", n, "warp_instructions_per_env_step"),
                      "kernel": "s2d::step_kernel<REACHBALL, DISCRETE, default ServerParam>", "launch_ms": launch_ms,
                      "algorithmic_bytes_per_launch": bytes16, "peak_source": peak_src,
                      "note": "K=16 keeps 16 cycles in registers: HBM traffic is 222 B per 16 env-steps by construction, "

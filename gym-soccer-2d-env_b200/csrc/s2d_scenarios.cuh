@@ -197,20 +197,36 @@ __device__ __forceinline__ bool scenario_check(Episode& e, const KernelParams& P
 }
 
 // trainer_reset_actions' draws (integers: x in [-50,50], y in [-30,30], body in [0,360]; ball velocity by
-// bounded rejection: the ball must stay on the pitch for max_steps cycles), then DoMoveBall / DoMovePlayer
-// (vel = 0) / DoRecover.  The caller still owes the episode ONE idle server cycle and the priming check
-// (the reference's reset observes the state one cycle after placement, reach_ball_env.py:163-168).
-template <class SP>
-__device__ __forceinline__ void place_new_episode(Episode& e, const KernelParams& P, const SP& sp, uint64_t gid) {
-  const uint4 w = philox4x32_10(P.seed, gid, e.episode, RNG_RESET, 0);
-  const float px = static_cast<float>(u32_to_int(w.x, -50, 50));
-  const float py = static_cast<float>(u32_to_int(w.y, -30, 30));
-  const float body = static_cast<float>(u32_to_int(w.z, 0, 360));
-  float bx = P.ball_position_x, by = P.ball_position_y;
-  if (P.change_ball_position) {
-    const uint4 w2 = philox4x32_10(P.seed, gid, e.episode, RNG_RESET, 1);
-    bx = static_cast<float>(u32_to_int(w.w, -50, 50));
-    by = static_cast<float>(u32_to_int(w2.x, -30, 30));
+// bounded rejection: the ball must stay on the pitch for max_steps cycles): what DoMoveBall / DoMovePlayer carry.
+struct Placement {
+  float px, py, body, bx, by, bvx, bvy;
+};
+
+__device__ __forceinline__ bool ball_stays_inside(const KernelParams& P, float bx, float by, float s_try, float sn, float cs) {
+  const float travel = s_try * P.travel_factor;
+  return fabsf(bx + travel * cs) <= 52.5f && fabsf(by + travel * sn) <= 34.0f;
+}
+
+// one thread draws everything (reset kernel; many lanes of a warp resetting at once)
+__device__ __forceinline__ Placement draw_placement(const KernelParams& P, uint64_t gid, uint32_t episode, int first_try = 0,
+                                                    float bx_known = 0.0f, float by_known = 0.0f) {
+  Placement pl;
+  if (first_try == 0) {
+    const uint4 w = philox4x32_10(P.seed, gid, episode, RNG_RESET, 0);
+    pl.px = static_cast<float>(u32_to_int(w.x, -50, 50));
+    pl.py = static_cast<float>(u32_to_int(w.y, -30, 30));
+    pl.body = static_cast<float>(u32_to_int(w.z, 0, 360));
+    pl.bx = P.ball_position_x;
+    pl.by = P.ball_position_y;
+    if (P.change_ball_position) {
+      const uint4 w2 = philox4x32_10(P.seed, gid, episode, RNG_RESET, 1);
+      pl.bx = static_cast<float>(u32_to_int(w.w, -50, 50));
+      pl.by = static_cast<float>(u32_to_int(w2.x, -30, 30));
+    }
+  } else {  // continuing a search the warp started (tries first_try .. kBallVelTries-1): only the velocity is used
+    pl.px = pl.py = pl.body = 0.0f;
+    pl.bx = bx_known;
+    pl.by = by_known;
   }
   float speed = P.ball_speed, d = P.ball_direction;
   if (P.change_ball_velocity) {
@@ -218,14 +234,14 @@ __device__ __forceinline__ void place_new_episode(Episode& e, const KernelParams
     d = 0.0f;
     uint4 wv = make_uint4(0, 0, 0, 0);
 #pragma unroll 1
-    for (int t = 0; t < kBallVelTries; ++t) {
-      if ((t & 1) == 0) wv = philox4x32_10(P.seed, gid, e.episode, RNG_BALLVEL, static_cast<uint32_t>(t >> 1));
+    for (int t = first_try; t < kBallVelTries; ++t) {
+      if ((t & 1) == 0 || t == first_try)
+        wv = philox4x32_10(P.seed, gid, episode, RNG_BALLVEL, static_cast<uint32_t>(t >> 1));
       const float s_try = u32_to_unit((t & 1) ? wv.z : wv.x) * 3.0f;
       const float d_try = static_cast<float>(u32_to_int((t & 1) ? wv.w : wv.y, 0, 360));
-      const float travel = s_try * P.travel_factor;
       float sn, cs;
       sincos_deg(d_try, sn, cs);
-      if (fabsf(bx + travel * cs) <= 52.5f && fabsf(by + travel * sn) <= 34.0f) {
+      if (ball_stays_inside(P, pl.bx, pl.by, s_try, sn, cs)) {
         speed = s_try;
         d = d_try;
         break;
@@ -234,14 +250,84 @@ __device__ __forceinline__ void place_new_episode(Episode& e, const KernelParams
   }
   float sn, cs;
   sincos_deg(d, sn, cs);
+  pl.bvx = speed * cs;
+  pl.bvy = speed * sn;
+  return pl;
+}
+
+#ifndef S2D_HOST_EMU
+// The same draws for ONE episode, made by the whole warp (a lane whose episode ended while its 31 neighbours wait):
+// lanes 0-1 compute the two placement blocks, lanes 2-31 thirty ball-velocity blocks (tries 0..59), every lane
+// evaluates one try per round, and a ballot picks the first accepted one - exactly the try the sequential loop of
+// draw_placement stops at.  Returns the placement in every lane.
+__device__ __forceinline__ Placement draw_placement_warp(const KernelParams& P, uint64_t gid, uint32_t episode, int lane) {
+  const unsigned full = 0xffffffffu;
+  const bool placement_lane = lane < 2;
+  const uint4 w = philox4x32_10(P.seed, gid, episode, placement_lane ? RNG_RESET : RNG_BALLVEL,
+                                static_cast<uint32_t>(placement_lane ? lane : lane - 2));
+  Placement pl;
+  pl.px = static_cast<float>(u32_to_int(__shfl_sync(full, w.x, 0), -50, 50));
+  pl.py = static_cast<float>(u32_to_int(__shfl_sync(full, w.y, 0), -30, 30));
+  pl.body = static_cast<float>(u32_to_int(__shfl_sync(full, w.z, 0), 0, 360));
+  const uint32_t ubx = __shfl_sync(full, w.w, 0), uby = __shfl_sync(full, w.x, 1);
+  pl.bx = P.change_ball_position ? static_cast<float>(u32_to_int(ubx, -50, 50)) : P.ball_position_x;
+  pl.by = P.change_ball_position ? static_cast<float>(u32_to_int(uby, -30, 30)) : P.ball_position_y;
+  float speed = P.ball_speed, sn, cs;
+  if (P.change_ball_velocity) {
+    speed = 0.0f;
+    bool found = false;
+#pragma unroll 1
+    for (int round = 0; round < 2 && !found; ++round) {
+      const int t = 32 * round + lane, block = t >> 1;
+      const bool have = block < 30;
+      const int src = have ? 2 + block : 2;
+      const uint32_t qx = __shfl_sync(full, w.x, src), qy = __shfl_sync(full, w.y, src), qz = __shfl_sync(full, w.z, src),
+                     qw = __shfl_sync(full, w.w, src);
+      const float s_try = u32_to_unit((t & 1) ? qz : qx) * 3.0f;
+      const float d_try = static_cast<float>(u32_to_int((t & 1) ? qw : qy, 0, 360));
+      float tsn, tcs;
+      sincos_deg(d_try, tsn, tcs);
+      const unsigned ok = __ballot_sync(full, have && ball_stays_inside(P, pl.bx, pl.by, s_try, tsn, tcs));
+      if (ok) {
+        const int first = __ffs(ok) - 1;
+        speed = __shfl_sync(full, s_try, first);
+        sn = __shfl_sync(full, tsn, first);
+        cs = __shfl_sync(full, tcs, first);
+        found = true;
+      }
+    }
+    if (!found) {  // tries 60..63: practically never; every lane walks them alone (same result in all lanes)
+      const Placement rest = draw_placement(P, gid, episode, 60, pl.bx, pl.by);
+      pl.bvx = rest.bvx;
+      pl.bvy = rest.bvy;
+      return pl;
+    }
+  } else {
+    sincos_deg(P.ball_direction, sn, cs);
+  }
+  pl.bvx = speed * cs;
+  pl.bvy = speed * sn;
+  return pl;
+}
+#endif
+
+// DoMoveBall / DoMovePlayer (vel = 0) / DoRecover.  The caller still owes the episode ONE idle server cycle and the
+// priming check (the reference's reset observes the state one cycle after placement, reach_ball_env.py:163-168).
+template <class SP>
+__device__ __forceinline__ void apply_placement(Episode& e, const Placement& pl, const SP& sp) {
   e.episode += 1u;
   e.step_number = 0;
   e.ep_return = 0.0f;
-  e.bx = bx; e.by = by; e.bvx = speed * cs; e.bvy = speed * sn;
-  e.px = px; e.py = py; e.vx = 0.0f; e.vy = 0.0f;
-  e.body = norm_deg(body);
+  e.bx = pl.bx; e.by = pl.by; e.bvx = pl.bvx; e.bvy = pl.bvy;
+  e.px = pl.px; e.py = pl.py; e.vx = 0.0f; e.vy = 0.0f;
+  e.body = norm_deg(pl.body);
   e.flags = 0u;
   recover(e, sp);
+}
+
+template <class SP>
+__device__ __forceinline__ void place_new_episode(Episode& e, const KernelParams& P, const SP& sp, uint64_t gid) {
+  apply_placement(e, draw_placement(P, gid, e.episode), sp);
 }
 
 // per-lane row store (terminal observations, reset kernel): 40-byte rows are 8-byte aligned
@@ -251,15 +337,21 @@ __device__ __forceinline__ void lane_store_row(float* __restrict__ dst, int64_t 
   for (int j = 0; j < kObsDim / 2; ++j) o[j] = make_float2(row[2 * j], row[2 * j + 1]);
 }
 
-// Soccer2DEnv.reset for one env: placement, the idle cycle, the priming check.
+// the second half of Soccer2DEnv.reset: the idle cycle after the placement and the priming check
 template <int SCN, class SP>
-__device__ __forceinline__ void reset_episode(Episode& e, const KernelParams& P, const SP& sp, uint64_t gid) {
-  place_new_episode(e, P, sp, gid);
+__device__ __forceinline__ void finish_reset(Episode& e, const KernelParams& P, const SP& sp, uint64_t gid) {
   float dx, dy, d2, rw;
   int rs;
   const float pbx = e.bx, pby = e.by;
   simulate_cycle<false, false>(e, S2D_CMD_NONE, 0.0f, 0.0f, 0.0f, sp, dx, dy, d2, P.seed, gid);
   scenario_check<SCN>(e, P, sp, dx, dy, d2, pbx, pby, rw, rs);  // reach_ball_env.py:166: primes the memory, reward discarded
+}
+
+// Soccer2DEnv.reset for one env: placement, the idle cycle, the priming check.
+template <int SCN, class SP>
+__device__ __forceinline__ void reset_episode(Episode& e, const KernelParams& P, const SP& sp, uint64_t gid) {
+  place_new_episode(e, P, sp, gid);
+  finish_reset<SCN>(e, P, sp, gid);
 }
 
 // ONE env-step = what Soccer2DEnv.step does: decode the action, run the server cycle, score it; when the
@@ -268,8 +360,10 @@ __device__ __forceinline__ void reset_episode(Episode& e, const KernelParams& P,
 //   continuous: a0 in [-1, 1]                                                    (ReachBall)
 //   turning:    [turn_prob, turn_angle, dash_prob, dash_angle], :65-68           (ReachBall)
 //   command:    {cmd, a, b, c} = proto PlayerAction dash / turn / kick / body_go_to_point
-template <int SCN, int ACT, class SP>
-__device__ __forceinline__ void substep(Episode& e, const KernelParams& P, const SP& sp, uint64_t gid, int64_t i, float a0,
+// DEFER_END: leave the end of the episode (tally, terminal observation, auto-reset) to the caller and return the
+// episode's result, S2D_RESULT_NONE while it goes on (step_kernel: the warp handles endings together, end_of_episode).
+template <int SCN, int ACT, class SP, bool DEFER_END = false>
+__device__ __forceinline__ int substep(Episode& e, const KernelParams& P, const SP& sp, uint64_t gid, int64_t i, float a0,
                                         float a1, float a2, float a3, LaunchOut& out) {
   constexpr bool kTurns = ACT == S2D_ACT_TURNING || ACT == S2D_ACT_COMMAND;
   constexpr bool kKicks = ACT == S2D_ACT_COMMAND || SCN == S2D_SCENARIO_SHOOT;
@@ -304,6 +398,7 @@ __device__ __forceinline__ void substep(Episode& e, const KernelParams& P, const
   const bool done = scenario_check<SCN>(e, P, sp, dx, dy, d2, pbx, pby, rw, rs);
   out.reward_sum += rw;
   e.ep_return += rw;
+  if (DEFER_END) return rs;
   if (done) {
     out.count(rs);
     out.ep_steps += static_cast<uint32_t>(e.step_number);
@@ -319,6 +414,7 @@ __device__ __forceinline__ void substep(Episode& e, const KernelParams& P, const
       e.flags |= S2D_FLAG_DONE;
     }
   }
+  return S2D_RESULT_NONE;
 }
 
 #ifndef S2D_HOST_EMU
@@ -385,6 +481,52 @@ struct VariantSP {
                                          typename std::conditional<VAR == kVarNoisy, NoisySP, RuntimeSP>::type>::type;
 };
 
+// The end of an episode inside the K loop, handled by the warp as a whole: one vote per step replaces a divergent
+// branch.  Episodes end in few lanes at a time (about one step in 60 per lane), and a lane that drew its next placement
+// alone would hold its 31 neighbours for ~560 instructions; so with up to kWarpDrawMax lanes due the warp makes each
+// lane's draws together (draw_placement_warp), with more (synchronised time-outs) every due lane draws for itself in
+// parallel.  Both orders consume the same Philox words: the results are identical.
+#ifndef S2D_WARP_DRAW_MAX
+#define S2D_WARP_DRAW_MAX 3
+#endif
+constexpr int kWarpDrawMax = S2D_WARP_DRAW_MAX;
+
+template <int SCN, class SP>
+__device__ __forceinline__ void end_of_episode(Episode& e, const KernelParams& P, const SP& sp, uint64_t gid, int64_t i,
+                                               bool valid, int rs, LaunchOut& out) {
+  const unsigned full = 0xffffffffu;
+  const bool done = rs != S2D_RESULT_NONE;
+  unsigned pending = __ballot_sync(full, done);
+  if (pending == 0u) return;
+  if (done) {
+    out.count(rs);
+    out.ep_steps += static_cast<uint32_t>(e.step_number);
+    out.ret += static_cast<double>(e.ep_return);
+    if (P.terminal_obs && valid) {
+      float row[kObsDim];
+      scenario_obs<SCN>(e, row);
+      lane_store_row(P.terminal_obs, i, row);
+    }
+    if (!P.auto_reset) e.flags |= S2D_FLAG_DONE;
+  }
+  if (!P.auto_reset) return;
+  if (__popc(pending) <= kWarpDrawMax) {
+    const int lane = threadIdx.x & 31;
+    do {
+      const int src = __ffs(pending) - 1;
+      pending &= pending - 1u;
+      const uint32_t g_lo = __shfl_sync(full, static_cast<uint32_t>(gid), src);
+      const uint32_t g_hi = __shfl_sync(full, static_cast<uint32_t>(gid >> 32), src);
+      const uint32_t episode = __shfl_sync(full, e.episode, src);
+      const Placement pl = draw_placement_warp(P, (static_cast<uint64_t>(g_hi) << 32) | g_lo, episode, lane);
+      if (lane == src) apply_placement(e, pl, sp);
+    } while (pending);
+    if (done) finish_reset<SCN>(e, P, sp, gid);
+  } else if (done) {
+    reset_episode<SCN>(e, P, sp, gid);
+  }
+}
+
 template <int SCN, int ACT, int VAR>
 __global__ void __launch_bounds__(kBlock, S2D_MIN_BLOCKS) step_kernel(const __grid_constant__ KernelParams P, const int K) {
   using SP = typename VariantSP<VAR>::type;
@@ -401,38 +543,49 @@ __global__ void __launch_bounds__(kBlock, S2D_MIN_BLOCKS) step_kernel(const __gr
   LaunchOut out;
   float obs_row[kObsDim];
 
-  if (valid) {
-    load_episode(P.state, n, i, e);
-    if (ACT == S2D_ACT_DISCRETE) {
-      // the 4 KB action table stays in L1 (read-only path); `act` walks the lane's K action bytes
-      const uint8_t* act = static_cast<const uint8_t*>(P.actions) + i * K;
+  // Every lane of the warp runs the K loop (the lanes past the end of a ragged last warp replay env n-1 and store
+  // nothing), so that the warp can handle the end of an episode together, see end_of_episode.
+  const int64_t il = valid ? i : n - 1;
+  load_episode(P.state, n, il, e);
+  if (ACT == S2D_ACT_DISCRETE) {
+    // the 4 KB action table stays in L1 (read-only path); `act` walks the lane's K action bytes
+    const uint8_t* act = static_cast<const uint8_t*>(P.actions) + il * K;
 #pragma unroll 1
-      for (int k = K; k > 0; --k, ++act) {
-        if (SCN == S2D_SCENARIO_SHOOT) {
-          const float4 t = __ldg(P.action_table + __ldg(act));
-          substep<SCN, ACT>(e, P, sp, gid, i, t.x, t.y, t.z, t.w, out);
-        } else {  // ReachBall: always Dash(100, .): only the lowered direction and its rate are needed
-          const float2 t = __ldg(reinterpret_cast<const float2*>(P.action_table + __ldg(act)) + 1);
-          substep<SCN, ACT>(e, P, sp, gid, i, 0.f, 0.f, t.x, t.y, out);
-        }
+    for (int k = K; k > 0; --k, ++act) {
+      int rs;
+      if (SCN == S2D_SCENARIO_SHOOT) {
+        const float4 t = __ldg(P.action_table + __ldg(act));
+        rs = substep<SCN, ACT, SP, true>(e, P, sp, gid, i, t.x, t.y, t.z, t.w, out);
+      } else {  // ReachBall: always Dash(100, .): only the lowered direction and its rate are needed
+        const float2 t = __ldg(reinterpret_cast<const float2*>(P.action_table + __ldg(act)) + 1);
+        rs = substep<SCN, ACT, SP, true>(e, P, sp, gid, i, 0.f, 0.f, t.x, t.y, out);
       }
-    } else if (ACT == S2D_ACT_CONTINUOUS) {
-      const float* act = static_cast<const float*>(P.actions) + i * K;
-#pragma unroll 1
-      for (int k = 0; k < K; ++k) substep<SCN, ACT>(e, P, sp, gid, i, __ldg(act + k), 0.f, 0.f, 0.f, out);
-    } else {
-      const float4* act = static_cast<const float4*>(P.actions) + i * K;
-#pragma unroll 1
-      for (int k = 0; k < K; ++k) {
-        const float4 a = __ldg(act + k);
-        substep<SCN, ACT>(e, P, sp, gid, i, a.x, a.y, a.z, a.w, out);
-      }
+      end_of_episode<SCN>(e, P, sp, gid, i, valid, rs, out);
     }
+  } else if (ACT == S2D_ACT_CONTINUOUS) {
+    const float* act = static_cast<const float*>(P.actions) + il * K;
+#pragma unroll 1
+    for (int k = 0; k < K; ++k) {
+      const int rs = substep<SCN, ACT, SP, true>(e, P, sp, gid, i, __ldg(act + k), 0.f, 0.f, 0.f, out);
+      end_of_episode<SCN>(e, P, sp, gid, i, valid, rs, out);
+    }
+  } else {
+    const float4* act = static_cast<const float4*>(P.actions) + il * K;
+#pragma unroll 1
+    for (int k = 0; k < K; ++k) {
+      const float4 a = __ldg(act + k);
+      const int rs = substep<SCN, ACT, SP, true>(e, P, sp, gid, i, a.x, a.y, a.z, a.w, out);
+      end_of_episode<SCN>(e, P, sp, gid, i, valid, rs, out);
+    }
+  }
+  if (valid) {
     store_episode(P.state, n, i, e);
     scenario_obs<SCN>(e, obs_row);
     P.reward[i] = out.reward_sum;
     P.done[i] = static_cast<uint8_t>(out.ended != 0);
     P.result[i] = static_cast<uint8_t>(out.last_result());
+  } else {
+    out = LaunchOut();  // a replayed lane tallies nothing
   }
   warp_store_obs(P.obs, warp_first, n, obs_row, valid, stage);
   flush_tally(out, P.stats);

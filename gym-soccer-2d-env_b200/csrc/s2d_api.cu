@@ -281,9 +281,10 @@ static cudaError_t launch_step(S2DSim* h, const KernelParams& kp, int k_substeps
   } while (0)
   if (h->cfg.scenario == S2D_SCENARIO_FULLGAME) {
     const int np = 2 * h->cfg.players_per_side, ht = h->cfg.half_time_cycles;
-    if (h->cfg.noise) fullgame_step_kernel<kVarNoisy><<<h->grid, kFgBlock, 0, s>>>(kp, k_substeps, np, ht);
-    else if (h->default_sp) fullgame_step_kernel<kVarDefault><<<h->grid, kFgBlock, 0, s>>>(kp, k_substeps, np, ht);
-    else fullgame_step_kernel<kVarRuntime><<<h->grid, kFgBlock, 0, s>>>(kp, k_substeps, np, ht);
+    if (h->cfg.noise) fullgame_step_kernel<kVarNoisy, 0><<<h->grid, kFgBlock, 0, s>>>(kp, k_substeps, np, ht);
+    else if (!h->default_sp) fullgame_step_kernel<kVarRuntime, 0><<<h->grid, kFgBlock, 0, s>>>(kp, k_substeps, np, ht);
+    else if (np == 22) fullgame_step_kernel<kVarDefault, 22><<<h->grid, kFgBlock, 0, s>>>(kp, k_substeps, np, ht);
+    else fullgame_step_kernel<kVarDefault, 0><<<h->grid, kFgBlock, 0, s>>>(kp, k_substeps, np, ht);
   } else if (h->cfg.scenario == S2D_SCENARIO_SHOOT) {
     if (h->cfg.action_mode == S2D_ACT_DISCRETE) S2D_LAUNCH(S2D_SCENARIO_SHOOT, S2D_ACT_DISCRETE);
     else S2D_LAUNCH(S2D_SCENARIO_SHOOT, S2D_ACT_COMMAND);

@@ -81,13 +81,13 @@ __device__ __forceinline__ void fg_place_player(Episode& p, const KernelParams& 
 // Returns this lane's bits: 1 = player collided, 2 = player touched the ball; ball_collided is warp-uniform.
 //
 // `sep` (kept in the match state) is a LOWER BOUND on the smallest distance between two players.  Every cycle it
-// shrinks by `shrink` = twice the largest distance a player can move in a cycle; only when it drops below the collision
-// distance is the exact minimum recomputed (the O(n^2 / 32) pair loop) - in open play every few cycles instead of
+// shrinks by twice the largest distance a player moved in that cycle (at most `shrink`, twice what the server
+// allows); only when it drops below the collision distance is the exact minimum recomputed (the O(n^2 / 32) pair loop) - in open play every few cycles instead of
 // every cycle.  The ball is tested against every player every cycle.  If neither test finds an overlap, the ordered
 // relaxation rounds - which would change nothing - are skipped, so the results do not depend on this shortcut.
 template <class SP>
 __device__ __forceinline__ int fg_collisions(Episode& p, bool active, int lane, int np, bool ball_fixed, const SP& sp,
-                                             bool& ball_collided, float& sep, float shrink) {
+                                             bool& ball_collided, float& sep, float shrink, float moved2) {
   const unsigned full = 0xffffffffu;
   bool collided = false, ballhit = false, ball_any = false;
   const float r = sp.player_size() + sp.ball_size();
@@ -100,7 +100,14 @@ __device__ __forceinline__ int fg_collisions(Episode& p, bool active, int lane, 
     const float dx = p.bx - p.px, dy = p.by - p.py;
     ball_overlap = dx * dx + dy * dy < r * r;
   }
-  sep -= shrink;
+  {
+    // the farthest any player moved this cycle: sqrt of the largest squared step over the lanes, rounded up; never
+    // more than the server's limit `shrink` / 2 that was used before the speeds were looked at
+    const float v2max = __uint_as_float(__reduce_max_sync(full, __float_as_uint(active ? moved2 : 0.0f)));
+    float moved;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(moved) : "f"(v2max));
+    sep -= fminf(shrink, 2.002f * moved + 1.0e-6f);
+  }
   bool pairs_close = false;
   if (sep < r2) {  // uniform: the bound has run out, measure the true minimum (lane i looks at (i + d) mod np, d <= np/2)
     float m2 = 3.0e38f;
@@ -242,6 +249,127 @@ __device__ __forceinline__ void fg_reset(Episode& p, Match& m, const KernelParam
   m.last_touch = S2D_SIDE_UNKNOWN;
 }
 
+// The 22 commands of a cycle.  In a match every lane may carry a different command, so a switch over the command
+// would make the warp walk dash, turn, kick and go-to-point one after the other, each with its own sincos / atan2 /
+// sqrt.  Here the commands are decomposed into the pieces they share, each evaluated ONCE per warp under a vote and
+// with per-lane operands:
+//   geometry to a reference point  (go-to-point: the target, kick: the ball)  -> distance, relative angle
+//   speed                          (turn and go-to-point's turn: inertia)
+//   sincos(body + direction)       (dash, go-to-point's dash (direction 0), kick)
+// Per lane the arithmetic is the sequence of decode_command + dash_apply / turn / kick (s2d_one_player.cuh), so the
+// results are the same bit for bit.  Returns whether this lane kicked (kax, kay = its push on the ball).
+template <class SP>
+__device__ __forceinline__ bool fg_commands(Episode& p, float4 a, float goto_dist_thr, const SP& sp, const NoiseCtx& nz,
+                                            int lane, bool active, bool left, bool may_kick, float& ax, float& ay,
+                                            float& kax, float& kay) {
+  const unsigned full = 0xffffffffu;
+  const int c = active ? static_cast<int>(a.x) : S2D_CMD_NONE;
+  const bool is_goto = c == S2D_CMD_GOTO;
+  const bool is_kick = c == S2D_CMD_KICK && may_kick;
+  const bool user_dash = c == S2D_CMD_DASH, user_turn = c == S2D_CMD_TURN;
+
+  // geometry: player -> reference point
+  float dist = 0.0f, rel = 0.0f;
+  if (__any_sync(full, is_goto || is_kick)) {
+    // (lanes that are not concerned get harmless operands: a zero numerator or denominator, or sqrt(0), would send
+    // the whole warp through the slow paths of the IEEE division and square root)
+    const float dx = is_goto ? a.y - p.px : is_kick ? p.bx - p.px : 1.0f;
+    const float dy = is_goto ? a.z - p.py : is_kick ? p.by - p.py : 0.5f;
+    dist = hypot2(dx, dy);
+    rel = norm_deg_360(atan2_deg(dy, dx) - p.body);
+  }
+
+  // go-to-point decides: nothing (arrived) | turn towards the target | dash straight at it
+  bool goto_turn = false, goto_dash = false;
+  if (__any_sync(full, is_goto)) {
+    const bool on_the_way = is_goto && !(dist < goto_dist_thr);
+    const float ratio = goto_dist_thr / (is_goto ? dist : 1.0f);
+    float athr = 15.0f;  // asin(ratio) exceeds 15 degrees only for ratio > sin(15 deg) = 0.2588
+    if (__any_sync(full, on_the_way && ratio > 0.25f)) {
+      const float wide = fmax_(15.0f, atan2_deg(ratio, sqrtf(fmax_(0.0f, 1.0f - ratio * ratio))));
+      athr = ratio > 0.25f ? wide : 15.0f;
+    }
+    goto_turn = on_the_way && fabsf(rel) > athr;
+    goto_dash = on_the_way && !goto_turn;
+  }
+
+  // turn
+  const bool do_turn = user_turn || goto_turn;
+  if (__any_sync(full, do_turn)) {
+    const float speed = hypot2(do_turn ? p.vx : 1.0f, do_turn ? p.vy : 0.0f);
+    const float inertia = 1.0f + sp.inertia_moment() * speed;
+    float moment = goto_turn ? clampf(sp.min_moment(), rel * inertia, sp.max_moment()) : user_turn ? a.y : 1.0f;
+    moment = clampf(sp.min_moment(), moment, sp.max_moment());
+    if (SP::kNoise) moment = moment * (1.0f + sp.player_rand() * u11(noise_block(nz, static_cast<uint32_t>(lane)).z));
+    const float body = norm_deg(p.body + moment / inertia);
+    p.body = do_turn ? body : p.body;
+  }
+
+  // dash direction (go-to-point dashes straight: direction 0) and the one sincos
+  const bool do_dash = user_dash || goto_dash;
+  float dir = 0.0f, rate = 1.0f;
+  if (__any_sync(full, do_dash)) dash_direction(user_dash ? a.z : 0.0f, sp, dir, rate);
+  const float user_power = clampf(sp.min_dash_power(), a.y, sp.max_dash_power());
+  const bool back = user_dash && user_power < 0.0f;
+  float sn = 0.0f, cs = 1.0f;
+  if (__any_sync(full, do_dash || is_kick)) {
+    const float kick_dir = clampf(sp.min_moment(), a.z, sp.max_moment());
+    const float d = is_kick ? kick_dir : back ? dir + 180.0f : dir;
+    sincos_deg(p.body + d, sn, cs);
+  }
+
+  // dash
+  if (__any_sync(full, do_dash)) {
+    float power = user_power;
+    if (__any_sync(full, goto_dash)) {
+      const float v_along = p.vx * cs + p.vy * sn;
+      const float need = (dist - v_along) / (goto_dash ? p.effort * sp.dash_power_rate() : 1.0f);
+      const float reach = clampf(sp.min_dash_power(), clampf(0.0f, need, a.w), sp.max_dash_power());
+      power = goto_dash ? reach : power;
+    }
+    float need = back ? power * -2.0f : power;
+    need = fmin_(need, p.stamina + sp.extra_stamina());
+    const float stamina = fmax_(0.0f, p.stamina - need);
+    power = back ? need * -0.5f : need;
+    float eff = fabsf(p.effort * power * rate * sp.dash_power_rate());
+    const float slow = left ? sp.slowness_on_top_for_left_team() : sp.slowness_on_top_for_right_team();
+    if (slow != 1.0f && p.py < 0.0f) eff = cold_div(eff, slow);
+    p.stamina = do_dash ? stamina : p.stamina;
+    ax = do_dash ? eff * cs : 0.0f;
+    ay = do_dash ? eff * sn : 0.0f;
+  }
+
+  // kick
+  bool kicked = false;
+  if (__any_sync(full, is_kick)) {
+    kicked = is_kick && !(dist > sp.kickable_area());
+    const float power = clampf(0.0f, a.y, sp.max_power());
+    const float dir_diff = fabsf(rel);
+    const float dist_ball = dist - sp.player_size() - sp.ball_size();
+    const float eff = power * sp.kick_power_rate() *
+                      (1.0f - 0.25f * dir_diff * static_cast<float>(1.0 / 180.0) - 0.25f * dist_ball / sp.kickable_margin());
+    float bax = 0.0f, bay = 0.0f;
+    bax += eff * cs;
+    bay += eff * sn;
+    if (SP::kNoise) {
+      if (__any_sync(full, kicked)) {
+        const uint4 w = noise_block(nz, static_cast<uint32_t>(lane)), w2 = noise_block(nz, 32u + static_cast<uint32_t>(lane));
+        const float pos_rate = 0.5f + 0.25f * (dir_diff * static_cast<float>(1.0 / 180.0) + dist_ball / sp.kickable_margin());
+        const float speed_rate = 0.5f + 0.5f * (hypot2(p.bvx, p.bvy) / (sp.ball_speed_max() * sp.ball_decay()));
+        const float max_rand = sp.kick_rand() * (power / sp.max_power()) * (pos_rate + speed_rate);
+        const float mag = u32_to_unit(w.w) * max_rand;
+        float ns, nc;
+        sincos_deg(u11(w2.x) * 180.0f, ns, nc);
+        bax += mag * nc;
+        bay += mag * ns;
+      }
+    }
+    kax = kicked ? bax : 0.0f;
+    kay = kicked ? bay : 0.0f;
+  }
+  return kicked;
+}
+
 // One cycle of the match.  `a` = this lane's command {cmd, a, b, c}.  Returns done; reward / result are uniform.
 template <class SP>
 __device__ __forceinline__ bool fg_cycle(Episode& p, Match& m, const KernelParams& P, const SP& sp, uint64_t gid, int lane,
@@ -256,20 +384,8 @@ __device__ __forceinline__ bool fg_cycle(Episode& p, Match& m, const KernelParam
 
   // ---- commands ----
   float ax = 0.0f, ay = 0.0f, kax = 0.0f, kay = 0.0f;
-  bool kicked = false;
   const NoiseCtx nz{P.seed, gid, m.cycle};
-  if (active) {
-    int cmd;
-    float power, dir, rate;
-    decode_command(p, a, P.goto_dist_thr, sp, cmd, power, dir, rate);
-    if (cmd == S2D_CMD_DASH) {
-      dash_apply(p, power, dir, rate, sp, ax, ay, left);
-    } else if (cmd == S2D_CMD_TURN) {
-      turn(p, dir, sp, nz, static_cast<uint32_t>(lane));
-    } else if (cmd == S2D_CMD_KICK && (!dead || my_side == m.side)) {
-      kicked = kick(p, power, dir, sp, kax, kay, nz, static_cast<uint32_t>(lane));
-    }
-  }
+  const bool kicked = fg_commands(p, a, P.goto_dist_thr, sp, nz, lane, active, left, !dead || my_side == m.side, ax, ay, kax, kay);
   const unsigned kick_ballot = __ballot_sync(full, kicked);
   float bax = 0.0f, bay = 0.0f;
   if (kick_ballot) {  // uniform; without a kicker both sums are exactly zero
@@ -287,6 +403,7 @@ __device__ __forceinline__ bool fg_cycle(Episode& p, Match& m, const KernelParam
 
   // ---- move ----
   const float pbx = p.bx, pby = p.by;
+  const float ppx = p.px, ppy = p.py;
   if (active)
     move_object<SP::kNoise>(p.px, p.py, p.vx, p.vy, ax, ay, sp.player_accel_max(), sp.player_accel_max2(),
                             sp.player_speed_max(), sp.player_speed_max2(), sp.player_decay(), sp.player_rand(), &nz,
@@ -302,7 +419,8 @@ __device__ __forceinline__ bool fg_cycle(Episode& p, Match& m, const KernelParam
   // ---- collisions ----
   // the farthest a player can move in a cycle: speed_max (the clamp) plus, with noise, up to rand * sqrt(2) of it
   const float vmax = sp.player_speed_max() * (SP::kNoise ? 1.0f + 1.5f * sp.player_rand() : 1.0f) * 1.001f;
-  const int hit = fg_collisions(p, active, lane, np, dead, sp, ball_collided, m.sep, 2.0f * vmax);
+  const float stepx = p.px - ppx, stepy = p.py - ppy;
+  const int hit = fg_collisions(p, active, lane, np, dead, sp, ball_collided, m.sep, 2.0f * vmax, stepx * stepx + stepy * stepy);
   collided_mask = __ballot_sync(full, (hit & 1) != 0);
   {
     const unsigned touch = __ballot_sync(full, (hit & 2) != 0);
@@ -436,10 +554,13 @@ __device__ __forceinline__ void fg_store(const KernelParams& P, const FgLayout& 
 #endif
 constexpr int kFgBlock = 128;  // 4 matches per block
 
-// K lockstep cycles of every match; actions float4 [N][K][np].
-template <int VAR>
+// K lockstep cycles of every match; actions float4 [N][K][np].  NP = 22 is the 11 v 11 instantiation (player count,
+// team masks and row strides become immediates; otherwise the compiler keeps re-reading them from the constant bank
+// under register pressure); NP = 0 takes the player count at run time.
+template <int VAR, int NP>
 __global__ void __launch_bounds__(kFgBlock, S2D_FG_MIN_BLOCKS) fullgame_step_kernel(const __grid_constant__ KernelParams P, const int K,
-                                                                 const int np, const int half_time) {
+                                                                 const int np_runtime, const int half_time) {
+  const int np = NP ? NP : np_runtime;
   using SP = typename VariantSP<VAR>::type;
   const SP sp(P.cc);
   __shared__ __align__(16) float s_stage[kFgBlock / 32][kFgObsDim];
@@ -458,10 +579,15 @@ __global__ void __launch_bounds__(kFgBlock, S2D_FG_MIN_BLOCKS) fullgame_step_ker
   bool ball_collided = false;
   float reward_sum = 0.0f;
   uint32_t any_done = 0, last_result = 0;
-  const float4* act = static_cast<const float4*>(P.actions) + (env * K) * np + lane;
+  // the lane's commands: K rows np apart.  The next row is fetched while this cycle computes (its latency would
+  // otherwise sit in front of every cycle: nothing can start before the command is known).
+  const float4* act = static_cast<const float4*>(P.actions) + (env * K) * np + (active ? lane : 0);
+  float4 a_next = __ldg(act);
 #pragma unroll 1
-  for (int k = 0; k < K; ++k) {
-    const float4 a = active ? __ldg(act + static_cast<int64_t>(k) * np) : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int k = K; k > 0; --k) {
+    const float4 a = active ? a_next : make_float4(0.f, 0.f, 0.f, 0.f);
+    act += np;
+    if (k > 1) a_next = __ldg(act);
     float rw;
     int rs;
     const bool done = fg_cycle(p, m, P, sp, gid, lane, active, np, half_time, a, rw, rs, collided_mask, kicked_mask,

@@ -134,8 +134,15 @@ __device__ __forceinline__ bool check_episode(Episode& e, const KernelParams& P,
 // reach_ball_env.py:87-111.  Must follow a check_episode on the same state: obs[0] is exactly the
 // body-to-ball angle that check just stored in mem_ang, so the atan2 is not repeated.
 __device__ __forceinline__ void build_obs(const Episode& e, float* o) {
-  const float speed = hypot2(e.bvx, e.bvy);
-  const float bdir = atan2_deg(e.bvy, e.bvx);
+  // A resting ball (the reference's default reset) or one rolling along an axis would send the warp through the slow
+  // paths of the IEEE square root (sqrt(0)) and division (zero numerator): those cases are answered without them.
+  const bool still = e.bvx == 0.0f && e.bvy == 0.0f;
+  const bool axis = e.bvx == 0.0f || e.bvy == 0.0f;
+  const float on_axis = e.bvy == 0.0f ? (e.bvx < 0.0f ? 180.0f : 0.0f) : (e.bvy > 0.0f ? 90.0f : -90.0f);
+  const float h = hypot2(still ? 1.0f : e.bvx, e.bvy);
+  const float t = atan2_deg(axis ? 1.0f : e.bvy, axis ? 2.0f : e.bvx);
+  const float speed = still ? 0.0f : h;
+  const float bdir = axis ? on_axis : t;
   o[0] = e.mem_ang * static_cast<float>(1.0 / 180.0);
   o[1] = e.body * static_cast<float>(1.0 / 180.0);
   o[2] = e.px * static_cast<float>(1.0 / 52.5);

@@ -9,7 +9,8 @@ import torch  # noqa: E402
 
 from soccer2d_b200 import Soccer2DVecEnv  # noqa: E402
 
-KW = dict(use_continuous_action=False, action_space_size=16, change_ball_position=True, change_ball_velocity=True)
+KW = dict(use_continuous_action=False, action_space_size=16, change_ball_position=True,
+          change_ball_velocity=os.environ.get("S2D_TUNE_STILL", "0") != "1")  # S2D_TUNE_STILL=1: the ball rests (reference default)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 out = []
 for name, n, k, warm, steps in (("k16", 1 << 20, 16, 14, 30), ("k1", 1 << 23, 1, 10, 30)):

@@ -19,6 +19,8 @@ struct S2DSim {
   S2DBuffers buf;
   KernelParams kp;
   float4* d_table = nullptr;
+  float* d_types = nullptr;  // heterogeneous players: [S2D_MAX_PLAYER_TYPES][PT_ROW]
+  bool hetero = false;
   bool default_sp = false;  // cfg.sp == rcssserver defaults: use the constant-folded kernels
   bool bound = false;
   // host-buffer pipeline (s2d_bind_pipeline / s2d_submit_host / s2d_wait_host): two slots of actions + outputs
@@ -214,6 +216,7 @@ int s2d_destroy(S2DHandle h) {
   {
     DeviceGuard guard(h->cfg.device);
     if (h->d_table) cudaFree(h->d_table);
+    if (h->d_types) cudaFree(h->d_types);
     if (h->st_in) {
       cudaStreamSynchronize(h->st_in);
       cudaStreamSynchronize(h->st_compute);
@@ -257,9 +260,12 @@ int s2d_reset(S2DHandle h, const uint8_t* device_mask_or_null, void* stream) {
   if (!h) return S2D_ERR_INVALID;
   if (!h->bound) return fail(h, S2D_ERR_UNBOUND, "s2d_bind has not been called");
   DeviceGuard guard(h->cfg.device);
-  if (h->cfg.scenario == S2D_SCENARIO_FULLGAME)
-    fullgame_reset_kernel<<<h->grid, kFgBlock, 0, static_cast<cudaStream_t>(stream)>>>(
-        h->kp, device_mask_or_null, 2 * h->cfg.players_per_side, h->cfg.half_time_cycles);
+  if (h->cfg.scenario == S2D_SCENARIO_FULLGAME) {
+    const int np = 2 * h->cfg.players_per_side, ht = h->cfg.half_time_cycles;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (h->hetero) fullgame_reset_kernel<true><<<h->grid, kFgBlock, 0, s>>>(h->kp, device_mask_or_null, np, ht);
+    else fullgame_reset_kernel<false><<<h->grid, kFgBlock, 0, s>>>(h->kp, device_mask_or_null, np, ht);
+  }
   else if (h->cfg.scenario == S2D_SCENARIO_SHOOT) {
     if (h->cfg.noise) reset_kernel<S2D_SCENARIO_SHOOT, true><<<h->grid, kBlock, 0, static_cast<cudaStream_t>(stream)>>>(h->kp, device_mask_or_null);
     else reset_kernel<S2D_SCENARIO_SHOOT, false><<<h->grid, kBlock, 0, static_cast<cudaStream_t>(stream)>>>(h->kp, device_mask_or_null);
@@ -281,7 +287,9 @@ static cudaError_t launch_step(S2DSim* h, const KernelParams& kp, int k_substeps
   } while (0)
   if (h->cfg.scenario == S2D_SCENARIO_FULLGAME) {
     const int np = 2 * h->cfg.players_per_side, ht = h->cfg.half_time_cycles;
-    if (h->cfg.noise) fullgame_step_kernel<kVarNoisy, 0><<<h->grid, kFgBlock, 0, s>>>(kp, k_substeps, np, ht);
+    if (h->hetero && h->cfg.noise) fullgame_step_kernel<kVarHeteroNoisy, 0><<<h->grid, kFgBlock, 0, s>>>(kp, k_substeps, np, ht);
+    else if (h->hetero) fullgame_step_kernel<kVarHetero, 0><<<h->grid, kFgBlock, 0, s>>>(kp, k_substeps, np, ht);
+    else if (h->cfg.noise) fullgame_step_kernel<kVarNoisy, 0><<<h->grid, kFgBlock, 0, s>>>(kp, k_substeps, np, ht);
     else if (!h->default_sp) fullgame_step_kernel<kVarRuntime, 0><<<h->grid, kFgBlock, 0, s>>>(kp, k_substeps, np, ht);
     else if (np == 22) fullgame_step_kernel<kVarDefault, 22><<<h->grid, kFgBlock, 0, s>>>(kp, k_substeps, np, ht);
     else fullgame_step_kernel<kVarDefault, 0><<<h->grid, kFgBlock, 0, s>>>(kp, k_substeps, np, ht);
@@ -526,6 +534,122 @@ int s2d_export_env(S2DHandle h, int64_t i, S2DEnvSnapshot* out, void* stream) {
   p.uniform_number = 1;  // DoMovePlayer(our_side=True, uniform_number=1), reach_ball_env.py:190-194
   p.collided = (u.w & S2D_FLAG_PLAYER_COLLIDED) ? 1 : 0;
   p.kicked = (u.w & S2D_FLAG_KICKED) ? 1 : 0;
+  return S2D_OK;
+}
+
+// ---- heterogeneous players ---------------------------------------------------------------------------------
+// host-side Philox4x32-10, the same function as s2d_math.cuh's (counter = (env lo, env hi, index, purpose<<24 | sub))
+static void philox_host(uint64_t seed, uint64_t env, uint32_t index, uint32_t purpose, uint32_t sub, uint32_t out[4]) {
+  uint32_t c0 = static_cast<uint32_t>(env), c1 = static_cast<uint32_t>(env >> 32), c2 = index, c3 = (purpose << 24) | sub;
+  uint32_t k0 = static_cast<uint32_t>(seed), k1 = static_cast<uint32_t>(seed >> 32);
+  for (int i = 0; i < 10; ++i) {
+    const uint64_t p0 = static_cast<uint64_t>(0xD2511F53u) * c0, p1 = static_cast<uint64_t>(0xCD9E8D57u) * c2;
+    const uint32_t n0 = static_cast<uint32_t>(p1 >> 32) ^ c1 ^ k0, n2 = static_cast<uint32_t>(p0 >> 32) ^ c3 ^ k1;
+    c1 = static_cast<uint32_t>(p1);
+    c3 = static_cast<uint32_t>(p0);
+    c0 = n0;
+    c2 = n2;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+static S2DPlayerType default_player_type(const S2DServerParam& sp) {
+  S2DPlayerType t{};
+  t.player_decay = sp.player_decay;
+  t.inertia_moment = sp.inertia_moment;
+  t.dash_power_rate = sp.dash_power_rate;
+  t.stamina_inc_max = sp.stamina_inc_max;
+  t.kickable_margin = sp.kickable_margin;
+  t.kick_rand = sp.kick_rand;
+  t.extra_stamina = sp.extra_stamina;
+  t.effort_max = sp.effort_max;
+  t.effort_min = sp.effort_min;
+  t.kick_power_rate = sp.kick_power_rate;
+  return t;
+}
+
+// rcssserver HeteroPlayer (heteroplayer.cpp; default player.conf): four independent trade-offs, re-drawn until the
+// speed the type can sustain, effort_max * dash_power_rate * max_dash_power / (1 - player_decay), lies within 0.1
+// below player_speed_max.  Draws: Philox (seed, type id, trial, purpose 4), one word per trade-off, in float.
+int s2d_generate_player_types(uint64_t seed, const S2DServerParam* sp, S2DPlayerType* out, int n) {
+  if (!sp || !out || n < 1 || n > S2D_MAX_PLAYER_TYPES) return S2D_ERR_INVALID;
+  out[0] = default_player_type(*sp);
+  for (int id = 1; id < n; ++id) {
+    S2DPlayerType t = out[0];
+    for (uint32_t trial = 0; trial < 1000u; ++trial) {
+      uint32_t w[4];
+      philox_host(seed, static_cast<uint64_t>(id), trial, 4u, 0u, w);
+      const float u0 = static_cast<float>(w[0] >> 8) * (1.0f / 16777216.0f), u1 = static_cast<float>(w[1] >> 8) * (1.0f / 16777216.0f);
+      const float u2 = static_cast<float>(w[2] >> 8) * (1.0f / 16777216.0f), u3 = static_cast<float>(w[3] >> 8) * (1.0f / 16777216.0f);
+      const float d_decay = -0.1f + 0.2f * u0;          // player_decay_delta_min / max
+      const float d_dash = -0.0012f + 0.002f * u1;      // new_dash_power_rate_delta_min / max
+      const float d_kick = -0.1f + 0.2f * u2;           // kickable_margin_delta_min / max
+      const float d_extra = 50.0f * u3;                 // extra_stamina_delta_min / max
+      S2DPlayerType c = out[0];
+      c.player_decay = sp->player_decay + d_decay;
+      c.inertia_moment = sp->inertia_moment + d_decay * 25.0f;   // inertia_moment_delta_factor
+      c.dash_power_rate = sp->dash_power_rate + d_dash;
+      c.stamina_inc_max = sp->stamina_inc_max + d_dash * -6000.0f;  // new_stamina_inc_max_delta_factor
+      c.kickable_margin = sp->kickable_margin + d_kick;
+      c.kick_rand = sp->kick_rand + d_kick * 1.0f;               // kick_rand_delta_factor
+      c.extra_stamina = sp->extra_stamina + d_extra;
+      c.effort_max = sp->effort_max + d_extra * -0.004f;         // effort_max_delta_factor
+      c.effort_min = sp->effort_min + d_extra * -0.004f;         // effort_min_delta_factor
+      const float real_speed_max = c.effort_max * c.dash_power_rate * sp->max_dash_power / (1.0f - c.player_decay);
+      if (sp->player_speed_max - 0.1f < real_speed_max && real_speed_max < sp->player_speed_max) {
+        t = c;
+        break;
+      }
+    }
+    out[id] = t;
+  }
+  return S2D_OK;
+}
+
+int s2d_set_player_types(S2DHandle h, const S2DPlayerType* types, int n, const uint8_t* type_of_player) {
+  if (!h) return S2D_ERR_INVALID;
+  if (h->cfg.scenario != S2D_SCENARIO_FULLGAME) return fail(h, S2D_ERR_INVALID, "player types exist in the FULLGAME scenario only");
+  if (n == 0) {
+    h->hetero = false;
+    return S2D_OK;
+  }
+  const int np = 2 * h->cfg.players_per_side;
+  if (!types || !type_of_player || n < 1 || n > S2D_MAX_PLAYER_TYPES) return fail(h, S2D_ERR_INVALID, "need 1..%d player types and the type of each of the %d players", S2D_MAX_PLAYER_TYPES, np);
+  float rows[S2D_MAX_PLAYER_TYPES * PT_ROW] = {};
+  for (int k = 0; k < n; ++k) {
+    const S2DPlayerType& t = types[k];
+    if (!(t.player_decay >= 0.0f && t.player_decay < 1.0f) || !(t.kickable_margin > 0.0f) || !(t.effort_min <= t.effort_max) ||
+        !(t.dash_power_rate > 0.0f) || !(t.inertia_moment >= 0.0f))
+      return fail(h, S2D_ERR_INVALID, "player type %d is not physical (decay in [0,1), kickable_margin > 0, effort_min <= effort_max, ...)", k);
+    float* r = rows + k * PT_ROW;
+    r[PT_PLAYER_DECAY] = t.player_decay;
+    r[PT_INERTIA_MOMENT] = t.inertia_moment;
+    r[PT_DASH_POWER_RATE] = t.dash_power_rate;
+    r[PT_STAMINA_INC_MAX] = t.stamina_inc_max;
+    r[PT_KICKABLE_MARGIN] = t.kickable_margin;
+    r[PT_KICK_RAND] = t.kick_rand;
+    r[PT_EXTRA_STAMINA] = t.extra_stamina;
+    r[PT_EFFORT_MAX] = t.effort_max;
+    r[PT_EFFORT_MIN] = t.effort_min;
+    r[PT_KICK_POWER_RATE] = t.kick_power_rate;
+    r[PT_KICKABLE_AREA] = h->cfg.sp.player_size + h->cfg.sp.ball_size + t.kickable_margin;  // as S2D_DERIVED_PARAMS
+  }
+  uint8_t type_of[32] = {};
+  for (int j = 0; j < np; ++j) {
+    if (type_of_player[j] >= n) return fail(h, S2D_ERR_INVALID, "player %d has type %d, but there are %d types", j, type_of_player[j], n);
+    type_of[j] = type_of_player[j];
+  }
+  DeviceGuard guard(h->cfg.device);
+  if (!h->d_types) S2D_CUDA(h, cudaMalloc(&h->d_types, sizeof(rows)));
+  S2D_CUDA(h, cudaMemcpy(h->d_types, rows, sizeof(rows), cudaMemcpyHostToDevice));  // synchronous: later launches see it
+  KernelParams* all[3] = {&h->kp, &h->pkp[0], &h->pkp[1]};
+  for (KernelParams* kp : all) {
+    kp->player_types = h->d_types;
+    memcpy(kp->type_of, type_of, sizeof(type_of));
+  }
+  h->hetero = true;
   return S2D_OK;
 }
 

@@ -549,6 +549,17 @@ __device__ __forceinline__ void fg_store(const KernelParams& P, const FgLayout& 
   }
 }
 
+// heterogeneous players: the block copies the type table to shared memory and every lane points at its player's row
+template <class SP>
+__device__ __forceinline__ void fg_bind_player_type(SP& sp, const KernelParams& P, int lane) {
+  if constexpr (SP::kHetero) {
+    __shared__ float s_types[S2D_MAX_PLAYER_TYPES * PT_ROW];
+    for (int k = threadIdx.x; k < S2D_MAX_PLAYER_TYPES * PT_ROW; k += blockDim.x) s_types[k] = __ldg(P.player_types + k);
+    __syncthreads();
+    sp.row = s_types + PT_ROW * P.type_of[lane];
+  }
+}
+
 #ifndef S2D_FG_MIN_BLOCKS
 #define S2D_FG_MIN_BLOCKS 8
 #endif
@@ -562,9 +573,10 @@ __global__ void __launch_bounds__(kFgBlock, S2D_FG_MIN_BLOCKS) fullgame_step_ker
                                                                  const int np_runtime, const int half_time) {
   const int np = NP ? NP : np_runtime;
   using SP = typename VariantSP<VAR>::type;
-  const SP sp(P.cc);
+  SP sp(P.cc);
   __shared__ __align__(16) float s_stage[kFgBlock / 32][kFgObsDim];
   const int lane = threadIdx.x & 31;
+  fg_bind_player_type(sp, P, lane);
   const int64_t env = static_cast<int64_t>(blockIdx.x) * (kFgBlock / 32) + (threadIdx.x >> 5);
   if (env >= P.num_envs) return;  // whole warp leaves together
   const FgLayout L{P.num_envs, np};
@@ -623,15 +635,18 @@ __global__ void __launch_bounds__(kFgBlock, S2D_FG_MIN_BLOCKS) fullgame_step_ker
   }
 }
 
+template <bool HETERO>
 __global__ void __launch_bounds__(kFgBlock) fullgame_reset_kernel(const __grid_constant__ KernelParams P,
                                                                   const uint8_t* __restrict__ mask, const int np,
                                                                   const int half_time) {
   __shared__ __align__(16) float s_stage[kFgBlock / 32][kFgObsDim];
   const int lane = threadIdx.x & 31;
+  using SP = typename std::conditional<HETERO, HeteroSP<false>, RuntimeSP>::type;
+  SP sp(P.cc);
+  fg_bind_player_type(sp, P, lane);
   const int64_t env = static_cast<int64_t>(blockIdx.x) * (kFgBlock / 32) + (threadIdx.x >> 5);
   if (env >= P.num_envs) return;
   if (mask && !mask[env]) return;
-  const RuntimeSP sp(P.cc);
   const FgLayout L{P.num_envs, np};
   const bool active = lane < np;
   Episode p;

@@ -101,6 +101,7 @@ inline bool is_default_server_param(const S2DServerParam& sp) {
 // accessors over the kernel's constant bank
 struct RuntimeSP {
   static constexpr bool kNoise = false;
+  static constexpr bool kHetero = false;
   const CycleConsts& c;
   S2D_HD explicit RuntimeSP(const CycleConsts& c_) : c(c_) {}
 #define X(name, def) S2D_HD float name() const { return c.sp.name; }
@@ -117,6 +118,30 @@ struct NoisySP : RuntimeSP {
   S2D_HD explicit NoisySP(const CycleConsts& c_) : RuntimeSP(c_) {}
 };
 
+// Heterogeneous players (FULLGAME): the per-player fields of S2DPlayerType come from this lane's row of the type table
+// (shared memory, 16 floats a row: S2DPlayerType with the derived kickable_area in reserved[0]); the rest as RuntimeSP.
+enum { PT_PLAYER_DECAY, PT_INERTIA_MOMENT, PT_DASH_POWER_RATE, PT_STAMINA_INC_MAX, PT_KICKABLE_MARGIN, PT_KICK_RAND,
+       PT_EXTRA_STAMINA, PT_EFFORT_MAX, PT_EFFORT_MIN, PT_KICK_POWER_RATE, PT_KICKABLE_AREA, PT_ROW = 16 };
+template <bool NOISE>
+struct HeteroSP : RuntimeSP {
+  static constexpr bool kNoise = NOISE;
+  static constexpr bool kHetero = true;
+  const float* row = nullptr;  // this player's type
+  S2D_HD explicit HeteroSP(const CycleConsts& c_) : RuntimeSP(c_) {}
+  S2D_HD float player_decay() const { return row[PT_PLAYER_DECAY]; }
+  S2D_HD float inertia_moment() const { return row[PT_INERTIA_MOMENT]; }
+  S2D_HD float dash_power_rate() const { return row[PT_DASH_POWER_RATE]; }
+  S2D_HD float stamina_inc_max() const { return row[PT_STAMINA_INC_MAX]; }
+  S2D_HD float kickable_margin() const { return row[PT_KICKABLE_MARGIN]; }
+  S2D_HD float kick_rand() const { return row[PT_KICK_RAND]; }
+  S2D_HD float extra_stamina() const { return row[PT_EXTRA_STAMINA]; }
+  S2D_HD float effort_max() const { return row[PT_EFFORT_MAX]; }
+  S2D_HD float effort_init() const { return row[PT_EFFORT_MAX]; }
+  S2D_HD float effort_min() const { return row[PT_EFFORT_MIN]; }
+  S2D_HD float kick_power_rate() const { return row[PT_KICK_POWER_RATE]; }
+  S2D_HD float kickable_area() const { return row[PT_KICKABLE_AREA]; }
+};
+
 // the default configuration as compile-time constants
 struct DefaultBase {
 #define X(name, def) S2D_HDC float name() { return def; }
@@ -125,6 +150,7 @@ struct DefaultBase {
 };
 struct DefaultSP : DefaultBase {
   static constexpr bool kNoise = false;
+  static constexpr bool kHetero = false;
   S2D_HD explicit DefaultSP(const CycleConsts&) {}
 #define Y(name, expr)                \
   S2D_HDC float name() {             \

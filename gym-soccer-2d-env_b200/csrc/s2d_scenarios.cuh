@@ -41,6 +41,8 @@ struct KernelParams {
   float* terminal_obs;
   unsigned long long* stats;  // [kStatSlots][kStatWords]
   int32_t kick_actions;       // SHOOT Discrete(n): the last kick_actions actions are kicks
+  const float* player_types;  // FULLGAME, heterogeneous players: [S2D_MAX_PLAYER_TYPES][PT_ROW] (device), else nullptr
+  uint8_t type_of[32];        // lane -> row of player_types
   const float4* action_table; // [256] Discrete(n) -> {cmd, power, lowered direction, dash direction rate}, built on the host
 };
 
@@ -481,11 +483,16 @@ constexpr int kBlock = S2D_BLOCK;
 // access pulls the lane's sector(s) into L1 and the following cycles hit there (ld.global.nc).
 // SCN: scenario; ACT: action encoding; VAR: how the constants come in (kVarRuntime: constant bank, kVarDefault: the
 // default ServerParam folded at compile time, kVarNoisy: constant bank + rcssserver noise).
-constexpr int kVarRuntime = 0, kVarDefault = 1, kVarNoisy = 2;
+// kVarHetero / kVarHeteroNoisy (FULLGAME): per-player PlayerType values from the handle's type table.
+constexpr int kVarRuntime = 0, kVarDefault = 1, kVarNoisy = 2, kVarHetero = 3, kVarHeteroNoisy = 4;
 template <int VAR>
 struct VariantSP {
-  using type = typename std::conditional<VAR == kVarDefault, DefaultSP,
-                                         typename std::conditional<VAR == kVarNoisy, NoisySP, RuntimeSP>::type>::type;
+  using type = typename std::conditional<
+      VAR == kVarDefault, DefaultSP,
+      typename std::conditional<
+          VAR == kVarNoisy, NoisySP,
+          typename std::conditional<VAR == kVarHetero, HeteroSP<false>,
+                                    typename std::conditional<VAR == kVarHeteroNoisy, HeteroSP<true>, RuntimeSP>::type>::type>::type>::type;
 };
 
 // The end of an episode inside the K loop, handled by the warp as a whole: one vote per step replaces a divergent

@@ -8,7 +8,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 # ---- constants (mirror include/soccer2d.h) ----------------------------------------------------------
 S2D_OK, S2D_ERR_INVALID, S2D_ERR_UNBOUND, S2D_ERR_CUDA, S2D_ERR_NO_DEVICE = 0, -1, -2, -3, -4
@@ -85,6 +85,19 @@ class EnvSnapshot(C.Structure):
                [("players", PlayerSnapshot * 22)]
 
 
+MAX_PLAYER_TYPES = 18
+_PT_FIELDS = ("player_decay inertia_moment dash_power_rate stamina_inc_max kickable_margin kick_rand extra_stamina "
+              "effort_max effort_min kick_power_rate").split()
+
+
+class PlayerType(C.Structure):
+    """proto PlayerType (idl/service.proto:1697-1732): the fields the cycle reads"""
+    _fields_ = [(n, C.c_float) for n in _PT_FIELDS] + [("reserved", C.c_float * 6)]
+
+    def as_dict(self) -> dict:
+        return {n: getattr(self, n) for n in _PT_FIELDS}
+
+
 # every symbol include/soccer2d.h declares: (restype, argtypes)
 _H = C.c_void_p
 SIGNATURES = {
@@ -111,6 +124,8 @@ SIGNATURES = {
     "s2d_stats_reset": (C.c_int, [_H, C.c_void_p]),
     "s2d_export_env": (C.c_int, [_H, C.c_int64, C.POINTER(EnvSnapshot), C.c_void_p]),
     "s2d_launch_info": (C.c_int, [_H, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "s2d_generate_player_types": (C.c_int, [C.c_uint64, C.POINTER(ServerParam), C.POINTER(PlayerType), C.c_int]),
+    "s2d_set_player_types": (C.c_int, [_H, C.POINTER(PlayerType), C.c_int, C.POINTER(C.c_uint8)]),
 }
 
 # S2D_LIB: alternative build of the same library (kernel tuning experiments); default = the in-tree build

@@ -108,3 +108,27 @@ def trainer_state_dict(snap: _abi.EnvSnapshot) -> dict:
         "left_team_score": int(snap.left_score), "right_team_score": int(snap.right_score),
     }
     return {"world_model": wm}
+
+
+def player_type_dict(type_id: int, t: dict, sp) -> dict:
+    """proto PlayerType (idl/service.proto:1697-1732) of one of the handle's player types: `t` = the fields of
+    _abi.PlayerType, `sp` = the env's ServerParam (for the fields rcssserver's default player.conf does not vary and
+    for the derived ones: kickable_area, real_speed_max, ...)."""
+    decay, dpr, emax = float(t["player_decay"]), float(t["dash_power_rate"]), float(t["effort_max"])
+    real_speed_max = min(emax * dpr * sp.max_dash_power / (1.0 - decay), sp.player_speed_max)
+    accel = emax * dpr * sp.max_dash_power
+    speed, cycles = 0.0, 0
+    while cycles < 50 and speed < real_speed_max - 0.01:  # librcsc PlayerType::cyclesToReachMaxSpeed
+        speed = speed * decay + accel
+        cycles += 1
+    return {
+        "id": int(type_id), "stamina_inc_max": float(t["stamina_inc_max"]), "player_decay": decay,
+        "inertia_moment": float(t["inertia_moment"]), "dash_power_rate": dpr, "player_size": float(sp.player_size),
+        "kickable_margin": float(t["kickable_margin"]), "kick_rand": float(t["kick_rand"]),
+        "extra_stamina": float(t["extra_stamina"]), "effort_max": emax, "effort_min": float(t["effort_min"]),
+        "kick_power_rate": float(t["kick_power_rate"]),
+        "kickable_area": float(sp.player_size + sp.ball_size + t["kickable_margin"]),
+        "real_speed_max": real_speed_max, "player_speed_max2": float(sp.player_speed_max) ** 2,
+        "real_speed_max2": real_speed_max ** 2, "cycles_to_reach_max_speed": cycles,
+        "player_speed_max": float(sp.player_speed_max),
+    }

@@ -63,6 +63,8 @@ class Soccer2DVecEnv(_VecEnvBase):
     use_command_action   actions are proto-style commands {cmd, a, b, c} (S2D_CMD_*: dash / turn / kick /
                    body_go_to_point) instead of the scenario's own action space; shape [N, K, 4] float32
     goto_dist_thr  Body_GoToPoint.distance_threshold for CMD_GOTO
+    hetero_seed    fullgame: draw rcssserver's 18 heterogeneous player types from this seed and give every player but
+                   the two goalkeepers a random one of them (see `set_player_types` for an explicit assignment)
     noise          rcssserver's player_rand / ball_rand / kick_rand noise from the counter-based RNG, keyed on
                    (seed, global env id, server cycle, agent): reproducible, independent of sharding and of
                    `substeps`.  Off by default (the mode in which runs are compared with the double-precision CPU truth)
@@ -77,7 +79,7 @@ class Soccer2DVecEnv(_VecEnvBase):
     def __init__(self, num_envs: int, scenario: str = "reachball", device="cuda", seed: int = 0, substeps: int = 1,
                  env_id_offset: int = 0, auto_reset: bool = True, terminal_obs: bool = False,
                  server_param: dict | None = None, use_command_action: bool = False, goto_dist_thr: float = 0.5,
-                 noise: bool = False, host_mapped_io: bool = False, **kwargs):
+                 noise: bool = False, host_mapped_io: bool = False, hetero_seed: int | None = None, **kwargs):
         if scenario.lower() not in _SCENARIOS:
             raise ValueError(f"Environment {scenario} not found.")  # environment_factory.py:28
         self.scenario = scenario.lower()
@@ -194,6 +196,14 @@ class Soccer2DVecEnv(_VecEnvBase):
         self._pinned = None
         self._pipe = None
         self._pending = None
+        self.player_types = None
+        self.type_of_player = None
+        if hetero_seed is not None:
+            types = self.generate_player_types(int(hetero_seed))
+            pick = np.random.default_rng(int(hetero_seed)).integers(1, len(types), size=self.num_players)
+            pps = self.num_players // 2
+            pick[0] = pick[pps] = 0  # goalkeepers keep the default type, as rcssserver requires
+            self.set_player_types(types, pick)
         if _VecEnvBase is not object:
             _VecEnvBase.__init__(self, self.num_envs, self.observation_space, self.action_space)
         self._closed = False
@@ -431,6 +441,29 @@ class Soccer2DVecEnv(_VecEnvBase):
             off += n * 16
         assert off == self.state.numel()
         return out
+
+    # ---- heterogeneous players (fullgame; proto PlayerType, idl/service.proto:1697-1732) ------------------------
+    def generate_player_types(self, seed: int, n: int = _abi.MAX_PLAYER_TYPES) -> list:
+        """rcssserver's HeteroPlayer draws for this env's ServerParam: [type 0 = default player, n - 1 drawn types]"""
+        out = (_abi.PlayerType * n)()
+        _abi.check(self.lib.s2d_generate_player_types(int(seed) & 0xFFFFFFFFFFFFFFFF, C.byref(self.cfg.sp), out, n))
+        return list(out)
+
+    def set_player_types(self, types, type_of_player) -> None:
+        """`types`: list of _abi.PlayerType (or dicts of its fields); `type_of_player[j]`: the type of player j (left
+        team first), the same in every match.  Call before reset(): effort starts at the type's effort_max."""
+        arr = (_abi.PlayerType * len(types))()
+        for k, t in enumerate(types):
+            d = t if isinstance(t, dict) else t.as_dict()
+            for name, v in d.items():
+                setattr(arr[k], name, float(v))
+        tof = np.ascontiguousarray(np.asarray(type_of_player, dtype=np.uint8))
+        if tof.shape != (self.num_players,):
+            raise ValueError(f"type_of_player needs {self.num_players} entries")
+        _abi.check(self.lib.s2d_set_player_types(self.handle, arr, len(types), tof.ctypes.data_as(C.POINTER(C.c_uint8))),
+                   self.handle)
+        self.player_types = [arr[k].as_dict() for k in range(len(types))]
+        self.type_of_player = tof.copy()
 
     def state_dict(self) -> dict:
         return {"state": self.state.clone(), "stats": self.stats_buf.clone(), "seed": self.seed_value,

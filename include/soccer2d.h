@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define S2D_ABI_VERSION 5
+#define S2D_ABI_VERSION 6
 
 /* error codes */
 #define S2D_OK 0
@@ -254,6 +254,39 @@ int s2d_wait_host(S2DHandle h, int slot); /* blocks the calling thread until the
 int s2d_stats(S2DHandle h, S2DStats* host_out, void* stream);   /* reduces the partials; synchronises */
 int s2d_stats_reset(S2DHandle h, void* stream);
 int s2d_export_env(S2DHandle h, int64_t local_env, S2DEnvSnapshot* host_out, void* stream); /* synchronises */
+
+/* Heterogeneous players (FULLGAME; proto PlayerType, idl/service.proto:1697-1732).  rcssserver draws 18 player types
+ * when it starts (HeteroPlayer: each type trades one quality against another) and every player is of one of them;
+ * type 0 is the default player = the ServerParam values.  The fields below are the ones the cycle reads; the others of
+ * the proto message either do not vary with rcssserver's default player.conf (player_size, player_speed_max,
+ * kick_power_rate delta ranges are [0, 0]; kick_power_rate is kept because the proto carries it) or belong to
+ * commands this library does not simulate (catch, tackle, foul). */
+#define S2D_MAX_PLAYER_TYPES 18
+typedef struct S2DPlayerType {
+  float player_decay;    /* :1701 */
+  float inertia_moment;  /* :1702 */
+  float dash_power_rate; /* :1703 */
+  float stamina_inc_max; /* :1700 */
+  float kickable_margin; /* :1705 */
+  float kick_rand;       /* :1706 */
+  float extra_stamina;   /* :1707 */
+  float effort_max;      /* :1708; also the effort a player starts an episode with */
+  float effort_min;      /* :1709 */
+  float kick_power_rate; /* :1710 */
+  float reserved[6];
+} S2DPlayerType;
+
+/* types[0] = the default player of `sp`; types[1..n-1] drawn like rcssserver's HeteroPlayer from (seed, type id) with
+ * the default player.conf ranges (SURVEY.md Appendix A.1 lineage: player_decay +-0.1 <-> inertia_moment x25,
+ * dash_power_rate -0.0012..+0.0008 <-> stamina_inc_max x-6000, kickable_margin +-0.1 <-> kick_rand x1,
+ * extra_stamina 0..50 <-> effort_max / effort_min x-0.004).  Host only, deterministic. */
+int s2d_generate_player_types(uint64_t seed, const S2DServerParam* sp, S2DPlayerType* out, int n);
+
+/* Gives the handle its player types: type_of_player[j] in [0, n) for player j (left team first, s2d_num_players
+ * entries), the same assignment in every match of the handle.  Call before the first s2d_reset (effort starts at the
+ * type's effort_max).  From then on the step / reset kernels read the per-player values; n = 0 returns the handle to
+ * homogeneous players.  FULLGAME only. */
+int s2d_set_player_types(S2DHandle h, const S2DPlayerType* types, int n, const uint8_t* type_of_player);
 
 /* Launch geometry actually used (for bench.py's gpu_launches / DESIGN.md): blocks, threads, kernels per step call */
 int s2d_launch_info(S2DHandle h, int* grid, int* block, int* kernels_per_step);

@@ -42,6 +42,10 @@ def lib(kind: str):
         L.s2do_set_state_fg.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
         L.s2do_set_ball_fg.argtypes = [C.c_void_p, C.c_int64] + [C.c_double] * 4 + [C.c_int] * 3
         L.s2do_set_player_fg.argtypes = [C.c_void_p, C.c_int64, C.c_int] + [C.c_double] * 5
+        L.s2do_generate_player_types.restype = C.c_int
+        L.s2do_generate_player_types.argtypes = [C.c_uint64, C.c_void_p, C.c_void_p, C.c_int]
+        L.s2do_set_player_types.restype = C.c_int
+        L.s2do_set_player_types.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.s2do_probe_sincos_deg.argtypes = [C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.s2do_probe_atan2_deg.restype = C.c_double
         L.s2do_probe_atan2_deg.argtypes = [C.c_double, C.c_double]
@@ -102,6 +106,11 @@ class OracleSim:
         self.L.s2do_step(self.h, _ptr(a), int(k), _ptr(self.obs), _ptr(self.reward), _ptr(self.done),
                          _ptr(self.result), _ptr(self.term_obs))
         return self.obs, self.reward, self.done, self.result
+
+    def set_player_types(self, types_array, n, type_of_player):
+        """types_array: ctypes array of the product's PlayerType struct (same layout as S2DPlayerType)"""
+        tof = np.ascontiguousarray(np.asarray(type_of_player, dtype=np.uint8))
+        assert self.L.s2do_set_player_types(self.h, C.byref(types_array), int(n), _ptr(tof)) == 0
 
     def stats(self, stats_struct):
         self.L.s2do_stats(self.h, C.byref(stats_struct))

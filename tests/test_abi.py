@@ -33,14 +33,14 @@ def test_abi_version_and_struct_sizes_match_the_header(tmp_path):
     assert lib.s2d_abi_version() == _abi.ABI_VERSION
     # ask the C compiler for the truth
     prog = tmp_path / "sizes.c"
-    prog.write_text('#include <stdio.h>\n#include "soccer2d.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %d\\n",'
+    prog.write_text('#include <stdio.h>\n#include "soccer2d.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %d\\n",'
                     "sizeof(S2DServerParam),sizeof(S2DConfig),sizeof(S2DBuffers),sizeof(S2DStats),"
-                    "sizeof(S2DPlayerSnapshot),sizeof(S2DEnvSnapshot),S2D_ABI_VERSION);return 0;}\n")
+                    "sizeof(S2DPlayerSnapshot),sizeof(S2DEnvSnapshot),sizeof(S2DPlayerType),S2D_ABI_VERSION);return 0;}\n")
     exe = tmp_path / "sizes"
     subprocess.run(["gcc", "-I", os.path.dirname(HEADER), str(prog), "-o", str(exe)], check=True)
     got = [int(x) for x in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
     want = [C.sizeof(t) for t in (_abi.ServerParam, _abi.Config, _abi.Buffers, _abi.Stats, _abi.PlayerSnapshot,
-                                  _abi.EnvSnapshot)] + [_abi.ABI_VERSION]
+                                  _abi.EnvSnapshot, _abi.PlayerType)] + [_abi.ABI_VERSION]
     assert got == want
 
 
@@ -110,3 +110,39 @@ def test_product_never_imports_the_oracle():
                 text = open(os.path.join(root, f)).read()
                 assert "oracle" not in text.lower() or f == "s2d_math.cuh", f  # s2d_math.cuh mentions the test oracle in a comment
                 assert "import oracle" not in text and "from oracle" not in text and "liboracle" not in text
+
+
+def test_player_types_are_rcssserver_hetero_draws_and_match_the_oracle():
+    """s2d_generate_player_types is host code: type 0 is the default player, the others trade decay against inertia,
+    dash power against stamina income, kickable margin against kick noise and extra stamina against effort, and can
+    sustain a speed within 0.1 below player_speed_max.  The oracle's float build draws the very same table."""
+    import oracle_lib as OL
+    lib = _abi.load()
+    sp = _abi.ServerParam()
+    assert lib.s2d_default_server_param(C.byref(sp)) == 0
+    for seed in (0, 7, 123456789):
+        mine = (_abi.PlayerType * 18)()
+        assert lib.s2d_generate_player_types(seed, C.byref(sp), mine, 18) == 0
+        theirs = (_abi.PlayerType * 18)()
+        assert OL.lib("f32").s2do_generate_player_types(seed, C.byref(sp), C.byref(theirs), 18) == 0
+        assert bytes(mine) == bytes(theirs)
+        truth = (_abi.PlayerType * 18)()
+        assert OL.lib("f64").s2do_generate_player_types(seed, C.byref(sp), C.byref(truth), 18) == 0
+        t0 = mine[0].as_dict()
+        assert t0 == pytest.approx({k: getattr(sp, k) for k in t0})
+        distinct = set()
+        for k in range(1, 18):
+            t, d = mine[k].as_dict(), truth[k].as_dict()
+            assert t == pytest.approx(d, rel=2e-6, abs=1e-7)
+            distinct.add(round(t["player_decay"], 6))
+            assert 0.3 <= t["player_decay"] <= 0.5 and 0.6 <= t["kickable_margin"] <= 0.8
+            assert 0.0048 - 1e-7 <= t["dash_power_rate"] <= 0.0068 + 1e-7 and 50.0 <= t["extra_stamina"] <= 100.0
+            assert t["inertia_moment"] == pytest.approx(5.0 + (t["player_decay"] - 0.4) * 25.0, abs=1e-4)
+            assert t["stamina_inc_max"] == pytest.approx(45.0 - (t["dash_power_rate"] - 0.006) * 6000.0, abs=1e-3)
+            assert t["kick_rand"] == pytest.approx(0.1 + (t["kickable_margin"] - 0.7), abs=1e-6)
+            assert t["effort_max"] == pytest.approx(1.0 - (t["extra_stamina"] - 50.0) * 0.004, abs=1e-5)
+            assert t["effort_min"] == pytest.approx(0.6 - (t["extra_stamina"] - 50.0) * 0.004, abs=1e-5)
+            rsm = t["effort_max"] * t["dash_power_rate"] * 100.0 / (1.0 - t["player_decay"])
+            assert 0.95 - 1e-6 < rsm < 1.05 + 1e-6
+        assert len(distinct) >= 15
+    assert lib.s2d_generate_player_types(0, C.byref(sp), mine, 19) == _abi.S2D_ERR_INVALID

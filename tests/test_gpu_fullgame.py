@@ -109,6 +109,51 @@ def test_fullgame_bit_exact_against_fp32_oracle(pps, k, default_sp):
     assert total_goals >= 0
 
 
+@pytest.mark.parametrize("noise", [False, True])
+def test_fullgame_heterogeneous_players_bit_exact(noise):
+    """rcssserver player types (PlayerType): every player but the goalkeepers plays with one of 17 drawn types; the
+    kernel reads the per-player values from the type table, the oracle from per-player copies of ServerParam."""
+    n, k = 67, 2
+    kw = dict(scenario="fullgame", device="cuda:0", seed=11, substeps=k, terminal_obs=True, half_time_cycles=100, noise=noise)
+    env = Soccer2DVecEnv(n, hetero_seed=3, **kw)
+    assert len(env.player_types) == 18 and env.type_of_player[0] == 0 and env.type_of_player[11] == 0
+    assert len(set(env.type_of_player.tolist())) > 5
+    types = (_abi.PlayerType * 18)()
+    for j, t in enumerate(env.player_types):
+        for name, v in t.items():
+            setattr(types[j], name, v)
+    sim = OL.OracleSim(env.cfg, "f32")
+    sim.set_player_types(types, 18, env.type_of_player)
+    plain = Soccer2DVecEnv(n, **kw)
+    assert np.array_equal(env.reset(), sim.reset())
+    plain.reset()
+    st = gpu_state_fg(env)
+    assert np.array_equal(st, sim.get_state_fg())
+    effort0 = st[:, :22 * 12].reshape(n, 22, 12)[0, :, 6]  # effort starts at the type's effort_max
+    assert np.allclose(effort0, [env.player_types[t]["effort_max"] for t in env.type_of_player])
+    rng = np.random.default_rng(1)
+    for t in range(150):
+        act = np.repeat(swarm_policy(sim.obs, 22, rng, random_frac=0.15), k, axis=1)
+        a = torch.from_numpy(act)
+        env.step_torch(a)
+        plain.step_torch(a)
+        sim.step(act.reshape(n, -1), k)
+        same_step(env, sim)
+    assert np.array_equal(gpu_state_fg(env), sim.get_state_fg())
+    assert not np.array_equal(env.obs.cpu().numpy(), plain.obs.cpu().numpy())  # the types do change the game
+    # back to homogeneous players: identical to a handle that never had types
+    env.lib.s2d_set_player_types(env.handle, None, 0, None)
+    env.reset()
+    plain.reset()
+    # (episode counters differ from a fresh handle only if resets differ: both were reset the same number of times)
+    for t in range(5):
+        act = np.repeat(swarm_policy(plain.obs.cpu().numpy(), 22, rng, random_frac=0.15), k, axis=1)
+        a = torch.from_numpy(act)
+        env.step_torch(a)
+        plain.step_torch(a)
+        assert np.array_equal(env.obs.cpu().numpy(), plain.obs.cpu().numpy())
+
+
 def test_fullgame_referee_and_collision_cases():
     """Hand-placed balls and players: kick-in, corner kick, goal kick, goals at both ends, dead-ball rules (the
     other side's kick is ignored, the awarded side's kick resumes play, drop ball after 100 cycles), two players

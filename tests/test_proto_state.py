@@ -9,7 +9,7 @@ import pytest
 
 import helpers as H  # noqa: F401  (sys.path)
 from soccer2d_b200 import _abi
-from soccer2d_b200.proto_state import state_dict, trainer_state_dict
+from soccer2d_b200.proto_state import player_type_dict, state_dict, trainer_state_dict
 
 REF = os.environ.get("S2D_REFERENCE", "/root/reference")
 pytestmark = pytest.mark.skipif(not os.path.exists(os.path.join(REF, "service_pb2.py")), reason="reference not mounted")
@@ -81,3 +81,29 @@ def test_state_dict_parses_into_the_reference_proto_and_feeds_its_hooks():
     assert (got["done"], got["result"]) == (d, O.RESULT_NAMES[res]) and got["reward"] == pytest.approx(rw, rel=1e-12)
     with pytest.raises(ValueError):
         state_dict(snap, unum=7, side=1)
+
+
+def test_player_types_parse_into_the_reference_proto():
+    """the drawn player types, exported with the proto's field names, fill the reference's own PlayerType message"""
+    import ctypes as C
+    import json
+    import subprocess
+
+    lib = _abi.load()
+    sp = _abi.ServerParam()
+    assert lib.s2d_default_server_param(C.byref(sp)) == 0
+    types = (_abi.PlayerType * 18)()
+    assert lib.s2d_generate_player_types(5, C.byref(sp), types, 18) == 0
+    payload = [player_type_dict(k, types[k].as_dict(), sp) for k in range(18)]
+    code = ("import json, sys\nsys.path.insert(0, sys.argv[1])\nfrom google.protobuf import json_format\n"
+            "import service_pb2 as pb2\nout = []\n"
+            "for d in json.load(sys.stdin):\n    m = json_format.ParseDict(d, pb2.PlayerType())\n"
+            "    out.append([m.id, m.player_decay, m.kickable_area, m.real_speed_max, m.cycles_to_reach_max_speed])\n"
+            "print(json.dumps(out))\n")
+    r = subprocess.run([sys.executable, "-c", code, REF], input=json.dumps(payload), capture_output=True, text=True,
+                       env={**os.environ, "PYTHONPATH": ""})
+    assert r.returncode == 0, r.stderr[-2000:]
+    got = json.loads(r.stdout.strip().splitlines()[-1])
+    assert [g[0] for g in got] == list(range(18))
+    assert got[0][1] == pytest.approx(0.4) and got[0][2] == pytest.approx(1.085) and got[0][3] == pytest.approx(1.0)
+    assert all(0.95 < g[3] <= 1.05 and 1 <= g[4] < 50 for g in got)

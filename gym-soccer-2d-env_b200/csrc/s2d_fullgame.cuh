@@ -263,6 +263,10 @@ __device__ __forceinline__ bool fg_commands(Episode& p, float4 a, float goto_dis
                                             int lane, bool active, bool left, bool may_kick, float& ax, float& ay,
                                             float& kax, float& kay) {
   const unsigned full = 0xffffffffu;
+  // the proxy's other body actions become a plain turn or kick first (rare: one vote when nobody uses them)
+  if (__any_sync(full, active && a.x >= static_cast<float>(S2D_CMD_TURN_TO_POINT))) {
+    if (active && a.x >= static_cast<float>(S2D_CMD_TURN_TO_POINT)) lower_body_action(p, a, sp);
+  }
   const int c = active ? static_cast<int>(a.x) : S2D_CMD_NONE;
   const bool is_goto = c == S2D_CMD_GOTO;
   const bool is_kick = c == S2D_CMD_KICK && may_kick;

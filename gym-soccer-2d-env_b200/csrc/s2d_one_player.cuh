@@ -191,11 +191,83 @@ __device__ __forceinline__ void lower_goto(const Episode& e, float tx, float ty,
   power = clampf(0.0f, need, max_power);
 }
 
+// d^n for 0 <= n <= 63 by binary powering (the order of the multiplications is part of the fp32 spec)
+__device__ __forceinline__ float pow_int(float d, int n) {
+  float r = 1.0f;
+#pragma unroll
+  for (int bit = 0; bit < 6; ++bit) {
+    r = ((n >> bit) & 1) ? r * d : r;
+    d = d * d;
+  }
+  return r;
+}
+// how far an object drifts in n cycles per unit of velocity: (1 - d^n) / (1 - d)
+__device__ __forceinline__ float inertia_factor(float decay, int n) { return (1.0f - pow_int(decay, n)) / (1.0f - decay); }
+
+// Body_TurnToPoint / Body_TurnToBall / Body_TurnToAngle / Body_KickOneStep / Body_StopBall (include/soccer2d.h,
+// S2D_CMD_TURN_TO_POINT ..): rewrites the command in place as the ONE turn or kick the proxy would send.
+// Out of line and fed by value (player, ball, constants accessor): taking the address of the episode for a cold call
+// would put it on the stack in the hot loop.
+struct Kinematics {
+  float px, py, vx, vy, body, bx, by, bvx, bvy;
+};
+template <class SP>
+__device__ __noinline__ float4 lower_body_action_cold(const Kinematics e, float4 a, const SP sp) {
+  const int c = static_cast<int>(a.x);
+  if (c == S2D_CMD_TURN_TO_POINT || c == S2D_CMD_TURN_TO_BALL || c == S2D_CMD_TURN_TO_ANGLE) {
+    float ang;
+    if (c == S2D_CMD_TURN_TO_ANGLE) {
+      ang = norm_deg(norm_deg(a.y) - e.body);
+    } else {
+      const float nf = rintf(c == S2D_CMD_TURN_TO_BALL ? a.y : a.w);
+      const int n = static_cast<int>(clampf(0.0f, nf, 63.0f));
+      float tx = a.y, ty = a.z;
+      if (c == S2D_CMD_TURN_TO_BALL) {
+        const float fb = inertia_factor(sp.ball_decay(), n);
+        tx = e.bx + e.bvx * fb;
+        ty = e.by + e.bvy * fb;
+      }
+      const float fp = inertia_factor(sp.player_decay(), n);
+      const float mx = e.px + e.vx * fp, my = e.py + e.vy * fp;
+      ang = norm_deg_360(atan2_deg(ty - my, tx - mx) - e.body);
+    }
+    const float speed = hypot2(e.vx, e.vy);
+    a = make_float4(static_cast<float>(S2D_CMD_TURN),
+                    clampf(sp.min_moment(), ang * (1.0f + sp.inertia_moment() * speed), sp.max_moment()), 0.0f, 0.0f);
+  } else if (c == S2D_CMD_KICK_ONE_STEP || c == S2D_CMD_STOP_BALL) {
+    const float dx = e.bx - e.px, dy = e.by - e.py;
+    const float dist = hypot2(dx, dy);
+    if (dist > sp.kickable_area()) return make_float4(static_cast<float>(S2D_CMD_NONE), 0.0f, 0.0f, 0.0f);
+    float wx = 0.0f, wy = 0.0f;  // the velocity the ball should leave with
+    if (c == S2D_CMD_KICK_ONE_STEP) {
+      const float first_speed = clampf(0.0f, a.w, sp.ball_speed_max());
+      float s, cs;
+      sincos_deg(atan2_deg(a.z - e.by, a.y - e.bx), s, cs);
+      wx = first_speed * cs;
+      wy = first_speed * s;
+    }
+    const float ax = wx - e.bvx, ay = wy - e.bvy;
+    const float acc = hypot2(ax, ay);
+    const float dir_diff = fabsf(norm_deg_360(atan2_deg(dy, dx) - e.body));
+    const float dist_ball = dist - sp.player_size() - sp.ball_size();
+    const float rate = sp.kick_power_rate() *
+                       (1.0f - 0.25f * dir_diff * static_cast<float>(1.0 / 180.0) - 0.25f * dist_ball / sp.kickable_margin());
+    a = make_float4(static_cast<float>(S2D_CMD_KICK), clampf(0.0f, acc / rate, sp.max_power()),
+                    norm_deg_360(atan2_deg(ay, ax) - e.body), 0.0f);
+  }
+  return a;
+}
+template <class SP>
+__device__ __forceinline__ void lower_body_action(const Episode& e, float4& a, const SP& sp) {
+  a = lower_body_action_cold(Kinematics{e.px, e.py, e.vx, e.vy, e.body, e.bx, e.by, e.bvx, e.bvy}, a, sp);
+}
+
 // S2D_ACT_COMMAND: {cmd, a, b, c} = proto PlayerAction dash / turn / kick / body_go_to_point (S2D_CMD_*).
 // Dashes come out with the direction already lowered by dash_direction.
 template <class SP>
 __device__ __forceinline__ void decode_command(const Episode& e, float4 a, float goto_dist_thr, const SP& sp, int& cmd,
                                                float& power, float& dir, float& rate) {
+  if (a.x >= static_cast<float>(S2D_CMD_TURN_TO_POINT)) lower_body_action(e, a, sp);
   const int c = static_cast<int>(a.x);
   cmd = S2D_CMD_NONE;
   power = 0.0f;

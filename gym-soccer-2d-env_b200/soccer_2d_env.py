@@ -17,7 +17,8 @@ Two ways to define a scenario:
     hooks are not called.  This is the fast path.
   * hooks: a subclass that overrides the reference's four hooks - `action_to_rpc_actions`, `state_to_observation`,
     `check_trainer_observation`, `trainer_reset_actions` - keeps working as it does on the reference: per step the
-    hook's PlayerAction (Dash / Turn / Kick / Body_GoToPoint / Body_HoldBall; `service_pb2` messages or
+    hook's PlayerAction (Dash / Turn / Kick / Body_GoToPoint / Body_TurnToPoint / Body_TurnToBall / Body_TurnToAngle /
+    Body_KickOneStep / Body_StopBall / Body_HoldBall; `service_pb2` messages or
     soccer2d_b200.pb2_lite ones) becomes one command for the GPU cycle, and the other hooks are fed proto-shaped
     State objects (real `service_pb2.State` when that module is importable, attribute views otherwise).  The physics
     still runs on the GPU; the Python hooks make it the slow, compatible path.
@@ -150,6 +151,18 @@ class Soccer2DEnv(Env):
                 warnings.warn(f"Body_GoToPoint.distance_threshold {thr} ignored: the handle was created with "
                               f"goto_dist_thr={self._vec.cfg.goto_dist_thr}", stacklevel=3)
             cmd[0, 0] = [_abi.CMD_GOTO, float(g.target_point.x), float(g.target_point.y), float(g.max_dash_power) or 100.0]
+        elif which == "body_turn_to_point":
+            t = action.body_turn_to_point
+            cmd[0, 0] = [_abi.CMD_TURN_TO_POINT, float(t.target_point.x), float(t.target_point.y), float(t.cycle) or 1.0]
+        elif which == "body_turn_to_ball":
+            cmd[0, 0] = [_abi.CMD_TURN_TO_BALL, float(action.body_turn_to_ball.cycle) or 1.0, 0.0, 0.0]
+        elif which == "body_turn_to_angle":
+            cmd[0, 0] = [_abi.CMD_TURN_TO_ANGLE, float(action.body_turn_to_angle.angle), 0.0, 0.0]
+        elif which == "body_kick_one_step":
+            k = action.body_kick_one_step  # (force_mode semantics: the kick is made even if first_speed cannot be reached)
+            cmd[0, 0] = [_abi.CMD_KICK_ONE_STEP, float(k.target_point.x), float(k.target_point.y), float(k.first_speed)]
+        elif which == "body_stop_ball":
+            cmd[0, 0] = [_abi.CMD_STOP_BALL, 0.0, 0.0, 0.0]
         elif which not in (None, "body_hold_ball"):
             warnings.warn(f"PlayerAction.{which} is not simulated; the player does nothing this cycle", stacklevel=3)
         return cmd

@@ -104,6 +104,21 @@ extern "C" {
 #define S2D_CMD_TURN 2 /* a = relative_direction              (service.proto:390-392) */
 #define S2D_CMD_KICK 3 /* a = power, b = relative_direction   (service.proto:394-397) */
 #define S2D_CMD_GOTO 4 /* a,b = target x,y, c = max_dash_power; distance_threshold = S2DConfig.goto_dist_thr (:684-688) */
+/* More of the proxy's body actions, each lowered to ONE turn or kick (librcsc's rules; n = cycles of inertia to look
+ * ahead, rounded and clamped to 0..63: an object with velocity v and decay d drifts v (1 - d^n) / (1 - d) in n cycles):
+ *   TURN_TO_POINT  face the point as seen from where the player will be after n cycles; the moment is the angle
+ *                  times (1 + inertia_moment * speed), clamped - what librcsc sends to cancel the server's inertia
+ *   TURN_TO_BALL   the same towards where the ball will be after n cycles
+ *   TURN_TO_ANGLE  the same towards an absolute body direction
+ *   KICK_ONE_STEP  if the ball is kickable: the kick that gives the ball `first_speed` (<= ball_speed_max) towards the
+ *                  target in one cycle - acceleration = wanted velocity - ball velocity, power = |acceleration| / kick
+ *                  rate (force mode: clamped to max_power), direction = its angle relative to the body; else nothing
+ *   STOP_BALL      KICK_ONE_STEP with a wanted velocity of zero */
+#define S2D_CMD_TURN_TO_POINT 5 /* a,b = target x,y, c = n           Body_TurnToPoint  (:777-780) */
+#define S2D_CMD_TURN_TO_BALL 6  /* a = n                              Body_TurnToBall   (:773-775) */
+#define S2D_CMD_TURN_TO_ANGLE 7 /* a = angle                          Body_TurnToAngle  (:769-771) */
+#define S2D_CMD_KICK_ONE_STEP 8 /* a,b = target x,y, c = first_speed  Body_KickOneStep  (:747-751, force_mode) */
+#define S2D_CMD_STOP_BALL 9     /*                                    Body_StopBall     (:753-754) */
 
 /* episode results: info['result'] of reach_ball_env.py:126,140,145,150 */
 #define S2D_RESULT_NONE 0

@@ -52,11 +52,13 @@ def random_actions(rng, mode, n, k=1, n_actions=16):
     return rng.uniform(-1.25, 1.25, size=(n, k, 4)).astype(np.float32)
 
 
-def random_commands(rng, n, k=1):
-    """[n, k, 4] float32 {cmd, a, b, c}: a mix of none / dash / turn / kick / go-to-point with out-of-range
-    arguments now and then (the clamps are part of the contract)."""
+def random_commands(rng, n, k=1, body_actions=True):
+    """[n, k, 4] float32 {cmd, a, b, c}: a mix of none / dash / turn / kick / go-to-point and (body_actions) the
+    proxy's turn-to-point / -ball / -angle, kick-one-step and stop-ball, with out-of-range arguments now and then
+    (the clamps are part of the contract)."""
     a = np.zeros((n, k, 4), np.float32)
-    cmd = rng.choice([0, 1, 1, 1, 2, 3, 3, 4, 4], size=(n, k))
+    menu = [0, 1, 1, 1, 2, 3, 3, 4, 4] + ([5, 6, 7, 8, 8, 9, 11] if body_actions else [])
+    cmd = rng.choice(menu, size=(n, k))
     a[..., 0] = cmd
     dash, turn, kick, goto = cmd == 1, cmd == 2, cmd == 3, cmd == 4
     a[..., 1] = np.where(dash | kick, rng.uniform(-30, 130, (n, k)), a[..., 1])
@@ -65,6 +67,13 @@ def random_commands(rng, n, k=1):
     a[..., 1] = np.where(goto, rng.uniform(-55, 55, (n, k)), a[..., 1])
     a[..., 2] = np.where(goto, rng.uniform(-36, 36, (n, k)), a[..., 2])
     a[..., 3] = np.where(goto, rng.uniform(20, 120, (n, k)), a[..., 3])
+    to_point, to_ball, to_angle, one_step = cmd == 5, cmd == 6, cmd == 7, cmd == 8
+    a[..., 1] = np.where(to_point | one_step, rng.uniform(-55, 55, (n, k)), a[..., 1])
+    a[..., 2] = np.where(to_point | one_step, rng.uniform(-36, 36, (n, k)), a[..., 2])
+    a[..., 3] = np.where(to_point, rng.integers(-2, 70, (n, k)), a[..., 3])
+    a[..., 3] = np.where(one_step, rng.uniform(-0.5, 3.5, (n, k)), a[..., 3])
+    a[..., 1] = np.where(to_ball, rng.integers(0, 12, (n, k)), a[..., 1])
+    a[..., 1] = np.where(to_angle, rng.uniform(-400, 400, (n, k)), a[..., 1])
     return a
 
 

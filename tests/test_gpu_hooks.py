@@ -109,4 +109,24 @@ def test_hook_mode_lowers_every_supported_action():
     env.step(pb2.PlayerAction(kick=pb2.Kick(power=100, relative_direction=0.0)))
     snap = env._vec.export_env(0)
     assert snap.players[0].kicked == 1 and np.hypot(snap.ball_vx, snap.ball_vy) > 1.0
+    # the proxy's other body actions: stop the ball, pass it on at 1.2 m per cycle, turn towards it, turn to an angle
+    p = snap.players[0]
+    env._apply_trainer_actions(pb2.TrainerAction(do_move_ball=pb2.DoMoveBall(position=pb2.RpcVector2D(x=p.x + 0.4, y=p.y + 0.2), velocity=pb2.RpcVector2D(x=0.3, y=-0.2))))
+    env._apply_trainer_actions(pb2.TrainerAction(do_move_player=pb2.DoMovePlayer(our_side=True, uniform_number=1, position=pb2.RpcVector2D(x=p.x, y=p.y), body_direction=10.0)))
+    env.step(pb2.PlayerAction(body_stop_ball=pb2.Body_StopBall()))
+    snap = env._vec.export_env(0)
+    assert np.hypot(snap.ball_vx, snap.ball_vy) < 1e-4
+    env.step(pb2.PlayerAction(body_kick_one_step=pb2.Body_KickOneStep(target_point=pb2.RpcVector2D(x=snap.ball_x + 30.0, y=snap.ball_y), first_speed=1.2, force_mode=True)))
+    snap = env._vec.export_env(0)
+    assert (snap.ball_vx, snap.ball_vy) == pytest.approx((1.2 * 0.94, 0.0), abs=1e-4)
+    env.step(pb2.PlayerAction(body_turn_to_ball=pb2.Body_TurnToBall(cycle=1)))
+    snap = env._vec.export_env(0)
+    p = snap.players[0]
+    # (cycle = 1: faces where the ball is after this cycle, from where the player is after this cycle = now)
+    assert p.body_direction == pytest.approx(np.degrees(np.arctan2(snap.ball_y - p.y, snap.ball_x - p.x)), abs=0.05)
+    env.step(pb2.PlayerAction(body_turn_to_angle=pb2.Body_TurnToAngle(angle=-120.0)))
+    assert env._vec.export_env(0).players[0].body_direction == pytest.approx(-120.0, abs=1e-3)
+    env.step(pb2.PlayerAction(body_turn_to_point=pb2.Body_TurnToPoint(target_point=pb2.RpcVector2D(x=0.0, y=0.0), cycle=1)))
+    p = env._vec.export_env(0).players[0]
+    assert p.body_direction == pytest.approx(np.degrees(np.arctan2(0.0 - p.y, 0.0 - p.x)), abs=0.05)
     env.close()

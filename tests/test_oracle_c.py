@@ -178,7 +178,7 @@ def test_shoot_c_f64_equals_python_oracle(mode):
             act = rng.integers(0, 24, size=(n, 1)).astype(np.uint8)
         else:
             act = H.chase_and_shoot(sim.obs, rng, kick_prob=0.9)
-            act = np.where(rng.uniform(size=(n, 1, 1)) < 0.1, H.random_commands(rng, n), act).astype(np.float32)
+            act = np.where(rng.uniform(size=(n, 1, 1)) < 0.1, H.random_commands(rng, n, body_actions=False), act).astype(np.float32)
         obs, rew, done, res = sim.step(act)
         for i, o in enumerate(py):
             a = int(act[i, 0]) if mode == "discrete" else act[i, 0]
@@ -190,3 +190,64 @@ def test_shoot_c_f64_equals_python_oracle(mode):
             kicks += o.player.kicked
     if mode == "command":
         assert {0, 1} <= results and kicks > 20
+
+
+def _place(sim, i, px, py, vx, vy, body, bx, by, bvx, bvy):
+    st = sim.get_state(i)
+    st[0:5] = [px, py, vx, vy, body]
+    st[9:13] = [bx, by, bvx, bvy]
+    sim.set_state(i, st)
+
+
+def test_body_actions_do_what_librcsc_intends():
+    """S2D_CMD_TURN_TO_POINT / _BALL / _ANGLE, KICK_ONE_STEP, STOP_BALL (include/soccer2d.h): properties of the
+    lowered turn / kick, in the double-precision build."""
+    cfg = H.make_config(8, "command", scenario=_abi.SCENARIO_SHOOT, auto_reset=0, max_steps=10 ** 6)
+    sim = OL.OracleSim(cfg, "f64")
+    sim.reset()
+    decay, bdecay = 0.4, 0.94
+    #          px,  py,  vx,   vy,  body,   bx,   by,  bvx,  bvy
+    _place(sim, 0, 0.0, 0.0, 0.0, 0.0, 30.0, 20.0, 20.0, 0.0, 0.0)    # standing: turn to a point
+    _place(sim, 1, 0.0, 0.0, 0.1, 0.05, 30.0, 20.0, 20.0, 0.0, 0.0)   # moving: turn to a point, n = 1
+    _place(sim, 2, 0.0, 0.0, 0.3, -0.1, 0.0, 10.0, 5.0, 1.0, 0.5)     # moving: turn to the ball, n = 3
+    _place(sim, 3, 1.0, 1.0, 0.0, 0.0, 170.0, 30.0, 0.0, 0.0, 0.0)    # turn to an absolute angle across the +-180 seam
+    _place(sim, 4, 0.0, 0.0, 0.0, 0.0, 20.0, 0.5, 0.3, 0.4, -0.2)     # kick one step
+    _place(sim, 5, 0.0, 0.0, 0.0, 0.0, -45.0, 0.6, -0.2, 1.0, 0.8)    # stop the ball
+    _place(sim, 6, 0.0, 0.0, 0.0, 0.0, 0.0, 3.0, 0.0, 0.5, 0.0)       # ball out of reach: nothing happens
+    _place(sim, 7, 0.0, 0.0, 0.0, 0.0, 0.0, 0.5, 0.0, -2.5, 0.0)      # wanted change needs more than max_power
+    act = np.zeros((8, 1, 4), np.float32)
+    act[0, 0] = [5, -10.0, 25.0, 1]
+    act[1, 0] = [5, -10.0, 25.0, 1]
+    act[2, 0] = [6, 3, 0, 0]
+    act[3, 0] = [7, -175.0, 0, 0]
+    act[4, 0] = [8, 30.0, 10.0, 1.5]
+    act[5, 0] = [9, 0, 0, 0]
+    act[6, 0] = [8, 30.0, 10.0, 1.5]
+    act[7, 0] = [8, 30.0, 0.0, 3.0]
+    before = sim.get_state()
+    sim.step(act)
+    st = sim.get_state()
+    deg = lambda y, x: np.degrees(np.arctan2(y, x))  # noqa: E731
+    norm = lambda d: (d + 180.0) % 360.0 - 180.0     # noqa: E731
+    # 0: a standing player faces the point after the turn
+    assert st[0, 4] == pytest.approx(deg(25.0, -10.0), abs=1e-3)
+    # 1: n = 1 looks from where the player is after this cycle; inertia is compensated exactly
+    assert st[1, 4] == pytest.approx(deg(25.0 - st[1, 1], -10.0 - st[1, 0]), abs=1e-3)
+    assert (st[1, 0], st[1, 1]) == pytest.approx((0.1, 0.05))
+    # 2: the ball as it will be 3 cycles on, seen from where the player will be 3 cycles on
+    f = lambda d, n: (1 - d ** n) / (1 - d)  # noqa: E731
+    tx, ty = 10.0 + 1.0 * f(bdecay, 3), 5.0 + 0.5 * f(bdecay, 3)
+    mx, my = 0.3 * f(decay, 3), -0.1 * f(decay, 3)
+    assert st[2, 4] == pytest.approx(deg(ty - my, tx - mx), abs=1e-3)
+    # 3: 170 -> -175 is a turn of +15 through the seam
+    assert st[3, 4] == pytest.approx(-175.0, abs=1e-3)
+    # 4: the ball leaves with first_speed towards the target (one decay later)
+    want = 1.5 * np.array([30.0 - 0.5, 10.0 - 0.3]) / np.hypot(30.0 - 0.5, 10.0 - 0.3)
+    assert st[4, 11:13] == pytest.approx(want * bdecay, abs=1e-4)
+    assert st[4, 9:11] == pytest.approx(np.array([0.5, 0.3]) + want, abs=1e-4)
+    # 5: the ball is stopped
+    assert st[5, 11:13] == pytest.approx([0.0, 0.0], abs=1e-5)
+    # 6: not kickable: the ball just rolls on
+    assert st[6, 11] == pytest.approx(0.5 * bdecay) and int(st[6, 19]) & 4 == 0
+    # 7: force mode: full power towards the wanted change, short of the wanted speed
+    assert int(st[7, 19]) & 4 and -2.5 * bdecay < st[7, 11] < 3.0 * bdecay and st[7, 11] > before[7, 11]

@@ -254,6 +254,24 @@ __device__ __noinline__ float4 lower_body_action_cold(const Kinematics e, float4
                        (1.0f - 0.25f * dir_diff * static_cast<float>(1.0 / 180.0) - 0.25f * dist_ball / sp.kickable_margin());
     a = make_float4(static_cast<float>(S2D_CMD_KICK), clampf(0.0f, acc / rate, sp.max_power()),
                     norm_deg_360(atan2_deg(ay, ax) - e.body), 0.0f);
+  } else if (c == S2D_CMD_INTERCEPT) {
+    // drift sums 1 + d + d^2 + ...: where ball and player are after t cycles if nobody touches them
+    const float reach0 = 0.8f * sp.kickable_area();
+    float fb = 0.0f, fp = 0.0f, pwb = 1.0f, pwp = 1.0f, tx = e.bx, ty = e.by;
+#pragma unroll 1
+    for (int t = 1; t <= 30; ++t) {
+      fb += pwb;
+      fp += pwp;
+      pwb *= sp.ball_decay();
+      pwp *= sp.player_decay();
+      tx = e.bx + e.bvx * fb;
+      ty = e.by + e.bvy * fb;
+      const float mx = e.px + e.vx * fp, my = e.py + e.vy * fp;
+      const float ddx = tx - mx, ddy = ty - my;
+      const float reach = reach0 + static_cast<float>(t - 1) * sp.player_speed_max();
+      if (ddx * ddx + ddy * ddy <= reach * reach) break;
+    }
+    a = make_float4(static_cast<float>(S2D_CMD_GOTO), tx, ty, 100.0f);
   }
   return a;
 }

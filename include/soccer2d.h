@@ -113,12 +113,17 @@ extern "C" {
  *   KICK_ONE_STEP  if the ball is kickable: the kick that gives the ball `first_speed` (<= ball_speed_max) towards the
  *                  target in one cycle - acceleration = wanted velocity - ball velocity, power = |acceleration| / kick
  *                  rate (force mode: clamped to max_power), direction = its angle relative to the body; else nothing
- *   STOP_BALL      KICK_ONE_STEP with a wanted velocity of zero */
+ *   STOP_BALL      KICK_ONE_STEP with a wanted velocity of zero
+ *   INTERCEPT      go to where the ball can first be met (simplified librcsc intercept table): for t = 1..30 cycles the
+ *                  ball's drift position b_t and the player's own drift position m_t are compared; the first t with
+ *                  |b_t - m_t| <= 0.8 kickable_area + (t - 1) player_speed_max (one cycle is kept for turning) gives the
+ *                  target b_t, else b_30; then Body_GoToPoint(target, max_dash_power 100) decides turn or dash */
 #define S2D_CMD_TURN_TO_POINT 5 /* a,b = target x,y, c = n           Body_TurnToPoint  (:777-780) */
 #define S2D_CMD_TURN_TO_BALL 6  /* a = n                              Body_TurnToBall   (:773-775) */
 #define S2D_CMD_TURN_TO_ANGLE 7 /* a = angle                          Body_TurnToAngle  (:769-771) */
 #define S2D_CMD_KICK_ONE_STEP 8 /* a,b = target x,y, c = first_speed  Body_KickOneStep  (:747-751, force_mode) */
 #define S2D_CMD_STOP_BALL 9     /*                                    Body_StopBall     (:753-754) */
+#define S2D_CMD_INTERCEPT 10    /*                                    Body_Intercept    (:742-745; save_recovery and face_point ignored) */
 
 /* episode results: info['result'] of reach_ball_env.py:126,140,145,150 */
 #define S2D_RESULT_NONE 0

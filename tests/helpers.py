@@ -54,10 +54,10 @@ def random_actions(rng, mode, n, k=1, n_actions=16):
 
 def random_commands(rng, n, k=1, body_actions=True):
     """[n, k, 4] float32 {cmd, a, b, c}: a mix of none / dash / turn / kick / go-to-point and (body_actions) the
-    proxy's turn-to-point / -ball / -angle, kick-one-step and stop-ball, with out-of-range arguments now and then
+    proxy's turn-to-point / -ball / -angle, kick-one-step, stop-ball and intercept, with out-of-range arguments now and then
     (the clamps are part of the contract)."""
     a = np.zeros((n, k, 4), np.float32)
-    menu = [0, 1, 1, 1, 2, 3, 3, 4, 4] + ([5, 6, 7, 8, 8, 9, 11] if body_actions else [])
+    menu = [0, 1, 1, 1, 2, 3, 3, 4, 4] + ([5, 6, 7, 8, 8, 9, 10, 10, 12] if body_actions else [])
     cmd = rng.choice(menu, size=(n, k))
     a[..., 0] = cmd
     dash, turn, kick, goto = cmd == 1, cmd == 2, cmd == 3, cmd == 4

@@ -129,4 +129,16 @@ def test_hook_mode_lowers_every_supported_action():
     env.step(pb2.PlayerAction(body_turn_to_point=pb2.Body_TurnToPoint(target_point=pb2.RpcVector2D(x=0.0, y=0.0), cycle=1)))
     p = env._vec.export_env(0).players[0]
     assert p.body_direction == pytest.approx(np.degrees(np.arctan2(0.0 - p.y, 0.0 - p.x)), abs=0.05)
+    # intercept: the ball rolls away; the player gets it back under control within a few cycles
+    snap = env._vec.export_env(0)
+    p = snap.players[0]
+    env._apply_trainer_actions(pb2.TrainerAction(do_move_ball=pb2.DoMoveBall(position=pb2.RpcVector2D(x=p.x + 3.0, y=p.y + 2.0), velocity=pb2.RpcVector2D(x=0.8, y=0.3))))
+    for _ in range(25):
+        env.step(pb2.PlayerAction(body_intercept=pb2.Body_Intercept(save_recovery=False)))
+        snap = env._vec.export_env(0)
+        p = snap.players[0]
+        if np.hypot(snap.ball_x - p.x, snap.ball_y - p.y) <= 1.085:
+            break
+    else:
+        raise AssertionError("the ball was never intercepted")
     env.close()

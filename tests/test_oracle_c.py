@@ -251,3 +251,25 @@ def test_body_actions_do_what_librcsc_intends():
     assert st[6, 11] == pytest.approx(0.5 * bdecay) and int(st[6, 19]) & 4 == 0
     # 7: force mode: full power towards the wanted change, short of the wanted speed
     assert int(st[7, 19]) & 4 and -2.5 * bdecay < st[7, 11] < 3.0 * bdecay and st[7, 11] > before[7, 11]
+
+
+def test_intercept_meets_a_rolling_ball_sooner_than_chasing_it():
+    """S2D_CMD_INTERCEPT aims at where the ball can first be met; S2D_CMD_GOTO at the ball's present position runs
+    after it.  Same start, ball rolling across the player's front."""
+    cfg = H.make_config(2, "command", scenario=_abi.SCENARIO_SHOOT, auto_reset=0, max_steps=10 ** 6, goto_dist_thr=0.5)
+    sim = OL.OracleSim(cfg, "f64")
+    sim.reset()
+    for i in range(2):
+        _place(sim, i, -10.0, 0.0, 0.0, 0.0, 0.0, 0.0, -12.0, 0.0, 2.2)
+    reached = [None, None]
+    for t in range(60):
+        st = sim.get_state()
+        act = np.zeros((2, 1, 4), np.float32)
+        act[0, 0] = [10, 0, 0, 0]
+        act[1, 0] = [4, st[1, 9], st[1, 10], 100.0]
+        sim.step(act)
+        st = sim.get_state()
+        for i in range(2):
+            if reached[i] is None and np.hypot(st[i, 9] - st[i, 0], st[i, 10] - st[i, 1]) <= 1.085:
+                reached[i] = t
+    assert reached[0] is not None and (reached[1] is None or reached[0] < reached[1]), reached

@@ -18,6 +18,7 @@ namespace s2d {
 constexpr int kFgObsDim = 120;        // 4 ball + 22 x 5 player + 6 referee values (rows are 16-byte multiples)
 constexpr int kFgDropBallTime = 100;  // cycles a dead ball waits for the awarded side before play resumes
 constexpr int kFgMaxPlayers = 22;
+constexpr float kFgFreeKickDist = 9.15f;  // the distance opponents keep from a dead ball
 
 // HBM layout of N matches with np players each (plane-major; every plane starts 16-byte aligned):
 //   PA float4 [N][np] {x, y, vx, vy}            PB float4 [N][np] {body, stamina, effort, recovery}
@@ -81,13 +82,13 @@ __device__ __forceinline__ void fg_place_player(Episode& p, const KernelParams& 
 // Returns this lane's bits: 1 = player collided, 2 = player touched the ball; ball_collided is warp-uniform.
 //
 // `sep` (kept in the match state) is a LOWER BOUND on the smallest distance between two players.  Every cycle it
-// shrinks by twice the largest distance a player moved in that cycle (at most `shrink`, twice what the server
-// allows); only when it drops below the collision distance is the exact minimum recomputed (the O(n^2 / 32) pair loop) - in open play every few cycles instead of
-// every cycle.  The ball is tested against every player every cycle.  If neither test finds an overlap, the ordered
+// shrinks by twice the largest distance a player moved in that cycle (`moved2` = this lane's squared step, the
+// referee's placements included); only when it drops below the collision distance is the exact minimum recomputed
+// (the O(n^2 / 32) pair loop) - in open play every few cycles instead of every cycle.  The ball is tested against every player every cycle.  If neither test finds an overlap, the ordered
 // relaxation rounds - which would change nothing - are skipped, so the results do not depend on this shortcut.
 template <class SP>
 __device__ __forceinline__ int fg_collisions(Episode& p, bool active, int lane, int np, bool ball_fixed, const SP& sp,
-                                             bool& ball_collided, float& sep, float shrink, float moved2) {
+                                             bool& ball_collided, float& sep, float moved2) {
   const unsigned full = 0xffffffffu;
   bool collided = false, ballhit = false, ball_any = false;
   const float r = sp.player_size() + sp.ball_size();
@@ -101,12 +102,12 @@ __device__ __forceinline__ int fg_collisions(Episode& p, bool active, int lane, 
     ball_overlap = dx * dx + dy * dy < r * r;
   }
   {
-    // the farthest any player moved this cycle: sqrt of the largest squared step over the lanes, rounded up; never
-    // more than the server's limit `shrink` / 2 that was used before the speeds were looked at
+    // the farthest any player moved this cycle (its own move, or the referee placing it 9.15 m from a dead ball):
+    // sqrt of the largest squared step over the lanes, rounded up
     const float v2max = __uint_as_float(__reduce_max_sync(full, __float_as_uint(active ? moved2 : 0.0f)));
     float moved;
     asm("sqrt.approx.f32 %0, %1;" : "=f"(moved) : "f"(v2max));
-    sep -= fminf(shrink, 2.002f * moved + 1.0e-6f);
+    sep -= 2.002f * moved + 1.0e-6f;
   }
   bool pairs_close = false;
   if (sep < r2) {  // uniform: the bound has run out, measure the true minimum (lane i looks at (i + d) mod np, d <= np/2)
@@ -420,11 +421,30 @@ __device__ __forceinline__ bool fg_cycle(Episode& p, Match& m, const KernelParam
     p.bvy = 0.0f;
   }
 
+  // ---- dead ball: the side that does not take the kick keeps 9.15 m away (uniform branch; rare) ----
+  if (dead && m.mode != S2D_PM_TIME_OVER) {
+    const float cx = p.px - p.bx, cy = p.py - p.by;
+    const float c2 = cx * cx + cy * cy;
+    const bool inside = active && my_side != m.side && c2 < kFgFreeKickDist * kFgFreeKickDist;
+    if (__any_sync(full, inside)) {
+      if (inside) {
+        const float c = sqrtf(c2);
+        float ux = left ? -1.0f : 1.0f, uy = 0.0f;
+        if (c >= 1.0e-6f) {
+          ux = cx / c;
+          uy = cy / c;
+        }
+        p.px = p.bx + ux * kFgFreeKickDist;
+        p.py = p.by + uy * kFgFreeKickDist;
+        p.vx = 0.0f;
+        p.vy = 0.0f;
+      }
+    }
+  }
+
   // ---- collisions ----
-  // the farthest a player can move in a cycle: speed_max (the clamp) plus, with noise, up to rand * sqrt(2) of it
-  const float vmax = sp.player_speed_max() * (SP::kNoise ? 1.0f + 1.5f * sp.player_rand() : 1.0f) * 1.001f;
   const float stepx = p.px - ppx, stepy = p.py - ppy;
-  const int hit = fg_collisions(p, active, lane, np, dead, sp, ball_collided, m.sep, 2.0f * vmax, stepx * stepx + stepy * stepy);
+  const int hit = fg_collisions(p, active, lane, np, dead, sp, ball_collided, m.sep, stepx * stepx + stepy * stepy);
   collided_mask = __ballot_sync(full, (hit & 1) != 0);
   {
     const unsigned touch = __ballot_sync(full, (hit & 2) != 0);

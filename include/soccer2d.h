@@ -85,7 +85,11 @@ extern "C" {
  *     dead ball  (KickOff, KickIn, CornerKick, GoalKick): the ball rests and takes no part in collisions; only the awarded
  *                side's kicks count, the first one resumes PlayOn; after 100 cycles without it play resumes anyway.
  *     last touch = side of the last kicker(s) / of the player(s) the ball collided with (unchanged if both sides did).
- *     Not modelled: 9.15 m clearance, AfterGoal pause, offside, fouls, tackle, catch, heterogeneous player types.
+ *     clearance  while the ball is dead, after the players have moved, every player of the side that does NOT take the
+ *                kick and stands closer than 9.15 m to the ball is placed on that circle (on the line ball -> player; a
+ *                player exactly on the ball goes towards its own goal) with velocity zero (Referee::clearPlayersFromBall).
+ *     Not modelled: AfterGoal pause, offside, fouls, tackle, catch; players are not confined to their half at kick-off.
+ *     Heterogeneous player types: s2d_set_player_types.
  *   Reward (left team's view) per cycle: 10 * (goals by left - goals by right) + 0.01 * (ball x after physics - before).
  *   Observation: 120 floats = ball {x/52.5, y/34, vx/3, vy/3}, then per player {x/52.5, y/34, vx, vy, body/180}
  *   (absent players zero), then [114] play mode, [115] side awarded, [116] left score, [117] right score,

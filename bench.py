@@ -300,8 +300,8 @@ def run_b200(args, rank, local_rank, world):
     del env1, pool1
 
     # ---- closed-loop policy rollout (configs[4]): obs -> 64-64 MLP -> argmax -> step, all on the device ----
-    from soccer2d_b200.rollout import QNetwork, measure_rollout
-    rollout = {}
+    from soccer2d_b200.rollout import QNetwork, measure_fused_rollout, measure_rollout
+    rollout, rollout_fused = {}, {}
     for nr in (1 << 16, 1 << 20):
         envr = Soccer2DVecEnv(nr, device=dev, seed=0, substeps=1, env_id_offset=rank * nr, **SCENARIO_KW)
         envr.reset_torch()
@@ -312,6 +312,8 @@ def run_b200(args, rank, local_rank, world):
         except Exception as exc:  # noqa: BLE001 - graph capture refused: time the eager loop
             rollout[str(nr)] = measure_rollout(envr, qnet, steps=max(10, min(args.steps, 50)), use_graph=False)
             rollout["note"] = f"CUDA graph capture failed ({type(exc).__name__}); eager launches"
+        # the same loop with the Q-network inside the step kernel: 16 cycles per launch (s2d_rollout_mlp)
+        rollout_fused[str(nr)] = measure_fused_rollout(envr, qnet, launches=max(5, min(args.steps, 20)), k=SUBSTEPS)
         envr.close()
         del envr
     clocks = sampler.summary()
@@ -385,7 +387,12 @@ def run_b200(args, rank, local_rank, world):
         "rollout_dqn": {"unit": UNIT + " per GPU", "policy": "64-64 ReLU MLP (SB3 DQN MlpPolicy shape), greedy, K=1, zero-copy obs/action "
                         "tensors, loop body replayed as a CUDA graph (torch fp32 matmuls for the policy, not part of the "
                         "step path)",
-                        "envs_to_value": rollout},
+                        "envs_to_value": rollout,
+                        "fused_policy_kernel": {
+                            "envs_to_value": rollout_fused, "substeps": SUBSTEPS,
+                            "path": "Soccer2DVecEnv.rollout_mlp -> s2d_rollout_mlp: observe -> Q-network (mma.sync m16n8k8, TF32 "
+                                    "operands, fp32 accumulate, weights in shared memory) -> argmax -> step, K cycles per "
+                                    "launch; observation and action never leave the SM"}},
         "single_env_gym_api": single,
         "clocks": clocks,
         "episode_stats": stats,

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "s2d_fullgame.cuh"
+#include "s2d_rollout.cuh"
 
 using namespace s2d;
 
@@ -650,6 +651,29 @@ int s2d_set_player_types(S2DHandle h, const S2DPlayerType* types, int n, const u
     memcpy(kp->type_of, type_of, sizeof(type_of));
   }
   h->hetero = true;
+  return S2D_OK;
+}
+
+int s2d_rollout_mlp(S2DHandle h, const S2DMlpPolicy* policy, int k_substeps, float epsilon, void* actions_out,
+                    void* q_out, void* stream) {
+  if (!h) return S2D_ERR_INVALID;
+  if (!h->bound) return fail(h, S2D_ERR_UNBOUND, "s2d_bind has not been called");
+  if (h->cfg.scenario != S2D_SCENARIO_REACHBALL || h->cfg.action_mode != S2D_ACT_DISCRETE || h->cfg.action_space_size > kMlpActions)
+    return fail(h, S2D_ERR_INVALID, "s2d_rollout_mlp: REACHBALL with Discrete(n <= %d) actions only", kMlpActions);
+  if (!policy || !policy->w1 || !policy->b1 || !policy->w2 || !policy->b2 || !policy->w3 || !policy->b3 || policy->hidden != kMlpHidden)
+    return fail(h, S2D_ERR_INVALID, "s2d_rollout_mlp: six weight pointers and hidden = %d are required", kMlpHidden);
+  if (k_substeps < 1 || k_substeps > kMaxSubsteps) return fail(h, S2D_ERR_INVALID, "k_substeps must be in 1..%d", kMaxSubsteps);
+  if (!(epsilon >= 0.0f && epsilon <= 1.0f)) return fail(h, S2D_ERR_INVALID, "epsilon must be in [0, 1]");
+  DeviceGuard guard(h->cfg.device);
+  const MlpWeights w{policy->w1, policy->b1, policy->w2, policy->b2, policy->w3, policy->b3, kObsDim, h->cfg.action_space_size};
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  uint8_t* ao = static_cast<uint8_t*>(actions_out);
+  float* qo = static_cast<float*>(q_out);
+  if (h->cfg.noise) rollout_mlp_kernel<kVarNoisy><<<h->grid, kBlock, 0, s>>>(h->kp, k_substeps, w, epsilon, ao, qo);
+  else if (h->default_sp) rollout_mlp_kernel<kVarDefault><<<h->grid, kBlock, 0, s>>>(h->kp, k_substeps, w, epsilon, ao, qo);
+  else rollout_mlp_kernel<kVarRuntime><<<h->grid, kBlock, 0, s>>>(h->kp, k_substeps, w, epsilon, ao, qo);
+  S2D_CUDA(h, cudaGetLastError());
+  h->env_steps += static_cast<uint64_t>(h->cfg.num_envs) * static_cast<uint64_t>(k_substeps);
   return S2D_OK;
 }
 

@@ -1,0 +1,224 @@
+// s2d_rollout.cuh - closed-loop rollout: the policy runs INSIDE the K loop of the step kernel.
+//
+// The caller of the path in the reference is SB3's DQN (dqn_stable_baselines3.py:33-55: MlpPolicy = obs -> 64 -> 64 ->
+// n_actions with ReLU; `model.predict(obs)` then `env.step(action)`).  With the policy in a separate (torch) launch a
+// closed loop is K = 1 by construction: obs and action go through HBM every cycle and the three small GEMMs run as
+// fp32 SIMT kernels.  Here a warp evaluates the Q-network for its 32 episodes with warp-level tensor-core MMAs
+// (mma.sync m16n8k8, TF32 operands, fp32 accumulate) from observations that never leave the SM, takes the greedy
+// (or epsilon-greedy) action and advances the episode, K times per launch:
+//
+//   observation (registers) -> shared memory, row = episode           [32 x 16], features 10..15 zero
+//   layer 1  [16 x 16] . [16 x 64]   per half-warp tile of 16 episodes: 2 k-steps x 8 n-tiles
+//   layer 2  [16 x 64] . [64 x 64]   8 x 8; the accumulator fragment of layer 1 IS the A fragment of layer 2 when the
+//   layer 3  [16 x 64] . [64 x 16]   8 x 2  weight rows are paired (2t, 2t+1) instead of (t, t+4): no shuffles
+//   argmax over 16 actions inside each quad of lanes, action -> shared memory -> the lane that owns the episode
+//
+// Weights arrive in torch nn.Linear layout (device pointers) and are re-laid in shared memory once per block, already
+// rounded to TF32, padded so that the 64-bit fragment loads are bank-conflict free.  TF32 carries 10 mantissa bits:
+// Q-values agree with an fp32 evaluation to ~1e-3 relative, so the greedy action can differ on near-ties (tests).
+#pragma once
+#include "s2d_scenarios.cuh"
+
+namespace s2d {
+
+constexpr int kMlpHidden = 64;
+constexpr int kMlpActions = 16;  // n-tiles of 8: up to 16 actions
+constexpr int kMlpPad = 4;       // row padding (in float2 entries) that spreads the four t-rows over the banks
+
+struct MlpWeights {  // device pointers, torch layout: weight [out][in] row-major, bias [out]
+  const float *w1, *b1, *w2, *b2, *w3, *b3;
+  int obs_dim, n_actions;
+};
+
+struct MlpShared {
+  float2 w1[2][4][kMlpHidden + kMlpPad];   // [k-step][t][n] = {W1[n][8k + t], W1[n][8k + t + 4]}
+  float2 w2[8][4][kMlpHidden + kMlpPad];   // [k-step][t][n] = {W2[n][8k + 2t], W2[n][8k + 2t + 1]}
+  float2 w3[8][4][kMlpActions + kMlpPad];  // [k-step][t][n] = {W3[n][8k + 2t], W3[n][8k + 2t + 1]}
+  float b1[kMlpHidden], b2[kMlpHidden], b3[kMlpActions];
+  float obs[kBlock / 32][32][20];          // row stride 20: the A-fragment loads hit 32 different banks
+  uint8_t act[kBlock / 32][32];
+};
+
+__device__ __forceinline__ float to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+// D = A(16x8, row) * B(8x8, col) + D.  Fragments (g = lane / 4, t = lane % 4):
+//   a0 (g, t)  a1 (g+8, t)  a2 (g, t+4)  a3 (g+8, t+4);  b0 (k = t, n = g)  b1 (k = t+4, n = g)
+//   d0 (g, 2t)  d1 (g, 2t+1)  d2 (g+8, 2t)  d3 (g+8, 2t+1)
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const float (&a)[4], float2 b) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(__float_as_uint(a[0])), "r"(__float_as_uint(a[1])), "r"(__float_as_uint(a[2])), "r"(__float_as_uint(a[3])),
+        "r"(__float_as_uint(b.x)), "r"(__float_as_uint(b.y)));
+}
+
+__device__ __forceinline__ void mlp_load_weights(MlpShared& s, const MlpWeights& w) {
+  for (int idx = threadIdx.x; idx < 2 * 4 * kMlpHidden; idx += blockDim.x) {
+    const int n = idx % kMlpHidden, t = (idx / kMlpHidden) % 4, k = idx / (4 * kMlpHidden);
+    const int f0 = 8 * k + t, f1 = f0 + 4;
+    s.w1[k][t][n] = make_float2(f0 < w.obs_dim ? to_tf32(__ldg(w.w1 + n * w.obs_dim + f0)) : 0.0f,
+                                f1 < w.obs_dim ? to_tf32(__ldg(w.w1 + n * w.obs_dim + f1)) : 0.0f);
+  }
+  for (int idx = threadIdx.x; idx < 8 * 4 * kMlpHidden; idx += blockDim.x) {
+    const int n = idx % kMlpHidden, t = (idx / kMlpHidden) % 4, k = idx / (4 * kMlpHidden);
+    const float* row = w.w2 + n * kMlpHidden + 8 * k + 2 * t;
+    s.w2[k][t][n] = make_float2(to_tf32(__ldg(row)), to_tf32(__ldg(row + 1)));
+  }
+  for (int idx = threadIdx.x; idx < 8 * 4 * kMlpActions; idx += blockDim.x) {
+    const int n = idx % kMlpActions, t = (idx / kMlpActions) % 4, k = idx / (4 * kMlpActions);
+    const float* row = w.w3 + n * kMlpHidden + 8 * k + 2 * t;
+    s.w3[k][t][n] = n < w.n_actions ? make_float2(to_tf32(__ldg(row)), to_tf32(__ldg(row + 1))) : make_float2(0.0f, 0.0f);
+  }
+  for (int idx = threadIdx.x; idx < kMlpHidden; idx += blockDim.x) {
+    s.b1[idx] = __ldg(w.b1 + idx);
+    s.b2[idx] = __ldg(w.b2 + idx);
+    if (idx < kMlpActions) s.b3[idx] = idx < w.n_actions ? __ldg(w.b3 + idx) : -3.0e38f;  // absent actions never win
+  }
+}
+
+// Q-values of the 16 episodes `tile` (0 | 1) of this warp, from the staged observations; q[j][..] in the accumulator
+// layout: actions 8j + 2t, 8j + 2t + 1 of episode 16 tile + g (q[j][0..1]) and of episode 16 tile + g + 8 (q[j][2..3]).
+__device__ __forceinline__ void mlp_forward_tile(const MlpShared& s, const float (*obs)[20], int tile, int g, int t,
+                                                 float (&q)[2][4]) {
+  float h1[8][4], h2[8][4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    h1[j][0] = h1[j][2] = s.b1[8 * j + 2 * t];
+    h1[j][1] = h1[j][3] = s.b1[8 * j + 2 * t + 1];
+  }
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const float* r0 = obs[16 * tile + g] + 8 * k + t;
+    const float* r1 = obs[16 * tile + g + 8] + 8 * k + t;
+    const float a[4] = {to_tf32(r0[0]), to_tf32(r1[0]), to_tf32(r0[4]), to_tf32(r1[4])};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) mma_tf32(h1[j], a, s.w1[k][t][8 * j + g]);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    h2[j][0] = h2[j][2] = s.b2[8 * j + 2 * t];
+    h2[j][1] = h2[j][3] = s.b2[8 * j + 2 * t + 1];
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {  // accumulator (g, 2t) (g, 2t+1) (g+8, 2t) (g+8, 2t+1) -> A (g, .) (g+8, .) (g, .) (g+8, .)
+    const float a[4] = {to_tf32(fmaxf(h1[k][0], 0.0f)), to_tf32(fmaxf(h1[k][2], 0.0f)), to_tf32(fmaxf(h1[k][1], 0.0f)),
+                        to_tf32(fmaxf(h1[k][3], 0.0f))};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) mma_tf32(h2[j], a, s.w2[k][t][8 * j + g]);
+  }
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    q[j][0] = q[j][2] = s.b3[8 * j + 2 * t];
+    q[j][1] = q[j][3] = s.b3[8 * j + 2 * t + 1];
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float a[4] = {to_tf32(fmaxf(h2[k][0], 0.0f)), to_tf32(fmaxf(h2[k][2], 0.0f)), to_tf32(fmaxf(h2[k][1], 0.0f)),
+                        to_tf32(fmaxf(h2[k][3], 0.0f))};
+#pragma unroll
+    for (int j = 0; j < 2; ++j) mma_tf32(q[j], a, s.w3[k][t][8 * j + g]);
+  }
+}
+
+// greedy action of every episode of the warp -> s.act[warp][episode]; optionally the Q-values to q_out [N][16]
+__device__ __forceinline__ void mlp_greedy(MlpShared& s, int warp, int lane, float* __restrict__ q_out, int64_t warp_first,
+                                           int64_t n) {
+  const unsigned full = 0xffffffffu;
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll 1
+  for (int tile = 0; tile < 2; ++tile) {
+    float q[2][4];
+    mlp_forward_tile(s, s.obs[warp], tile, g, t, q);
+    if (q_out) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int64_t e0 = warp_first + 16 * tile + g, e1 = e0 + 8;
+        if (e0 < n) *reinterpret_cast<float2*>(q_out + e0 * kMlpActions + 8 * j + 2 * t) = make_float2(q[j][0], q[j][1]);
+        if (e1 < n) *reinterpret_cast<float2*>(q_out + e1 * kMlpActions + 8 * j + 2 * t) = make_float2(q[j][2], q[j][3]);
+      }
+    }
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {  // rows g and g + 8
+      float best = q[0][2 * half];
+      int arg = 2 * t;
+      if (q[0][2 * half + 1] > best) { best = q[0][2 * half + 1]; arg = 2 * t + 1; }
+      if (q[1][2 * half] > best) { best = q[1][2 * half]; arg = 8 + 2 * t; }
+      if (q[1][2 * half + 1] > best) { best = q[1][2 * half + 1]; arg = 8 + 2 * t + 1; }
+#pragma unroll
+      for (int m = 1; m <= 2; m <<= 1) {  // the quad: same g, t = 0..3; ties go to the lower action index
+        const float ob = __shfl_xor_sync(full, best, m);
+        const int oa = __shfl_xor_sync(full, arg, m);
+        if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+      }
+      if (t == 0) s.act[warp][16 * tile + g + 8 * half] = static_cast<uint8_t>(arg);
+    }
+  }
+}
+
+#ifndef S2D_ROLLOUT_MIN_BLOCKS
+#define S2D_ROLLOUT_MIN_BLOCKS 4
+#endif
+
+// K closed-loop cycles of ReachBall with Discrete(n <= 16) actions: observe, Q-network, (epsilon-)greedy action, step.
+template <int VAR>
+__global__ void __launch_bounds__(kBlock, S2D_ROLLOUT_MIN_BLOCKS)
+    rollout_mlp_kernel(const __grid_constant__ KernelParams P, const int K, const MlpWeights W, const float epsilon,
+                       uint8_t* __restrict__ actions_out, float* __restrict__ q_out) {
+  constexpr int SCN = S2D_SCENARIO_REACHBALL;
+  using SP = typename VariantSP<VAR>::type;
+  const SP sp(P.cc);
+  __shared__ __align__(16) MlpShared s;
+  __shared__ __align__(16) float s_stage[kBlock / 32][32 * kObsDim];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  mlp_load_weights(s, W);
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * kBlock + threadIdx.x;
+  const int64_t n = P.num_envs;
+  const bool valid = i < n;
+  const uint64_t gid = static_cast<uint64_t>(P.env_id_offset + i);
+  const int64_t warp_first = i - lane;
+  const int64_t il = valid ? i : n - 1;
+#pragma unroll
+  for (int f = kObsDim; f < 16; ++f) s.obs[warp][lane][f] = 0.0f;
+  __syncthreads();
+  if (warp_first >= n) return;  // (whole warp; after the only block-wide barrier)
+
+  Episode e;
+  LaunchOut out;
+  float obs_row[kObsDim];
+  load_episode(P.state, n, il, e);
+#pragma unroll 1
+  for (int k = 0; k < K; ++k) {
+    scenario_obs<SCN>(e, obs_row);
+#pragma unroll
+    for (int f = 0; f < kObsDim; ++f) s.obs[warp][lane][f] = obs_row[f];
+    __syncwarp();
+    mlp_greedy(s, warp, lane, k == K - 1 ? q_out : nullptr, warp_first, n);
+    __syncwarp();
+    int a = s.act[warp][lane];
+    if (epsilon > 0.0f) {  // exploration: the same counter stream as the turning action's draw (RNG_ACTION)
+      const uint4 w = philox4x32_10(P.seed, gid, e.cycle, RNG_ACTION, 1);
+      if (u32_to_unit(w.x) < epsilon) a = u32_to_int(w.y, 0, W.n_actions - 1);
+    }
+    if (actions_out && valid) actions_out[i * K + k] = static_cast<uint8_t>(a);
+    const float2 tab = __ldg(reinterpret_cast<const float2*>(P.action_table + a) + 1);
+    const int rs = substep<SCN, S2D_ACT_DISCRETE, SP, true>(e, P, sp, gid, i, 0.f, 0.f, tab.x, tab.y, out);
+    end_of_episode<SCN>(e, P, sp, gid, i, valid, rs, out);
+  }
+  if (valid) {
+    store_episode(P.state, n, i, e);
+    scenario_obs<SCN>(e, obs_row);
+    P.reward[i] = out.reward_sum;
+    P.done[i] = static_cast<uint8_t>(out.ended != 0);
+    P.result[i] = static_cast<uint8_t>(out.last_result());
+  } else {
+    out = LaunchOut();
+  }
+  warp_store_obs(P.obs, warp_first, n, obs_row, valid, s_stage[warp]);
+  flush_tally(out, P.stats);
+}
+
+}  // namespace s2d

@@ -8,7 +8,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 # ---- constants (mirror include/soccer2d.h) ----------------------------------------------------------
 S2D_OK, S2D_ERR_INVALID, S2D_ERR_UNBOUND, S2D_ERR_CUDA, S2D_ERR_NO_DEVICE = 0, -1, -2, -3, -4
@@ -99,6 +99,12 @@ class PlayerType(C.Structure):
         return {n: getattr(self, n) for n in _PT_FIELDS}
 
 
+class MlpPolicy(C.Structure):
+    """S2DMlpPolicy: device pointers to a 64-64 Q-network in torch nn.Linear layout"""
+    _fields_ = [("w1", C.c_void_p), ("b1", C.c_void_p), ("w2", C.c_void_p), ("b2", C.c_void_p), ("w3", C.c_void_p),
+                ("b3", C.c_void_p), ("hidden", C.c_int32), ("reserved", C.c_int32)]
+
+
 # every symbol include/soccer2d.h declares: (restype, argtypes)
 _H = C.c_void_p
 SIGNATURES = {
@@ -127,6 +133,7 @@ SIGNATURES = {
     "s2d_launch_info": (C.c_int, [_H, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "s2d_generate_player_types": (C.c_int, [C.c_uint64, C.POINTER(ServerParam), C.POINTER(PlayerType), C.c_int]),
     "s2d_set_player_types": (C.c_int, [_H, C.POINTER(PlayerType), C.c_int, C.POINTER(C.c_uint8)]),
+    "s2d_rollout_mlp": (C.c_int, [_H, C.POINTER(MlpPolicy), C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 
 # S2D_LIB: alternative build of the same library (kernel tuning experiments); default = the in-tree build

@@ -174,11 +174,18 @@ class DeviceDQN:
         return c.log
 
     @torch.no_grad()
-    def evaluate(self, steps: int) -> dict:
-        """Greedy rollout (the reference's `test()`, dqn_ddpg_stable_baselines3.py:56-75): outcome rates."""
+    def evaluate(self, steps: int, fused: bool = False) -> dict:
+        """Greedy rollout (the reference's `test()`, dqn_ddpg_stable_baselines3.py:56-75): outcome rates.
+        fused: run it with Soccer2DVecEnv.rollout_mlp (TF32 Q-values: the action can differ on near-ties)."""
         before = self.env.stats()
-        for _ in range(steps):
-            self.rollout_step(0.0, store=False)
+        if fused and self.env.scenario == "reachball" and self.env.cfg.action_space_size <= 16:
+            # the Q-network inside the step kernel: 16 cycles per launch, nothing leaves the SM in between
+            layers = mlp_layers(self.q)
+            for lo in range(0, steps, 16):
+                self.env.rollout_mlp(layers, min(16, steps - lo))
+        else:
+            for _ in range(steps):
+                self.rollout_step(0.0, store=False)
         after = self.env.stats()
         d = {k: after[k] - before[k] for k in ("episodes", "goals", "outs", "timeouts", "return_sum")}
         ep = max(1, d["episodes"])
@@ -223,6 +230,30 @@ def measure_rollout(env, qnet: nn.Module, steps: int, warmup: int = 5, use_graph
     e.record()
     torch.cuda.synchronize()
     return env.num_envs * steps / (s.elapsed_time(e) * 1e-3)
+
+
+def mlp_layers(qnet: nn.Module) -> list:
+    """[(weight, bias)] of the three Linear layers of a QNetwork, as Soccer2DVecEnv.rollout_mlp takes them"""
+    lin = [m for m in qnet.modules() if isinstance(m, nn.Linear)]
+    assert len(lin) == 3, "a 64-64 MLP has three Linear layers"
+    return [(m.weight.detach().contiguous(), m.bias.detach().contiguous()) for m in lin]
+
+
+@torch.no_grad()
+def measure_fused_rollout(env, qnet: nn.Module, launches: int, k: int | None = None, warmup: int = 5) -> float:
+    """env-steps/s of the same closed loop with the Q-network INSIDE the step kernel (s2d_rollout_mlp: `k` cycles of
+    observe -> Q -> argmax -> step per launch, TF32 tensor-core MMAs), timed with CUDA events."""
+    k = env.substeps if k is None else k
+    layers = mlp_layers(qnet)
+    for _ in range(warmup):
+        env.rollout_mlp(layers, k)
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(launches):
+        env.rollout_mlp(layers, k)
+    e.record()
+    torch.cuda.synchronize()
+    return env.num_envs * k * launches / (s.elapsed_time(e) * 1e-3)
 
 
 # ---------------------------------------------------------------------------------------------------------

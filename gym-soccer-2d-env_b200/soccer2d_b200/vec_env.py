@@ -442,6 +442,33 @@ class Soccer2DVecEnv(_VecEnvBase):
         assert off == self.state.numel()
         return out
 
+    # ---- closed-loop rollout with the Q-network inside the kernel (s2d_rollout_mlp) ------------------------------
+    def rollout_mlp(self, layers, k: int | None = None, epsilon: float = 0.0, actions_out: torch.Tensor | None = None,
+                    q_out: torch.Tensor | None = None) -> None:
+        """`k` cycles of observe -> Q(obs) -> (epsilon-)greedy action -> step in ONE launch (ReachBall, Discrete(n <= 16)).
+        `layers` = [(weight, bias)] * 3 of a 64-64 ReLU MLP as torch nn.Linear stores them (float32 CUDA tensors:
+        [64, 10], [64], [64, 64], [64], [n, 64], [n]), e.g. `[(l.weight, l.bias) for l in qnet.linears]`.
+        Outputs land in the env's obs / reward / done_u8 / result tensors as after `step_torch`; optional
+        `actions_out` uint8 [N, k] receives the actions taken and `q_out` float32 [N, 16] the Q-values of the last cycle."""
+        k = self.substeps if k is None else int(k)
+        ptrs = []
+        for (w, b), shape in zip(layers, ((64, self.obs_dim), (64, 64), (self.cfg.action_space_size, 64))):
+            if tuple(w.shape) != shape or tuple(b.shape) != shape[:1]:
+                raise ValueError(f"rollout_mlp: expected weight {shape} and bias {shape[:1]}, got {tuple(w.shape)} / {tuple(b.shape)}")
+            for t in (w, b):
+                if t.dtype != torch.float32 or not t.is_cuda or not t.is_contiguous() or t.device != self.device:
+                    raise ValueError("rollout_mlp: weights must be contiguous float32 tensors on the env's device")
+            ptrs += [w.data_ptr(), b.data_ptr()]
+        if actions_out is not None:
+            assert actions_out.dtype == torch.uint8 and tuple(actions_out.shape) == (self.num_envs, k) and actions_out.is_contiguous()
+        if q_out is not None:
+            assert q_out.dtype == torch.float32 and tuple(q_out.shape) == (self.num_envs, 16) and q_out.is_contiguous()
+        pol = _abi.MlpPolicy(*ptrs, 64, 0)
+        _abi.check(self.lib.s2d_rollout_mlp(self.handle, C.byref(pol), k, float(epsilon),
+                                            actions_out.data_ptr() if actions_out is not None else None,
+                                            q_out.data_ptr() if q_out is not None else None, _stream_ptr(self.device)),
+                   self.handle)
+
     # ---- heterogeneous players (fullgame; proto PlayerType, idl/service.proto:1697-1732) ------------------------
     def generate_player_types(self, seed: int, n: int = _abi.MAX_PLAYER_TYPES) -> list:
         """rcssserver's HeteroPlayer draws for this env's ServerParam: [type 0 = default player, n - 1 drawn types]"""

@@ -20,4 +20,7 @@ python profiles/prof_fullgame.py > /dev/null 2>&1 && {
   ncu --set full --clock-control none --import-source on -k regex:fullgame_step -s 3 -c 1 -o $O/prof_${TAG}_fg_k1 -f python profiles/prof_fullgame.py >> $O/ncu_full.log 2>&1
   ncu --set full --clock-control none --import-source on -k regex:fullgame_step -s 8 -c 1 -o $O/prof_${TAG}_fg_k16 -f python profiles/prof_fullgame.py >> $O/ncu_full.log 2>&1
 }
+python profiles/tune_rollout.py >> $O/${TAG}_scenarios.txt 2>&1
+python profiles/prof_rollout.py > /dev/null 2>&1 && \
+  ncu --set full --clock-control none --import-source on -k regex:rollout_mlp -s 2 -c 1 -o $O/prof_${TAG}_rollout -f python profiles/prof_rollout.py >> $O/ncu_full.log 2>&1
 ls -la $O | tail -20

@@ -5,7 +5,7 @@ import torch
 
 import helpers as H
 import oracle_lib as OL
-from soccer2d_b200 import Soccer2DVecEnv
+from soccer2d_b200 import Soccer2DVecEnv, _abi
 from soccer2d_b200.rollout import DeviceDQN, DeviceReplayBuffer, DQNConfig, QNetwork, measure_rollout
 
 pytestmark = pytest.mark.gpu
@@ -63,14 +63,19 @@ def test_dqn_learns_to_reach_the_ball():
     trained = agent.evaluate(400)
     assert trained["episodes"] > 4096 and random_policy["episodes"] == 0
     assert trained["goal_rate"] > max(0.6, 3 * random_goal_rate), (trained, random_goal_rate)
+    # the same greedy evaluation with the Q-network inside the step kernel (TF32): the same policy, the same outcome rates
+    fused = agent.evaluate(400, fused=True)
+    assert fused["episodes"] > 4096 and abs(fused["goal_rate"] - trained["goal_rate"]) < 0.05, (fused, trained)
 
 
 def test_measure_rollout_runs():
+    from soccer2d_b200.rollout import measure_fused_rollout
     env = Soccer2DVecEnv(1 << 16, device="cuda:0", seed=0, **KW)
     env.reset_torch()
     q = QNetwork(10, 16).to("cuda:0")
     rate = measure_rollout(env, q, steps=20)
     assert rate > 1e7
+    assert measure_fused_rollout(env, q, launches=10, k=16) > 5 * rate
 
 
 def test_ddpg_learns_to_reach_the_ball():
@@ -87,3 +92,86 @@ def test_ddpg_learns_to_reach_the_ball():
     trained = agent.evaluate(400)
     assert trained["episodes"] > 4096
     assert trained["goal_rate"] > max(0.6, 2 * random_goal_rate), (trained, random_goal_rate)
+
+
+# ---- the Q-network inside the kernel (s2d_rollout_mlp) ---------------------------------------------------------------
+
+def _layers(q):
+    lin = [m for m in q.net if isinstance(m, torch.nn.Linear)]
+    return [(l.weight.detach().contiguous(), l.bias.detach().contiguous()) for l in lin]
+
+
+@pytest.mark.parametrize("n_actions,n", [(16, 4096 + 37), (12, 1000)])
+def test_fused_policy_rollout_matches_policy_then_step(n_actions, n):
+    """K cycles of observe -> Q -> argmax -> step in one launch.  The env half is checked bit for bit (replaying the
+    recorded actions through the ordinary step kernel gives the same state), the policy half against torch fp32:
+    Q-values within TF32 accuracy, and the greedy action equal except where fp32 itself sees a near-tie."""
+    from soccer2d_b200.rollout import QNetwork
+    torch.manual_seed(0)
+    k = 5
+    kw = dict(device="cuda:0", seed=4, use_continuous_action=False, action_space_size=n_actions, change_ball_velocity=True)
+    fused = Soccer2DVecEnv(n, substeps=k, **kw)
+    plain = Soccer2DVecEnv(n, substeps=1, **kw)
+    qnet = QNetwork(10, n_actions).cuda()
+    with torch.no_grad():  # weights of a trained net are O(1): make the test's larger than the default init
+        for p in qnet.parameters():
+            p.mul_(3.0)
+    layers = _layers(qnet)
+    fused.reset_torch()
+    plain.reset_torch()
+    actions = torch.zeros((n, k), dtype=torch.uint8, device="cuda")
+    q_seen = torch.zeros((n, 16), dtype=torch.float32, device="cuda")
+    agree = total = 0
+    worst_q = 0.0
+    for launch in range(50):  # 250 cycles: episodes end and restart inside the launches
+        fused.rollout_mlp(layers, k, 0.0, actions, q_seen)
+        for j in range(k):
+            with torch.no_grad():
+                q32 = qnet(plain.obs)
+            a32 = q32.argmax(dim=1)
+            taken = actions[:, j].long()
+            agree += int((a32 == taken).sum())
+            total += n
+            # where the kernel chose differently, fp32 itself must see (almost) a tie between the two actions
+            gap = (q32.gather(1, a32[:, None]) - q32.gather(1, taken[:, None])).squeeze(1)
+            scale = q32.abs().max(dim=1).values + 1.0
+            assert float((gap / scale).max()) < 5e-3
+            if j == k - 1:
+                worst_q = max(worst_q, float(((q_seen[:, :n_actions] - q32).abs().max(dim=1).values / scale).max()))
+                if n_actions < 16:
+                    assert float(q_seen[:, n_actions:].max()) < -1e38
+            plain.step_torch(actions[:, j:j + 1].contiguous())
+        assert torch.equal(fused.state, plain.state) and torch.equal(fused.obs, plain.obs)
+        assert torch.equal(fused.done_u8, plain.done_u8) or k > 1  # (done of a fused launch = any cycle ended)
+    assert worst_q < 3e-3, worst_q
+    assert agree / total > 0.985, agree / total
+    sf, sp = fused.stats(), plain.stats()
+    assert sf["episodes"] == sp["episodes"] > 0 and sf["env_steps"] == sp["env_steps"] == n * k * 50
+    fused.close()
+    plain.close()
+
+
+def test_fused_policy_rollout_epsilon_and_errors():
+    from soccer2d_b200.rollout import QNetwork
+    n, k = 8192, 8
+    env = Soccer2DVecEnv(n, device="cuda:0", seed=1, substeps=k, use_continuous_action=False, action_space_size=16)
+    qnet = QNetwork(10, 16).cuda()
+    layers = _layers(qnet)
+    env.reset_torch()
+    greedy = torch.zeros((n, k), dtype=torch.uint8, device="cuda")
+    env.rollout_mlp(layers, k, 0.0, greedy)
+    env.reset_torch()  # (a new episode number: other start states, so compare distributions, not actions)
+    explore = torch.zeros((n, k), dtype=torch.uint8, device="cuda")
+    env.rollout_mlp(layers, k, 1.0, explore)
+    counts = torch.bincount(explore.flatten().long(), minlength=16).float()
+    assert float(counts.min()) > 0.8 * n * k / 16 and float(counts.max()) < 1.2 * n * k / 16  # uniform over 16 actions
+    assert torch.bincount(greedy.flatten().long(), minlength=16).float().max() > 2.0 * n * k / 16  # a policy is not uniform
+    with pytest.raises(ValueError):
+        env.rollout_mlp(layers[:2] + [(layers[2][0][:8].contiguous(), layers[2][1][:8].contiguous())], k)
+    cont = Soccer2DVecEnv(64, device="cuda:0", use_continuous_action=True)
+    with pytest.raises(_abi.Soccer2DError):
+        cont.rollout_mlp([(torch.zeros(64, 10, device="cuda"), torch.zeros(64, device="cuda")),
+                          (torch.zeros(64, 64, device="cuda"), torch.zeros(64, device="cuda")),
+                          (torch.zeros(16, 64, device="cuda"), torch.zeros(16, device="cuda"))], 1)
+    env.close()
+    cont.close()

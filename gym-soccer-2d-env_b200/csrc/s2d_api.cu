@@ -658,8 +658,9 @@ int s2d_rollout_mlp(S2DHandle h, const S2DMlpPolicy* policy, int k_substeps, flo
                     void* q_out, void* stream) {
   if (!h) return S2D_ERR_INVALID;
   if (!h->bound) return fail(h, S2D_ERR_UNBOUND, "s2d_bind has not been called");
-  if (h->cfg.scenario != S2D_SCENARIO_REACHBALL || h->cfg.action_mode != S2D_ACT_DISCRETE || h->cfg.action_space_size > kMlpActions)
-    return fail(h, S2D_ERR_INVALID, "s2d_rollout_mlp: REACHBALL with Discrete(n <= %d) actions only", kMlpActions);
+  const bool shoot = h->cfg.scenario == S2D_SCENARIO_SHOOT;
+  if (h->cfg.scenario == S2D_SCENARIO_FULLGAME || h->cfg.action_mode != S2D_ACT_DISCRETE || h->cfg.action_space_size > (shoot ? 24 : 16))
+    return fail(h, S2D_ERR_INVALID, "s2d_rollout_mlp: REACHBALL with Discrete(n <= 16) or SHOOT with Discrete(n <= 24) actions only");
   if (!policy || !policy->w1 || !policy->b1 || !policy->w2 || !policy->b2 || !policy->w3 || !policy->b3 || policy->hidden != kMlpHidden)
     return fail(h, S2D_ERR_INVALID, "s2d_rollout_mlp: six weight pointers and hidden = %d are required", kMlpHidden);
   if (k_substeps < 1 || k_substeps > kMaxSubsteps) return fail(h, S2D_ERR_INVALID, "k_substeps must be in 1..%d", kMaxSubsteps);
@@ -669,9 +670,15 @@ int s2d_rollout_mlp(S2DHandle h, const S2DMlpPolicy* policy, int k_substeps, flo
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   uint8_t* ao = static_cast<uint8_t*>(actions_out);
   float* qo = static_cast<float*>(q_out);
-  if (h->cfg.noise) rollout_mlp_kernel<kVarNoisy><<<h->grid, kBlock, 0, s>>>(h->kp, k_substeps, w, epsilon, ao, qo);
-  else if (h->default_sp) rollout_mlp_kernel<kVarDefault><<<h->grid, kBlock, 0, s>>>(h->kp, k_substeps, w, epsilon, ao, qo);
-  else rollout_mlp_kernel<kVarRuntime><<<h->grid, kBlock, 0, s>>>(h->kp, k_substeps, w, epsilon, ao, qo);
+#define S2D_ROLLOUT(SCN)                                                                                             \
+  do {                                                                                                               \
+    if (h->cfg.noise) rollout_mlp_kernel<SCN, kVarNoisy><<<h->grid, kBlock, 0, s>>>(h->kp, k_substeps, w, epsilon, ao, qo); \
+    else if (h->default_sp) rollout_mlp_kernel<SCN, kVarDefault><<<h->grid, kBlock, 0, s>>>(h->kp, k_substeps, w, epsilon, ao, qo); \
+    else rollout_mlp_kernel<SCN, kVarRuntime><<<h->grid, kBlock, 0, s>>>(h->kp, k_substeps, w, epsilon, ao, qo);       \
+  } while (0)
+  if (shoot) S2D_ROLLOUT(S2D_SCENARIO_SHOOT);
+  else S2D_ROLLOUT(S2D_SCENARIO_REACHBALL);
+#undef S2D_ROLLOUT
   S2D_CUDA(h, cudaGetLastError());
   h->env_steps += static_cast<uint64_t>(h->cfg.num_envs) * static_cast<uint64_t>(k_substeps);
   return S2D_OK;

@@ -22,7 +22,7 @@
 namespace s2d {
 
 constexpr int kMlpHidden = 64;
-constexpr int kMlpActions = 16;  // n-tiles of 8: up to 16 actions
+constexpr int kMlpActions = 24;  // room for 3 column tiles of 8 actions (ReachBall uses 2: Discrete(n <= 16); Shoot 3: n <= 24)
 constexpr int kMlpPad = 4;       // row padding (in float2 entries) that spreads the four t-rows over the banks
 
 struct MlpWeights {  // device pointers, torch layout: weight [out][in] row-major, bias [out]
@@ -82,8 +82,9 @@ __device__ __forceinline__ void mlp_load_weights(MlpShared& s, const MlpWeights&
 
 // Q-values of the 16 episodes `tile` (0 | 1) of this warp, from the staged observations; q[j][..] in the accumulator
 // layout: actions 8j + 2t, 8j + 2t + 1 of episode 16 tile + g (q[j][0..1]) and of episode 16 tile + g + 8 (q[j][2..3]).
+template <int NT>
 __device__ __forceinline__ void mlp_forward_tile(const MlpShared& s, const float (*obs)[20], int tile, int g, int t,
-                                                 float (&q)[2][4]) {
+                                                 float (&q)[NT][4]) {
   float h1[8][4], h2[8][4];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -111,7 +112,7 @@ __device__ __forceinline__ void mlp_forward_tile(const MlpShared& s, const float
     for (int j = 0; j < 8; ++j) mma_tf32(h2[j], a, s.w2[k][t][8 * j + g]);
   }
 #pragma unroll
-  for (int j = 0; j < 2; ++j) {
+  for (int j = 0; j < NT; ++j) {
     q[j][0] = q[j][2] = s.b3[8 * j + 2 * t];
     q[j][1] = q[j][3] = s.b3[8 * j + 2 * t + 1];
   }
@@ -120,34 +121,37 @@ __device__ __forceinline__ void mlp_forward_tile(const MlpShared& s, const float
     const float a[4] = {to_tf32(fmaxf(h2[k][0], 0.0f)), to_tf32(fmaxf(h2[k][2], 0.0f)), to_tf32(fmaxf(h2[k][1], 0.0f)),
                         to_tf32(fmaxf(h2[k][3], 0.0f))};
 #pragma unroll
-    for (int j = 0; j < 2; ++j) mma_tf32(q[j], a, s.w3[k][t][8 * j + g]);
+    for (int j = 0; j < NT; ++j) mma_tf32(q[j], a, s.w3[k][t][8 * j + g]);
   }
 }
 
-// greedy action of every episode of the warp -> s.act[warp][episode]; optionally the Q-values to q_out [N][16]
+// greedy action of every episode of the warp -> s.act[warp][episode]; optionally the Q-values to q_out [N][8 NT]
+template <int NT>
 __device__ __forceinline__ void mlp_greedy(MlpShared& s, int warp, int lane, float* __restrict__ q_out, int64_t warp_first,
                                            int64_t n) {
   const unsigned full = 0xffffffffu;
   const int g = lane >> 2, t = lane & 3;
 #pragma unroll 1
   for (int tile = 0; tile < 2; ++tile) {
-    float q[2][4];
-    mlp_forward_tile(s, s.obs[warp], tile, g, t, q);
+    float q[NT][4];
+    mlp_forward_tile<NT>(s, s.obs[warp], tile, g, t, q);
     if (q_out) {
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
+      for (int j = 0; j < NT; ++j) {
         const int64_t e0 = warp_first + 16 * tile + g, e1 = e0 + 8;
-        if (e0 < n) *reinterpret_cast<float2*>(q_out + e0 * kMlpActions + 8 * j + 2 * t) = make_float2(q[j][0], q[j][1]);
-        if (e1 < n) *reinterpret_cast<float2*>(q_out + e1 * kMlpActions + 8 * j + 2 * t) = make_float2(q[j][2], q[j][3]);
+        if (e0 < n) *reinterpret_cast<float2*>(q_out + e0 * (8 * NT) + 8 * j + 2 * t) = make_float2(q[j][0], q[j][1]);
+        if (e1 < n) *reinterpret_cast<float2*>(q_out + e1 * (8 * NT) + 8 * j + 2 * t) = make_float2(q[j][2], q[j][3]);
       }
     }
 #pragma unroll
     for (int half = 0; half < 2; ++half) {  // rows g and g + 8
       float best = q[0][2 * half];
       int arg = 2 * t;
-      if (q[0][2 * half + 1] > best) { best = q[0][2 * half + 1]; arg = 2 * t + 1; }
-      if (q[1][2 * half] > best) { best = q[1][2 * half]; arg = 8 + 2 * t; }
-      if (q[1][2 * half + 1] > best) { best = q[1][2 * half + 1]; arg = 8 + 2 * t + 1; }
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {  // ascending action index: a strict > keeps the lower index on ties
+        if (j > 0 && q[j][2 * half] > best) { best = q[j][2 * half]; arg = 8 * j + 2 * t; }
+        if (q[j][2 * half + 1] > best) { best = q[j][2 * half + 1]; arg = 8 * j + 2 * t + 1; }
+      }
 #pragma unroll
       for (int m = 1; m <= 2; m <<= 1) {  // the quad: same g, t = 0..3; ties go to the lower action index
         const float ob = __shfl_xor_sync(full, best, m);
@@ -163,12 +167,13 @@ __device__ __forceinline__ void mlp_greedy(MlpShared& s, int warp, int lane, flo
 #define S2D_ROLLOUT_MIN_BLOCKS 4
 #endif
 
-// K closed-loop cycles of ReachBall with Discrete(n <= 16) actions: observe, Q-network, (epsilon-)greedy action, step.
-template <int VAR>
+// K closed-loop cycles of a one-player scenario with Discrete actions (ReachBall: n <= 16, Shoot: n <= 24): observe,
+// Q-network, (epsilon-)greedy action, step.
+template <int SCN, int VAR>
 __global__ void __launch_bounds__(kBlock, S2D_ROLLOUT_MIN_BLOCKS)
     rollout_mlp_kernel(const __grid_constant__ KernelParams P, const int K, const MlpWeights W, const float epsilon,
                        uint8_t* __restrict__ actions_out, float* __restrict__ q_out) {
-  constexpr int SCN = S2D_SCENARIO_REACHBALL;
+  constexpr int NT = SCN == S2D_SCENARIO_SHOOT ? 3 : 2;
   using SP = typename VariantSP<VAR>::type;
   const SP sp(P.cc);
   __shared__ __align__(16) MlpShared s;
@@ -196,7 +201,7 @@ __global__ void __launch_bounds__(kBlock, S2D_ROLLOUT_MIN_BLOCKS)
 #pragma unroll
     for (int f = 0; f < kObsDim; ++f) s.obs[warp][lane][f] = obs_row[f];
     __syncwarp();
-    mlp_greedy(s, warp, lane, k == K - 1 ? q_out : nullptr, warp_first, n);
+    mlp_greedy<NT>(s, warp, lane, k == K - 1 ? q_out : nullptr, warp_first, n);
     __syncwarp();
     int a = s.act[warp][lane];
     if (epsilon > 0.0f) {  // exploration: the same counter stream as the turning action's draw (RNG_ACTION)
@@ -204,8 +209,14 @@ __global__ void __launch_bounds__(kBlock, S2D_ROLLOUT_MIN_BLOCKS)
       if (u32_to_unit(w.x) < epsilon) a = u32_to_int(w.y, 0, W.n_actions - 1);
     }
     if (actions_out && valid) actions_out[i * K + k] = static_cast<uint8_t>(a);
-    const float2 tab = __ldg(reinterpret_cast<const float2*>(P.action_table + a) + 1);
-    const int rs = substep<SCN, S2D_ACT_DISCRETE, SP, true>(e, P, sp, gid, i, 0.f, 0.f, tab.x, tab.y, out);
+    int rs;
+    if (SCN == S2D_SCENARIO_SHOOT) {
+      const float4 tab = __ldg(P.action_table + a);
+      rs = substep<SCN, S2D_ACT_DISCRETE, SP, true>(e, P, sp, gid, i, tab.x, tab.y, tab.z, tab.w, out);
+    } else {
+      const float2 tab = __ldg(reinterpret_cast<const float2*>(P.action_table + a) + 1);
+      rs = substep<SCN, S2D_ACT_DISCRETE, SP, true>(e, P, sp, gid, i, 0.f, 0.f, tab.x, tab.y, out);
+    }
     end_of_episode<SCN>(e, P, sp, gid, i, valid, rs, out);
   }
   if (valid) {

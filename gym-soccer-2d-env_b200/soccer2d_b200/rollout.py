@@ -178,7 +178,7 @@ class DeviceDQN:
         """Greedy rollout (the reference's `test()`, dqn_ddpg_stable_baselines3.py:56-75): outcome rates.
         fused: run it with Soccer2DVecEnv.rollout_mlp (TF32 Q-values: the action can differ on near-ties)."""
         before = self.env.stats()
-        if fused and self.env.scenario == "reachball" and self.env.cfg.action_space_size <= 16:
+        if fused and self.env.action_mode == 0 and self.env.cfg.action_space_size <= (24 if self.env.scenario == "shoot" else 16):
             # the Q-network inside the step kernel: 16 cycles per launch, nothing leaves the SM in between
             layers = mlp_layers(self.q)
             for lo in range(0, steps, 16):

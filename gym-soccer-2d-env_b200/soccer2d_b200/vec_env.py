@@ -445,11 +445,12 @@ class Soccer2DVecEnv(_VecEnvBase):
     # ---- closed-loop rollout with the Q-network inside the kernel (s2d_rollout_mlp) ------------------------------
     def rollout_mlp(self, layers, k: int | None = None, epsilon: float = 0.0, actions_out: torch.Tensor | None = None,
                     q_out: torch.Tensor | None = None) -> None:
-        """`k` cycles of observe -> Q(obs) -> (epsilon-)greedy action -> step in ONE launch (ReachBall, Discrete(n <= 16)).
+        """`k` cycles of observe -> Q(obs) -> (epsilon-)greedy action -> step in ONE launch (Discrete actions: ReachBall
+        with n <= 16, Shoot with n <= 24).
         `layers` = [(weight, bias)] * 3 of a 64-64 ReLU MLP as torch nn.Linear stores them (float32 CUDA tensors:
         [64, 10], [64], [64, 64], [64], [n, 64], [n]), e.g. `[(l.weight, l.bias) for l in qnet.linears]`.
         Outputs land in the env's obs / reward / done_u8 / result tensors as after `step_torch`; optional
-        `actions_out` uint8 [N, k] receives the actions taken and `q_out` float32 [N, 16] the Q-values of the last cycle."""
+        `actions_out` uint8 [N, k] receives the actions taken and `q_out` float32 [N, 16] (Shoot: [N, 24]) the Q-values of the last cycle."""
         k = self.substeps if k is None else int(k)
         ptrs = []
         for (w, b), shape in zip(layers, ((64, self.obs_dim), (64, 64), (self.cfg.action_space_size, 64))):
@@ -462,7 +463,8 @@ class Soccer2DVecEnv(_VecEnvBase):
         if actions_out is not None:
             assert actions_out.dtype == torch.uint8 and tuple(actions_out.shape) == (self.num_envs, k) and actions_out.is_contiguous()
         if q_out is not None:
-            assert q_out.dtype == torch.float32 and tuple(q_out.shape) == (self.num_envs, 16) and q_out.is_contiguous()
+            width = 24 if self.scenario == "shoot" else 16
+            assert q_out.dtype == torch.float32 and tuple(q_out.shape) == (self.num_envs, width) and q_out.is_contiguous()
         pol = _abi.MlpPolicy(*ptrs, 64, 0)
         _abi.check(self.lib.s2d_rollout_mlp(self.handle, C.byref(pol), k, float(epsilon),
                                             actions_out.data_ptr() if actions_out is not None else None,

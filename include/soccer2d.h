@@ -312,14 +312,16 @@ int s2d_generate_player_types(uint64_t seed, const S2DServerParam* sp, S2DPlayer
  * homogeneous players.  FULLGAME only. */
 int s2d_set_player_types(S2DHandle h, const S2DPlayerType* types, int n, const uint8_t* type_of_player);
 
-/* Closed-loop rollout with the policy inside the kernel (REACHBALL, S2D_ACT_DISCRETE with at most 16 actions).
+/* Closed-loop rollout with the policy inside the kernel (S2D_ACT_DISCRETE; REACHBALL with at most 16 actions, SHOOT
+ * with at most 24).
  * The reference's caller is SB3 DQN (dqn_stable_baselines3.py:33-55): MlpPolicy = obs -> 64 -> 64 -> n_actions with
  * ReLU, `action = argmax Q(obs)`, `env.step(action)`.  s2d_rollout_mlp runs k_substeps cycles of
  *     observe -> Q-network (warp-level tensor-core MMAs, TF32 operands, fp32 accumulate) -> action -> step
  * per launch without the observation or the action leaving the SM; with probability `epsilon` the action is uniform
  * random instead (counter RNG keyed on (seed, global env id, cycle)).  Outputs as s2d_step (obs after the last cycle,
  * reward summed, done / result, statistics); `actions_out` (device, uint8 [num_envs][k_substeps]) and `q_out` (device,
- * float [num_envs][16]: Q-values seen before the LAST cycle, absent actions -3e38) are optional.
+ * float [num_envs][16] for REACHBALL, [num_envs][24] for SHOOT: the Q-values seen before the LAST cycle, absent actions
+ * -3e38) are optional.
  * Weights: device pointers in torch nn.Linear layout (weight [out][in] row-major, bias [out]); hidden must be 64.
  * TF32 has 10 mantissa bits: Q agrees with an fp32 evaluation to about 1e-3 of its scale, so the greedy action can
  * differ from an fp32 policy's on near-ties. */

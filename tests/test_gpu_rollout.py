@@ -101,15 +101,18 @@ def _layers(q):
     return [(l.weight.detach().contiguous(), l.bias.detach().contiguous()) for l in lin]
 
 
-@pytest.mark.parametrize("n_actions,n", [(16, 4096 + 37), (12, 1000)])
-def test_fused_policy_rollout_matches_policy_then_step(n_actions, n):
+@pytest.mark.parametrize("scenario,n_actions,n", [("reachball", 16, 4096 + 37), ("reachball", 12, 1000), ("shoot", 24, 2000 + 5)])
+def test_fused_policy_rollout_matches_policy_then_step(scenario, n_actions, n):
     """K cycles of observe -> Q -> argmax -> step in one launch.  The env half is checked bit for bit (replaying the
     recorded actions through the ordinary step kernel gives the same state), the policy half against torch fp32:
     Q-values within TF32 accuracy, and the greedy action equal except where fp32 itself sees a near-tie."""
     from soccer2d_b200.rollout import QNetwork
     torch.manual_seed(0)
     k = 5
-    kw = dict(device="cuda:0", seed=4, use_continuous_action=False, action_space_size=n_actions, change_ball_velocity=True)
+    kw = dict(device="cuda:0", seed=4, scenario=scenario, action_space_size=n_actions, change_ball_velocity=True)
+    if scenario == "reachball":
+        kw["use_continuous_action"] = False
+    width = 24 if scenario == "shoot" else 16
     fused = Soccer2DVecEnv(n, substeps=k, **kw)
     plain = Soccer2DVecEnv(n, substeps=1, **kw)
     qnet = QNetwork(10, n_actions).cuda()
@@ -120,7 +123,7 @@ def test_fused_policy_rollout_matches_policy_then_step(n_actions, n):
     fused.reset_torch()
     plain.reset_torch()
     actions = torch.zeros((n, k), dtype=torch.uint8, device="cuda")
-    q_seen = torch.zeros((n, 16), dtype=torch.float32, device="cuda")
+    q_seen = torch.zeros((n, width), dtype=torch.float32, device="cuda")
     agree = total = 0
     worst_q = 0.0
     for launch in range(50):  # 250 cycles: episodes end and restart inside the launches
@@ -138,7 +141,7 @@ def test_fused_policy_rollout_matches_policy_then_step(n_actions, n):
             assert float((gap / scale).max()) < 5e-3
             if j == k - 1:
                 worst_q = max(worst_q, float(((q_seen[:, :n_actions] - q32).abs().max(dim=1).values / scale).max()))
-                if n_actions < 16:
+                if n_actions < width:
                     assert float(q_seen[:, n_actions:].max()) < -1e38
             plain.step_torch(actions[:, j:j + 1].contiguous())
         assert torch.equal(fused.state, plain.state) and torch.equal(fused.obs, plain.obs)

@@ -35,7 +35,6 @@ def main():
         print(json.dumps(rep), flush=True)
     print(json.dumps({"test": agent.evaluate(args.test_steps)}), flush=True)
     env.close()
-    env.close()
 
 
 if __name__ == "__main__":

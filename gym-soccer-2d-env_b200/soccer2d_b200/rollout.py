@@ -296,15 +296,17 @@ class DDPGConfig:
 
 
 class DeviceDDPG:
-    """DDPG with the rollout, the replay buffer and the learner on the GPU.  `env`: a Box(-1, 1, (1,)) ReachBall
-    Soccer2DVecEnv (use_continuous_action=True, use_turning=False) with substeps=1, auto_reset and terminal_obs."""
+    """DDPG with the rollout, the replay buffer and the learner on the GPU.  `env`: a ReachBall Soccer2DVecEnv with a
+    Box action space - Box(-1, 1, (1,)) (use_continuous_action=True: ddpg_stable_baselines3.py) or Box(-1, 1, (4,))
+    (use_turning=True: dqn_ddpg_stable_baselines3.py) - with substeps=1, auto_reset and terminal_obs."""
 
     def __init__(self, env, cfg: DDPGConfig | None = None):
         assert env.substeps == 1 and env.auto_reset and env.terminal_obs is not None
-        assert env.actions.dtype == torch.float32 and env.actions.dim() == 2, "Box(-1, 1, (1,)) action space required"
+        assert env.actions.dtype == torch.float32 and env.actions.dim() in (2, 3), "a Box action space is required"
         self.env, self.cfg, self.device = env, cfg or DDPGConfig(), env.device
         torch.manual_seed(self.cfg.seed)
-        od, ad = env.obs_dim, 1
+        od, ad = env.obs_dim, (1 if env.actions.dim() == 2 else env.actions.shape[-1])
+        self.act_dim = ad
         self.actor, self.actor_t = Actor(od, ad).to(self.device), Actor(od, ad).to(self.device)
         self.critic, self.critic_t = Critic(od, ad).to(self.device), Critic(od, ad).to(self.device)
         self.actor_t.load_state_dict(self.actor.state_dict())
@@ -334,12 +336,12 @@ class DeviceDDPG:
     def rollout_step(self, noise_std: float, store: bool = True, random: bool = False):
         env = self.env
         if random:
-            a = torch.rand((env.num_envs, 1), device=self.device, generator=self.gen) * 2 - 1
+            a = torch.rand((env.num_envs, self.act_dim), device=self.device, generator=self.gen) * 2 - 1
         else:
             a = self.actor(self._obs)
             if noise_std > 0:
                 a = (a + noise_std * torch.randn(a.shape, device=self.device, generator=self.gen)).clamp_(-1, 1)
-        env.actions.copy_(a)  # [N, 1] float32: written in place, zero copy
+        env.actions.view(env.num_envs, self.act_dim).copy_(a)  # [N, 1(, 4)] float32: written in place, zero copy
         obs, reward, done, _ = env.step_torch()
         if store:
             nxt = torch.where(done.unsqueeze(1), env.terminal_obs, obs)

@@ -178,3 +178,22 @@ def test_fused_policy_rollout_epsilon_and_errors():
                           (torch.zeros(16, 64, device="cuda"), torch.zeros(16, device="cuda"))], 1)
     env.close()
     cont.close()
+
+
+def test_ddpg_drives_the_turning_action_space():
+    """Box(4) = [turn_prob, turn_angle, dash_prob, dash_angle] (dqn_ddpg_stable_baselines3.py's configuration): the agent
+    fills the [N, 1, 4] action tensor in place and learns on it (a short run: it must at least beat the random policy)."""
+    from soccer2d_b200.rollout import DDPGConfig, DeviceDDPG
+    kw = dict(change_ball_position=False, use_continuous_action=True, use_turning=True)
+    env = Soccer2DVecEnv(2048, device="cuda:0", seed=0, terminal_obs=True, **kw)
+    assert tuple(env.actions.shape) == (2048, 1, 4)
+    agent = DeviceDDPG(env, DDPGConfig(seed=0, learning_starts=1 << 14))
+    assert agent.act_dim == 4
+    for _ in range(250):
+        agent.rollout_step(0.0, store=False, random=True)
+    st = env.stats()
+    random_goal_rate = st["goals"] / max(1, st["episodes"])
+    agent.learn(1200)
+    trained = agent.evaluate(300)
+    assert trained["episodes"] > 1000 and trained["goal_rate"] > random_goal_rate + 0.1, (trained, random_goal_rate)
+    env.close()

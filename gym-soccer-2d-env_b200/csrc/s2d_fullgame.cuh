@@ -19,11 +19,12 @@ constexpr int kFgObsDim = 120;        // 4 ball + 22 x 5 player + 6 referee valu
 constexpr int kFgDropBallTime = 100;  // cycles a dead ball waits for the awarded side before play resumes
 constexpr int kFgMaxPlayers = 22;
 constexpr float kFgFreeKickDist = 9.15f;  // the distance opponents keep from a dead ball
+constexpr float kFgOffsideArea = 2.5f;    // offside_active_area_size: a marked player this close to the ball takes part
 
 // HBM layout of N matches with np players each (plane-major; every plane starts 16-byte aligned):
 //   PA float4 [N][np] {x, y, vx, vy}            PB float4 [N][np] {body, stamina, effort, recovery}
 //   PC float  [N][np] stamina_capacity (plane padded to 16 B)
-//   EB float4 [N] ball {x, y, vx, vy}           EF float4 [N] {episode return, player separation bound, -, -}
+//   EB float4 [N] ball {x, y, vx, vy}           EF float4 [N] {episode return, player separation bound, offside marks (bits), -}
 //   EI uint4  [N] {step_number, cycle, episode, mode | side<<8 | last_touch<<10 | timer<<12 | ball_collided<<20 | done<<21}
 //   EJ uint4  [N] {score_l, score_r, collided mask (bit = player), kicked mask}
 struct FgLayout {
@@ -48,6 +49,7 @@ struct Match {
   int score_l, score_r;
   float ep_return;
   float sep;  // lower bound on the smallest player-player distance (see fg_collisions); 0 = unknown
+  uint32_t offside;  // bit = player marked offside at the last pass of its team (all bits from one team)
   bool done_flag;
 };
 
@@ -58,6 +60,12 @@ __device__ __constant__ float kFgFormY[11] = {0, -20, -7, 7, 20, -24, -8, 8, 24,
 __device__ __forceinline__ float butterfly_sum(float v) {
 #pragma unroll
   for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+  return v;
+}
+
+__device__ __forceinline__ float butterfly_max(float v) {
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, m));
   return v;
 }
 
@@ -243,6 +251,7 @@ __device__ __forceinline__ void fg_reset(Episode& p, Match& m, const KernelParam
   m.step_number = 0;
   m.ep_return = 0.0f;
   m.sep = 0.0f;
+  m.offside = 0u;
   m.done_flag = false;
   m.mode = S2D_PM_KICK_OFF;
   m.side = S2D_SIDE_LEFT;
@@ -400,11 +409,31 @@ __device__ __forceinline__ bool fg_cycle(Episode& p, Match& m, const KernelParam
   const unsigned left_lanes = (1u << pps) - 1u;
   const bool kick_l = (kick_ballot & left_lanes) != 0, kick_r = (kick_ballot & ~left_lanes) != 0;
   if (kick_l != kick_r) m.last_touch = kick_l ? S2D_SIDE_LEFT : S2D_SIDE_RIGHT;
+  const int mode_at_kick = m.mode;
   if (dead && ((m.side == S2D_SIDE_LEFT && kick_l) || (m.side == S2D_SIDE_RIGHT && kick_r))) {
     m.mode = S2D_PM_PLAY_ON;
     dead = false;
   }
   kicked_mask = kick_ballot;
+  // ---- offside marks (OffsideRef): taken at the moment of a pass; uniform branch, only in cycles with a kick ----
+  if (kick_ballot && !dead) {
+    m.offside = 0u;  // whoever kicks: the old marks are void
+    const bool exempt = mode_at_kick == S2D_PM_KICK_IN || mode_at_kick == S2D_PM_CORNER_KICK || mode_at_kick == S2D_PM_GOAL_KICK;
+    if (kick_l != kick_r && !exempt) {
+      // in the attackers' direction (x mirrored for the right team): beyond the ball, the half-way line and the
+      // second-last defender = offside
+      const bool att_left = kick_l;
+      const float sgn = att_left ? 1.0f : -1.0f;
+      const bool defender = active && left != att_left;
+      const float v = defender ? sgn * p.px : -3.0e38f;
+      const float last = butterfly_max(v);
+      const int who = __ffs(__ballot_sync(full, defender && v == last)) - 1;
+      const float second = butterfly_max(lane == who ? -3.0e38f : v);
+      const float line_x = fmaxf(fmaxf(second, sgn * p.bx), 0.0f);
+      const bool marked = active && left == att_left && ((kick_ballot >> lane) & 1u) == 0u && sgn * p.px > line_x;
+      m.offside = __ballot_sync(full, marked);
+    }
+  }
 
   // ---- move ----
   const float pbx = p.bx, pby = p.by;
@@ -450,6 +479,7 @@ __device__ __forceinline__ bool fg_cycle(Episode& p, Match& m, const KernelParam
     const unsigned touch = __ballot_sync(full, (hit & 2) != 0);
     const bool hit_l = (touch & left_lanes) != 0, hit_r = (touch & ~left_lanes) != 0;
     if (hit_l != hit_r) m.last_touch = hit_l ? S2D_SIDE_LEFT : S2D_SIDE_RIGHT;
+    if (m.offside && (touch & ((m.offside & left_lanes) ? ~left_lanes : left_lanes))) m.offside = 0u;  // the defenders got the ball
   }
 
   // ---- referee (uniform across the warp) ----
@@ -458,7 +488,26 @@ __device__ __forceinline__ bool fg_cycle(Episode& p, Match& m, const KernelParam
   bool kick_off = false;
   const float line = sp.pitch_half_length() + sp.ball_size();
   const float side_line = sp.pitch_half_width() + sp.ball_size();
-  if (!dead && !(fabsf(p.bx) > line || fabsf(p.by) > side_line)) {
+  bool offside_called = false;
+  if (!dead && m.offside) {  // a marked player within 2.5 m of the ball takes part in play: free kick where it stands
+    const float ox = p.px - p.bx, oy = p.py - p.by;
+    const unsigned part = __ballot_sync(full, ((m.offside >> lane) & 1u) != 0u && ox * ox + oy * oy < kFgOffsideArea * kFgOffsideArea);
+    if (part) {
+      const int who = __ffs(part) - 1;
+      const float fx = __shfl_sync(full, p.px, who), fy = __shfl_sync(full, p.py, who);
+      m.mode = S2D_PM_FREE_KICK;
+      m.side = who < pps ? S2D_SIDE_RIGHT : S2D_SIDE_LEFT;
+      m.timer = 0;
+      p.bx = clampf(-sp.pitch_half_length(), fx, sp.pitch_half_length());
+      p.by = clampf(-sp.pitch_half_width(), fy, sp.pitch_half_width());
+      p.bvx = 0.0f;
+      p.bvy = 0.0f;
+      offside_called = true;
+    }
+  }
+  if (offside_called) {
+    // (the ball was re-placed inside the pitch: nothing else to rule on this cycle)
+  } else if (!dead && !(fabsf(p.bx) > line || fabsf(p.by) > side_line)) {
     // ball inside the field: every ruling below needs it beyond a line, so there is nothing to decide (the common case)
   } else if (!dead) {
     const float bx = p.bx, by = p.by;
@@ -516,6 +565,7 @@ __device__ __forceinline__ bool fg_cycle(Episode& p, Match& m, const KernelParam
     if (active) fg_place_player(p, P, gid, m.episode, lane, pps, m.score_l + m.score_r);
     p.bx = p.by = p.bvx = p.bvy = 0.0f;
   }
+  if (m.mode != S2D_PM_PLAY_ON) m.offside = 0u;  // marks live only while play goes on
   if (active) update_stamina(p, sp);
   m.cycle += 1u;
   reward = static_cast<float>(goal_l - goal_r) * 10.0f + (bx_phys - pbx) * 0.01f;
@@ -544,6 +594,7 @@ __device__ __forceinline__ void fg_load(const KernelParams& P, const FgLayout& L
   p.bx = ball.x; p.by = ball.y; p.bvx = ball.z; p.bvy = ball.w;
   m.ep_return = ef.x;
   m.sep = ef.y;
+  m.offside = __float_as_uint(ef.z);
   m.step_number = static_cast<int>(ei.x); m.cycle = ei.y; m.episode = ei.z;
   m.mode = ei.w & 0xff; m.side = (ei.w >> 8) & 3; m.last_touch = (ei.w >> 10) & 3; m.timer = (ei.w >> 12) & 0xff;
   m.done_flag = (ei.w >> 21) & 1;
@@ -562,7 +613,7 @@ __device__ __forceinline__ void fg_store(const KernelParams& P, const FgLayout& 
   }
   if (lane == 0) {
     *(reinterpret_cast<float4*>(base + L.eb()) + env) = make_float4(p.bx, p.by, p.bvx, p.bvy);
-    *(reinterpret_cast<float4*>(base + L.ef()) + env) = make_float4(m.ep_return, m.sep, 0.0f, 0.0f);
+    *(reinterpret_cast<float4*>(base + L.ef()) + env) = make_float4(m.ep_return, m.sep, __uint_as_float(m.offside), 0.0f);
     const uint32_t packed = static_cast<uint32_t>(m.mode) | (static_cast<uint32_t>(m.side) << 8) |
                             (static_cast<uint32_t>(m.last_touch) << 10) | (static_cast<uint32_t>(m.timer) << 12) |
                             (ball_collided ? 1u << 20 : 0u) | (m.done_flag ? 1u << 21 : 0u);

@@ -82,13 +82,20 @@ extern "C" {
  *     goal line  crossed elsewhere: last touched by the defending side -> CornerKick for the attackers at
  *                (+-(half_length - 1), +-(half_width - 1)); else GoalKick for the defenders at (+-(half_length - 5.5), +-9.16)
  *     side line  |y| > pitch_half_width + ball_size -> KickIn for the side that did not touch it last, ball on the line
- *     dead ball  (KickOff, KickIn, CornerKick, GoalKick): the ball rests and takes no part in collisions; only the awarded
+ *     dead ball  (KickOff, KickIn, CornerKick, GoalKick, FreeKick): the ball rests and takes no part in collisions; only the awarded
  *                side's kicks count, the first one resumes PlayOn; after 100 cycles without it play resumes anyway.
  *     last touch = side of the last kicker(s) / of the player(s) the ball collided with (unchanged if both sides did).
  *     clearance  while the ball is dead, after the players have moved, every player of the side that does NOT take the
  *                kick and stands closer than 9.15 m to the ball is placed on that circle (on the line ball -> player; a
  *                player exactly on the ball goes towards its own goal) with velocity zero (Referee::clearPlayersFromBall).
- *     Not modelled: AfterGoal pause, offside, fouls, tackle, catch; players are not confined to their half at kick-off.
+ *     offside    (OffsideRef) when ONE team kicks the ball in PlayOn - not the kick that takes a kick-in, corner kick or
+ *                goal kick - its players other than the kickers who are, in their direction of attack, beyond the ball,
+ *                the half-way line and the second-last opponent (positions before that cycle's move) are marked; any
+ *                kick replaces the marks, the other team touching the ball or a dead ball clears them.  A marked player
+ *                closer than 2.5 m (offside_active_area_size) to the ball after the collisions -> FreeKick for the other
+ *                team with the ball where that player stands (lowest player index if several), nothing else is ruled
+ *                on in that cycle.
+ *     Not modelled: AfterGoal pause, fouls, tackle, catch; players are not confined to their half at kick-off.
  *     Heterogeneous player types: s2d_set_player_types.
  *   Reward (left team's view) per cycle: 10 * (goals by left - goals by right) + 0.01 * (ball x after physics - before).
  *   Observation: 120 floats = ball {x/52.5, y/34, vx/3, vy/3}, then per player {x/52.5, y/34, vx, vy, body/180}

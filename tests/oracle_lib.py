@@ -124,16 +124,16 @@ class OracleSim:
         return out
 
     def get_state_fg(self, i=None):
-        """FULLGAME: [np*12 + 5 + 11] doubles per env (layout: s2do_get_state_fg)."""
+        """FULLGAME: [np*12 + 5 + 12] doubles per env (layout: s2do_get_state_fg)."""
         if i is None:
             return np.stack([self.get_state_fg(j) for j in range(self.n)])
         np_ = 2 * int(self.cfg.players_per_side)
-        out = np.zeros(np_ * 12 + 16, np.float64)
+        out = np.zeros(np_ * 12 + 17, np.float64)
         assert self.L.s2do_get_state_fg(self.h, int(i), _ptr(out)) == out.size
         return out
 
     def set_state_fg(self, states):
-        """FULLGAME: overwrite every env's state from an [N, np*12+16] array (layout of get_state_fg)."""
+        """FULLGAME: overwrite every env's state from an [N, np*12+17] array (layout of get_state_fg)."""
         st = np.ascontiguousarray(states, dtype=np.float64)
         for i in range(self.n):
             self.L.s2do_set_state_fg(self.h, i, _ptr(st[i]))

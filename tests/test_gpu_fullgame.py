@@ -36,11 +36,11 @@ def swarm_policy(obs, np_players, rng=None, random_frac=0.0):
 
 
 def gpu_state_fg(env):
-    """[N, np*12 + 16] float64 in the layout of s2do_get_state_fg"""
+    """[N, np*12 + 17] float64 in the layout of s2do_get_state_fg"""
     pl = {k: v.cpu().numpy() for k, v in env.fullgame_planes().items()}
     n, p = env.num_envs, env.num_players
     pps = p // 2
-    out = np.zeros((n, p * 12 + 16))
+    out = np.zeros((n, p * 12 + 17))
     players = out[:, :p * 12].reshape(n, p, 12)
     players[:, :, 0:4] = pl["pa"]
     players[:, :, 4:8] = pl["pb"]
@@ -64,6 +64,7 @@ def gpu_state_fg(env):
     out[:, k + 13] = (ei[:, 3] >> 10) & 3
     out[:, k + 14] = pl["ef"][:, 0]
     out[:, k + 15] = (ei[:, 3] >> 21) & 1
+    out[:, k + 16] = pl["ef"][:, 2].copy().view(np.uint32)  # offside marks: a bit mask kept in a float slot
     return out
 
 
@@ -235,6 +236,65 @@ def test_fullgame_referee_and_collision_cases():
     snap = env.export_env(4)
     assert (snap.left_score, snap.right_score, snap.num_players) == (1, 0, 22)
     assert snap.players[11].side == 2 and snap.players[11].uniform_number == 1
+
+
+def test_fullgame_offside():
+    """OffsideRef: a pass marks the team-mates beyond the ball, the half-way line and the second-last defender; a marked
+    player within 2.5 m of the ball gives the defenders a free kick where it stands.  Onside receiver, a pass from a
+    kick-in and a ball won back by the defenders do not."""
+    n = 4
+    env = Soccer2DVecEnv(n, scenario="fullgame", device="cuda:0", seed=13, half_time_cycles=1000)
+    sim = OL.OracleSim(env.cfg, "f32")
+    env.reset_torch()
+    sim.reset()
+    pl = env.fullgame_planes()
+
+    def put_ball(i, x, y, vx, vy, mode, side, touch):
+        sim.L.s2do_set_ball_fg(sim.h, i, x, y, vx, vy, mode, side, touch)
+        pl["ball"][i] = torch.tensor([x, y, vx, vy], device="cuda")
+        pl["ei"][i, 3] = mode | (side << 8) | (touch << 10)
+
+    def put_player(i, j, x, y, body):
+        sim.L.s2do_set_player_fg(sim.h, i, j, x, y, 0.0, 0.0, body)
+        pl["pa"][i, j] = torch.tensor([x, y, 0.0, 0.0], device="cuda")
+        pl["pb"][i, j, 0] = body
+
+    for i in range(n):
+        put_ball(i, 10.5, 0.0, 0.0, 0.0, 4 if i == 2 else 2, 1 if i == 2 else 0, 0)  # env 2: kick-in for the left team
+        put_player(i, 3, 10.0, 0.0, 0.0)                       # the passer
+        put_player(i, 9, 25.0 if i == 1 else 45.0, 5.0, 0.0)   # the receiver: behind / beyond the second-last defender
+    put_player(3, 15, 30.0, 20.0, 180.0)                       # env 3: a defender who will win the ball
+    k = 22 * 12
+    act = np.zeros((n, 1, 22, 4), np.float32)
+    act[:, 0, 3, :3] = [3, 100, 0]
+
+    def step():
+        env.step_torch(torch.from_numpy(act))
+        sim.step(act.reshape(n, -1))
+        same_step(env, sim)
+        g = gpu_state_fg(env)
+        assert np.array_equal(g, sim.get_state_fg())
+        return g
+
+    g = step()  # the pass
+    assert g[:, k + 8].tolist() == [2, 2, 2, 2]                # play on everywhere (the kick-in was taken)
+    assert g[:, k + 16].tolist() == [1 << 9, 0, 0, 1 << 9]     # receiver marked, onside, exempt restart, marked
+    act[:] = 0
+    # the ball reaches the receiver (envs 0-2) / the defender (env 3), who kicks it on
+    for i in range(3):
+        put_ball(i, 44.0 if i != 1 else 24.0, 5.0, 0.0, 0.0, 2, 0, 1)
+    put_ball(3, 29.5, 20.0, 0.0, 0.0, 2, 0, 1)
+    act[3, 0, 15, :3] = [3, 50, 0]
+    g = step()
+    assert (g[0, k + 8], g[0, k + 9], g[0, k + 16]) == (5, 2, 0)   # offside: free kick for the right team ...
+    assert g[0, k:k + 4].tolist() == [45.0, 5.0, 0.0, 0.0]         # ... where the receiver stands
+    assert (g[1, k + 8], g[2, k + 8], g[3, k + 8]) == (2, 2, 2)    # no call
+    assert g[3, k + 16] == 0 and g[3, 15 * 12 + 10] == 1           # the defenders won the ball: the mark is void
+    # the free kick is taken; the left team stays 9.15 m away meanwhile
+    for _ in range(3):
+        g = step()
+    assert g[0, k + 8] == 5 and np.hypot(g[0, 9 * 12] - 45.0, g[0, 9 * 12 + 1] - 5.0) >= 9.15 - 1e-4
+    env.close()
 
 
 def _abi_pm(name):

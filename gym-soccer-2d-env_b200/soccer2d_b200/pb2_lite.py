@@ -74,13 +74,14 @@ Body_GoToPoint = _message("Body_GoToPoint")  # target_point, distance_threshold,
 Body_HoldBall = _message("Body_HoldBall")    # (:748-752)
 Body_Intercept = _message("Body_Intercept")      # save_recovery, face_point (:742-745)
 Body_KickOneStep = _message("Body_KickOneStep")  # target_point, first_speed, force_mode (:747-751)
+Body_SmartKick = _message("Body_SmartKick")      # target_point, first_speed, first_speed_threshold, max_steps (:690-695)
 Body_StopBall = _message("Body_StopBall")        # (:753-754)
 Body_TurnToAngle = _message("Body_TurnToAngle")  # angle (:769-771)
 Body_TurnToBall = _message("Body_TurnToBall")    # cycle (:773-775)
 Body_TurnToPoint = _message("Body_TurnToPoint")  # target_point, cycle (:777-780)
 PlayerAction = _message("PlayerAction", oneof=("dash", "turn", "kick", "body_go_to_point", "body_hold_ball",
                                                "body_kick_one_step", "body_stop_ball", "body_turn_to_angle",
-                                               "body_turn_to_ball", "body_turn_to_point", "body_intercept"))
+                                               "body_turn_to_ball", "body_turn_to_point", "body_intercept", "body_smart_kick"))
 DoMoveBall = _message("DoMoveBall")          # position, velocity              (:1395-1398)
 DoMovePlayer = _message("DoMovePlayer")      # our_side, uniform_number, position, body_direction (:1400-1405)
 DoRecover = _message("DoRecover")            # (:1407)

@@ -18,7 +18,7 @@ Two ways to define a scenario:
   * hooks: a subclass that overrides the reference's four hooks - `action_to_rpc_actions`, `state_to_observation`,
     `check_trainer_observation`, `trainer_reset_actions` - keeps working as it does on the reference: per step the
     hook's PlayerAction (Dash / Turn / Kick / Body_GoToPoint / Body_TurnToPoint / Body_TurnToBall / Body_TurnToAngle /
-    Body_KickOneStep / Body_StopBall / Body_Intercept / Body_HoldBall; `service_pb2` messages or
+    Body_KickOneStep / Body_SmartKick (its first kick) / Body_StopBall / Body_Intercept / Body_HoldBall; `service_pb2` messages or
     soccer2d_b200.pb2_lite ones) becomes one command for the GPU cycle, and the other hooks are fed proto-shaped
     State objects (real `service_pb2.State` when that module is importable, attribute views otherwise).  The physics
     still runs on the GPU; the Python hooks make it the slow, compatible path.
@@ -160,6 +160,9 @@ class Soccer2DEnv(Env):
             cmd[0, 0] = [_abi.CMD_TURN_TO_ANGLE, float(action.body_turn_to_angle.angle), 0.0, 0.0]
         elif which == "body_kick_one_step":
             k = action.body_kick_one_step  # (force_mode semantics: the kick is made even if first_speed cannot be reached)
+            cmd[0, 0] = [_abi.CMD_KICK_ONE_STEP, float(k.target_point.x), float(k.target_point.y), float(k.first_speed)]
+        elif which == "body_smart_kick":
+            k = action.body_smart_kick  # librcsc plans up to max_steps kicks; here the first (and only) one: as KickOneStep
             cmd[0, 0] = [_abi.CMD_KICK_ONE_STEP, float(k.target_point.x), float(k.target_point.y), float(k.first_speed)]
         elif which == "body_stop_ball":
             cmd[0, 0] = [_abi.CMD_STOP_BALL, 0.0, 0.0, 0.0]

@@ -654,8 +654,8 @@ int s2d_set_player_types(S2DHandle h, const S2DPlayerType* types, int n, const u
   return S2D_OK;
 }
 
-int s2d_rollout_mlp(S2DHandle h, const S2DMlpPolicy* policy, int k_substeps, float epsilon, void* actions_out,
-                    void* q_out, void* stream) {
+static int rollout_mlp(S2DHandle h, const S2DMlpPolicy* policy, int k_substeps, float epsilon, void* actions_out,
+                       void* q_out, const TrajOut& traj, void* stream) {
   if (!h) return S2D_ERR_INVALID;
   if (!h->bound) return fail(h, S2D_ERR_UNBOUND, "s2d_bind has not been called");
   const bool shoot = h->cfg.scenario == S2D_SCENARIO_SHOOT;
@@ -672,9 +672,9 @@ int s2d_rollout_mlp(S2DHandle h, const S2DMlpPolicy* policy, int k_substeps, flo
   float* qo = static_cast<float*>(q_out);
 #define S2D_ROLLOUT(SCN)                                                                                             \
   do {                                                                                                               \
-    if (h->cfg.noise) rollout_mlp_kernel<SCN, kVarNoisy><<<h->grid, kBlock, 0, s>>>(h->kp, k_substeps, w, epsilon, ao, qo); \
-    else if (h->default_sp) rollout_mlp_kernel<SCN, kVarDefault><<<h->grid, kBlock, 0, s>>>(h->kp, k_substeps, w, epsilon, ao, qo); \
-    else rollout_mlp_kernel<SCN, kVarRuntime><<<h->grid, kBlock, 0, s>>>(h->kp, k_substeps, w, epsilon, ao, qo);       \
+    if (h->cfg.noise) rollout_mlp_kernel<SCN, kVarNoisy><<<h->grid, kBlock, 0, s>>>(h->kp, k_substeps, w, epsilon, ao, qo, traj); \
+    else if (h->default_sp) rollout_mlp_kernel<SCN, kVarDefault><<<h->grid, kBlock, 0, s>>>(h->kp, k_substeps, w, epsilon, ao, qo, traj); \
+    else rollout_mlp_kernel<SCN, kVarRuntime><<<h->grid, kBlock, 0, s>>>(h->kp, k_substeps, w, epsilon, ao, qo, traj); \
   } while (0)
   if (shoot) S2D_ROLLOUT(S2D_SCENARIO_SHOOT);
   else S2D_ROLLOUT(S2D_SCENARIO_REACHBALL);
@@ -682,6 +682,18 @@ int s2d_rollout_mlp(S2DHandle h, const S2DMlpPolicy* policy, int k_substeps, flo
   S2D_CUDA(h, cudaGetLastError());
   h->env_steps += static_cast<uint64_t>(h->cfg.num_envs) * static_cast<uint64_t>(k_substeps);
   return S2D_OK;
+}
+
+int s2d_rollout_mlp(S2DHandle h, const S2DMlpPolicy* policy, int k_substeps, float epsilon, void* actions_out,
+                    void* q_out, void* stream) {
+  return rollout_mlp(h, policy, k_substeps, epsilon, actions_out, q_out, TrajOut{nullptr, nullptr, nullptr, nullptr}, stream);
+}
+
+int s2d_rollout_mlp_collect(S2DHandle h, const S2DMlpPolicy* policy, int k_substeps, float epsilon,
+                            const S2DTrajectory* t, void* stream) {
+  if (!h) return S2D_ERR_INVALID;
+  if (!t) return fail(h, S2D_ERR_INVALID, "trajectory pointer is NULL");
+  return rollout_mlp(h, policy, k_substeps, epsilon, nullptr, nullptr, TrajOut{t->obs, t->actions, t->reward, t->done}, stream);
 }
 
 int s2d_launch_info(S2DHandle h, int* grid, int* block, int* kernels_per_step) {

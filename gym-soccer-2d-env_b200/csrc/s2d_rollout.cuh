@@ -30,6 +30,14 @@ struct MlpWeights {  // device pointers, torch layout: weight [out][in] row-majo
   int obs_dim, n_actions;
 };
 
+// optional per-cycle output of a rollout (time-major, so that a warp's writes are contiguous): what a replay buffer needs
+struct TrajOut {
+  float* obs;        // [K + 1][N][10]: obs[k] = what the policy saw in cycle k, obs[K] = the final observation
+  uint8_t* actions;  // [K][N]
+  float* reward;     // [K][N]
+  uint8_t* done;     // [K][N]: the episode ended in cycle k (obs[k + 1] then opens the next episode)
+};
+
 struct MlpShared {
   float2 w1[2][4][kMlpHidden + kMlpPad];   // [k-step][t][n] = {W1[n][8k + t], W1[n][8k + t + 4]}
   float2 w2[8][4][kMlpHidden + kMlpPad];   // [k-step][t][n] = {W2[n][8k + 2t], W2[n][8k + 2t + 1]}
@@ -172,7 +180,7 @@ __device__ __forceinline__ void mlp_greedy(MlpShared& s, int warp, int lane, flo
 template <int SCN, int VAR>
 __global__ void __launch_bounds__(kBlock, S2D_ROLLOUT_MIN_BLOCKS)
     rollout_mlp_kernel(const __grid_constant__ KernelParams P, const int K, const MlpWeights W, const float epsilon,
-                       uint8_t* __restrict__ actions_out, float* __restrict__ q_out) {
+                       uint8_t* __restrict__ actions_out, float* __restrict__ q_out, const TrajOut T) {
   constexpr int NT = SCN == S2D_SCENARIO_SHOOT ? 3 : 2;
   using SP = typename VariantSP<VAR>::type;
   const SP sp(P.cc);
@@ -201,6 +209,15 @@ __global__ void __launch_bounds__(kBlock, S2D_ROLLOUT_MIN_BLOCKS)
 #pragma unroll
     for (int f = 0; f < kObsDim; ++f) s.obs[warp][lane][f] = obs_row[f];
     __syncwarp();
+    if (T.obs) {  // the staged rows of the warp, 320 contiguous floats
+      float* dst = T.obs + (static_cast<int64_t>(k) * n + warp_first) * kObsDim;
+      const int rows = static_cast<int>(n - warp_first < 32 ? n - warp_first : 32);
+#pragma unroll
+      for (int m = 0; m < kObsDim; ++m) {
+        const int idx = lane + 32 * m, row = idx / kObsDim;
+        if (row < rows) dst[idx] = s.obs[warp][row][idx - row * kObsDim];
+      }
+    }
     mlp_greedy<NT>(s, warp, lane, k == K - 1 ? q_out : nullptr, warp_first, n);
     __syncwarp();
     int a = s.act[warp][lane];
@@ -209,6 +226,8 @@ __global__ void __launch_bounds__(kBlock, S2D_ROLLOUT_MIN_BLOCKS)
       if (u32_to_unit(w.x) < epsilon) a = u32_to_int(w.y, 0, W.n_actions - 1);
     }
     if (actions_out && valid) actions_out[i * K + k] = static_cast<uint8_t>(a);
+    const float reward_before = out.reward_sum;  // (this cycle's reward is taken out exactly: the sum restarts at 0 ...
+    out.reward_sum = 0.0f;
     int rs;
     if (SCN == S2D_SCENARIO_SHOOT) {
       const float4 tab = __ldg(P.action_table + a);
@@ -217,11 +236,24 @@ __global__ void __launch_bounds__(kBlock, S2D_ROLLOUT_MIN_BLOCKS)
       const float2 tab = __ldg(reinterpret_cast<const float2*>(P.action_table + a) + 1);
       rs = substep<SCN, S2D_ACT_DISCRETE, SP, true>(e, P, sp, gid, i, 0.f, 0.f, tab.x, tab.y, out);
     }
+    const float rw = out.reward_sum;
+    out.reward_sum = reward_before + rw;  // ... and is put back together in the order the step kernel adds it up)
+    if (valid) {
+      const int64_t at = static_cast<int64_t>(k) * n + i;
+      if (T.actions) T.actions[at] = static_cast<uint8_t>(a);
+      if (T.reward) T.reward[at] = rw;
+      if (T.done) T.done[at] = static_cast<uint8_t>(rs != S2D_RESULT_NONE);
+    }
     end_of_episode<SCN>(e, P, sp, gid, i, valid, rs, out);
   }
   if (valid) {
     store_episode(P.state, n, i, e);
     scenario_obs<SCN>(e, obs_row);
+    if (T.obs) {
+      float* dst = T.obs + (static_cast<int64_t>(K) * n + i) * kObsDim;
+#pragma unroll
+      for (int f = 0; f < kObsDim; ++f) dst[f] = obs_row[f];
+    }
     P.reward[i] = out.reward_sum;
     P.done[i] = static_cast<uint8_t>(out.ended != 0);
     P.result[i] = static_cast<uint8_t>(out.last_result());

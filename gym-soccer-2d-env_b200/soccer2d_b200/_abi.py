@@ -8,7 +8,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 # ---- constants (mirror include/soccer2d.h) ----------------------------------------------------------
 S2D_OK, S2D_ERR_INVALID, S2D_ERR_UNBOUND, S2D_ERR_CUDA, S2D_ERR_NO_DEVICE = 0, -1, -2, -3, -4
@@ -105,6 +105,11 @@ class MlpPolicy(C.Structure):
                 ("b3", C.c_void_p), ("hidden", C.c_int32), ("reserved", C.c_int32)]
 
 
+class Trajectory(C.Structure):
+    """S2DTrajectory: optional time-major device buffers for the transitions of a fused rollout"""
+    _fields_ = [("obs", C.c_void_p), ("actions", C.c_void_p), ("reward", C.c_void_p), ("done", C.c_void_p)]
+
+
 # every symbol include/soccer2d.h declares: (restype, argtypes)
 _H = C.c_void_p
 SIGNATURES = {
@@ -134,6 +139,7 @@ SIGNATURES = {
     "s2d_generate_player_types": (C.c_int, [C.c_uint64, C.POINTER(ServerParam), C.POINTER(PlayerType), C.c_int]),
     "s2d_set_player_types": (C.c_int, [_H, C.POINTER(PlayerType), C.c_int, C.POINTER(C.c_uint8)]),
     "s2d_rollout_mlp": (C.c_int, [_H, C.POINTER(MlpPolicy), C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "s2d_rollout_mlp_collect": (C.c_int, [_H, C.POINTER(MlpPolicy), C.c_int, C.c_float, C.POINTER(Trajectory), C.c_void_p]),
 }
 
 # S2D_LIB: alternative build of the same library (kernel tuning experiments); default = the in-tree build

@@ -173,6 +173,39 @@ class DeviceDQN:
                 c.log.append(rep)
         return c.log
 
+    def learn_fused(self, total_steps: int, k: int = 8, report_every: int = 0):
+        """The same training loop with the rollout collected by the fused kernel (s2d_rollout_mlp_collect): one launch
+        plays `k` epsilon-greedy cycles with the current Q-network inside the step kernel and writes the k x N
+        transitions straight into time-major tensors, which are appended to the replay buffer in one go; then
+        k / train_every x gradient_steps gradient steps, as `learn` would have made over those cycles.  TF32
+        Q-values decide the actions (see Soccer2DVecEnv.rollout_mlp)."""
+        c, env = self.cfg, self.env
+        n, dev = env.num_envs, self.device
+        traj = {"obs": torch.empty((k + 1, n, env.obs_dim), device=dev), "actions": torch.empty((k, n), dtype=torch.uint8, device=dev),
+                "reward": torch.empty((k, n), device=dev), "done": torch.empty((k, n), dtype=torch.uint8, device=dev)}
+        last, t0 = env.stats(), time.perf_counter()
+        next_report = report_every
+        for step in range(k, total_steps + 1, k):
+            env.rollout_mlp(mlp_layers(self.q), k, self.epsilon(total_steps), traj=traj)
+            self.buffer.add_batch(traj["obs"][:k].reshape(k * n, -1), traj["actions"].reshape(-1), traj["reward"].reshape(-1),
+                                  traj["obs"][1:].reshape(k * n, -1), traj["done"].reshape(-1).bool())
+            self.env_steps += k
+            if self.buffer.size >= c.learning_starts:
+                for _ in range(max(1, k // c.train_every) * c.gradient_steps):
+                    self.train_step()
+            if report_every and step >= next_report:
+                next_report += report_every
+                now = env.stats()
+                d = {kk: now[kk] - last[kk] for kk in ("episodes", "goals", "outs", "timeouts", "episode_steps", "return_sum")}
+                last = now
+                ep = max(1, d["episodes"])
+                c.log.append({"step": step, "transitions": step * n, "epsilon": round(self.epsilon(total_steps), 3),
+                              "episodes": d["episodes"], "goal_rate": d["goals"] / ep, "out_rate": d["outs"] / ep,
+                              "timeout_rate": d["timeouts"] / ep, "mean_return": d["return_sum"] / ep,
+                              "mean_length": d["episode_steps"] / ep, "wall_s": round(time.perf_counter() - t0, 2)})
+        self._obs.copy_(env.obs)  # what the agent sees next, for rollout_step / evaluate
+        return c.log
+
     @torch.no_grad()
     def evaluate(self, steps: int, fused: bool = False) -> dict:
         """Greedy rollout (the reference's `test()`, dqn_ddpg_stable_baselines3.py:56-75): outcome rates.
@@ -183,6 +216,7 @@ class DeviceDQN:
             layers = mlp_layers(self.q)
             for lo in range(0, steps, 16):
                 self.env.rollout_mlp(layers, min(16, steps - lo))
+            self._obs.copy_(self.env.obs)
         else:
             for _ in range(steps):
                 self.rollout_step(0.0, store=False)

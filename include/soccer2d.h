@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define S2D_ABI_VERSION 7
+#define S2D_ABI_VERSION 8
 
 /* error codes */
 #define S2D_OK 0
@@ -341,6 +341,19 @@ typedef struct S2DMlpPolicy {
 } S2DMlpPolicy;
 int s2d_rollout_mlp(S2DHandle h, const S2DMlpPolicy* policy, int k_substeps, float epsilon, void* actions_out,
                     void* q_out, void* stream);
+
+/* The same rollout as a collector for a replay buffer: every cycle's transition is written out, time-major (device
+ * buffers, each optional).  obs[k] is what the policy saw in cycle k and obs[k + 1] the observation after it; when
+ * done[k] is set that next observation already belongs to the next episode (auto-reset), which is all a TD target
+ * masked by (1 - done) needs. */
+typedef struct S2DTrajectory {
+  float* obs;       /* [k_substeps + 1][num_envs][obs_dim] */
+  uint8_t* actions; /* [k_substeps][num_envs] */
+  float* reward;    /* [k_substeps][num_envs] */
+  uint8_t* done;    /* [k_substeps][num_envs] */
+} S2DTrajectory;
+int s2d_rollout_mlp_collect(S2DHandle h, const S2DMlpPolicy* policy, int k_substeps, float epsilon,
+                            const S2DTrajectory* trajectory, void* stream);
 
 /* Launch geometry actually used (for bench.py's gpu_launches / DESIGN.md): blocks, threads, kernels per step call */
 int s2d_launch_info(S2DHandle h, int* grid, int* block, int* kernels_per_step);

@@ -33,14 +33,14 @@ def test_abi_version_and_struct_sizes_match_the_header(tmp_path):
     assert lib.s2d_abi_version() == _abi.ABI_VERSION
     # ask the C compiler for the truth
     prog = tmp_path / "sizes.c"
-    prog.write_text('#include <stdio.h>\n#include "soccer2d.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %d\\n",'
+    prog.write_text('#include <stdio.h>\n#include "soccer2d.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %d\\n",'
                     "sizeof(S2DServerParam),sizeof(S2DConfig),sizeof(S2DBuffers),sizeof(S2DStats),"
-                    "sizeof(S2DPlayerSnapshot),sizeof(S2DEnvSnapshot),sizeof(S2DPlayerType),sizeof(S2DMlpPolicy),S2D_ABI_VERSION);return 0;}\n")
+                    "sizeof(S2DPlayerSnapshot),sizeof(S2DEnvSnapshot),sizeof(S2DPlayerType),sizeof(S2DMlpPolicy),sizeof(S2DTrajectory),S2D_ABI_VERSION);return 0;}\n")
     exe = tmp_path / "sizes"
     subprocess.run(["gcc", "-I", os.path.dirname(HEADER), str(prog), "-o", str(exe)], check=True)
     got = [int(x) for x in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
     want = [C.sizeof(t) for t in (_abi.ServerParam, _abi.Config, _abi.Buffers, _abi.Stats, _abi.PlayerSnapshot,
-                                  _abi.EnvSnapshot, _abi.PlayerType, _abi.MlpPolicy)] + [_abi.ABI_VERSION]
+                                  _abi.EnvSnapshot, _abi.PlayerType, _abi.MlpPolicy, _abi.Trajectory)] + [_abi.ABI_VERSION]
     assert got == want
 
 

@@ -197,3 +197,45 @@ def test_ddpg_drives_the_turning_action_space():
     trained = agent.evaluate(300)
     assert trained["episodes"] > 1000 and trained["goal_rate"] > random_goal_rate + 0.1, (trained, random_goal_rate)
     env.close()
+
+
+def test_fused_rollout_collects_the_transitions_a_replay_buffer_needs():
+    """s2d_rollout_mlp_collect: obs[k] -> action[k] -> reward[k], done[k], obs[k + 1], time-major.  Replaying the recorded
+    actions through the ordinary step kernel, one cycle per launch, reproduces every recorded tensor bit for bit."""
+    from soccer2d_b200.rollout import mlp_layers
+    torch.manual_seed(1)
+    n, k = 3000 + 11, 6
+    kw = dict(device="cuda:0", seed=8, use_continuous_action=False, action_space_size=16, change_ball_velocity=True, max_steps=40)
+    fused = Soccer2DVecEnv(n, substeps=k, **kw)
+    plain = Soccer2DVecEnv(n, substeps=1, **kw)
+    qnet = QNetwork(10, 16).cuda()
+    fused.reset_torch()
+    plain.reset_torch()
+    traj = {"obs": torch.zeros((k + 1, n, 10), device="cuda"), "actions": torch.zeros((k, n), dtype=torch.uint8, device="cuda"),
+            "reward": torch.zeros((k, n), device="cuda"), "done": torch.zeros((k, n), dtype=torch.uint8, device="cuda")}
+    ended = 0
+    for launch in range(12):
+        first_obs = plain.obs.clone()
+        fused.rollout_mlp(mlp_layers(qnet), k, 0.2, traj=traj)
+        assert torch.equal(traj["obs"][0], first_obs)
+        for j in range(k):
+            plain.step_torch(traj["actions"][j].unsqueeze(1).contiguous())
+            assert torch.equal(traj["obs"][j + 1], plain.obs)
+            assert torch.equal(traj["reward"][j], plain.reward) and torch.equal(traj["done"][j], plain.done_u8)
+        assert torch.equal(fused.state, plain.state) and torch.equal(fused.obs, plain.obs)
+        assert torch.allclose(traj["reward"].sum(dim=0), fused.reward, rtol=1e-5, atol=1e-5)
+        ended += int(traj["done"].sum())
+    assert ended == fused.stats()["episodes"] > n
+    fused.close()
+    plain.close()
+
+
+def test_dqn_learns_from_fused_collection():
+    env = Soccer2DVecEnv(4096, device="cuda:0", seed=0, terminal_obs=True, **KW)
+    agent = DeviceDQN(env, DQNConfig(seed=0, learning_starts=1 << 15, lr=5e-4, eps_fraction=0.5))
+    log = agent.learn_fused(1504, k=8, report_every=752)
+    assert len(log) == 2 and log[-1]["transitions"] == 1504 * 4096
+    trained = agent.evaluate(400, fused=True)
+    assert trained["episodes"] > 4096 and trained["goal_rate"] > 0.6, trained
+    agent.rollout_step(0.0, store=False)  # the unfused path carries on from the fused one's observation
+    env.close()

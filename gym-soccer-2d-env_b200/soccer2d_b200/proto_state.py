@@ -30,9 +30,10 @@ def _norm_deg(d):
     return d - 360.0 if d > 180.0 else d + 360.0 if d < -180.0 else d
 
 
-def _player(p, ball, ident, kickable_area):
+def _player(p, ball, ident, kickable_area, type_id=0):
     dx, dy = ball[0] - p.x, ball[1] - p.y
     return {
+        "type_id": int(type_id),
         "position": _vec(p.x, p.y), "seen_position": _vec(p.x, p.y), "velocity": _vec(p.vx, p.vy),
         "seen_velocity": _vec(p.vx, p.vy), "id": ident, "side": SIDE_NAMES[p.side], "uniform_number": int(p.uniform_number),
         "is_goalie": p.uniform_number == 1, "body_direction": float(p.body_direction),
@@ -41,10 +42,13 @@ def _player(p, ball, ident, kickable_area):
     }
 
 
-def state_dict(snap: _abi.EnvSnapshot, unum: int = 1, side: int = 1, kickable_area: float = 1.085) -> dict:
+def state_dict(snap: _abi.EnvSnapshot, unum: int = 1, side: int = 1, kickable_area: float = 1.085,
+               type_of_player=None) -> dict:
     """proto `State` (as a dict) seen by player `unum` of `side` (1 = LEFT, 2 = RIGHT) in full-state mode: the
-    world model is the true state, all *_count fields are 0 (just seen)."""
+    world model is the true state, all *_count fields are 0 (just seen).  `type_of_player[j]`: the heterogeneous type
+    of snapshot player j (Player.type_id / Self.type_id, idl/service.proto:174, :216); default 0."""
     players = [snap.players[j] for j in range(snap.num_players)]
+    tid = {id(p): (int(type_of_player[j]) if type_of_player is not None else 0) for j, p in enumerate(players)}
     me = next((p for p in players if p.side == side and p.uniform_number == unum), None)
     if me is None:
         raise ValueError(f"no player {unum} on side {side} in this env")
@@ -68,17 +72,17 @@ def state_dict(snap: _abi.EnvSnapshot, unum: int = 1, side: int = 1, kickable_ar
             "body_direction": float(me.body_direction), "face_direction": float(me.body_direction),
             "is_kicking": bool(me.kicked), "dist_from_ball": dist, "angle_from_ball": _norm_deg(ang + 180.0),
             "stamina": float(me.stamina), "is_kickable": dist <= kickable_area, "recovery": float(me.recovery),
-            "stamina_capacity": float(me.stamina_capacity), "effort": float(me.effort),
+            "stamina_capacity": float(me.stamina_capacity), "effort": float(me.effort), "type_id": tid[id(me)],
         },
         "ball": {
             "position": _vec(ball[0], ball[1]), "relative_position": _vec(dx, dy), "seen_position": _vec(ball[0], ball[1]),
             "velocity": _vec(ball[2], ball[3]), "seen_velocity": _vec(ball[2], ball[3]), "dist_from_self": dist,
             "angle_from_self": ang,
         },
-        "teammates": [_player(p, ball, ident[id(p)], kickable_area) for p in mates],
-        "opponents": [_player(p, ball, ident[id(p)], kickable_area) for p in opps],
-        "our_players_dict": {int(p.uniform_number): _player(p, ball, ident[id(p)], kickable_area) for p in mates + [me]},
-        "their_players_dict": {int(p.uniform_number): _player(p, ball, ident[id(p)], kickable_area) for p in opps},
+        "teammates": [_player(p, ball, ident[id(p)], kickable_area, tid[id(p)]) for p in mates],
+        "opponents": [_player(p, ball, ident[id(p)], kickable_area, tid[id(p)]) for p in opps],
+        "our_players_dict": {int(p.uniform_number): _player(p, ball, ident[id(p)], kickable_area, tid[id(p)]) for p in mates + [me]},
+        "their_players_dict": {int(p.uniform_number): _player(p, ball, ident[id(p)], kickable_area, tid[id(p)]) for p in opps},
         "our_goalie_uniform_number": 1, "their_goalie_uniform_number": 1 if opps else 0,
         "kickable_teammate_id": ident[id(kick_mates[0])] if kick_mates else 0,
         "kickable_opponent_id": ident[id(kick_opps[0])] if kick_opps else 0,

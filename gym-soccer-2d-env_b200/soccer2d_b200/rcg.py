@@ -5,6 +5,7 @@ the path.  Input: the `EnvSnapshot`s of `Soccer2DVecEnv.export_env(i)`, one per 
 Layout of a cycle (rcssserver's logger, version 4/5 text format):
     (playmode <t> <name>)                      when the mode changes
     (team <t> <left> <right> <score_l> <score_r>)   when a score changes
+    (player_type (id 0)(player_speed_max ..)(stamina_inc_max ..) ...)   header, one per heterogeneous type (optional)
     (show <t> ((b) x y vx vy)
               ((l 1) <type> <state> x y vx vy body neck (v h 180) (s stamina effort recovery capacity)
                      (c kick dash turn catch move tneck view say tackle pointto attention)) ...)
@@ -23,12 +24,21 @@ def _f(v: float) -> str:
 
 
 class RcgWriter:
-    def __init__(self, path: str, left: str = "left", right: str = "right"):
+    def __init__(self, path: str, left: str = "left", right: str = "right", player_types: list | None = None,
+                 type_of_player=None):
+        """player_types: the dicts of `proto_state.player_type_dict` (one `(player_type ...)` header line each, as
+        rcssserver logs its heterogeneous types); type_of_player[j]: the type id shown for snapshot player j."""
         self.f = open(path, "w")
         self.left, self.right = left, right
         self.last_mode = None
         self.last_score = None
+        self.type_of_player = type_of_player
         self.f.write("ULG5\n")
+        for t in player_types or []:
+            fields = ("id", "player_speed_max", "stamina_inc_max", "player_decay", "inertia_moment", "dash_power_rate",
+                      "player_size", "kickable_margin", "kick_rand", "extra_stamina", "effort_max", "effort_min",
+                      "kick_power_rate")
+            self.f.write("(player_type " + "".join(f"({k} {_f(t[k]) if k != 'id' else int(t[k])})" for k in fields) + ")\n")
 
     def _playmode_name(self, snap) -> str:
         name = PLAYMODE_NAMES.get(int(snap.game_mode_type), "play_on")
@@ -53,7 +63,8 @@ class RcgWriter:
             state = STATE_STAND | (STATE_KICK if p.kicked else 0) | (STATE_GOALIE if p.uniform_number == 1 else 0)
             state |= STATE_PLAYER_COLLIDE if p.collided else 0
             side = "l" if p.side == 1 else "r"
-            parts.append(f" (({side} {int(p.uniform_number)}) 0 {hex(state)} {_f(p.x)} {_f(p.y)} {_f(p.vx)} {_f(p.vy)} "
+            tid = int(self.type_of_player[j]) if self.type_of_player is not None else 0
+            parts.append(f" (({side} {int(p.uniform_number)}) {tid} {hex(state)} {_f(p.x)} {_f(p.y)} {_f(p.vx)} {_f(p.vy)} "
                          f"{_f(p.body_direction)} 0 (v h 180) (s {_f(p.stamina)} {_f(p.effort)} {_f(p.recovery)} "
                          f"{_f(p.stamina_capacity)}) (c 0 0 0 0 0 0 0 0 0 0 0))")
         parts.append(")\n")

@@ -415,7 +415,8 @@ class Soccer2DVecEnv(_VecEnvBase):
         (idl/service.proto:306-359); `json_format.ParseDict(d, service_pb2.State())` turns it into the message."""
         from .proto_state import state_dict
         return state_dict(self.export_env(i), unum=unum, side=side,
-                          kickable_area=self.cfg.sp.player_size + self.cfg.sp.ball_size + self.cfg.sp.kickable_margin)
+                          kickable_area=self.cfg.sp.player_size + self.cfg.sp.ball_size + self.cfg.sp.kickable_margin,
+                          type_of_player=self.type_of_player)
 
     def state_planes(self):
         """One-player scenarios: views of the SoA planes (float32 [4, N, 4], int32 [N, 4]) - layout in DESIGN.md."""

@@ -50,6 +50,7 @@ print(json.dumps({
     "self_side_is_left": wm.self.side == pb2.Side.LEFT, "stamina": wm.self.stamina, "n_mates": len(wm.teammates),
     "n_opps": len(wm.opponents), "left_score": wm.left_team_score, "ball_x": wm.ball.position.x, "ball_vy": wm.ball.velocity.y,
     "kickable_mate": wm.kickable_teammate_existance, "mate_unum": wm.teammates[0].uniform_number,
+    "type_ids": [wm.self.type_id, wm.teammates[0].type_id, wm.opponents[0].type_id],
     "our_dict": sorted(wm.our_players_dict), "their_dict": sorted(wm.their_players_dict),
     "obs": [float(v) for v in obs], "done": bool(done), "reward": float(reward), "result": info["result"]}))
 """
@@ -63,7 +64,7 @@ def test_state_dict_parses_into_the_reference_proto_and_feeds_its_hooks():
     from oracle import soccer2d_oracle as O
 
     snap = _snapshot()
-    payload = {"player": state_dict(snap, unum=1, side=1), "trainer": trainer_state_dict(snap)}
+    payload = {"player": state_dict(snap, unum=1, side=1, type_of_player=[0, 7, 3]), "trainer": trainer_state_dict(snap)}
     r = subprocess.run([sys.executable, "-c", _REF_SIDE, os.path.join(H.ROOT, "tests", "golden", "_shims"), REF],
                        input=json.dumps(payload), capture_output=True, text=True, env={**os.environ, "PYTHONPATH": ""})
     assert r.returncode == 0, r.stderr[-2000:]
@@ -73,7 +74,7 @@ def test_state_dict_parses_into_the_reference_proto_and_feeds_its_hooks():
     assert (got["n_mates"], got["n_opps"], got["left_score"]) == (1, 1, 1)
     assert got["ball_x"] == 10.5 and got["ball_vy"] == 0.125
     assert got["kickable_mate"] and got["mate_unum"] == 2  # player 2 stands next to the ball
-    assert got["our_dict"] == [1, 2] and got["their_dict"] == [1]
+    assert got["our_dict"] == [1, 2] and got["their_dict"] == [1] and got["type_ids"] == [0, 7, 3]
     # the reference's own observation / reward code on the exported State == the simulator's formulas
     want = O.build_obs(10.5, -3.25, 0.5, 0.125, -20.0, 4.0, 135.0)
     assert np.allclose(got["obs"], want, rtol=0, atol=1e-12)

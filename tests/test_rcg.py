@@ -35,3 +35,24 @@ def test_rcg_writer_format(tmp_path):
     assert "(playmode 2 play_on)" in lines and "(team 3 b200_l b200_r 1 0)" in lines
     assert "((l 1) 0 0xb -10 0.5" in show[0]  # stand | kick | goalie
     assert all(l.count("(") == l.count(")") for l in lines[1:])
+
+
+def test_rcg_writer_logs_heterogeneous_player_types(tmp_path):
+    import ctypes as C
+
+    from soccer2d_b200.proto_state import player_type_dict
+    lib = _abi.load()
+    sp = _abi.ServerParam()
+    assert lib.s2d_default_server_param(C.byref(sp)) == 0
+    types = (_abi.PlayerType * 18)()
+    assert lib.s2d_generate_player_types(3, C.byref(sp), types, 18) == 0
+    path = tmp_path / "hetero.rcg"
+    with RcgWriter(str(path), player_types=[player_type_dict(k, types[k].as_dict(), sp) for k in range(18)],
+                   type_of_player=[0, 5]) as w:
+        w.write(_snap(1, 2, 0, 0))
+    lines = path.read_text().splitlines()
+    heads = [l for l in lines if l.startswith("(player_type ")]
+    assert len(heads) == 18 and heads[0].startswith("(player_type (id 0)(player_speed_max 1.05)(stamina_inc_max 45)(player_decay 0.4)")
+    assert all(l.count("(") == l.count(")") for l in heads)
+    show = [l for l in lines if l.startswith("(show ")][0]
+    assert "((l 1) 0 0x" in show and "((r 1) 5 0x" in show

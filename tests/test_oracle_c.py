@@ -273,3 +273,52 @@ def test_intercept_meets_a_rolling_ball_sooner_than_chasing_it():
             if reached[i] is None and np.hypot(st[i, 9] - st[i, 0], st[i, 10] - st[i, 1]) <= 1.085:
                 reached[i] = t
     assert reached[0] is not None and (reached[1] is None or reached[0] < reached[1]), reached
+
+
+def test_fullgame_invariants_with_player_types_and_referee():
+    """11 v 11 in the f64 build with rcssserver's heterogeneous player types, swarm play for 400 cycles: the physical
+    limits of every player's own type hold, the referee's state stays consistent (dead ball inside the pitch, offside
+    marks from one team only and only while play goes on, nobody of the other side within 9.15 m of a dead ball)."""
+    import ctypes as C
+    from test_gpu_fullgame import swarm_policy  # (pure numpy helper; the module's GPU tests are not collected here)
+    n, p = 24, 22
+    lib = _abi.load()
+    cfg = H.make_config(n, "command", scenario=_abi.SCENARIO_FULLGAME, seed=5, half_time_cycles=150)
+    types = (_abi.PlayerType * 18)()
+    assert lib.s2d_generate_player_types(9, C.byref(cfg.sp), types, 18) == 0
+    rng = np.random.default_rng(3)
+    type_of = rng.integers(1, 18, size=p)
+    type_of[0] = type_of[11] = 0
+    sim = OL.OracleSim(cfg, "f64")
+    sim.set_player_types(types, 18, type_of)
+    sim.reset()
+    decay = np.array([types[t].player_decay for t in type_of])
+    emax = np.array([types[t].effort_max for t in type_of])
+    emin = np.array([types[t].effort_min for t in type_of])
+    k = p * 12
+    seen_modes, offside_calls, marks_seen = set(), 0, 0
+    for t in range(400):
+        act = swarm_policy(sim.obs, p, rng, random_frac=0.2)
+        sim.step(act.reshape(n, -1))
+        s = sim.get_state_fg()
+        P = s[:, :k].reshape(n, p, 12)
+        assert np.isfinite(s).all()
+        hit = P[:, :, 9] != 0  # (a collision multiplies the velocity by -0.1 afterwards: still below the limit)
+        assert (np.hypot(P[:, :, 2], P[:, :, 3]) <= 1.05 * decay[None, :] + 1e-9).all() or hit.any()
+        assert (P[:, :, 5] >= 0).all() and (P[:, :, 5] <= 8000.0).all()
+        assert (P[:, :, 6] >= emin[None, :] - 1e-9).all() and (P[:, :, 6] <= emax[None, :] + 1e-9).all()
+        assert (np.abs(P[:, :, 4]) <= 180.0).all()
+        mode, side, marks = s[:, k + 8].astype(int), s[:, k + 9].astype(int), s[:, k + 16].astype(np.int64)
+        seen_modes |= set(mode.tolist())
+        dead = (mode != 2) & (mode != 1)
+        assert (np.abs(s[dead, k]) <= 52.5 + 1e-9).all() and (np.abs(s[dead, k + 1]) <= 34.0 + 1e-9).all()
+        assert (marks[mode != 2] == 0).all()
+        left_bits, right_bits = marks & 0x7FF, marks >> 11
+        assert ((left_bits == 0) | (right_bits == 0)).all()
+        marks_seen += int((marks != 0).sum())
+        for i in np.nonzero(dead & (s[:, k + 10] > 0))[0]:  # one cycle after the ruling the other side has been cleared
+            others = P[i, :, 11] != side[i]
+            d = np.hypot(P[i, others, 0] - s[i, k], P[i, others, 1] - s[i, k + 1])
+            assert (d >= 9.15 - 0.61).all()  # (placed on the circle; a player-player collision may then push by < 0.6)
+        offside_calls += int(((mode == 5) & (s[:, k + 10] == 0)).sum())
+    assert {2, 3} <= seen_modes and marks_seen > 0

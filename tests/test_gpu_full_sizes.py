@@ -100,3 +100,30 @@ def test_fullgame_256k_matches_properties_and_oracle_sample():
     assert st["episodes"] == n * (k * launches // 16) == st["goals"] + st["outs"] + st["timeouts"]
     for e in (fused, single, shard):
         e.close()
+
+
+def test_reachball_2_to_the_27_envs_addresses_in_64_bits():
+    """134 M episodes on one GPU (11 GB of state, 5 GB of observations): byte offsets exceed 2^32.  The last thousand
+    envs of the big handle equal a small handle that owns the same global env ids, bit for bit, after fused launches."""
+    n, k, tail = 1 << 27, 4, 1000
+    kw = dict(device="cuda:0", seed=2, substeps=k, use_continuous_action=False, action_space_size=16, change_ball_velocity=True)
+    big = Soccer2DVecEnv(n, **kw)
+    small = Soccer2DVecEnv(tail, env_id_offset=n - tail, **kw)
+    big.reset_torch()
+    small.reset_torch()
+    assert torch.equal(big.obs[n - tail:], small.obs)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    for launch in range(3):
+        act = torch.randint(0, 16, (n, k), dtype=torch.uint8, device="cuda", generator=g)
+        ev[0].record()
+        big.step_torch(act)
+        ev[1].record()
+        small.step_torch(act[n - tail:].contiguous())
+        assert torch.equal(big.obs[n - tail:], small.obs) and torch.equal(big.reward[n - tail:], small.reward)
+    torch.cuda.synchronize()
+    assert big.stats()["env_steps"] == n * k * 3
+    rate = n * k / (ev[0].elapsed_time(ev[1]) * 1e-3)
+    assert rate > 2e10, rate  # K = 4: still HBM-bound, four cycles per 222 bytes
+    big.close()
+    small.close()

@@ -655,29 +655,37 @@ int s2d_set_player_types(S2DHandle h, const S2DPlayerType* types, int n, const u
 }
 
 static int rollout_mlp(S2DHandle h, const S2DMlpPolicy* policy, int k_substeps, float epsilon, void* actions_out,
-                       void* q_out, const TrajOut& traj, void* stream) {
+                       void* q_out, const TrajOut& traj, bool actor, void* stream) {
   if (!h) return S2D_ERR_INVALID;
   if (!h->bound) return fail(h, S2D_ERR_UNBOUND, "s2d_bind has not been called");
   const bool shoot = h->cfg.scenario == S2D_SCENARIO_SHOOT;
-  if (h->cfg.scenario == S2D_SCENARIO_FULLGAME || h->cfg.action_mode != S2D_ACT_DISCRETE || h->cfg.action_space_size > (shoot ? 24 : 16))
+  const int mode = h->cfg.action_mode;
+  if (actor) {
+    if (h->cfg.scenario != S2D_SCENARIO_REACHBALL || (mode != S2D_ACT_CONTINUOUS && mode != S2D_ACT_TURNING))
+      return fail(h, S2D_ERR_INVALID, "s2d_rollout_actor_collect: REACHBALL with Box(1) or Box(4) actions only");
+  } else if (h->cfg.scenario == S2D_SCENARIO_FULLGAME || mode != S2D_ACT_DISCRETE || h->cfg.action_space_size > (shoot ? 24 : 16)) {
     return fail(h, S2D_ERR_INVALID, "s2d_rollout_mlp: REACHBALL with Discrete(n <= 16) or SHOOT with Discrete(n <= 24) actions only");
+  }
   if (!policy || !policy->w1 || !policy->b1 || !policy->w2 || !policy->b2 || !policy->w3 || !policy->b3 || policy->hidden != kMlpHidden)
     return fail(h, S2D_ERR_INVALID, "s2d_rollout_mlp: six weight pointers and hidden = %d are required", kMlpHidden);
   if (k_substeps < 1 || k_substeps > kMaxSubsteps) return fail(h, S2D_ERR_INVALID, "k_substeps must be in 1..%d", kMaxSubsteps);
-  if (!(epsilon >= 0.0f && epsilon <= 1.0f)) return fail(h, S2D_ERR_INVALID, "epsilon must be in [0, 1]");
+  if (!(epsilon >= 0.0f && epsilon <= 1.0f)) return fail(h, S2D_ERR_INVALID, "epsilon / noise must be in [0, 1]");
   DeviceGuard guard(h->cfg.device);
-  const MlpWeights w{policy->w1, policy->b1, policy->w2, policy->b2, policy->w3, policy->b3, kObsDim, h->cfg.action_space_size};
+  const int outputs = actor ? (mode == S2D_ACT_TURNING ? 4 : 1) : h->cfg.action_space_size;
+  const MlpWeights w{policy->w1, policy->b1, policy->w2, policy->b2, policy->w3, policy->b3, kObsDim, outputs};
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   uint8_t* ao = static_cast<uint8_t*>(actions_out);
   float* qo = static_cast<float*>(q_out);
-#define S2D_ROLLOUT(SCN)                                                                                             \
-  do {                                                                                                               \
-    if (h->cfg.noise) rollout_mlp_kernel<SCN, kVarNoisy><<<h->grid, kBlock, 0, s>>>(h->kp, k_substeps, w, epsilon, ao, qo, traj); \
-    else if (h->default_sp) rollout_mlp_kernel<SCN, kVarDefault><<<h->grid, kBlock, 0, s>>>(h->kp, k_substeps, w, epsilon, ao, qo, traj); \
-    else rollout_mlp_kernel<SCN, kVarRuntime><<<h->grid, kBlock, 0, s>>>(h->kp, k_substeps, w, epsilon, ao, qo, traj); \
+#define S2D_ROLLOUT(SCN, ACT)                                                                                         \
+  do {                                                                                                                \
+    if (h->cfg.noise) rollout_mlp_kernel<SCN, kVarNoisy, ACT><<<h->grid, kBlock, 0, s>>>(h->kp, k_substeps, w, epsilon, ao, qo, traj); \
+    else if (h->default_sp) rollout_mlp_kernel<SCN, kVarDefault, ACT><<<h->grid, kBlock, 0, s>>>(h->kp, k_substeps, w, epsilon, ao, qo, traj); \
+    else rollout_mlp_kernel<SCN, kVarRuntime, ACT><<<h->grid, kBlock, 0, s>>>(h->kp, k_substeps, w, epsilon, ao, qo, traj); \
   } while (0)
-  if (shoot) S2D_ROLLOUT(S2D_SCENARIO_SHOOT);
-  else S2D_ROLLOUT(S2D_SCENARIO_REACHBALL);
+  if (actor && mode == S2D_ACT_TURNING) S2D_ROLLOUT(S2D_SCENARIO_REACHBALL, S2D_ACT_TURNING);
+  else if (actor) S2D_ROLLOUT(S2D_SCENARIO_REACHBALL, S2D_ACT_CONTINUOUS);
+  else if (shoot) S2D_ROLLOUT(S2D_SCENARIO_SHOOT, S2D_ACT_DISCRETE);
+  else S2D_ROLLOUT(S2D_SCENARIO_REACHBALL, S2D_ACT_DISCRETE);
 #undef S2D_ROLLOUT
   S2D_CUDA(h, cudaGetLastError());
   h->env_steps += static_cast<uint64_t>(h->cfg.num_envs) * static_cast<uint64_t>(k_substeps);
@@ -686,14 +694,23 @@ static int rollout_mlp(S2DHandle h, const S2DMlpPolicy* policy, int k_substeps, 
 
 int s2d_rollout_mlp(S2DHandle h, const S2DMlpPolicy* policy, int k_substeps, float epsilon, void* actions_out,
                     void* q_out, void* stream) {
-  return rollout_mlp(h, policy, k_substeps, epsilon, actions_out, q_out, TrajOut{nullptr, nullptr, nullptr, nullptr}, stream);
+  return rollout_mlp(h, policy, k_substeps, epsilon, actions_out, q_out, TrajOut{nullptr, nullptr, nullptr, nullptr, nullptr},
+                     false, stream);
 }
 
 int s2d_rollout_mlp_collect(S2DHandle h, const S2DMlpPolicy* policy, int k_substeps, float epsilon,
                             const S2DTrajectory* t, void* stream) {
   if (!h) return S2D_ERR_INVALID;
   if (!t) return fail(h, S2D_ERR_INVALID, "trajectory pointer is NULL");
-  return rollout_mlp(h, policy, k_substeps, epsilon, nullptr, nullptr, TrajOut{t->obs, t->actions, t->reward, t->done}, stream);
+  return rollout_mlp(h, policy, k_substeps, epsilon, nullptr, nullptr, TrajOut{t->obs, t->actions, nullptr, t->reward, t->done},
+                     false, stream);
+}
+
+int s2d_rollout_actor_collect(S2DHandle h, const S2DMlpPolicy* actor, int k_substeps, float noise,
+                              const S2DTrajectory* t, void* stream) {
+  const TrajOut traj = t ? TrajOut{t->obs, nullptr, t->actions_f, t->reward, t->done}
+                         : TrajOut{nullptr, nullptr, nullptr, nullptr, nullptr};
+  return rollout_mlp(h, actor, k_substeps, noise, nullptr, nullptr, traj, true, stream);
 }
 
 int s2d_launch_info(S2DHandle h, int* grid, int* block, int* kernels_per_step) {

@@ -33,7 +33,8 @@ struct MlpWeights {  // device pointers, torch layout: weight [out][in] row-majo
 // optional per-cycle output of a rollout (time-major, so that a warp's writes are contiguous): what a replay buffer needs
 struct TrajOut {
   float* obs;        // [K + 1][N][10]: obs[k] = what the policy saw in cycle k, obs[K] = the final observation
-  uint8_t* actions;  // [K][N]
+  uint8_t* actions;  // [K][N] (Discrete)
+  float* actions_f;  // [K][N][action_dim] (Box: the actor's rollout)
   float* reward;     // [K][N]
   uint8_t* done;     // [K][N]: the episode ended in cycle k (obs[k + 1] then opens the next episode)
 };
@@ -45,6 +46,7 @@ struct MlpShared {
   float b1[kMlpHidden], b2[kMlpHidden], b3[kMlpActions];
   float obs[kBlock / 32][32][20];          // row stride 20: the A-fragment loads hit 32 different banks
   uint8_t act[kBlock / 32][32];
+  float actf[kBlock / 32][32][4];          // the actor's outputs (Box actions), row = episode
 };
 
 __device__ __forceinline__ float to_tf32(float x) {
@@ -64,7 +66,7 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const float (&a)[4], flo
         "r"(__float_as_uint(b.x)), "r"(__float_as_uint(b.y)));
 }
 
-__device__ __forceinline__ void mlp_load_weights(MlpShared& s, const MlpWeights& w) {
+__device__ __forceinline__ void mlp_load_weights(MlpShared& s, const MlpWeights& w, float absent_bias = -3.0e38f) {
   for (int idx = threadIdx.x; idx < 2 * 4 * kMlpHidden; idx += blockDim.x) {
     const int n = idx % kMlpHidden, t = (idx / kMlpHidden) % 4, k = idx / (4 * kMlpHidden);
     const int f0 = 8 * k + t, f1 = f0 + 4;
@@ -84,7 +86,7 @@ __device__ __forceinline__ void mlp_load_weights(MlpShared& s, const MlpWeights&
   for (int idx = threadIdx.x; idx < kMlpHidden; idx += blockDim.x) {
     s.b1[idx] = __ldg(w.b1 + idx);
     s.b2[idx] = __ldg(w.b2 + idx);
-    if (idx < kMlpActions) s.b3[idx] = idx < w.n_actions ? __ldg(w.b3 + idx) : -3.0e38f;  // absent actions never win
+    if (idx < kMlpActions) s.b3[idx] = idx < w.n_actions ? __ldg(w.b3 + idx) : absent_bias;  // (Q: absent actions never win)
   }
 }
 
@@ -171,23 +173,49 @@ __device__ __forceinline__ void mlp_greedy(MlpShared& s, int warp, int lane, flo
   }
 }
 
+// tanh from the kernels' own exponential (s2d_math.cuh): 1 - 2 / (e^(2|x|) + 1), sign restored
+__device__ __forceinline__ float tanh_poly(float x) {
+  const float ax = fminf(fabsf(x), 20.0f);
+  const float t = 1.0f - 2.0f / (exp_poly(2.0f * ax) + 1.0f);
+  return copysignf(t, x);
+}
+
+// the actor's action (tanh of the last layer's first `dim` <= 4 outputs) of every episode of the warp -> s.actf
+__device__ __forceinline__ void mlp_actor(MlpShared& s, int warp, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll 1
+  for (int tile = 0; tile < 2; ++tile) {
+    float q[1][4];
+    mlp_forward_tile<1>(s, s.obs[warp], tile, g, t, q);
+    if (t < 2) {  // columns 2t, 2t + 1 of rows g and g + 8
+      *reinterpret_cast<float2*>(&s.actf[warp][16 * tile + g][2 * t]) = make_float2(tanh_poly(q[0][0]), tanh_poly(q[0][1]));
+      *reinterpret_cast<float2*>(&s.actf[warp][16 * tile + g + 8][2 * t]) = make_float2(tanh_poly(q[0][2]), tanh_poly(q[0][3]));
+    }
+  }
+}
+
 #ifndef S2D_ROLLOUT_MIN_BLOCKS
 #define S2D_ROLLOUT_MIN_BLOCKS 4
 #endif
 
 // K closed-loop cycles of a one-player scenario with Discrete actions (ReachBall: n <= 16, Shoot: n <= 24): observe,
 // Q-network, (epsilon-)greedy action, step.
-template <int SCN, int VAR>
+// ACT = S2D_ACT_DISCRETE: W is a Q-network, `epsilon` the exploration rate.  ACT = S2D_ACT_CONTINUOUS / S2D_ACT_TURNING
+// (ReachBall): W is a DDPG actor (last layer -> tanh -> the Box(1) / Box(4) action) and `epsilon` the half-width of a
+// uniform exploration noise added to every action component before the clip to [-1, 1].
+template <int SCN, int VAR, int ACT = S2D_ACT_DISCRETE>
 __global__ void __launch_bounds__(kBlock, S2D_ROLLOUT_MIN_BLOCKS)
     rollout_mlp_kernel(const __grid_constant__ KernelParams P, const int K, const MlpWeights W, const float epsilon,
                        uint8_t* __restrict__ actions_out, float* __restrict__ q_out, const TrajOut T) {
   constexpr int NT = SCN == S2D_SCENARIO_SHOOT ? 3 : 2;
+  constexpr bool kActor = ACT != S2D_ACT_DISCRETE;
+  constexpr int kActDim = ACT == S2D_ACT_TURNING ? 4 : 1;
   using SP = typename VariantSP<VAR>::type;
   const SP sp(P.cc);
   __shared__ __align__(16) MlpShared s;
   __shared__ __align__(16) float s_stage[kBlock / 32][32 * kObsDim];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  mlp_load_weights(s, W);
+  mlp_load_weights(s, W, kActor ? 0.0f : -3.0e38f);
   const int64_t i = static_cast<int64_t>(blockIdx.x) * kBlock + threadIdx.x;
   const int64_t n = P.num_envs;
   const bool valid = i < n;
@@ -218,23 +246,45 @@ __global__ void __launch_bounds__(kBlock, S2D_ROLLOUT_MIN_BLOCKS)
         if (row < rows) dst[idx] = s.obs[warp][row][idx - row * kObsDim];
       }
     }
-    mlp_greedy<NT>(s, warp, lane, k == K - 1 ? q_out : nullptr, warp_first, n);
-    __syncwarp();
-    int a = s.act[warp][lane];
-    if (epsilon > 0.0f) {  // exploration: the same counter stream as the turning action's draw (RNG_ACTION)
-      const uint4 w = philox4x32_10(P.seed, gid, e.cycle, RNG_ACTION, 1);
-      if (u32_to_unit(w.x) < epsilon) a = u32_to_int(w.y, 0, W.n_actions - 1);
-    }
-    if (actions_out && valid) actions_out[i * K + k] = static_cast<uint8_t>(a);
-    const float reward_before = out.reward_sum;  // (this cycle's reward is taken out exactly: the sum restarts at 0 ...
-    out.reward_sum = 0.0f;
+    int a = 0;
     int rs;
-    if (SCN == S2D_SCENARIO_SHOOT) {
-      const float4 tab = __ldg(P.action_table + a);
-      rs = substep<SCN, S2D_ACT_DISCRETE, SP, true>(e, P, sp, gid, i, tab.x, tab.y, tab.z, tab.w, out);
+    const float reward_before = out.reward_sum;  // (this cycle's reward is taken out exactly: the sum restarts at 0 ...
+    if (!kActor) {
+      mlp_greedy<NT>(s, warp, lane, k == K - 1 ? q_out : nullptr, warp_first, n);
+      __syncwarp();
+      a = s.act[warp][lane];
+      if (epsilon > 0.0f) {  // exploration: the same counter stream as the turning action's draw (RNG_ACTION)
+        const uint4 w = philox4x32_10(P.seed, gid, e.cycle, RNG_ACTION, 1);
+        if (u32_to_unit(w.x) < epsilon) a = u32_to_int(w.y, 0, W.n_actions - 1);
+      }
+      if (actions_out && valid) actions_out[i * K + k] = static_cast<uint8_t>(a);
+      out.reward_sum = 0.0f;
+      if (SCN == S2D_SCENARIO_SHOOT) {
+        const float4 tab = __ldg(P.action_table + a);
+        rs = substep<SCN, S2D_ACT_DISCRETE, SP, true>(e, P, sp, gid, i, tab.x, tab.y, tab.z, tab.w, out);
+      } else {
+        const float2 tab = __ldg(reinterpret_cast<const float2*>(P.action_table + a) + 1);
+        rs = substep<SCN, S2D_ACT_DISCRETE, SP, true>(e, P, sp, gid, i, 0.f, 0.f, tab.x, tab.y, out);
+      }
     } else {
-      const float2 tab = __ldg(reinterpret_cast<const float2*>(P.action_table + a) + 1);
-      rs = substep<SCN, S2D_ACT_DISCRETE, SP, true>(e, P, sp, gid, i, 0.f, 0.f, tab.x, tab.y, out);
+      mlp_actor(s, warp, lane);
+      __syncwarp();
+      float4 av = *reinterpret_cast<const float4*>(s.actf[warp][lane]);
+      if (epsilon > 0.0f) {
+        const uint4 w = philox4x32_10(P.seed, gid, e.cycle, RNG_ACTION, 2);
+        av.x = clampf(-1.0f, av.x + epsilon * u11(w.x), 1.0f);
+        av.y = clampf(-1.0f, av.y + epsilon * u11(w.y), 1.0f);
+        av.z = clampf(-1.0f, av.z + epsilon * u11(w.z), 1.0f);
+        av.w = clampf(-1.0f, av.w + epsilon * u11(w.w), 1.0f);
+      }
+      if (T.actions_f && valid) {
+        float* dst = T.actions_f + (static_cast<int64_t>(k) * n + i) * kActDim;
+        dst[0] = av.x;
+        if (kActDim == 4) { dst[1] = av.y; dst[2] = av.z; dst[3] = av.w; }
+      }
+      out.reward_sum = 0.0f;
+      rs = substep<SCN, ACT, SP, true>(e, P, sp, gid, i, av.x, kActDim == 4 ? av.y : 0.f, kActDim == 4 ? av.z : 0.f,
+                                       kActDim == 4 ? av.w : 0.f, out);
     }
     const float rw = out.reward_sum;
     out.reward_sum = reward_before + rw;  // ... and is put back together in the order the step kernel adds it up)

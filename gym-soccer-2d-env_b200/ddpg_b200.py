@@ -28,12 +28,16 @@ def main():
     ap.add_argument("--report-every", type=int, default=500)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--device", default="cuda:0")
+    ap.add_argument("--fused", type=int, default=0, metavar="K",
+                    help="collect the rollout with the actor inside the step kernel, K cycles per launch (0: torch actor)")
     args = ap.parse_args()
     env = Soccer2DVecEnv(args.envs, device=args.device, seed=args.seed, terminal_obs=True, **KWARGS)
     agent = DeviceDDPG(env, DDPGConfig(seed=args.seed, learning_starts=min(1 << 16, 16 * args.envs)))
-    for rep in agent.learn(args.steps, report_every=args.report_every):
+    log = (agent.learn_fused(args.steps, k=args.fused, report_every=args.report_every) if args.fused
+           else agent.learn(args.steps, report_every=args.report_every))
+    for rep in log:
         print(json.dumps(rep), flush=True)
-    print(json.dumps({"test": agent.evaluate(args.test_steps)}), flush=True)
+    print(json.dumps({"test": agent.evaluate(args.test_steps, fused=bool(args.fused))}), flush=True)
     env.close()
 
 

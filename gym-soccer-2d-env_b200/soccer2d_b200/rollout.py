@@ -420,9 +420,47 @@ class DeviceDDPG:
                               "mean_return": d["return_sum"] / ep, "wall_s": round(time.perf_counter() - t0, 2)})
         return c.log
 
+    def learn_fused(self, total_steps: int, k: int = 8, report_every: int = 0):
+        """`learn` with the rollout collected by the fused kernel (Soccer2DVecEnv.rollout_actor): one launch plays `k`
+        cycles with the current actor inside the step kernel (uniform exploration noise of the same variance as the
+        Gaussian of `learn`: half-width sqrt(3) * action_noise; uniformly random actions while the buffer warms up) and
+        writes the k x N transitions out time-major; then k gradient steps."""
+        c, env = self.cfg, self.env
+        n, dev, ad = env.num_envs, self.device, self.act_dim
+        traj = {"obs": torch.empty((k + 1, n, env.obs_dim), device=dev), "actions": torch.empty((k, n, ad), device=dev),
+                "reward": torch.empty((k, n), device=dev), "done": torch.empty((k, n), dtype=torch.uint8, device=dev)}
+        last, t0 = env.stats(), time.perf_counter()
+        next_report = report_every
+        for step in range(k, total_steps + 1, k):
+            warm = self.size < c.learning_starts
+            env.rollout_actor(mlp_layers(self.actor), k, 1.0 if warm else min(1.0, 3 ** 0.5 * c.action_noise), traj=traj)
+            self._store(traj["obs"][:k].reshape(k * n, -1), traj["actions"].reshape(k * n, ad), traj["reward"].reshape(-1),
+                        traj["obs"][1:].reshape(k * n, -1), traj["done"].reshape(-1).bool())
+            self.env_steps += k
+            if not warm:
+                for _ in range(k):
+                    self.train_step()
+            if report_every and step >= next_report:
+                next_report += report_every
+                now = env.stats()
+                d = {kk: now[kk] - last[kk] for kk in ("episodes", "goals", "outs", "timeouts", "return_sum")}
+                last = now
+                ep = max(1, d["episodes"])
+                c.log.append({"step": step, "transitions": step * n, "episodes": d["episodes"],
+                              "goal_rate": d["goals"] / ep, "out_rate": d["outs"] / ep, "timeout_rate": d["timeouts"] / ep,
+                              "mean_return": d["return_sum"] / ep, "wall_s": round(time.perf_counter() - t0, 2)})
+        self._obs.copy_(env.obs)
+        return c.log
+
     @torch.no_grad()
-    def evaluate(self, steps: int) -> dict:
+    def evaluate(self, steps: int, fused: bool = False) -> dict:
         before = self.env.stats()
+        if fused:
+            layers = mlp_layers(self.actor)
+            for lo in range(0, steps, 16):
+                self.env.rollout_actor(layers, min(16, steps - lo))
+            self._obs.copy_(self.env.obs)
+            steps = 0
         for _ in range(steps):
             self.rollout_step(0.0, store=False)
         after = self.env.stats()

@@ -486,6 +486,35 @@ class Soccer2DVecEnv(_VecEnvBase):
                                             q_out.data_ptr() if q_out is not None else None, _stream_ptr(self.device)),
                    self.handle)
 
+    def rollout_actor(self, layers, k: int | None = None, noise: float = 0.0, traj: dict | None = None) -> None:
+        """`k` cycles of observe -> actor(obs) -> Box action -> step in ONE launch (ReachBall with the Box(1) or the Box(4)
+        turning action space): the DDPG counterpart of `rollout_mlp` (s2d_rollout_actor_collect).  `layers` = [(weight,
+        bias)] * 3 of a 64-64 ReLU MLP whose last layer has action_dim rows; tanh is applied in the kernel.  `noise`: the
+        half-width of a uniform exploration noise.  `traj`: time-major tensors, any of obs float32 [k + 1, N, 10],
+        actions float32 [k, N, action_dim], reward float32 [k, N], done uint8 [k, N]."""
+        k = self.substeps if k is None else int(k)
+        ad = 4 if self.action_mode == _abi.ACT_TURNING else 1
+        ptrs = []
+        for (w, b), shape in zip(layers, ((64, self.obs_dim), (64, 64), (ad, 64))):
+            if tuple(w.shape) != shape or tuple(b.shape) != shape[:1]:
+                raise ValueError(f"rollout_actor: expected weight {shape} and bias {shape[:1]}, got {tuple(w.shape)} / {tuple(b.shape)}")
+            for t in (w, b):
+                if t.dtype != torch.float32 or not t.is_cuda or not t.is_contiguous() or t.device != self.device:
+                    raise ValueError("rollout_actor: weights must be contiguous float32 tensors on the env's device")
+            ptrs += [w.data_ptr(), b.data_ptr()]
+        pol = _abi.MlpPolicy(*ptrs, 64, 0)
+        t = _abi.Trajectory()
+        want = {"obs": ((k + 1, self.num_envs, self.obs_dim), torch.float32, "obs"),
+                "actions": ((k, self.num_envs, ad), torch.float32, "actions_f"),
+                "reward": ((k, self.num_envs), torch.float32, "reward"), "done": ((k, self.num_envs), torch.uint8, "done")}
+        for name, ten in (traj or {}).items():
+            shape, dt, field = want[name]
+            assert tuple(ten.shape) == shape and ten.dtype == dt and ten.is_contiguous() and ten.device == self.device, name
+            setattr(t, field, ten.data_ptr())
+        _abi.check(self.lib.s2d_rollout_actor_collect(self.handle, C.byref(pol), k, float(noise),
+                                                      C.byref(t) if traj is not None else None, _stream_ptr(self.device)),
+                   self.handle)
+
     # ---- heterogeneous players (fullgame; proto PlayerType, idl/service.proto:1697-1732) ------------------------
     def generate_player_types(self, seed: int, n: int = _abi.MAX_PLAYER_TYPES) -> list:
         """rcssserver's HeteroPlayer draws for this env's ServerParam: [type 0 = default player, n - 1 drawn types]"""

@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define S2D_ABI_VERSION 8
+#define S2D_ABI_VERSION 9
 
 /* error codes */
 #define S2D_OK 0
@@ -351,9 +351,17 @@ typedef struct S2DTrajectory {
   uint8_t* actions; /* [k_substeps][num_envs] */
   float* reward;    /* [k_substeps][num_envs] */
   uint8_t* done;    /* [k_substeps][num_envs] */
+  float* actions_f; /* [k_substeps][num_envs][action_dim]: the Box actions of s2d_rollout_actor_collect */
 } S2DTrajectory;
 int s2d_rollout_mlp_collect(S2DHandle h, const S2DMlpPolicy* policy, int k_substeps, float epsilon,
                             const S2DTrajectory* trajectory, void* stream);
+
+/* The same for a deterministic actor (DDPG, ddpg_stable_baselines3.py / dqn_ddpg_stable_baselines3.py): REACHBALL with
+ * S2D_ACT_CONTINUOUS (Box(1)) or S2D_ACT_TURNING (Box(4)).  `actor` = obs -> 64 -> 64 -> action_dim with ReLU and a
+ * final tanh (w3: [action_dim][64]); `noise` = half-width of a uniform exploration noise added to every component
+ * before the clip to [-1, 1] (0: the deterministic policy).  `trajectory` may be NULL; its `actions` is not used. */
+int s2d_rollout_actor_collect(S2DHandle h, const S2DMlpPolicy* actor, int k_substeps, float noise,
+                              const S2DTrajectory* trajectory, void* stream);
 
 /* Launch geometry actually used (for bench.py's gpu_launches / DESIGN.md): blocks, threads, kernels per step call */
 int s2d_launch_info(S2DHandle h, int* grid, int* block, int* kernels_per_step);

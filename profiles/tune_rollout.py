@@ -31,5 +31,25 @@ for n, k in ((1 << 20, 16), (1 << 20, 1), (1 << 16, 16)):
     med = ms[len(ms) // 2]
     print(f"fused policy+step: {n} envs K={k}: median {med:.4f} ms  min {ms[0]:.4f}  {n * k / med / 1e6:.2f} G env-steps/s  stats {env.stats()['episodes']}")
     env.close()
+from soccer2d_b200.rollout import Actor, mlp_layers  # noqa: E402
+for turning in (False, True):
+    n, k = 1 << 20, 16
+    env = Soccer2DVecEnv(n, device="cuda:0", seed=0, substeps=k, use_continuous_action=True, use_turning=turning,
+                         change_ball_position=True, change_ball_velocity=True)
+    actor = Actor(10, 4 if turning else 1).cuda()
+    env.reset_torch()
+    for _ in range(14):
+        env.rollout_actor(mlp_layers(actor), k)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(20)]
+    for a, b in ev:
+        flush.zero_()
+        a.record()
+        env.rollout_actor(mlp_layers(actor), k)
+        b.record()
+    torch.cuda.synchronize()
+    ms = sorted(a.elapsed_time(b) for a, b in ev)
+    print(f"fused actor+step ({'Box(4) turning' if turning else 'Box(1)'}): {n} envs K={k}: median {ms[len(ms) // 2]:.4f} ms  "
+          f"{n * k / ms[len(ms) // 2] / 1e6:.2f} G env-steps/s")
+    env.close()
 env = Soccer2DVecEnv(1 << 20, device="cuda:0", seed=0, substeps=1, **KW)
 print("torch policy + step (CUDA graph), 2^20 envs:", f"{measure_rollout(env, qnet, steps=50, use_graph=True) / 1e9:.3f} G env-steps/s")

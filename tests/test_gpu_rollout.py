@@ -239,3 +239,64 @@ def test_dqn_learns_from_fused_collection():
     assert trained["episodes"] > 4096 and trained["goal_rate"] > 0.6, trained
     agent.rollout_step(0.0, store=False)  # the unfused path carries on from the fused one's observation
     env.close()
+
+
+@pytest.mark.parametrize("turning", [False, True])
+def test_fused_actor_rollout_matches_actor_then_step(turning):
+    """s2d_rollout_actor_collect: the DDPG actor inside the step kernel, Box(1) and Box(4) action spaces.  The recorded
+    actions equal torch's fp32 actor on the recorded observations to TF32 accuracy; replaying them through the ordinary
+    step kernel reproduces every recorded observation, reward and done flag bit for bit."""
+    from soccer2d_b200.rollout import Actor, mlp_layers
+    torch.manual_seed(2)
+    n, k = 2048 + 9, 5
+    ad = 4 if turning else 1
+    kw = dict(device="cuda:0", seed=6, use_continuous_action=True, use_turning=turning, change_ball_velocity=True, max_steps=50)
+    fused = Soccer2DVecEnv(n, substeps=k, **kw)
+    plain = Soccer2DVecEnv(n, substeps=1, **kw)
+    actor = Actor(10, ad).cuda()
+    with torch.no_grad():
+        for p in actor.parameters():
+            p.mul_(2.0)
+    fused.reset_torch()
+    plain.reset_torch()
+    traj = {"obs": torch.zeros((k + 1, n, 10), device="cuda"), "actions": torch.zeros((k, n, ad), device="cuda"),
+            "reward": torch.zeros((k, n), device="cuda"), "done": torch.zeros((k, n), dtype=torch.uint8, device="cuda")}
+    worst = 0.0
+    for launch in range(20):
+        fused.rollout_actor(mlp_layers(actor), k, 0.0, traj=traj)
+        assert torch.equal(traj["obs"][0], plain.obs)
+        for j in range(k):
+            with torch.no_grad():
+                want = actor(plain.obs)
+            worst = max(worst, float((traj["actions"][j] - want).abs().max()))
+            plain.step_torch(traj["actions"][j].reshape(plain.actions.shape).contiguous())
+            assert torch.equal(traj["obs"][j + 1], plain.obs)
+            assert torch.equal(traj["reward"][j], plain.reward) and torch.equal(traj["done"][j], plain.done_u8)
+        assert torch.equal(fused.state, plain.state)
+    assert worst < 5e-3, worst
+    assert fused.stats()["episodes"] == plain.stats()["episodes"] > 0
+    # exploration noise: uniform of the given half-width around the deterministic action, clipped
+    det = torch.zeros((k, n, ad), device="cuda")
+    noisy = torch.zeros((k, n, ad), device="cuda")
+    state = fused.state.clone()
+    fused.rollout_actor(mlp_layers(actor), k, 0.0, traj={"actions": det})
+    fused.state.copy_(state)
+    fused.rollout_actor(mlp_layers(actor), k, 0.25, traj={"actions": noisy})
+    d = (noisy[0] - det[0])  # first cycle: the same state, so the same deterministic action
+    inside = det[0].abs() < 0.7
+    assert float(d[inside].abs().max()) <= 0.25 + 1e-6 and float(d[inside].std()) == pytest.approx(0.25 / 3 ** 0.5, rel=0.05)
+    assert float(noisy.abs().max()) <= 1.0
+    fused.close()
+    plain.close()
+
+
+def test_ddpg_learns_from_fused_collection():
+    from soccer2d_b200.rollout import DDPGConfig, DeviceDDPG
+    kw = dict(change_ball_position=False, use_continuous_action=True, use_turning=False)
+    env = Soccer2DVecEnv(4096, device="cuda:0", seed=0, terminal_obs=True, **kw)
+    agent = DeviceDDPG(env, DDPGConfig(seed=0, learning_starts=1 << 15))
+    agent.learn_fused(1200, k=8)
+    trained = agent.evaluate(320, fused=True)
+    assert trained["episodes"] > 4096 and trained["goal_rate"] > 0.6, trained
+    agent.rollout_step(0.0, store=False)
+    env.close()

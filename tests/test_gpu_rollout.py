@@ -300,3 +300,41 @@ def test_ddpg_learns_from_fused_collection():
     assert trained["episodes"] > 4096 and trained["goal_rate"] > 0.6, trained
     agent.rollout_step(0.0, store=False)
     env.close()
+
+
+@pytest.mark.parametrize("n", [33, 1000])
+def test_fused_rollouts_stay_inside_their_buffers(n):
+    """(compute-sanitizer is not available on this pool) every output of the fused kernels is the middle of a larger
+    tensor filled with a sentinel; ragged sizes; the guard bytes on both sides must survive."""
+    from soccer2d_b200.rollout import Actor, mlp_layers
+    guard, k = 4096, 3
+    big = []
+
+    def guarded(shape, dtype):
+        nbytes = int(np.prod(shape)) * torch.empty((), dtype=dtype).element_size()
+        buf = torch.full((nbytes + 2 * guard,), 0xA5, dtype=torch.uint8, device="cuda")
+        big.append((buf, nbytes))
+        return buf[guard:guard + nbytes].view(dtype).view(shape)
+
+    env = Soccer2DVecEnv(n, device="cuda:0", seed=1, substeps=k, use_continuous_action=False, action_space_size=16, max_steps=5)
+    env.reset_torch()
+    q = QNetwork(10, 16).cuda()
+    traj = {"obs": guarded((k + 1, n, 10), torch.float32), "actions": guarded((k, n), torch.uint8),
+            "reward": guarded((k, n), torch.float32), "done": guarded((k, n), torch.uint8)}
+    acts, qv = guarded((n, k), torch.uint8), guarded((n, 16), torch.float32)
+    for _ in range(4):
+        env.rollout_mlp(mlp_layers(q), k, 0.3, traj=traj)
+        env.rollout_mlp(mlp_layers(q), k, 0.3, actions_out=acts, q_out=qv)
+    cont = Soccer2DVecEnv(n, device="cuda:0", seed=1, substeps=k, use_continuous_action=True, use_turning=True, max_steps=5)
+    cont.reset_torch()
+    actor = Actor(10, 4).cuda()
+    ctraj = {"obs": guarded((k + 1, n, 10), torch.float32), "actions": guarded((k, n, 4), torch.float32),
+             "reward": guarded((k, n), torch.float32), "done": guarded((k, n), torch.uint8)}
+    for _ in range(4):
+        cont.rollout_actor(mlp_layers(actor), k, 0.1, traj=ctraj)
+    torch.cuda.synchronize()
+    for buf, nbytes in big:
+        assert bool((buf[:guard] == 0xA5).all()) and bool((buf[guard + nbytes:] == 0xA5).all())
+    assert float(traj["obs"].abs().sum()) > 0 and float(ctraj["actions"].abs().sum()) > 0 and int(traj["done"].sum()) > 0
+    env.close()
+    cont.close()

@@ -366,6 +366,8 @@ def run_b200(args, rank, local_rank, world):
             "timing": "sum of per-launch CUDA-event durations on the launching stream, max over ranks"}),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3,
+                "d2h_gbs": d2h * e2e_steps / e2e_s / 1e9, "h2d_gbs": h2d * e2e_steps / e2e_s / 1e9,
+                "bound": "PCIe device-to-host (46 bytes of results per env and launch; both directions run concurrently)",
                 "path": "Soccer2DVecEnv.submit_host / wait_host -> s2d_submit_host / s2d_wait_host: pinned host actions in, "
                         "obs/reward/done/result out, two steps in flight (copies overlap the kernel)",
                 "synchronous": {"value": e2e_sync_value, "ms_per_step": e2e_sync_s / e2e_steps * 1e3,

@@ -682,7 +682,17 @@ static int rollout_mlp(S2DHandle h, const S2DMlpPolicy* policy, int k_substeps, 
     else if (h->default_sp) rollout_mlp_kernel<SCN, kVarDefault, ACT><<<h->grid, kBlock, 0, s>>>(h->kp, k_substeps, w, epsilon, ao, qo, traj); \
     else rollout_mlp_kernel<SCN, kVarRuntime, ACT><<<h->grid, kBlock, 0, s>>>(h->kp, k_substeps, w, epsilon, ao, qo, traj); \
   } while (0)
-  if (actor && mode == S2D_ACT_TURNING) S2D_ROLLOUT(S2D_SCENARIO_REACHBALL, S2D_ACT_TURNING);
+  if (policy->precision != 0 && (policy->precision != 1 || actor || h->cfg.noise))
+    return fail(h, S2D_ERR_INVALID, "precision: 0 (TF32), or 1 (bf16) for a Q-network on a handle without noise");
+  if (policy->precision == 1) {
+    if (shoot) {
+      if (h->default_sp) rollout_mlp_kernel<S2D_SCENARIO_SHOOT, kVarDefault, S2D_ACT_DISCRETE, true><<<h->grid, kBlock, 0, s>>>(h->kp, k_substeps, w, epsilon, ao, qo, traj);
+      else rollout_mlp_kernel<S2D_SCENARIO_SHOOT, kVarRuntime, S2D_ACT_DISCRETE, true><<<h->grid, kBlock, 0, s>>>(h->kp, k_substeps, w, epsilon, ao, qo, traj);
+    } else {
+      if (h->default_sp) rollout_mlp_kernel<S2D_SCENARIO_REACHBALL, kVarDefault, S2D_ACT_DISCRETE, true><<<h->grid, kBlock, 0, s>>>(h->kp, k_substeps, w, epsilon, ao, qo, traj);
+      else rollout_mlp_kernel<S2D_SCENARIO_REACHBALL, kVarRuntime, S2D_ACT_DISCRETE, true><<<h->grid, kBlock, 0, s>>>(h->kp, k_substeps, w, epsilon, ao, qo, traj);
+    }
+  } else if (actor && mode == S2D_ACT_TURNING) S2D_ROLLOUT(S2D_SCENARIO_REACHBALL, S2D_ACT_TURNING);
   else if (actor) S2D_ROLLOUT(S2D_SCENARIO_REACHBALL, S2D_ACT_CONTINUOUS);
   else if (shoot) S2D_ROLLOUT(S2D_SCENARIO_SHOOT, S2D_ACT_DISCRETE);
   else S2D_ROLLOUT(S2D_SCENARIO_REACHBALL, S2D_ACT_DISCRETE);

@@ -90,6 +90,95 @@ __device__ __forceinline__ void mlp_load_weights(MlpShared& s, const MlpWeights&
   }
 }
 
+// ---- the same network with bf16 operands (fp32 accumulate): mma.sync m16n8k16 --------------------------------------
+// Half the MMAs and half the fragment loads of the TF32 form; 8 mantissa bits, so Q-values agree with fp32 only to
+// about 1e-2 of their scale: an option for rollouts that tolerate it (S2DMlpPolicy.precision = 1), never the default.
+//   A (16x16, row): a0 {(g, 2t), (g, 2t+1)}  a1 {(g+8, ..)}  a2 {(g, 2t+8), (g, 2t+9)}  a3 {(g+8, ..)}   (bf16 pairs)
+//   B (16x8, col):  b0 {(k = 2t, n = g), (2t+1, g)}  b1 {(2t+8, g), (2t+9, g)};  D as above
+// so two consecutive accumulator column tiles of one layer ARE the A fragment of the next layer's k-step, in order.
+// The weight fragments live in the first half of the float2 slots of MlpShared (w1[0], w2[0..3], w3[0..3]).
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], float2 b) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(__float_as_uint(b.x)), "r"(__float_as_uint(b.y)));
+}
+
+__device__ __forceinline__ void mlp_load_weights_bf16(MlpShared& s, const MlpWeights& w, float absent_bias) {
+  auto w1at = [&](int n, int f) { return f < w.obs_dim ? __ldg(w.w1 + n * w.obs_dim + f) : 0.0f; };
+  for (int idx = threadIdx.x; idx < 4 * kMlpHidden; idx += blockDim.x) {
+    const int n = idx % kMlpHidden, t = idx / kMlpHidden;
+    s.w1[0][t][n] = make_float2(__uint_as_float(pack_bf16(w1at(n, 2 * t), w1at(n, 2 * t + 1))),
+                                __uint_as_float(pack_bf16(w1at(n, 2 * t + 8), w1at(n, 2 * t + 9))));
+  }
+  for (int idx = threadIdx.x; idx < 4 * 4 * kMlpHidden; idx += blockDim.x) {
+    const int n = idx % kMlpHidden, t = (idx / kMlpHidden) % 4, k = idx / (4 * kMlpHidden);
+    const float* row = w.w2 + n * kMlpHidden + 16 * k + 2 * t;
+    s.w2[k][t][n] = make_float2(__uint_as_float(pack_bf16(__ldg(row), __ldg(row + 1))),
+                                __uint_as_float(pack_bf16(__ldg(row + 8), __ldg(row + 9))));
+  }
+  for (int idx = threadIdx.x; idx < 4 * 4 * kMlpActions; idx += blockDim.x) {
+    const int n = idx % kMlpActions, t = (idx / kMlpActions) % 4, k = idx / (4 * kMlpActions);
+    const float* row = w.w3 + n * kMlpHidden + 16 * k + 2 * t;
+    s.w3[k][t][n] = n < w.n_actions ? make_float2(__uint_as_float(pack_bf16(__ldg(row), __ldg(row + 1))),
+                                                  __uint_as_float(pack_bf16(__ldg(row + 8), __ldg(row + 9))))
+                                    : make_float2(0.0f, 0.0f);
+  }
+  for (int idx = threadIdx.x; idx < kMlpHidden; idx += blockDim.x) {
+    s.b1[idx] = __ldg(w.b1 + idx);
+    s.b2[idx] = __ldg(w.b2 + idx);
+    if (idx < kMlpActions) s.b3[idx] = idx < w.n_actions ? __ldg(w.b3 + idx) : absent_bias;
+  }
+}
+
+template <int NT>
+__device__ __forceinline__ void mlp_forward_tile_bf16(const MlpShared& s, const float (*obs)[20], int tile, int g, int t,
+                                                      float (&q)[NT][4]) {
+  float h1[8][4], h2[8][4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    h1[j][0] = h1[j][2] = s.b1[8 * j + 2 * t];
+    h1[j][1] = h1[j][3] = s.b1[8 * j + 2 * t + 1];
+    h2[j][0] = h2[j][2] = s.b2[8 * j + 2 * t];
+    h2[j][1] = h2[j][3] = s.b2[8 * j + 2 * t + 1];
+  }
+  {
+    const float* r0 = obs[16 * tile + g] + 2 * t;
+    const float* r1 = obs[16 * tile + g + 8] + 2 * t;
+    const uint32_t a[4] = {pack_bf16(r0[0], r0[1]), pack_bf16(r1[0], r1[1]), pack_bf16(r0[8], r0[9]), pack_bf16(r1[8], r1[9])};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) mma_bf16(h1[j], a, s.w1[0][t][8 * j + g]);
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const uint32_t a[4] = {pack_bf16(fmaxf(h1[2 * k][0], 0.0f), fmaxf(h1[2 * k][1], 0.0f)),
+                           pack_bf16(fmaxf(h1[2 * k][2], 0.0f), fmaxf(h1[2 * k][3], 0.0f)),
+                           pack_bf16(fmaxf(h1[2 * k + 1][0], 0.0f), fmaxf(h1[2 * k + 1][1], 0.0f)),
+                           pack_bf16(fmaxf(h1[2 * k + 1][2], 0.0f), fmaxf(h1[2 * k + 1][3], 0.0f))};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) mma_bf16(h2[j], a, s.w2[k][t][8 * j + g]);
+  }
+#pragma unroll
+  for (int j = 0; j < NT; ++j) {
+    q[j][0] = q[j][2] = s.b3[8 * j + 2 * t];
+    q[j][1] = q[j][3] = s.b3[8 * j + 2 * t + 1];
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const uint32_t a[4] = {pack_bf16(fmaxf(h2[2 * k][0], 0.0f), fmaxf(h2[2 * k][1], 0.0f)),
+                           pack_bf16(fmaxf(h2[2 * k][2], 0.0f), fmaxf(h2[2 * k][3], 0.0f)),
+                           pack_bf16(fmaxf(h2[2 * k + 1][0], 0.0f), fmaxf(h2[2 * k + 1][1], 0.0f)),
+                           pack_bf16(fmaxf(h2[2 * k + 1][2], 0.0f), fmaxf(h2[2 * k + 1][3], 0.0f))};
+#pragma unroll
+    for (int j = 0; j < NT; ++j) mma_bf16(q[j], a, s.w3[k][t][8 * j + g]);
+  }
+}
+
 // Q-values of the 16 episodes `tile` (0 | 1) of this warp, from the staged observations; q[j][..] in the accumulator
 // layout: actions 8j + 2t, 8j + 2t + 1 of episode 16 tile + g (q[j][0..1]) and of episode 16 tile + g + 8 (q[j][2..3]).
 template <int NT>
@@ -136,7 +225,7 @@ __device__ __forceinline__ void mlp_forward_tile(const MlpShared& s, const float
 }
 
 // greedy action of every episode of the warp -> s.act[warp][episode]; optionally the Q-values to q_out [N][8 NT]
-template <int NT>
+template <int NT, bool BF16 = false>
 __device__ __forceinline__ void mlp_greedy(MlpShared& s, int warp, int lane, float* __restrict__ q_out, int64_t warp_first,
                                            int64_t n) {
   const unsigned full = 0xffffffffu;
@@ -144,7 +233,8 @@ __device__ __forceinline__ void mlp_greedy(MlpShared& s, int warp, int lane, flo
 #pragma unroll 1
   for (int tile = 0; tile < 2; ++tile) {
     float q[NT][4];
-    mlp_forward_tile<NT>(s, s.obs[warp], tile, g, t, q);
+    if (BF16) mlp_forward_tile_bf16<NT>(s, s.obs[warp], tile, g, t, q);
+    else mlp_forward_tile<NT>(s, s.obs[warp], tile, g, t, q);
     if (q_out) {
 #pragma unroll
       for (int j = 0; j < NT; ++j) {
@@ -203,7 +293,7 @@ __device__ __forceinline__ void mlp_actor(MlpShared& s, int warp, int lane) {
 // ACT = S2D_ACT_DISCRETE: W is a Q-network, `epsilon` the exploration rate.  ACT = S2D_ACT_CONTINUOUS / S2D_ACT_TURNING
 // (ReachBall): W is a DDPG actor (last layer -> tanh -> the Box(1) / Box(4) action) and `epsilon` the half-width of a
 // uniform exploration noise added to every action component before the clip to [-1, 1].
-template <int SCN, int VAR, int ACT = S2D_ACT_DISCRETE>
+template <int SCN, int VAR, int ACT = S2D_ACT_DISCRETE, bool BF16 = false>
 __global__ void __launch_bounds__(kBlock, S2D_ROLLOUT_MIN_BLOCKS)
     rollout_mlp_kernel(const __grid_constant__ KernelParams P, const int K, const MlpWeights W, const float epsilon,
                        uint8_t* __restrict__ actions_out, float* __restrict__ q_out, const TrajOut T) {
@@ -215,7 +305,8 @@ __global__ void __launch_bounds__(kBlock, S2D_ROLLOUT_MIN_BLOCKS)
   __shared__ __align__(16) MlpShared s;
   __shared__ __align__(16) float s_stage[kBlock / 32][32 * kObsDim];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  mlp_load_weights(s, W, kActor ? 0.0f : -3.0e38f);
+  if (BF16) mlp_load_weights_bf16(s, W, kActor ? 0.0f : -3.0e38f);
+  else mlp_load_weights(s, W, kActor ? 0.0f : -3.0e38f);
   const int64_t i = static_cast<int64_t>(blockIdx.x) * kBlock + threadIdx.x;
   const int64_t n = P.num_envs;
   const bool valid = i < n;
@@ -250,7 +341,7 @@ __global__ void __launch_bounds__(kBlock, S2D_ROLLOUT_MIN_BLOCKS)
     int rs;
     const float reward_before = out.reward_sum;  // (this cycle's reward is taken out exactly: the sum restarts at 0 ...
     if (!kActor) {
-      mlp_greedy<NT>(s, warp, lane, k == K - 1 ? q_out : nullptr, warp_first, n);
+      mlp_greedy<NT, BF16>(s, warp, lane, k == K - 1 ? q_out : nullptr, warp_first, n);
       __syncwarp();
       a = s.act[warp][lane];
       if (epsilon > 0.0f) {  // exploration: the same counter stream as the turning action's draw (RNG_ACTION)

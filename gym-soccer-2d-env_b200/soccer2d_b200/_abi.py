@@ -102,7 +102,7 @@ class PlayerType(C.Structure):
 class MlpPolicy(C.Structure):
     """S2DMlpPolicy: device pointers to a 64-64 Q-network in torch nn.Linear layout"""
     _fields_ = [("w1", C.c_void_p), ("b1", C.c_void_p), ("w2", C.c_void_p), ("b2", C.c_void_p), ("w3", C.c_void_p),
-                ("b3", C.c_void_p), ("hidden", C.c_int32), ("reserved", C.c_int32)]
+                ("b3", C.c_void_p), ("hidden", C.c_int32), ("precision", C.c_int32)]
 
 
 class Trajectory(C.Structure):

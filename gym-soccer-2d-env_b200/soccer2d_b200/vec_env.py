@@ -445,13 +445,14 @@ class Soccer2DVecEnv(_VecEnvBase):
 
     # ---- closed-loop rollout with the Q-network inside the kernel (s2d_rollout_mlp) ------------------------------
     def rollout_mlp(self, layers, k: int | None = None, epsilon: float = 0.0, actions_out: torch.Tensor | None = None,
-                    q_out: torch.Tensor | None = None, traj: dict | None = None) -> None:
+                    q_out: torch.Tensor | None = None, traj: dict | None = None, precision: str = "tf32") -> None:
         """`k` cycles of observe -> Q(obs) -> (epsilon-)greedy action -> step in ONE launch (Discrete actions: ReachBall
         with n <= 16, Shoot with n <= 24).
         `layers` = [(weight, bias)] * 3 of a 64-64 ReLU MLP as torch nn.Linear stores them (float32 CUDA tensors:
         [64, 10], [64], [64, 64], [64], [n, 64], [n]), e.g. `[(l.weight, l.bias) for l in qnet.linears]`.
         Outputs land in the env's obs / reward / done_u8 / result tensors as after `step_torch`; optional
         `actions_out` uint8 [N, k] receives the actions taken and `q_out` float32 [N, 16] (Shoot: [N, 24]) the Q-values of the last cycle.
+        `precision`: "tf32" (default) or "bf16" (half the tensor-core work; Q-values then agree with fp32 only to ~1e-2).
         `traj` (s2d_rollout_mlp_collect): time-major tensors for every cycle's transition, any of obs float32
         [k + 1, N, 10], actions uint8 [k, N], reward float32 [k, N], done uint8 [k, N] - what a replay buffer takes."""
         k = self.substeps if k is None else int(k)
@@ -468,7 +469,7 @@ class Soccer2DVecEnv(_VecEnvBase):
         if q_out is not None:
             width = 24 if self.scenario == "shoot" else 16
             assert q_out.dtype == torch.float32 and tuple(q_out.shape) == (self.num_envs, width) and q_out.is_contiguous()
-        pol = _abi.MlpPolicy(*ptrs, 64, 0)
+        pol = _abi.MlpPolicy(*ptrs, 64, {"tf32": 0, "bf16": 1}[precision])
         if traj is not None:
             assert actions_out is None and q_out is None, "traj replaces actions_out / q_out"
             want = {"obs": ((k + 1, self.num_envs, self.obs_dim), torch.float32), "actions": ((k, self.num_envs), torch.uint8),

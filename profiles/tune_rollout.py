@@ -15,21 +15,21 @@ torch.manual_seed(0)
 qnet = QNetwork(10, 16).cuda()
 layers = [(m.weight.detach().contiguous(), m.bias.detach().contiguous()) for m in qnet.net if isinstance(m, torch.nn.Linear)]
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-for n, k in ((1 << 20, 16), (1 << 20, 1), (1 << 16, 16)):
+for n, k, prec in ((1 << 20, 16, "tf32"), (1 << 20, 1, "tf32"), (1 << 16, 16, "tf32"), (1 << 20, 16, "bf16")):
     env = Soccer2DVecEnv(n, device="cuda:0", seed=0, substeps=k, **KW)
     env.reset_torch()
     for _ in range(14 if k > 1 else 5):
-        env.rollout_mlp(layers, k)
+        env.rollout_mlp(layers, k, precision=prec)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(20)]
     for a, b in ev:
         flush.zero_()
         a.record()
-        env.rollout_mlp(layers, k)
+        env.rollout_mlp(layers, k, precision=prec)
         b.record()
     torch.cuda.synchronize()
     ms = sorted(a.elapsed_time(b) for a, b in ev)
     med = ms[len(ms) // 2]
-    print(f"fused policy+step: {n} envs K={k}: median {med:.4f} ms  min {ms[0]:.4f}  {n * k / med / 1e6:.2f} G env-steps/s  stats {env.stats()['episodes']}")
+    print(f"fused policy+step ({prec}): {n} envs K={k}: median {med:.4f} ms  min {ms[0]:.4f}  {n * k / med / 1e6:.2f} G env-steps/s  stats {env.stats()['episodes']}")
     env.close()
 from soccer2d_b200.rollout import Actor, mlp_layers  # noqa: E402
 for turning in (False, True):

@@ -338,3 +338,41 @@ def test_fused_rollouts_stay_inside_their_buffers(n):
     assert float(traj["obs"].abs().sum()) > 0 and float(ctraj["actions"].abs().sum()) > 0 and int(traj["done"].sum()) > 0
     env.close()
     cont.close()
+
+
+def test_fused_policy_rollout_bf16_option():
+    """precision="bf16": the env half is still bit-exact; Q-values agree with torch fp32 to bf16 accuracy and the greedy
+    action mostly; it is refused for actors and noisy handles."""
+    from soccer2d_b200.rollout import Actor, mlp_layers
+    torch.manual_seed(0)
+    n, k = 4096 + 37, 5
+    kw = dict(device="cuda:0", seed=4, use_continuous_action=False, action_space_size=16, change_ball_velocity=True)
+    fused, plain = Soccer2DVecEnv(n, substeps=k, **kw), Soccer2DVecEnv(n, substeps=1, **kw)
+    qnet = QNetwork(10, 16).cuda()
+    with torch.no_grad():
+        for p in qnet.parameters():
+            p.mul_(3.0)
+    fused.reset_torch()
+    plain.reset_torch()
+    actions = torch.zeros((n, k), dtype=torch.uint8, device="cuda")
+    q_seen = torch.zeros((n, 16), device="cuda")
+    agree = total = 0
+    worst = 0.0
+    for launch in range(20):
+        fused.rollout_mlp(mlp_layers(qnet), k, 0.0, actions, q_seen, precision="bf16")
+        for j in range(k):
+            with torch.no_grad():
+                q32 = qnet(plain.obs)
+            agree += int((q32.argmax(dim=1) == actions[:, j].long()).sum())
+            total += n
+            if j == k - 1:
+                scale = q32.abs().max(dim=1).values + 1.0
+                worst = max(worst, float(((q_seen - q32).abs().max(dim=1).values / scale).max()))
+            plain.step_torch(actions[:, j:j + 1].contiguous())
+        assert torch.equal(fused.state, plain.state) and torch.equal(fused.obs, plain.obs)
+    assert worst < 4e-2 and agree / total > 0.9, (worst, agree / total)
+    noisy = Soccer2DVecEnv(64, device="cuda:0", noise=True, use_continuous_action=False)
+    with pytest.raises(_abi.Soccer2DError):
+        noisy.rollout_mlp(mlp_layers(qnet), 1, precision="bf16")
+    for e in (fused, plain, noisy):
+        e.close()

@@ -8,7 +8,7 @@ mkdir -p $O
 python bench.py > $O/${TAG}_bench_n1.json 2> $O/${TAG}_bench_n1.err || { echo "bench failed"; tail -5 $O/${TAG}_bench_n1.err; exit 1; }
 python bench.py --impl reference --steps 3 --warmup 1 > $O/${TAG}_bench_reference.json 2>> $O/${TAG}_bench_n1.err || echo "reference arm failed"
 python bench.py --steps 20 --warmup 3 > /dev/null 2>&1 && \
-  ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file $O/${TAG}_launches_bench.csv \
+  ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file $O/${TAG}_launches_bench.csv \
       python bench.py --steps 20 --warmup 3 > $O/ncu_launches.log 2>&1
 python profiles/tune_scenarios.py > $O/${TAG}_scenarios.txt 2>&1
 python profiles/tune.py >> $O/${TAG}_scenarios.txt 2>&1

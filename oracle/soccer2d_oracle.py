@@ -320,6 +320,71 @@ def lower_goto(p: Player, tx: float, ty: float, dist_thr: float, max_power: floa
     return CMD_DASH, clamp(0.0, need, max_power), 0.0
 
 
+CMD_TURN_TO_POINT, CMD_TURN_TO_BALL, CMD_TURN_TO_ANGLE, CMD_KICK_ONE_STEP, CMD_STOP_BALL, CMD_INTERCEPT = 5, 6, 7, 8, 9, 10
+
+
+def inertia_factor(decay: float, n: int) -> float:
+    """(1 - d^n) / (1 - d): how far an object drifts in n cycles per unit of velocity"""
+    return (1.0 - decay ** n) / (1.0 - decay)
+
+
+def lower_body_action(p: Player, b: Ball, c: int, a1: float, a2: float, a3: float, sp: ServerParam):
+    """Body_TurnToPoint / Body_TurnToBall / Body_TurnToAngle / Body_KickOneStep (force mode) / Body_StopBall /
+    Body_Intercept (idl/service.proto:742-780; the spec is in include/soccer2d.h) lowered, as the proxy does with
+    librcsc's rules, to (cmd, a1, a2, a3) of the basic vocabulary.  Values handed on are proto floats (f32)."""
+    if c in (CMD_TURN_TO_POINT, CMD_TURN_TO_BALL, CMD_TURN_TO_ANGLE):
+        if c == CMD_TURN_TO_ANGLE:
+            ang = norm_deg(norm_deg(a1) - p.body)
+        else:
+            n = int(clamp(0.0, float(round_half_even(a1 if c == CMD_TURN_TO_BALL else a3)), 63.0))
+            tx, ty = a1, a2
+            if c == CMD_TURN_TO_BALL:
+                fb = inertia_factor(sp.ball_decay, n)
+                tx, ty = b.x + b.vx * fb, b.y + b.vy * fb
+            fp = inertia_factor(sp.player_decay, n)
+            mx, my = p.x + p.vx * fp, p.y + p.vy * fp
+            ang = norm_deg(atan2_deg(ty - my, tx - mx) - p.body)
+        speed = hypot2(p.vx, p.vy)
+        return CMD_TURN, f32(clamp(sp.min_moment, ang * (1.0 + sp.inertia_moment * speed), sp.max_moment)), 0.0, 0.0
+    if c in (CMD_KICK_ONE_STEP, CMD_STOP_BALL):
+        dx, dy = b.x - p.x, b.y - p.y
+        dist = hypot2(dx, dy)
+        if dist > sp.player_size + sp.ball_size + sp.kickable_margin:
+            return CMD_NONE, 0.0, 0.0, 0.0
+        wx = wy = 0.0
+        if c == CMD_KICK_ONE_STEP:
+            first_speed = clamp(0.0, a3, sp.ball_speed_max)
+            th = math.radians(atan2_deg(a2 - b.y, a1 - b.x))
+            wx, wy = first_speed * math.cos(th), first_speed * math.sin(th)
+        ax, ay = wx - b.vx, wy - b.vy
+        acc = hypot2(ax, ay)
+        dir_diff = math.fabs(norm_deg(atan2_deg(dy, dx) - p.body))
+        dist_ball = dist - sp.player_size - sp.ball_size
+        rate = sp.kick_power_rate * (1.0 - 0.25 * dir_diff / 180.0 - 0.25 * dist_ball / sp.kickable_margin)
+        return CMD_KICK, f32(clamp(0.0, acc / rate, sp.max_power)), f32(norm_deg(atan2_deg(ay, ax) - p.body)), 0.0
+    if c == CMD_INTERCEPT:
+        reach0 = 0.8 * (sp.player_size + sp.ball_size + sp.kickable_margin)
+        fb = fp = 0.0
+        pwb = pwp = 1.0
+        tx, ty = b.x, b.y
+        for t in range(1, 31):
+            fb += pwb
+            fp += pwp
+            pwb *= sp.ball_decay
+            pwp *= sp.player_decay
+            tx, ty = b.x + b.vx * fb, b.y + b.vy * fb
+            mx, my = p.x + p.vx * fp, p.y + p.vy * fp
+            reach = reach0 + (t - 1) * sp.player_speed_max
+            if (tx - mx) ** 2 + (ty - my) ** 2 <= reach * reach:
+                break
+        return CMD_GOTO, f32(tx), f32(ty), 100.0
+    return c, a1, a2, a3
+
+
+def round_half_even(x: float) -> float:
+    return float(round(x))  # Python rounds halves to even, like rint
+
+
 def obj_inc(o, accel_max: float, speed_max: float, decay: float) -> None:
     """MPObject::_inc (rcssserver src/object.cpp; SURVEY A.4), noise off, no wind."""
     if o.ax != 0.0 or o.ay != 0.0:
@@ -710,6 +775,8 @@ class ShootOracle(ReachBallOracle):
                 return CMD_DASH, 100.0, self._dirs(a, n_dash)
             return CMD_KICK, 100.0, self._dirs(a - n_dash, cfg.kick_actions)
         c, a1, a2, a3 = (float(v) for v in action)
+        if c >= CMD_TURN_TO_POINT:
+            c, a1, a2, a3 = lower_body_action(self.player, self.ball, int(c), a1, a2, a3, self.sp)
         c = int(c)
         if c in (CMD_DASH, CMD_KICK):
             return c, a1, a2

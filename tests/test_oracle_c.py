@@ -178,7 +178,7 @@ def test_shoot_c_f64_equals_python_oracle(mode):
             act = rng.integers(0, 24, size=(n, 1)).astype(np.uint8)
         else:
             act = H.chase_and_shoot(sim.obs, rng, kick_prob=0.9)
-            act = np.where(rng.uniform(size=(n, 1, 1)) < 0.1, H.random_commands(rng, n, body_actions=False), act).astype(np.float32)
+            act = np.where(rng.uniform(size=(n, 1, 1)) < 0.1, H.random_commands(rng, n), act).astype(np.float32)
         obs, rew, done, res = sim.step(act)
         for i, o in enumerate(py):
             a = int(act[i, 0]) if mode == "discrete" else act[i, 0]

@@ -322,3 +322,59 @@ def test_fullgame_invariants_with_player_types_and_referee():
             assert (d >= 9.15 - 0.61).all()  # (placed on the circle; a player-player collision may then push by < 0.6)
         offside_calls += int(((mode == 5) & (s[:, k + 10] == 0)).sum())
     assert {2, 3} <= seen_modes and marks_seen > 0
+
+
+def test_fullgame_c_oracle_equals_an_independent_python_twin():
+    """The FULLGAME spec (include/soccer2d.h) restated twice: oracle/s2d_oracle.c and tests/fullgame_twin.py (built on
+    the Python oracle's building blocks).  They are stepped from the same state and compared one cycle ahead - every
+    state of 300 cycles of swarm play with heterogeneous players, body actions, goals, restarts and offside calls."""
+    import ctypes as C
+    import fullgame_twin as T
+    from oracle import soccer2d_oracle as O
+    from test_gpu_fullgame import swarm_policy
+    n, p, half = 5, 22, 120
+    lib = _abi.load()
+    cfg = H.make_config(n, "command", scenario=_abi.SCENARIO_FULLGAME, seed=21, half_time_cycles=half, goto_dist_thr=0.5)
+    types = (_abi.PlayerType * 18)()
+    assert lib.s2d_generate_player_types(4, C.byref(cfg.sp), types, 18) == 0
+    rng = np.random.default_rng(11)
+    type_of = rng.integers(1, 18, size=p)
+    type_of[0] = type_of[11] = 0
+    sim = OL.OracleSim(cfg, "f64")
+    sim.set_player_types(types, 18, type_of)
+    sim.reset()
+    base = O.ServerParam(**{k: getattr(cfg.sp, k) for k in _abi._SP_FIELDS if hasattr(O.ServerParam(), k)})
+    sps = []
+    for j in range(p):
+        q = O.ServerParam(**vars(base))
+        for k, v in types[type_of[j]].as_dict().items():
+            if hasattr(q, k):
+                setattr(q, k, float(v))
+        sps.append(q)
+    k = p * 12
+    scale = np.concatenate([np.tile([52.5, 34.0, 1.05, 1.05, 180.0, 8000.0, 1.0, 1.0, 130600.0, 1, 1, 1], p),
+                            [52.5, 34.0, 3.0, 3.0, 1], np.ones(12)])
+    modes, calls, goals = set(), 0, 0
+    for t in range(300):
+        before = sim.get_state_fg()
+        act = swarm_policy(sim.obs, p, rng, random_frac=0.25)
+        sim.step(act.reshape(n, -1))
+        after = sim.get_state_fg()
+        for i in range(n):
+            m = T.Match(before[i].tolist(), p)
+            rw, done, res = T.cycle(m, act[i, 0], sps, base, int(cfg.seed), int(cfg.env_id_offset) + i,
+                                    float(np.float32(cfg.goto_dist_thr)), half)
+            assert done == bool(sim.done[i]) and res == int(sim.result[i]), (t, i)
+            assert rw == pytest.approx(float(sim.reward[i]), abs=1e-9), (t, i)
+            if done:
+                continue  # (the C side has already started the next match)
+            m.ep_return += rw
+            got = np.array(m.vector())
+            err = np.abs(got - after[i]) / scale
+            err[4:k:12] = np.minimum(err[4:k:12], np.abs(360.0 / 180.0 - err[4:k:12]))  # body direction on the +-180 seam
+            assert err.max() < 1e-9, (t, i, int(err.argmax()), got[int(err.argmax())], after[i][int(err.argmax())])
+            modes.add(m.mode)
+            calls += int(m.mode == 5 and m.timer == 0 and before[i][k + 8] == 2)
+            goals += int(after[i][k + 11] + after[i][k + 12] > before[i][k + 11] + before[i][k + 12])
+    assert {2, 3} <= modes and len(modes) >= 3
+    assert goals > 0 and calls > 0, (sorted(modes), calls, goals)  # goals, kick-ins and an offside call were compared

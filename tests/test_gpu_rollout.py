@@ -376,3 +376,22 @@ def test_fused_policy_rollout_bf16_option():
         noisy.rollout_mlp(mlp_layers(qnet), 1, precision="bf16")
     for e in (fused, plain, noisy):
         e.close()
+
+
+def test_info_collector_reads_results_from_the_device():
+    from utils.info_collector_callback import InfoCollectorCallback
+    env = Soccer2DVecEnv(2048, device="cuda:0", seed=3, max_steps=30, **KW)
+    env.reset_torch()
+    cb = InfoCollectorCallback()
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for _ in range(80):
+        env.step_torch(torch.randint(0, 16, (2048, 1), dtype=torch.uint8, device="cuda", generator=g))
+        cb.collect(env)
+    st = env.stats()
+    got = [i["result"] for i in cb.infos]
+    assert (got.count("Goal"), got.count("Out"), got.count("Timeout")) == (st["goals"], st["outs"], st["timeouts"])
+    assert len(got) == st["episodes"] > 2048
+    import logging
+    goal, out, timeout = cb.update_results_dict(logging.getLogger("x")).values()
+    assert len(goal) == (len(got) + 99) // 100 and abs(goal[0] + out[0] + timeout[0] - 100.0) < 1e-9
+    env.close()

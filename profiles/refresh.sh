@@ -12,6 +12,7 @@ python bench.py --steps 20 --warmup 3 > /dev/null 2>&1 && \
       python bench.py --steps 20 --warmup 3 > $O/ncu_launches.log 2>&1
 python profiles/tune_scenarios.py > $O/${TAG}_scenarios.txt 2>&1
 python profiles/tune.py >> $O/${TAG}_scenarios.txt 2>&1
+python profiles/tune_variants.py >> $O/${TAG}_scenarios.txt 2>&1
 python profiles/prof_step.py both 2 > /dev/null 2>&1 && {
   ncu --set full --clock-control none --import-source on -k regex:step_kernel -s 14 -c 1 -o $O/prof_${TAG}_k16 -f python profiles/prof_step.py k16 2 > $O/ncu_full.log 2>&1
   ncu --set full --clock-control none --import-source on -k regex:step_kernel -s 6 -c 1 -o $O/prof_${TAG}_k1 -f python profiles/prof_step.py k1 2 >> $O/ncu_full.log 2>&1

@@ -41,31 +41,36 @@ def time_env(env, pool, warm, steps):
     return ms[len(ms) // 2]
 
 
-rows = []
-for name, n, k, mode in (("shoot discrete K=16", 1 << 22, 16, "discrete"), ("shoot discrete K=1", 1 << 22, 1, "discrete"),
-                         ("shoot command K=1", 1 << 22, 1, "command")):
-    env = Soccer2DVecEnv(n, scenario="shoot", device="cuda:0", seed=0, substeps=k, use_command_action=mode == "command")
-    if mode == "discrete":
-        pool = [torch.randint(0, 24, (n, k), dtype=torch.uint8, device="cuda", generator=g) for _ in range(2)]
-        abytes = k
-    else:
-        pool = [commands((n, k)) for _ in range(2)]
-        abytes = 16 * k
-    med = time_env(env, pool, 14 if k > 1 else 6, 20)
-    per_env = 160 + abytes + 46
-    rows.append(f"{name}: {n} envs  {med:.4f} ms  {n * k / med / 1e6:.1f} G env-steps/s  {n * per_env / med / 1e6:.0f} GB/s algorithmic")
-    env.close()
-    del env, pool
-    torch.cuda.empty_cache()
+def main():
+    rows = []
+    for name, n, k, mode in (("shoot discrete K=16", 1 << 22, 16, "discrete"), ("shoot discrete K=1", 1 << 22, 1, "discrete"),
+                             ("shoot command K=1", 1 << 22, 1, "command")):
+        env = Soccer2DVecEnv(n, scenario="shoot", device="cuda:0", seed=0, substeps=k, use_command_action=mode == "command")
+        if mode == "discrete":
+            pool = [torch.randint(0, 24, (n, k), dtype=torch.uint8, device="cuda", generator=g) for _ in range(2)]
+            abytes = k
+        else:
+            pool = [commands((n, k)) for _ in range(2)]
+            abytes = 16 * k
+        med = time_env(env, pool, 14 if k > 1 else 6, 20)
+        per_env = 160 + abytes + 46
+        rows.append(f"{name}: {n} envs  {med:.4f} ms  {n * k / med / 1e6:.1f} G env-steps/s  {n * per_env / med / 1e6:.0f} GB/s algorithmic")
+        env.close()
+        del env, pool
+        torch.cuda.empty_cache()
 
-for name, n, k in (("fullgame 11v11 K=1", 1 << 18, 1), ("fullgame 11v11 K=16", 1 << 18, 16)):
-    env = Soccer2DVecEnv(n, scenario="fullgame", device="cuda:0", seed=0, substeps=k, half_time_cycles=3000)
-    pool = [commands((n, k, 22)) for _ in range(2)]
-    med = time_env(env, pool, 6, 20)
-    per_env = 2 * (22 * 36 + 64) + 22 * 16 * k + 480 + 6
-    rows.append(f"{name}: {n} envs  {med:.4f} ms  {n * k / med / 1e6:.2f} G env-steps/s ({22 * n * k / med / 1e6:.1f} G agent-steps/s)  "
-                f"{n * per_env / med / 1e6:.0f} GB/s algorithmic  stats {env.stats()['episodes']}")
-    env.close()
-    del env, pool
-    torch.cuda.empty_cache()
-print("\n".join(rows))
+    for name, n, k in (("fullgame 11v11 K=1", 1 << 18, 1), ("fullgame 11v11 K=16", 1 << 18, 16)):
+        env = Soccer2DVecEnv(n, scenario="fullgame", device="cuda:0", seed=0, substeps=k, half_time_cycles=3000)
+        pool = [commands((n, k, 22)) for _ in range(2)]
+        med = time_env(env, pool, 6, 20)
+        per_env = 2 * (22 * 36 + 64) + 22 * 16 * k + 480 + 6
+        rows.append(f"{name}: {n} envs  {med:.4f} ms  {n * k / med / 1e6:.2f} G env-steps/s ({22 * n * k / med / 1e6:.1f} G agent-steps/s)  "
+                    f"{n * per_env / med / 1e6:.0f} GB/s algorithmic  stats {env.stats()['episodes']}")
+        env.close()
+        del env, pool
+        torch.cuda.empty_cache()
+    print("\n".join(rows))
+
+
+if __name__ == "__main__":
+    main()

@@ -289,8 +289,10 @@ static cudaError_t launch_step(S2DSim* h, const KernelParams& kp, int k_substeps
   if (h->cfg.scenario == S2D_SCENARIO_FULLGAME) {
     const int np = 2 * h->cfg.players_per_side, ht = h->cfg.half_time_cycles;
     if (h->hetero && h->cfg.noise) fullgame_step_kernel<kVarHeteroNoisy, 0><<<h->grid, kFgBlock, 0, s>>>(kp, k_substeps, np, ht);
+    else if (h->hetero && np == 22) fullgame_step_kernel<kVarHetero, 22><<<h->grid, kFgBlock, 0, s>>>(kp, k_substeps, np, ht);
     else if (h->hetero) fullgame_step_kernel<kVarHetero, 0><<<h->grid, kFgBlock, 0, s>>>(kp, k_substeps, np, ht);
     else if (h->cfg.noise) fullgame_step_kernel<kVarNoisy, 0><<<h->grid, kFgBlock, 0, s>>>(kp, k_substeps, np, ht);
+    else if (!h->default_sp && np == 22) fullgame_step_kernel<kVarRuntime, 22><<<h->grid, kFgBlock, 0, s>>>(kp, k_substeps, np, ht);
     else if (!h->default_sp) fullgame_step_kernel<kVarRuntime, 0><<<h->grid, kFgBlock, 0, s>>>(kp, k_substeps, np, ht);
     else if (np == 22) fullgame_step_kernel<kVarDefault, 22><<<h->grid, kFgBlock, 0, s>>>(kp, k_substeps, np, ht);
     else fullgame_step_kernel<kVarDefault, 0><<<h->grid, kFgBlock, 0, s>>>(kp, k_substeps, np, ht);

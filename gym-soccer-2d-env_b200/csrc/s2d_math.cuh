@@ -103,7 +103,8 @@ __device__ __forceinline__ float exp_poly(float x) {
   p = __fmaf_rn(r, p, 1.6666665459e-1f);
   p = __fmaf_rn(r, p, 5.0000001201e-1f);
   p = __fmaf_rn(p, r * r, r) + 1.0f;
-  return __int_as_float(__float_as_int(p) + (static_cast<int>(k) << 23));
+  // (the exponent goes in through unsigned arithmetic: shifting a negative int is undefined before C++20)
+  return __uint_as_float(__float_as_uint(p) + (static_cast<uint32_t>(static_cast<int>(k)) << 23));
 }
 
 // softmax([a, b])[0] = e^a / (e^a + e^b), written with one exponential

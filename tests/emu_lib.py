@@ -8,7 +8,8 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 EMU_DIR = os.path.join(HERE, "emu")
-SO = os.path.join(EMU_DIR, "_build", "libemu_reachball.so")
+# S2D_EMU_LIB: another build of the same source, e.g. one made with -fsanitize=undefined (see tests/emu/Makefile `ubsan`)
+SO = os.environ.get("S2D_EMU_LIB") or os.path.join(EMU_DIR, "_build", "libemu_reachball.so")
 
 _lib = None
 

@@ -146,3 +146,22 @@ def test_player_types_are_rcssserver_hetero_draws_and_match_the_oracle():
             assert 0.95 - 1e-6 < rsm < 1.05 + 1e-6
         assert len(distinct) >= 15
     assert lib.s2d_generate_player_types(0, C.byref(sp), mine, 19) == _abi.S2D_ERR_INVALID
+
+
+def test_python_constants_equal_the_header_defines():
+    """every S2D_<GROUP>_<NAME> the Python host mirrors has the header's value (commands, action modes, scenarios,
+    results, flags, error codes), and the oracle's Python constants agree for the command vocabulary"""
+    import re
+    from oracle import soccer2d_oracle as O
+    text = open(HEADER).read()
+    defines = {m.group(1): int(m.group(2), 0) for m in re.finditer(r"#define\s+S2D_(\w+)\s+\(?(-?(?:0x[0-9a-fA-F]+|\d+))u?\)?", text)}
+    checked = 0
+    for name, value in defines.items():
+        for attr in (name, "S2D_" + name):
+            if hasattr(_abi, attr) and isinstance(getattr(_abi, attr), int):
+                assert getattr(_abi, attr) == value, (attr, getattr(_abi, attr), value)
+                checked += 1
+    assert checked >= 30 and defines["CMD_INTERCEPT"] == 10 and defines["ABI_VERSION"] == _abi.ABI_VERSION
+    for name in ("NONE", "DASH", "TURN", "KICK", "GOTO", "TURN_TO_POINT", "TURN_TO_BALL", "TURN_TO_ANGLE", "KICK_ONE_STEP",
+                 "STOP_BALL", "INTERCEPT"):
+        assert getattr(O, "CMD_" + name) == defines["CMD_" + name]

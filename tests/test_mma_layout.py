@@ -91,3 +91,61 @@ def test_quad_argmax_keeps_the_lowest_index_on_ties():
                 nxt[t] = (ov, oa) if ov > v or (ov == v and oa < a) else (v, a)
             best = nxt
         assert all(best[t][1] == int(np.argmax(q)) for t in range(4))
+
+
+def mma_m16n8k16(d, a, b):
+    """bf16 form, values kept exact here: a0 {(g, 2t), (g, 2t+1)} a1 {(g+8, ..)} a2 {(g, 2t+8), (g, 2t+9)} a3 {(g+8, ..)};
+    b0 {(k = 2t, n = g), (2t+1, g)} b1 {(2t+8, g), (2t+9, g)}; d as m16n8k8"""
+    A = np.zeros((16, 16))
+    B = np.zeros((16, 8))
+    for lane in range(32):
+        g, t = lane // 4, lane % 4
+        (A[g, 2 * t], A[g, 2 * t + 1]), (A[g + 8, 2 * t], A[g + 8, 2 * t + 1]) = a[lane][0], a[lane][1]
+        (A[g, 2 * t + 8], A[g, 2 * t + 9]), (A[g + 8, 2 * t + 8], A[g + 8, 2 * t + 9]) = a[lane][2], a[lane][3]
+        (B[2 * t, g], B[2 * t + 1, g]), (B[2 * t + 8, g], B[2 * t + 9, g]) = b[lane]
+    D = A @ B
+    for lane in range(32):
+        g, t = lane // 4, lane % 4
+        d[lane] += [D[g, 2 * t], D[g, 2 * t + 1], D[g + 8, 2 * t], D[g + 8, 2 * t + 1]]
+
+
+def test_bf16_form_chains_two_column_tiles_per_k_step():
+    """mlp_forward_tile_bf16: two consecutive accumulator column tiles ARE the A fragment of the next k16 step, in order"""
+    rng = np.random.default_rng(2)
+    obs = np.zeros((16, 16))
+    obs[:, :10] = rng.uniform(-1, 1, (16, 10))
+    W1 = np.zeros((64, 16))
+    W1[:, :10] = rng.normal(size=(64, 10))
+    b1, W2, b2 = rng.normal(size=64), rng.normal(size=(64, 64)) / 8, rng.normal(size=64)
+    W3, b3 = rng.normal(size=(24, 64)) / 8, rng.normal(size=24)
+    gt = [(lane // 4, lane % 4) for lane in range(32)]
+
+    def bias(bv, j):
+        return np.array([[bv[8 * j + 2 * t], bv[8 * j + 2 * t + 1]] * 2 for (g, t) in gt], dtype=float)
+
+    def bfrag(W, k, j):
+        return [((W[8 * j + g, 16 * k + 2 * t], W[8 * j + g, 16 * k + 2 * t + 1]),
+                 (W[8 * j + g, 16 * k + 2 * t + 8], W[8 * j + g, 16 * k + 2 * t + 9])) for (g, t) in gt]
+
+    h1 = [bias(b1, j) for j in range(8)]
+    a = [((obs[g, 2 * t], obs[g, 2 * t + 1]), (obs[g + 8, 2 * t], obs[g + 8, 2 * t + 1]),
+          (obs[g, 2 * t + 8], obs[g, 2 * t + 9]), (obs[g + 8, 2 * t + 8], obs[g + 8, 2 * t + 9])) for (g, t) in gt]
+    for j in range(8):
+        mma_m16n8k16(h1[j], a, bfrag(W1, 0, j))
+
+    def chained(prev, W, bv, n_tiles):
+        out = [bias(bv, j) for j in range(n_tiles)]
+        for k in range(4):
+            lo, hi = np.maximum(prev[2 * k], 0.0), np.maximum(prev[2 * k + 1], 0.0)
+            a = [((lo[l][0], lo[l][1]), (lo[l][2], lo[l][3]), (hi[l][0], hi[l][1]), (hi[l][2], hi[l][3])) for l in range(32)]
+            for j in range(n_tiles):
+                mma_m16n8k16(out[j], a, bfrag(W, k, j))
+        return out
+
+    q = chained(chained(h1, W2, b2, 8), W3, b3, 3)
+    Q = np.zeros((16, 24))
+    for lane, (g, t) in enumerate(gt):
+        for j in range(3):
+            Q[g, 8 * j + 2 * t], Q[g, 8 * j + 2 * t + 1], Q[g + 8, 8 * j + 2 * t], Q[g + 8, 8 * j + 2 * t + 1] = q[j][lane]
+    want = np.maximum(np.maximum(obs @ W1.T + b1, 0.0) @ W2.T + b2, 0.0) @ W3.T + b3
+    assert np.allclose(Q, want, rtol=1e-12, atol=1e-12)

@@ -378,3 +378,65 @@ def test_fullgame_c_oracle_equals_an_independent_python_twin():
             goals += int(after[i][k + 11] + after[i][k + 12] > before[i][k + 11] + before[i][k + 12])
     assert {2, 3} <= modes and len(modes) >= 3
     assert goals > 0 and calls > 0, (sorted(modes), calls, goals)  # goals, kick-ins and an offside call were compared
+
+
+def test_fullgame_c_oracle_equals_the_twin_on_random_states():
+    """The same comparison from hand-made states instead of a trajectory: players scattered or piled up around the ball,
+    the ball near or beyond every line, every play mode with either side and timer, stale offside marks - one cycle
+    with random commands.  Reaches the referee branches a swarm trajectory rarely visits."""
+    import fullgame_twin as T
+    from oracle import soccer2d_oracle as O
+    n, p, half = 64, 22, 10 ** 6
+    cfg = H.make_config(n, "command", scenario=_abi.SCENARIO_FULLGAME, seed=2, half_time_cycles=half, goto_dist_thr=0.5, auto_reset=0)
+    sim = OL.OracleSim(cfg, "f64")
+    sim.reset()
+    base = O.ServerParam(**{k: getattr(cfg.sp, k) for k in _abi._SP_FIELDS if hasattr(O.ServerParam(), k)})
+    sps = [base] * p
+    rng = np.random.default_rng(5)
+    k = p * 12
+    scale = np.concatenate([np.tile([52.5, 34.0, 1.05, 1.05, 180.0, 8000.0, 1.0, 1.0, 130600.0, 1, 1, 1], p),
+                            [52.5, 34.0, 3.0, 3.0, 1], np.ones(12)])
+    seen = set()
+    for rnd in range(12):
+        st = sim.get_state_fg()
+        for i in range(n):
+            kind = rng.integers(0, 5)
+            bx = rng.choice([rng.uniform(-50, 50), 52.4, -52.4, 52.58, -52.58]) if kind else rng.uniform(-50, 50)
+            by = rng.choice([rng.uniform(-30, 30), 33.95, -33.95, 34.08, -34.08, 3.0, -6.9]) if kind else rng.uniform(-30, 30)
+            st[i, k:k + 4] = [bx, by, rng.uniform(-2.5, 2.5), rng.uniform(-2.5, 2.5)]
+            P = st[i, :k].reshape(p, 12)
+            P[:, 0] = rng.uniform(-52, 52, p)
+            P[:, 1] = rng.uniform(-33, 33, p)
+            crowd = rng.integers(0, 7)
+            P[:crowd, 0] = bx + rng.uniform(-0.5, 0.5, crowd)  # a pile-up on the ball
+            P[:crowd, 1] = by + rng.uniform(-0.5, 0.5, crowd)
+            P[:, 2:4] = rng.uniform(-0.4, 0.4, (p, 2))
+            P[:, 4] = rng.uniform(-180, 180, p)
+            P[:, 5] = rng.uniform(0, 8000, p)
+            P[:, 6] = rng.uniform(0.6, 1.0, p)
+            P[:, 7] = rng.uniform(0.5, 1.0, p)
+            mode = int(rng.choice([2, 2, 2, 3, 4, 5, 6, 7]))
+            st[i, k + 5] = rnd  # step_number
+            st[i, k + 8:k + 11] = [mode, int(rng.integers(1, 3)) if mode != 2 else 0, int(rng.choice([0, 5, 98, 99]))]
+            st[i, k + 13] = int(rng.integers(0, 3))  # last touch
+            st[i, k + 15] = 0
+            marks = int(rng.integers(0, 1 << 11)) << (11 * int(rng.integers(0, 2))) if mode == 2 and rng.uniform() < 0.5 else 0
+            st[i, k + 16] = marks
+        sim.set_state_fg(st)
+        before = sim.get_state_fg()
+        act = H.random_commands(rng, n * p).reshape(n, 1, p, 4)
+        act[:, 0, :, 0] = np.where(rng.uniform(size=(n, p)) < 0.3, 3, act[:, 0, :, 0])  # more kicks
+        sim.step(act.reshape(n, -1))
+        after = sim.get_state_fg()
+        for i in range(n):
+            m = T.Match(before[i].tolist(), p)
+            rw, done, res = T.cycle(m, act[i, 0], sps, base, int(cfg.seed), i, 0.5, half)
+            assert not done and rw == pytest.approx(float(sim.reward[i]), abs=1e-9), (rnd, i)
+            m.ep_return += rw
+            err = np.abs(np.array(m.vector()) - after[i]) / scale
+            err[4:k:12] = np.minimum(err[4:k:12], np.abs(2.0 - err[4:k:12]))
+            j = int(err.argmax())
+            assert err.max() < 1e-9, (rnd, i, j, m.vector()[j], after[i][j], int(before[i][k + 8]))
+            seen.add((int(before[i][k + 8]), m.mode))
+    modes_after = {b for _, b in seen}
+    assert {2, 3, 4, 5, 6, 7} <= modes_after, sorted(seen)  # play on, kick-off (goal), kick-in, free kick (offside), corner, goal kick

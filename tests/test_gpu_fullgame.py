@@ -374,3 +374,84 @@ def test_fullgame_with_noise_bit_exact():
         same_step(env, sim)
     assert np.array_equal(gpu_state_fg(env), sim.get_state_fg())
     assert env.stats()["episodes"] == n
+
+
+def set_gpu_state_fg(env, vec):
+    """inverse of gpu_state_fg: write [N, np*12 + 17] states into the planes of the env"""
+    pl = env.fullgame_planes()
+    n, p = env.num_envs, env.num_players
+    P = vec[:, :p * 12].reshape(n, p, 12)
+    k = p * 12
+    pl["pa"].copy_(torch.from_numpy(P[:, :, 0:4].astype(np.float32)))
+    pl["pb"].copy_(torch.from_numpy(P[:, :, 4:8].astype(np.float32)))
+    pl["pc"].copy_(torch.from_numpy(P[:, :, 8].astype(np.float32)))
+    pl["ball"].copy_(torch.from_numpy(vec[:, k:k + 4].astype(np.float32)))
+    ef = np.zeros((n, 4), np.float32)
+    ef[:, 0] = vec[:, k + 14]
+    ef[:, 2] = vec[:, k + 16].astype(np.uint32).view(np.float32)
+    pl["ef"].copy_(torch.from_numpy(ef))
+    ei = np.zeros((n, 4), np.int64)
+    ei[:, 0], ei[:, 1], ei[:, 2] = vec[:, k + 5], vec[:, k + 6], vec[:, k + 7]
+    ei[:, 3] = (vec[:, k + 8].astype(np.int64) | (vec[:, k + 9].astype(np.int64) << 8) | (vec[:, k + 13].astype(np.int64) << 10)
+                | (vec[:, k + 10].astype(np.int64) << 12) | (vec[:, k + 4].astype(np.int64) << 20) | (vec[:, k + 15].astype(np.int64) << 21))
+    pl["ei"].copy_(torch.from_numpy(ei.astype(np.uint32).view(np.int32)))
+    ej = np.zeros((n, 4), np.int64)
+    ej[:, 0], ej[:, 1] = vec[:, k + 11], vec[:, k + 12]
+    for j in range(p):
+        ej[:, 2] |= P[:, j, 9].astype(np.int64) << j
+        ej[:, 3] |= P[:, j, 10].astype(np.int64) << j
+    pl["ej"].copy_(torch.from_numpy(ej.astype(np.uint32).view(np.int32)))
+
+
+def test_fullgame_random_states_bit_exact():
+    """One cycle from hand-made states (players piled on the ball, the ball near or beyond every line, every play mode,
+    stale offside marks) with random commands: reaches the referee branches a trajectory rarely visits."""
+    n, p = 512, 22
+    env = Soccer2DVecEnv(n, scenario="fullgame", device="cuda:0", seed=2, half_time_cycles=10 ** 6, auto_reset=False)
+    sim = OL.OracleSim(env.cfg, "f32")
+    env.reset_torch()
+    sim.reset()
+    rng = np.random.default_rng(5)
+    k = p * 12
+    modes_after = set()
+    for rnd in range(10):
+        st = sim.get_state_fg()
+        for i in range(n):
+            kind = rng.integers(0, 5)
+            bx = rng.choice([rng.uniform(-50, 50), 52.4, -52.4, 52.58, -52.58]) if kind else rng.uniform(-50, 50)
+            by = rng.choice([rng.uniform(-30, 30), 33.95, -33.95, 34.08, -34.08, 3.0, -6.9]) if kind else rng.uniform(-30, 30)
+            st[i, k:k + 4] = np.float32([bx, by, rng.uniform(-2.5, 2.5), rng.uniform(-2.5, 2.5)])
+            P = st[i, :k].reshape(p, 12)
+            P[:, 0] = rng.uniform(-52, 52, p)
+            P[:, 1] = rng.uniform(-33, 33, p)
+            crowd = rng.integers(0, 7)
+            P[:crowd, 0] = bx + rng.uniform(-0.5, 0.5, crowd)
+            P[:crowd, 1] = by + rng.uniform(-0.5, 0.5, crowd)
+            P[:, 2:4] = rng.uniform(-0.4, 0.4, (p, 2))
+            P[:, 4] = rng.uniform(-180, 180, p)
+            P[:, 5] = rng.uniform(0, 8000, p)
+            P[:, 6] = rng.uniform(0.6, 1.0, p)
+            P[:, 7] = rng.uniform(0.5, 1.0, p)
+            P[:, 0:9] = P[:, 0:9].astype(np.float32)
+            P[:, 9:11] = 0
+            mode = int(rng.choice([2, 2, 2, 3, 4, 5, 6, 7]))
+            st[i, k + 4] = 0
+            st[i, k + 5] = rnd
+            st[i, k + 8:k + 11] = [mode, int(rng.integers(1, 3)) if mode != 2 else 0, int(rng.choice([0, 5, 98, 99]))]
+            st[i, k + 13] = int(rng.integers(0, 3))
+            st[i, k + 14] = 0.0
+            st[i, k + 15] = 0
+            st[i, k + 16] = int(rng.integers(0, 1 << 11)) << (11 * int(rng.integers(0, 2))) if mode == 2 and rng.uniform() < 0.5 else 0
+        sim.set_state_fg(st)
+        set_gpu_state_fg(env, st)
+        assert np.array_equal(gpu_state_fg(env), sim.get_state_fg())
+        act = H.random_commands(rng, n * p).reshape(n, 1, p, 4)
+        act[:, 0, :, 0] = np.where(rng.uniform(size=(n, p)) < 0.3, 3, act[:, 0, :, 0])
+        env.step_torch(torch.from_numpy(act))
+        sim.step(act.reshape(n, -1))
+        same_step(env, sim)
+        g = gpu_state_fg(env)
+        assert np.array_equal(g, sim.get_state_fg())
+        modes_after |= set(g[:, k + 8].astype(int).tolist())
+    assert {2, 3, 4, 5, 6, 7} <= modes_after
+    env.close()

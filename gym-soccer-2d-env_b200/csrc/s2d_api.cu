@@ -24,13 +24,18 @@ struct S2DSim {
   bool hetero = false;
   bool default_sp = false;  // cfg.sp == rcssserver defaults: use the constant-folded kernels
   bool bound = false;
-  // host-buffer pipeline (s2d_bind_pipeline / s2d_submit_host / s2d_wait_host): two slots of actions + outputs
+  // host-buffer pipeline (s2d_bind_pipeline_slot / s2d_submit_host / s2d_wait_host): up to kSlots slots of actions +
+  // outputs; slot 0 = the buffers of s2d_bind
   bool piped = false;
-  S2DBuffers pbuf[2];
-  KernelParams pkp[2];
+  S2DBuffers pbuf[S2D_MAX_PIPELINE_SLOTS];
+  KernelParams pkp[S2D_MAX_PIPELINE_SLOTS];
+  bool slot_bound[S2D_MAX_PIPELINE_SLOTS] = {false, false, false, false};
   cudaStream_t st_in = nullptr, st_compute = nullptr, st_out = nullptr;
-  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_kernel[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
-  bool used[2] = {false, false};
+  cudaEvent_t ev_in[S2D_MAX_PIPELINE_SLOTS] = {}, ev_kernel[S2D_MAX_PIPELINE_SLOTS] = {}, ev_out[S2D_MAX_PIPELINE_SLOTS] = {};
+  cudaEvent_t ev_user = nullptr;  // end of the last caller-stream operation that touched the shared state
+  bool used[S2D_MAX_PIPELINE_SLOTS] = {false, false, false, false};
+  bool user_pending = false;
+  int last_d2h_copies = 0;  // device-to-host copies the last host-buffer step issued (1 = the packed block)
   int grid = 0;
   uint64_t env_steps = 0;
   char err[512];
@@ -222,11 +227,12 @@ int s2d_destroy(S2DHandle h) {
       cudaStreamSynchronize(h->st_in);
       cudaStreamSynchronize(h->st_compute);
       cudaStreamSynchronize(h->st_out);
-      for (int k = 0; k < 2; ++k) {
-        cudaEventDestroy(h->ev_in[k]);
-        cudaEventDestroy(h->ev_kernel[k]);
-        cudaEventDestroy(h->ev_out[k]);
+      for (int k = 0; k < S2D_MAX_PIPELINE_SLOTS; ++k) {
+        if (h->ev_in[k]) cudaEventDestroy(h->ev_in[k]);
+        if (h->ev_kernel[k]) cudaEventDestroy(h->ev_kernel[k]);
+        if (h->ev_out[k]) cudaEventDestroy(h->ev_out[k]);
       }
+      if (h->ev_user) cudaEventDestroy(h->ev_user);
       cudaStreamDestroy(h->st_in);
       cudaStreamDestroy(h->st_compute);
       cudaStreamDestroy(h->st_out);
@@ -234,6 +240,36 @@ int s2d_destroy(S2DHandle h) {
   }
   delete h;
   return S2D_OK;
+}
+
+// ---- ordering between the caller's stream and the pipeline's internal streams -------------------------------
+// The state and the statistics are shared by every slot and by the caller-stream entry points; slot 0's actions and
+// outputs are the buffers of s2d_bind.  before_user_op makes the caller's stream wait (on the device, the host does not
+// block) for every kernel the pipeline has submitted and for the copies that still read slot 0's outputs;
+// after_user_op records where that caller-stream work ends so that the next s2d_submit_host waits for it.
+static int before_user_op(S2DSim* h, cudaStream_t s) {
+  if (!h->piped) return S2D_OK;
+  for (int k = 0; k < S2D_MAX_PIPELINE_SLOTS; ++k)
+    if (h->used[k]) S2D_CUDA(h, cudaStreamWaitEvent(s, h->ev_kernel[k], 0));
+  if (h->used[0]) S2D_CUDA(h, cudaStreamWaitEvent(s, h->ev_out[0], 0));
+  return S2D_OK;
+}
+static int after_user_op(S2DSim* h, cudaStream_t s) {
+  if (!h->piped) return S2D_OK;
+  S2D_CUDA(h, cudaEventRecord(h->ev_user, s));
+  h->user_pending = true;
+  return S2D_OK;
+}
+
+static void slot_params(S2DSim* h, int k) {
+  KernelParams& kp = h->pkp[k];
+  kp = h->kp;  // constants, state, stats, player types
+  kp.actions = h->pbuf[k].actions;
+  kp.obs = h->pbuf[k].obs;
+  kp.reward = h->pbuf[k].reward;
+  kp.done = h->pbuf[k].done;
+  kp.result = h->pbuf[k].result;
+  kp.terminal_obs = h->pbuf[k].terminal_obs;
 }
 
 int s2d_bind(S2DHandle h, const S2DBuffers* b) {
@@ -254,6 +290,52 @@ int s2d_bind(S2DHandle h, const S2DBuffers* b) {
   h->kp.terminal_obs = b->terminal_obs;
   h->kp.stats = static_cast<unsigned long long*>(b->stats);
   h->bound = true;
+  if (h->piped) {  // a re-bind (new action tensor, new state) reaches the pipeline's parameter blocks too
+    h->pbuf[0] = h->buf;
+    for (int k = 0; k < S2D_MAX_PIPELINE_SLOTS; ++k) {
+      if (!h->slot_bound[k]) continue;
+      h->pbuf[k].state = b->state;
+      h->pbuf[k].stats = b->stats;
+      slot_params(h, k);
+    }
+  }
+  return S2D_OK;
+}
+
+int s2d_fence(S2DHandle h, void* stream) {
+  if (!h) return S2D_ERR_INVALID;
+  if (!h->piped) return S2D_OK;
+  DeviceGuard guard(h->cfg.device);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (int rc = before_user_op(h, s)) return rc;
+  return after_user_op(h, s);
+}
+
+int s2d_clear(S2DHandle h, void* stream) {
+  if (!h) return S2D_ERR_INVALID;
+  if (!h->bound) return fail(h, S2D_ERR_UNBOUND, "s2d_bind has not been called");
+  DeviceGuard guard(h->cfg.device);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (int rc = before_user_op(h, s)) return rc;
+  S2D_CUDA(h, cudaMemsetAsync(h->buf.state, 0, s2d_state_bytes(&h->cfg), s));
+  S2D_CUDA(h, cudaMemsetAsync(h->buf.stats, 0, s2d_stats_bytes(&h->cfg), s));
+  h->env_steps = 0;
+  return after_user_op(h, s);
+}
+
+static size_t align256(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
+
+int s2d_output_layout(const S2DConfig* c, S2DOutputLayout* out) {
+  if (!c || !out || c->num_envs < 1) return S2D_ERR_INVALID;
+  const size_t n = static_cast<size_t>(c->num_envs), row = static_cast<size_t>(s2d_obs_dim(c)) * sizeof(float);
+  out->obs = 0;
+  out->reward = align256(n * row);
+  out->done = out->reward + align256(n * sizeof(float));
+  out->result = out->done + align256(n);
+  out->step_bytes = out->result + n;
+  out->bytes = out->result + align256(n);
+  out->terminal_obs = out->bytes;
+  out->bytes_with_terminal_obs = out->bytes + align256(n * row);
   return S2D_OK;
 }
 
@@ -261,21 +343,22 @@ int s2d_reset(S2DHandle h, const uint8_t* device_mask_or_null, void* stream) {
   if (!h) return S2D_ERR_INVALID;
   if (!h->bound) return fail(h, S2D_ERR_UNBOUND, "s2d_bind has not been called");
   DeviceGuard guard(h->cfg.device);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (int rc = before_user_op(h, s)) return rc;
   if (h->cfg.scenario == S2D_SCENARIO_FULLGAME) {
     const int np = 2 * h->cfg.players_per_side, ht = h->cfg.half_time_cycles;
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (h->hetero) fullgame_reset_kernel<true><<<h->grid, kFgBlock, 0, s>>>(h->kp, device_mask_or_null, np, ht);
     else fullgame_reset_kernel<false><<<h->grid, kFgBlock, 0, s>>>(h->kp, device_mask_or_null, np, ht);
   }
   else if (h->cfg.scenario == S2D_SCENARIO_SHOOT) {
-    if (h->cfg.noise) reset_kernel<S2D_SCENARIO_SHOOT, true><<<h->grid, kBlock, 0, static_cast<cudaStream_t>(stream)>>>(h->kp, device_mask_or_null);
-    else reset_kernel<S2D_SCENARIO_SHOOT, false><<<h->grid, kBlock, 0, static_cast<cudaStream_t>(stream)>>>(h->kp, device_mask_or_null);
+    if (h->cfg.noise) reset_kernel<S2D_SCENARIO_SHOOT, true><<<h->grid, kBlock, 0, s>>>(h->kp, device_mask_or_null);
+    else reset_kernel<S2D_SCENARIO_SHOOT, false><<<h->grid, kBlock, 0, s>>>(h->kp, device_mask_or_null);
   } else {
-    if (h->cfg.noise) reset_kernel<S2D_SCENARIO_REACHBALL, true><<<h->grid, kBlock, 0, static_cast<cudaStream_t>(stream)>>>(h->kp, device_mask_or_null);
-    else reset_kernel<S2D_SCENARIO_REACHBALL, false><<<h->grid, kBlock, 0, static_cast<cudaStream_t>(stream)>>>(h->kp, device_mask_or_null);
+    if (h->cfg.noise) reset_kernel<S2D_SCENARIO_REACHBALL, true><<<h->grid, kBlock, 0, s>>>(h->kp, device_mask_or_null);
+    else reset_kernel<S2D_SCENARIO_REACHBALL, false><<<h->grid, kBlock, 0, s>>>(h->kp, device_mask_or_null);
   }
   S2D_CUDA(h, cudaGetLastError());
-  return S2D_OK;
+  return after_user_op(h, s);
 }
 
 // one launch of the scenario's step kernel with the given parameter block
@@ -317,68 +400,105 @@ int s2d_step(S2DHandle h, int k_substeps, void* stream) {
   if (k_substeps < 1 || k_substeps > kMaxSubsteps)
     return fail(h, S2D_ERR_INVALID, "k_substeps must be in 1..%d", kMaxSubsteps);
   DeviceGuard guard(h->cfg.device);
-  S2D_CUDA(h, launch_step(h, h->kp, k_substeps, static_cast<cudaStream_t>(stream)));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (int rc = before_user_op(h, s)) return rc;
+  S2D_CUDA(h, launch_step(h, h->kp, k_substeps, s));
   h->env_steps += static_cast<uint64_t>(h->cfg.num_envs) * static_cast<uint64_t>(k_substeps);
+  return after_user_op(h, s);
+}
+
+// Device-to-host copies of one step's outputs.  When the host pointers mirror the device layout (one block carved as
+// s2d_output_layout says - or any other common layout with obs first and result last) the outputs leave in ONE copy.
+static int copy_outputs(S2DSim* h, const S2DBuffers& b, float* h_obs, float* h_reward, uint8_t* h_done, uint8_t* h_result,
+                        cudaStream_t s) {
+  const size_t n = static_cast<size_t>(h->cfg.num_envs);
+  const size_t obs_bytes = n * s2d_obs_dim(&h->cfg) * sizeof(float);
+  if (h_obs && h_reward && h_done && h_result) {
+    const char* d0 = reinterpret_cast<const char*>(b.obs);
+    const char* h0 = reinterpret_cast<const char*>(h_obs);
+    const ptrdiff_t dr = reinterpret_cast<const char*>(b.reward) - d0, dd = reinterpret_cast<const char*>(b.done) - d0,
+                    ds = reinterpret_cast<const char*>(b.result) - d0;
+    const bool mirrored = reinterpret_cast<const char*>(h_reward) - h0 == dr && reinterpret_cast<const char*>(h_done) - h0 == dd &&
+                          reinterpret_cast<const char*>(h_result) - h0 == ds;
+    const bool ordered = dr >= static_cast<ptrdiff_t>(obs_bytes) && dd >= dr + static_cast<ptrdiff_t>(n * sizeof(float)) &&
+                         ds >= dd + static_cast<ptrdiff_t>(n);
+    // one block: at most 3 x 255 bytes of padding travel along
+    if (mirrored && ordered && static_cast<size_t>(ds) + n <= obs_bytes + n * 6 + 3 * 256) {
+      S2D_CUDA(h, cudaMemcpyAsync(h_obs, b.obs, static_cast<size_t>(ds) + n, cudaMemcpyDeviceToHost, s));
+      h->last_d2h_copies = 1;
+      return S2D_OK;
+    }
+  }
+  if (h_obs) S2D_CUDA(h, cudaMemcpyAsync(h_obs, b.obs, obs_bytes, cudaMemcpyDeviceToHost, s));
+  if (h_reward) S2D_CUDA(h, cudaMemcpyAsync(h_reward, b.reward, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+  if (h_done) S2D_CUDA(h, cudaMemcpyAsync(h_done, b.done, n, cudaMemcpyDeviceToHost, s));
+  if (h_result) S2D_CUDA(h, cudaMemcpyAsync(h_result, b.result, n, cudaMemcpyDeviceToHost, s));
+  h->last_d2h_copies = (h_obs != nullptr) + (h_reward != nullptr) + (h_done != nullptr) + (h_result != nullptr);
   return S2D_OK;
 }
 
 // ---- pipelined host-buffer stepping ----------------------------------------------------------------------
-// Slot s owns a device actions buffer and device output buffers (slot 0 = the buffers of s2d_bind, slot 1 = the ones
+// Slot s owns a device actions buffer and device output buffers (slot 0 = the buffers of s2d_bind, the others are
 // given here).  s2d_submit_host enqueues, on three internal streams, H2D(actions) -> step kernel -> D2H(outputs) for
-// one slot; consecutive submissions alternate slots, so the copies of step i overlap the kernel and the copies of
-// step i+1.  The step kernels themselves stay in submission order (they share the state).
+// one slot; consecutive submissions rotate the slots, so the copies of step i overlap the kernel and the copies of
+// the following steps.  The step kernels themselves stay in submission order (they share the state).
 
-int s2d_bind_pipeline(S2DHandle h, const S2DBuffers* second) {
+int s2d_bind_pipeline_slot(S2DHandle h, int slot, const S2DBuffers* second) {
   if (!h) return S2D_ERR_INVALID;
   if (!h->bound) return fail(h, S2D_ERR_UNBOUND, "s2d_bind must come first");
+  if (slot < 1 || slot >= S2D_MAX_PIPELINE_SLOTS) return fail(h, S2D_ERR_INVALID, "slot must be in 1..%d (slot 0 = the buffers of s2d_bind)", S2D_MAX_PIPELINE_SLOTS - 1);
   if (!second || !second->actions || !second->obs || !second->reward || !second->done || !second->result)
-    return fail(h, S2D_ERR_UNBOUND, "the second slot needs actions, obs, reward, done and result buffers");
-  if ((reinterpret_cast<uintptr_t>(second->actions) & 15) || (reinterpret_cast<uintptr_t>(second->obs) & 15))
-    return fail(h, S2D_ERR_INVALID, "actions / obs must be 16-byte aligned");
+    return fail(h, S2D_ERR_UNBOUND, "a pipeline slot needs actions, obs, reward, done and result buffers");
+  if ((reinterpret_cast<uintptr_t>(second->actions) & 15) || (reinterpret_cast<uintptr_t>(second->obs) & 15) ||
+      (second->terminal_obs && (reinterpret_cast<uintptr_t>(second->terminal_obs) & 15)))
+    return fail(h, S2D_ERR_INVALID, "actions / obs / terminal_obs must be 16-byte aligned");
   DeviceGuard guard(h->cfg.device);
   if (!h->st_in) {
     S2D_CUDA(h, cudaStreamCreateWithFlags(&h->st_in, cudaStreamNonBlocking));
     S2D_CUDA(h, cudaStreamCreateWithFlags(&h->st_compute, cudaStreamNonBlocking));
     S2D_CUDA(h, cudaStreamCreateWithFlags(&h->st_out, cudaStreamNonBlocking));
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < S2D_MAX_PIPELINE_SLOTS; ++k) {
       S2D_CUDA(h, cudaEventCreateWithFlags(&h->ev_in[k], cudaEventDisableTiming));
       S2D_CUDA(h, cudaEventCreateWithFlags(&h->ev_kernel[k], cudaEventDisableTiming));
       S2D_CUDA(h, cudaEventCreateWithFlags(&h->ev_out[k], cudaEventDisableTiming));
     }
+    S2D_CUDA(h, cudaEventCreateWithFlags(&h->ev_user, cudaEventDisableTiming));
   }
+  if (h->used[slot]) S2D_CUDA(h, cudaEventSynchronize(h->ev_out[slot]));  // re-binding a slot that is in flight
   h->pbuf[0] = h->buf;
-  h->pbuf[1] = h->buf;  // state and stats are shared
-  h->pbuf[1].actions = second->actions;
-  h->pbuf[1].obs = second->obs;
-  h->pbuf[1].reward = second->reward;
-  h->pbuf[1].done = second->done;
-  h->pbuf[1].result = second->result;
-  h->pbuf[1].terminal_obs = second->terminal_obs;
-  for (int k = 0; k < 2; ++k) {
-    h->pkp[k] = h->kp;
-    h->pkp[k].actions = h->pbuf[k].actions;
-    h->pkp[k].obs = h->pbuf[k].obs;
-    h->pkp[k].reward = h->pbuf[k].reward;
-    h->pkp[k].done = h->pbuf[k].done;
-    h->pkp[k].result = h->pbuf[k].result;
-    h->pkp[k].terminal_obs = h->pbuf[k].terminal_obs;
-    h->used[k] = false;
-  }
+  h->slot_bound[0] = true;
+  slot_params(h, 0);
+  h->pbuf[slot] = h->buf;  // state and stats are shared
+  h->pbuf[slot].actions = second->actions;
+  h->pbuf[slot].obs = second->obs;
+  h->pbuf[slot].reward = second->reward;
+  h->pbuf[slot].done = second->done;
+  h->pbuf[slot].result = second->result;
+  h->pbuf[slot].terminal_obs = second->terminal_obs;
+  h->slot_bound[slot] = true;
+  h->used[slot] = false;
+  slot_params(h, slot);
   h->piped = true;
   return S2D_OK;
 }
+
+int s2d_bind_pipeline(S2DHandle h, const S2DBuffers* second) { return s2d_bind_pipeline_slot(h, 1, second); }
 
 int s2d_submit_host(S2DHandle h, int k_substeps, int slot, const void* h_actions, float* h_obs, float* h_reward,
                     uint8_t* h_done, uint8_t* h_result) {
   if (!h) return S2D_ERR_INVALID;
   if (!h->piped) return fail(h, S2D_ERR_UNBOUND, "s2d_bind_pipeline has not been called");
-  if (slot < 0 || slot > 1) return fail(h, S2D_ERR_INVALID, "slot must be 0 or 1");
+  if (slot < 0 || slot >= S2D_MAX_PIPELINE_SLOTS || !h->slot_bound[slot]) return fail(h, S2D_ERR_INVALID, "slot %d is not bound", slot);
   if (!h_actions) return fail(h, S2D_ERR_INVALID, "h_actions is NULL");
   if (k_substeps < 1 || k_substeps > kMaxSubsteps)
     return fail(h, S2D_ERR_INVALID, "k_substeps must be in 1..%d", kMaxSubsteps);
   DeviceGuard guard(h->cfg.device);
-  const size_t n = static_cast<size_t>(h->cfg.num_envs);
   const S2DBuffers& b = h->pbuf[slot];
+  if (h->user_pending) {  // caller-stream work on the shared state / slot 0's buffers comes first
+    S2D_CUDA(h, cudaStreamWaitEvent(h->st_in, h->ev_user, 0));
+    S2D_CUDA(h, cudaStreamWaitEvent(h->st_compute, h->ev_user, 0));
+    h->user_pending = false;
+  }
   // actions[slot] may be overwritten once the kernel that read them is done; outputs[slot] once their D2H is done
   if (h->used[slot]) S2D_CUDA(h, cudaStreamWaitEvent(h->st_in, h->ev_kernel[slot], 0));
   S2D_CUDA(h, cudaMemcpyAsync(b.actions, h_actions, s2d_action_bytes(&h->cfg) * k_substeps, cudaMemcpyHostToDevice, h->st_in));
@@ -388,10 +508,7 @@ int s2d_submit_host(S2DHandle h, int k_substeps, int slot, const void* h_actions
   S2D_CUDA(h, launch_step(h, h->pkp[slot], k_substeps, h->st_compute));
   S2D_CUDA(h, cudaEventRecord(h->ev_kernel[slot], h->st_compute));
   S2D_CUDA(h, cudaStreamWaitEvent(h->st_out, h->ev_kernel[slot], 0));
-  if (h_obs) S2D_CUDA(h, cudaMemcpyAsync(h_obs, b.obs, n * s2d_obs_dim(&h->cfg) * sizeof(float), cudaMemcpyDeviceToHost, h->st_out));
-  if (h_reward) S2D_CUDA(h, cudaMemcpyAsync(h_reward, b.reward, n * sizeof(float), cudaMemcpyDeviceToHost, h->st_out));
-  if (h_done) S2D_CUDA(h, cudaMemcpyAsync(h_done, b.done, n, cudaMemcpyDeviceToHost, h->st_out));
-  if (h_result) S2D_CUDA(h, cudaMemcpyAsync(h_result, b.result, n, cudaMemcpyDeviceToHost, h->st_out));
+  if (int rc = copy_outputs(h, b, h_obs, h_reward, h_done, h_result, h->st_out)) return rc;
   S2D_CUDA(h, cudaEventRecord(h->ev_out[slot], h->st_out));
   h->used[slot] = true;
   h->env_steps += static_cast<uint64_t>(h->cfg.num_envs) * static_cast<uint64_t>(k_substeps);
@@ -401,7 +518,7 @@ int s2d_submit_host(S2DHandle h, int k_substeps, int slot, const void* h_actions
 int s2d_wait_host(S2DHandle h, int slot) {
   if (!h) return S2D_ERR_INVALID;
   if (!h->piped) return fail(h, S2D_ERR_UNBOUND, "s2d_bind_pipeline has not been called");
-  if (slot < 0 || slot > 1) return fail(h, S2D_ERR_INVALID, "slot must be 0 or 1");
+  if (slot < 0 || slot >= S2D_MAX_PIPELINE_SLOTS || !h->slot_bound[slot]) return fail(h, S2D_ERR_INVALID, "slot %d is not bound", slot);
   if (!h->used[slot]) return S2D_OK;
   DeviceGuard guard(h->cfg.device);
   S2D_CUDA(h, cudaEventSynchronize(h->ev_out[slot]));
@@ -417,15 +534,12 @@ int s2d_step_host(S2DHandle h, int k_substeps, const void* h_actions, float* h_o
     return fail(h, S2D_ERR_INVALID, "k_substeps must be in 1..%d", kMaxSubsteps);
   DeviceGuard guard(h->cfg.device);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const size_t n = static_cast<size_t>(h->cfg.num_envs);
+  if (int rc = before_user_op(h, s)) return rc;
   S2D_CUDA(h, cudaMemcpyAsync(h->buf.actions, h_actions, s2d_action_bytes(&h->cfg) * k_substeps, cudaMemcpyHostToDevice, s));
   const int rc = s2d_step(h, k_substeps, stream);
   if (rc != S2D_OK) return rc;
-  if (h_obs) S2D_CUDA(h, cudaMemcpyAsync(h_obs, h->buf.obs, n * s2d_obs_dim(&h->cfg) * sizeof(float), cudaMemcpyDeviceToHost, s));
-  if (h_reward) S2D_CUDA(h, cudaMemcpyAsync(h_reward, h->buf.reward, n * sizeof(float), cudaMemcpyDeviceToHost, s));
-  if (h_done) S2D_CUDA(h, cudaMemcpyAsync(h_done, h->buf.done, n, cudaMemcpyDeviceToHost, s));
-  if (h_result) S2D_CUDA(h, cudaMemcpyAsync(h_result, h->buf.result, n, cudaMemcpyDeviceToHost, s));
-  return S2D_OK;
+  if (int rc2 = copy_outputs(h, h->buf, h_obs, h_reward, h_done, h_result, s)) return rc2;
+  return after_user_op(h, s);
 }
 
 int s2d_stats(S2DHandle h, S2DStats* out, void* stream) {
@@ -433,6 +547,7 @@ int s2d_stats(S2DHandle h, S2DStats* out, void* stream) {
   if (!h->bound) return fail(h, S2D_ERR_UNBOUND, "s2d_bind has not been called");
   DeviceGuard guard(h->cfg.device);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (int rc = before_user_op(h, s)) return rc;
   std::vector<unsigned long long> host(kStatSlots * kStatWords);
   S2D_CUDA(h, cudaMemcpyAsync(host.data(), h->buf.stats, host.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
   S2D_CUDA(h, cudaStreamSynchronize(s));
@@ -456,9 +571,10 @@ int s2d_stats_reset(S2DHandle h, void* stream) {
   if (!h) return S2D_ERR_INVALID;
   if (!h->bound) return fail(h, S2D_ERR_UNBOUND, "s2d_bind has not been called");
   DeviceGuard guard(h->cfg.device);
+  if (int rc = before_user_op(h, static_cast<cudaStream_t>(stream))) return rc;
   S2D_CUDA(h, cudaMemsetAsync(h->buf.stats, 0, s2d_stats_bytes(&h->cfg), static_cast<cudaStream_t>(stream)));
   h->env_steps = 0;
-  return S2D_OK;
+  return after_user_op(h, static_cast<cudaStream_t>(stream));
 }
 
 int s2d_export_env(S2DHandle h, int64_t i, S2DEnvSnapshot* out, void* stream) {
@@ -467,6 +583,7 @@ int s2d_export_env(S2DHandle h, int64_t i, S2DEnvSnapshot* out, void* stream) {
   if (i < 0 || i >= h->cfg.num_envs) return fail(h, S2D_ERR_INVALID, "env index %lld out of range", static_cast<long long>(i));
   DeviceGuard guard(h->cfg.device);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (int rc = before_user_op(h, s)) return rc;
   const char* base = static_cast<const char*>(h->buf.state);
   const size_t n = static_cast<size_t>(h->cfg.num_envs);
   if (h->cfg.scenario == S2D_SCENARIO_FULLGAME) {
@@ -647,11 +764,10 @@ int s2d_set_player_types(S2DHandle h, const S2DPlayerType* types, int n, const u
   DeviceGuard guard(h->cfg.device);
   if (!h->d_types) S2D_CUDA(h, cudaMalloc(&h->d_types, sizeof(rows)));
   S2D_CUDA(h, cudaMemcpy(h->d_types, rows, sizeof(rows), cudaMemcpyHostToDevice));  // synchronous: later launches see it
-  KernelParams* all[3] = {&h->kp, &h->pkp[0], &h->pkp[1]};
-  for (KernelParams* kp : all) {
-    kp->player_types = h->d_types;
-    memcpy(kp->type_of, type_of, sizeof(type_of));
-  }
+  h->kp.player_types = h->d_types;
+  memcpy(h->kp.type_of, type_of, sizeof(type_of));
+  for (int k = 0; k < S2D_MAX_PIPELINE_SLOTS; ++k)
+    if (h->slot_bound[k]) slot_params(h, k);
   h->hetero = true;
   return S2D_OK;
 }
@@ -676,6 +792,7 @@ static int rollout_mlp(S2DHandle h, const S2DMlpPolicy* policy, int k_substeps, 
   const int outputs = actor ? (mode == S2D_ACT_TURNING ? 4 : 1) : h->cfg.action_space_size;
   const MlpWeights w{policy->w1, policy->b1, policy->w2, policy->b2, policy->w3, policy->b3, kObsDim, outputs};
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (int rc = before_user_op(h, s)) return rc;
   uint8_t* ao = static_cast<uint8_t*>(actions_out);
   float* qo = static_cast<float*>(q_out);
 #define S2D_ROLLOUT(SCN, ACT)                                                                                         \
@@ -701,7 +818,7 @@ static int rollout_mlp(S2DHandle h, const S2DMlpPolicy* policy, int k_substeps, 
 #undef S2D_ROLLOUT
   S2D_CUDA(h, cudaGetLastError());
   h->env_steps += static_cast<uint64_t>(h->cfg.num_envs) * static_cast<uint64_t>(k_substeps);
-  return S2D_OK;
+  return after_user_op(h, s);
 }
 
 int s2d_rollout_mlp(S2DHandle h, const S2DMlpPolicy* policy, int k_substeps, float epsilon, void* actions_out,
@@ -723,6 +840,15 @@ int s2d_rollout_actor_collect(S2DHandle h, const S2DMlpPolicy* actor, int k_subs
   const TrajOut traj = t ? TrajOut{t->obs, nullptr, t->actions_f, t->reward, t->done}
                          : TrajOut{nullptr, nullptr, nullptr, nullptr, nullptr};
   return rollout_mlp(h, actor, k_substeps, noise, nullptr, nullptr, traj, true, stream);
+}
+
+int s2d_pipeline_info(S2DHandle h, int* slots_bound, int* d2h_copies_last_step) {
+  if (!h) return S2D_ERR_INVALID;
+  int nb = 0;
+  for (int k = 0; k < S2D_MAX_PIPELINE_SLOTS; ++k) nb += h->slot_bound[k] ? 1 : 0;
+  if (slots_bound) *slots_bound = nb;
+  if (d2h_copies_last_step) *d2h_copies_last_step = h->last_d2h_copies;
+  return S2D_OK;
 }
 
 int s2d_launch_info(S2DHandle h, int* grid, int* block, int* kernels_per_step) {

@@ -244,7 +244,7 @@ __device__ __forceinline__ void fg_reset(Episode& p, Match& m, const KernelParam
                                          int pps) {
   m.score_l = 0;
   m.score_r = 0;
-  fg_place_player(p, P, gid, m.episode, lane, pps, 0);
+  if (lane < 2 * pps) fg_place_player(p, P, gid, m.episode, lane, pps, 0);  // (idle lanes would index past the formation)
   recover(p, sp);
   p.bx = p.by = p.bvx = p.bvy = 0.0f;
   m.episode += 1u;
@@ -684,7 +684,7 @@ __global__ void __launch_bounds__(kFgBlock, S2D_FG_MIN_BLOCKS) fullgame_step_ker
     if (done) {
       any_done = 1;
       last_result = static_cast<uint32_t>(rs);
-      if (lane == 0) {
+      if (lane == 0 && !m.done_flag) {  // (a finished match stepped on with auto_reset off is tallied once)
         unsigned long long* slot = P.stats + static_cast<size_t>(env % kStatSlots) * kStatWords;
         atomicAdd(slot + ST_EPISODES, 1ull);
         atomicAdd(slot + (rs == 1 ? ST_GOALS : rs == 2 ? ST_OUTS : ST_TIMEOUTS), 1ull);

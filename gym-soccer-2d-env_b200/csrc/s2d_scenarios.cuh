@@ -103,6 +103,11 @@ struct LaunchOut {
   uint32_t ep_steps = 0;
   double ret = 0.0;
   __device__ __forceinline__ void count(int result) { ended = ((ended & 0x3fffffffu) + (1u << (10 * (result - 1)))) | (static_cast<uint32_t>(result) << 30); }
+  // an episode that had already ended (auto_reset off: S2D_FLAG_DONE) and is stepped on: done / result are reported
+  // again, the statistics are not
+  __device__ __forceinline__ void report_only(int result) { ended = (ended & 0x3fffffffu) | (static_cast<uint32_t>(result) << 30); }
+  // finished episodes to tally: at most one per launch can be a re-report, and then it is the only ending
+  __device__ __forceinline__ bool any_ended() const { return ended != 0; }
   __device__ __forceinline__ uint32_t goals() const { return ended & 0x3ffu; }
   __device__ __forceinline__ uint32_t outs() const { return (ended >> 10) & 0x3ffu; }
   __device__ __forceinline__ uint32_t timeouts() const { return (ended >> 20) & 0x3ffu; }
@@ -409,9 +414,13 @@ __device__ __forceinline__ int substep(Episode& e, const KernelParams& P, const 
   e.ep_return += rw;
   if (DEFER_END) return rs;
   if (done) {
-    out.count(rs);
-    out.ep_steps += static_cast<uint32_t>(e.step_number);
-    out.ret += static_cast<double>(e.ep_return);
+    if (e.flags & S2D_FLAG_DONE) {
+      out.report_only(rs);
+    } else {
+      out.count(rs);
+      out.ep_steps += static_cast<uint32_t>(e.step_number);
+      out.ret += static_cast<double>(e.ep_return);
+    }
     if (P.terminal_obs) {
       float row[kObsDim];
       scenario_obs<SCN>(e, row);
@@ -450,7 +459,7 @@ __device__ __forceinline__ void warp_store_obs(float* __restrict__ dst, int64_t 
 // warp-level sum of the launch's episode statistics, then one lane adds them to a stats slot
 __device__ __forceinline__ void flush_tally(const LaunchOut& t, unsigned long long* stats) {
   const unsigned full = 0xffffffffu;
-  if (!__any_sync(full, t.ended != 0)) return;
+  if (!__any_sync(full, (t.ended & 0x3fffffffu) != 0)) return;
   const uint32_t g = __reduce_add_sync(full, t.goals()), o = __reduce_add_sync(full, t.outs()),
                  to = __reduce_add_sync(full, t.timeouts()), st = __reduce_add_sync(full, t.ep_steps);
   double r = t.ret;
@@ -513,9 +522,13 @@ __device__ __forceinline__ void end_of_episode(Episode& e, const KernelParams& P
   unsigned pending = __ballot_sync(full, done);
   if (pending == 0u) return;
   if (done) {
-    out.count(rs);
-    out.ep_steps += static_cast<uint32_t>(e.step_number);
-    out.ret += static_cast<double>(e.ep_return);
+    if (e.flags & S2D_FLAG_DONE) {
+      out.report_only(rs);
+    } else {
+      out.count(rs);
+      out.ep_steps += static_cast<uint32_t>(e.step_number);
+      out.ret += static_cast<double>(e.ep_return);
+    }
     if (P.terminal_obs && valid) {
       float row[kObsDim];
       scenario_obs<SCN>(e, row);

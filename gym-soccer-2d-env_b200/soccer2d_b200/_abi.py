@@ -8,7 +8,8 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-ABI_VERSION = 9
+ABI_VERSION = 10
+MAX_PIPELINE_SLOTS = 4
 
 # ---- constants (mirror include/soccer2d.h) ----------------------------------------------------------
 S2D_OK, S2D_ERR_INVALID, S2D_ERR_UNBOUND, S2D_ERR_CUDA, S2D_ERR_NO_DEVICE = 0, -1, -2, -3, -4
@@ -62,6 +63,12 @@ class Buffers(C.Structure):
         ("state", C.c_void_p), ("actions", C.c_void_p), ("obs", C.c_void_p), ("reward", C.c_void_p),
         ("done", C.c_void_p), ("result", C.c_void_p), ("terminal_obs", C.c_void_p), ("stats", C.c_void_p),
     ]
+
+
+class OutputLayout(C.Structure):
+    """S2DOutputLayout: byte offsets of obs | reward | done | result (| terminal_obs) inside one output block"""
+    _fields_ = [(n, C.c_size_t) for n in
+                "obs reward done result step_bytes terminal_obs bytes bytes_with_terminal_obs".split()]
 
 
 class Stats(C.Structure):
@@ -131,11 +138,16 @@ SIGNATURES = {
     "s2d_step": (C.c_int, [_H, C.c_int, C.c_void_p]),
     "s2d_step_host": (C.c_int, [_H, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "s2d_bind_pipeline": (C.c_int, [_H, C.POINTER(Buffers)]),
+    "s2d_bind_pipeline_slot": (C.c_int, [_H, C.c_int, C.POINTER(Buffers)]),
+    "s2d_output_layout": (C.c_int, [C.POINTER(Config), C.POINTER(OutputLayout)]),
+    "s2d_fence": (C.c_int, [_H, C.c_void_p]),
+    "s2d_clear": (C.c_int, [_H, C.c_void_p]),
     "s2d_submit_host": (C.c_int, [_H, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "s2d_wait_host": (C.c_int, [_H, C.c_int]),
     "s2d_stats": (C.c_int, [_H, C.POINTER(Stats), C.c_void_p]),
     "s2d_stats_reset": (C.c_int, [_H, C.c_void_p]),
     "s2d_export_env": (C.c_int, [_H, C.c_int64, C.POINTER(EnvSnapshot), C.c_void_p]),
+    "s2d_pipeline_info": (C.c_int, [_H, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "s2d_launch_info": (C.c_int, [_H, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "s2d_generate_player_types": (C.c_int, [C.c_uint64, C.POINTER(ServerParam), C.POINTER(PlayerType), C.c_int]),
     "s2d_set_player_types": (C.c_int, [_H, C.POINTER(PlayerType), C.c_int, C.POINTER(C.c_uint8)]),

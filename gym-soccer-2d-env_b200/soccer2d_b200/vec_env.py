@@ -48,6 +48,26 @@ def _stream_ptr(device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
 
+def _carve(block: torch.Tensor, offset: int, shape, dtype) -> torch.Tensor:
+    """typed view of `shape` at byte `offset` of a uint8 block (offsets of s2d_output_layout are 256-byte aligned)"""
+    shape = (shape,) if isinstance(shape, int) else tuple(shape)
+    nbytes = int(np.prod(shape)) * torch.empty((), dtype=dtype).element_size()
+    return block[offset:offset + nbytes].view(dtype).view(shape)
+
+
+class _SharedInfo(dict):
+    """The info dict of every env whose episode goes on: ONE object shared by all of them (step_wait must not build
+    num_envs dicts per step).  Read-only; `.copy()` gives a plain dict, which is what SB3's VecMonitor mutates."""
+
+    def _ro(self, *a, **k):
+        raise TypeError("the info dict of a running episode is shared between envs; copy() it before writing")
+
+    __setitem__ = __delitem__ = update = pop = popitem = clear = setdefault = _ro
+
+
+_RUNNING = _SharedInfo(result=None)
+
+
 class Soccer2DVecEnv(_VecEnvBase):
     """`num_envs` ReachBall episodes on one GPU.
 
@@ -181,12 +201,14 @@ class Soccer2DVecEnv(_VecEnvBase):
         else:
             self.actions = io((n, k, 4), torch.float32)
         assert self.actions.numel() * self.actions.element_size() == self.lib.s2d_action_bytes(C.byref(cfg)) * k
-        self.obs = io((n, self.obs_dim), torch.float32)
-        self.reward = io(n, torch.float32)
-        self.done_u8 = io(n, torch.uint8)
+        # obs | reward | done | result (| terminal_obs) are carved out of ONE block (s2d_output_layout), so that the
+        # host-buffer calls can bring a step's outputs back with a single device-to-host copy
+        self.layout = lay = _abi.OutputLayout()
+        _abi.check(self.lib.s2d_output_layout(C.byref(cfg), C.byref(lay)))
+        self._with_term = bool(terminal_obs)
+        self.out_block = io(lay.bytes_with_terminal_obs if terminal_obs else lay.bytes, torch.uint8)
+        self.obs, self.reward, self.done_u8, self.result, self.terminal_obs = self._carve_outputs(self.out_block)
         self.done = self.done_u8.view(torch.bool)
-        self.result = io(n, torch.uint8)
-        self.terminal_obs = io((n, self.obs_dim), torch.float32) if terminal_obs else None
         self.stats_buf = torch.zeros(self.lib.s2d_stats_bytes(C.byref(cfg)), dtype=torch.uint8, device=dev)
         self._bufs = bufs = _abi.Buffers(
             state=self.state.data_ptr(), actions=self.actions.data_ptr(), obs=self.obs.data_ptr(),
@@ -196,6 +218,7 @@ class Soccer2DVecEnv(_VecEnvBase):
         self._pinned = None
         self._pipe = None
         self._pending = None
+        self._user_dirty = False
         self.player_types = None
         self.type_of_player = None
         if hetero_seed is not None:
@@ -206,7 +229,22 @@ class Soccer2DVecEnv(_VecEnvBase):
             self.set_player_types(types, pick)
         if _VecEnvBase is not object:
             _VecEnvBase.__init__(self, self.num_envs, self.observation_space, self.action_space)
+        self.render_mode = None  # soccer_2d_env.py:36; SB3 reads it with get_attr("render_mode")
         self._closed = False
+
+    def _carve_outputs(self, block: torch.Tensor):
+        lay, n = self.layout, self.num_envs
+        return (_carve(block, lay.obs, (n, self.obs_dim), torch.float32), _carve(block, lay.reward, n, torch.float32),
+                _carve(block, lay.done, n, torch.uint8), _carve(block, lay.result, n, torch.uint8),
+                _carve(block, lay.terminal_obs, (n, self.obs_dim), torch.float32) if self._with_term else None)
+
+    def _pinned_outputs(self) -> dict:
+        """one pinned host block with the device block's layout: a step's outputs arrive in ONE copy"""
+        block = torch.empty(self.layout.bytes, dtype=torch.uint8, pin_memory=True)
+        self._with_term, keep = False, self._with_term
+        obs, reward, done, result, _ = self._carve_outputs(block)
+        self._with_term = keep
+        return dict(block=block, obs=obs, reward=reward, done=done, result=result)
 
     # ---- torch-native API: device tensors in, device tensors out, no host sync ------------------------
     def reset_torch(self, mask: torch.Tensor | None = None) -> torch.Tensor:
@@ -219,15 +257,23 @@ class Soccer2DVecEnv(_VecEnvBase):
             assert mask.numel() == self.num_envs
             ptr = mask.data_ptr()
         _abi.check(self.lib.s2d_reset(self.handle, ptr, _stream_ptr(self.device)), self.handle)
+        self._user_dirty = True
         return self.obs
+
+    def _fence(self) -> None:
+        """order this stream against the host-buffer pipeline in both directions (s2d_fence); no-op without one"""
+        if self._pipe is not None:
+            _abi.check(self.lib.s2d_fence(self.handle, _stream_ptr(self.device)), self.handle)
 
     def step_torch(self, actions: torch.Tensor | None = None):
         """One launch = `substeps` cycles of every env.  `actions=None` uses what is already in
         `self.actions` (a policy may write there directly).  Returns (obs, reward, done, result): views of
         the persistent tensors, valid until the next step."""
         if actions is not None:
+            self._fence()  # slot 0's kernel may still be reading the tensor this copy overwrites
             self.actions.copy_(actions.to(self.device).reshape(self.actions.shape), non_blocking=True)
         _abi.check(self.lib.s2d_step(self.handle, self.substeps, _stream_ptr(self.device)), self.handle)
+        self._user_dirty = True
         return self.obs, self.reward, self.done, self.result
 
     def bind_actions(self, actions: torch.Tensor) -> None:
@@ -244,9 +290,8 @@ class Soccer2DVecEnv(_VecEnvBase):
         """Pinned host staging tensors: 'actions' (fill it in place for zero-copy submission) and the
         outputs 'obs', 'reward', 'done', 'result' that step_host fills."""
         if self._pinned is None:
-            pin = lambda t: torch.empty(t.shape, dtype=t.dtype, pin_memory=True)  # noqa: E731
-            self._pinned = dict(actions=pin(self.actions), obs=pin(self.obs), reward=pin(self.reward),
-                                done=pin(self.done_u8), result=pin(self.result))
+            self._pinned = dict(self._pinned_outputs(),
+                                actions=torch.empty(self.actions.shape, dtype=self.actions.dtype, pin_memory=True))
         return self._pinned
 
     def step_host(self, actions=None):
@@ -276,34 +321,38 @@ class Soccer2DVecEnv(_VecEnvBase):
         return p["obs"].numpy(), p["reward"].numpy(), p["done"].numpy().view(np.bool_), p["result"].numpy()
 
     # ---- pipelined host API: submit step i+1 while the results of step i are still coming back ---------
-    def enable_pipeline(self) -> None:
-        """Allocate the second slot (device actions + outputs, pinned host outputs) and bind it."""
+    def enable_pipeline(self, slots: int = 3) -> None:
+        """Allocate `slots` - 1 further slots (device actions + output block, pinned host output block) and bind them;
+        slot 0 = this env's own buffers.  With three slots the device-to-host copy of step i, the kernel of step i + 1
+        and the host-to-device copy of step i + 2 run at the same time."""
         if getattr(self, "_pipe", None) is not None:
             return
+        if not 2 <= slots <= _abi.MAX_PIPELINE_SLOTS:
+            raise ValueError(f"slots must be in 2..{_abi.MAX_PIPELINE_SLOTS}")
         dev = self.device
-        like = lambda t: torch.zeros_like(t, device=dev)  # noqa: E731
-        pin = lambda t: torch.empty(t.shape, dtype=t.dtype, pin_memory=True)  # noqa: E731
-        second = dict(actions=like(self.actions), obs=like(self.obs), reward=like(self.reward), done=like(self.done_u8),
-                      result=like(self.result),
-                      terminal_obs=like(self.terminal_obs) if self.terminal_obs is not None else None)
-        b = _abi.Buffers(state=self.state.data_ptr(), actions=second["actions"].data_ptr(), obs=second["obs"].data_ptr(),
-                         reward=second["reward"].data_ptr(), done=second["done"].data_ptr(),
-                         result=second["result"].data_ptr(),
-                         terminal_obs=second["terminal_obs"].data_ptr() if second["terminal_obs"] is not None else None,
-                         stats=self.stats_buf.data_ptr())
         torch.cuda.current_stream(dev).synchronize()
-        _abi.check(self.lib.s2d_bind_pipeline(self.handle, C.byref(b)), self.handle)
-        host = [dict(obs=pin(self.obs), reward=pin(self.reward), done=pin(self.done_u8), result=pin(self.result))
-                for _ in range(2)]
-        self._pipe = dict(device=second, host=host, next_slot=0, keep=[None, None])
+        device = [None]
+        for k in range(1, slots):
+            block = torch.zeros_like(self.out_block, device=dev)
+            obs, reward, done, result, term = self._carve_outputs(block)
+            actions = torch.zeros_like(self.actions, device=dev)
+            b = _abi.Buffers(state=self.state.data_ptr(), actions=actions.data_ptr(), obs=obs.data_ptr(),
+                             reward=reward.data_ptr(), done=done.data_ptr(), result=result.data_ptr(),
+                             terminal_obs=term.data_ptr() if term is not None else None, stats=self.stats_buf.data_ptr())
+            _abi.check(self.lib.s2d_bind_pipeline_slot(self.handle, k, C.byref(b)), self.handle)
+            device.append(dict(block=block, actions=actions, obs=obs, reward=reward, done=done, result=result,
+                               terminal_obs=term))
+        host = [self._pinned_outputs() for _ in range(slots)]
+        self._pipe = dict(device=device, host=host, next_slot=0, keep=[None] * slots, slots=slots)
 
     def submit_host(self, actions) -> int:
         """Enqueue one step from host `actions` (pinned CPU tensor / numpy array of the action shape) and return
-        its ticket (the slot).  At most two steps can be in flight: wait_host() the older one first."""
+        its ticket (the slot).  At most `slots` steps can be in flight: wait_host() the oldest one before re-using
+        its slot."""
         self.enable_pipeline()
         pipe = self._pipe
         slot = pipe["next_slot"]
-        pipe["next_slot"] = 1 - slot
+        pipe["next_slot"] = (slot + 1) % pipe["slots"]
         if isinstance(actions, torch.Tensor):
             src = actions.to(dtype=self.actions.dtype).reshape(self.actions.shape).contiguous()
         else:
@@ -311,10 +360,19 @@ class Soccer2DVecEnv(_VecEnvBase):
             src = src.to(dtype=self.actions.dtype)
         pipe["keep"][slot] = src  # keep the host source alive until the copy has happened
         ho = pipe["host"][slot]
+        if self._user_dirty:  # what this stream still does with the state / slot 0's tensors comes first
+            self._fence()
+            self._user_dirty = False
         _abi.check(self.lib.s2d_submit_host(self.handle, self.substeps, slot, src.data_ptr(), ho["obs"].data_ptr(),
                                             ho["reward"].data_ptr(), ho["done"].data_ptr(), ho["result"].data_ptr()),
                    self.handle)
         return slot
+
+    def pipeline_info(self) -> dict:
+        """slots bound and the number of device-to-host copies the last host-buffer step needed (1 = packed block)"""
+        slots, copies = C.c_int(0), C.c_int(0)
+        _abi.check(self.lib.s2d_pipeline_info(self.handle, C.byref(slots), C.byref(copies)), self.handle)
+        return {"slots": slots.value, "d2h_copies_last_step": copies.value}
 
     def wait_host(self, ticket: int):
         """Block until the step submitted with `ticket` is on the host; returns numpy views of that slot's pinned
@@ -335,16 +393,25 @@ class Soccer2DVecEnv(_VecEnvBase):
         self._pending = actions
 
     def step_wait(self):
+        """SB3's VecEnv.step_wait.  `infos` costs O(episodes that ended), not O(num_envs): every running env shares one
+        read-only {'result': None}; an env whose episode ended gets its own dict with 'result' (what
+        utils/info_collector_callback.py:23-27 reads) and, with terminal_obs=True, 'terminal_observation'."""
         obs, reward, done, result = self.step_host(self._pending)
         self._pending = None
-        infos = [{"result": None} for _ in range(self.num_envs)]
-        idx = np.nonzero(done)[0]
+        infos = [_RUNNING] * self.num_envs
+        idx = np.flatnonzero(done)
         if idx.size:
-            term = self.terminal_obs.cpu().numpy() if self.terminal_obs is not None else None
-            for i in idx:
-                infos[i]["result"] = _abi.RESULT_NAMES[int(result[i])]
+            term = None
+            if self.terminal_obs is not None:  # only the rows of the finished episodes cross the bus
+                rows = torch.from_numpy(idx).to(self.device)
+                term = self.terminal_obs.index_select(0, rows).cpu().numpy() if not self.host_mapped_io \
+                    else self.terminal_obs.numpy()[idx].copy()
+            names = _abi.RESULT_NAMES
+            for j, i in enumerate(idx.tolist()):
+                info = {"result": names[int(result[i])]}
                 if term is not None:
-                    infos[i]["terminal_observation"] = term[i].copy()
+                    info["terminal_observation"] = term[j]
+                infos[i] = info
         return obs.copy(), reward.copy(), done.copy(), infos
 
     def step(self, actions):
@@ -367,14 +434,26 @@ class Soccer2DVecEnv(_VecEnvBase):
     def seed(self, seed=None):
         return [None] * self.num_envs  # the Philox key is fixed at construction
 
+    # kernel constants: fixed when the handle is created
+    _FROZEN = frozenset(REACHBALL_DEFAULTS) | frozenset(SHOOT_DEFAULTS) | frozenset(FULLGAME_DEFAULTS) | {
+        "num_envs", "substeps", "scenario", "device", "seed_value", "env_id_offset", "auto_reset", "observation_space",
+        "action_space"}
+
     def get_attr(self, attr_name, indices=None):
         return [getattr(self, attr_name)] * len(self._indices(indices))
 
     def set_attr(self, attr_name, value, indices=None):
-        raise AttributeError("episode parameters are fixed at construction (they are kernel constants)")
+        """All envs are one object: an attribute set for some of them is set for all (SB3 wrappers use this for
+        bookkeeping attributes such as render_mode); episode parameters are kernel constants and cannot change."""
+        if attr_name in self._FROZEN:
+            raise AttributeError(f"{attr_name} is fixed at construction (it is a kernel constant)")
+        setattr(self, attr_name, value)
 
     def env_method(self, method_name, *args, indices=None, **kwargs):
-        raise AttributeError(f"{method_name}: per-env Python methods do not exist on the GPU path")
+        """Calls the method ONCE on this object and repeats its result per requested env."""
+        if method_name.startswith("_") or not callable(getattr(self, method_name, None)):
+            raise AttributeError(f"{method_name}: per-env Python methods do not exist on the GPU path")
+        return [getattr(self, method_name)(*args, **kwargs)] * len(self._indices(indices))
 
     def env_is_wrapped(self, wrapper_class, indices=None):
         return [False] * len(self._indices(indices))
@@ -456,6 +535,7 @@ class Soccer2DVecEnv(_VecEnvBase):
         `traj` (s2d_rollout_mlp_collect): time-major tensors for every cycle's transition, any of obs float32
         [k + 1, N, 10], actions uint8 [k, N], reward float32 [k, N], done uint8 [k, N] - what a replay buffer takes."""
         k = self.substeps if k is None else int(k)
+        self._user_dirty = True
         ptrs = []
         for (w, b), shape in zip(layers, ((64, self.obs_dim), (64, 64), (self.cfg.action_space_size, 64))):
             if tuple(w.shape) != shape or tuple(b.shape) != shape[:1]:
@@ -494,6 +574,7 @@ class Soccer2DVecEnv(_VecEnvBase):
         half-width of a uniform exploration noise.  `traj`: time-major tensors, any of obs float32 [k + 1, N, 10],
         actions float32 [k, N, action_dim], reward float32 [k, N], done uint8 [k, N]."""
         k = self.substeps if k is None else int(k)
+        self._user_dirty = True
         ad = 4 if self.action_mode == _abi.ACT_TURNING else 1
         ptrs = []
         for (w, b), shape in zip(layers, ((64, self.obs_dim), (64, 64), (ad, 64))):

@@ -68,6 +68,10 @@ class Soccer2DEnv(Env):
                                        server_param=server_param, use_command_action=True, noise=noise, host_mapped_io=True,
                                        goto_dist_thr=scenario_kwargs.pop("goto_dist_thr", 0.5),
                                        min_distance_to_ball=-1.0, max_steps=2**31 - 1)
+            # rcssserver gives a player full stamina / effort / recovery when it connects: start from a recovered
+            # player even if the subclass's trainer_reset_actions sends no DoRecover
+            self._vec.reset_torch()
+            torch.cuda.current_stream(self._vec.device).synchronize()
             self._pb2 = self._find_pb2()
             self._latest_player_state = None
             self._latest_trainer_state = None

@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define S2D_ABI_VERSION 9
+#define S2D_ABI_VERSION 10
 
 /* error codes */
 #define S2D_OK 0
@@ -270,17 +270,48 @@ int s2d_step(S2DHandle h, int k_substeps, void* stream);
 int s2d_step_host(S2DHandle h, int k_substeps, const void* h_actions, float* h_obs, float* h_reward,
                   uint8_t* h_done, uint8_t* h_result, void* stream);
 
-/* Pipelined host-buffer stepping: the copies of one step overlap the kernel and the copies of the next.
- * s2d_bind_pipeline gives the handle a SECOND set of device actions / obs / reward / done / result (/ terminal_obs)
- * buffers (slot 1; slot 0 = the buffers of s2d_bind; state and stats are shared).  s2d_submit_host enqueues
- * H2D(actions) -> step kernel -> D2H(outputs) for one slot on three internal streams and returns at once; alternate
- * the slots between consecutive submissions and call s2d_wait_host(slot) before reading that slot's host outputs (or
- * re-using its host action buffer).  Host buffers should be pinned.  Do not mix with s2d_step / s2d_step_host on
- * other streams without draining both slots first. */
+/* Pipelined host-buffer stepping: the copies of one step overlap the kernel and the copies of the next ones.
+ * s2d_bind_pipeline_slot gives the handle another set of device actions / obs / reward / done / result (/ terminal_obs)
+ * buffers (slot 1 .. S2D_MAX_PIPELINE_SLOTS - 1; slot 0 = the buffers of s2d_bind; state and stats are shared);
+ * s2d_bind_pipeline(h, b) = s2d_bind_pipeline_slot(h, 1, b).  s2d_submit_host enqueues H2D(actions) -> step kernel ->
+ * D2H(outputs) for one slot on three internal streams and returns at once; rotate the slots between consecutive
+ * submissions and call s2d_wait_host(slot) before reading that slot's host outputs (or re-using its host action
+ * buffer).  Host buffers should be pinned.
+ * ONE device-to-host copy per step: when a slot's device outputs and its host outputs are both laid out as
+ * s2d_output_layout says (obs | reward | done | result inside one block), s2d_submit_host and s2d_step_host move the
+ * whole block with a single cudaMemcpyAsync instead of four.
+ * Ordering: s2d_reset / s2d_step / s2d_step_host / s2d_rollout_* / s2d_stats / s2d_export_env issued on the caller's
+ * stream while slots are in flight first wait (on the device) for every submitted kernel and for slot 0's copies,
+ * and the next s2d_submit_host waits for that caller-stream work: the shared state is never raced.
+ * What the library cannot see is work the CALLER enqueues on its own stream that touches slot 0's buffers (a copy into
+ * the bound action tensor before s2d_step, a kernel reading obs after it).  s2d_fence(h, stream) orders both ways: work
+ * enqueued on `stream` after the call waits for everything the pipeline has submitted, and the next s2d_submit_host
+ * waits for everything enqueued on `stream` before the call.  Device-side only; the host does not block. */
+#define S2D_MAX_PIPELINE_SLOTS 4
+int s2d_fence(S2DHandle h, void* stream);
 int s2d_bind_pipeline(S2DHandle h, const S2DBuffers* second_slot);
+int s2d_bind_pipeline_slot(S2DHandle h, int slot, const S2DBuffers* slot_buffers);
 int s2d_submit_host(S2DHandle h, int k_substeps, int slot, const void* h_actions, float* h_obs, float* h_reward,
                     uint8_t* h_done, uint8_t* h_result);
 int s2d_wait_host(S2DHandle h, int slot); /* blocks the calling thread until the slot's outputs are on the host */
+
+/* Offsets (256-byte aligned) of the per-step outputs inside ONE block of `bytes` bytes, for callers that want the single
+ * copy described above: allocate the block once on the device and once in pinned host memory and hand the carved
+ * pointers to s2d_bind / s2d_bind_pipeline_slot / s2d_submit_host.  terminal_obs (optional) sits after the others and
+ * is not part of the per-step copy (only the rows of finished episodes are ever read). */
+typedef struct S2DOutputLayout {
+  size_t obs, reward, done, result; /* byte offsets */
+  size_t step_bytes;                /* obs .. end of result: what one step copies to the host */
+  size_t terminal_obs;              /* byte offset; the block then has `bytes_with_terminal_obs` bytes */
+  size_t bytes, bytes_with_terminal_obs;
+} S2DOutputLayout;
+int s2d_output_layout(const S2DConfig* cfg, S2DOutputLayout* out);
+
+/* Zero-fills the bound state and statistics buffers (asynchronously on `stream`).  The reset kernels READ the episode
+ * and cycle counters from the state (the RNG is keyed on them), so a caller that binds freshly allocated device memory
+ * must call this (or memset the buffers itself) before the first s2d_reset - otherwise episodes differ from run to run.
+ * Not needed when the buffers come zero-initialised (torch.zeros in the Python host) or from a checkpoint. */
+int s2d_clear(S2DHandle h, void* stream);
 
 int s2d_stats(S2DHandle h, S2DStats* host_out, void* stream);   /* reduces the partials; synchronises */
 int s2d_stats_reset(S2DHandle h, void* stream);
@@ -362,6 +393,10 @@ int s2d_rollout_mlp_collect(S2DHandle h, const S2DMlpPolicy* policy, int k_subst
  * before the clip to [-1, 1] (0: the deterministic policy).  `trajectory` may be NULL; its `actions` is not used. */
 int s2d_rollout_actor_collect(S2DHandle h, const S2DMlpPolicy* actor, int k_substeps, float noise,
                               const S2DTrajectory* trajectory, void* stream);
+
+/* Host-buffer path, for measurement: how many pipeline slots are bound (0 = no pipeline) and how many device-to-host
+ * copies the last s2d_step_host / s2d_submit_host issued (1 when the packed output block went out in one piece). */
+int s2d_pipeline_info(S2DHandle h, int* slots_bound, int* d2h_copies_last_step);
 
 /* Launch geometry actually used (for bench.py's gpu_launches / DESIGN.md): blocks, threads, kernels per step call */
 int s2d_launch_info(S2DHandle h, int* grid, int* block, int* kernels_per_step);

@@ -11,14 +11,20 @@ region.  One JSON line is printed by rank 0.
 
   value      env-steps/s with actions and state resident in HBM, sum of per-launch CUDA-event durations
              (L2 flushed between launches, flush not timed), max over ranks
-  e2e        the same workload through the host-buffer call (s2d_step_host): pinned host actions -> H2D ->
-             kernel -> D2H of obs/reward/done/result, wall clock between stream syncs, max over ranks
+  e2e        the same workload through the host-buffer calls of the C ABI (s2d_submit_host / s2d_wait_host): pinned
+             host actions -> H2D -> kernel -> ONE D2H of the packed obs/reward/done/result block, three steps in
+             flight, the host reads every step's result; wall clock between barriers, max over ranks.
+             `pcie_probe` = plain cudaMemcpyAsync of the same byte counts (both directions at once, all ranks at once):
+             the ceiling this box gives that path; `frac_of_probe` = e2e / probe
   roofline   the step kernel at the bench workload (K = 16): algorithmic bytes / launch time vs the measured
              HBM copy peak; `roofline_k1` is the same kernel in its HBM-bound regime (closed loop, K = 1)
+  shoot, fullgame   BASELINE configs[2] / [3] (4M shoot-on-goal envs, 256K 11v11 matches, sharded over the ranks):
+             value, launch time, roofline fraction and e2e of each, measured in the same run
   cpu_baseline  the C oracle (oracle/s2d_oracle.c, f64, OpenMP) on this box's host cores, bounded sample
 
---impl reference times that CPU oracle alone (the reference's own step path needs rcssserver + the C++ proxy,
-which are external binaries that cannot run offline; the oracle is the CPU restatement of the same path).
+--impl reference times that CPU oracle alone on the SAME workload (2^20 envs x 16 cycles per step).  The reference's own
+step path needs rcssserver + the C++ proxy, external binaries that cannot run offline; the oracle is the CPU restatement
+of the same path.  That arm imports neither the product package nor libsoccer2d.so.
 """
 import argparse
 import json
@@ -40,6 +46,7 @@ SUBSTEPS = 16
 SCENARIO_KW = dict(use_continuous_action=False, action_space_size=16, change_ball_position=True,
                    change_ball_velocity=True, min_distance_to_ball=5.0, max_steps=200)
 STATE_BYTES, OBS_BYTES, OUT_BYTES = 80, 40, 6  # per env: state planes; obs row; reward + done + result
+FG_STATE_BYTES, FG_OBS_BYTES = 22 * 36 + 64, 480  # per 11v11 match
 
 
 def algorithmic_bytes_per_env(k):
@@ -47,13 +54,16 @@ def algorithmic_bytes_per_env(k):
     return 2 * STATE_BYTES + k + OBS_BYTES + OUT_BYTES
 
 
-def workload_config(n_gpus, envs, k, extra=None):
-    cfg = {"workload": f"ReachBall {envs} lockstep envs per GPU (1 player + ball, dash only, Discrete(16)), "
-                       f"fused K={k} substeps per launch, noise off, auto-reset",
-           "envs_per_gpu": envs, "substeps": k, "global_envs": envs * n_gpus,
-           "scenario_kwargs": SCENARIO_KW, "parallelism": f"episode-shard x{n_gpus}"}
-    cfg.update(extra or {})
-    return cfg
+def workload_config(n_gpus, envs, k):
+    """The `config` of the JSON line - the same dict, key for key, in the B200 arm and in the reference arm."""
+    return {"workload": f"ReachBall {envs} lockstep envs per GPU (1 player + ball, dash only, Discrete(16)), "
+                        f"fused K={k} substeps per launch, noise off, auto-reset",
+            "envs_per_gpu": envs, "substeps": k, "global_envs": envs * n_gpus,
+            "scenario_kwargs": SCENARIO_KW, "parallelism": f"episode-shard x{n_gpus}",
+            "l2": "B200 arm: L2 flushed between timed launches (256 MiB memset, not timed), the K=1 run uses a working "
+                  "set >> L2; CPU arm: 2^20 envs of state (>> last-level cache) streamed every step",
+            "timing": "B200 arm: sum of per-launch CUDA-event durations on the launching stream, max over ranks; CPU arm: "
+                      "wall clock around the timed steps"}
 
 
 def load_traffic(key, envs, field="traffic_bytes"):
@@ -62,6 +72,15 @@ def load_traffic(key, envs, field="traffic_bytes"):
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             return json.load(f)[f"{key}_envs_{envs}"][field]
+    except Exception:  # noqa: BLE001
+        return None
+
+
+def load_parity():
+    """fp32-vs-f64 flag-flip rate measured over ALL seeds (profiles/flag_flips.py -> profiles/parity_flips.json)"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "parity_flips.json")) as f:
+            return json.load(f)
     except Exception:  # noqa: BLE001
         return None
 
@@ -117,27 +136,35 @@ class ClockSampler(threading.Thread):
         return out
 
 
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:  # noqa: BLE001
+        return os.cpu_count() or 1
+
+
+# ---- the CPU arm: oracle only (tests/oracle_lib.py -> oracle/_build/liboracle_f64.so); no product import ---------
 def time_cpu_oracle(envs, k, min_seconds, max_launches=10**9, warmup=1, fixed_launches=None):
     """env-steps/s of the C oracle (f64 build, OpenMP over all host cores) on `envs` episodes x k cycles per call."""
     # torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm is meant to use every host thread it can
     os.environ["OMP_NUM_THREADS"] = str(host_threads())
     import numpy as np
 
-    import helpers as H
     import oracle_lib as OL
-    cfg = H.make_config(envs, "discrete", seed=0, change_ball_velocity=1, max_steps=SCENARIO_KW["max_steps"],
-                        min_distance_to_ball=SCENARIO_KW["min_distance_to_ball"],
-                        action_space_size=SCENARIO_KW["action_space_size"])
+    cfg = OL.default_config(envs, 0, action_mode=OL.ACT_DISCRETE, seed=0, change_ball_velocity=1,
+                            change_ball_position=1, max_steps=SCENARIO_KW["max_steps"],
+                            min_distance_to_ball=SCENARIO_KW["min_distance_to_ball"],
+                            action_space_size=SCENARIO_KW["action_space_size"])
     sim = OL.OracleSim(cfg, "f64")
     OL.lib("f64").s2do_set_threads(host_threads())
     sim.reset()
     rng = np.random.default_rng(0)
-    pool = [H.random_actions(rng, "discrete", envs, k) for _ in range(4)]
+    pool = [rng.integers(0, 16, size=(envs, k)).astype(np.uint8) for _ in range(2)]
     for i in range(warmup):
-        sim.step(pool[i % 4], k)
+        sim.step(pool[i % 2], k)
     launches, t0 = 0, time.perf_counter()
     while True:
-        sim.step(pool[launches % 4], k)
+        sim.step(pool[launches % 2], k)
         launches += 1
         dt = time.perf_counter() - t0
         if fixed_launches is not None:
@@ -149,28 +176,21 @@ def time_cpu_oracle(envs, k, min_seconds, max_launches=10**9, warmup=1, fixed_la
     return envs * k * launches / dt, launches, dt
 
 
-def host_threads():
-    try:
-        return len(os.sched_getaffinity(0))
-    except Exception:  # noqa: BLE001
-        return os.cpu_count() or 1
-
-
 def run_reference(args, rank):
     if rank != 0:
         return
-    envs = 1 << 16
-    value, launches, dt = time_cpu_oracle(envs, SUBSTEPS, 0, warmup=args.warmup, fixed_launches=args.steps)
+    envs, k = args.envs, args.substeps
+    value, launches, dt = time_cpu_oracle(envs, k, 0, warmup=args.warmup, fixed_launches=args.steps)
     cores = host_threads()
-    sample = f"{envs} envs x {SUBSTEPS} cycles per step ({envs * SUBSTEPS} env-steps), {launches} steps, {dt:.1f} s"
+    sample = (f"oracle/s2d_oracle.c (f64, OpenMP, {cores} threads): {envs} envs x {k} cycles per step "
+              f"({envs * k} env-steps), {launches} steps, {dt:.1f} s")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt / launches * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args.gpus, ENVS_PER_GPU, SUBSTEPS, {
-                "reference_note": "the reference's Soccer2DEnv.step needs rcssserver + soccer-simulation-proxy "
-                                  "(external binaries, not available offline); this arm times oracle/s2d_oracle.c, "
-                                  "the CPU restatement of that path, OpenMP over the host cores",
-                "sample": sample}),
+            "config": workload_config(args.gpus, envs, k),
+            "reference_note": "the reference's Soccer2DEnv.step needs rcssserver + soccer-simulation-proxy (external "
+                              "binaries, not available offline); this arm times oracle/s2d_oracle.c, the CPU restatement "
+                              "of that path, OpenMP over the host cores, on one GPU's share of the workload",
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -194,34 +214,217 @@ def time_launches(env, pool, steps, flush):
     return [s.elapsed_time(e) for s, e in zip(starts, stops)]
 
 
+class Ranks:
+    """barrier / max-over-ranks of the timing contract"""
+
+    def __init__(self, world, dev):
+        self.world, self.dev = world, dev
+
+    def barrier(self):
+        import torch
+        import torch.distributed as dist
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max(self, x):
+        if self.world == 1:
+            return x
+        import torch
+        import torch.distributed as dist
+        t = torch.tensor([x], dtype=torch.float64, device=self.dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def gather(self, x):
+        """list of one float per rank (on every rank)"""
+        if self.world == 1:
+            return [x]
+        import torch
+        import torch.distributed as dist
+        t = torch.zeros(self.world, dtype=torch.float64, device=self.dev)
+        t[dist.get_rank()] = x
+        dist.all_reduce(t)
+        return [float(v) for v in t.tolist()]
+
+
+def e2e_pipelined(env, host_pool, steps, ranks, slots=3):
+    """`steps` steps through submit_host / wait_host with `slots` in flight; the host reads every step's reward.
+    Returns seconds (max over ranks)."""
+    import torch
+    env.enable_pipeline(slots=slots)
+    pend = [env.submit_host(host_pool[i % len(host_pool)]) for i in range(slots)]  # warm every slot once
+    for t in pend:
+        env.wait_host(t)
+    ranks.barrier()
+    t0 = time.perf_counter()
+    pend, checksum, sent = [], 0.0, 0
+    while sent < min(slots - 1, steps):
+        pend.append(env.submit_host(host_pool[sent % len(host_pool)]))
+        sent += 1
+    for _ in range(steps):
+        if sent < steps:
+            pend.append(env.submit_host(host_pool[sent % len(host_pool)]))
+            sent += 1
+        _, reward, _, _ = env.wait_host(pend.pop(0))
+        checksum += float(reward[0])
+    torch.cuda.synchronize()
+    dt = ranks.max(time.perf_counter() - t0)
+    ranks.barrier()
+    return dt, checksum
+
+
+def pcie_probe(env, h2d_bytes, d2h_bytes, steps, ranks):
+    """The ceiling of the host-buffer path on THIS box: plain cudaMemcpyAsync of one step's byte counts, pinned host
+    memory (allocated like the env's staging blocks), no kernel; all ranks at the same time.  Three measurements:
+    device-to-host alone, host-to-device alone, both directions concurrently (what the pipeline does)."""
+    import torch
+    dev = env.device
+    d_in, d_out = torch.empty(h2d_bytes, dtype=torch.uint8, device=dev), torch.zeros(d2h_bytes, dtype=torch.uint8, device=dev)
+    h_in, h_out = env.pinned_bytes(h2d_bytes), env.pinned_bytes(d2h_bytes)
+    h_in.zero_()
+    s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
+    def run(do_in, do_out):
+        for rep in range(2):  # first pass warms up
+            ranks.barrier()
+            t0 = time.perf_counter()
+            for _ in range(steps if rep else 3):
+                if do_in:
+                    with torch.cuda.stream(s_in):
+                        d_in.copy_(h_in, non_blocking=True)
+                if do_out:
+                    with torch.cuda.stream(s_out):
+                        h_out.copy_(d_out, non_blocking=True)
+            s_in.synchronize()
+            s_out.synchronize()
+            dt = time.perf_counter() - t0
+        return ranks.max(dt), ranks.gather(dt)
+
+    t_out, per_out = run(False, True)
+    t_in, _ = run(True, False)
+    t_both, per_both = run(True, True)
+    ranks.barrier()
+    return {"steps": steps, "d2h_only_gbs_per_rank": d2h_bytes * steps / t_out / 1e9,
+            "h2d_only_gbs_per_rank": h2d_bytes * steps / t_in / 1e9,
+            "both_d2h_gbs_per_rank": d2h_bytes * steps / t_both / 1e9, "both_h2d_gbs_per_rank": h2d_bytes * steps / t_both / 1e9,
+            "both_seconds": t_both, "d2h_only_gbs_each_rank": [d2h_bytes * steps / t / 1e9 for t in per_out],
+            "both_d2h_gbs_each_rank": [d2h_bytes * steps / t / 1e9 for t in per_both],
+            "what": "cudaMemcpyAsync pinned<->device of one step's bytes (no kernel), all ranks concurrently, slowest rank"}
+
+
+def commands(torch, gen, dev, shape):
+    """synthetic proto-style commands {cmd, a, b, c}: none / dash / turn / kick / go-to-point, uniformly"""
+    a = torch.zeros(shape + (4,), device=dev)
+    cmd = torch.randint(0, 5, shape, device=dev, generator=gen)
+    u = lambda: torch.rand(shape, device=dev, generator=gen)  # noqa: E731
+    a[..., 0] = cmd.float()
+    a[..., 1] = torch.where(cmd == 4, u() * 100 - 50, u() * 100)
+    a[..., 2] = torch.where(cmd == 4, u() * 60 - 30, u() * 360 - 180)
+    a[..., 3] = 100.0
+    return a
+
+
+def measure_scenario(kind, total, k, steps, warmup, rank, world, dev, ranks, numa_node, with_e2e=True):
+    """BASELINE configs[2] (kind = "shoot": 1v0 shoot-on-goal, `total` envs) / configs[3] ("fullgame": 11v11, `total`
+    matches), sharded over the ranks (strong scaling, shard_range), command actions resident in HBM.  Same timing rules
+    as the main arm.  Returns the section dict (identical on every rank)."""
+    import torch
+
+    from soccer2d_b200 import Soccer2DVecEnv, shard_range
+    gen = torch.Generator(device=dev).manual_seed(99 + rank)
+    off, n = shard_range(rank, world, total)
+    if kind == "shoot":
+        env = Soccer2DVecEnv(n, scenario="shoot", device=dev, seed=0, substeps=k, env_id_offset=off, use_command_action=True,
+                             host_numa_node=numa_node)
+        pool = [commands(torch, gen, dev, (n, k)) for _ in range(2)]
+        per_env = 2 * STATE_BYTES + 16 * k + OBS_BYTES + OUT_BYTES
+        name = f"1v0 shoot-on-goal, {total} envs in total, proto-style command actions (dash/turn/kick/go-to-point), K={k}"
+        kernel = "s2d::step_kernel<SHOOT, COMMAND, default ServerParam>"
+    else:
+        env = Soccer2DVecEnv(n, scenario="fullgame", device=dev, seed=0, substeps=k, env_id_offset=off, host_numa_node=numa_node)
+        pool = [commands(torch, gen, dev, (n, k, 22)) for _ in range(2)]
+        per_env = 2 * FG_STATE_BYTES + 22 * 16 * k + FG_OBS_BYTES + OUT_BYTES
+        name = f"11v11 full game, {total} matches in total, one command per player per cycle, K={k}"
+        kernel = "s2d::fullgame_step_kernel<default ServerParam, 11v11>"
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    env.reset_torch()
+    time_launches(env, pool, max(warmup, 3), flush)
+    ranks.barrier()
+    ms = time_launches(env, pool, steps, flush)
+    ranks.barrier()
+    total_ms = ranks.max(sum(ms))
+    launch_ms = sum(ms) / len(ms)
+    out = {"workload": name, "value": total * k * steps / (total_ms * 1e-3), "unit": UNIT, "scaling": "strong",
+           "envs_per_gpu": n, "global_envs": total, "substeps": k, "steps": steps, "launch_ms": launch_ms,
+           "ms_per_step": total_ms / steps, "gpu_launches": steps}
+    peak, peak_src = load_peaks()
+    ach = per_env * n / (launch_ms * 1e-3) / 1e9
+    key = f"fullgame_k{k}"
+    out["roofline"] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                       "traffic": load_traffic(key, n) if kind == "fullgame" else None,
+                       "issue_slots_busy_pct_ncu": load_traffic(key, n, "issue_active_pct") if kind == "fullgame" else None,
+                       "kernel": kernel, "launch_ms": launch_ms, "algorithmic_bytes_per_launch": per_env * n,
+                       "peak_source": peak_src}
+    if with_e2e:
+        host_pool = [env.pinned_like(p) for p in pool]
+        for hp, p in zip(host_pool, pool):
+            hp.copy_(p)
+        e2e_steps = max(3, min(steps, 20))
+        e2e_s, _ = e2e_pipelined(env, host_pool, e2e_steps, ranks)
+        h2d = pool[0].numel() * pool[0].element_size()
+        out["e2e"] = {"value": total * k * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                      "d2h_bytes_per_step": int(env.layout.step_bytes), "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3,
+                      "d2h_copies_per_step": env.pipeline_info()["d2h_copies_last_step"],
+                      "path": "Soccer2DVecEnv.submit_host / wait_host (s2d_submit_host / s2d_wait_host), pinned host buffers, "
+                              "3 slots in flight"}
+    out["episode_stats"] = env.allreduce_stats()
+    env.close()
+    del env, pool, flush
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_b200(args, rank, local_rank, world):
     import torch
     import torch.distributed as dist
 
-    from soccer2d_b200 import Soccer2DVecEnv
-
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device - the B200 arm has no CPU fallback (use --impl reference)")
+    from soccer2d_b200 import Soccer2DVecEnv, numa
+
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # the rank's host side next to its GPU: CPU affinity and the pinned staging buffers on the GPU's NUMA node
+    placement = numa.bind_process_to_gpu(local_rank) if args.numa else {"disabled": True, "node": None}
+    numa_node = placement.get("node")
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    ranks = Ranks(world, dev)
 
-    def barrier():
-        torch.cuda.synchronize()
+    if args.workload != "reachball":
+        total = args.envs if args.envs != ENVS_PER_GPU else (1 << 22 if args.workload == "shoot" else 1 << 18)
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        sec = measure_scenario(args.workload, total, args.substeps, args.steps, args.warmup, rank, world, dev, ranks, numa_node)
+        clocks = sampler.summary()
+        if rank == 0:
+            line = {"metric": METRIC, "value": sec["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                    "warmup": max(args.warmup, 3), "ms_per_step": sec["ms_per_step"], "higher_is_better": True,
+                    "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                    "config": {"workload": sec["workload"], "envs_per_gpu": sec["envs_per_gpu"], "substeps": sec["substeps"],
+                               "global_envs": sec["global_envs"], "parallelism": f"episode-shard x{world}",
+                               "l2": "flushed between timed launches (256 MiB memset, not timed)"},
+                    "e2e": sec["e2e"], "gpu_launches": sec["gpu_launches"], "roofline": sec["roofline"], "clocks": clocks,
+                    "episode_stats": sec["episode_stats"], "host_placement": placement}
+            print(json.dumps(line), flush=True)
         if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+            dist.destroy_process_group()
+        return
 
     n, k = args.envs, args.substeps
-    env = Soccer2DVecEnv(n, device=dev, seed=0, substeps=k, env_id_offset=rank * n, **SCENARIO_KW)
+    env = Soccer2DVecEnv(n, device=dev, seed=0, substeps=k, env_id_offset=rank * n, host_numa_node=numa_node, **SCENARIO_KW)
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     pool = [torch.randint(0, 16, (n, k), dtype=torch.uint8, device=dev, generator=gen) for _ in range(4)]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # 2x the 126 MB L2
@@ -232,51 +435,46 @@ def run_b200(args, rank, local_rank, world):
     sampler.start()
 
     # ---- value: device-resident inputs --------------------------------------------------------------
-    barrier()
+    ranks.barrier()
     ms = time_launches(env, pool, args.steps, flush)
-    barrier()
-    total_ms = max_over_ranks(sum(ms))
+    ranks.barrier()
+    total_ms = ranks.max(sum(ms))
     value = world * n * k * args.steps / (total_ms * 1e-3)
     launch_ms = sum(ms) / len(ms)
 
     # ---- e2e: host buffers, every step's actions H2D and results D2H inside the timed region --------------
-    hb = env.host_buffers()
-    host_pool = [p.cpu().pin_memory() for p in pool[:2]]
+    host_pool = [env.pinned_like(p) for p in pool[:3]]
+    for hp, p in zip(host_pool, pool):
+        hp.copy_(p)
     e2e_steps = max(3, min(args.steps, 30))
     h2d = pool[0].numel() * pool[0].element_size()
-    d2h = sum(hb[x].numel() * hb[x].element_size() for x in ("obs", "reward", "done", "result"))
+    d2h = int(env.layout.step_bytes)
     # (a) synchronous call: s2d_step_host, one step at a time (H2D -> kernel -> D2H -> host reads the reward)
     for i in range(3):
-        env.step_host(host_pool[i % 2])
-    barrier()
+        env.step_host(host_pool[i % 3])
+    ranks.barrier()
     t0 = time.perf_counter()
     checksum = 0.0
     for i in range(e2e_steps):
-        _, reward, _, _ = env.step_host(host_pool[i % 2])
+        _, reward, _, _ = env.step_host(host_pool[i % 3])
         checksum += float(reward[0])
     torch.cuda.synchronize()
-    e2e_sync_s = max_over_ranks(time.perf_counter() - t0)
-    barrier()
-    # (b) pipelined call: s2d_submit_host / s2d_wait_host, two steps in flight - the copies of one step overlap
-    #     the kernel and the copies of the next; the host still reads every step's result
-    env.enable_pipeline()
-    t = env.submit_host(host_pool[0])
-    env.wait_host(t)
-    barrier()
-    t0 = time.perf_counter()
-    ticket = env.submit_host(host_pool[0])
-    for i in range(1, e2e_steps):
-        nxt = env.submit_host(host_pool[i % 2])
-        _, reward, _, _ = env.wait_host(ticket)
-        checksum += float(reward[0])
-        ticket = nxt
-    _, reward, _, _ = env.wait_host(ticket)
-    checksum += float(reward[0])
-    torch.cuda.synchronize()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    barrier()
+    e2e_sync_s = ranks.max(time.perf_counter() - t0)
+    ranks.barrier()
+    # (b) pipelined call: s2d_submit_host / s2d_wait_host, three steps in flight - the D2H of step i, the kernel of
+    #     step i+1 and the H2D of step i+2 overlap; the host still reads every step's result
+    e2e_s, c2 = e2e_pipelined(env, host_pool, e2e_steps, ranks, slots=3)
+    d2h_copies = env.pipeline_info()["d2h_copies_last_step"]
     e2e_value = world * n * k * e2e_steps / e2e_s
     e2e_sync_value = world * n * k * e2e_steps / e2e_sync_s
+    # (c) what the box gives plain copies of the same sizes
+    probe = pcie_probe(env, h2d, d2h, e2e_steps, ranks)
+    probe_value = world * n * k * e2e_steps / probe["both_seconds"]
+    kernel_s = launch_ms * 1e-3
+    copy_s = probe["both_seconds"] / e2e_steps
+    limiter = ("host<->device copies: the D2H of 46 bytes of results per env and launch at the box's concurrent PCIe rate "
+               f"({probe['both_d2h_gbs_per_rank']:.1f} GB/s per rank with {world} rank(s) copying)" if copy_s > kernel_s
+               else "the step kernel")
 
     stats = env.allreduce_stats()  # NCCL all-reduce of the episode statistics (the only collective)
     env.close()
@@ -290,14 +488,21 @@ def run_b200(args, rank, local_rank, world):
     env1.reset_torch()
     k1_steps = max(10, min(args.steps, 100))
     time_launches(env1, pool1, 5, None)
-    barrier()
+    ranks.barrier()
     ms1 = time_launches(env1, pool1, k1_steps, None)
-    barrier()
-    k1_total_ms = max_over_ranks(sum(ms1))
+    ranks.barrier()
+    k1_total_ms = ranks.max(sum(ms1))
     k1_launch_ms = sum(ms1) / len(ms1)
     k1_value = world * n1 * k1_steps / (k1_total_ms * 1e-3)
     env1.close()
     del env1, pool1
+
+    # ---- BASELINE configs[2] and [3] in the same run (short): 4M shoot envs / 256K 11v11 matches over the ranks ----
+    extra_steps = max(3, min(args.steps, 20))
+    shoot = fullgame = None
+    if not args.no_extras:
+        shoot = measure_scenario("shoot", 1 << 22, 1, extra_steps, 3, rank, world, dev, ranks, numa_node)
+        fullgame = measure_scenario("fullgame", 1 << 18, 1, extra_steps, 3, rank, world, dev, ranks, numa_node)
 
     # ---- closed-loop policy rollout (configs[4]): obs -> 64-64 MLP -> argmax -> step, all on the device ----
     from soccer2d_b200.rollout import QNetwork, measure_fused_rollout, measure_rollout
@@ -353,23 +558,22 @@ def run_b200(args, rank, local_rank, world):
     ach1 = bytes1 / (k1_launch_ms * 1e-3) / 1e9
     cpu_line = None
     if world == 1:
-        cpu_envs = 1 << 16
-        cv, cl, cdt = time_cpu_oracle(cpu_envs, k, args.cpu_seconds)
+        cv, cl, cdt = time_cpu_oracle(n, k, args.cpu_seconds)
         cpu_line = {"value": cv, "unit": UNIT, "cores": host_threads(), "kind": "port",
-                    "sample": f"oracle/s2d_oracle.c (f64, OpenMP): {cpu_envs} envs x {k} cycles x {cl} launches, {cdt:.1f} s"}
+                    "sample": f"oracle/s2d_oracle.c (f64, OpenMP): {n} envs x {k} cycles x {cl} launches, {cdt:.1f} s"}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": workload_config(world, n, k, {
-            "l2": "flushed between timed launches (256 MiB memset, not timed); K=1 run uses a working set >> L2",
-            "timing": "sum of per-launch CUDA-event durations on the launching stream, max over ranks"}),
+        "config": workload_config(world, n, k),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3,
                 "d2h_gbs": d2h * e2e_steps / e2e_s / 1e9, "h2d_gbs": h2d * e2e_steps / e2e_s / 1e9,
-                "bound": "PCIe device-to-host (46 bytes of results per env and launch; both directions run concurrently)",
+                "d2h_copies_per_step": d2h_copies, "slots_in_flight": 3,
+                "pcie_probe": dict(probe, value=probe_value, unit=UNIT), "frac_of_probe": e2e_value / probe_value,
+                "limiter": limiter,
                 "path": "Soccer2DVecEnv.submit_host / wait_host -> s2d_submit_host / s2d_wait_host: pinned host actions in, "
-                        "obs/reward/done/result out, two steps in flight (copies overlap the kernel)",
+                        "ONE packed obs|reward|done|result block out, three steps in flight (copies overlap the kernel)",
                 "synchronous": {"value": e2e_sync_value, "ms_per_step": e2e_sync_s / e2e_steps * 1e3,
                                 "path": "Soccer2DVecEnv.step_host -> s2d_step_host, one step at a time"}},
         "gpu_launches": args.steps,
@@ -386,6 +590,7 @@ def run_b200(args, rank, local_rank, world):
                         "kernel": "s2d::step_kernel<REACHBALL, DISCRETE, default ServerParam>", "launch_ms": k1_launch_ms, "envs_per_gpu": n1,
                         "substeps": 1, "algorithmic_bytes_per_launch": bytes1, "env_steps_per_sec": k1_value,
                         "peak_source": peak_src},
+        "shoot": shoot, "fullgame": fullgame,
         "rollout_dqn": {"unit": UNIT + " per GPU", "policy": "64-64 ReLU MLP (SB3 DQN MlpPolicy shape), greedy, K=1, zero-copy obs/action "
                         "tensors, loop body replayed as a CUDA graph (torch fp32 matmuls for the policy, not part of the "
                         "step path)",
@@ -398,123 +603,12 @@ def run_b200(args, rank, local_rank, world):
         "single_env_gym_api": single,
         "clocks": clocks,
         "episode_stats": stats,
+        "host_placement": placement,
+        "parity": load_parity(),
     }
     if cpu_line:
         line["cpu_baseline"] = cpu_line
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
-
-
-def run_other_workload(args, rank, local_rank, world):
-    """--workload shoot | fullgame: BASELINE configs[2] (1v0 shoot, 4M envs in total) and configs[3] (11v11, 256K
-    matches in total), sharded over the ranks (strong scaling, shard_range), command actions resident in HBM.
-    Same timing rules as the main arm; prints one JSON line with value, roofline and the pipelined e2e."""
-    import torch
-    import torch.distributed as dist
-
-    from soccer2d_b200 import Soccer2DVecEnv, shard_range
-
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    k = args.substeps
-    gen = torch.Generator(device=dev).manual_seed(99 + rank)
-
-    def commands(shape):
-        a = torch.zeros(shape + (4,), device=dev)
-        cmd = torch.randint(0, 5, shape, device=dev, generator=gen)
-        u = lambda: torch.rand(shape, device=dev, generator=gen)  # noqa: E731
-        a[..., 0] = cmd.float()
-        a[..., 1] = torch.where(cmd == 4, u() * 100 - 50, u() * 100)
-        a[..., 2] = torch.where(cmd == 4, u() * 60 - 30, u() * 360 - 180)
-        a[..., 3] = 100.0
-        return a
-
-    if args.workload == "shoot":
-        total = args.envs if args.envs != ENVS_PER_GPU else 1 << 22
-        off, n = shard_range(rank, world, total)
-        env = Soccer2DVecEnv(n, scenario="shoot", device=dev, seed=0, substeps=k, env_id_offset=off, use_command_action=True)
-        pool = [commands((n, k)) for _ in range(2)]
-        per_env = 2 * STATE_BYTES + 16 * k + OBS_BYTES + OUT_BYTES
-        name = f"1v0 shoot-on-goal, {total} envs in total, proto-style command actions (dash/turn/kick/go-to-point), K={k}"
-        kernel = "s2d::step_kernel<SHOOT, COMMAND, default ServerParam>"
-    else:
-        total = args.envs if args.envs != ENVS_PER_GPU else 1 << 18
-        off, n = shard_range(rank, world, total)
-        env = Soccer2DVecEnv(n, scenario="fullgame", device=dev, seed=0, substeps=k, env_id_offset=off)
-        pool = [commands((n, k, 22)) for _ in range(2)]
-        per_env = 2 * (22 * 36 + 64) + 22 * 16 * k + 480 + OUT_BYTES
-        name = f"11v11 full game, {total} matches in total, one command per player per cycle, K={k}"
-        kernel = "s2d::fullgame_step_kernel<default ServerParam, 11v11>"
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    env.reset_torch()
-    time_launches(env, pool, max(args.warmup, 3), flush)
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    barrier()
-    ms = time_launches(env, pool, args.steps, flush)
-    barrier()
-    total_ms = max_over_ranks(sum(ms))
-    value = total * k * args.steps / (total_ms * 1e-3)
-    launch_ms = sum(ms) / len(ms)
-    # e2e, pipelined host buffers
-    host_pool = [p.cpu().pin_memory() for p in pool]
-    e2e_steps = max(3, min(args.steps, 20))
-    env.enable_pipeline()
-    env.wait_host(env.submit_host(host_pool[0]))
-    barrier()
-    t0 = time.perf_counter()
-    ticket = env.submit_host(host_pool[0])
-    checksum = 0.0
-    for i in range(1, e2e_steps):
-        nxt = env.submit_host(host_pool[i % 2])
-        checksum += float(env.wait_host(ticket)[1][0])
-        ticket = nxt
-    checksum += float(env.wait_host(ticket)[1][0])
-    torch.cuda.synchronize()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    barrier()
-    hb = env._pipe["host"][0]
-    h2d = pool[0].numel() * pool[0].element_size()
-    d2h = sum(hb[x].numel() * hb[x].element_size() for x in ("obs", "reward", "done", "result"))
-    stats = env.allreduce_stats()
-    clocks = sampler.summary()
-    env.close()
-    if rank == 0:
-        peak, peak_src = load_peaks()
-        ach = per_env * n / (launch_ms * 1e-3) / 1e9
-        print(json.dumps({
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": name, "envs_per_gpu": n, "substeps": k, "global_envs": total,
-                       "parallelism": f"episode-shard x{world}", "l2": "flushed between timed launches (256 MiB memset, not timed)"},
-            "e2e": {"value": total * k * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3,
-                    "path": "Soccer2DVecEnv.submit_host / wait_host (s2d_submit_host / s2d_wait_host), pinned host buffers"},
-            "gpu_launches": args.steps,
-            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                         "traffic": load_traffic(f"fullgame_k{k}", n) if args.workload == "fullgame" else None,
-                         "issue_slots_busy_pct_ncu": load_traffic(f"fullgame_k{k}", n, "issue_active_pct") if args.workload == "fullgame" else None,
-                         "kernel": kernel, "launch_ms": launch_ms, "algorithmic_bytes_per_launch": per_env * n,
-                         "peak_source": peak_src},
-            "clocks": clocks, "episode_stats": stats}), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -526,26 +620,28 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="reachball", choices=["reachball", "shoot", "fullgame"],
-                    help="reachball = BASELINE configs[1] (the contract line); shoot / fullgame = configs[2] / [3]")
+                    help="reachball = BASELINE configs[1] (the contract line, with short shoot / fullgame sections); "
+                         "shoot / fullgame = configs[2] / [3] as the whole line")
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="episodes per GPU (default 2^20, configs[1])")
     ap.add_argument("--substeps", type=int, default=SUBSTEPS)
     ap.add_argument("--envs-k1", type=int, default=1 << 23, help="episodes per GPU of the K=1 roofline run")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="bound on the cpu_baseline sample")
+    ap.add_argument("--no-extras", action="store_true", help="skip the shoot / fullgame sections of the default line")
+    ap.add_argument("--no-numa", dest="numa", action="store_false", help="do not bind the rank to its GPU's NUMA node")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
+        if args.steps == 200:  # the default K of the B200 arm would take minutes on the CPU: keep it bounded
+            args.steps = 10
         run_reference(args, rank)
         return
     if world != args.gpus and world == 1 and args.gpus > 1:
         raise SystemExit(f"--gpus {args.gpus} needs torchrun: python -m torch.distributed.run --nproc-per-node {args.gpus} "
                          f"--master-addr 127.0.0.1 bench.py --gpus {args.gpus} ...")
-    if args.workload != "reachball":
-        if args.substeps == SUBSTEPS:
-            args.substeps = 1
-        run_other_workload(args, rank, local_rank, world)
-        return
+    if args.workload != "reachball" and args.substeps == SUBSTEPS:
+        args.substeps = 1
     run_b200(args, rank, local_rank, world)
 
 

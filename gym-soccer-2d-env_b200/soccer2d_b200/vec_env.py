@@ -13,6 +13,8 @@ tallies).  The torch-native calls (`reset_torch`, `step_torch`) return device te
 from __future__ import annotations
 
 import ctypes as C
+import operator
+from collections.abc import Sequence
 
 import numpy as np
 import torch
@@ -68,6 +70,58 @@ class _SharedInfo(dict):
 _RUNNING = _SharedInfo(result=None)
 
 
+class LazyInfos(Sequence):
+    """`infos` of Soccer2DVecEnv.step_wait: behaves like the list of per-env info dicts SB3 expects, but nothing is built
+    until somebody looks.  Every running env answers with one shared read-only {'result': None}; an env whose episode
+    ended gets its own dict {'result': 'Goal' | 'Out' | 'Timeout'[, 'terminal_observation': row]} on first access.
+    `infos[:]` and iteration give plain lists (what VecMonitor copies).  It reads the step's host arrays, which the env
+    recycles after `host_ring` further steps: an access later than that raises instead of returning another step's data."""
+    __slots__ = ("_env", "_n", "_done", "_result", "_term", "_serial", "_cache")
+
+    def __init__(self, env, done, result, term):
+        self._env, self._n, self._done, self._result, self._term = env, env.num_envs, done, result, term
+        self._serial, self._cache = env._step_serial, None
+
+    def __len__(self):
+        return self._n
+
+    def _finished(self) -> dict:
+        if self._cache is None:
+            if self._env._step_serial - self._serial >= self._env.host_ring:
+                raise RuntimeError("these infos belong to a step whose host buffers have been recycled; read infos within "
+                                   f"{self._env.host_ring - 1} steps or construct the env with a larger host_ring")
+            idx = np.flatnonzero(self._done).tolist()
+            names, result, term = _abi.RESULT_NAMES, self._result, self._term
+            if term is None:
+                self._cache = {i: {"result": names[int(result[i])]} for i in idx}
+            else:
+                self._cache = {i: {"result": names[int(result[i])], "terminal_observation": term[i].copy()} for i in idx}
+            self._done = self._result = self._term = None
+        return self._cache
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            out = [_RUNNING] * self._n
+            for j, info in self._finished().items():
+                out[j] = info
+            return out[i]
+        i = operator.index(i)
+        if i < 0:
+            i += self._n
+        if not 0 <= i < self._n:
+            raise IndexError("info index out of range")
+        return self._finished().get(i, _RUNNING)
+
+    def __iter__(self):
+        return iter(self[:])
+
+    def __eq__(self, other):
+        return self[:] == (other[:] if isinstance(other, LazyInfos) else other)
+
+    def __repr__(self):
+        return f"LazyInfos({self._n} envs, {len(self._finished())} finished)"
+
+
 class Soccer2DVecEnv(_VecEnvBase):
     """`num_envs` ReachBall episodes on one GPU.
 
@@ -88,6 +142,12 @@ class Soccer2DVecEnv(_VecEnvBase):
     noise          rcssserver's player_rand / ball_rand / kick_rand noise from the counter-based RNG, keyed on
                    (seed, global env id, server cycle, agent): reproducible, independent of sharding and of
                    `substeps`.  Off by default (the mode in which runs are compared with the double-precision CPU truth)
+    host_numa_node NUMA node for the pinned host staging blocks of step_host / submit_host (soccer2d_b200.numa: the node of
+                   this rank's GPU keeps the copies off the inter-socket link); None = wherever the driver allocates
+    host_ring      step_wait() hands out views of pinned host blocks, `host_ring` of them in rotation: the arrays (and the
+                   lazily built infos) of one step stay valid for the next host_ring - 1 steps - long enough for SB3's
+                   collect_rollouts / VecMonitor / VecNormalize, which copy what they keep - and no num_envs-sized copy is
+                   made per step.  step_wait(copy=True) returns private copies instead
     host_mapped_io actions / obs / reward / done / result live in PINNED HOST memory that the kernel reads and writes
                    directly over PCIe (unified addressing): no memcpy calls at all - the lowest-latency path for a
                    handful of envs (the single-env gym API uses it); the state stays in HBM
@@ -99,7 +159,8 @@ class Soccer2DVecEnv(_VecEnvBase):
     def __init__(self, num_envs: int, scenario: str = "reachball", device="cuda", seed: int = 0, substeps: int = 1,
                  env_id_offset: int = 0, auto_reset: bool = True, terminal_obs: bool = False,
                  server_param: dict | None = None, use_command_action: bool = False, goto_dist_thr: float = 0.5,
-                 noise: bool = False, host_mapped_io: bool = False, hetero_seed: int | None = None, **kwargs):
+                 noise: bool = False, host_mapped_io: bool = False, hetero_seed: int | None = None,
+                 host_numa_node: int | None = None, host_ring: int = 4, **kwargs):
         if scenario.lower() not in _SCENARIOS:
             raise ValueError(f"Environment {scenario} not found.")  # environment_factory.py:28
         self.scenario = scenario.lower()
@@ -116,6 +177,9 @@ class Soccer2DVecEnv(_VecEnvBase):
         if self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
         self.num_envs = int(num_envs)
+        self.host_numa_node = host_numa_node
+        self.host_ring = max(2, int(host_ring))
+        self._ring, self._ring_pos, self._step_serial = None, 0, 0
         self.substeps = int(substeps)
         self.kw = dict(defaults, **kwargs)
         for k, v in self.kw.items():
@@ -218,6 +282,7 @@ class Soccer2DVecEnv(_VecEnvBase):
         self._pinned = None
         self._pipe = None
         self._pending = None
+        self._numa_blocks = []
         self._user_dirty = False
         self.player_types = None
         self.type_of_player = None
@@ -238,9 +303,22 @@ class Soccer2DVecEnv(_VecEnvBase):
                 _carve(block, lay.done, n, torch.uint8), _carve(block, lay.result, n, torch.uint8),
                 _carve(block, lay.terminal_obs, (n, self.obs_dim), torch.float32) if self._with_term else None)
 
+    def pinned_bytes(self, nbytes: int) -> torch.Tensor:
+        """page-locked uint8 host tensor, on `host_numa_node` when one was given"""
+        if self.host_numa_node is None:
+            return torch.empty(int(nbytes), dtype=torch.uint8, pin_memory=True)
+        from .numa import PinnedBlock
+        pb = PinnedBlock(nbytes, self.host_numa_node)
+        self._numa_blocks.append(pb)  # keeps the registration alive as long as the env
+        return pb.tensor
+
+    def pinned_like(self, t: torch.Tensor) -> torch.Tensor:
+        """page-locked host tensor of t's shape / dtype (see pinned_bytes), e.g. for the actions of submit_host"""
+        return self.pinned_bytes(t.numel() * t.element_size()).view(t.dtype).view(t.shape)
+
     def _pinned_outputs(self) -> dict:
         """one pinned host block with the device block's layout: a step's outputs arrive in ONE copy"""
-        block = torch.empty(self.layout.bytes, dtype=torch.uint8, pin_memory=True)
+        block = self.pinned_bytes(self.layout.bytes)
         self._with_term, keep = False, self._with_term
         obs, reward, done, result, _ = self._carve_outputs(block)
         self._with_term = keep
@@ -290,15 +368,15 @@ class Soccer2DVecEnv(_VecEnvBase):
         """Pinned host staging tensors: 'actions' (fill it in place for zero-copy submission) and the
         outputs 'obs', 'reward', 'done', 'result' that step_host fills."""
         if self._pinned is None:
-            self._pinned = dict(self._pinned_outputs(),
-                                actions=torch.empty(self.actions.shape, dtype=self.actions.dtype, pin_memory=True))
+            self._pinned = dict(self._pinned_outputs(), actions=self.pinned_like(self.actions))
         return self._pinned
 
-    def step_host(self, actions=None):
+    def step_host(self, actions=None, out: dict | None = None, sync: bool = True):
         """Host actions in, host results out: H2D of the actions, the step launch and D2H of
         obs/reward/done/result are enqueued by ONE C-ABI call (s2d_step_host), then the stream is drained.
         `actions`: numpy array / CPU tensor of the action shape (pinned memory makes the copy asynchronous),
-        or None to submit host_buffers()['actions'].  Returns numpy views of the pinned output buffers."""
+        or None to submit host_buffers()['actions'].  Returns numpy views of the pinned output buffers (`out`: another
+        block of _pinned_outputs() to receive them; sync=False leaves the stream un-drained)."""
         if self.host_mapped_io:  # the kernel reads the actions from / writes the results to host memory itself
             if actions is not None:
                 self.actions.numpy()[...] = np.asarray(actions).reshape(tuple(self.actions.shape))
@@ -314,11 +392,14 @@ class Soccer2DVecEnv(_VecEnvBase):
         else:
             src = torch.from_numpy(np.ascontiguousarray(
                 np.asarray(actions).reshape(tuple(self.actions.shape)), dtype=p["actions"].numpy().dtype))
-        _abi.check(self.lib.s2d_step_host(self.handle, self.substeps, src.data_ptr(), p["obs"].data_ptr(),
-                                          p["reward"].data_ptr(), p["done"].data_ptr(), p["result"].data_ptr(),
+        self._host_src = src  # keep the host source alive until the copy has happened
+        o = out if out is not None else p
+        _abi.check(self.lib.s2d_step_host(self.handle, self.substeps, src.data_ptr(), o["obs"].data_ptr(),
+                                          o["reward"].data_ptr(), o["done"].data_ptr(), o["result"].data_ptr(),
                                           _stream_ptr(self.device)), self.handle)
-        torch.cuda.current_stream(self.device).synchronize()
-        return p["obs"].numpy(), p["reward"].numpy(), p["done"].numpy().view(np.bool_), p["result"].numpy()
+        if sync:
+            torch.cuda.current_stream(self.device).synchronize()
+        return o["obs"].numpy(), o["reward"].numpy(), o["done"].numpy().view(np.bool_), o["result"].numpy()
 
     # ---- pipelined host API: submit step i+1 while the results of step i are still coming back ---------
     def enable_pipeline(self, slots: int = 3) -> None:
@@ -392,27 +473,38 @@ class Soccer2DVecEnv(_VecEnvBase):
     def step_async(self, actions) -> None:
         self._pending = actions
 
-    def step_wait(self):
-        """SB3's VecEnv.step_wait.  `infos` costs O(episodes that ended), not O(num_envs): every running env shares one
-        read-only {'result': None}; an env whose episode ended gets its own dict with 'result' (what
-        utils/info_collector_callback.py:23-27 reads) and, with terminal_obs=True, 'terminal_observation'."""
-        obs, reward, done, result = self.step_host(self._pending)
-        self._pending = None
-        infos = [_RUNNING] * self.num_envs
-        idx = np.flatnonzero(done)
-        if idx.size:
-            term = None
-            if self.terminal_obs is not None:  # only the rows of the finished episodes cross the bus
-                rows = torch.from_numpy(idx).to(self.device)
-                term = self.terminal_obs.index_select(0, rows).cpu().numpy() if not self.host_mapped_io \
-                    else self.terminal_obs.numpy()[idx].copy()
-            names = _abi.RESULT_NAMES
-            for j, i in enumerate(idx.tolist()):
-                info = {"result": names[int(result[i])]}
-                if term is not None:
-                    info["terminal_observation"] = term[j]
-                infos[i] = info
-        return obs.copy(), reward.copy(), done.copy(), infos
+    def step_wait(self, copy: bool = False):
+        """SB3's VecEnv.step_wait.  Python work per step is O(1): the arrays are views of a pinned host block out of a
+        ring of `host_ring` (see the class docstring; copy=True for private copies) and `infos` is a LazyInfos that builds
+        dicts only for the envs whose episode ended, and only when read ('result' is what
+        utils/info_collector_callback.py:23-27 looks at; 'terminal_observation' with terminal_obs=True)."""
+        actions, self._pending = self._pending, None
+        if self.host_mapped_io:
+            obs, reward, done, result = self.step_host(actions)
+            obs, reward, done, result = obs.copy(), reward.copy(), done.copy(), result.copy()
+            term = self.terminal_obs.numpy() if self.terminal_obs is not None else None
+            self._step_serial += 1
+            return obs, reward, done, LazyInfos(self, done, result, term)
+        if self._ring is None:
+            self._ring = []
+            for _ in range(self.host_ring):
+                blk = self._pinned_outputs()
+                if self.terminal_obs is not None:
+                    blk["term"] = self.pinned_like(self.terminal_obs)
+                self._ring.append(blk)
+        self._ring_pos = (self._ring_pos + 1) % self.host_ring
+        blk = self._ring[self._ring_pos]
+        term = blk.get("term")
+        obs, reward, done, result = self.step_host(actions, out=blk, sync=term is None)
+        if term is not None:  # the whole block in one more async copy: no second synchronisation, no gather kernel
+            term.copy_(self.terminal_obs, non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()
+            term = term.numpy()
+        self._step_serial += 1
+        if copy:
+            obs, reward, done, result = obs.copy(), reward.copy(), done.copy(), result.copy()
+            term = term.copy() if term is not None else None
+        return obs, reward, done, LazyInfos(self, done, result, term)
 
     def step(self, actions):
         self.step_async(actions)

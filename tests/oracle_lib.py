@@ -12,6 +12,48 @@ STATE_FIELDS = ("px py vx vy body stamina effort recovery capacity bx by bvx bvy
                 "step_number cycle episode flags").split()
 
 
+# ---- S2DConfig as the oracle sees it: an independent ctypes mirror of include/soccer2d.h, so that a process that only
+# ---- times the CPU arm (bench.py --impl reference) never imports the product package or maps libsoccer2d.so.
+# ---- tests/test_oracle_c.py checks it field by field against soccer2d_b200._abi.Config.
+SP_FIELDS = (
+    "pitch_half_length pitch_half_width goal_width goal_post_radius ball_size ball_decay ball_rand ball_speed_max "
+    "ball_accel_max player_size player_decay player_rand player_speed_max player_accel_max dash_power_rate inertia_moment "
+    "min_dash_power max_dash_power min_dash_angle max_dash_angle dash_angle_step side_dash_rate back_dash_rate "
+    "min_power max_power min_moment max_moment kick_power_rate kickable_margin kick_rand "
+    "stamina_max stamina_inc_max extra_stamina stamina_capacity recover_init recover_min recover_dec recover_dec_thr "
+    "effort_init effort_max effort_min effort_dec effort_dec_thr effort_inc effort_inc_thr "
+    "slowness_on_top_for_left_team slowness_on_top_for_right_team").split()
+
+
+class OracleServerParam(C.Structure):
+    _fields_ = [(n, C.c_float) for n in SP_FIELDS] + [("reserved", C.c_float * 5)]
+
+
+class OracleConfig(C.Structure):
+    _fields_ = [("struct_size", C.c_int32), ("scenario", C.c_int32), ("num_envs", C.c_int64), ("env_id_offset", C.c_int64),
+                ("seed", C.c_uint64), ("device", C.c_int32), ("action_mode", C.c_int32), ("action_space_size", C.c_int32),
+                ("max_steps", C.c_int32), ("auto_reset", C.c_int32), ("change_ball_position", C.c_int32),
+                ("change_ball_velocity", C.c_int32), ("noise", C.c_int32), ("players_per_side", C.c_int32),
+                ("half_time_cycles", C.c_int32), ("kick_actions", C.c_int32), ("reserved_i", C.c_int32 * 3),
+                ("min_distance_to_ball", C.c_float), ("ball_position_x", C.c_float), ("ball_position_y", C.c_float),
+                ("ball_speed", C.c_float), ("ball_direction", C.c_float), ("goto_dist_thr", C.c_float),
+                ("reserved_f", C.c_float * 3), ("sp", OracleServerParam)]
+
+
+ACT_DISCRETE, ACT_CONTINUOUS, ACT_TURNING, ACT_COMMAND = 0, 1, 2, 3
+
+
+def default_config(num_envs, scenario=0, kind="f64", **kw):
+    """the oracle's own S2DConfig defaults (s2do_default_config) with overrides named like the struct fields"""
+    cfg = OracleConfig()
+    assert lib(kind).s2do_default_config(C.byref(cfg), int(scenario)) == 0
+    cfg.num_envs = int(num_envs)
+    for k, v in kw.items():
+        assert hasattr(cfg, k), k
+        setattr(cfg, k, v)
+    return cfg
+
+
 def build():
     subprocess.run(["make", "-s", "-C", ORACLE_DIR], check=True, capture_output=True)
 
@@ -29,6 +71,8 @@ def lib(kind: str):
         L.s2do_create.restype = C.c_int
         L.s2do_create.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
         L.s2do_destroy.argtypes = [C.c_void_p]
+        L.s2do_default_config.restype = C.c_int
+        L.s2do_default_config.argtypes = [C.c_void_p, C.c_int]
         L.s2do_set_threads.restype = C.c_int
         L.s2do_set_threads.argtypes = [C.c_int]
         L.s2do_reset.argtypes = [C.c_void_p, C.c_void_p]

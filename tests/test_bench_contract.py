@@ -34,6 +34,31 @@ def test_reference_arm_prints_the_contract_line():
     assert r.returncode == 0 and r.stdout.strip() == ""
 
 
+def test_reference_arm_is_the_same_workload_and_never_touches_the_product():
+    """the CPU arm must step the B200 arm's workload (2^20 envs x 16 cycles per step, same `config` dict) and
+    its process must neither import the product package nor map libsoccer2d.so."""
+    code = (
+        "import json, runpy, sys, io, contextlib\n"
+        f"sys.argv = [{BENCH!r}, '--impl', 'reference', '--steps', '1', '--warmup', '0']\n"
+        "buf = io.StringIO()\n"
+        "with contextlib.redirect_stdout(buf):\n"
+        f"    runpy.run_path({BENCH!r}, run_name='__main__')\n"
+        "maps = open('/proc/self/maps').read()\n"
+        "assert 'libsoccer2d' not in maps, 'the reference arm mapped the product library'\n"
+        "assert not any(m.startswith('soccer2d_b200') for m in sys.modules), 'the reference arm imported the product'\n"
+        "assert 'liboracle_f64' in maps\n"
+        "print(buf.getvalue())\n")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][0])
+    sys.path.insert(0, H.ROOT)
+    import bench
+    assert d["config"] == bench.workload_config(1, 1 << 20, 16)  # what the B200 arm prints, key for key
+    assert d["config"]["envs_per_gpu"] == 1 << 20 and d["config"]["substeps"] == 16
+    assert f"{1 << 20} envs x 16 cycles per step" in d["cpu_baseline"]["sample"]
+    assert abs(d["value"] - (1 << 24) / (d["ms_per_step"] * 1e-3)) < 1e-6 * d["value"]  # one step = 2^24 env-steps
+
+
 def test_b200_arm_fails_loudly_without_a_gpu():
     import torch
     if torch.cuda.is_available():

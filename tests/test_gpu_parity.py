@@ -120,22 +120,39 @@ def test_non_default_server_param_kernels_bit_exact(mode):
     env.close()
 
 
+# fp32 thresholds (`dist < 5`, `|x| > 52.5`) can fall on the other side of the f64 truth's: measured over all 2^20 envs x
+# 1 000 cycles of the bench workload this happens about 2.5e-6 times per env-step (profiles/parity_flips.json).  After such
+# a flip the two runs of that env are different episodes, so the env leaves the comparison; the test bounds the RATE on
+# seeds that were not looked at beforehand instead of demanding zero flips on hand-picked ones.
+MAX_FLIP_RATE = 2.0e-5
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
 @pytest.mark.parametrize("mode", ["discrete", "continuous", "turning"])
-def test_against_f64_truth_1000_cycles(mode):
-    """north star: flags bit-exact, floats within 1e-5 relative over 1 000 cycles against the double oracle."""
-    n = 192
-    env = make_env(n, mode, seed=2024, change_ball_velocity=True)
+def test_against_f64_truth_1000_cycles(mode, seed):
+    """north star: flags bit-exact, floats within 1e-5 relative over 1 000 cycles against the double oracle - for every
+    env until (if ever) an fp32 threshold flips one of its flags; the flip rate is bounded."""
+    n = 1024
+    env = make_env(n, mode, seed=seed, change_ball_velocity=True)
     sim = OL.OracleSim(env.cfg, "f64")
     assert H.obs_close(env.reset(), sim.reset()) < H.TOL
-    rng = np.random.default_rng(5)
-    episodes = 0
+    rng = np.random.default_rng(100 + seed)
+    alive = np.ones(n, bool)
+    episodes = compared = 0
     for _ in range(1000):
         act = H.random_actions(rng, mode, n)
         env.step_torch(torch.from_numpy(act))
         sim.step(act)
-        episodes += assert_same_step(env, sim, exact=False)
+        done, res = env.done_u8.cpu().numpy(), env.result.cpu().numpy()
+        compared += int(alive.sum())
+        alive &= (done == sim.done) & (res == sim.result)
+        assert H.obs_close(env.obs.cpu().numpy()[alive], sim.obs[alive]) < H.TOL
+        assert np.abs(env.reward.cpu().numpy()[alive] - sim.reward[alive]).max() < H.TOL * 100.0
+        episodes += int(done[alive].sum())
     assert episodes > n
-    g, o = gpu_state(env), sim.get_state()
+    flips = int((~alive).sum())
+    assert flips <= max(2, MAX_FLIP_RATE * compared), (flips, compared)
+    g, o = gpu_state(env)[alive], sim.get_state()[alive]
     assert np.array_equal(g[:, 16:], o[:, 16:])  # step_number, cycle, episode, collision flags
     assert H.state_err(g, o) < H.TOL
     env.close()

@@ -440,3 +440,34 @@ def test_fullgame_c_oracle_equals_the_twin_on_random_states():
             seen.add((int(before[i][k + 8]), m.mode))
     modes_after = {b for _, b in seen}
     assert {2, 3, 4, 5, 6, 7} <= modes_after, sorted(seen)  # play on, kick-off (goal), kick-in, free kick (offside), corner, goal kick
+
+
+def test_oracle_config_mirror_matches_the_product_struct_and_defaults():
+    """tests/oracle_lib.OracleConfig (what bench.py --impl reference fills without touching the product) has the layout
+    of soccer2d_b200._abi.Config, and s2do_default_config restates s2d_default_config for every scenario."""
+    import ctypes as C
+
+    from soccer2d_b200 import _abi
+    assert C.sizeof(OL.OracleConfig) == C.sizeof(_abi.Config)
+    for (na, ta), (nb, tb) in zip(OL.OracleConfig._fields_, _abi.Config._fields_):
+        assert na == nb and C.sizeof(ta) == C.sizeof(tb)
+        assert getattr(OL.OracleConfig, na).offset == getattr(_abi.Config, nb).offset
+    assert [f for f, _ in OL.OracleServerParam._fields_] == [f for f, _ in _abi.ServerParam._fields_]
+    lib = _abi.load()
+    for scenario in (_abi.SCENARIO_REACHBALL, _abi.SCENARIO_SHOOT, _abi.SCENARIO_FULLGAME):
+        mine = OL.default_config(1, scenario)
+        theirs = _abi.Config()
+        assert lib.s2d_default_config(C.byref(theirs), scenario) == 0
+        assert bytes(mine) == bytes(theirs)
+
+
+def test_oracle_envs_are_compact():
+    """one-player scenarios: a 2^16-env oracle steps the same as before with the compact env records (np players each)"""
+    cfg = OL.default_config(3000, action_mode=OL.ACT_DISCRETE, change_ball_velocity=1, seed=5)
+    a, b = OL.OracleSim(cfg, "f64"), OL.OracleSim(cfg, "f32")
+    a.reset(), b.reset()
+    rng = np.random.default_rng(0)
+    for _ in range(50):
+        act = rng.integers(0, 16, size=(3000, 4)).astype(np.uint8)
+        a.step(act, 4), b.step(act, 4)
+    assert np.array_equal(a.done, b.done) and np.abs(a.obs - b.obs).max() < 1e-3

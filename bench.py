@@ -623,7 +623,7 @@ def main():
                     help="reachball = BASELINE configs[1] (the contract line, with short shoot / fullgame sections); "
                          "shoot / fullgame = configs[2] / [3] as the whole line")
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="episodes per GPU (default 2^20, configs[1])")
-    ap.add_argument("--substeps", type=int, default=SUBSTEPS)
+    ap.add_argument("--substeps", type=int, default=None, help="fused cycles per launch (default: 16 for reachball, 1 for shoot / fullgame)")
     ap.add_argument("--envs-k1", type=int, default=1 << 23, help="episodes per GPU of the K=1 roofline run")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="bound on the cpu_baseline sample")
     ap.add_argument("--no-extras", action="store_true", help="skip the shoot / fullgame sections of the default line")
@@ -633,6 +633,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
+        args.substeps = args.substeps or SUBSTEPS
         if args.steps == 200:  # the default K of the B200 arm would take minutes on the CPU: keep it bounded
             args.steps = 10
         run_reference(args, rank)
@@ -640,8 +641,8 @@ def main():
     if world != args.gpus and world == 1 and args.gpus > 1:
         raise SystemExit(f"--gpus {args.gpus} needs torchrun: python -m torch.distributed.run --nproc-per-node {args.gpus} "
                          f"--master-addr 127.0.0.1 bench.py --gpus {args.gpus} ...")
-    if args.workload != "reachball" and args.substeps == SUBSTEPS:
-        args.substeps = 1
+    if args.substeps is None:
+        args.substeps = SUBSTEPS if args.workload == "reachball" else 1
     run_b200(args, rank, local_rank, world)
 
 

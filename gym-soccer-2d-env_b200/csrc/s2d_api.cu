@@ -210,9 +210,8 @@ int s2d_create(const S2DConfig* cfg, S2DHandle* out) {
     return S2D_ERR_CUDA;
   }
   kp.action_table = h->d_table;
-  h->grid = cfg->scenario == S2D_SCENARIO_FULLGAME
-                ? static_cast<int>((cfg->num_envs + (kFgBlock / 32) - 1) / (kFgBlock / 32))
-                : static_cast<int>((cfg->num_envs + kBlock - 1) / kBlock);
+  h->grid = cfg->scenario == S2D_SCENARIO_FULLGAME ? static_cast<int>((cfg->num_envs + kFgBlock - 1) / kFgBlock)  // thread = match
+                                                   : static_cast<int>((cfg->num_envs + kBlock - 1) / kBlock);
   *out = h;
   return S2D_OK;
 }
@@ -280,6 +279,10 @@ int s2d_bind(S2DHandle h, const S2DBuffers* b) {
   if ((reinterpret_cast<uintptr_t>(b->state) & 255) || (reinterpret_cast<uintptr_t>(b->actions) & 15) ||
       (reinterpret_cast<uintptr_t>(b->obs) & 15) || (b->terminal_obs && (reinterpret_cast<uintptr_t>(b->terminal_obs) & 15)))
     return fail(h, S2D_ERR_INVALID, "state must be 256-byte aligned; actions / obs / terminal_obs 16-byte aligned");
+  if (h->cfg.scenario == S2D_SCENARIO_FULLGAME &&
+      ((reinterpret_cast<uintptr_t>(b->actions) & 31) || (reinterpret_cast<uintptr_t>(b->obs) & 31) ||
+       (b->terminal_obs && (reinterpret_cast<uintptr_t>(b->terminal_obs) & 31))))
+    return fail(h, S2D_ERR_INVALID, "FULLGAME: actions / obs / terminal_obs must be 32-byte aligned (256-bit accesses)");
   h->buf = *b;
   h->kp.state = b->state;
   h->kp.actions = b->actions;
@@ -452,6 +455,10 @@ int s2d_bind_pipeline_slot(S2DHandle h, int slot, const S2DBuffers* second) {
   if ((reinterpret_cast<uintptr_t>(second->actions) & 15) || (reinterpret_cast<uintptr_t>(second->obs) & 15) ||
       (second->terminal_obs && (reinterpret_cast<uintptr_t>(second->terminal_obs) & 15)))
     return fail(h, S2D_ERR_INVALID, "actions / obs / terminal_obs must be 16-byte aligned");
+  if (h->cfg.scenario == S2D_SCENARIO_FULLGAME &&
+      ((reinterpret_cast<uintptr_t>(second->actions) & 31) || (reinterpret_cast<uintptr_t>(second->obs) & 31) ||
+       (second->terminal_obs && (reinterpret_cast<uintptr_t>(second->terminal_obs) & 31))))
+    return fail(h, S2D_ERR_INVALID, "FULLGAME: actions / obs / terminal_obs must be 32-byte aligned (256-bit accesses)");
   DeviceGuard guard(h->cfg.device);
   if (!h->st_in) {
     S2D_CUDA(h, cudaStreamCreateWithFlags(&h->st_in, cudaStreamNonBlocking));
@@ -592,10 +599,11 @@ int s2d_export_env(S2DHandle h, int64_t i, S2DEnvSnapshot* out, void* stream) {
     float4 pa[kFgMaxPlayers], pb[kFgMaxPlayers], ball, ef;
     float pc[kFgMaxPlayers];
     uint4 ei, ej;
-    const size_t first = static_cast<size_t>(i) * np;
-    S2D_CUDA(h, cudaMemcpyAsync(pa, base + L.pa() + first * 16, static_cast<size_t>(np) * 16, cudaMemcpyDeviceToHost, s));
-    S2D_CUDA(h, cudaMemcpyAsync(pb, base + L.pb() + first * 16, static_cast<size_t>(np) * 16, cudaMemcpyDeviceToHost, s));
-    S2D_CUDA(h, cudaMemcpyAsync(pc, base + L.pc() + first * 4, static_cast<size_t>(np) * 4, cudaMemcpyDeviceToHost, s));
+    // match-minor planes: player j of match i sits at row j, column i - one strided copy per plane
+    const size_t col = static_cast<size_t>(i);
+    S2D_CUDA(h, cudaMemcpy2DAsync(pa, 16, base + L.pa() + col * 16, n * 16, 16, np, cudaMemcpyDeviceToHost, s));
+    S2D_CUDA(h, cudaMemcpy2DAsync(pb, 16, base + L.pb() + col * 16, n * 16, 16, np, cudaMemcpyDeviceToHost, s));
+    S2D_CUDA(h, cudaMemcpy2DAsync(pc, 4, base + L.pc() + col * 4, L.nr() * 4, 4, np, cudaMemcpyDeviceToHost, s));
     S2D_CUDA(h, cudaMemcpyAsync(&ball, base + L.eb() + static_cast<size_t>(i) * 16, 16, cudaMemcpyDeviceToHost, s));
     S2D_CUDA(h, cudaMemcpyAsync(&ef, base + L.ef() + static_cast<size_t>(i) * 16, 16, cudaMemcpyDeviceToHost, s));
     S2D_CUDA(h, cudaMemcpyAsync(&ei, base + L.ei() + static_cast<size_t>(i) * 16, 16, cudaMemcpyDeviceToHost, s));

@@ -1,15 +1,21 @@
-// s2d_fullgame.cuh - the FULLGAME scenario (BASELINE configs[3]): up to 11 v 11, one WARP per match.
+// s2d_fullgame.cuh - the FULLGAME scenario (BASELINE configs[3]): up to 11 v 11, one THREAD per match.
 //
-// Lane l < np owns player l (l < pps: left team, uniform number l+1; else right team); the ball and the referee
-// state are replicated in every lane (computed redundantly, so they stay bit-identical across the warp).  Per-team
-// and per-match reductions are warp primitives: xor-butterfly shuffles for sums (kick accelerations on the ball,
-// collision proposals), ballots for "who kicked / who touched the ball", shuffles to broadcast a partner's position
-// in the collision loop.  The player block never leaves registers during the K fused cycles.
+// Thread t of the grid owns match t and walks its players in a loop; the 32 lanes of a warp are 32 different matches.
+// Nothing is exchanged between lanes, every lane carries work (a warp-per-match mapping leaves 10 of 32 lanes idle and
+// repeats the ball / referee arithmetic in all of them: 956 warp-instructions per match and cycle, round 1), and the
+// state is laid out match-minor in HBM, so that the lanes of a warp read and write 512 contiguous bytes per access.
+// A player streams through registers, one at a time (its three plane entries and its command are fetched while the
+// previous player computes); a copy of the positions sits in shared memory for the n-body parts of the cycle (nearest
+// pair, collisions, offside line, dead-ball clearance).
 //
 // Physics per player = the one-player functions of s2d_one_player.cuh (dash / turn / kick / Body_GoToPoint lowering,
 // MPObject::_inc, stamina) plus rcssserver's Stadium::collisions for n players; referee subset: goals, ball out ->
-// kick-in / corner kick / goal kick, kick-off after a goal, time over.  NOT in the reference (which only ever runs
-// one player with the referee off, soccer_2d_env.py:363-369): the spec is include/soccer2d.h.
+// kick-in / corner kick / goal kick, kick-off after a goal, offside, time over.  NOT in the reference (which only ever
+// runs one player with the referee off, soccer_2d_env.py:363-369): the spec is include/soccer2d.h.
+//
+// Sums over the players of a match (kick accelerations on the ball, collision proposals for the ball) are part of the
+// fp32 spec: they are added as a 32-leaf xor-butterfly (leaf = player index, absent players and non-contributors 0.0),
+// see tree_sum32 - the order the oracle uses.
 #pragma once
 #include "s2d_scenarios.cuh"
 
@@ -21,19 +27,21 @@ constexpr int kFgMaxPlayers = 22;
 constexpr float kFgFreeKickDist = 9.15f;  // the distance opponents keep from a dead ball
 constexpr float kFgOffsideArea = 2.5f;    // offside_active_area_size: a marked player this close to the ball takes part
 
-// HBM layout of N matches with np players each (plane-major; every plane starts 16-byte aligned):
-//   PA float4 [N][np] {x, y, vx, vy}            PB float4 [N][np] {body, stamina, effort, recovery}
-//   PC float  [N][np] stamina_capacity (plane padded to 16 B)
+// HBM layout of N matches with np players each: plane-major, MATCH-MINOR (consecutive matches are consecutive in
+// memory, so a warp = 32 matches touches 512 contiguous bytes per float4 access); every row starts 16-byte aligned:
+//   PA float4 [np][N] {x, y, vx, vy}            PB float4 [np][N] {body, stamina, effort, recovery}
+//   PC float  [np][Nr] stamina_capacity (Nr = N rounded up to a multiple of 4)
 //   EB float4 [N] ball {x, y, vx, vy}           EF float4 [N] {episode return, player separation bound, offside marks (bits), -}
 //   EI uint4  [N] {step_number, cycle, episode, mode | side<<8 | last_touch<<10 | timer<<12 | ball_collided<<20 | done<<21}
 //   EJ uint4  [N] {score_l, score_r, collided mask (bit = player), kicked mask}
 struct FgLayout {
   int64_t n;
   int np;
+  __host__ __device__ size_t nr() const { return (static_cast<size_t>(n) + 3) & ~static_cast<size_t>(3); }
   __host__ __device__ size_t pa() const { return 0; }
   __host__ __device__ size_t pb() const { return static_cast<size_t>(n) * np * 16; }
   __host__ __device__ size_t pc() const { return static_cast<size_t>(n) * np * 32; }
-  __host__ __device__ size_t eb() const { return pc() + ((static_cast<size_t>(n) * np * 4 + 15) & ~static_cast<size_t>(15)); }
+  __host__ __device__ size_t eb() const { return pc() + nr() * np * 4; }
   __host__ __device__ size_t ef() const { return eb() + static_cast<size_t>(n) * 16; }
   __host__ __device__ size_t ei() const { return ef() + static_cast<size_t>(n) * 16; }
   __host__ __device__ size_t ej() const { return ei() + static_cast<size_t>(n) * 16; }
@@ -51,202 +59,107 @@ struct Match {
   float sep;  // lower bound on the smallest player-player distance (see fg_collisions); 0 = unknown
   uint32_t offside;  // bit = player marked offside at the last pass of its team (all bits from one team)
   bool done_flag;
+  float bx, by, bvx, bvy;  // the ball
+};
+
+constexpr int kFgBlock = 64;  // matches (= threads) per block
+#ifndef S2D_FG_MIN_BLOCKS
+#define S2D_FG_MIN_BLOCKS 10  // 10 x 17 KB of shared memory per SM; up to 102 registers per thread
+#endif
+
+// The block's shared memory: per player a row of kFgBlock entries (lane-minor: conflict-free).
+struct FgShared {
+  float2 xy[kFgMaxPlayers][kFgBlock];  // position (the same values as plane PA holds)
+  float oldx[kFgMaxPlayers][kFgBlock]; // x before this cycle's move (the offside line is drawn at the moment of the pass)
+};
+
+// Plane pointers of one match (column t of every row), advanced by a row to go from player j to player j + 1.
+struct FgPlanes {
+  float4* pa;
+  float4* pb;
+  float* pc;
+  size_t row, rowc;  // elements per row
+  __device__ __forceinline__ FgPlanes(const KernelParams& P, const FgLayout& L, int64_t env) {
+    char* base = static_cast<char*>(P.state);
+    pa = reinterpret_cast<float4*>(base + L.pa()) + env;
+    pb = reinterpret_cast<float4*>(base + L.pb()) + env;
+    pc = reinterpret_cast<float*>(base + L.pc()) + env;
+    row = static_cast<size_t>(L.n);
+    rowc = L.nr();
+  }
 };
 
 // 4-4-2 kick-off formation of the left team (own half); the right team is the mirror image
 __device__ __constant__ float kFgFormX[11] = {-50, -36, -36, -36, -36, -20, -20, -20, -20, -9, -9};
 __device__ __constant__ float kFgFormY[11] = {0, -20, -7, 7, 20, -24, -8, 8, 24, -10, 10};
 
-__device__ __forceinline__ float butterfly_sum(float v) {
-#pragma unroll
-  for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
-  return v;
+// Sum of 32 leaves in xor-butterfly order ((i, i^16), then (i, i^8), ...): leaf i = v[i] where bit i of `mask` is set,
+// else 0.0.  Cold (only cycles with a kick or a ball collision get here), so the leaves live in local memory.
+__device__ __noinline__ float tree_sum32(const float* v, uint32_t mask) {
+  float leaf[32];
+#pragma unroll 1
+  for (int i = 0; i < 32; ++i) leaf[i] = ((mask >> i) & 1u) ? v[i] : 0.0f;
+#pragma unroll 1
+  for (int s = 16; s > 0; s >>= 1) {
+#pragma unroll 1
+    for (int i = 0; i < s; ++i) leaf[i] = leaf[i] + leaf[i + s];
+  }
+  return leaf[0];
 }
 
-__device__ __forceinline__ float butterfly_max(float v) {
-#pragma unroll
-  for (int m = 16; m >= 1; m >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, m));
-  return v;
-}
-
-// kick-off placement of one player (lane): formation spot plus a +-2 m jitter drawn per (episode, kick-off, player)
-__device__ __forceinline__ void fg_place_player(Episode& p, const KernelParams& P, uint64_t gid, uint32_t episode,
-                                                int lane, int pps, int kick_offs) {
-  const bool left = lane < pps;
-  const int k = left ? lane : lane - pps;
+// kick-off placement of one player: formation spot plus a +-2 m jitter drawn per (episode, kick-off, player)
+__device__ __forceinline__ void fg_place_player(float2& xy, float& body, const KernelParams& P, uint64_t gid, uint32_t episode,
+                                                int j, int pps, int kick_offs) {
+  const bool left = j < pps;
+  const int k = left ? j : j - pps;
   const uint4 w = philox4x32_10(P.seed, gid, episode, RNG_RESET,
-                                static_cast<uint32_t>(2 + lane) + 32u * (static_cast<uint32_t>(kick_offs) & 0xFFFFu));
+                                static_cast<uint32_t>(2 + j) + 32u * (static_cast<uint32_t>(kick_offs) & 0xFFFFu));
   const float jx = u32_to_unit(w.x) * 4.0f - 2.0f, jy = u32_to_unit(w.y) * 4.0f - 2.0f;
   const float fx = kFgFormX[k], fy = kFgFormY[k];
-  p.px = (left ? fx : -fx) + jx;
-  p.py = (left ? fy : -fy) + jy;
-  p.vx = 0.0f;
-  p.vy = 0.0f;
-  p.body = left ? 0.0f : 180.0f;
+  xy.x = (left ? fx : -fx) + jx;
+  xy.y = (left ? fy : -fy) + jy;
+  body = left ? 0.0f : 180.0f;
 }
 
-// Stadium::collisions for np players and the ball, one lane per player.  In a round every object collects the
-// positions proposed for it and moves to their average; afterwards whatever collided gets vel *= -0.1 once.
-// Returns this lane's bits: 1 = player collided, 2 = player touched the ball; ball_collided is warp-uniform.
-//
-// `sep` (kept in the match state) is a LOWER BOUND on the smallest distance between two players.  Every cycle it
-// shrinks by twice the largest distance a player moved in that cycle (`moved2` = this lane's squared step, the
-// referee's placements included); only when it drops below the collision distance is the exact minimum recomputed
-// (the O(n^2 / 32) pair loop) - in open play every few cycles instead of every cycle.  The ball is tested against every player every cycle.  If neither test finds an overlap, the ordered
-// relaxation rounds - which would change nothing - are skipped, so the results do not depend on this shortcut.
-template <class SP>
-__device__ __forceinline__ int fg_collisions(Episode& p, bool active, int lane, int np, bool ball_fixed, const SP& sp,
-                                             bool& ball_collided, float& sep, float moved2) {
-  const unsigned full = 0xffffffffu;
-  bool collided = false, ballhit = false, ball_any = false;
-  const float r = sp.player_size() + sp.ball_size();
-  const float r2 = sp.player_size() + sp.player_size();
-  const float h = r2 / 2.0f + kCollideEps;
-  ball_collided = false;
-
-  bool ball_overlap = false;
-  if (active && !ball_fixed) {
-    const float dx = p.bx - p.px, dy = p.by - p.py;
-    ball_overlap = dx * dx + dy * dy < r * r;
-  }
-  {
-    // the farthest any player moved this cycle (its own move, or the referee placing it 9.15 m from a dead ball):
-    // sqrt of the largest squared step over the lanes, rounded up
-    const float v2max = __uint_as_float(__reduce_max_sync(full, __float_as_uint(active ? moved2 : 0.0f)));
-    float moved;
-    asm("sqrt.approx.f32 %0, %1;" : "=f"(moved) : "f"(v2max));
-    sep -= 2.002f * moved + 1.0e-6f;
-  }
-  bool pairs_close = false;
-  if (sep < r2) {  // uniform: the bound has run out, measure the true minimum (lane i looks at (i + d) mod np, d <= np/2)
-    float m2 = 3.0e38f;
-    int j = lane;
+// every player to its kick-off spot, at rest, facing the opponents (after a goal; cold)
+__device__ __noinline__ void fg_kick_off_formation(FgShared& S, int t, FgPlanes g, const KernelParams& P, uint64_t gid,
+                                                   uint32_t episode, int np, int kick_offs) {
 #pragma unroll 1
-    for (int d = 1; d <= (np >> 1); ++d) {
-      j = j + 1 >= np ? j + 1 - np : j + 1;
-      const float xj = __shfl_sync(full, p.px, j), yj = __shfl_sync(full, p.py, j);
-      const float ex = p.px - xj, ey = p.py - yj;
-      m2 = fminf(m2, ex * ex + ey * ey);
-    }
-    m2 = active ? m2 : 3.0e38f;
-    m2 = __uint_as_float(__reduce_min_sync(full, __float_as_uint(m2)));  // non-negative floats order like their bits
-    pairs_close = m2 < r2 * r2;
-    sep = sqrtf(m2) * 0.999f;
+  for (int j = 0; j < np; ++j) {
+    float2 xy;
+    float body;
+    fg_place_player(xy, body, P, gid, episode, j, np >> 1, kick_offs);
+    S.xy[j][t] = xy;
+    *g.pa = make_float4(xy.x, xy.y, 0.0f, 0.0f);
+    float4 b = *g.pb;
+    b.x = body;
+    *g.pb = b;
+    g.pa += g.row;
+    g.pb += g.row;
   }
-  if (!pairs_close && !__any_sync(full, ball_overlap)) return 0;
-
-#pragma unroll 1
-  for (int round = 0; round < 10; ++round) {
-    bool col = false;
-    int cnt = 0;
-    float sx = 0.0f, sy = 0.0f, bpx = 0.0f, bpy = 0.0f;
-    bool bc = false;
-#pragma unroll 1
-    for (int j = 0; j < np; ++j) {
-      const float xj = __shfl_sync(full, p.px, j), yj = __shfl_sync(full, p.py, j);
-      if (!active) continue;
-      if (j == lane) {
-        if (ball_fixed) continue;
-        const float dx = p.bx - p.px, dy = p.by - p.py;
-        if (dx * dx + dy * dy < r * r) {
-          col = collided = ballhit = bc = true;
-          const float2 b = ball_back_trace(p.px, p.py, p.bx, p.by, p.bvx, p.bvy, r + kCollideEps);
-          bpx = b.x;
-          bpy = b.y;
-          sx += p.px;
-          sy += p.py;
-          cnt += 1;
-        }
-      } else {
-        const float ex = p.px - xj, ey = p.py - yj;
-        if (ex * ex + ey * ey < r2 * r2) {
-          col = collided = true;
-          const float mx = (p.px + xj) / 2.0f, my = (p.py + yj) / 2.0f;
-          const float d = hypot2(ex, ey);
-          float ux, uy;
-          if (d < 1.0e-10f) {
-            ux = lane < j ? 1.0f : -1.0f;
-            uy = 0.0f;
-          } else {
-            ux = ex / d;
-            uy = ey / d;
-          }
-          sx += mx + ux * h;
-          sy += my + uy * h;
-          cnt += 1;
-        }
-      }
-    }
-    const int bcnt = __popc(__ballot_sync(full, bc));
-    const float bsx = butterfly_sum(bpx), bsy = butterfly_sum(bpy);
-    if (bcnt) {
-      p.bx = bsx / static_cast<float>(bcnt);
-      p.by = bsy / static_cast<float>(bcnt);
-      ball_any = true;
-    }
-    if (cnt) {
-      p.px = sx / static_cast<float>(cnt);
-      p.py = sy / static_cast<float>(cnt);
-    }
-    if (!__any_sync(full, col)) break;
-  }
-  sep = 0.0f;  // players were pushed around: measure again next cycle
-  if (ball_any) {
-    p.bvx *= -0.1f;
-    p.bvy *= -0.1f;
-  }
-  if (collided) {
-    p.vx *= -0.1f;
-    p.vy *= -0.1f;
-  }
-  ball_collided = ball_any;
-  return (collided ? 1 : 0) | (ballhit ? 2 : 0);
-}
-
-// 120-float observation of a match: ball, 22 x {x, y, vx, vy, body}, referee state.  Staged in shared memory and
-// written by lanes 0..29 as one float4 each (480 contiguous bytes).
-__device__ __forceinline__ void fg_write_obs(float* __restrict__ dst, int64_t env, const Episode& p, const Match& m,
-                                             bool active, int lane, int np, int half_time,
-                                             float* stage /* [120] */) {
-  if (np < kFgMaxPlayers) {  // fewer than 11 a side: the rows of the absent players are zero
-    for (int k = lane; k < kFgObsDim; k += 32) stage[k] = 0.0f;
-    __syncwarp();
-  }
-  if (active) {
-    float* o = stage + 4 + 5 * lane;
-    o[0] = p.px * static_cast<float>(1.0 / 52.5);
-    o[1] = p.py * static_cast<float>(1.0 / 34.0);
-    o[2] = p.vx;
-    o[3] = p.vy;
-    o[4] = p.body * static_cast<float>(1.0 / 180.0);
-  }
-  if (lane == 31) {
-    stage[0] = p.bx * static_cast<float>(1.0 / 52.5);
-    stage[1] = p.by * static_cast<float>(1.0 / 34.0);
-    stage[2] = p.bvx * static_cast<float>(1.0 / 3.0);
-    stage[3] = p.bvy * static_cast<float>(1.0 / 3.0);
-    stage[114] = static_cast<float>(m.mode);
-    stage[115] = static_cast<float>(m.side);
-    stage[116] = static_cast<float>(m.score_l);
-    stage[117] = static_cast<float>(m.score_r);
-    stage[118] = static_cast<float>(m.step_number) / static_cast<float>(2 * half_time);
-    stage[119] = 0.0f;
-  }
-  __syncwarp();
-  if (lane < kFgObsDim / 4)
-    st_stream(reinterpret_cast<float4*>(dst + env * kFgObsDim) + lane, reinterpret_cast<const float4*>(stage)[lane]);
-  __syncwarp();
 }
 
 // new match: scores 0, kick-off formation, everybody recovered, kick-off for the left team
 template <class SP>
-__device__ __forceinline__ void fg_reset(Episode& p, Match& m, const KernelParams& P, const SP& sp, uint64_t gid, int lane,
-                                         int pps) {
+__device__ __noinline__ void fg_reset(FgShared& S, int t, FgPlanes g, Match& m, const KernelParams& P, SP sp, uint64_t gid, int np) {
   m.score_l = 0;
   m.score_r = 0;
-  if (lane < 2 * pps) fg_place_player(p, P, gid, m.episode, lane, pps, 0);  // (idle lanes would index past the formation)
-  recover(p, sp);
-  p.bx = p.by = p.bvx = p.bvy = 0.0f;
+#pragma unroll 1
+  for (int j = 0; j < np; ++j) {
+    if constexpr (SP::kHetero) sp.row = sp.table + PT_ROW * P.type_of[j];
+    float2 xy;
+    Episode p;
+    fg_place_player(xy, p.body, P, gid, m.episode, j, np >> 1, 0);
+    recover(p, sp);
+    S.xy[j][t] = xy;
+    *g.pa = make_float4(xy.x, xy.y, 0.0f, 0.0f);
+    *g.pb = make_float4(p.body, p.stamina, p.effort, p.recovery);
+    *g.pc = p.capacity;
+    g.pa += g.row;
+    g.pb += g.row;
+    g.pc += g.rowc;
+  }
+  m.bx = m.by = m.bvx = m.bvy = 0.0f;
   m.episode += 1u;
   m.step_number = 0;
   m.ep_return = 0.0f;
@@ -259,25 +172,24 @@ __device__ __forceinline__ void fg_reset(Episode& p, Match& m, const KernelParam
   m.last_touch = S2D_SIDE_UNKNOWN;
 }
 
-// The 22 commands of a cycle.  In a match every lane may carry a different command, so a switch over the command
-// would make the warp walk dash, turn, kick and go-to-point one after the other, each with its own sincos / atan2 /
-// sqrt.  Here the commands are decomposed into the pieces they share, each evaluated ONCE per warp under a vote and
-// with per-lane operands:
+// The command of player `agent` in the 32 matches of a warp.  Every lane may carry a different command, so a switch over
+// the command would make the warp walk dash, turn, kick and go-to-point one after the other, each with its own sincos /
+// atan2 / sqrt.  Here the commands are decomposed into the pieces they share, each evaluated ONCE per warp under a vote
+// (`full` = the lanes of the warp that hold a match) and with per-lane operands:
 //   geometry to a reference point  (go-to-point: the target, kick: the ball)  -> distance, relative angle
 //   speed                          (turn and go-to-point's turn: inertia)
 //   sincos(body + direction)       (dash, go-to-point's dash (direction 0), kick)
 // Per lane the arithmetic is the sequence of decode_command + dash_apply / turn / kick (s2d_one_player.cuh), so the
-// results are the same bit for bit.  Returns whether this lane kicked (kax, kay = its push on the ball).
+// results are the same bit for bit.  Returns whether the player kicked (kax, kay = its push on the ball).
 template <class SP>
 __device__ __forceinline__ bool fg_commands(Episode& p, float4 a, float goto_dist_thr, const SP& sp, const NoiseCtx& nz,
-                                            int lane, bool active, bool left, bool may_kick, float& ax, float& ay,
+                                            const unsigned full, int agent, bool left, bool may_kick, float& ax, float& ay,
                                             float& kax, float& kay) {
-  const unsigned full = 0xffffffffu;
   // the proxy's other body actions become a plain turn or kick first (rare: one vote when nobody uses them)
-  if (__any_sync(full, active && a.x >= static_cast<float>(S2D_CMD_TURN_TO_POINT))) {
-    if (active && a.x >= static_cast<float>(S2D_CMD_TURN_TO_POINT)) lower_body_action(p, a, sp);
+  if (__any_sync(full, a.x >= static_cast<float>(S2D_CMD_TURN_TO_POINT))) {
+    if (a.x >= static_cast<float>(S2D_CMD_TURN_TO_POINT)) lower_body_action(p, a, sp);
   }
-  const int c = active ? static_cast<int>(a.x) : S2D_CMD_NONE;
+  const int c = static_cast<int>(a.x);
   const bool is_goto = c == S2D_CMD_GOTO;
   const bool is_kick = c == S2D_CMD_KICK && may_kick;
   const bool user_dash = c == S2D_CMD_DASH, user_turn = c == S2D_CMD_TURN;
@@ -314,7 +226,7 @@ __device__ __forceinline__ bool fg_commands(Episode& p, float4 a, float goto_dis
     const float inertia = 1.0f + sp.inertia_moment() * speed;
     float moment = goto_turn ? clampf(sp.min_moment(), rel * inertia, sp.max_moment()) : user_turn ? a.y : 1.0f;
     moment = clampf(sp.min_moment(), moment, sp.max_moment());
-    if (SP::kNoise) moment = moment * (1.0f + sp.player_rand() * u11(noise_block(nz, static_cast<uint32_t>(lane)).z));
+    if (SP::kNoise) moment = moment * (1.0f + sp.player_rand() * u11(noise_block(nz, static_cast<uint32_t>(agent)).z));
     const float body = norm_deg(p.body + moment / inertia);
     p.body = do_turn ? body : p.body;
   }
@@ -367,7 +279,7 @@ __device__ __forceinline__ bool fg_commands(Episode& p, float4 a, float goto_dis
     bay += eff * sn;
     if (SP::kNoise) {
       if (__any_sync(full, kicked)) {
-        const uint4 w = noise_block(nz, static_cast<uint32_t>(lane)), w2 = noise_block(nz, 32u + static_cast<uint32_t>(lane));
+        const uint4 w = noise_block(nz, static_cast<uint32_t>(agent)), w2 = noise_block(nz, 32u + static_cast<uint32_t>(agent));
         const float pos_rate = 0.5f + 0.25f * (dir_diff * static_cast<float>(1.0 / 180.0) + dist_ball / sp.kickable_margin());
         const float speed_rate = 0.5f + 0.5f * (hypot2(p.bvx, p.bvy) / (sp.ball_speed_max() * sp.ball_decay()));
         const float max_rand = sp.kick_rand() * (power / sp.max_power()) * (pos_rate + speed_rate);
@@ -384,133 +296,429 @@ __device__ __forceinline__ bool fg_commands(Episode& p, float4 a, float goto_dis
   return kicked;
 }
 
-// One cycle of the match.  `a` = this lane's command {cmd, a, b, c}.  Returns done; reward / result are uniform.
-template <class SP>
-__device__ __forceinline__ bool fg_cycle(Episode& p, Match& m, const KernelParams& P, const SP& sp, uint64_t gid, int lane,
-                                         bool active, int np, int half_time, float4 a, float& reward, int& result,
-                                         uint32_t& collided_mask, uint32_t& kicked_mask, bool& ball_collided) {
-  const unsigned full = 0xffffffffu;
-  const int pps = np >> 1;
-  const bool left = lane < pps;
-  const int my_side = left ? S2D_SIDE_LEFT : S2D_SIDE_RIGHT;
-  bool dead = m.mode != S2D_PM_PLAY_ON;
-  m.step_number += 1;
 
-  // ---- commands ----
-  float ax = 0.0f, ay = 0.0f, kax = 0.0f, kay = 0.0f;
-  const NoiseCtx nz{P.seed, gid, m.cycle};
-  const bool kicked = fg_commands(p, a, P.goto_dist_thr, sp, nz, lane, active, left, !dead || my_side == m.side, ax, ay, kax, kay);
-  const unsigned kick_ballot = __ballot_sync(full, kicked);
-  float bax = 0.0f, bay = 0.0f;
-  if (kick_ballot) {  // uniform; without a kicker both sums are exactly zero
-    bax = butterfly_sum(kax);
-    bay = butterfly_sum(kay);
+// Stadium::collisions for np players and the ball of ONE match (cold: only when something overlaps).  In a round every
+// object collects the positions proposed for it and moves to their average; afterwards whatever collided gets
+// vel *= -0.1 once.  Returns the masks: players that collided, players that touched the ball; ball_collided by reference.
+//
+// `cand` = the players known to overlap something before the first round (close pairs from the pair scan, ball overlaps
+// from the second walk).  A pair can only overlap in a round if one of the two was involved in the round before (the
+// others have not moved and did not overlap then), so a player outside that set is tested against its members only -
+// in ascending order, like the full walk over all partners, whose other terms would be empty: the sums are the same.
+__device__ __noinline__ uint2 fg_resolve_collisions(FgShared& S, int t, FgPlanes g, Match& m, int np, bool ball_fixed, float r,
+                                                    float r2, uint32_t cand, bool& ball_collided) {
+  const float h = r2 / 2.0f + kCollideEps;
+  const uint32_t all = np >= 32 ? 0xffffffffu : (1u << np) - 1u;
+  uint32_t collided = 0, ballhit = 0, moved = 0;
+  bool ball_any = false, ball_moved = false;
+  float nx[kFgMaxPlayers], ny[kFgMaxPlayers], bpx[32], bpy[32];
+#pragma unroll 1
+  for (int round = 0; round < 10; ++round) {
+    uint32_t col = 0, bc = 0;
+#pragma unroll 1
+    for (int i = 0; i < np; ++i) {
+      const bool involved = (cand >> i) & 1u;
+      const bool with_ball = !ball_fixed && (involved || ball_moved);
+      uint32_t partners = ((involved ? all : cand) & ~(1u << i)) | (with_ball ? 1u << i : 0u);
+      if (!partners) continue;
+      const float2 pi = S.xy[i][t];
+      int cnt = 0;
+      float sx = 0.0f, sy = 0.0f;
+#pragma unroll 1
+      for (; partners; partners &= partners - 1u) {
+        const int j = __ffs(partners) - 1;
+        if (j == i) {
+          const float dx = m.bx - pi.x, dy = m.by - pi.y;
+          if (dx * dx + dy * dy < r * r) {
+            bc |= 1u << i;
+            const float2 b = ball_back_trace(pi.x, pi.y, m.bx, m.by, m.bvx, m.bvy, r + kCollideEps);
+            bpx[i] = b.x;
+            bpy[i] = b.y;
+            sx += pi.x;
+            sy += pi.y;
+            cnt += 1;
+          }
+        } else {
+          const float2 pj = S.xy[j][t];
+          const float ex = pi.x - pj.x, ey = pi.y - pj.y;
+          if (ex * ex + ey * ey < r2 * r2) {
+            const float mx = (pi.x + pj.x) / 2.0f, my = (pi.y + pj.y) / 2.0f;
+            const float d = hypot2(ex, ey);
+            float ux, uy;
+            if (d < 1.0e-10f) {
+              ux = i < j ? 1.0f : -1.0f;
+              uy = 0.0f;
+            } else {
+              ux = ex / d;
+              uy = ey / d;
+            }
+            sx += mx + ux * h;
+            sy += my + uy * h;
+            cnt += 1;
+          }
+        }
+      }
+      if (cnt) {
+        col |= 1u << i;
+        nx[i] = sx / static_cast<float>(cnt);
+        ny[i] = sy / static_cast<float>(cnt);
+      }
+    }
+    collided |= col;
+    ballhit |= bc;
+    ball_moved = bc != 0u;
+    if (bc) {
+      const float bcnt = static_cast<float>(__popc(bc));
+      m.bx = tree_sum32(bpx, bc) / bcnt;
+      m.by = tree_sum32(bpy, bc) / bcnt;
+      ball_any = true;
+    }
+#pragma unroll 1
+    for (uint32_t rest = col; rest; rest &= rest - 1u) {
+      const int i = __ffs(rest) - 1;
+      S.xy[i][t] = make_float2(nx[i], ny[i]);
+    }
+    moved |= col;
+    cand = col;
+    if (!col) break;
   }
-  const unsigned left_lanes = (1u << pps) - 1u;
-  const bool kick_l = (kick_ballot & left_lanes) != 0, kick_r = (kick_ballot & ~left_lanes) != 0;
+  m.sep = 0.0f;  // players were pushed around: measure again next cycle
+  if (ball_any) {
+    m.bvx *= -0.1f;
+    m.bvy *= -0.1f;
+  }
+#pragma unroll 1
+  for (uint32_t rest = moved; rest; rest &= rest - 1u) {  // (moved == collided: a player with a proposal collided)
+    const int i = __ffs(rest) - 1;
+    float4* pa = g.pa + static_cast<size_t>(i) * g.row;
+    const float4 a = *pa;
+    const float2 xy = S.xy[i][t];
+    *pa = make_float4(xy.x, xy.y, a.z * -0.1f, a.w * -0.1f);
+  }
+  ball_collided = ball_any;
+  return make_uint2(collided, ballhit);
+}
+
+// the players of the close pairs (distance below r2), as a mask: second pass of the pair scan, only when its minimum says so
+__device__ __noinline__ uint32_t fg_close_pairs(const FgShared& S, int t, int np, float r2) {
+  uint32_t mask = 0;
+#pragma unroll 1
+  for (int i = 0; i + 1 < np; ++i) {
+    const float2 pi = S.xy[i][t];
+#pragma unroll 1
+    for (int j = i + 1; j < np; ++j) {
+      const float2 pj = S.xy[j][t];
+      const float ex = pi.x - pj.x, ey = pi.y - pj.y;
+      if (ex * ex + ey * ey < r2 * r2) mask |= (1u << i) | (1u << j);
+    }
+  }
+  return mask;
+}
+
+// Offside marks (OffsideRef), taken at the moment of a pass by ONE team in PlayOn: the passer's team-mates that are, in
+// their direction of attack, beyond the ball, the half-way line and the second-last opponent.  Positions are those
+// before the cycle's move (S.oldx, the ball before its move).  Cold: only cycles with a kick.
+__device__ __noinline__ uint32_t fg_offside_marks(const FgShared& S, int t, int np, bool att_left, uint32_t kick_mask, float ball_x) {
+  const int pps = np >> 1;
+  const float sgn = att_left ? 1.0f : -1.0f;
+  const int d0 = att_left ? pps : 0, a0 = att_left ? 0 : pps;
+  float last = -3.0e38f, second = -3.0e38f;  // the two largest of the defenders (equal values count twice)
+#pragma unroll 1
+  for (int j = d0; j < d0 + pps; ++j) {
+    const float v = sgn * S.oldx[j][t];
+    if (v > last) {
+      second = last;
+      last = v;
+    } else if (v > second) {
+      second = v;
+    }
+  }
+  const float line_x = fmaxf(fmaxf(second, sgn * ball_x), 0.0f);
+  uint32_t marks = 0;
+#pragma unroll 1
+  for (int j = a0; j < a0 + pps; ++j)
+    if (((kick_mask >> j) & 1u) == 0u && sgn * S.oldx[j][t] > line_x) marks |= 1u << j;
+  return marks;
+}
+
+// The 120-float observation row of a match: ball, 22 x {x, y, vx, vy, body}, referee state (absent players zero).
+// Written by the match's own thread as 15 full 32-byte sectors; the plane entries of the next four players are in
+// flight while the current four are converted and stored.
+struct FgObsGroup {
+  float4 a[4];
+  float body[4];
+};
+__device__ __forceinline__ void fg_obs_load(FgObsGroup& q, const float4* pa, const float4* pb, size_t row, int first, int np) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    q.a[k] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    q.body[k] = 0.0f;
+    if (first + k < np) {
+      q.a[k] = pa[static_cast<size_t>(first + k) * row];
+      q.body[k] = reinterpret_cast<const float*>(pb + static_cast<size_t>(first + k) * row)[0];
+    }
+  }
+}
+__device__ __forceinline__ void fg_write_obs(float* __restrict__ dst, int64_t env, const FgPlanes& g, const Match& m, int np,
+                                             int half_time) {
+  float4* row = reinterpret_cast<float4*>(dst + env * kFgObsDim);
+  FgObsGroup nxt;
+  fg_obs_load(nxt, g.pa, g.pb, g.row, 0, np);
+  // carry: the float4 that completes a 32-byte sector with the first float4 of the next group (row[0] = the ball)
+  float4 carry = make_float4(m.bx * static_cast<float>(1.0 / 52.5), m.by * static_cast<float>(1.0 / 34.0),
+                             m.bvx * static_cast<float>(1.0 / 3.0), m.bvy * static_cast<float>(1.0 / 3.0));
+#pragma unroll 1
+  for (int grp = 0; grp < 6; ++grp) {  // four players = 20 floats = 5 float4; the last group: 2 players + the 6 referee values
+    const FgObsGroup cur = nxt;
+    if (grp < 5) fg_obs_load(nxt, g.pa, g.pb, g.row, 4 * grp + 4, np);
+    float f[20];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      f[5 * q + 0] = cur.a[q].x * static_cast<float>(1.0 / 52.5);
+      f[5 * q + 1] = cur.a[q].y * static_cast<float>(1.0 / 34.0);
+      f[5 * q + 2] = cur.a[q].z;
+      f[5 * q + 3] = cur.a[q].w;
+      f[5 * q + 4] = cur.body[q] * static_cast<float>(1.0 / 180.0);
+    }
+    if (grp == 5) {
+      f[10] = static_cast<float>(m.mode);
+      f[11] = static_cast<float>(m.side);
+      f[12] = static_cast<float>(m.score_l);
+      f[13] = static_cast<float>(m.score_r);
+      f[14] = static_cast<float>(m.step_number) / static_cast<float>(2 * half_time);
+      f[15] = 0.0f;
+    }
+    // float4 index of this group's first value: 1 + 5 grp.  Even groups start on the odd half of a sector (completed
+    // by `carry`), odd groups on the even half and leave their fifth float4 as the next carry.
+    float4* o = row + 5 * grp;
+    const float4 v0 = make_float4(f[0], f[1], f[2], f[3]), v1 = make_float4(f[4], f[5], f[6], f[7]);
+    const float4 v2 = make_float4(f[8], f[9], f[10], f[11]), v3 = make_float4(f[12], f[13], f[14], f[15]);
+    const float4 v4 = make_float4(f[16], f[17], f[18], f[19]);
+    if ((grp & 1) == 0) {  // row + 5 grp is sector aligned: {carry, v0} {v1, v2} {v3, v4}
+      st_stream_256(o, carry, v0);
+      st_stream_256(o + 2, v1, v2);
+      st_stream_256(o + 4, v3, v4);
+    } else {               // row + 5 grp + 1 is sector aligned: {v0, v1} {v2, v3}, v4 carried
+      st_stream_256(o + 1, v0, v1);
+      st_stream_256(o + 3, v2, v3);
+      carry = v4;
+    }
+  }
+}
+
+// One cycle of the match.  Commands: float4 {cmd, a, b, c} of player j at act[j].  Returns done.
+template <class SP>
+__device__ __forceinline__ bool fg_cycle(FgShared& S, const int t, const FgPlanes& g, Match& m, const KernelParams& P, SP& sp,
+                                         const unsigned full, uint64_t gid, int np, int half_time, const float4* __restrict__ act,
+                                         float& reward, int& result, uint32_t& collided_mask, uint32_t& kicked_mask,
+                                         bool& ball_collided) {
+  const int pps = np >> 1;
+  const unsigned left_set = (1u << pps) - 1u;
+  bool dead = m.mode != S2D_PM_PLAY_ON;
+  const bool dead_at_start = dead;
+  m.step_number += 1;
+  const NoiseCtx nz{P.seed, gid, m.cycle};
+
+  // ---- every player: command, move, stamina (the private part of the player streams through registers) ----
+  uint32_t kick_mask = 0;
+  float kx[32], ky[32];  // the kickers' pushes on the ball (local memory; written only when somebody kicks)
+  float moved2 = 0.0f;
+  {
+    float4* gpa = g.pa;
+    float4* gpb = g.pb;
+    float* gpc = g.pc;
+    // software pipeline: player j + 1's plane entries are in flight while player j computes; the commands come two
+    // players (one 32-byte sector) at a time
+    float4 n_a = ld_stream(gpa), n_b = ld_stream(gpb), cmd0, cmd1, n_cmd0, n_cmd1;
+    float n_c = ld_stream(gpc);
+    ld_nc_256(act, n_cmd0, n_cmd1);
+#pragma unroll 1
+    for (int j = 0; j < np; ++j) {
+      if constexpr (SP::kHetero) sp.row = sp.table + PT_ROW * P.type_of[j];
+      const float4 pa = n_a, b = n_b;
+      const float cap = n_c;
+      if ((j & 1) == 0) {  // (np is even)
+        cmd0 = n_cmd0;
+        cmd1 = n_cmd1;
+        if (j + 2 < np) ld_nc_256(act + j + 2, n_cmd0, n_cmd1);
+      }
+      const float4 a = (j & 1) ? cmd1 : cmd0;
+      float4* const wpa = gpa;
+      float4* const wpb = gpb;
+      float* const wpc = gpc;
+      gpa += g.row;
+      gpb += g.row;
+      gpc += g.rowc;
+      if (j + 1 < np) {
+        n_a = ld_stream(gpa);
+        n_b = ld_stream(gpb);
+        n_c = ld_stream(gpc);
+      }
+      const bool left = j < pps;
+      const int my_side = left ? S2D_SIDE_LEFT : S2D_SIDE_RIGHT;
+      Episode p;
+      p.px = pa.x; p.py = pa.y; p.vx = pa.z; p.vy = pa.w;
+      p.body = b.x; p.stamina = b.y; p.effort = b.z; p.recovery = b.w;
+      p.capacity = cap;
+      p.bx = m.bx; p.by = m.by; p.bvx = m.bvx; p.bvy = m.bvy;
+      S.oldx[j][t] = p.px;
+      float ax = 0.0f, ay = 0.0f, kax = 0.0f, kay = 0.0f;
+      const bool kicked = fg_commands(p, a, P.goto_dist_thr, sp, nz, full, j, left, !dead_at_start || my_side == m.side, ax, ay, kax, kay);
+      if (kicked) {
+        kick_mask |= 1u << j;
+        kx[j] = kax;
+        ky[j] = kay;
+      }
+      move_object<SP::kNoise>(p.px, p.py, p.vx, p.vy, ax, ay, sp.player_accel_max(), sp.player_accel_max2(),
+                              sp.player_speed_max(), sp.player_speed_max2(), sp.player_decay(), sp.player_rand(), &nz,
+                              static_cast<uint32_t>(j));
+      const float stepx = p.px - pa.x, stepy = p.py - pa.y;
+      moved2 = fmaxf(moved2, stepx * stepx + stepy * stepy);
+      update_stamina(p, sp);
+      S.xy[j][t] = make_float2(p.px, p.py);
+      st_stream(wpa, make_float4(p.px, p.py, p.vx, p.vy));
+      st_stream(wpb, make_float4(p.body, p.stamina, p.effort, p.recovery));
+      st_stream(wpc, p.capacity);
+    }
+  }
+
+  // ---- the kicks: acceleration of the ball, last touch, a dead ball comes alive, offside marks ----
+  float bax = 0.0f, bay = 0.0f;
+  if (kick_mask) {  // without a kicker both sums are exactly zero
+    bax = tree_sum32(kx, kick_mask);
+    bay = tree_sum32(ky, kick_mask);
+  }
+  const bool kick_l = (kick_mask & left_set) != 0, kick_r = (kick_mask & ~left_set) != 0;
   if (kick_l != kick_r) m.last_touch = kick_l ? S2D_SIDE_LEFT : S2D_SIDE_RIGHT;
   const int mode_at_kick = m.mode;
   if (dead && ((m.side == S2D_SIDE_LEFT && kick_l) || (m.side == S2D_SIDE_RIGHT && kick_r))) {
     m.mode = S2D_PM_PLAY_ON;
     dead = false;
   }
-  kicked_mask = kick_ballot;
-  // ---- offside marks (OffsideRef): taken at the moment of a pass; uniform branch, only in cycles with a kick ----
-  if (kick_ballot && !dead) {
+  kicked_mask = kick_mask;
+  if (kick_mask && !dead) {
     m.offside = 0u;  // whoever kicks: the old marks are void
     const bool exempt = mode_at_kick == S2D_PM_KICK_IN || mode_at_kick == S2D_PM_CORNER_KICK || mode_at_kick == S2D_PM_GOAL_KICK;
-    if (kick_l != kick_r && !exempt) {
-      // in the attackers' direction (x mirrored for the right team): beyond the ball, the half-way line and the
-      // second-last defender = offside
-      const bool att_left = kick_l;
-      const float sgn = att_left ? 1.0f : -1.0f;
-      const bool defender = active && left != att_left;
-      const float v = defender ? sgn * p.px : -3.0e38f;
-      const float last = butterfly_max(v);
-      const int who = __ffs(__ballot_sync(full, defender && v == last)) - 1;
-      const float second = butterfly_max(lane == who ? -3.0e38f : v);
-      const float line_x = fmaxf(fmaxf(second, sgn * p.bx), 0.0f);
-      const bool marked = active && left == att_left && ((kick_ballot >> lane) & 1u) == 0u && sgn * p.px > line_x;
-      m.offside = __ballot_sync(full, marked);
-    }
+    if (kick_l != kick_r && !exempt) m.offside = fg_offside_marks(S, t, np, kick_l, kick_mask, m.bx);
   }
 
-  // ---- move ----
-  const float pbx = p.bx, pby = p.by;
-  const float ppx = p.px, ppy = p.py;
-  if (active)
-    move_object<SP::kNoise>(p.px, p.py, p.vx, p.vy, ax, ay, sp.player_accel_max(), sp.player_accel_max2(),
-                            sp.player_speed_max(), sp.player_speed_max2(), sp.player_decay(), sp.player_rand(), &nz,
-                            static_cast<uint32_t>(lane));
+  // ---- the ball moves ----
+  const float pbx = m.bx, pby = m.by;
   if (!dead) {
-    move_object<SP::kNoise>(p.bx, p.by, p.bvx, p.bvy, bax, bay, sp.ball_accel_max(), sp.ball_accel_max2(),
+    move_object<SP::kNoise>(m.bx, m.by, m.bvx, m.bvy, bax, bay, sp.ball_accel_max(), sp.ball_accel_max2(),
                             sp.ball_speed_max(), sp.ball_speed_max2(), sp.ball_decay(), sp.ball_rand(), &nz, kBallAgent);
   } else {
-    p.bvx = 0.0f;
-    p.bvy = 0.0f;
+    m.bvx = 0.0f;
+    m.bvy = 0.0f;
   }
 
-  // ---- dead ball: the side that does not take the kick keeps 9.15 m away (uniform branch; rare) ----
-  if (dead && m.mode != S2D_PM_TIME_OVER) {
-    const float cx = p.px - p.bx, cy = p.py - p.by;
+  // ---- second walk over the players, now that ball and play mode are settled: a dead ball keeps the side that does
+  // ---- not take the kick 9.15 m away; a live ball is tested against every player ----
+  const float r = sp.player_size() + sp.ball_size();
+  const float r2 = sp.player_size() + sp.player_size();
+  const bool clearing = dead && m.mode != S2D_PM_TIME_OVER;
+  uint32_t ball_mask = 0;  // players the live ball overlaps
+  float cleared2 = 0.0f;
+#pragma unroll 1
+  for (int j = 0; j < np; ++j) {
+    float2 xy = S.xy[j][t];
+    const float cx = xy.x - m.bx, cy = xy.y - m.by;
     const float c2 = cx * cx + cy * cy;
-    const bool inside = active && my_side != m.side && c2 < kFgFreeKickDist * kFgFreeKickDist;
-    if (__any_sync(full, inside)) {
-      if (inside) {
-        const float c = sqrtf(c2);
-        float ux = left ? -1.0f : 1.0f, uy = 0.0f;
-        if (c >= 1.0e-6f) {
-          ux = cx / c;
-          uy = cy / c;
-        }
-        p.px = p.bx + ux * kFgFreeKickDist;
-        p.py = p.by + uy * kFgFreeKickDist;
-        p.vx = 0.0f;
-        p.vy = 0.0f;
+    const bool left = j < pps;
+    const int my_side = left ? S2D_SIDE_LEFT : S2D_SIDE_RIGHT;
+    if (clearing && my_side != m.side && c2 < kFgFreeKickDist * kFgFreeKickDist) {
+      const float c = sqrtf(c2);
+      float ux = left ? -1.0f : 1.0f, uy = 0.0f;
+      if (c >= 1.0e-6f) {
+        ux = cx / c;
+        uy = cy / c;
       }
+      const float nx = m.bx + ux * kFgFreeKickDist, ny = m.by + uy * kFgFreeKickDist;
+      const float sx = nx - xy.x, sy = ny - xy.y;
+      cleared2 = fmaxf(cleared2, sx * sx + sy * sy);
+      S.xy[j][t] = make_float2(nx, ny);
+      g.pa[static_cast<size_t>(j) * g.row] = make_float4(nx, ny, 0.0f, 0.0f);
     }
+    if (!dead && c2 < r * r) ball_mask |= 1u << j;
   }
 
   // ---- collisions ----
-  const float stepx = p.px - ppx, stepy = p.py - ppy;
-  const int hit = fg_collisions(p, active, lane, np, dead, sp, ball_collided, m.sep, stepx * stepx + stepy * stepy);
-  collided_mask = __ballot_sync(full, (hit & 1) != 0);
+  // `sep` (kept in the match state) is a LOWER BOUND on the smallest distance between two players.  Every cycle it
+  // shrinks by twice the farthest any player moved; only when it drops below the collision distance is the exact
+  // minimum measured (all pairs, from shared memory) - and then for every match of the warp, since the lanes walk the
+  // pairs together anyway.  Without a close pair and without a ball overlap the relaxation rounds - which would change
+  // nothing - are skipped, so the results do not depend on this shortcut.
   {
-    const unsigned touch = __ballot_sync(full, (hit & 2) != 0);
-    const bool hit_l = (touch & left_lanes) != 0, hit_r = (touch & ~left_lanes) != 0;
+    float moved, cleared;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(moved) : "f"(moved2));
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(cleared) : "f"(cleared2));
+    m.sep -= 2.002f * (moved + cleared) + 1.0e-6f;
+  }
+  uint32_t close_mask = 0;
+  if (__any_sync(full, m.sep < r2)) {
+    float m2 = 3.0e38f;
+#pragma unroll 1
+    for (int i = 0; i + 1 < np; ++i) {
+      const float2 pi = S.xy[i][t];
+#pragma unroll 1
+      for (int j = i + 1; j < np; ++j) {
+        const float2 pj = S.xy[j][t];
+        const float ex = pi.x - pj.x, ey = pi.y - pj.y;
+        m2 = fminf(m2, ex * ex + ey * ey);
+      }
+    }
+    if (m2 < r2 * r2) close_mask = fg_close_pairs(S, t, np, r2);
+    m.sep = sqrtf(m2) * 0.999f;
+  }
+  collided_mask = 0;
+  ball_collided = false;
+  uint32_t touch = 0;
+  if (close_mask | ball_mask) {
+    const uint2 hit = fg_resolve_collisions(S, t, g, m, np, dead, r, r2, close_mask | ball_mask, ball_collided);
+    collided_mask = hit.x;
+    touch = hit.y;
+  }
+  {
+    const bool hit_l = (touch & left_set) != 0, hit_r = (touch & ~left_set) != 0;
     if (hit_l != hit_r) m.last_touch = hit_l ? S2D_SIDE_LEFT : S2D_SIDE_RIGHT;
-    if (m.offside && (touch & ((m.offside & left_lanes) ? ~left_lanes : left_lanes))) m.offside = 0u;  // the defenders got the ball
+    if (m.offside && (touch & ((m.offside & left_set) ? ~left_set : left_set))) m.offside = 0u;  // the defenders got the ball
   }
 
-  // ---- referee (uniform across the warp) ----
+  // ---- referee ----
   int goal_l = 0, goal_r = 0;
-  const float bx_phys = p.bx;
+  const float bx_phys = m.bx;
   bool kick_off = false;
   const float line = sp.pitch_half_length() + sp.ball_size();
   const float side_line = sp.pitch_half_width() + sp.ball_size();
   bool offside_called = false;
   if (!dead && m.offside) {  // a marked player within 2.5 m of the ball takes part in play: free kick where it stands
-    const float ox = p.px - p.bx, oy = p.py - p.by;
-    const unsigned part = __ballot_sync(full, ((m.offside >> lane) & 1u) != 0u && ox * ox + oy * oy < kFgOffsideArea * kFgOffsideArea);
+    uint32_t part = 0;
+#pragma unroll 1
+    for (uint32_t rest = m.offside; rest; rest &= rest - 1u) {
+      const int j = __ffs(rest) - 1;
+      const float2 xy = S.xy[j][t];
+      const float ox = xy.x - m.bx, oy = xy.y - m.by;
+      if (ox * ox + oy * oy < kFgOffsideArea * kFgOffsideArea) part |= 1u << j;
+    }
     if (part) {
       const int who = __ffs(part) - 1;
-      const float fx = __shfl_sync(full, p.px, who), fy = __shfl_sync(full, p.py, who);
+      const float2 f = S.xy[who][t];
       m.mode = S2D_PM_FREE_KICK;
       m.side = who < pps ? S2D_SIDE_RIGHT : S2D_SIDE_LEFT;
       m.timer = 0;
-      p.bx = clampf(-sp.pitch_half_length(), fx, sp.pitch_half_length());
-      p.by = clampf(-sp.pitch_half_width(), fy, sp.pitch_half_width());
-      p.bvx = 0.0f;
-      p.bvy = 0.0f;
+      m.bx = clampf(-sp.pitch_half_length(), f.x, sp.pitch_half_length());
+      m.by = clampf(-sp.pitch_half_width(), f.y, sp.pitch_half_width());
+      m.bvx = 0.0f;
+      m.bvy = 0.0f;
       offside_called = true;
     }
   }
   if (offside_called) {
     // (the ball was re-placed inside the pitch: nothing else to rule on this cycle)
-  } else if (!dead && !(fabsf(p.bx) > line || fabsf(p.by) > side_line)) {
+  } else if (!dead && !(fabsf(m.bx) > line || fabsf(m.by) > side_line)) {
     // ball inside the field: every ruling below needs it beyond a line, so there is nothing to decide (the common case)
   } else if (!dead) {
-    const float bx = p.bx, by = p.by;
+    const float bx = m.bx, by = m.by;
     const float post = sp.goal_width() * 0.5f + sp.goal_post_radius();
     if (bx > line && !(pbx > line)) {
       const float yc = pby + (by - pby) * ((line - pbx) / (bx - pbx));
@@ -533,24 +741,24 @@ __device__ __forceinline__ bool fg_cycle(Episode& p, Match& m, const KernelParam
       if (m.last_touch == defending) {
         m.mode = S2D_PM_CORNER_KICK;
         m.side = defending == S2D_SIDE_LEFT ? S2D_SIDE_RIGHT : S2D_SIDE_LEFT;
-        p.bx = sx * (sp.pitch_half_length() - 1.0f);
-        p.by = sy * (sp.pitch_half_width() - 1.0f);
+        m.bx = sx * (sp.pitch_half_length() - 1.0f);
+        m.by = sy * (sp.pitch_half_width() - 1.0f);
       } else {
         m.mode = S2D_PM_GOAL_KICK;
         m.side = defending;
-        p.bx = sx * (sp.pitch_half_length() - 5.5f);
-        p.by = sy * 9.16f;
+        m.bx = sx * (sp.pitch_half_length() - 5.5f);
+        m.by = sy * 9.16f;
       }
-      p.bvx = 0.0f;
-      p.bvy = 0.0f;
+      m.bvx = 0.0f;
+      m.bvy = 0.0f;
       m.timer = 0;
     } else if (fabsf(by) > side_line) {
       m.mode = S2D_PM_KICK_IN;
       m.side = m.last_touch == S2D_SIDE_LEFT ? S2D_SIDE_RIGHT : S2D_SIDE_LEFT;
-      p.bx = clampf(-sp.pitch_half_length(), bx, sp.pitch_half_length());
-      p.by = by > 0.0f ? sp.pitch_half_width() : -sp.pitch_half_width();
-      p.bvx = 0.0f;
-      p.bvy = 0.0f;
+      m.bx = clampf(-sp.pitch_half_length(), bx, sp.pitch_half_length());
+      m.by = by > 0.0f ? sp.pitch_half_width() : -sp.pitch_half_width();
+      m.bvx = 0.0f;
+      m.bvy = 0.0f;
       m.timer = 0;
     }
   } else {
@@ -562,11 +770,10 @@ __device__ __forceinline__ bool fg_cycle(Episode& p, Match& m, const KernelParam
   }
   if (kick_off) {
     m.sep = 0.0f;
-    if (active) fg_place_player(p, P, gid, m.episode, lane, pps, m.score_l + m.score_r);
-    p.bx = p.by = p.bvx = p.bvy = 0.0f;
+    fg_kick_off_formation(S, t, g, P, gid, m.episode, np, m.score_l + m.score_r);
+    m.bx = m.by = m.bvx = m.bvy = 0.0f;
   }
   if (m.mode != S2D_PM_PLAY_ON) m.offside = 0u;  // marks live only while play goes on
-  if (active) update_stamina(p, sp);
   m.cycle += 1u;
   reward = static_cast<float>(goal_l - goal_r) * 10.0f + (bx_phys - pbx) * 0.01f;
   const bool done = m.step_number >= 2 * half_time;
@@ -575,23 +782,14 @@ __device__ __forceinline__ bool fg_cycle(Episode& p, Match& m, const KernelParam
   return done;
 }
 
-__device__ __forceinline__ void fg_load(const KernelParams& P, const FgLayout& L, int64_t env, int lane, bool active,
-                                        Episode& p, Match& m) {
+// match-level state: four coalesced 16-byte loads / stores per lane
+__device__ __forceinline__ void fg_load(const KernelParams& P, const FgLayout& L, int64_t env, Match& m) {
   const char* base = static_cast<const char*>(P.state);
-  p = Episode{};
-  if (active) {
-    const int64_t idx = env * L.np + lane;
-    const float4 a = ld_stream(reinterpret_cast<const float4*>(base + L.pa()) + idx);
-    const float4 b = ld_stream(reinterpret_cast<const float4*>(base + L.pb()) + idx);
-    p.px = a.x; p.py = a.y; p.vx = a.z; p.vy = a.w;
-    p.body = b.x; p.stamina = b.y; p.effort = b.z; p.recovery = b.w;
-    p.capacity = *(reinterpret_cast<const float*>(base + L.pc()) + idx);
-  }
-  const float4 ball = *(reinterpret_cast<const float4*>(base + L.eb()) + env);
-  const float4 ef = *(reinterpret_cast<const float4*>(base + L.ef()) + env);
-  const uint4 ei = *(reinterpret_cast<const uint4*>(base + L.ei()) + env);
-  const uint4 ej = *(reinterpret_cast<const uint4*>(base + L.ej()) + env);
-  p.bx = ball.x; p.by = ball.y; p.bvx = ball.z; p.bvy = ball.w;
+  const float4 ball = ld_stream(reinterpret_cast<const float4*>(base + L.eb()) + env);
+  const float4 ef = ld_stream(reinterpret_cast<const float4*>(base + L.ef()) + env);
+  const uint4 ei = ld_stream(reinterpret_cast<const uint4*>(base + L.ei()) + env);
+  const uint4 ej = ld_stream(reinterpret_cast<const uint4*>(base + L.ej()) + env);
+  m.bx = ball.x; m.by = ball.y; m.bvx = ball.z; m.bvy = ball.w;
   m.ep_return = ef.x;
   m.sep = ef.y;
   m.offside = __float_as_uint(ef.z);
@@ -601,99 +799,92 @@ __device__ __forceinline__ void fg_load(const KernelParams& P, const FgLayout& L
   m.score_l = static_cast<int>(ej.x); m.score_r = static_cast<int>(ej.y);
 }
 
-__device__ __forceinline__ void fg_store(const KernelParams& P, const FgLayout& L, int64_t env, int lane, bool active,
-                                         const Episode& p, const Match& m, uint32_t collided_mask, uint32_t kicked_mask,
-                                         bool ball_collided) {
+__device__ __forceinline__ void fg_store(const KernelParams& P, const FgLayout& L, int64_t env, const Match& m,
+                                         uint32_t collided_mask, uint32_t kicked_mask, bool ball_collided) {
   char* base = static_cast<char*>(P.state);
-  if (active) {
-    const int64_t idx = env * L.np + lane;
-    st_stream(reinterpret_cast<float4*>(base + L.pa()) + idx, make_float4(p.px, p.py, p.vx, p.vy));
-    st_stream(reinterpret_cast<float4*>(base + L.pb()) + idx, make_float4(p.body, p.stamina, p.effort, p.recovery));
-    *(reinterpret_cast<float*>(base + L.pc()) + idx) = p.capacity;
-  }
-  if (lane == 0) {
-    *(reinterpret_cast<float4*>(base + L.eb()) + env) = make_float4(p.bx, p.by, p.bvx, p.bvy);
-    *(reinterpret_cast<float4*>(base + L.ef()) + env) = make_float4(m.ep_return, m.sep, __uint_as_float(m.offside), 0.0f);
-    const uint32_t packed = static_cast<uint32_t>(m.mode) | (static_cast<uint32_t>(m.side) << 8) |
-                            (static_cast<uint32_t>(m.last_touch) << 10) | (static_cast<uint32_t>(m.timer) << 12) |
-                            (ball_collided ? 1u << 20 : 0u) | (m.done_flag ? 1u << 21 : 0u);
-    *(reinterpret_cast<uint4*>(base + L.ei()) + env) =
-        make_uint4(static_cast<uint32_t>(m.step_number), m.cycle, m.episode, packed);
-    *(reinterpret_cast<uint4*>(base + L.ej()) + env) =
-        make_uint4(static_cast<uint32_t>(m.score_l), static_cast<uint32_t>(m.score_r), collided_mask, kicked_mask);
-  }
+  st_stream(reinterpret_cast<float4*>(base + L.eb()) + env, make_float4(m.bx, m.by, m.bvx, m.bvy));
+  st_stream(reinterpret_cast<float4*>(base + L.ef()) + env, make_float4(m.ep_return, m.sep, __uint_as_float(m.offside), 0.0f));
+  const uint32_t packed = static_cast<uint32_t>(m.mode) | (static_cast<uint32_t>(m.side) << 8) |
+                          (static_cast<uint32_t>(m.last_touch) << 10) | (static_cast<uint32_t>(m.timer) << 12) |
+                          (ball_collided ? 1u << 20 : 0u) | (m.done_flag ? 1u << 21 : 0u);
+  st_stream(reinterpret_cast<uint4*>(base + L.ei()) + env, make_uint4(static_cast<uint32_t>(m.step_number), m.cycle, m.episode, packed));
+  st_stream(reinterpret_cast<uint4*>(base + L.ej()) + env,
+            make_uint4(static_cast<uint32_t>(m.score_l), static_cast<uint32_t>(m.score_r), collided_mask, kicked_mask));
 }
 
-// heterogeneous players: the block copies the type table to shared memory and every lane points at its player's row
+// heterogeneous players: the block copies the type table to shared memory; the player loops point sp.row at the row of
+// the player they are at
 template <class SP>
-__device__ __forceinline__ void fg_bind_player_type(SP& sp, const KernelParams& P, int lane) {
+__device__ __forceinline__ void fg_bind_player_types(SP& sp, const KernelParams& P) {
   if constexpr (SP::kHetero) {
     __shared__ float s_types[S2D_MAX_PLAYER_TYPES * PT_ROW];
     for (int k = threadIdx.x; k < S2D_MAX_PLAYER_TYPES * PT_ROW; k += blockDim.x) s_types[k] = __ldg(P.player_types + k);
     __syncthreads();
-    sp.row = s_types + PT_ROW * P.type_of[lane];
+    sp.table = s_types;
+    sp.row = s_types;
   }
 }
 
-#ifndef S2D_FG_MIN_BLOCKS
-#define S2D_FG_MIN_BLOCKS 8
-#endif
-constexpr int kFgBlock = 128;  // 4 matches per block
-
-// K lockstep cycles of every match; actions float4 [N][K][np].  NP = 22 is the 11 v 11 instantiation (player count,
-// team masks and row strides become immediates; otherwise the compiler keeps re-reading them from the constant bank
-// under register pressure); NP = 0 takes the player count at run time.
+// K lockstep cycles of every match; actions float4 [N][K][np].  NP = 22 is the 11 v 11 instantiation (player count and
+// team masks become immediates); NP = 0 takes the player count at run time.
 template <int VAR, int NP>
 __global__ void __launch_bounds__(kFgBlock, S2D_FG_MIN_BLOCKS) fullgame_step_kernel(const __grid_constant__ KernelParams P, const int K,
                                                                  const int np_runtime, const int half_time) {
   const int np = NP ? NP : np_runtime;
   using SP = typename VariantSP<VAR>::type;
   SP sp(P.cc);
-  __shared__ __align__(16) float s_stage[kFgBlock / 32][kFgObsDim];
-  const int lane = threadIdx.x & 31;
-  fg_bind_player_type(sp, P, lane);
-  const int64_t env = static_cast<int64_t>(blockIdx.x) * (kFgBlock / 32) + (threadIdx.x >> 5);
-  if (env >= P.num_envs) return;  // whole warp leaves together
+  __shared__ FgShared S;
+  fg_bind_player_types(sp, P);
+  const int t = threadIdx.x;
+  const int64_t env = static_cast<int64_t>(blockIdx.x) * kFgBlock + t;
+  if (env >= P.num_envs) return;
+  const unsigned full = __activemask();  // the lanes of this warp that hold a match (ragged last warp)
   const FgLayout L{P.num_envs, np};
-  const bool active = lane < np;
+  const FgPlanes g(P, L, env);
   const uint64_t gid = static_cast<uint64_t>(P.env_id_offset + env);
-  float* stage = s_stage[threadIdx.x >> 5];
 
-  Episode p;
+  // Ask the L2 for everything the block will read, with a handful of instructions and no registers: thread j < np its
+  // player row of the three planes (64 consecutive matches: 1 KB / 1 KB / 256 B), one thread the block's commands (K = 1:
+  // 22 KB in one piece).  The loads in the player loop then wait for the L2, not for DRAM.
+  {
+    const int64_t first = static_cast<int64_t>(blockIdx.x) * kFgBlock;
+    const int64_t left = P.num_envs - first;
+    const uint32_t cols = left < kFgBlock ? static_cast<uint32_t>(left) & ~3u : kFgBlock;  // 16-byte granules
+    if (t < np && cols) {
+      prefetch_l2_bulk(g.pa + (static_cast<size_t>(t) * g.row - t), cols * 16u);
+      prefetch_l2_bulk(g.pb + (static_cast<size_t>(t) * g.row - t), cols * 16u);
+      prefetch_l2_bulk(g.pc + (static_cast<size_t>(t) * g.rowc - t), cols * 4u);
+    }
+    if (t == 32 && K == 1 && cols)
+      prefetch_l2_bulk(static_cast<const float4*>(P.actions) + first * np, cols * static_cast<uint32_t>(np) * 16u);
+  }
   Match m;
-  fg_load(P, L, env, lane, active, p, m);
+  fg_load(P, L, env, m);
   uint32_t collided_mask = 0, kicked_mask = 0;
   bool ball_collided = false;
   float reward_sum = 0.0f;
   uint32_t any_done = 0, last_result = 0;
-  // the lane's commands: K rows np apart.  The next row is fetched while this cycle computes (its latency would
-  // otherwise sit in front of every cycle: nothing can start before the command is known).
-  const float4* act = static_cast<const float4*>(P.actions) + (env * K) * np + (active ? lane : 0);
-  float4 a_next = __ldg(act);
+  const float4* act = static_cast<const float4*>(P.actions) + (env * K) * np;
 #pragma unroll 1
-  for (int k = K; k > 0; --k) {
-    const float4 a = active ? a_next : make_float4(0.f, 0.f, 0.f, 0.f);
-    act += np;
-    if (k > 1) a_next = __ldg(act);
+  for (int k = K; k > 0; --k, act += np) {
     float rw;
     int rs;
-    const bool done = fg_cycle(p, m, P, sp, gid, lane, active, np, half_time, a, rw, rs, collided_mask, kicked_mask,
-                               ball_collided);
+    const bool done = fg_cycle(S, t, g, m, P, sp, full, gid, np, half_time, act, rw, rs, collided_mask, kicked_mask, ball_collided);
     reward_sum += rw;
     m.ep_return += rw;
     if (done) {
       any_done = 1;
       last_result = static_cast<uint32_t>(rs);
-      if (lane == 0 && !m.done_flag) {  // (a finished match stepped on with auto_reset off is tallied once)
+      if (!m.done_flag) {  // (a finished match stepped on with auto_reset off is tallied once)
         unsigned long long* slot = P.stats + static_cast<size_t>(env % kStatSlots) * kStatWords;
         atomicAdd(slot + ST_EPISODES, 1ull);
         atomicAdd(slot + (rs == 1 ? ST_GOALS : rs == 2 ? ST_OUTS : ST_TIMEOUTS), 1ull);
         atomicAdd(slot + ST_EP_STEPS, static_cast<unsigned long long>(m.step_number));
         atomicAdd(reinterpret_cast<double*>(slot + ST_RETURN), static_cast<double>(m.ep_return));
       }
-      if (P.terminal_obs) fg_write_obs(P.terminal_obs, env, p, m, active, lane, np, half_time, stage);
+      if (P.terminal_obs) fg_write_obs(P.terminal_obs, env, g, m, np, half_time);
       if (P.auto_reset) {
-        fg_reset(p, m, P, sp, gid, lane, np >> 1);
+        fg_reset(S, t, g, m, P, sp, gid, np);
         collided_mask = kicked_mask = 0;
         ball_collided = false;
       } else {
@@ -701,40 +892,35 @@ __global__ void __launch_bounds__(kFgBlock, S2D_FG_MIN_BLOCKS) fullgame_step_ker
       }
     }
   }
-  fg_store(P, L, env, lane, active, p, m, collided_mask, kicked_mask, ball_collided);
-  fg_write_obs(P.obs, env, p, m, active, lane, np, half_time, stage);
-  if (lane == 0) {
-    P.reward[env] = reward_sum;
-    P.done[env] = static_cast<uint8_t>(any_done);
-    P.result[env] = static_cast<uint8_t>(last_result);
-  }
+  fg_store(P, L, env, m, collided_mask, kicked_mask, ball_collided);
+  fg_write_obs(P.obs, env, g, m, np, half_time);
+  P.reward[env] = reward_sum;
+  P.done[env] = static_cast<uint8_t>(any_done);
+  P.result[env] = static_cast<uint8_t>(last_result);
 }
 
 template <bool HETERO>
 __global__ void __launch_bounds__(kFgBlock) fullgame_reset_kernel(const __grid_constant__ KernelParams P,
                                                                   const uint8_t* __restrict__ mask, const int np,
                                                                   const int half_time) {
-  __shared__ __align__(16) float s_stage[kFgBlock / 32][kFgObsDim];
-  const int lane = threadIdx.x & 31;
   using SP = typename std::conditional<HETERO, HeteroSP<false>, RuntimeSP>::type;
   SP sp(P.cc);
-  fg_bind_player_type(sp, P, lane);
-  const int64_t env = static_cast<int64_t>(blockIdx.x) * (kFgBlock / 32) + (threadIdx.x >> 5);
+  __shared__ FgShared S;
+  fg_bind_player_types(sp, P);
+  const int t = threadIdx.x;
+  const int64_t env = static_cast<int64_t>(blockIdx.x) * kFgBlock + t;
   if (env >= P.num_envs) return;
   if (mask && !mask[env]) return;
   const FgLayout L{P.num_envs, np};
-  const bool active = lane < np;
-  Episode p;
+  const FgPlanes g(P, L, env);
   Match m;
-  fg_load(P, L, env, lane, active, p, m);
-  fg_reset(p, m, P, sp, static_cast<uint64_t>(P.env_id_offset + env), lane, np >> 1);
-  fg_store(P, L, env, lane, active, p, m, 0u, 0u, false);
-  fg_write_obs(P.obs, env, p, m, active, lane, np, half_time, s_stage[threadIdx.x >> 5]);
-  if (lane == 0) {
-    P.reward[env] = 0.0f;
-    P.done[env] = 0;
-    P.result[env] = 0;
-  }
+  fg_load(P, L, env, m);
+  fg_reset(S, t, g, m, P, sp, static_cast<uint64_t>(P.env_id_offset + env), np);
+  fg_store(P, L, env, m, 0u, 0u, false);
+  fg_write_obs(P.obs, env, g, m, np, half_time);
+  P.reward[env] = 0.0f;
+  P.done[env] = 0;
+  P.result[env] = 0;
 }
 
 #endif  // !S2D_HOST_EMU

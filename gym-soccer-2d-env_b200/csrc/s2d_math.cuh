@@ -170,7 +170,47 @@ __device__ __forceinline__ void st_stream(uint4* p, const uint4& v) {
                "r"(v.w)
                : "memory");
 }
+// 256-bit accesses (sm_100): one full 32-byte sector per lane
+__device__ __forceinline__ void ld_nc_256(const float4* p, float4& a, float4& b) {
+  asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+               : "l"(p));
+}
+__device__ __forceinline__ void st_stream_256(float4* p, const float4& a, const float4& b) {
+  asm volatile("st.global.L1::no_allocate.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(a.x), "f"(a.y), "f"(a.z),
+               "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w)
+               : "memory");
+}
+// asks the L2 to fetch `bytes` (a multiple of 16) starting at the 16-byte aligned p: one instruction, no registers
+__device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ float ld_stream(const float* p) {
+  float v;
+  asm volatile("ld.global.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void st_stream(float* p, float v) {
+  asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
 #else
+// 256-bit accesses (sm_100): one full 32-byte sector per lane
+__device__ __forceinline__ void ld_nc_256(const float4* p, float4& a, float4& b) {
+  asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+               : "l"(p));
+}
+__device__ __forceinline__ void st_stream_256(float4* p, const float4& a, const float4& b) {
+  asm volatile("st.global.L1::no_allocate.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(a.x), "f"(a.y), "f"(a.z),
+               "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w)
+               : "memory");
+}
+// asks the L2 to fetch `bytes` (a multiple of 16) starting at the 16-byte aligned p: one instruction, no registers
+__device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ float ld_stream(const float* p) { return *p; }
+__device__ __forceinline__ void st_stream(float* p, float v) { *p = v; }
 __device__ __forceinline__ float4 ld_stream(const float4* p) { return *p; }
 __device__ __forceinline__ uint4 ld_stream(const uint4* p) { return *p; }
 __device__ __forceinline__ void st_stream(float4* p, const float4& v) { *p = v; }

@@ -126,7 +126,8 @@ template <bool NOISE>
 struct HeteroSP : RuntimeSP {
   static constexpr bool kNoise = NOISE;
   static constexpr bool kHetero = true;
-  const float* row = nullptr;  // this player's type
+  const float* row = nullptr;    // this player's type
+  const float* table = nullptr;  // all types: [S2D_MAX_PLAYER_TYPES][PT_ROW]
   S2D_HD explicit HeteroSP(const CycleConsts& c_) : RuntimeSP(c_) {}
   S2D_HD float player_decay() const { return row[PT_PLAYER_DECAY]; }
   S2D_HD float inertia_moment() const { return row[PT_INERTIA_MOMENT]; }

@@ -598,16 +598,18 @@ class Soccer2DVecEnv(_VecEnvBase):
         return f, u
 
     def fullgame_planes(self) -> dict:
-        """FULLGAME: views of the planes (layout: csrc/s2d_fullgame.cuh FgLayout)."""
+        """FULLGAME: views of the planes, indexed [match, player(, field)] (in memory they are match-minor - player rows
+        of N consecutive matches - see csrc/s2d_fullgame.cuh FgLayout)."""
         assert self.scenario == "fullgame"
         n, p = self.num_envs, self.num_players
         off = 0
         out = {}
-        for name, rows, width, dt in (("pa", n * p, 4, torch.float32), ("pb", n * p, 4, torch.float32)):
-            out[name] = self.state[off:off + rows * width * 4].view(dt).view(n, p, width)
-            off += rows * width * 4
-        out["pc"] = self.state[off:off + n * p * 4].view(torch.float32).view(n, p)
-        off += (n * p * 4 + 15) // 16 * 16
+        for name in ("pa", "pb"):
+            out[name] = self.state[off:off + n * p * 16].view(torch.float32).view(p, n, 4).permute(1, 0, 2)
+            off += n * p * 16
+        nr = (n + 3) // 4 * 4
+        out["pc"] = self.state[off:off + nr * p * 4].view(torch.float32).view(p, nr)[:, :n].t()
+        off += nr * p * 4
         for name, dt in (("ball", torch.float32), ("ef", torch.float32), ("ei", torch.int32), ("ej", torch.int32)):
             out[name] = self.state[off:off + n * 16].view(dt).view(n, 4)
             off += n * 16

@@ -207,7 +207,7 @@ typedef struct S2DConfig {
 /* Device buffers, owned by the caller.  Sizes come from the s2d_*_bytes helpers. */
 typedef struct S2DBuffers {
   void* state;         /* s2d_state_bytes(cfg), 256-B aligned; plane-major SoA (layout in DESIGN.md) */
-  void* actions;       /* k_max * s2d_action_bytes(cfg) */
+  void* actions;       /* k_max * s2d_action_bytes(cfg); 16-byte aligned (FULLGAME: actions, obs, terminal_obs 32-byte) */
   float* obs;          /* [num_envs][s2d_obs_dim(cfg)] row-major fp32 */
   float* reward;       /* [num_envs] (sum over the K substeps of one launch) */
   uint8_t* done;       /* [num_envs] 1 if an episode ended during the launch */

@@ -601,8 +601,8 @@ int s2d_export_env(S2DHandle h, int64_t i, S2DEnvSnapshot* out, void* stream) {
     uint4 ei, ej;
     // match-minor planes: player j of match i sits at row j, column i - one strided copy per plane
     const size_t col = static_cast<size_t>(i);
-    S2D_CUDA(h, cudaMemcpy2DAsync(pa, 16, base + L.pa() + col * 16, n * 16, 16, np, cudaMemcpyDeviceToHost, s));
-    S2D_CUDA(h, cudaMemcpy2DAsync(pb, 16, base + L.pb() + col * 16, n * 16, 16, np, cudaMemcpyDeviceToHost, s));
+    S2D_CUDA(h, cudaMemcpy2DAsync(pa, 16, base + L.pa() + col * 16, L.nr() * 16, 16, np, cudaMemcpyDeviceToHost, s));
+    S2D_CUDA(h, cudaMemcpy2DAsync(pb, 16, base + L.pb() + col * 16, L.nr() * 16, 16, np, cudaMemcpyDeviceToHost, s));
     S2D_CUDA(h, cudaMemcpy2DAsync(pc, 4, base + L.pc() + col * 4, L.nr() * 4, 4, np, cudaMemcpyDeviceToHost, s));
     S2D_CUDA(h, cudaMemcpyAsync(&ball, base + L.eb() + static_cast<size_t>(i) * 16, 16, cudaMemcpyDeviceToHost, s));
     S2D_CUDA(h, cudaMemcpyAsync(&ef, base + L.ef() + static_cast<size_t>(i) * 16, 16, cudaMemcpyDeviceToHost, s));

@@ -28,24 +28,27 @@ constexpr float kFgFreeKickDist = 9.15f;  // the distance opponents keep from a 
 constexpr float kFgOffsideArea = 2.5f;    // offside_active_area_size: a marked player this close to the ball takes part
 
 // HBM layout of N matches with np players each: plane-major, MATCH-MINOR (consecutive matches are consecutive in
-// memory, so a warp = 32 matches touches 512 contiguous bytes per float4 access); every row starts 16-byte aligned:
-//   PA float4 [np][N] {x, y, vx, vy}            PB float4 [np][N] {body, stamina, effort, recovery}
-//   PC float  [np][Nr] stamina_capacity (Nr = N rounded up to a multiple of 4)
-//   EB float4 [N] ball {x, y, vx, vy}           EF float4 [N] {episode return, player separation bound, offside marks (bits), -}
-//   EI uint4  [N] {step_number, cycle, episode, mode | side<<8 | last_touch<<10 | timer<<12 | ball_collided<<20 | done<<21}
-//   EJ uint4  [N] {score_l, score_r, collided mask (bit = player), kicked mask}
+// memory, so a warp = 32 matches touches 512 contiguous bytes per float4 access).  Rows hold Nr = N rounded up to the
+// block size (64) entries: every thread of the grid owns a column, so warps are always whole (the columns past N are
+// scratch matches that are simulated and never reported):
+//   PA float4 [np][Nr] {x, y, vx, vy}           PB float4 [np][Nr] {body, stamina, effort, recovery}
+//   PC float  [np][Nr] stamina_capacity
+//   EB float4 [Nr] ball {x, y, vx, vy}          EF float4 [Nr] {episode return, player separation bound, offside marks (bits), -}
+//   EI uint4  [Nr] {step_number, cycle, episode, mode | side<<8 | last_touch<<10 | timer<<12 | ball_collided<<20 | done<<21}
+//   EJ uint4  [Nr] {score_l, score_r, collided mask (bit = player), kicked mask}
+constexpr int kFgBlock = 64;  // matches (= threads) per block
 struct FgLayout {
   int64_t n;
   int np;
-  __host__ __device__ size_t nr() const { return (static_cast<size_t>(n) + 3) & ~static_cast<size_t>(3); }
+  __host__ __device__ size_t nr() const { return (static_cast<size_t>(n) + kFgBlock - 1) / kFgBlock * kFgBlock; }
   __host__ __device__ size_t pa() const { return 0; }
-  __host__ __device__ size_t pb() const { return static_cast<size_t>(n) * np * 16; }
-  __host__ __device__ size_t pc() const { return static_cast<size_t>(n) * np * 32; }
+  __host__ __device__ size_t pb() const { return nr() * np * 16; }
+  __host__ __device__ size_t pc() const { return nr() * np * 32; }
   __host__ __device__ size_t eb() const { return pc() + nr() * np * 4; }
-  __host__ __device__ size_t ef() const { return eb() + static_cast<size_t>(n) * 16; }
-  __host__ __device__ size_t ei() const { return ef() + static_cast<size_t>(n) * 16; }
-  __host__ __device__ size_t ej() const { return ei() + static_cast<size_t>(n) * 16; }
-  __host__ __device__ size_t bytes() const { return ej() + static_cast<size_t>(n) * 16; }
+  __host__ __device__ size_t ef() const { return eb() + nr() * 16; }
+  __host__ __device__ size_t ei() const { return ef() + nr() * 16; }
+  __host__ __device__ size_t ej() const { return ei() + nr() * 16; }
+  __host__ __device__ size_t bytes() const { return ej() + nr() * 16; }
 };
 
 #ifndef S2D_HOST_EMU
@@ -62,15 +65,18 @@ struct Match {
   float bx, by, bvx, bvy;  // the ball
 };
 
-constexpr int kFgBlock = 64;  // matches (= threads) per block
+#ifndef S2D_FG_AHEAD
+#define S2D_FG_AHEAD 2  // player rows the L2 is asked for ahead of the register prefetch (measured: 0 -> 201 us, 1..3 -> 190 us)
+#endif
 #ifndef S2D_FG_MIN_BLOCKS
-#define S2D_FG_MIN_BLOCKS 10  // 10 x 17 KB of shared memory per SM; up to 102 registers per thread
+#define S2D_FG_MIN_BLOCKS 10  // 92 registers per thread (no spills), 20 warps per SM, 10 x 22 KB of shared memory
 #endif
 
 // The block's shared memory: per player a row of kFgBlock entries (lane-minor: conflict-free).
 struct FgShared {
   float2 xy[kFgMaxPlayers][kFgBlock];  // position (the same values as plane PA holds)
   float oldx[kFgMaxPlayers][kFgBlock]; // x before this cycle's move (the offside line is drawn at the moment of the pass)
+  float obs[20][kFgBlock];             // four players' worth of the observation row on its way out (five float4)
 };
 
 // Plane pointers of one match (column t of every row), advanced by a row to go from player j to player j + 1.
@@ -84,7 +90,7 @@ struct FgPlanes {
     pa = reinterpret_cast<float4*>(base + L.pa()) + env;
     pb = reinterpret_cast<float4*>(base + L.pb()) + env;
     pc = reinterpret_cast<float*>(base + L.pc()) + env;
-    row = static_cast<size_t>(L.n);
+    row = L.nr();
     rowc = L.nr();
   }
 };
@@ -297,56 +303,70 @@ __device__ __forceinline__ bool fg_commands(Episode& p, float4 a, float goto_dis
 }
 
 
-// Stadium::collisions for np players and the ball of ONE match (cold: only when something overlaps).  In a round every
-// object collects the positions proposed for it and moves to their average; afterwards whatever collided gets
-// vel *= -0.1 once.  Returns the masks: players that collided, players that touched the ball; ball_collided by reference.
-//
-// `cand` = the players known to overlap something before the first round (close pairs from the pair scan, ball overlaps
-// from the second walk).  A pair can only overlap in a round if one of the two was involved in the round before (the
-// others have not moved and did not overlap then), so a player outside that set is tested against its members only -
-// in ascending order, like the full walk over all partners, whose other terms would be empty: the sums are the same.
-__device__ __noinline__ uint2 fg_resolve_collisions(FgShared& S, int t, FgPlanes g, Match& m, int np, bool ball_fixed, float r,
-                                                    float r2, uint32_t cand, bool& ball_collided) {
+__device__ __forceinline__ float butterfly_sum(float v) {
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+  return v;
+}
+
+// Stadium::collisions for the matches of a warp that have an overlap (`need`: one bit per lane = match).  Overlaps are
+// rare (a few per cent of the matches per cycle), and resolving one is an O(np^2) affair that would hold the other 31
+// matches of the warp: so the WARP resolves each such match together, lane l = player l of that match - positions come
+// from shared memory, partner positions are shuffle broadcasts, the ball's proposals are summed with an xor butterfly.
+// In a round every object collects the positions proposed for it and moves to their average; afterwards whatever
+// collided gets vel *= -0.1 once.  The lane that owns the match receives the masks (players that collided, players that
+// touched the ball) and the ball; the player lanes write positions and velocities back (shared memory, plane PA and,
+// when `obs_rows` (the observation tensor) is set - last cycle of a launch -, the row the player loop has already written).
+__device__ __noinline__ void fg_resolve_collisions(FgShared& S, const int t, const FgPlanes g, Match& m, const int np, unsigned need,
+                                                   const bool dead, const float r, const float r2, float* obs_rows, const int64_t env,
+                                                   const bool valid,
+                                                   uint32_t& collided_mask, uint32_t& touch, bool& ball_collided) {
+  const unsigned full = 0xffffffffu;
+  const int lane = t & 31;
+  const bool active = lane < np;
   const float h = r2 / 2.0f + kCollideEps;
-  const uint32_t all = np >= 32 ? 0xffffffffu : (1u << np) - 1u;
-  uint32_t collided = 0, ballhit = 0, moved = 0;
-  bool ball_any = false, ball_moved = false;
-  float nx[kFgMaxPlayers], ny[kFgMaxPlayers], bpx[32], bpy[32];
 #pragma unroll 1
-  for (int round = 0; round < 10; ++round) {
-    uint32_t col = 0, bc = 0;
+  while (need) {
+    const int src = __ffs(need) - 1;
+    need &= need - 1u;
+    const int ts = t - lane + src;  // the match's column in shared memory
+    float bx = __shfl_sync(full, m.bx, src), by = __shfl_sync(full, m.by, src);
+    const float bvx = __shfl_sync(full, m.bvx, src), bvy = __shfl_sync(full, m.bvy, src);
+    const bool ball_fixed = __shfl_sync(full, static_cast<int>(dead), src) != 0;
+    const bool report = __shfl_sync(full, static_cast<int>(valid), src) != 0;
+    float2 pos = active ? S.xy[lane][ts] : make_float2(0.0f, 0.0f);
+    bool collided = false, ballhit = false, ball_any = false;
 #pragma unroll 1
-    for (int i = 0; i < np; ++i) {
-      const bool involved = (cand >> i) & 1u;
-      const bool with_ball = !ball_fixed && (involved || ball_moved);
-      uint32_t partners = ((involved ? all : cand) & ~(1u << i)) | (with_ball ? 1u << i : 0u);
-      if (!partners) continue;
-      const float2 pi = S.xy[i][t];
+    for (int round = 0; round < 10; ++round) {
+      bool col = false;
       int cnt = 0;
-      float sx = 0.0f, sy = 0.0f;
+      float sx = 0.0f, sy = 0.0f, bpx = 0.0f, bpy = 0.0f;
+      bool bc = false;
 #pragma unroll 1
-      for (; partners; partners &= partners - 1u) {
-        const int j = __ffs(partners) - 1;
-        if (j == i) {
-          const float dx = m.bx - pi.x, dy = m.by - pi.y;
+      for (int j = 0; j < np; ++j) {
+        const float xj = __shfl_sync(full, pos.x, j), yj = __shfl_sync(full, pos.y, j);
+        if (!active) continue;
+        if (j == lane) {
+          if (ball_fixed) continue;
+          const float dx = bx - pos.x, dy = by - pos.y;
           if (dx * dx + dy * dy < r * r) {
-            bc |= 1u << i;
-            const float2 b = ball_back_trace(pi.x, pi.y, m.bx, m.by, m.bvx, m.bvy, r + kCollideEps);
-            bpx[i] = b.x;
-            bpy[i] = b.y;
-            sx += pi.x;
-            sy += pi.y;
+            col = collided = ballhit = bc = true;
+            const float2 b = ball_back_trace(pos.x, pos.y, bx, by, bvx, bvy, r + kCollideEps);
+            bpx = b.x;
+            bpy = b.y;
+            sx += pos.x;
+            sy += pos.y;
             cnt += 1;
           }
         } else {
-          const float2 pj = S.xy[j][t];
-          const float ex = pi.x - pj.x, ey = pi.y - pj.y;
+          const float ex = pos.x - xj, ey = pos.y - yj;
           if (ex * ex + ey * ey < r2 * r2) {
-            const float mx = (pi.x + pj.x) / 2.0f, my = (pi.y + pj.y) / 2.0f;
+            col = collided = true;
+            const float mx = (pos.x + xj) / 2.0f, my = (pos.y + yj) / 2.0f;
             const float d = hypot2(ex, ey);
             float ux, uy;
             if (d < 1.0e-10f) {
-              ux = i < j ? 1.0f : -1.0f;
+              ux = lane < j ? 1.0f : -1.0f;
               uy = 0.0f;
             } else {
               ux = ex / d;
@@ -358,61 +378,47 @@ __device__ __noinline__ uint2 fg_resolve_collisions(FgShared& S, int t, FgPlanes
           }
         }
       }
+      const int bcnt = __popc(__ballot_sync(full, bc));
+      const float bsx = butterfly_sum(bpx), bsy = butterfly_sum(bpy);
+      if (bcnt) {
+        bx = bsx / static_cast<float>(bcnt);
+        by = bsy / static_cast<float>(bcnt);
+        ball_any = true;
+      }
       if (cnt) {
-        col |= 1u << i;
-        nx[i] = sx / static_cast<float>(cnt);
-        ny[i] = sy / static_cast<float>(cnt);
+        pos.x = sx / static_cast<float>(cnt);
+        pos.y = sy / static_cast<float>(cnt);
+      }
+      if (!__any_sync(full, col)) break;
+    }
+    const unsigned cm = __ballot_sync(full, collided), tm = __ballot_sync(full, ballhit);
+    if (collided) {  // (active lanes only)
+      S.xy[lane][ts] = pos;
+      float4* pa = g.pa + (src - lane) + static_cast<size_t>(lane) * g.row;
+      const float4 a = *pa;
+      const float vx = a.z * -0.1f, vy = a.w * -0.1f;
+      *pa = make_float4(pos.x, pos.y, vx, vy);
+      if (obs_rows && report) {
+        float* o = obs_rows + (env - lane + src) * kFgObsDim + 4 + 5 * lane;
+        o[0] = pos.x * static_cast<float>(1.0 / 52.5);
+        o[1] = pos.y * static_cast<float>(1.0 / 34.0);
+        o[2] = vx;
+        o[3] = vy;
       }
     }
-    collided |= col;
-    ballhit |= bc;
-    ball_moved = bc != 0u;
-    if (bc) {
-      const float bcnt = static_cast<float>(__popc(bc));
-      m.bx = tree_sum32(bpx, bc) / bcnt;
-      m.by = tree_sum32(bpy, bc) / bcnt;
-      ball_any = true;
-    }
-#pragma unroll 1
-    for (uint32_t rest = col; rest; rest &= rest - 1u) {
-      const int i = __ffs(rest) - 1;
-      S.xy[i][t] = make_float2(nx[i], ny[i]);
-    }
-    moved |= col;
-    cand = col;
-    if (!col) break;
-  }
-  m.sep = 0.0f;  // players were pushed around: measure again next cycle
-  if (ball_any) {
-    m.bvx *= -0.1f;
-    m.bvy *= -0.1f;
-  }
-#pragma unroll 1
-  for (uint32_t rest = moved; rest; rest &= rest - 1u) {  // (moved == collided: a player with a proposal collided)
-    const int i = __ffs(rest) - 1;
-    float4* pa = g.pa + static_cast<size_t>(i) * g.row;
-    const float4 a = *pa;
-    const float2 xy = S.xy[i][t];
-    *pa = make_float4(xy.x, xy.y, a.z * -0.1f, a.w * -0.1f);
-  }
-  ball_collided = ball_any;
-  return make_uint2(collided, ballhit);
-}
-
-// the players of the close pairs (distance below r2), as a mask: second pass of the pair scan, only when its minimum says so
-__device__ __noinline__ uint32_t fg_close_pairs(const FgShared& S, int t, int np, float r2) {
-  uint32_t mask = 0;
-#pragma unroll 1
-  for (int i = 0; i + 1 < np; ++i) {
-    const float2 pi = S.xy[i][t];
-#pragma unroll 1
-    for (int j = i + 1; j < np; ++j) {
-      const float2 pj = S.xy[j][t];
-      const float ex = pi.x - pj.x, ey = pi.y - pj.y;
-      if (ex * ex + ey * ey < r2 * r2) mask |= (1u << i) | (1u << j);
+    if (lane == src) {
+      m.bx = bx;
+      m.by = by;
+      if (ball_any) {
+        m.bvx *= -0.1f;
+        m.bvy *= -0.1f;
+      }
+      m.sep = 0.0f;  // players were pushed around: measure again next cycle
+      collided_mask = cm;
+      touch = tm;
+      ball_collided = ball_any;
     }
   }
-  return mask;
 }
 
 // Offside marks (OffsideRef), taken at the moment of a pass by ONE team in PlayOn: the passer's team-mates that are, in
@@ -507,17 +513,28 @@ __device__ __forceinline__ void fg_write_obs(float* __restrict__ dst, int64_t en
 }
 
 // One cycle of the match.  Commands: float4 {cmd, a, b, c} of player j at act[j].  Returns done.
+// `obs_row` != nullptr (last cycle of a launch, 11 v 11): the player loop writes the players' part of the observation
+// row as it goes (the values are in registers then), and whatever moves a player afterwards patches its entry;
+// obs_dirty is raised where the whole row has to be written again (kick-off).
 template <class SP>
 __device__ __forceinline__ bool fg_cycle(FgShared& S, const int t, const FgPlanes& g, Match& m, const KernelParams& P, SP& sp,
-                                         const unsigned full, uint64_t gid, int np, int half_time, const float4* __restrict__ act,
-                                         float& reward, int& result, uint32_t& collided_mask, uint32_t& kicked_mask,
-                                         bool& ball_collided) {
+                                         uint64_t gid, int np, int half_time, const float4* __restrict__ act, float* obs_row,
+                                         const bool valid, bool& obs_dirty, float& reward, int& result, uint32_t& collided_mask,
+                                         uint32_t& kicked_mask, bool& ball_collided) {
+  const unsigned full = 0xffffffffu;
   const int pps = np >> 1;
   const unsigned left_set = (1u << pps) - 1u;
   bool dead = m.mode != S2D_PM_PLAY_ON;
   const bool dead_at_start = dead;
   m.step_number += 1;
   const NoiseCtx nz{P.seed, gid, m.cycle};
+  {  // the match's command row (np x 16 bytes, 32-byte aligned): ask the L2 for its lines now, the loop loads them later
+    const char* row = reinterpret_cast<const char*>(act);
+    const int bytes = np * 16;
+#pragma unroll 1
+    for (int o = 0; o < bytes; o += 128) prefetch_l2(row + o);
+    prefetch_l2(row + bytes - 32);
+  }
 
   // ---- every player: command, move, stamina (the private part of the player streams through registers) ----
   uint32_t kick_mask = 0;
@@ -528,21 +545,24 @@ __device__ __forceinline__ bool fg_cycle(FgShared& S, const int t, const FgPlane
     float4* gpb = g.pb;
     float* gpc = g.pc;
     // software pipeline: player j + 1's plane entries are in flight while player j computes; the commands come two
-    // players (one 32-byte sector) at a time
-    float4 n_a = ld_stream(gpa), n_b = ld_stream(gpb), cmd0, cmd1, n_cmd0, n_cmd1;
+    // players (one 32-byte sector) at a time, so the loop walks the players in pairs (np is even)
+    float4 n_a = ld_stream(gpa), n_b = ld_stream(gpb), n_cmd0, n_cmd1;
     float n_c = ld_stream(gpc);
     ld_nc_256(act, n_cmd0, n_cmd1);
-#pragma unroll 1
-    for (int j = 0; j < np; ++j) {
+    constexpr int kAhead = S2D_FG_AHEAD;  // rows the L2 is asked for ahead of the register prefetch (no registers held)
+#pragma unroll
+    for (int a = 1; a <= kAhead; ++a) {
+      if (a < np) {
+        prefetch_l2(gpa + a * g.row);
+        prefetch_l2(gpb + a * g.row);
+        prefetch_l2(gpc + a * g.rowc);
+      }
+    }
+
+    auto one_player = [&](const int j, const float4 a) {
       if constexpr (SP::kHetero) sp.row = sp.table + PT_ROW * P.type_of[j];
       const float4 pa = n_a, b = n_b;
       const float cap = n_c;
-      if ((j & 1) == 0) {  // (np is even)
-        cmd0 = n_cmd0;
-        cmd1 = n_cmd1;
-        if (j + 2 < np) ld_nc_256(act + j + 2, n_cmd0, n_cmd1);
-      }
-      const float4 a = (j & 1) ? cmd1 : cmd0;
       float4* const wpa = gpa;
       float4* const wpb = gpb;
       float* const wpc = gpc;
@@ -553,6 +573,11 @@ __device__ __forceinline__ bool fg_cycle(FgShared& S, const int t, const FgPlane
         n_a = ld_stream(gpa);
         n_b = ld_stream(gpb);
         n_c = ld_stream(gpc);
+      }
+      if (kAhead > 0 && j + 1 + kAhead < np) {
+        prefetch_l2(gpa + kAhead * g.row);
+        prefetch_l2(gpb + kAhead * g.row);
+        prefetch_l2(gpc + kAhead * g.rowc);
       }
       const bool left = j < pps;
       const int my_side = left ? S2D_SIDE_LEFT : S2D_SIDE_RIGHT;
@@ -579,6 +604,34 @@ __device__ __forceinline__ bool fg_cycle(FgShared& S, const int t, const FgPlane
       st_stream(wpa, make_float4(p.px, p.py, p.vx, p.vy));
       st_stream(wpb, make_float4(p.body, p.stamina, p.effort, p.recovery));
       st_stream(wpc, p.capacity);
+      if (obs_row) {  // (uniform) four players = 20 floats = five float4 of the row, starting at float4 1 + 5 (j / 4)
+        const int q = j & 3;
+        float(*stg)[kFgBlock] = S.obs + 5 * q;
+        stg[0][t] = p.px * static_cast<float>(1.0 / 52.5);
+        stg[1][t] = p.py * static_cast<float>(1.0 / 34.0);
+        stg[2][t] = p.vx;
+        stg[3][t] = p.vy;
+        stg[4][t] = p.body * static_cast<float>(1.0 / 180.0);
+        if (valid && (q == 3 || j == np - 1)) {
+          float4* o = reinterpret_cast<float4*>(obs_row) + 1 + 5 * (j >> 2);
+          st_stream(o, make_float4(S.obs[0][t], S.obs[1][t], S.obs[2][t], S.obs[3][t]));
+          st_stream(o + 1, make_float4(S.obs[4][t], S.obs[5][t], S.obs[6][t], S.obs[7][t]));
+          if (q == 3) {
+            st_stream(o + 2, make_float4(S.obs[8][t], S.obs[9][t], S.obs[10][t], S.obs[11][t]));
+            st_stream(o + 3, make_float4(S.obs[12][t], S.obs[13][t], S.obs[14][t], S.obs[15][t]));
+            st_stream(o + 4, make_float4(S.obs[16][t], S.obs[17][t], S.obs[18][t], S.obs[19][t]));
+          } else {  // players 20 and 21: floats 104..113; 114..119 are the referee's, written at the end of the launch
+            reinterpret_cast<float2*>(o + 2)[0] = make_float2(S.obs[8][t], S.obs[9][t]);
+          }
+        }
+      }
+    };
+#pragma unroll 1
+    for (int j = 0; j < np; j += 2) {
+      const float4 c0 = n_cmd0, c1 = n_cmd1;
+      if (j + 2 < np) ld_nc_256(act + j + 2, n_cmd0, n_cmd1);
+      one_player(j, c0);
+      one_player(j + 1, c1);
     }
   }
 
@@ -638,6 +691,13 @@ __device__ __forceinline__ bool fg_cycle(FgShared& S, const int t, const FgPlane
       cleared2 = fmaxf(cleared2, sx * sx + sy * sy);
       S.xy[j][t] = make_float2(nx, ny);
       g.pa[static_cast<size_t>(j) * g.row] = make_float4(nx, ny, 0.0f, 0.0f);
+      if (obs_row && valid) {
+        float* o = obs_row + 4 + 5 * j;
+        o[0] = nx * static_cast<float>(1.0 / 52.5);
+        o[1] = ny * static_cast<float>(1.0 / 34.0);
+        o[2] = 0.0f;
+        o[3] = 0.0f;
+      }
     }
     if (!dead && c2 < r * r) ball_mask |= 1u << j;
   }
@@ -654,29 +714,30 @@ __device__ __forceinline__ bool fg_cycle(FgShared& S, const int t, const FgPlane
     asm("sqrt.approx.f32 %0, %1;" : "=f"(cleared) : "f"(cleared2));
     m.sep -= 2.002f * (moved + cleared) + 1.0e-6f;
   }
-  uint32_t close_mask = 0;
+  bool pairs_close = false;
   if (__any_sync(full, m.sep < r2)) {
     float m2 = 3.0e38f;
 #pragma unroll 1
     for (int i = 0; i + 1 < np; ++i) {
       const float2 pi = S.xy[i][t];
-#pragma unroll 1
+#pragma unroll 4
       for (int j = i + 1; j < np; ++j) {
         const float2 pj = S.xy[j][t];
         const float ex = pi.x - pj.x, ey = pi.y - pj.y;
         m2 = fminf(m2, ex * ex + ey * ey);
       }
     }
-    if (m2 < r2 * r2) close_mask = fg_close_pairs(S, t, np, r2);
+    pairs_close = m2 < r2 * r2;
     m.sep = sqrtf(m2) * 0.999f;
   }
   collided_mask = 0;
   ball_collided = false;
   uint32_t touch = 0;
-  if (close_mask | ball_mask) {
-    const uint2 hit = fg_resolve_collisions(S, t, g, m, np, dead, r, r2, close_mask | ball_mask, ball_collided);
-    collided_mask = hit.x;
-    touch = hit.y;
+  {
+    const unsigned need = __ballot_sync(full, pairs_close || ball_mask != 0u);
+    if (need)
+      fg_resolve_collisions(S, t, g, m, np, need, dead, r, r2, obs_row ? P.obs : nullptr,
+                            static_cast<int64_t>(blockIdx.x) * kFgBlock + t, valid, collided_mask, touch, ball_collided);
   }
   {
     const bool hit_l = (touch & left_set) != 0, hit_r = (touch & ~left_set) != 0;
@@ -770,6 +831,7 @@ __device__ __forceinline__ bool fg_cycle(FgShared& S, const int t, const FgPlane
   }
   if (kick_off) {
     m.sep = 0.0f;
+    obs_dirty = true;
     fg_kick_off_formation(S, t, g, P, gid, m.episode, np, m.score_l + m.score_r);
     m.bx = m.by = m.bvx = m.bvy = 0.0f;
   }
@@ -836,64 +898,66 @@ __global__ void __launch_bounds__(kFgBlock, S2D_FG_MIN_BLOCKS) fullgame_step_ker
   __shared__ FgShared S;
   fg_bind_player_types(sp, P);
   const int t = threadIdx.x;
+  // Every thread owns a column of the state (rows are padded to the block size), so warps are whole: the columns past
+  // num_envs are scratch matches - they run the commands of the last real match and report nothing.
   const int64_t env = static_cast<int64_t>(blockIdx.x) * kFgBlock + t;
-  if (env >= P.num_envs) return;
-  const unsigned full = __activemask();  // the lanes of this warp that hold a match (ragged last warp)
+  const bool valid = env < P.num_envs;
+  const int64_t env_in = valid ? env : P.num_envs - 1;
   const FgLayout L{P.num_envs, np};
   const FgPlanes g(P, L, env);
   const uint64_t gid = static_cast<uint64_t>(P.env_id_offset + env);
 
-  // Ask the L2 for everything the block will read, with a handful of instructions and no registers: thread j < np its
-  // player row of the three planes (64 consecutive matches: 1 KB / 1 KB / 256 B), one thread the block's commands (K = 1:
-  // 22 KB in one piece).  The loads in the player loop then wait for the L2, not for DRAM.
-  {
-    const int64_t first = static_cast<int64_t>(blockIdx.x) * kFgBlock;
-    const int64_t left = P.num_envs - first;
-    const uint32_t cols = left < kFgBlock ? static_cast<uint32_t>(left) & ~3u : kFgBlock;  // 16-byte granules
-    if (t < np && cols) {
-      prefetch_l2_bulk(g.pa + (static_cast<size_t>(t) * g.row - t), cols * 16u);
-      prefetch_l2_bulk(g.pb + (static_cast<size_t>(t) * g.row - t), cols * 16u);
-      prefetch_l2_bulk(g.pc + (static_cast<size_t>(t) * g.rowc - t), cols * 4u);
-    }
-    if (t == 32 && K == 1 && cols)
-      prefetch_l2_bulk(static_cast<const float4*>(P.actions) + first * np, cols * static_cast<uint32_t>(np) * 16u);
-  }
   Match m;
   fg_load(P, L, env, m);
   uint32_t collided_mask = 0, kicked_mask = 0;
-  bool ball_collided = false;
+  bool ball_collided = false, obs_dirty = false;
   float reward_sum = 0.0f;
   uint32_t any_done = 0, last_result = 0;
-  const float4* act = static_cast<const float4*>(P.actions) + (env * K) * np;
+  const float4* act = static_cast<const float4*>(P.actions) + (env_in * K) * np;
+  float* const my_obs = P.obs + env_in * kFgObsDim;
 #pragma unroll 1
   for (int k = K; k > 0; --k, act += np) {
     float rw;
     int rs;
-    const bool done = fg_cycle(S, t, g, m, P, sp, full, gid, np, half_time, act, rw, rs, collided_mask, kicked_mask, ball_collided);
+    // in the last cycle of an 11 v 11 launch the player loop writes the observation row itself
+    float* const obs_row = (NP == kFgMaxPlayers && k == 1) ? my_obs : nullptr;
+    const bool done = fg_cycle(S, t, g, m, P, sp, gid, np, half_time, act, obs_row, valid, obs_dirty, rw, rs, collided_mask,
+                               kicked_mask, ball_collided);
     reward_sum += rw;
     m.ep_return += rw;
     if (done) {
       any_done = 1;
       last_result = static_cast<uint32_t>(rs);
-      if (!m.done_flag) {  // (a finished match stepped on with auto_reset off is tallied once)
+      if (!m.done_flag && valid) {  // (a finished match stepped on with auto_reset off is tallied once)
         unsigned long long* slot = P.stats + static_cast<size_t>(env % kStatSlots) * kStatWords;
         atomicAdd(slot + ST_EPISODES, 1ull);
         atomicAdd(slot + (rs == 1 ? ST_GOALS : rs == 2 ? ST_OUTS : ST_TIMEOUTS), 1ull);
         atomicAdd(slot + ST_EP_STEPS, static_cast<unsigned long long>(m.step_number));
         atomicAdd(reinterpret_cast<double*>(slot + ST_RETURN), static_cast<double>(m.ep_return));
       }
-      if (P.terminal_obs) fg_write_obs(P.terminal_obs, env, g, m, np, half_time);
+      if (P.terminal_obs && valid) fg_write_obs(P.terminal_obs, env, g, m, np, half_time);
       if (P.auto_reset) {
         fg_reset(S, t, g, m, P, sp, gid, np);
         collided_mask = kicked_mask = 0;
         ball_collided = false;
+        obs_dirty = true;
       } else {
         m.done_flag = true;
       }
     }
   }
   fg_store(P, L, env, m, collided_mask, kicked_mask, ball_collided);
-  fg_write_obs(P.obs, env, g, m, np, half_time);
+  if (!valid) return;
+  if (NP != kFgMaxPlayers || obs_dirty) {
+    fg_write_obs(P.obs, env, g, m, np, half_time);  // the whole row from the planes
+  } else {  // the players' part is written: the ball and the referee's six values
+    float4* row = reinterpret_cast<float4*>(my_obs);
+    st_stream(row, make_float4(m.bx * static_cast<float>(1.0 / 52.5), m.by * static_cast<float>(1.0 / 34.0),
+                               m.bvx * static_cast<float>(1.0 / 3.0), m.bvy * static_cast<float>(1.0 / 3.0)));
+    reinterpret_cast<float2*>(my_obs)[57] = make_float2(static_cast<float>(m.mode), static_cast<float>(m.side));
+    st_stream(row + 29, make_float4(static_cast<float>(m.score_l), static_cast<float>(m.score_r),
+                                    static_cast<float>(m.step_number) / static_cast<float>(2 * half_time), 0.0f));
+  }
   P.reward[env] = reward_sum;
   P.done[env] = static_cast<uint8_t>(any_done);
   P.result[env] = static_cast<uint8_t>(last_result);
@@ -909,14 +973,15 @@ __global__ void __launch_bounds__(kFgBlock) fullgame_reset_kernel(const __grid_c
   fg_bind_player_types(sp, P);
   const int t = threadIdx.x;
   const int64_t env = static_cast<int64_t>(blockIdx.x) * kFgBlock + t;
-  if (env >= P.num_envs) return;
-  if (mask && !mask[env]) return;
+  const bool valid = env < P.num_envs;
+  if (valid && mask && !mask[env]) return;  // (the scratch columns past num_envs are reset with every call)
   const FgLayout L{P.num_envs, np};
   const FgPlanes g(P, L, env);
   Match m;
   fg_load(P, L, env, m);
   fg_reset(S, t, g, m, P, sp, static_cast<uint64_t>(P.env_id_offset + env), np);
   fg_store(P, L, env, m, 0u, 0u, false);
+  if (!valid) return;
   fg_write_obs(P.obs, env, g, m, np, half_time);
   P.reward[env] = 0.0f;
   P.done[env] = 0;

@@ -181,10 +181,8 @@ __device__ __forceinline__ void st_stream_256(float4* p, const float4& a, const 
                "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w)
                : "memory");
 }
-// asks the L2 to fetch `bytes` (a multiple of 16) starting at the 16-byte aligned p: one instruction, no registers
-__device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
-}
+// asks the L2 for the line of p: one instruction per lane, no registers held while the data travels
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ float ld_stream(const float* p) {
   float v;
   asm volatile("ld.global.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
@@ -205,10 +203,8 @@ __device__ __forceinline__ void st_stream_256(float4* p, const float4& a, const 
                "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w)
                : "memory");
 }
-// asks the L2 to fetch `bytes` (a multiple of 16) starting at the 16-byte aligned p: one instruction, no registers
-__device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
-}
+// asks the L2 for the line of p: one instruction per lane, no registers held while the data travels
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ float ld_stream(const float* p) { return *p; }
 __device__ __forceinline__ void st_stream(float* p, float v) { *p = v; }
 __device__ __forceinline__ float4 ld_stream(const float4* p) { return *p; }

@@ -602,17 +602,17 @@ class Soccer2DVecEnv(_VecEnvBase):
         of N consecutive matches - see csrc/s2d_fullgame.cuh FgLayout)."""
         assert self.scenario == "fullgame"
         n, p = self.num_envs, self.num_players
+        nr = (n + 63) // 64 * 64  # rows are padded to the kernel's block size (scratch matches past num_envs)
         off = 0
         out = {}
         for name in ("pa", "pb"):
-            out[name] = self.state[off:off + n * p * 16].view(torch.float32).view(p, n, 4).permute(1, 0, 2)
-            off += n * p * 16
-        nr = (n + 3) // 4 * 4
+            out[name] = self.state[off:off + nr * p * 16].view(torch.float32).view(p, nr, 4)[:, :n].permute(1, 0, 2)
+            off += nr * p * 16
         out["pc"] = self.state[off:off + nr * p * 4].view(torch.float32).view(p, nr)[:, :n].t()
         off += nr * p * 4
         for name, dt in (("ball", torch.float32), ("ef", torch.float32), ("ei", torch.int32), ("ej", torch.int32)):
-            out[name] = self.state[off:off + n * 16].view(dt).view(n, 4)
-            off += n * 16
+            out[name] = self.state[off:off + nr * 16].view(dt).view(nr, 4)[:n]
+            off += nr * 16
         assert off == self.state.numel()
         return out
 

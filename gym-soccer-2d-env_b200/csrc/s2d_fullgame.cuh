@@ -15,7 +15,7 @@
 //
 // Sums over the players of a match (kick accelerations on the ball, collision proposals for the ball) are part of the
 // fp32 spec: they are added as a 32-leaf xor-butterfly (leaf = player index, absent players and non-contributors 0.0),
-// see tree_sum32 - the order the oracle uses.
+// see tree_sum32 - the order include/soccer2d.h fixes for those sums.
 #pragma once
 #include "s2d_scenarios.cuh"
 

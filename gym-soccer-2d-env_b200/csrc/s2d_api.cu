@@ -153,6 +153,10 @@ static bool config_ok(const S2DConfig* c, char* why, size_t n) {
     return false;
   }
   if (c->max_steps < 0) { snprintf(why, n, "max_steps must be >= 0"); return false; }
+  if (c->collision_model != S2D_COLLISION_MIDPOINT && c->collision_model != S2D_COLLISION_BACKTRACE) {
+    snprintf(why, n, "collision_model %d does not exist", c->collision_model);
+    return false;
+  }
   return true;
 }
 
@@ -200,7 +204,7 @@ int s2d_create(const S2DConfig* cfg, S2DHandle* out) {
   KernelParams& kp = h->kp;
   float4 table[256];
   make_kernel_params(*cfg, kp, table);
-  h->default_sp = is_default_server_param(cfg->sp);
+  h->default_sp = is_default_server_param(cfg->sp) && cfg->collision_model == S2D_COLLISION_MIDPOINT;
   cudaError_t e = cudaMalloc(&h->d_table, sizeof(table));
   if (e == cudaSuccess) e = cudaMemcpy(h->d_table, table, sizeof(table), cudaMemcpyHostToDevice);
   if (e != cudaSuccess) {

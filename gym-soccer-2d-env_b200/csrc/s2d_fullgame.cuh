@@ -318,8 +318,8 @@ __device__ __forceinline__ float butterfly_sum(float v) {
 // touched the ball) and the ball; the player lanes write positions and velocities back (shared memory, plane PA and,
 // when `obs_rows` (the observation tensor) is set - last cycle of a launch -, the row the player loop has already written).
 __device__ __noinline__ void fg_resolve_collisions(FgShared& S, const int t, const FgPlanes g, Match& m, const int np, unsigned need,
-                                                   const bool dead, const float r, const float r2, float* obs_rows, const int64_t env,
-                                                   const bool valid,
+                                                   const bool dead, const float r, const float r2, const int model, float* obs_rows,
+                                                   const int64_t env, const bool valid,
                                                    uint32_t& collided_mask, uint32_t& touch, bool& ball_collided) {
   const unsigned full = 0xffffffffu;
   const int lane = t & 31;
@@ -335,6 +335,12 @@ __device__ __noinline__ void fg_resolve_collisions(FgShared& S, const int t, con
     const bool ball_fixed = __shfl_sync(full, static_cast<int>(dead), src) != 0;
     const bool report = __shfl_sync(full, static_cast<int>(valid), src) != 0;
     float2 pos = active ? S.xy[lane][ts] : make_float2(0.0f, 0.0f);
+    float4* const my_pa = g.pa + (src - lane) + static_cast<size_t>(active ? lane : 0) * g.row;  // (player lane, match src)
+    float2 vel = make_float2(0.0f, 0.0f);  // BACKTRACE: every object backs up along its own velocity
+    if (model == S2D_COLLISION_BACKTRACE && active) {
+      const float4 a = *my_pa;
+      vel = make_float2(a.z, a.w);
+    }
     bool collided = false, ballhit = false, ball_any = false;
 #pragma unroll 1
     for (int round = 0; round < 10; ++round) {
@@ -354,26 +360,34 @@ __device__ __noinline__ void fg_resolve_collisions(FgShared& S, const int t, con
             const float2 b = ball_back_trace(pos.x, pos.y, bx, by, bvx, bvy, r + kCollideEps);
             bpx = b.x;
             bpy = b.y;
-            sx += pos.x;
-            sy += pos.y;
+            float2 own = pos;
+            if (model == S2D_COLLISION_BACKTRACE) own = ball_back_trace(bx, by, pos.x, pos.y, vel.x, vel.y, r + kCollideEps, -1.0f);
+            sx += own.x;
+            sy += own.y;
             cnt += 1;
           }
         } else {
           const float ex = pos.x - xj, ey = pos.y - yj;
           if (ex * ex + ey * ey < r2 * r2) {
             col = collided = true;
-            const float mx = (pos.x + xj) / 2.0f, my = (pos.y + yj) / 2.0f;
-            const float d = hypot2(ex, ey);
-            float ux, uy;
-            if (d < 1.0e-10f) {
-              ux = lane < j ? 1.0f : -1.0f;
-              uy = 0.0f;
+            if (model == S2D_COLLISION_BACKTRACE) {
+              const float2 own = ball_back_trace(xj, yj, pos.x, pos.y, vel.x, vel.y, r2 + kCollideEps, lane < j ? 1.0f : -1.0f);
+              sx += own.x;
+              sy += own.y;
             } else {
-              ux = ex / d;
-              uy = ey / d;
+              const float mx = (pos.x + xj) / 2.0f, my = (pos.y + yj) / 2.0f;
+              const float d = hypot2(ex, ey);
+              float ux, uy;
+              if (d < 1.0e-10f) {
+                ux = lane < j ? 1.0f : -1.0f;
+                uy = 0.0f;
+              } else {
+                ux = ex / d;
+                uy = ey / d;
+              }
+              sx += mx + ux * h;
+              sy += my + uy * h;
             }
-            sx += mx + ux * h;
-            sy += my + uy * h;
             cnt += 1;
           }
         }
@@ -394,10 +408,9 @@ __device__ __noinline__ void fg_resolve_collisions(FgShared& S, const int t, con
     const unsigned cm = __ballot_sync(full, collided), tm = __ballot_sync(full, ballhit);
     if (collided) {  // (active lanes only)
       S.xy[lane][ts] = pos;
-      float4* pa = g.pa + (src - lane) + static_cast<size_t>(lane) * g.row;
-      const float4 a = *pa;
+      const float4 a = *my_pa;
       const float vx = a.z * -0.1f, vy = a.w * -0.1f;
-      *pa = make_float4(pos.x, pos.y, vx, vy);
+      *my_pa = make_float4(pos.x, pos.y, vx, vy);
       if (obs_rows && report) {
         float* o = obs_rows + (env - lane + src) * kFgObsDim + 4 + 5 * lane;
         o[0] = pos.x * static_cast<float>(1.0 / 52.5);
@@ -736,7 +749,7 @@ __device__ __forceinline__ bool fg_cycle(FgShared& S, const int t, const FgPlane
   {
     const unsigned need = __ballot_sync(full, pairs_close || ball_mask != 0u);
     if (need)
-      fg_resolve_collisions(S, t, g, m, np, need, dead, r, r2, obs_row ? P.obs : nullptr,
+      fg_resolve_collisions(S, t, g, m, np, need, dead, r, r2, sp.collision_model(), obs_row ? P.obs : nullptr,
                             static_cast<int64_t>(blockIdx.x) * kFgBlock + t, valid, collided_mask, touch, ball_collided);
   }
   {

@@ -343,9 +343,12 @@ __device__ __forceinline__ void move_object(float& x, float& y, float& vx, float
 
 constexpr float kCollideEps = 1.0e-6f;
 
-// Where the ball goes when it overlaps a player: back along its own velocity until the two are `rr` apart; if it is
-// not moving (or that line misses), straight out along the line of centres.
-__device__ __forceinline__ float2 ball_back_trace(float px, float py, float bx, float by, float bvx, float bvy, float rr) {
+// Where an object at (bx, by) moving with (bvx, bvy) goes when it overlaps an object at (px, py): back along its own
+// velocity until the two are `rr` apart; if it is not moving (or that line misses), straight out along the line of
+// centres; coincident centres separate along x (`side` = +1 or -1).  The ball of a ball-player contact in both collision
+// models, and every colliding object in the BACKTRACE model (include/soccer2d.h).
+__device__ __forceinline__ float2 ball_back_trace(float px, float py, float bx, float by, float bvx, float bvy, float rr,
+                                                  float side = 1.0f) {
   const float dx = bx - px, dy = by - py;
   const float v = hypot2(bvx, bvy);
   if (v > 1.0e-10f) {
@@ -358,12 +361,12 @@ __device__ __forceinline__ float2 ball_back_trace(float px, float py, float bx, 
     }
   }
   const float d = hypot2(dx, dy);
-  if (d < 1.0e-10f) return make_float2(px + rr, py);
+  if (d < 1.0e-10f) return make_float2(px + side * rr, py);
   return make_float2(px + dx / d * rr, py + dy / d * rr);
 }
 
-// Ball overlapping the single player (rare): up to ten relaxation rounds as in the server; the player keeps its
-// place (the average of its proposals is its own position).  The caller applies vel *= -0.1 to both.
+// Ball overlapping the single player (rare): up to ten relaxation rounds as in the server.  MIDPOINT model: the player
+// keeps its place (the average of its proposals is its own position).  The caller applies vel *= -0.1 to both.
 __device__ __noinline__ float2 resolve_ball_player_overlap(float px, float py, float bx, float by, float bvx, float bvy,
                                                            float r) {
   const float r2 = r * r;
@@ -378,17 +381,43 @@ __device__ __noinline__ float2 resolve_ball_player_overlap(float px, float py, f
   }
   return make_float2(bx, by);
 }
+// BACKTRACE model: the player backs up along its own velocity as well.  Returns {ball x, y, player x, y}.
+__device__ __noinline__ float4 resolve_ball_player_overlap_backtrace(float px, float py, float vx, float vy, float bx, float by,
+                                                                     float bvx, float bvy, float r) {
+  const float r2 = r * r;
+  const float rr = r + kCollideEps;
+#pragma unroll 1
+  for (int round = 0; round < 10; ++round) {
+    const float dx = bx - px, dy = by - py;
+    if (!(dx * dx + dy * dy < r2)) break;
+    const float2 b = ball_back_trace(px, py, bx, by, bvx, bvy, rr);
+    const float2 q = ball_back_trace(bx, by, px, py, vx, vy, rr, -1.0f);
+    px = q.x;
+    py = q.y;
+    bx = b.x;
+    by = b.y;
+  }
+  return make_float4(bx, by, px, py);
+}
 
 template <class SP>
 // (dx, dy) = ball - player and d2 = dx*dx + dy*dy come from the caller, which re-uses them for the reward when
-// nothing collided (the common case).  Returns true when the ball was moved.
+// nothing collided (the common case).  Returns true when something was moved.
 __device__ __forceinline__ bool collide_ball_player(Episode& e, float d2, const SP& sp) {
   uint32_t hit = 0;
   if (d2 < sp.collide_r2()) {
     hit = S2D_FLAG_BALL_COLLIDED | S2D_FLAG_PLAYER_COLLIDED;
-    const float2 b = resolve_ball_player_overlap(e.px, e.py, e.bx, e.by, e.bvx, e.bvy, sp.collide_r());
-    e.bx = b.x;
-    e.by = b.y;
+    if (sp.collision_model() == S2D_COLLISION_BACKTRACE) {
+      const float4 b = resolve_ball_player_overlap_backtrace(e.px, e.py, e.vx, e.vy, e.bx, e.by, e.bvx, e.bvy, sp.collide_r());
+      e.bx = b.x;
+      e.by = b.y;
+      e.px = b.z;
+      e.py = b.w;
+    } else {
+      const float2 b = resolve_ball_player_overlap(e.px, e.py, e.bx, e.by, e.bvx, e.bvy, sp.collide_r());
+      e.bx = b.x;
+      e.by = b.y;
+    }
     e.bvx *= -0.1f;
     e.bvy *= -0.1f;
     e.vx *= -0.1f;

@@ -68,6 +68,7 @@ struct RawSP {
 // float arithmetic (so device and host agree on every bit).
 struct CycleConsts {
   S2DServerParam sp;
+  int collision_model;  // S2D_COLLISION_* (set by make_kernel_params)
 #define Y(name, expr) float name;
   S2D_DERIVED_PARAMS(Y)
 #undef Y
@@ -76,6 +77,7 @@ struct CycleConsts {
 inline CycleConsts make_cycle_consts(const S2DServerParam& sp) {
   CycleConsts c;
   c.sp = sp;
+  c.collision_model = S2D_COLLISION_MIDPOINT;
   const RawSP p{sp};
 #define Y(name, expr) c.name = (expr);
   S2D_DERIVED_PARAMS(Y)
@@ -104,6 +106,7 @@ struct RuntimeSP {
   static constexpr bool kHetero = false;
   const CycleConsts& c;
   S2D_HD explicit RuntimeSP(const CycleConsts& c_) : c(c_) {}
+  S2D_HD int collision_model() const { return c.collision_model; }
 #define X(name, def) S2D_HD float name() const { return c.sp.name; }
   S2D_SERVER_PARAMS(X)
 #undef X
@@ -150,6 +153,7 @@ struct DefaultBase {
 #undef X
 };
 struct DefaultSP : DefaultBase {
+  S2D_HDC int collision_model() { return S2D_COLLISION_MIDPOINT; }  // (other models run the RuntimeSP kernels)
   static constexpr bool kNoise = false;
   static constexpr bool kHetero = false;
   S2D_HD explicit DefaultSP(const CycleConsts&) {}

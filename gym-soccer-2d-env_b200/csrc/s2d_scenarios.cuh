@@ -53,6 +53,7 @@ struct KernelParams {
 inline void make_kernel_params(const S2DConfig& cfg, KernelParams& kp, float4 table[256]) {
   memset(&kp, 0, sizeof(kp));
   kp.cc = make_cycle_consts(cfg.sp);
+  kp.cc.collision_model = cfg.collision_model;
   kp.num_envs = cfg.num_envs;
   kp.env_id_offset = cfg.env_id_offset;
   kp.seed = cfg.seed;

@@ -20,6 +20,8 @@ CMD_TURN_TO_POINT, CMD_TURN_TO_BALL, CMD_TURN_TO_ANGLE, CMD_KICK_ONE_STEP, CMD_S
 RESULT_NONE, RESULT_GOAL, RESULT_OUT, RESULT_TIMEOUT = 0, 1, 2, 3
 RESULT_NAMES = (None, "Goal", "Out", "Timeout")  # info['result'], reach_ball_env.py:126,140,145,150
 FLAG_BALL_COLLIDED, FLAG_PLAYER_COLLIDED, FLAG_KICKED, FLAG_DONE = 1, 2, 4, 8
+COLLISION_MIDPOINT, COLLISION_BACKTRACE = 0, 1
+COLLISION_MODELS = {"midpoint": COLLISION_MIDPOINT, "backtrace": COLLISION_BACKTRACE}
 
 _SP_FIELDS = (
     "pitch_half_length pitch_half_width goal_width goal_post_radius "
@@ -49,7 +51,7 @@ class Config(C.Structure):
         ("max_steps", C.c_int32), ("auto_reset", C.c_int32),
         ("change_ball_position", C.c_int32), ("change_ball_velocity", C.c_int32), ("noise", C.c_int32),
         ("players_per_side", C.c_int32), ("half_time_cycles", C.c_int32),
-        ("kick_actions", C.c_int32), ("reserved_i", C.c_int32 * 3),
+        ("kick_actions", C.c_int32), ("collision_model", C.c_int32), ("reserved_i", C.c_int32 * 2),
         ("min_distance_to_ball", C.c_float),
         ("ball_position_x", C.c_float), ("ball_position_y", C.c_float),
         ("ball_speed", C.c_float), ("ball_direction", C.c_float),

@@ -79,3 +79,34 @@ class RcgWriter:
 
     def __exit__(self, *exc):
         self.close()
+
+
+class RclWriter:
+    """The commands of a game as rcssserver's text log (`.rcl`) writes them: one line per player and cycle,
+    `<cycle>,<stopped>\tRecv <team>_<unum>: (dash 100 30)`.  Only what the server itself understands can appear in such
+    a log - dash / turn / kick (S2D_CMD_DASH / TURN / KICK); the proxy's body actions are lowered before they get here."""
+    NAMES = {1: "dash", 2: "turn", 3: "kick"}
+
+    def __init__(self, path: str, left: str = "left", right: str = "right"):
+        self.f = open(path, "w")
+        self.left, self.right = left, right
+
+    def write(self, cycle: int, commands, players_per_side: int) -> None:
+        """commands: [num_players][4] rows {cmd, a, b, c} given in `cycle` (left team first)"""
+        for j, c in enumerate(commands):
+            name = self.NAMES.get(int(c[0]))
+            if name is None:
+                continue
+            team, unum = (self.left, j + 1) if j < players_per_side else (self.right, j - players_per_side + 1)
+            args = f"{_f(c[1])}" if name == "turn" else f"{_f(c[1])} {_f(c[2])}"
+            self.f.write(f"{int(cycle)},0\tRecv {team}_{unum}: ({name} {args})\n")
+
+    def close(self) -> None:
+        if not self.f.closed:
+            self.f.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()

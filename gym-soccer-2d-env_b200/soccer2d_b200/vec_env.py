@@ -142,6 +142,8 @@ class Soccer2DVecEnv(_VecEnvBase):
     noise          rcssserver's player_rand / ball_rand / kick_rand noise from the counter-based RNG, keyed on
                    (seed, global env id, server cycle, agent): reproducible, independent of sharding and of
                    `substeps`.  Off by default (the mode in which runs are compared with the double-precision CPU truth)
+    collision_model  "midpoint" (default) or "backtrace": which reading of rcssserver's pair rule Stadium::collisions uses
+                   (include/soccer2d.h "Collision models"; the binary is not available offline, both are implemented)
     host_numa_node NUMA node for the pinned host staging blocks of step_host / submit_host (soccer2d_b200.numa: the node of
                    this rank's GPU keeps the copies off the inter-socket link); None = wherever the driver allocates
     host_ring      step_wait() hands out views of pinned host blocks, `host_ring` of them in rotation: the arrays (and the
@@ -160,7 +162,7 @@ class Soccer2DVecEnv(_VecEnvBase):
                  env_id_offset: int = 0, auto_reset: bool = True, terminal_obs: bool = False,
                  server_param: dict | None = None, use_command_action: bool = False, goto_dist_thr: float = 0.5,
                  noise: bool = False, host_mapped_io: bool = False, hetero_seed: int | None = None,
-                 host_numa_node: int | None = None, host_ring: int = 4, **kwargs):
+                 host_numa_node: int | None = None, host_ring: int = 4, collision_model: str = "midpoint", **kwargs):
         if scenario.lower() not in _SCENARIOS:
             raise ValueError(f"Environment {scenario} not found.")  # environment_factory.py:28
         self.scenario = scenario.lower()
@@ -210,6 +212,9 @@ class Soccer2DVecEnv(_VecEnvBase):
         cfg.kick_actions = int(self.kw.get("kick_actions", 0))
         cfg.goto_dist_thr = float(goto_dist_thr)
         cfg.noise = int(bool(noise))
+        if collision_model not in _abi.COLLISION_MODELS:
+            raise ValueError(f"collision_model must be one of {sorted(_abi.COLLISION_MODELS)}")
+        cfg.collision_model = _abi.COLLISION_MODELS[collision_model]
         cfg.max_steps = int(self.kw.get("max_steps", 200))
         cfg.auto_reset = int(self.auto_reset)
         cfg.change_ball_position = int(bool(self.kw.get("change_ball_position", True)))

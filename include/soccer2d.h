@@ -136,6 +136,23 @@ extern "C" {
 #define S2D_CMD_STOP_BALL 9     /*                                    Body_StopBall     (:753-754) */
 #define S2D_CMD_INTERCEPT 10    /*                                    Body_Intercept    (:742-745; save_recovery and face_point ignored) */
 
+/* Collision models (S2DConfig.collision_model).  rcssserver's Stadium::collisions repeats up to ten rounds in which every
+ * overlapping pair proposes new positions, every object moves to the average of its proposals, and what collided gets
+ * vel *= -0.1 at the end.  The binary is not available offline (SURVEY.md Appendix A.5 marks the pair rule with a
+ * warning sign), so both readings of the pair rule are implemented, bit-exact against the oracle:
+ *   MIDPOINT   (default; our reading of Stadium::calcCollPos / calcBallCollPos) player-player: both are placed
+ *              symmetrically about their midpoint, (size_i + size_j) / 2 + eps each (coincident centres separate along x,
+ *              lower index towards +x); ball-player: the ball is moved back along its own velocity until the two touch
+ *              (straight out along the line of centres if it is at rest or its line of motion misses), the player keeps
+ *              its place.
+ *   BACKTRACE  (the other reading, MPObject::collide backing each object up) EVERY colliding object is moved back along
+ *              its OWN velocity until it touches the other one, taken at its current place: both players of a pair, and
+ *              in a ball-player contact the player as well as the ball.  An object at rest, or whose line of motion
+ *              misses, is pushed straight out along the line of centres (coincident centres: along x, the lower index /
+ *              the ball towards +x).  eps = 1e-6 in both. */
+#define S2D_COLLISION_MIDPOINT 0
+#define S2D_COLLISION_BACKTRACE 1
+
 /* episode results: info['result'] of reach_ball_env.py:126,140,145,150 */
 #define S2D_RESULT_NONE 0
 #define S2D_RESULT_GOAL 1
@@ -196,7 +213,8 @@ typedef struct S2DConfig {
   int32_t players_per_side; /* FULLGAME: 1..11 */
   int32_t half_time_cycles; /* FULLGAME: cycles per half (rcssserver: 3000) */
   int32_t kick_actions;     /* SHOOT + S2D_ACT_DISCRETE: how many of the action_space_size actions are kicks */
-  int32_t reserved_i[3];
+  int32_t collision_model;  /* S2D_COLLISION_* (below); 0 = default */
+  int32_t reserved_i[2];
   float min_distance_to_ball; /* reach_ball_env.py:32 */
   float ball_position_x, ball_position_y, ball_speed, ball_direction; /* reach_ball_env.py:28-31 */
   float goto_dist_thr; /* Body_GoToPoint.distance_threshold for S2D_CMD_GOTO */

@@ -411,13 +411,19 @@ def obj_inc(o, accel_max: float, speed_max: float, decay: float) -> None:
 COLLIDE_EPS = 1.0e-6  # DECISION: upstream EPS is 1e-10 in double; 1e-6 is representable next to 0.385 in f32
 
 
-def collisions(ball: Ball, players: list, sp: ServerParam) -> None:
+COLLISION_MIDPOINT, COLLISION_BACKTRACE = 0, 1  # include/soccer2d.h "Collision models"
+
+
+def collisions(ball: Ball, players: list, sp: ServerParam, model: int = COLLISION_MIDPOINT) -> None:
     """Stadium::collisions (SURVEY A.5): <=10 relaxation rounds; every object moves to the AVERAGE of the
     positions proposed for it in a round; afterwards each object that collided gets vel *= -0.1 once.
     DECISIONS: ball-player: the ball is moved back along its own velocity to the touching distance and the
     player keeps its place; if the ball is (numerically) not moving, or the back-trace has no solution, the
     symmetric player-player rule is used.  Coincident centres separate along +x (noise off, so no random
-    direction)."""
+    direction).
+    model = COLLISION_BACKTRACE (the other reading of the pair rule; SURVEY A.5 marks it uncertain): EVERY colliding object
+    backs up along its own velocity until it touches the other one - both players of a pair, and the player of a
+    ball-player contact as well as the ball."""
     ball.collided = False
     for p in players:
         p.collided = False
@@ -439,8 +445,10 @@ def collisions(ball: Ball, players: list, sp: ServerParam) -> None:
                 bsx += nx
                 bsy += ny
                 bcnt += 1
-                acc[i][0] += pi.x
-                acc[i][1] += pi.y
+                qx, qy = (pi.x, pi.y) if model == COLLISION_MIDPOINT else \
+                    _trace_back(pi.x, pi.y, pi.vx, pi.vy, ball.x, ball.y, r + COLLIDE_EPS, -1.0)
+                acc[i][0] += qx
+                acc[i][1] += qy
                 acc[i][2] += 1
             for j in range(i + 1, n):
                 pj = players[j]
@@ -450,6 +458,14 @@ def collisions(ball: Ball, players: list, sp: ServerParam) -> None:
                     col = True
                     pi.collided = True
                     pj.collided = True
+                    if model == COLLISION_BACKTRACE:
+                        for a, o, side in ((i, j, 1.0), (j, i, -1.0)):
+                            pa, po = players[a], players[o]
+                            qx, qy = _trace_back(pa.x, pa.y, pa.vx, pa.vy, po.x, po.y, r2 + COLLIDE_EPS, side)
+                            acc[a][0] += qx
+                            acc[a][1] += qy
+                            acc[a][2] += 1
+                        continue
                     mx, my = (pi.x + pj.x) / 2.0, (pi.y + pj.y) / 2.0
                     d = hypot2(dx, dy)
                     if d < 1.0e-10:
@@ -479,24 +495,30 @@ def collisions(ball: Ball, players: list, sp: ServerParam) -> None:
             p.vy *= -0.1
 
 
-def _ball_back_trace(ball: Ball, p: Player, r: float):
-    """Point on the ball's incoming line (pos - t*vel_dir, t >= 0) at distance r from the player."""
-    # the velocity the ball arrived with (vel was already decayed by _inc; direction is what matters)
-    v = hypot2(ball.vx, ball.vy)
-    dx, dy = ball.x - p.x, ball.y - p.y
+def _trace_back(x, y, vx, vy, fx, fy, r: float, side: float = 1.0):
+    """Point on the incoming line of the object at (x, y) with velocity (vx, vy) - pos - t*vel_dir, t >= 0 - at distance
+    r from the object at (fx, fy); at rest or when the line misses: straight out along the line of centres; coincident
+    centres separate along x (side)."""
+    # the velocity the object arrived with (vel was already decayed by _inc; direction is what matters)
+    v = hypot2(vx, vy)
+    dx, dy = x - fx, y - fy
     if v > 1.0e-10:
-        ux, uy = ball.vx / v, ball.vy / v
-        # |d - t u|^2 = r^2  ->  t^2 - 2 t (d.u) + |d|^2 - r^2 = 0, larger root moves the ball back out
+        ux, uy = vx / v, vy / v
+        # |d - t u|^2 = r^2  ->  t^2 - 2 t (d.u) + |d|^2 - r^2 = 0, larger root moves the object back out
         du = dx * ux + dy * uy
         disc = du * du - (dx * dx + dy * dy - r * r)
         if disc >= 0.0:
             t = du + math.sqrt(disc)
             if t >= 0.0:
-                return ball.x - t * ux, ball.y - t * uy
+                return x - t * ux, y - t * uy
     d = hypot2(dx, dy)
     if d < 1.0e-10:
-        return p.x + r, p.y
-    return p.x + dx / d * r, p.y + dy / d * r
+        return fx + side * r, fy
+    return fx + dx / d * r, fy + dy / d * r
+
+
+def _ball_back_trace(ball: Ball, p: Player, r: float):
+    return _trace_back(ball.x, ball.y, ball.vx, ball.vy, p.x, p.y, r)
 
 
 def update_stamina(p: Player, sp: ServerParam) -> None:
@@ -548,6 +570,7 @@ class ReachBallConfig:
     use_turning: bool = False
     seed: int = 0
     sp: ServerParam = field(default_factory=ServerParam)
+    collision_model: int = 0  # COLLISION_MIDPOINT / COLLISION_BACKTRACE
 
     @property
     def action_mode(self) -> int:
@@ -680,7 +703,7 @@ class ReachBallOracle:
             cmd_turn(p, direction, sp)
         obj_inc(p, sp.player_accel_max, sp.player_speed_max, sp.player_decay)
         obj_inc(b, sp.ball_accel_max, sp.ball_speed_max, sp.ball_decay)
-        collisions(b, [p], sp)
+        collisions(b, [p], sp, getattr(self.cfg, "collision_model", COLLISION_MIDPOINT))
         update_stamina(p, sp)
         self.cycle += 1
 
@@ -735,6 +758,7 @@ class ShootConfig:
     sp: ServerParam = field(default_factory=ServerParam)
     # ReachBallOracle.sample_reset reads these
     min_distance_to_ball: float = 5.0
+    collision_model: int = 0  # COLLISION_MIDPOINT / COLLISION_BACKTRACE
 
 
 def check_shoot(cfg, mem_pb, mem_bg, step_number, bx, by, px, py, prev_bx, prev_by):
@@ -797,7 +821,7 @@ class ShootOracle(ReachBallOracle):
             cmd_kick(p, b, power, direction, sp)
         obj_inc(p, sp.player_accel_max, sp.player_speed_max, sp.player_decay)
         obj_inc(b, sp.ball_accel_max, sp.ball_speed_max, sp.ball_decay)
-        collisions(b, [p], sp)
+        collisions(b, [p], sp, getattr(self.cfg, "collision_model", COLLISION_MIDPOINT))
         update_stamina(p, sp)
         self.cycle += 1
 

@@ -53,7 +53,7 @@ extern "C" {
 void* emu_create(const S2DConfig* cfg) {
   Emu* h = new Emu();
   make_kernel_params(*cfg, h->kp, h->table);
-  h->default_sp = is_default_server_param(cfg->sp);
+  h->default_sp = is_default_server_param(cfg->sp) && cfg->collision_model == S2D_COLLISION_MIDPOINT;
   h->state.assign((size_t)cfg->num_envs * kStateBytesPerEnv, 0);
   h->kp.state = h->state.data();
   h->kp.action_table = h->table;

@@ -73,7 +73,7 @@ def decode(p, ball, a, goto_thr, sp):
     return O.CMD_NONE, 0.0, 0.0
 
 
-def cycle(m: Match, actions, sps, sp, seed: int, gid: int, goto_thr: float, half_time: int):
+def cycle(m: Match, actions, sps, sp, seed: int, gid: int, goto_thr: float, half_time: int, collision_model: int = 0):
     """one cycle; `actions` [np][4]; `sps[j]` = player j's ServerParam (its player type written over `sp`).
     Returns (reward, done, result)."""
     n, b = m.n, m.ball
@@ -133,7 +133,7 @@ def cycle(m: Match, actions, sps, sp, seed: int, gid: int, goto_thr: float, half
                 ux, uy = ((-1.0 if p.side == O.SIDE_LEFT else 1.0), 0.0) if c < 1.0e-6 else (cx / c, cy / c)
                 p.x, p.y, p.vx, p.vy = b.x + ux * FREE_KICK_DIST, b.y + uy * FREE_KICK_DIST, 0.0, 0.0
     # ---- collisions (a dead ball takes no part) ----
-    touched = collide(m, sp, dead)
+    touched = collide(m, sp, dead, collision_model)
     hit_l = any(t and p.side == O.SIDE_LEFT for t, p in zip(touched, m.players))
     hit_r = any(t and p.side == O.SIDE_RIGHT for t, p in zip(touched, m.players))
     if hit_l != hit_r:
@@ -210,7 +210,7 @@ def cycle(m: Match, actions, sps, sp, seed: int, gid: int, goto_thr: float, half
     return reward, done, result
 
 
-def collide(m: Match, sp, ball_fixed: bool):
+def collide(m: Match, sp, ball_fixed: bool, model: int = 0):
     """Stadium::collisions as the spec states it: up to 10 rounds; in a round every object collects the positions
     proposed for it and moves to their average; what collided gets vel *= -0.1 once.  Returns who touched the ball."""
     b, pl, n = m.ball, m.players, m.n
@@ -234,13 +234,21 @@ def collide(m: Match, sp, ball_fixed: bool):
                         col = b.collided = pi.collided = touched[i] = True
                         nx, ny = O._ball_back_trace(b, pi, r + O.COLLIDE_EPS)
                         bsx, bsy, bcnt = bsx + nx, bsy + ny, bcnt + 1
-                        prop[i][0] += pi.x
-                        prop[i][1] += pi.y
+                        qx, qy = (pi.x, pi.y) if model == 0 else \
+                            O._trace_back(pi.x, pi.y, pi.vx, pi.vy, b.x, b.y, r + O.COLLIDE_EPS, -1.0)
+                        prop[i][0] += qx
+                        prop[i][1] += qy
                         prop[i][2] += 1
                 else:
                     ex, ey = pi.x - pj.x, pi.y - pj.y
                     if ex * ex + ey * ey < r2 * r2:
                         col = pi.collided = True
+                        if model == 1:  # BACKTRACE: the player backs up along its own velocity
+                            qx, qy = O._trace_back(pi.x, pi.y, pi.vx, pi.vy, pj.x, pj.y, r2 + O.COLLIDE_EPS, 1.0 if i < j else -1.0)
+                            prop[i][0] += qx
+                            prop[i][1] += qy
+                            prop[i][2] += 1
+                            continue
                         d = math.hypot(ex, ey)
                         ux, uy = ((1.0 if i < j else -1.0), 0.0) if d < 1.0e-10 else (ex / d, ey / d)
                         h = r2 / 2.0 + O.COLLIDE_EPS

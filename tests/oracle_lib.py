@@ -34,7 +34,7 @@ class OracleConfig(C.Structure):
                 ("seed", C.c_uint64), ("device", C.c_int32), ("action_mode", C.c_int32), ("action_space_size", C.c_int32),
                 ("max_steps", C.c_int32), ("auto_reset", C.c_int32), ("change_ball_position", C.c_int32),
                 ("change_ball_velocity", C.c_int32), ("noise", C.c_int32), ("players_per_side", C.c_int32),
-                ("half_time_cycles", C.c_int32), ("kick_actions", C.c_int32), ("reserved_i", C.c_int32 * 3),
+                ("half_time_cycles", C.c_int32), ("kick_actions", C.c_int32), ("collision_model", C.c_int32), ("reserved_i", C.c_int32 * 2),
                 ("min_distance_to_ball", C.c_float), ("ball_position_x", C.c_float), ("ball_position_y", C.c_float),
                 ("ball_speed", C.c_float), ("ball_direction", C.c_float), ("goto_dist_thr", C.c_float),
                 ("reserved_f", C.c_float * 3), ("sp", OracleServerParam)]

@@ -77,13 +77,15 @@ def same_step(env, sim):
         assert np.array_equal(env.terminal_obs.cpu().numpy()[d], sim.term_obs[d])
 
 
-@pytest.mark.parametrize("pps,k,default_sp", [(11, 1, True), (11, 4, True), (3, 1, True), (11, 1, False)])
-def test_fullgame_bit_exact_against_fp32_oracle(pps, k, default_sp):
+@pytest.mark.parametrize("pps,k,default_sp,collision_model", [(11, 1, True, "midpoint"), (11, 4, True, "midpoint"),
+                                                             (3, 1, True, "midpoint"), (11, 1, False, "midpoint"),
+                                                             (11, 1, True, "backtrace"), (5, 3, False, "backtrace")])
+def test_fullgame_bit_exact_against_fp32_oracle(pps, k, default_sp, collision_model):
     n = 131
     sp = None if default_sp else dict(player_decay=0.45, kickable_margin=0.8, slowness_on_top_for_right_team=1.1,
                                      ball_decay=0.95, kick_power_rate=0.03)
     env = Soccer2DVecEnv(n, scenario="fullgame", device="cuda:0", seed=5, substeps=k, terminal_obs=True,
-                         players_per_side=pps, half_time_cycles=120, server_param=sp)
+                         players_per_side=pps, half_time_cycles=120, server_param=sp, collision_model=collision_model)
     p = 2 * pps
     assert env.obs.shape == (n, 120) and env.actions.shape == (n, k, p, 4)
     sim = OL.OracleSim(env.cfg, "f32")
@@ -403,11 +405,13 @@ def set_gpu_state_fg(env, vec):
     pl["ej"].copy_(torch.from_numpy(ej.astype(np.uint32).view(np.int32)))
 
 
-def test_fullgame_random_states_bit_exact():
+@pytest.mark.parametrize("collision_model", ["midpoint", "backtrace"])
+def test_fullgame_random_states_bit_exact(collision_model):
     """One cycle from hand-made states (players piled on the ball, the ball near or beyond every line, every play mode,
     stale offside marks) with random commands: reaches the referee branches a trajectory rarely visits."""
     n, p = 512, 22
-    env = Soccer2DVecEnv(n, scenario="fullgame", device="cuda:0", seed=2, half_time_cycles=10 ** 6, auto_reset=False)
+    env = Soccer2DVecEnv(n, scenario="fullgame", device="cuda:0", seed=2, half_time_cycles=10 ** 6, auto_reset=False,
+                         collision_model=collision_model)
     sim = OL.OracleSim(env.cfg, "f32")
     env.reset_torch()
     sim.reset()

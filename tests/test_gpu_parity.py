@@ -253,12 +253,15 @@ def test_ragged_sizes(n):
     assert canary.shape == env.obs.shape
 
 
-def test_collisions_stamina_and_boundaries_match_oracle():
+@pytest.mark.parametrize("collision_model", ["midpoint", "backtrace"])
+def test_collisions_stamina_and_boundaries_match_oracle(collision_model):
     """Hand-placed states: ball inside the player (moving and at rest, centres coincident), player at the
-    pitch edge, exhausted stamina (effort / recovery decay), capacity nearly used up."""
-    cases = HAND_PLACED_STATES
+    pitch edge, exhausted stamina (effort / recovery decay), capacity nearly used up - under both collision models."""
+    cases = HAND_PLACED_STATES + [[0, 0, 0.2, 0, 0, 8000, 1, 1, 130600, 1.0, 0, -0.5, 0, 1, 5, 0, 3, 3, 1],      # head-on, both moving
+             [0, 0, 0.3, 0.1, 0, 8000, 1, 1, 130600, 0.5, 0.2, 0, 0, 1, 5, 0, 3, 3, 1]]     # the player runs into a resting ball
     n = len(cases)
-    env = make_env(n, "continuous", seed=1, min_distance_to_ball=0.05, max_steps=100000, terminal_obs=True)
+    env = make_env(n, "continuous", seed=1, min_distance_to_ball=0.05, max_steps=100000, terminal_obs=True,
+                   collision_model=collision_model)
     sim = OL.OracleSim(env.cfg, "f32")
     env.reset_torch()
     sim.reset()

@@ -62,10 +62,12 @@ def test_kernel_source_runtime_params_path(mode):
     assert np.array_equal(emu.get_state(), sim.get_state())
 
 
-def test_kernel_source_hand_placed_states():
-    cases = HAND_PLACED_STATES
+@pytest.mark.parametrize("collision_model", [0, 1])
+def test_kernel_source_hand_placed_states(collision_model):
+    cases = HAND_PLACED_STATES + [[0, 0, 0.2, 0, 0, 8000, 1, 1, 130600, 1.0, 0, -0.5, 0, 1, 5, 0, 3, 3, 1],
+                                  [0, 0, 0.3, 0.1, 0, 8000, 1, 1, 130600, 0.5, 0.2, 0, 0, 1, 5, 0, 3, 3, 1]]
     n = len(cases)
-    cfg = H.make_config(n, "continuous", seed=1, min_distance_to_ball=0.05, max_steps=100000)
+    cfg = H.make_config(n, "continuous", seed=1, min_distance_to_ball=0.05, max_steps=100000, collision_model=collision_model)
     emu, sim = EL.EmuSim(cfg), OL.OracleSim(cfg, "f32")
     emu.reset()
     sim.reset()

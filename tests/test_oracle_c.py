@@ -324,7 +324,8 @@ def test_fullgame_invariants_with_player_types_and_referee():
     assert {2, 3} <= seen_modes and marks_seen > 0
 
 
-def test_fullgame_c_oracle_equals_an_independent_python_twin():
+@pytest.mark.parametrize("collision_model", [0, 1])
+def test_fullgame_c_oracle_equals_an_independent_python_twin(collision_model):
     """The FULLGAME spec (include/soccer2d.h) restated twice: oracle/s2d_oracle.c and tests/fullgame_twin.py (built on
     the Python oracle's building blocks).  They are stepped from the same state and compared one cycle ahead - every
     state of 300 cycles of swarm play with heterogeneous players, body actions, goals, restarts and offside calls."""
@@ -334,7 +335,8 @@ def test_fullgame_c_oracle_equals_an_independent_python_twin():
     from test_gpu_fullgame import swarm_policy
     n, p, half = 5, 22, 120
     lib = _abi.load()
-    cfg = H.make_config(n, "command", scenario=_abi.SCENARIO_FULLGAME, seed=21, half_time_cycles=half, goto_dist_thr=0.5)
+    cfg = H.make_config(n, "command", scenario=_abi.SCENARIO_FULLGAME, seed=21, half_time_cycles=half, goto_dist_thr=0.5,
+                        collision_model=collision_model)
     types = (_abi.PlayerType * 18)()
     assert lib.s2d_generate_player_types(4, C.byref(cfg.sp), types, 18) == 0
     rng = np.random.default_rng(11)
@@ -363,7 +365,7 @@ def test_fullgame_c_oracle_equals_an_independent_python_twin():
         for i in range(n):
             m = T.Match(before[i].tolist(), p)
             rw, done, res = T.cycle(m, act[i, 0], sps, base, int(cfg.seed), int(cfg.env_id_offset) + i,
-                                    float(np.float32(cfg.goto_dist_thr)), half)
+                                    float(np.float32(cfg.goto_dist_thr)), half, collision_model)
             assert done == bool(sim.done[i]) and res == int(sim.result[i]), (t, i)
             assert rw == pytest.approx(float(sim.reward[i]), abs=1e-9), (t, i)
             if done:
@@ -376,18 +378,21 @@ def test_fullgame_c_oracle_equals_an_independent_python_twin():
             modes.add(m.mode)
             calls += int(m.mode == 5 and m.timer == 0 and before[i][k + 8] == 2)
             goals += int(after[i][k + 11] + after[i][k + 12] > before[i][k + 11] + before[i][k + 12])
-    assert {2, 3} <= modes and len(modes) >= 3
-    assert goals > 0 and calls > 0, (sorted(modes), calls, goals)  # goals, kick-ins and an offside call were compared
+    assert {2, 3} <= modes
+    if collision_model == 0:  # (the other model plays a different match from the same seed: the comparison above is the point)
+        assert len(modes) >= 3 and goals > 0 and calls > 0, (sorted(modes), calls, goals)  # goals, kick-ins, an offside call
 
 
-def test_fullgame_c_oracle_equals_the_twin_on_random_states():
+@pytest.mark.parametrize("collision_model", [0, 1])
+def test_fullgame_c_oracle_equals_the_twin_on_random_states(collision_model):
     """The same comparison from hand-made states instead of a trajectory: players scattered or piled up around the ball,
     the ball near or beyond every line, every play mode with either side and timer, stale offside marks - one cycle
     with random commands.  Reaches the referee branches a swarm trajectory rarely visits."""
     import fullgame_twin as T
     from oracle import soccer2d_oracle as O
     n, p, half = 64, 22, 10 ** 6
-    cfg = H.make_config(n, "command", scenario=_abi.SCENARIO_FULLGAME, seed=2, half_time_cycles=half, goto_dist_thr=0.5, auto_reset=0)
+    cfg = H.make_config(n, "command", scenario=_abi.SCENARIO_FULLGAME, seed=2, half_time_cycles=half, goto_dist_thr=0.5, auto_reset=0,
+                        collision_model=collision_model)
     sim = OL.OracleSim(cfg, "f64")
     sim.reset()
     base = O.ServerParam(**{k: getattr(cfg.sp, k) for k in _abi._SP_FIELDS if hasattr(O.ServerParam(), k)})
@@ -430,7 +435,7 @@ def test_fullgame_c_oracle_equals_the_twin_on_random_states():
         after = sim.get_state_fg()
         for i in range(n):
             m = T.Match(before[i].tolist(), p)
-            rw, done, res = T.cycle(m, act[i, 0], sps, base, int(cfg.seed), i, 0.5, half)
+            rw, done, res = T.cycle(m, act[i, 0], sps, base, int(cfg.seed), i, 0.5, half, collision_model)
             assert not done and rw == pytest.approx(float(sim.reward[i]), abs=1e-9), (rnd, i)
             m.ep_return += rw
             err = np.abs(np.array(m.vector()) - after[i]) / scale
@@ -471,3 +476,40 @@ def test_oracle_envs_are_compact():
         act = rng.integers(0, 16, size=(3000, 4)).astype(np.uint8)
         a.step(act, 4), b.step(act, 4)
     assert np.array_equal(a.done, b.done) and np.abs(a.obs - b.obs).max() < 1e-3
+
+
+@pytest.mark.parametrize("collision_model", [0, 1])
+def test_one_player_collision_models_c_equals_python(collision_model):
+    """The ball-player contact of the one-player scenarios under both collision models (include/soccer2d.h): C f64 and the
+    Python oracle's `collisions` agree from hand-placed overlaps (moving ball, ball at rest, coincident centres, a
+    moving player), and under BACKTRACE the player is moved as well."""
+    from oracle import soccer2d_oracle as O
+    from test_gpu_parity_cases import HAND_PLACED_STATES
+    cases = [c for c in HAND_PLACED_STATES[:4]] + [[0, 0, 0.2, 0, 0, 8000, 1, 1, 130600, 1.0, 0, -0.5, 0, 1, 5, 0, 3, 3, 1],      # head-on, both moving
+             [0, 0, 0.3, 0.1, 0, 8000, 1, 1, 130600, 0.5, 0.2, 0, 0, 1, 5, 0, 3, 3, 1]]     # the player runs into a resting ball
+    n = len(cases)
+    cfg = H.make_config(n, "continuous", seed=1, min_distance_to_ball=0.05, max_steps=100000, collision_model=collision_model,
+                        sp=dict(dash_power_rate=0.0))
+    sim = OL.OracleSim(cfg, "f64")
+    sim.reset()
+    sp = O.ServerParam().as_f32()
+    sp.dash_power_rate = 0.0
+    moved_player, hits = False, 0
+    for i, c in enumerate(cases):
+        sim.set_state(i, np.array(c + [0], dtype=np.float64))
+    sim.step(np.zeros((n, 1), np.float32))
+    for i, c in enumerate(cases):
+        p = O.Player(x=c[0], y=c[1], vx=c[2], vy=c[3], body=c[4], stamina=c[5], effort=c[6], recovery=c[7], capacity=c[8])
+        b = O.Ball(x=c[9], y=c[10], vx=c[11], vy=c[12])
+        O.obj_inc(p, sp.player_accel_max, sp.player_speed_max, sp.player_decay)
+        O.obj_inc(b, sp.ball_accel_max, sp.ball_speed_max, sp.ball_decay)
+        before = (p.x, p.y)
+        O.collisions(b, [p], sp, collision_model)
+        got = sim.get_state(i)
+        assert b.collided == p.collided == (int(got[19]) & 3 == 3)
+        assert np.allclose([p.x, p.y, p.vx, p.vy], got[0:4], rtol=0, atol=1e-12)
+        assert np.allclose([b.x, b.y, b.vx, b.vy], got[9:13], rtol=0, atol=1e-12)
+        assert math.hypot(b.x - p.x, b.y - p.y) >= sp.player_size + sp.ball_size
+        hits += b.collided
+        moved_player |= (p.x, p.y) != before
+    assert hits >= 3 and moved_player == (collision_model == 1)

@@ -26,6 +26,11 @@ constexpr int kFgDropBallTime = 100;  // cycles a dead ball waits for the awarde
 constexpr int kFgMaxPlayers = 22;
 constexpr float kFgFreeKickDist = 9.15f;  // the distance opponents keep from a dead ball
 constexpr float kFgOffsideArea = 2.5f;    // offside_active_area_size: a marked player this close to the ball takes part
+constexpr int kFgAfterGoalWait = 50;      // stopped cycles between a goal and the kick-off
+constexpr int kFgTackleCycles = 10;       // tackle_cycles: how long a player lies on the ground after a tackle
+constexpr int kFgCatchBan = 5;            // catch_ban_cycle
+constexpr float kFgCatchLength = 1.2f, kFgCatchWidth = 1.0f;             // catch_area_l, catch_area_w
+constexpr float kFgPenaltyLength = 16.5f, kFgPenaltyHalfWidth = 20.16f;  // the penalty area
 
 // HBM layout of N matches with np players each: plane-major, MATCH-MINOR (consecutive matches are consecutive in
 // memory, so a warp = 32 matches touches 512 contiguous bytes per float4 access).  Rows hold Nr = N rounded up to the
@@ -36,6 +41,7 @@ constexpr float kFgOffsideArea = 2.5f;    // offside_active_area_size: a marked 
 //   EB float4 [Nr] ball {x, y, vx, vy}          EF float4 [Nr] {episode return, player separation bound, offside marks (bits), -}
 //   EI uint4  [Nr] {step_number, cycle, episode, mode | side<<8 | last_touch<<10 | timer<<12 | ball_collided<<20 | done<<21}
 //   EJ uint4  [Nr] {score_l, score_r, collided mask (bit = player), kicked mask}
+//   EK uint4  [Nr] {tackle counters of players 0-7, 8-15, 16-21 (a nibble each), catch bans (left keeper | right << 4)}
 constexpr int kFgBlock = 64;  // matches (= threads) per block
 struct FgLayout {
   int64_t n;
@@ -48,7 +54,8 @@ struct FgLayout {
   __host__ __device__ size_t ef() const { return eb() + nr() * 16; }
   __host__ __device__ size_t ei() const { return ef() + nr() * 16; }
   __host__ __device__ size_t ej() const { return ei() + nr() * 16; }
-  __host__ __device__ size_t bytes() const { return ej() + nr() * 16; }
+  __host__ __device__ size_t ek() const { return ej() + nr() * 16; }
+  __host__ __device__ size_t bytes() const { return ek() + nr() * 16; }
 };
 
 #ifndef S2D_HOST_EMU
@@ -63,6 +70,8 @@ struct Match {
   uint32_t offside;  // bit = player marked offside at the last pass of its team (all bits from one team)
   bool done_flag;
   float bx, by, bvx, bvy;  // the ball
+  uint32_t tk0, tk1, tk2;  // cycles each player still lies on the ground after a tackle: a nibble per player
+  uint32_t ban;            // cycles until the goalkeepers may catch again (left | right << 4)
 };
 
 #ifndef S2D_FG_AHEAD
@@ -166,6 +175,7 @@ __device__ __noinline__ void fg_reset(FgShared& S, int t, FgPlanes g, Match& m, 
     g.pc += g.rowc;
   }
   m.bx = m.by = m.bvx = m.bvy = 0.0f;
+  m.tk0 = m.tk1 = m.tk2 = m.ban = 0u;
   m.episode += 1u;
   m.step_number = 0;
   m.ep_return = 0.0f;
@@ -189,8 +199,8 @@ __device__ __noinline__ void fg_reset(FgShared& S, int t, FgPlanes g, Match& m, 
 // results are the same bit for bit.  Returns whether the player kicked (kax, kay = its push on the ball).
 template <class SP>
 __device__ __forceinline__ bool fg_commands(Episode& p, float4 a, float goto_dist_thr, const SP& sp, const NoiseCtx& nz,
-                                            const unsigned full, int agent, bool left, bool may_kick, float& ax, float& ay,
-                                            float& kax, float& kay) {
+                                            const unsigned full, int agent, bool left, bool may_kick, bool may_dash, float& ax,
+                                            float& ay, float& kax, float& kay) {
   // the proxy's other body actions become a plain turn or kick first (rare: one vote when nobody uses them)
   if (__any_sync(full, a.x >= static_cast<float>(S2D_CMD_TURN_TO_POINT))) {
     if (a.x >= static_cast<float>(S2D_CMD_TURN_TO_POINT)) lower_body_action(p, a, sp);
@@ -238,7 +248,7 @@ __device__ __forceinline__ bool fg_commands(Episode& p, float4 a, float goto_dis
   }
 
   // dash direction (go-to-point dashes straight: direction 0) and the one sincos
-  const bool do_dash = user_dash || goto_dash;
+  const bool do_dash = (user_dash || goto_dash) && may_dash;  // (AfterGoal: the clock stands still, only turns work)
   float dir = 0.0f, rate = 1.0f;
   if (__any_sync(full, do_dash)) dash_direction(user_dash ? a.z : 0.0f, sp, dir, rate);
   const float user_power = clampf(sp.min_dash_power(), a.y, sp.max_dash_power());
@@ -539,6 +549,8 @@ __device__ __forceinline__ bool fg_cycle(FgShared& S, const int t, const FgPlane
   const unsigned left_set = (1u << pps) - 1u;
   bool dead = m.mode != S2D_PM_PLAY_ON;
   const bool dead_at_start = dead;
+  const bool stopped = m.mode == S2D_PM_AFTER_GOAL;  // the server's clock stands still: nothing moves, only turns work
+  int caught = -1;                                   // the goalkeeper (player index) that caught the ball this cycle
   m.step_number += 1;
   const NoiseCtx nz{P.seed, gid, m.cycle};
   {  // the match's command row (np x 16 bytes, 32-byte aligned): ask the L2 for its lines now, the loop loads them later
@@ -601,7 +613,83 @@ __device__ __forceinline__ bool fg_cycle(FgShared& S, const int t, const FgPlane
       p.bx = m.bx; p.by = m.by; p.bvx = m.bvx; p.bvy = m.bvy;
       S.oldx[j][t] = p.px;
       float ax = 0.0f, ay = 0.0f, kax = 0.0f, kay = 0.0f;
-      const bool kicked = fg_commands(p, a, P.goto_dist_thr, sp, nz, full, j, left, !dead_at_start || my_side == m.side, ax, ay, kax, kay);
+      // tackle / catch and their after-effects (Player::tackle, Player::goalieCatch; spec: include/soccer2d.h).  One
+      // vote skips all of it while nobody in the warp tackles, catches, lies on the ground or waits for its next catch.
+      float4 cmd = a;
+      bool tackled = false;
+      float tkx = 0.0f, tky = 0.0f;  // a tackle's push on the ball
+      const int raw = static_cast<int>(a.x);
+      if (__any_sync(full, (m.tk0 | m.tk1 | m.tk2 | m.ban) != 0u || raw == S2D_CMD_TACKLE || raw == S2D_CMD_CATCH)) {
+        const int word = j >> 3, shift = (j & 7) * 4;
+        const uint32_t w = word == 0 ? m.tk0 : word == 1 ? m.tk1 : m.tk2;
+        uint32_t count = (w >> shift) & 15u;
+        const bool keeper = j == 0 || j == pps;
+        const int ban_shift = j == 0 ? 0 : 4;
+        uint32_t ban = keeper ? (m.ban >> ban_shift) & 15u : 0u;
+        if (!stopped && ban > 0u) ban -= 1u;
+        if (!stopped && count > 0u) {  // on the ground after a tackle: whatever it was told, it does nothing
+          count -= 1u;
+          cmd.x = static_cast<float>(S2D_CMD_NONE);
+        } else if (raw == S2D_CMD_TACKLE) {
+          cmd.x = static_cast<float>(S2D_CMD_NONE);
+          if (!stopped) {
+            float sn, cs;
+            sincos_deg(p.body, sn, cs);
+            const float dx = p.bx - p.px, dy = p.by - p.py;
+            const float rx = dx * cs + dy * sn, ry = dy * cs - dx * sn;  // the ball in the body frame, x ahead
+            count = kFgTackleCycles;
+            bool ok = false;
+            if (rx > 0.0f) {
+              const float fx = rx * static_cast<float>(1.0 / 2.0), fy = fabsf(ry) * static_cast<float>(1.0 / 1.25);
+              const float fx2 = fx * fx, fy2 = fy * fy;
+              const float fail = (fx2 * fx2) * fx2 + (fy2 * fy2) * fy2;
+              if (fail < 1.0f)
+                ok = u32_to_unit(philox4x32_10(P.seed, gid, m.cycle, RNG_TACKLE, static_cast<uint32_t>(j)).x) < 1.0f - fail;
+            }
+            if (ok && !dead_at_start) {
+              const float d = clampf(-180.0f, a.y, 180.0f);
+              float eff = 100.0f * (1.0f - fabsf(d) * static_cast<float>(1.0 / 180.0)) * 0.027f;
+              eff = eff * (1.0f - 0.5f * fabsf(atan2_deg(ry, rx)) * static_cast<float>(1.0 / 180.0));
+              sincos_deg(p.body + d, sn, cs);
+              tkx = eff * cs;
+              tky = eff * sn;
+              tackled = true;
+            }
+          }
+        } else if (raw == S2D_CMD_CATCH) {
+          cmd.x = static_cast<float>(S2D_CMD_NONE);
+          if (!stopped && !dead_at_start && keeper && ban == 0u) {
+            const float d = clampf(-180.0f, a.y, 180.0f);
+            float sn, cs;
+            sincos_deg(p.body + d, sn, cs);
+            const float dx = p.bx - p.px, dy = p.by - p.py;
+            const float rx = dx * cs + dy * sn, ry = dy * cs - dx * sn;
+            const bool in_rect = rx >= 0.0f && rx <= kFgCatchLength && fabsf(ry) <= kFgCatchWidth * static_cast<float>(1.0 / 2.0);
+            const float edge = sp.pitch_half_length() - kFgPenaltyLength;
+            const bool in_area = (j == 0 ? p.bx <= -edge : p.bx >= edge) && fabsf(p.by) <= kFgPenaltyHalfWidth;
+            if (in_rect && in_area) {
+              caught = j;
+              ban = kFgCatchBan;
+            }
+          }
+        }
+        const uint32_t nw = (w & ~(15u << shift)) | (count << shift);
+        m.tk0 = word == 0 ? nw : m.tk0;
+        m.tk1 = word == 1 ? nw : m.tk1;
+        m.tk2 = word == 2 ? nw : m.tk2;
+        if (keeper) m.ban = (m.ban & ~(15u << ban_shift)) | (ban << ban_shift);
+      }
+      bool kicked = fg_commands(p, cmd, P.goto_dist_thr, sp, nz, full, j, left, (!dead_at_start || my_side == m.side) && !stopped,
+                                !stopped, ax, ay, kax, kay);
+      if (tackled) {  // counts as a kick: last touch, kicked flag, offside
+        kicked = true;
+        kax = tkx;
+        kay = tky;
+      }
+      if (stopped) {
+        p.vx = 0.0f;
+        p.vy = 0.0f;
+      }
       if (kicked) {
         kick_mask |= 1u << j;
         kx[j] = kax;
@@ -612,7 +700,7 @@ __device__ __forceinline__ bool fg_cycle(FgShared& S, const int t, const FgPlane
                               static_cast<uint32_t>(j));
       const float stepx = p.px - pa.x, stepy = p.py - pa.y;
       moved2 = fmaxf(moved2, stepx * stepx + stepy * stepy);
-      update_stamina(p, sp);
+      if (!stopped) update_stamina(p, sp);
       S.xy[j][t] = make_float2(p.px, p.py);
       st_stream(wpa, make_float4(p.px, p.py, p.vx, p.vy));
       st_stream(wpb, make_float4(p.body, p.stamina, p.effort, p.recovery));
@@ -662,6 +750,13 @@ __device__ __forceinline__ bool fg_cycle(FgShared& S, const int t, const FgPlane
     dead = false;
   }
   kicked_mask = kick_mask;
+  if (caught >= 0) {  // the goalkeeper holds the ball: free kick for its side; what the others did to the ball is void
+    m.mode = S2D_PM_FREE_KICK;
+    m.side = caught < pps ? S2D_SIDE_LEFT : S2D_SIDE_RIGHT;
+    m.timer = 0;
+    m.last_touch = m.side;
+    dead = true;
+  }
   if (kick_mask && !dead) {
     m.offside = 0u;  // whoever kicks: the old marks are void
     const bool exempt = mode_at_kick == S2D_PM_KICK_IN || mode_at_kick == S2D_PM_CORNER_KICK || mode_at_kick == S2D_PM_GOAL_KICK;
@@ -677,21 +772,35 @@ __device__ __forceinline__ bool fg_cycle(FgShared& S, const int t, const FgPlane
     m.bvx = 0.0f;
     m.bvy = 0.0f;
   }
+  if (caught >= 0) {  // in the keeper's hands
+    const float2 k = S.xy[caught][t];
+    m.bx = k.x;
+    m.by = k.y;
+  }
 
   // ---- second walk over the players, now that ball and play mode are settled: a dead ball keeps the side that does
   // ---- not take the kick 9.15 m away; a live ball is tested against every player ----
   const float r = sp.player_size() + sp.ball_size();
   const float r2 = sp.player_size() + sp.player_size();
-  const bool clearing = dead && m.mode != S2D_PM_TIME_OVER;
+  const bool clearing = dead && m.mode != S2D_PM_TIME_OVER && m.mode != S2D_PM_AFTER_GOAL;
+  const bool own_half = m.mode == S2D_PM_KICK_OFF;  // Referee::placePlayersInTheirField
   uint32_t ball_mask = 0;  // players the live ball overlaps
   float cleared2 = 0.0f;
 #pragma unroll 1
   for (int j = 0; j < np; ++j) {
     float2 xy = S.xy[j][t];
-    const float cx = xy.x - m.bx, cy = xy.y - m.by;
-    const float c2 = cx * cx + cy * cy;
     const bool left = j < pps;
     const int my_side = left ? S2D_SIDE_LEFT : S2D_SIDE_RIGHT;
+    bool placed = false;
+    float sx = 0.0f, sy = 0.0f;  // how far the referee moved the player
+    if (own_half && (left ? xy.x > 0.0f : xy.x < 0.0f)) {
+      const float nx = left ? -sp.player_size() : sp.player_size();
+      sx = nx - xy.x;
+      xy.x = nx;
+      placed = true;
+    }
+    const float cx = xy.x - m.bx, cy = xy.y - m.by;
+    const float c2 = cx * cx + cy * cy;
     if (clearing && my_side != m.side && c2 < kFgFreeKickDist * kFgFreeKickDist) {
       const float c = sqrtf(c2);
       float ux = left ? -1.0f : 1.0f, uy = 0.0f;
@@ -700,14 +809,19 @@ __device__ __forceinline__ bool fg_cycle(FgShared& S, const int t, const FgPlane
         uy = cy / c;
       }
       const float nx = m.bx + ux * kFgFreeKickDist, ny = m.by + uy * kFgFreeKickDist;
-      const float sx = nx - xy.x, sy = ny - xy.y;
+      sx += nx - xy.x;
+      sy += ny - xy.y;
+      xy = make_float2(nx, ny);
+      placed = true;
+    }
+    if (placed) {
       cleared2 = fmaxf(cleared2, sx * sx + sy * sy);
-      S.xy[j][t] = make_float2(nx, ny);
-      g.pa[static_cast<size_t>(j) * g.row] = make_float4(nx, ny, 0.0f, 0.0f);
+      S.xy[j][t] = xy;
+      g.pa[static_cast<size_t>(j) * g.row] = make_float4(xy.x, xy.y, 0.0f, 0.0f);
       if (obs_row && valid) {
         float* o = obs_row + 4 + 5 * j;
-        o[0] = nx * static_cast<float>(1.0 / 52.5);
-        o[1] = ny * static_cast<float>(1.0 / 34.0);
+        o[0] = xy.x * static_cast<float>(1.0 / 52.5);
+        o[1] = xy.y * static_cast<float>(1.0 / 34.0);
         o[2] = 0.0f;
         o[3] = 0.0f;
       }
@@ -747,7 +861,7 @@ __device__ __forceinline__ bool fg_cycle(FgShared& S, const int t, const FgPlane
   ball_collided = false;
   uint32_t touch = 0;
   {
-    const unsigned need = __ballot_sync(full, pairs_close || ball_mask != 0u);
+    const unsigned need = __ballot_sync(full, (pairs_close || ball_mask != 0u) && !stopped);  // (AfterGoal: nothing moves)
     if (need)
       fg_resolve_collisions(S, t, g, m, np, need, dead, r, r2, sp.collision_model(), obs_row ? P.obs : nullptr,
                             static_cast<int64_t>(blockIdx.x) * kFgBlock + t, valid, collided_mask, touch, ball_collided);
@@ -804,11 +918,12 @@ __device__ __forceinline__ bool fg_cycle(FgShared& S, const int t, const FgPlane
     if (goal_l || goal_r) {
       if (goal_l) m.score_l += 1;
       else m.score_r += 1;
-      kick_off = true;
-      m.mode = S2D_PM_KICK_OFF;
-      m.side = goal_l ? S2D_SIDE_RIGHT : S2D_SIDE_LEFT;  // the conceding side kicks off
+      m.mode = S2D_PM_AFTER_GOAL;  // AfterGoal_ + the scoring side: the clock stops for kFgAfterGoalWait cycles
+      m.side = goal_l ? S2D_SIDE_LEFT : S2D_SIDE_RIGHT;
       m.timer = 0;
       m.last_touch = S2D_SIDE_UNKNOWN;
+      m.bvx = 0.0f;
+      m.bvy = 0.0f;
     } else if (fabsf(bx) > line) {  // over a goal line outside the goal: corner kick or goal kick
       const int defending = bx > 0.0f ? S2D_SIDE_RIGHT : S2D_SIDE_LEFT;
       const float sx = bx > 0.0f ? 1.0f : -1.0f, sy = by > 0.0f ? 1.0f : -1.0f;
@@ -837,7 +952,14 @@ __device__ __forceinline__ bool fg_cycle(FgShared& S, const int t, const FgPlane
     }
   } else {
     m.timer += 1;
-    if (m.timer >= kFgDropBallTime) {
+    if (m.mode == S2D_PM_AFTER_GOAL) {
+      if (m.timer >= kFgAfterGoalWait) {  // kick-off for the side that conceded
+        kick_off = true;
+        m.mode = S2D_PM_KICK_OFF;
+        m.side = m.side == S2D_SIDE_LEFT ? S2D_SIDE_RIGHT : S2D_SIDE_LEFT;
+        m.timer = 0;
+      }
+    } else if (m.timer >= kFgDropBallTime) {
       m.mode = S2D_PM_PLAY_ON;
       m.timer = 0;
     }
@@ -849,7 +971,7 @@ __device__ __forceinline__ bool fg_cycle(FgShared& S, const int t, const FgPlane
     m.bx = m.by = m.bvx = m.bvy = 0.0f;
   }
   if (m.mode != S2D_PM_PLAY_ON) m.offside = 0u;  // marks live only while play goes on
-  m.cycle += 1u;
+  m.cycle += stopped ? 0u : 1u;
   reward = static_cast<float>(goal_l - goal_r) * 10.0f + (bx_phys - pbx) * 0.01f;
   const bool done = m.step_number >= 2 * half_time;
   result = !done ? S2D_RESULT_NONE : m.score_l > m.score_r ? 1 : m.score_r > m.score_l ? 2 : 3;
@@ -872,6 +994,8 @@ __device__ __forceinline__ void fg_load(const KernelParams& P, const FgLayout& L
   m.mode = ei.w & 0xff; m.side = (ei.w >> 8) & 3; m.last_touch = (ei.w >> 10) & 3; m.timer = (ei.w >> 12) & 0xff;
   m.done_flag = (ei.w >> 21) & 1;
   m.score_l = static_cast<int>(ej.x); m.score_r = static_cast<int>(ej.y);
+  const uint4 ek = ld_stream(reinterpret_cast<const uint4*>(base + L.ek()) + env);
+  m.tk0 = ek.x; m.tk1 = ek.y; m.tk2 = ek.z; m.ban = ek.w;
 }
 
 __device__ __forceinline__ void fg_store(const KernelParams& P, const FgLayout& L, int64_t env, const Match& m,
@@ -885,6 +1009,7 @@ __device__ __forceinline__ void fg_store(const KernelParams& P, const FgLayout& 
   st_stream(reinterpret_cast<uint4*>(base + L.ei()) + env, make_uint4(static_cast<uint32_t>(m.step_number), m.cycle, m.episode, packed));
   st_stream(reinterpret_cast<uint4*>(base + L.ej()) + env,
             make_uint4(static_cast<uint32_t>(m.score_l), static_cast<uint32_t>(m.score_r), collided_mask, kicked_mask));
+  st_stream(reinterpret_cast<uint4*>(base + L.ek()) + env, make_uint4(m.tk0, m.tk1, m.tk2, m.ban));
 }
 
 // heterogeneous players: the block copies the type table to shared memory; the player loops point sp.row at the row of

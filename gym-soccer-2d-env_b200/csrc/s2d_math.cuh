@@ -116,7 +116,7 @@ __device__ __forceinline__ float softmax_first(float a, float b) { return 1.0f /
 // `index` is the episode number for reset draws and the server cycle for per-step draws, so a stream never
 // depends on how envs are sharded over GPUs or how many substeps a launch fuses.
 // ------------------------------------------------------------------------------------------------------
-enum RngPurpose : uint32_t { RNG_RESET = 0, RNG_BALLVEL = 1, RNG_ACTION = 2, RNG_NOISE = 3 };
+enum RngPurpose : uint32_t { RNG_RESET = 0, RNG_BALLVEL = 1, RNG_ACTION = 2, RNG_NOISE = 3, RNG_TACKLE = 5 };  // (4: player-type draws)
 
 __device__ __forceinline__ uint4 philox4x32_10(uint64_t seed, uint64_t env, uint32_t index, uint32_t purpose,
                                                uint32_t sub) {

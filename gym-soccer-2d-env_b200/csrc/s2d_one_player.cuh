@@ -254,6 +254,33 @@ __device__ __noinline__ float4 lower_body_action_cold(const Kinematics e, float4
                        (1.0f - 0.25f * dir_diff * static_cast<float>(1.0 / 180.0) - 0.25f * dist_ball / sp.kickable_margin());
     a = make_float4(static_cast<float>(S2D_CMD_KICK), clampf(0.0f, acc / rate, sp.max_power()),
                     norm_deg_360(atan2_deg(ay, ax) - e.body), 0.0f);
+  } else if (c == S2D_CMD_SMART_KICK) {  // release if one kick can do it, else stage (include/soccer2d.h)
+    const float dx = e.bx - e.px, dy = e.by - e.py;
+    const float dist = hypot2(dx, dy);
+    if (dist > sp.kickable_area()) return make_float4(static_cast<float>(S2D_CMD_NONE), 0.0f, 0.0f, 0.0f);
+    const float first_speed = clampf(0.0f, a.w, sp.ball_speed_max());
+    float s, cs;
+    sincos_deg(atan2_deg(a.z - e.by, a.y - e.bx), s, cs);
+    float ax = first_speed * cs - e.bvx, ay = first_speed * s - e.bvy;
+    float acc = hypot2(ax, ay);
+    const float dir_diff = fabsf(norm_deg_360(atan2_deg(dy, dx) - e.body));
+    const float dist_ball = dist - sp.player_size() - sp.ball_size();
+    const float rate = sp.kick_power_rate() *
+                       (1.0f - 0.25f * dir_diff * static_cast<float>(1.0 / 180.0) - 0.25f * dist_ball / sp.kickable_margin());
+    if (!(acc <= sp.max_power() * rate)) {
+      const float nx = e.px + e.vx, ny = e.py + e.vy;
+      sincos_deg(atan2_deg(a.z - ny, a.y - nx), s, cs);
+      const float d = sp.player_size() + sp.ball_size() + 0.3f * sp.kickable_margin();
+      const float sax = ((nx + d * cs) - e.bx) - e.bvx, say = ((ny + d * s) - e.by) - e.bvy;
+      const float sacc = hypot2(sax, say);
+      if (sacc >= 0.05f) {  // (else it is staged already: release with what max_power gives)
+        ax = sax;
+        ay = say;
+        acc = sacc;
+      }
+    }
+    a = make_float4(static_cast<float>(S2D_CMD_KICK), clampf(0.0f, acc / rate, sp.max_power()),
+                    norm_deg_360(atan2_deg(ay, ax) - e.body), 0.0f);
   } else if (c == S2D_CMD_INTERCEPT) {
     // drift sums 1 + d + d^2 + ...: where ball and player are after t cycles if nobody touches them
     const float reach0 = 0.8f * sp.kickable_area();

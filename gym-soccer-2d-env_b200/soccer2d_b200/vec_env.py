@@ -615,7 +615,8 @@ class Soccer2DVecEnv(_VecEnvBase):
             off += nr * p * 16
         out["pc"] = self.state[off:off + nr * p * 4].view(torch.float32).view(p, nr)[:, :n].t()
         off += nr * p * 4
-        for name, dt in (("ball", torch.float32), ("ef", torch.float32), ("ei", torch.int32), ("ej", torch.int32)):
+        for name, dt in (("ball", torch.float32), ("ef", torch.float32), ("ei", torch.int32), ("ej", torch.int32),
+                         ("ek", torch.int32)):
             out[name] = self.state[off:off + nr * 16].view(dt).view(nr, 4)[:n]
             off += nr * 16
         assert off == self.state.numel()

@@ -166,8 +166,8 @@ class Soccer2DEnv(Env):
             k = action.body_kick_one_step  # (force_mode semantics: the kick is made even if first_speed cannot be reached)
             cmd[0, 0] = [_abi.CMD_KICK_ONE_STEP, float(k.target_point.x), float(k.target_point.y), float(k.first_speed)]
         elif which == "body_smart_kick":
-            k = action.body_smart_kick  # librcsc plans up to max_steps kicks; here the first (and only) one: as KickOneStep
-            cmd[0, 0] = [_abi.CMD_KICK_ONE_STEP, float(k.target_point.x), float(k.target_point.y), float(k.first_speed)]
+            k = action.body_smart_kick  # staged over 2-3 cycles when one kick cannot reach first_speed (include/soccer2d.h)
+            cmd[0, 0] = [_abi.CMD_SMART_KICK, float(k.target_point.x), float(k.target_point.y), float(k.first_speed)]
         elif which == "body_stop_ball":
             cmd[0, 0] = [_abi.CMD_STOP_BALL, 0.0, 0.0, 0.0]
         elif which == "body_intercept":

@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define S2D_ABI_VERSION 10
+#define S2D_ABI_VERSION 11
 
 /* error codes */
 #define S2D_OK 0
@@ -78,7 +78,15 @@ extern "C" {
  *   180 deg, ball at the centre, play mode KickOff for the left team (after a goal: for the conceding side, next cycle).
  *   Referee subset (play modes = proto GameModeType, idl/service.proto:267-301):
  *     goal       ball beyond x = +-(pitch_half_length + ball_size) having crossed the line between the posts
- *                (|y| <= goal_width/2 + goal_post_radius at the crossing)      -> score, KickOff
+ *                (|y| <= goal_width/2 + goal_post_radius at the crossing)      -> score, AfterGoal for the scoring side
+ *     after goal (AfterGoal_, proto GameModeType 8) the server's clock stands still for 50 cycles (rcssserver: only
+ *                `stoped_cycle` advances, S2DEnvSnapshot.stoped_cycle here): nothing moves or collides, velocities are zero, dash / kick
+ *                / tackle / catch have no effect and cost no stamina, turn works, stamina is not updated, `cycle` does not
+ *                advance (step_number does: an env step is an env step).  Then: kick-off formation, KickOff for the
+ *                conceding side.
+ *     kick-off   while the mode is KickOff every player stays in its own half: after the players have moved, one beyond the
+ *                half-way line is put back at x = -+player_size on its side, at rest (Referee::placePlayersInTheirField);
+ *                the 9.15 m clearance then applies to the side that does not kick off
  *     goal line  crossed elsewhere: last touched by the defending side -> CornerKick for the attackers at
  *                (+-(half_length - 1), +-(half_width - 1)); else GoalKick for the defenders at (+-(half_length - 5.5), +-9.16)
  *     side line  |y| > pitch_half_width + ball_size -> KickIn for the side that did not touch it last, ball on the line
@@ -95,13 +103,30 @@ extern "C" {
  *                closer than 2.5 m (offside_active_area_size) to the ball after the collisions -> FreeKick for the other
  *                team with the ball where that player stands (lowest player index if several), nothing else is ruled
  *                on in that cycle.
- *     Not modelled: AfterGoal pause, fouls, tackle, catch; players are not confined to their half at kick-off.
+ *     tackle     S2D_CMD_TACKLE (Player::tackle, rcssserver defaults as constants: tackle_dist 2.0, tackle_back_dist 0,
+ *                tackle_width 1.25, tackle_exponent 6, tackle_cycles 10, tackle_power_rate 0.027, max_tackle_power 100,
+ *                max_back_tackle_power 0).  Ball relative to the player in its body frame (x ahead): behind (x <= 0) the
+ *                tackle fails; else fail = (x / 2.0)^6 + (|y| / 1.25)^6; with fail < 1 it succeeds when a uniform draw
+ *                (counter RNG: seed, global env id, cycle, player) is below 1 - fail.  Success, in PlayOn only: the ball is
+ *                pushed like a kick by 100 (1 - |dir| / 180) 0.027 (1 - 0.5 |angle of the ball in the body frame| / 180)
+ *                towards body + dir (dir clamped to +-180); it counts as a kick for last touch, kicked flags and offside.
+ *                Either way the player can do nothing for the next 10 cycles (its commands are ignored).  The foul flag of
+ *                the proto message is ignored (no cards).
+ *     catch      S2D_CMD_CATCH, goalkeepers only (player 0 of each team), PlayOn, not within 5 cycles (catch_ban_cycle) of
+ *                its last catch: succeeds (catch_probability 1) when the ball is inside the keeper's own penalty area
+ *                (|x| >= pitch_half_length - 16.5 on its side, |y| <= 20.16) and inside the catch rectangle - 1.2 long
+ *                (catch_area_l), 1.0 wide (catch_area_w), starting at the keeper and pointing to body + dir.  Then: FreeKick
+ *                for the keeper's side with the ball in the keeper's hands (at its position, at rest), last touch = its side.
+ *     Not modelled: fouls and cards, back tackles, the keeper carrying the ball with `move`, the stretched catch area.
  *     Heterogeneous player types: s2d_set_player_types.
  *   Reward (left team's view) per cycle: 10 * (goals by left - goals by right) + 0.01 * (ball x after physics - before).
  *   Observation: 120 floats = ball {x/52.5, y/34, vx/3, vy/3}, then per player {x/52.5, y/34, vx, vy, body/180}
  *   (absent players zero), then [114] play mode, [115] side awarded, [116] left score, [117] right score,
  *   [118] step_number / (2 * half_time_cycles), [119] 0.
- *   State buffer: s2d_state_bytes(cfg) = N * (np * 36 + 64) bytes (+ padding), plane-major (layout: DESIGN.md). */
+ *   Sums over the players of a match (kick pushes on the ball, collision proposals for the ball) are added as a 32-leaf
+ *   xor butterfly ((i, i^16), (i, i^8), ... ; leaf = player index, the others 0.0): part of the fp32 result.
+ *   State buffer: s2d_state_bytes(cfg) = Nr * (np * 36 + 80) bytes, Nr = N rounded up to 64; plane-major, match-minor
+ *   (layout: DESIGN.md). */
 
 /* action encodings (reach_ball_env.py:39-47, :53-85) */
 #define S2D_ACT_DISCRETE 0   /* uint8  [N][K]      Discrete(n): Dash(100, (a*360/n)%360-180) (+ kicks in SHOOT)  */
@@ -135,6 +160,19 @@ extern "C" {
 #define S2D_CMD_KICK_ONE_STEP 8 /* a,b = target x,y, c = first_speed  Body_KickOneStep  (:747-751, force_mode) */
 #define S2D_CMD_STOP_BALL 9     /*                                    Body_StopBall     (:753-754) */
 #define S2D_CMD_INTERCEPT 10    /*                                    Body_Intercept    (:742-745; save_recovery and face_point ignored) */
+/* FULLGAME only (ignored = no command elsewhere): */
+#define S2D_CMD_TACKLE 11       /* a = power_or_dir (a direction, deg)  Tackle            (:399-402; foul ignored) */
+#define S2D_CMD_CATCH 12        /* a = direction relative to the body   Catch             (:404-406; the proxy aims at the ball) */
+/* Body_SmartKick (:690-695): the kick that gives the ball `first_speed` towards the target, planned over more than one
+ * cycle when one kick cannot do it.  Stateless, decided anew every cycle:
+ *   release  if the acceleration it needs is within what max_power yields at the ball's current place: as KICK_ONE_STEP;
+ *   stage    else the ball is kicked to the staging point - on the line from where the player will be next cycle
+ *            (position + velocity) to the target, player_size + ball_size + 0.3 kickable_margin in front of it: the
+ *            acceleration asked for is staging point - (ball position + ball velocity), the power is clamped to
+ *            max_power.  If that acceleration is below 0.05 the ball IS staged: release with whatever max_power gives.
+ *            From the staging point (close, in front when the player faces the target) the kick rate is near its best
+ *            and the ball is slow: 2-3 cycles in all. */
+#define S2D_CMD_SMART_KICK 13   /* a,b = target x,y, c = first_speed    Body_SmartKick    (:690-695; first_speed_threshold, max_steps ignored) */
 
 /* Collision models (S2DConfig.collision_model).  rcssserver's Stadium::collisions repeats up to ten rounds in which every
  * overlapping pair proposes new positions, every object moves to the average of its proposals, and what collided gets

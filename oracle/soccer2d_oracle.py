@@ -321,6 +321,7 @@ def lower_goto(p: Player, tx: float, ty: float, dist_thr: float, max_power: floa
 
 
 CMD_TURN_TO_POINT, CMD_TURN_TO_BALL, CMD_TURN_TO_ANGLE, CMD_KICK_ONE_STEP, CMD_STOP_BALL, CMD_INTERCEPT = 5, 6, 7, 8, 9, 10
+CMD_TACKLE, CMD_CATCH, CMD_SMART_KICK = 11, 12, 13  # tackle / catch: FULLGAME only (tests/fullgame_twin.py)
 
 
 def inertia_factor(decay: float, n: int) -> float:
@@ -361,6 +362,27 @@ def lower_body_action(p: Player, b: Ball, c: int, a1: float, a2: float, a3: floa
         dir_diff = math.fabs(norm_deg(atan2_deg(dy, dx) - p.body))
         dist_ball = dist - sp.player_size - sp.ball_size
         rate = sp.kick_power_rate * (1.0 - 0.25 * dir_diff / 180.0 - 0.25 * dist_ball / sp.kickable_margin)
+        return CMD_KICK, f32(clamp(0.0, acc / rate, sp.max_power)), f32(norm_deg(atan2_deg(ay, ax) - p.body)), 0.0
+    if c == CMD_SMART_KICK:  # Body_SmartKick (idl/service.proto:690-695): release if one kick can do it, else stage
+        dx, dy = b.x - p.x, b.y - p.y
+        dist = hypot2(dx, dy)
+        if dist > sp.player_size + sp.ball_size + sp.kickable_margin:
+            return CMD_NONE, 0.0, 0.0, 0.0
+        first_speed = clamp(0.0, a3, sp.ball_speed_max)
+        th = math.radians(atan2_deg(a2 - b.y, a1 - b.x))
+        ax, ay = first_speed * math.cos(th) - b.vx, first_speed * math.sin(th) - b.vy
+        acc = hypot2(ax, ay)
+        dir_diff = math.fabs(norm_deg(atan2_deg(dy, dx) - p.body))
+        dist_ball = dist - sp.player_size - sp.ball_size
+        rate = sp.kick_power_rate * (1.0 - 0.25 * dir_diff / 180.0 - 0.25 * dist_ball / sp.kickable_margin)
+        if not acc <= sp.max_power * rate:
+            nx, ny = p.x + p.vx, p.y + p.vy
+            th = math.radians(atan2_deg(a2 - ny, a1 - nx))
+            d = sp.player_size + sp.ball_size + 0.3 * sp.kickable_margin
+            sax, say = ((nx + d * math.cos(th)) - b.x) - b.vx, ((ny + d * math.sin(th)) - b.y) - b.vy
+            if hypot2(sax, say) >= 0.05:  # (else it is staged already: release with what max_power gives)
+                ax, ay = sax, say
+                acc = hypot2(ax, ay)
         return CMD_KICK, f32(clamp(0.0, acc / rate, sp.max_power)), f32(norm_deg(atan2_deg(ay, ax) - p.body)), 0.0
     if c == CMD_INTERCEPT:
         reach0 = 0.8 * (sp.player_size + sp.ball_size + sp.kickable_margin)

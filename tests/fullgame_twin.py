@@ -11,6 +11,8 @@ from oracle import soccer2d_oracle as O
 
 FORM = [(-50, 0), (-36, -20), (-36, -7), (-36, 7), (-36, 20), (-20, -24), (-20, -8), (-20, 8), (-20, 24), (-9, -10), (-9, 10)]
 DROP_BALL_TIME, FREE_KICK_DIST, OFFSIDE_AREA = 100, 9.15, 2.5
+AFTER_GOAL_WAIT, TACKLE_CYCLES, CATCH_BAN, RNG_TACKLE = 50, 10, 5, 5
+PM_AfterGoal = 8
 
 
 class Match:
@@ -31,6 +33,16 @@ class Match:
         (self.step_number, self.cycle, self.episode, self.mode, self.side, self.timer, self.score_l, self.score_r,
          self.last_touch) = (int(x) for x in vec[k + 5:k + 14])
         self.ep_return, self.done_flag, self.offside = float(vec[k + 14]), int(vec[k + 15]), int(vec[k + 16])
+        self.tackle = [0] * n       # cycles each player still lies on the ground after a tackle
+        self.catch_ban = [0, 0]     # left / right goalkeeper
+
+    def set_extra(self, extra):
+        """[np tackle counters, catch ban left, catch ban right] (s2do_get_extra_fg)"""
+        self.tackle = [int(x) for x in extra[:self.n]]
+        self.catch_ban = [int(extra[self.n]), int(extra[self.n + 1])]
+
+    def extra(self):
+        return [float(x) for x in self.tackle + self.catch_ban]
 
     def vector(self):
         out = []
@@ -80,11 +92,60 @@ def cycle(m: Match, actions, sps, sp, seed: int, gid: int, goto_thr: float, half
     dead = m.mode != O.PM_PlayOn
     m.step_number += 1
     # ---- commands ----
+    stopped = m.mode == PM_AfterGoal  # the server's clock stands still: only turns work
+    pps = n // 2
     b.ax = b.ay = 0.0
     kick_l = kick_r = False
+    caught = -1
     for j, p in enumerate(m.players):
         p.kicked = False
+        raw = int(actions[j][0])
+        keeper = 0 if j == 0 else 1 if j == pps else -1
+        if not stopped and keeper >= 0 and m.catch_ban[keeper] > 0:
+            m.catch_ban[keeper] -= 1
+        if not stopped and m.tackle[j] > 0:  # on the ground after a tackle
+            m.tackle[j] -= 1
+            continue
+        if raw == O.CMD_TACKLE:
+            if stopped:
+                continue
+            th = math.radians(p.body)
+            dx, dy = b.x - p.x, b.y - p.y
+            rx, ry = dx * math.cos(th) + dy * math.sin(th), dy * math.cos(th) - dx * math.sin(th)
+            m.tackle[j] = TACKLE_CYCLES
+            ok = False
+            if rx > 0.0:
+                fail = (rx / 2.0) ** 6 + (abs(ry) / 1.25) ** 6
+                if fail < 1.0:
+                    ok = O.u32_to_unit(O.rng_block(seed, gid, m.cycle, RNG_TACKLE, j)[0]) < 1.0 - fail
+            if ok and not dead:
+                d = O.clamp(-180.0, float(actions[j][1]), 180.0)
+                eff = 100.0 * (1.0 - abs(d) / 180.0) * 0.027 * (1.0 - 0.5 * abs(O.atan2_deg(ry, rx)) / 180.0)
+                t2 = math.radians(p.body + d)
+                b.ax += eff * math.cos(t2)
+                b.ay += eff * math.sin(t2)
+                p.kicked = True
+                if p.side == O.SIDE_LEFT:
+                    kick_l = True
+                else:
+                    kick_r = True
+            continue
+        if raw == O.CMD_CATCH:
+            if stopped or dead or keeper < 0 or m.catch_ban[keeper] > 0:
+                continue
+            d = O.clamp(-180.0, float(actions[j][1]), 180.0)
+            th = math.radians(p.body + d)
+            dx, dy = b.x - p.x, b.y - p.y
+            rx, ry = dx * math.cos(th) + dy * math.sin(th), dy * math.cos(th) - dx * math.sin(th)
+            edge = sp.pitch_half_length - 16.5
+            in_area = (b.x <= -edge if keeper == 0 else b.x >= edge) and abs(b.y) <= 20.16
+            if 0.0 <= rx <= 1.2 and abs(ry) <= 0.5 and in_area:
+                caught = j
+                m.catch_ban[keeper] = CATCH_BAN
+            continue
         cmd, power, direction = decode(p, b, actions[j], goto_thr, sps[j])
+        if stopped and cmd != O.CMD_TURN:
+            continue
         if cmd == O.CMD_DASH:
             O.cmd_dash(p, power, direction, sps[j])
         elif cmd == O.CMD_TURN:
@@ -100,6 +161,9 @@ def cycle(m: Match, actions, sps, sp, seed: int, gid: int, goto_thr: float, half
     mode_at_kick = m.mode
     if dead and ((m.side == O.SIDE_LEFT and kick_l) or (m.side == O.SIDE_RIGHT and kick_r)):
         m.mode, dead = O.PM_PlayOn, False
+    if caught >= 0:  # the goalkeeper holds the ball: free kick for its side
+        keeper_side = m.players[caught].side
+        m.mode, m.side, m.timer, m.last_touch, dead = O.PM_FreeKick, keeper_side, 0, keeper_side, True
     # ---- offside marks ----
     if (kick_l or kick_r) and not dead:
         m.offside = 0
@@ -116,13 +180,24 @@ def cycle(m: Match, actions, sps, sp, seed: int, gid: int, goto_thr: float, half
     # ---- move ----
     pbx, pby = b.x, b.y
     for j, p in enumerate(m.players):
-        O.obj_inc(p, sp.player_accel_max, sp.player_speed_max, sps[j].player_decay)
+        if stopped:
+            p.vx = p.vy = p.ax = p.ay = 0.0
+        else:
+            O.obj_inc(p, sp.player_accel_max, sp.player_speed_max, sps[j].player_decay)
     if not dead:
         O.obj_inc(b, sp.ball_accel_max, sp.ball_speed_max, sp.ball_decay)
     else:
         b.vx = b.vy = b.ax = b.ay = 0.0
+    if caught >= 0:
+        b.x, b.y = m.players[caught].x, m.players[caught].y
+    # ---- kick-off: everybody in its own half ----
+    if m.mode == O.PM_KickOff:
+        for p in m.players:
+            if (p.x > 0.0) if p.side == O.SIDE_LEFT else (p.x < 0.0):
+                p.x = -sp.player_size if p.side == O.SIDE_LEFT else sp.player_size
+                p.vx = p.vy = 0.0
     # ---- dead-ball clearance ----
-    if dead and m.mode != O.PM_TimeOver:
+    if dead and m.mode not in (O.PM_TimeOver, PM_AfterGoal):
         for p in m.players:
             if p.side == m.side:
                 continue
@@ -133,7 +208,13 @@ def cycle(m: Match, actions, sps, sp, seed: int, gid: int, goto_thr: float, half
                 ux, uy = ((-1.0 if p.side == O.SIDE_LEFT else 1.0), 0.0) if c < 1.0e-6 else (cx / c, cy / c)
                 p.x, p.y, p.vx, p.vy = b.x + ux * FREE_KICK_DIST, b.y + uy * FREE_KICK_DIST, 0.0, 0.0
     # ---- collisions (a dead ball takes no part) ----
-    touched = collide(m, sp, dead, collision_model)
+    if stopped:  # nothing moves, so nothing is pushed apart either
+        touched = [False] * n
+        b.collided = False
+        for p in m.players:
+            p.collided = False
+    else:
+        touched = collide(m, sp, dead, collision_model)
     hit_l = any(t and p.side == O.SIDE_LEFT for t, p in zip(touched, m.players))
     hit_r = any(t and p.side == O.SIDE_RIGHT for t, p in zip(touched, m.players))
     if hit_l != hit_r:
@@ -171,9 +252,9 @@ def cycle(m: Match, actions, sps, sp, seed: int, gid: int, goto_thr: float, half
                 m.score_l += 1
             else:
                 m.score_r += 1
-            place_formation(m, seed, gid)
-            m.mode, m.timer, m.last_touch = O.PM_KickOff, 0, O.SIDE_UNKNOWN
-            m.side = O.SIDE_RIGHT if goal_l else O.SIDE_LEFT
+            m.mode, m.timer, m.last_touch = PM_AfterGoal, 0, O.SIDE_UNKNOWN
+            m.side = O.SIDE_LEFT if goal_l else O.SIDE_RIGHT  # AfterGoal_ + the scoring side
+            b.vx = b.vy = 0.0
         elif abs(bx) > line:
             defending = O.SIDE_RIGHT if bx > 0.0 else O.SIDE_LEFT
             sx, sy = (1.0 if bx > 0.0 else -1.0), (1.0 if by > 0.0 else -1.0)
@@ -195,13 +276,19 @@ def cycle(m: Match, actions, sps, sp, seed: int, gid: int, goto_thr: float, half
             m.timer = 0
     else:
         m.timer += 1
-        if m.timer >= DROP_BALL_TIME:
+        if m.mode == PM_AfterGoal:
+            if m.timer >= AFTER_GOAL_WAIT:  # kick-off for the side that conceded
+                place_formation(m, seed, gid)
+                m.mode, m.timer = O.PM_KickOff, 0
+                m.side = O.SIDE_RIGHT if m.side == O.SIDE_LEFT else O.SIDE_LEFT
+        elif m.timer >= DROP_BALL_TIME:
             m.mode, m.timer = O.PM_PlayOn, 0
     if m.mode != O.PM_PlayOn:
         m.offside = 0
-    for j, p in enumerate(m.players):
-        O.update_stamina(p, sps[j])
-    m.cycle += 1
+    if not stopped:
+        for j, p in enumerate(m.players):
+            O.update_stamina(p, sps[j])
+        m.cycle += 1
     reward = (goal_l - goal_r) * 10.0 + (O.f32(bx_phys) - O.f32(pbx)) * 0.01
     done = m.step_number >= 2 * half_time
     result = 0 if not done else 1 if m.score_l > m.score_r else 2 if m.score_r > m.score_l else 3

@@ -57,7 +57,7 @@ def random_commands(rng, n, k=1, body_actions=True):
     proxy's turn-to-point / -ball / -angle, kick-one-step, stop-ball and intercept, with out-of-range arguments now and then
     (the clamps are part of the contract)."""
     a = np.zeros((n, k, 4), np.float32)
-    menu = [0, 1, 1, 1, 2, 3, 3, 4, 4] + ([5, 6, 7, 8, 8, 9, 10, 10, 12] if body_actions else [])
+    menu = [0, 1, 1, 1, 2, 3, 3, 4, 4] + ([5, 6, 7, 8, 8, 9, 10, 10, 11, 12, 13, 13, 14] if body_actions else [])
     cmd = rng.choice(menu, size=(n, k))
     a[..., 0] = cmd
     dash, turn, kick, goto = cmd == 1, cmd == 2, cmd == 3, cmd == 4
@@ -67,7 +67,9 @@ def random_commands(rng, n, k=1, body_actions=True):
     a[..., 1] = np.where(goto, rng.uniform(-55, 55, (n, k)), a[..., 1])
     a[..., 2] = np.where(goto, rng.uniform(-36, 36, (n, k)), a[..., 2])
     a[..., 3] = np.where(goto, rng.uniform(20, 120, (n, k)), a[..., 3])
-    to_point, to_ball, to_angle, one_step = cmd == 5, cmd == 6, cmd == 7, cmd == 8
+    to_point, to_ball, to_angle, one_step = cmd == 5, cmd == 6, cmd == 7, (cmd == 8) | (cmd == 13)  # 13: smart kick
+    tackle_or_catch = (cmd == 11) | (cmd == 12)  # (14 does not exist: no command)
+    a[..., 1] = np.where(tackle_or_catch, rng.uniform(-200, 200, (n, k)), a[..., 1])
     a[..., 1] = np.where(to_point | one_step, rng.uniform(-55, 55, (n, k)), a[..., 1])
     a[..., 2] = np.where(to_point | one_step, rng.uniform(-36, 36, (n, k)), a[..., 2])
     a[..., 3] = np.where(to_point, rng.integers(-2, 70, (n, k)), a[..., 3])

@@ -84,6 +84,8 @@ def lib(kind: str):
         L.s2do_obs_dim.argtypes = [C.c_void_p]
         L.s2do_get_state_fg.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
         L.s2do_set_state_fg.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
+        L.s2do_get_extra_fg.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
+        L.s2do_set_extra_fg.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
         L.s2do_set_ball_fg.argtypes = [C.c_void_p, C.c_int64] + [C.c_double] * 4 + [C.c_int] * 3
         L.s2do_set_player_fg.argtypes = [C.c_void_p, C.c_int64, C.c_int] + [C.c_double] * 5
         L.s2do_generate_player_types.restype = C.c_int
@@ -175,6 +177,19 @@ class OracleSim:
         out = np.zeros(np_ * 12 + 17, np.float64)
         assert self.L.s2do_get_state_fg(self.h, int(i), _ptr(out)) == out.size
         return out
+
+    def get_extra_fg(self, i=None):
+        """FULLGAME: [np tackle counters, catch ban of the left keeper, of the right keeper] per env"""
+        if i is None:
+            return np.stack([self.get_extra_fg(j) for j in range(self.n)])
+        out = np.zeros(2 * int(self.cfg.players_per_side) + 2, np.float64)
+        assert self.L.s2do_get_extra_fg(self.h, int(i), _ptr(out)) == out.size
+        return out
+
+    def set_extra_fg(self, extras):
+        ex = np.ascontiguousarray(extras, dtype=np.float64)
+        for i in range(self.n):
+            self.L.s2do_set_extra_fg(self.h, i, _ptr(ex[i]))
 
     def set_state_fg(self, states):
         """FULLGAME: overwrite every env's state from an [N, np*12+17] array (layout of get_state_fg)."""

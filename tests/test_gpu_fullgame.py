@@ -68,6 +68,31 @@ def gpu_state_fg(env):
     return out
 
 
+def gpu_extra_fg(env):
+    """[N, np + 2]: tackle counters per player, catch bans of the two keepers (layout of s2do_get_extra_fg)"""
+    ek = env.fullgame_planes()["ek"].cpu().numpy().astype(np.int64) & 0xFFFFFFFF
+    n, p = env.num_envs, env.num_players
+    out = np.zeros((n, p + 2))
+    for j in range(p):
+        out[:, j] = (ek[:, j >> 3] >> (4 * (j & 7))) & 15
+    out[:, p], out[:, p + 1] = ek[:, 3] & 15, (ek[:, 3] >> 4) & 15
+    return out
+
+
+def set_gpu_extra_fg(env, extra):
+    n, p = env.num_envs, env.num_players
+    ek = np.zeros((n, 4), np.int64)
+    for j in range(p):
+        ek[:, j >> 3] |= extra[:, j].astype(np.int64) << (4 * (j & 7))
+    ek[:, 3] = extra[:, p].astype(np.int64) | (extra[:, p + 1].astype(np.int64) << 4)
+    env.fullgame_planes()["ek"].copy_(torch.from_numpy(ek.astype(np.uint32).view(np.int32)))
+
+
+def same_state(env, sim):
+    assert np.array_equal(gpu_state_fg(env), sim.get_state_fg())
+    assert np.array_equal(gpu_extra_fg(env), sim.get_extra_fg())
+
+
 def same_step(env, sim):
     assert np.array_equal(env.done_u8.cpu().numpy(), sim.done) and np.array_equal(env.result.cpu().numpy(), sim.result)
     assert np.array_equal(env.obs.cpu().numpy(), sim.obs)
@@ -100,8 +125,8 @@ def test_fullgame_bit_exact_against_fp32_oracle(pps, k, default_sp, collision_mo
         same_step(env, sim)
         modes |= set(sim.obs[:, 114].astype(int).tolist())
         if t % 25 == 24:
-            assert np.array_equal(gpu_state_fg(env), sim.get_state_fg())
-    assert np.array_equal(gpu_state_fg(env), sim.get_state_fg())
+            same_state(env, sim)
+    same_state(env, sim)
     st, so = env.stats(), sim.stats(_abi.Stats())
     for key in ("episodes", "goals", "outs", "timeouts", "episode_steps", "env_steps"):
         assert st[key] == getattr(so, key), key
@@ -110,6 +135,64 @@ def test_fullgame_bit_exact_against_fp32_oracle(pps, k, default_sp, collision_mo
     assert _abi.RESULT_NAMES and {2, 3} <= modes  # PlayOn and KickOff at least
     total_goals = int(sim.get_state_fg()[:, p * 12 + 11:p * 12 + 13].sum())
     assert total_goals >= 0
+
+
+def rules_policy(obs, rng):
+    """11 v 11 with the whole vocabulary: run to the ball, SmartKick it at the other goal, tackle it off an opponent's
+    foot, keepers catch what comes close"""
+    obs = np.asarray(obs, np.float64)
+    n = obs.shape[0]
+    a = np.zeros((n, 1, 22, 4), np.float32)
+    bx, by = obs[:, 0] * 52.5, obs[:, 1] * 34.0
+    P = obs[:, 4:114].reshape(n, 22, 5)
+    px, py, body = P[:, :, 0] * 52.5, P[:, :, 1] * 34.0, P[:, :, 4] * 180.0
+    dx, dy = bx[:, None] - px, by[:, None] - py
+    d = np.hypot(dx, dy)
+    rel = (np.degrees(np.arctan2(dy, dx)) - body + 180.0) % 360.0 - 180.0
+    gx = np.where(np.arange(22) < 11, 52.5, -52.5)[None, :] * np.ones((n, 1))
+    near = d < 1.0
+    a[:, 0, :, 0] = np.where(near, 13, 4)                      # SmartKick | GoToPoint
+    a[:, 0, :, 1] = np.where(near, gx, bx[:, None])
+    a[:, 0, :, 2] = np.where(near, rng.uniform(-5, 5, (n, 22)), by[:, None])
+    a[:, 0, :, 3] = np.where(near, 2.8, 100.0)
+    tackle = (d < 1.9) & ~near & (np.abs(rel) < 60) & (rng.uniform(size=(n, 22)) < 0.5)
+    a[:, 0, :, 0] = np.where(tackle, 11, a[:, 0, :, 0])
+    a[:, 0, :, 1] = np.where(tackle, np.rint(rng.uniform(-90, 90, (n, 22))), a[:, 0, :, 1])
+    for kpr in (0, 11):                                           # the keepers stay home and catch
+        home = np.stack([np.full(n, -48.0 if kpr == 0 else 48.0), np.clip(by, -6, 6)], axis=1)
+        a[:, 0, kpr] = np.stack([np.full(n, 4.0), home[:, 0], home[:, 1], np.full(n, 100.0)], axis=1)
+        reach = d[:, kpr] < 1.3
+        a[reach, 0, kpr] = np.stack([np.full(reach.sum(), 12.0), np.rint(rel[reach, kpr]), np.zeros(reach.sum()), np.zeros(reach.sum())], axis=1)
+    return a
+
+
+@pytest.mark.parametrize("k", [1, 3])
+def test_fullgame_tackles_catches_smart_kicks_and_the_goal_pause_bit_exact(k):
+    """round 2 rules (include/soccer2d.h): tackle, goalkeeper catch, Body_SmartKick, the AfterGoal pause and the kick-off
+    confinement, in a match where all of them happen - GPU against the fp32 oracle, bit for bit."""
+    n = 96
+    env = Soccer2DVecEnv(n, scenario="fullgame", device="cuda:0", seed=9, substeps=k, terminal_obs=True, half_time_cycles=300)
+    sim = OL.OracleSim(env.cfg, "f32")
+    assert np.array_equal(env.reset(), sim.reset())
+    rng = np.random.default_rng(2)
+    modes, floored, bans = set(), 0, 0
+    for t in range(900 // k):
+        act = np.repeat(rules_policy(sim.obs, rng), k, axis=1)
+        env.step_torch(torch.from_numpy(act))
+        sim.step(act.reshape(n, -1), k)
+        same_step(env, sim)
+        modes |= set(sim.obs[:, 114].astype(int).tolist())
+        if t % 10 == 9:
+            same_state(env, sim)
+            ex = gpu_extra_fg(env)
+            floored += int((ex[:, :22] > 0).sum())
+            bans += int((ex[:, 22:] > 0).sum())
+    same_state(env, sim)
+    assert {2, 3, 5, 8} <= modes, sorted(modes)  # play on, kick-off, free kick (catch / offside), after goal
+    assert floored > 0 and bans > 0, (floored, bans)
+    st, so = env.stats(), sim.stats(_abi.Stats())
+    assert st["episodes"] == so.episodes > 0
+    env.close()
 
 
 @pytest.mark.parametrize("noise", [False, True])
@@ -147,8 +230,8 @@ def test_fullgame_heterogeneous_players_bit_exact(noise):
     # back to homogeneous players: identical to a handle that never had types
     env.lib.s2d_set_player_types(env.handle, None, 0, None)
     env.reset()
-    plain.reset()
-    # (episode counters differ from a fresh handle only if resets differ: both were reset the same number of times)
+    plain.state.copy_(env.state)  # the same matches (the two have paused for different goals: their server clocks differ)
+    plain.obs.copy_(env.obs)
     for t in range(5):
         act = np.repeat(swarm_policy(plain.obs.cpu().numpy(), 22, rng, random_frac=0.15), k, axis=1)
         a = torch.from_numpy(act)
@@ -214,8 +297,8 @@ def test_fullgame_referee_and_collision_cases():
     mode, side, sl, sr = g[:, k + 8], g[:, k + 9], g[:, k + 11], g[:, k + 12]
     assert (mode[0], side[0]) == (_abi_pm("KICK_IN"), 2) and (mode[1], side[1]) == (_abi_pm("KICK_IN"), 1)
     assert (mode[2], side[2]) == (_abi_pm("CORNER_KICK"), 1) and (mode[3], side[3]) == (_abi_pm("GOAL_KICK"), 2)
-    assert (mode[4], side[4], sl[4], sr[4]) == (_abi_pm("KICK_OFF"), 2, 1, 0)
-    assert (mode[5], side[5], sl[5], sr[5]) == (_abi_pm("KICK_OFF"), 1, 0, 1)
+    assert (mode[4], side[4], sl[4], sr[4]) == (_abi_pm("AFTER_GOAL"), 1, 1, 0)  # AfterGoal_ + the side that scored
+    assert (mode[5], side[5], sl[5], sr[5]) == (_abi_pm("AFTER_GOAL"), 2, 0, 1)
     assert mode[6] == _abi_pm("KICK_IN") and not g[6, 12 * 12 + 10]  # still a dead ball, no kick registered
     assert g[8, 1 * 12 + 9] and g[8, 13 * 12 + 9] and g[8, 2 * 12 + 9]  # collided flags
     assert g[9, k + 4] == 1  # ball collided
@@ -235,6 +318,9 @@ def test_fullgame_referee_and_collision_cases():
     g = gpu_state_fg(env)
     assert np.array_equal(g, sim.get_state_fg())
     assert g[7, k + 8] == _abi_pm("PLAY_ON")  # dropped after 100 cycles
+    # the goals: 50 stopped cycles (the server clock did not advance), then the kick-off for the side that conceded
+    assert (g[4, k + 8], g[4, k + 9]) == (_abi_pm("KICK_OFF"), 2) and (g[5, k + 8], g[5, k + 9]) == (_abi_pm("KICK_OFF"), 1)
+    assert g[4, k + 6] == g[0, k + 6] - 50 and g[4, k + 10] == 60  # cycle; the kick-off has been waiting for 60 cycles
     snap = env.export_env(4)
     assert (snap.left_score, snap.right_score, snap.num_players) == (1, 0, 22)
     assert snap.players[11].side == 2 and snap.players[11].uniform_number == 1
@@ -438,7 +524,14 @@ def test_fullgame_random_states_bit_exact(collision_model):
             P[:, 7] = rng.uniform(0.5, 1.0, p)
             P[:, 0:9] = P[:, 0:9].astype(np.float32)
             P[:, 9:11] = 0
-            mode = int(rng.choice([2, 2, 2, 3, 4, 5, 6, 7]))
+            mode = int(rng.choice([2, 2, 2, 3, 4, 5, 6, 7, 8]))
+            if rng.uniform() < 0.15:  # the ball in front of a goalkeeper, inside its penalty area
+                side = int(rng.integers(0, 2))
+                P[11 * side, 0:2] = np.float32([(-1) ** (side + 1) * rng.uniform(40, 50), rng.uniform(-15, 15)])
+                P[11 * side, 4] = np.float32(rng.uniform(-180, 180))
+                th = np.radians(P[11 * side, 4]) + rng.uniform(-0.3, 0.3)
+                d = rng.uniform(0.2, 1.4)
+                st[i, k:k + 2] = np.float32([P[11 * side, 0] + d * np.cos(th), P[11 * side, 1] + d * np.sin(th)])
             st[i, k + 4] = 0
             st[i, k + 5] = rnd
             st[i, k + 8:k + 11] = [mode, int(rng.integers(1, 3)) if mode != 2 else 0, int(rng.choice([0, 5, 98, 99]))]
@@ -448,14 +541,22 @@ def test_fullgame_random_states_bit_exact(collision_model):
             st[i, k + 16] = int(rng.integers(0, 1 << 11)) << (11 * int(rng.integers(0, 2))) if mode == 2 and rng.uniform() < 0.5 else 0
         sim.set_state_fg(st)
         set_gpu_state_fg(env, st)
-        assert np.array_equal(gpu_state_fg(env), sim.get_state_fg())
+        extra = np.zeros((n, p + 2))
+        extra[:, :p] = np.where(rng.uniform(size=(n, p)) < 0.1, rng.integers(1, 11, (n, p)), 0)  # some lie on the ground
+        extra[:, p:] = np.where(rng.uniform(size=(n, 2)) < 0.2, rng.integers(1, 6, (n, 2)), 0)
+        sim.set_extra_fg(extra)
+        set_gpu_extra_fg(env, extra)
+        same_state(env, sim)
         act = H.random_commands(rng, n * p).reshape(n, 1, p, 4)
         act[:, 0, :, 0] = np.where(rng.uniform(size=(n, p)) < 0.3, 3, act[:, 0, :, 0])
+        act[:, 0, :, 0] = np.where(rng.uniform(size=(n, p)) < 0.1, 11, act[:, 0, :, 0])  # tackles into the pile-up
+        act[:, 0, 0, 0] = np.where(rng.uniform(size=n) < 0.5, 12, act[:, 0, 0, 0])     # the keepers try to catch
+        act[:, 0, 11, 0] = np.where(rng.uniform(size=n) < 0.5, 12, act[:, 0, 11, 0])
         env.step_torch(torch.from_numpy(act))
         sim.step(act.reshape(n, -1))
         same_step(env, sim)
+        same_state(env, sim)
         g = gpu_state_fg(env)
-        assert np.array_equal(g, sim.get_state_fg())
         modes_after |= set(g[:, k + 8].astype(int).tolist())
-    assert {2, 3, 4, 5, 6, 7} <= modes_after
+    assert {2, 4, 5, 6, 7, 8} <= modes_after  # (a goal is followed by the 50-cycle pause now: kick-off is not reached in one cycle)
     env.close()

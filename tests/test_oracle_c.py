@@ -296,7 +296,7 @@ def test_fullgame_invariants_with_player_types_and_referee():
     emax = np.array([types[t].effort_max for t in type_of])
     emin = np.array([types[t].effort_min for t in type_of])
     k = p * 12
-    seen_modes, offside_calls, marks_seen = set(), 0, 0
+    seen_modes, offside_calls, marks_seen, pauses, prev = set(), 0, 0, 0, None
     for t in range(400):
         act = swarm_policy(sim.obs, p, rng, random_frac=0.2)
         sim.step(act.reshape(n, -1))
@@ -310,8 +310,22 @@ def test_fullgame_invariants_with_player_types_and_referee():
         assert (np.abs(P[:, :, 4]) <= 180.0).all()
         mode, side, marks = s[:, k + 8].astype(int), s[:, k + 9].astype(int), s[:, k + 16].astype(np.int64)
         seen_modes |= set(mode.tolist())
-        dead = (mode != 2) & (mode != 1)
+        dead = (mode != 2) & (mode != 1) & (mode != 8)
         assert (np.abs(s[dead, k]) <= 52.5 + 1e-9).all() and (np.abs(s[dead, k + 1]) <= 34.0 + 1e-9).all()
+        paused = mode == 8  # AfterGoal: the ball lies in the goal, the clock stands still and nothing moves
+        assert (np.abs(s[paused, k]) > 52.5).all() and (s[paused, k + 2:k + 4] == 0).all()
+        if prev is not None:
+            still = paused & (prev[:, k + 8] == 8)
+            assert np.array_equal(s[still][:, :k].reshape(-1, p, 12)[:, :, 0:2], prev[still][:, :k].reshape(-1, p, 12)[:, :, 0:2])
+            assert np.array_equal(s[still, k + 6], prev[still, k + 6]) and (s[still, k + 10] == prev[still, k + 10] + 1).all()
+            kicked_off = (mode == 3) & (prev[:, k + 8] == 8) & (s[:, k + 7] == prev[:, k + 7])  # ... for 50 cycles, then the kick-off
+            assert (prev[kicked_off, k + 10] == 49).all() and (side[kicked_off] != prev[kicked_off, k + 9]).all()
+            pauses += int(kicked_off.sum())
+        if (mode == 3).any():  # kick-off: everybody in its own half
+            ko = mode == 3
+            # (put back at -+player_size; a player-player collision may then push by < 0.6)
+            assert (P[ko][:, :11, 0] <= 0.61).all() and (P[ko][:, 11:, 0] >= -0.61).all()
+        prev = s
         assert (marks[mode != 2] == 0).all()
         left_bits, right_bits = marks & 0x7FF, marks >> 11
         assert ((left_bits == 0) | (right_bits == 0)).all()
@@ -322,6 +336,7 @@ def test_fullgame_invariants_with_player_types_and_referee():
             assert (d >= 9.15 - 0.61).all()  # (placed on the circle; a player-player collision may then push by < 0.6)
         offside_calls += int(((mode == 5) & (s[:, k + 10] == 0)).sum())
     assert {2, 3} <= seen_modes and marks_seen > 0
+    assert 8 in seen_modes and pauses > 0, sorted(seen_modes)  # goals were scored and waited out
 
 
 @pytest.mark.parametrize("collision_model", [0, 1])
@@ -358,18 +373,20 @@ def test_fullgame_c_oracle_equals_an_independent_python_twin(collision_model):
                             [52.5, 34.0, 3.0, 3.0, 1], np.ones(12)])
     modes, calls, goals = set(), 0, 0
     for t in range(300):
-        before = sim.get_state_fg()
+        before, extra_before = sim.get_state_fg(), sim.get_extra_fg()
         act = swarm_policy(sim.obs, p, rng, random_frac=0.25)
         sim.step(act.reshape(n, -1))
-        after = sim.get_state_fg()
+        after, extra_after = sim.get_state_fg(), sim.get_extra_fg()
         for i in range(n):
             m = T.Match(before[i].tolist(), p)
+            m.set_extra(extra_before[i])
             rw, done, res = T.cycle(m, act[i, 0], sps, base, int(cfg.seed), int(cfg.env_id_offset) + i,
                                     float(np.float32(cfg.goto_dist_thr)), half, collision_model)
             assert done == bool(sim.done[i]) and res == int(sim.result[i]), (t, i)
             assert rw == pytest.approx(float(sim.reward[i]), abs=1e-9), (t, i)
             if done:
                 continue  # (the C side has already started the next match)
+            assert m.extra() == extra_after[i].tolist(), (t, i)
             m.ep_return += rw
             got = np.array(m.vector())
             err = np.abs(got - after[i]) / scale
@@ -420,7 +437,14 @@ def test_fullgame_c_oracle_equals_the_twin_on_random_states(collision_model):
             P[:, 5] = rng.uniform(0, 8000, p)
             P[:, 6] = rng.uniform(0.6, 1.0, p)
             P[:, 7] = rng.uniform(0.5, 1.0, p)
-            mode = int(rng.choice([2, 2, 2, 3, 4, 5, 6, 7]))
+            mode = int(rng.choice([2, 2, 2, 3, 4, 5, 6, 7, 8]))
+            if rng.uniform() < 0.15:  # the ball in front of a goalkeeper, inside its penalty area
+                side = int(rng.integers(0, 2))
+                P[11 * side, 0:2] = [(-1) ** (side + 1) * rng.uniform(40, 50), rng.uniform(-15, 15)]
+                P[11 * side, 4] = rng.uniform(-180, 180)
+                th = np.radians(P[11 * side, 4]) + rng.uniform(-0.3, 0.3)
+                d = rng.uniform(0.2, 1.4)
+                st[i, k:k + 2] = [P[11 * side, 0] + d * np.cos(th), P[11 * side, 1] + d * np.sin(th)]
             st[i, k + 5] = rnd  # step_number
             st[i, k + 8:k + 11] = [mode, int(rng.integers(1, 3)) if mode != 2 else 0, int(rng.choice([0, 5, 98, 99]))]
             st[i, k + 13] = int(rng.integers(0, 3))  # last touch
@@ -428,14 +452,23 @@ def test_fullgame_c_oracle_equals_the_twin_on_random_states(collision_model):
             marks = int(rng.integers(0, 1 << 11)) << (11 * int(rng.integers(0, 2))) if mode == 2 and rng.uniform() < 0.5 else 0
             st[i, k + 16] = marks
         sim.set_state_fg(st)
+        extra = np.zeros((n, p + 2))
+        extra[:, :p] = np.where(rng.uniform(size=(n, p)) < 0.1, rng.integers(1, 11, (n, p)), 0)  # some lie on the ground
+        extra[:, p:] = np.where(rng.uniform(size=(n, 2)) < 0.2, rng.integers(1, 6, (n, 2)), 0)
+        sim.set_extra_fg(extra)
         before = sim.get_state_fg()
         act = H.random_commands(rng, n * p).reshape(n, 1, p, 4)
         act[:, 0, :, 0] = np.where(rng.uniform(size=(n, p)) < 0.3, 3, act[:, 0, :, 0])  # more kicks
+        act[:, 0, :, 0] = np.where(rng.uniform(size=(n, p)) < 0.1, 11, act[:, 0, :, 0])  # tackles into the pile-up
+        act[:, 0, 0, 0] = np.where(rng.uniform(size=n) < 0.5, 12, act[:, 0, 0, 0])     # the keepers try to catch
+        act[:, 0, 11, 0] = np.where(rng.uniform(size=n) < 0.5, 12, act[:, 0, 11, 0])
         sim.step(act.reshape(n, -1))
-        after = sim.get_state_fg()
+        after, extra_after = sim.get_state_fg(), sim.get_extra_fg()
         for i in range(n):
             m = T.Match(before[i].tolist(), p)
+            m.set_extra(extra[i])
             rw, done, res = T.cycle(m, act[i, 0], sps, base, int(cfg.seed), i, 0.5, half, collision_model)
+            assert m.extra() == extra_after[i].tolist(), (rnd, i)
             assert not done and rw == pytest.approx(float(sim.reward[i]), abs=1e-9), (rnd, i)
             m.ep_return += rw
             err = np.abs(np.array(m.vector()) - after[i]) / scale
@@ -444,7 +477,9 @@ def test_fullgame_c_oracle_equals_the_twin_on_random_states(collision_model):
             assert err.max() < 1e-9, (rnd, i, j, m.vector()[j], after[i][j], int(before[i][k + 8]))
             seen.add((int(before[i][k + 8]), m.mode))
     modes_after = {b for _, b in seen}
-    assert {2, 3, 4, 5, 6, 7} <= modes_after, sorted(seen)  # play on, kick-off (goal), kick-in, free kick (offside), corner, goal kick
+    # play on, kick-off (after the goal pause), kick-in, free kick (offside / catch), corner, goal kick, after goal
+    assert {2, 4, 5, 6, 7, 8} <= modes_after, sorted(seen)
+    assert (2, 8) in seen and (8, 8) in seen, sorted(seen)  # a goal stops the clock, and it stays stopped
 
 
 def test_oracle_config_mirror_matches_the_product_struct_and_defaults():

@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -35,6 +36,7 @@ struct S2DSim {
   cudaEvent_t ev_user = nullptr;  // end of the last caller-stream operation that touched the shared state
   bool used[S2D_MAX_PIPELINE_SLOTS] = {false, false, false, false};
   bool user_pending = false;
+  int fg_lanes_per_match = 0;  // FULLGAME: 0 = chosen by the shard size (launch_step); S2D_FG_LANES overrides (tuning)
   int last_d2h_copies = 0;  // device-to-host copies the last host-buffer step issued (1 = the packed block)
   int grid = 0;
   uint64_t env_steps = 0;
@@ -214,6 +216,10 @@ int s2d_create(const S2DConfig* cfg, S2DHandle* out) {
     return S2D_ERR_CUDA;
   }
   kp.action_table = h->d_table;
+  if (const char* v = getenv("S2D_FG_LANES")) {  // tuning aid: lanes per match of the 11 v 11 kernel (1, 2)
+    const int l = atoi(v);
+    if (l == 1 || l == 2) h->fg_lanes_per_match = l;
+  }
   h->grid = cfg->scenario == S2D_SCENARIO_FULLGAME ? static_cast<int>((cfg->num_envs + kFgBlock - 1) / kFgBlock)  // thread = match
                                                    : static_cast<int>((cfg->num_envs + kBlock - 1) / kBlock);
   *out = h;
@@ -378,14 +384,26 @@ static cudaError_t launch_step(S2DSim* h, const KernelParams& kp, int k_substeps
   } while (0)
   if (h->cfg.scenario == S2D_SCENARIO_FULLGAME) {
     const int np = 2 * h->cfg.players_per_side, ht = h->cfg.half_time_cycles;
-    if (h->hetero && h->cfg.noise) fullgame_step_kernel<kVarHeteroNoisy, 0><<<h->grid, kFgBlock, 0, s>>>(kp, k_substeps, np, ht);
-    else if (h->hetero && np == 22) fullgame_step_kernel<kVarHetero, 22><<<h->grid, kFgBlock, 0, s>>>(kp, k_substeps, np, ht);
-    else if (h->hetero) fullgame_step_kernel<kVarHetero, 0><<<h->grid, kFgBlock, 0, s>>>(kp, k_substeps, np, ht);
-    else if (h->cfg.noise) fullgame_step_kernel<kVarNoisy, 0><<<h->grid, kFgBlock, 0, s>>>(kp, k_substeps, np, ht);
-    else if (!h->default_sp && np == 22) fullgame_step_kernel<kVarRuntime, 22><<<h->grid, kFgBlock, 0, s>>>(kp, k_substeps, np, ht);
-    else if (!h->default_sp) fullgame_step_kernel<kVarRuntime, 0><<<h->grid, kFgBlock, 0, s>>>(kp, k_substeps, np, ht);
-    else if (np == 22) fullgame_step_kernel<kVarDefault, 22><<<h->grid, kFgBlock, 0, s>>>(kp, k_substeps, np, ht);
-    else fullgame_step_kernel<kVarDefault, 0><<<h->grid, kFgBlock, 0, s>>>(kp, k_substeps, np, ht);
+    // One thread per match fills the GPU from about 10^5 matches on (148 SMs x 20 warps x 32).  A small shard is bound
+    // by the latency of its slowest warp; two lanes sharing a match shorten the player loop (measured on 2^18 matches in
+    // total: 45 -> 41 us per cycle at 32 K matches per GPU; no gain from 64 K on, none from four lanes: profiles/README.md).
+    const int64_t nr = static_cast<int64_t>(FgLayout{h->cfg.num_envs, np}.nr());
+    const int lpm = h->fg_lanes_per_match > 0 ? h->fg_lanes_per_match : nr <= 49152 ? 2 : 1;
+    const int g1 = static_cast<int>(nr / kFgBlock);
+#define S2D_FG(VAR)                                                                                          \
+  do {                                                                                                       \
+    if (lpm == 2) fullgame_step_kernel<VAR, 22, 2><<<g1 * 2, kFgBlock, 0, s>>>(kp, k_substeps, np, ht);      \
+    else fullgame_step_kernel<VAR, 22, 1><<<g1, kFgBlock, 0, s>>>(kp, k_substeps, np, ht);                   \
+  } while (0)
+    if (h->hetero && h->cfg.noise) fullgame_step_kernel<kVarHeteroNoisy, 0, 1><<<g1, kFgBlock, 0, s>>>(kp, k_substeps, np, ht);
+    else if (h->hetero && np == 22) fullgame_step_kernel<kVarHetero, 22, 1><<<g1, kFgBlock, 0, s>>>(kp, k_substeps, np, ht);
+    else if (h->hetero) fullgame_step_kernel<kVarHetero, 0, 1><<<g1, kFgBlock, 0, s>>>(kp, k_substeps, np, ht);
+    else if (h->cfg.noise) fullgame_step_kernel<kVarNoisy, 0, 1><<<g1, kFgBlock, 0, s>>>(kp, k_substeps, np, ht);
+    else if (!h->default_sp && np == 22) S2D_FG(kVarRuntime);
+    else if (!h->default_sp) fullgame_step_kernel<kVarRuntime, 0, 1><<<g1, kFgBlock, 0, s>>>(kp, k_substeps, np, ht);
+    else if (np == 22) S2D_FG(kVarDefault);
+    else fullgame_step_kernel<kVarDefault, 0, 1><<<g1, kFgBlock, 0, s>>>(kp, k_substeps, np, ht);
+#undef S2D_FG
   } else if (h->cfg.scenario == S2D_SCENARIO_SHOOT) {
     if (h->cfg.action_mode == S2D_ACT_DISCRETE) S2D_LAUNCH(S2D_SCENARIO_SHOOT, S2D_ACT_DISCRETE);
     else S2D_LAUNCH(S2D_SCENARIO_SHOOT, S2D_ACT_COMMAND);

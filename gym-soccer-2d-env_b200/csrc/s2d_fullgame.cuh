@@ -327,25 +327,27 @@ __device__ __forceinline__ float butterfly_sum(float v) {
 // collided gets vel *= -0.1 once.  The lane that owns the match receives the masks (players that collided, players that
 // touched the ball) and the ball; the player lanes write positions and velocities back (shared memory, plane PA and,
 // when `obs_rows` (the observation tensor) is set - last cycle of a launch -, the row the player loop has already written).
-__device__ __noinline__ void fg_resolve_collisions(FgShared& S, const int t, const FgPlanes g, Match& m, const int np, unsigned need,
+__device__ __noinline__ void fg_resolve_collisions(FgShared& S, const int t, const int lane, const int lpm, const FgPlanes g, Match& m,
+                                                   const int np, unsigned need,
                                                    const bool dead, const float r, const float r2, const int model, float* obs_rows,
                                                    const int64_t env, const bool valid,
                                                    uint32_t& collided_mask, uint32_t& touch, bool& ball_collided) {
+  // (t = this thread's match column in shared memory; with lpm lanes per match, lane l holds column t - l / lpm + ..)
   const unsigned full = 0xffffffffu;
-  const int lane = t & 31;
   const bool active = lane < np;
   const float h = r2 / 2.0f + kCollideEps;
 #pragma unroll 1
   while (need) {
     const int src = __ffs(need) - 1;
     need &= need - 1u;
-    const int ts = t - lane + src;  // the match's column in shared memory
+    const int dcol = src / lpm - lane / lpm;  // from this thread's match to the match being resolved
+    const int ts = t + dcol;                  // its column in shared memory
     float bx = __shfl_sync(full, m.bx, src), by = __shfl_sync(full, m.by, src);
     const float bvx = __shfl_sync(full, m.bvx, src), bvy = __shfl_sync(full, m.bvy, src);
     const bool ball_fixed = __shfl_sync(full, static_cast<int>(dead), src) != 0;
     const bool report = __shfl_sync(full, static_cast<int>(valid), src) != 0;
     float2 pos = active ? S.xy[lane][ts] : make_float2(0.0f, 0.0f);
-    float4* const my_pa = g.pa + (src - lane) + static_cast<size_t>(active ? lane : 0) * g.row;  // (player lane, match src)
+    float4* const my_pa = g.pa + dcol + static_cast<size_t>(active ? lane : 0) * g.row;  // (player lane, match src)
     float2 vel = make_float2(0.0f, 0.0f);  // BACKTRACE: every object backs up along its own velocity
     if (model == S2D_COLLISION_BACKTRACE && active) {
       const float4 a = *my_pa;
@@ -422,7 +424,7 @@ __device__ __noinline__ void fg_resolve_collisions(FgShared& S, const int t, con
       const float vx = a.z * -0.1f, vy = a.w * -0.1f;
       *my_pa = make_float4(pos.x, pos.y, vx, vy);
       if (obs_rows && report) {
-        float* o = obs_rows + (env - lane + src) * kFgObsDim + 4 + 5 * lane;
+        float* o = obs_rows + (env + dcol) * kFgObsDim + 4 + 5 * lane;
         o[0] = pos.x * static_cast<float>(1.0 / 52.5);
         o[1] = pos.y * static_cast<float>(1.0 / 34.0);
         o[2] = vx;
@@ -442,6 +444,7 @@ __device__ __noinline__ void fg_resolve_collisions(FgShared& S, const int t, con
       ball_collided = ball_any;
     }
   }
+  __syncwarp();  // what the player lanes wrote (shared memory, plane PA) is read by the matches' own threads next
 }
 
 // Offside marks (OffsideRef), taken at the moment of a pass by ONE team in PlayOn: the passer's team-mates that are, in
@@ -539,13 +542,23 @@ __device__ __forceinline__ void fg_write_obs(float* __restrict__ dst, int64_t en
 // `obs_row` != nullptr (last cycle of a launch, 11 v 11): the player loop writes the players' part of the observation
 // row as it goes (the values are in registers then), and whatever moves a player afterwards patches its entry;
 // obs_dirty is raised where the whole row has to be written again (kick-off).
-template <class SP>
-__device__ __forceinline__ bool fg_cycle(FgShared& S, const int t, const FgPlanes& g, Match& m, const KernelParams& P, SP& sp,
-                                         uint64_t gid, int np, int half_time, const float4* __restrict__ act, float* obs_row,
-                                         const bool valid, bool& obs_dirty, float& reward, int& result, uint32_t& collided_mask,
-                                         uint32_t& kicked_mask, bool& ball_collided) {
+//
+// LPM = lanes per match (1, 2 or 4 adjacent lanes).  With more than one, the lanes of a match share its players in the
+// two player loops (sub-lane h takes the groups of four players h, h + LPM, ...) and in the pair scan, merge what they
+// found with shuffles, and repeat the cheap per-match arithmetic (ball, referee) redundantly - bit-identical by
+// construction.  It shortens the dependent chain of a cycle: for shards too small to fill the GPU with one thread per match.
+template <int LPM, class SP>
+__device__ __forceinline__ bool fg_cycle(FgShared& S, const int t, const int tid, const FgPlanes& g, Match& m, const KernelParams& P,
+                                         SP& sp, uint64_t gid, int np, int half_time, const float4* __restrict__ act,
+                                         float* obs_row, const bool valid, bool& obs_dirty, float& reward, int& result,
+                                         uint32_t& collided_mask, uint32_t& kicked_mask, bool& ball_collided) {
   const unsigned full = 0xffffffffu;
   const int pps = np >> 1;
+  const int h = tid & (LPM - 1);  // sub-lane within the match
+  const int lane = tid & 31;
+  // the players of this sub-lane, in the order it walks them; LPM = 1: simply 0 .. np - 1
+  auto player_at = [&](int it) { return LPM == 1 ? it : 4 * ((it >> 2) * LPM + h) + (it & 3); };
+  const int iters = LPM == 1 ? np : 4 * ((((np + 3) >> 2) + LPM - 1) / LPM);
   const unsigned left_set = (1u << pps) - 1u;
   bool dead = m.mode != S2D_PM_PLAY_ON;
   const bool dead_at_start = dead;
@@ -565,45 +578,50 @@ __device__ __forceinline__ bool fg_cycle(FgShared& S, const int t, const FgPlane
   uint32_t kick_mask = 0;
   float kx[32], ky[32];  // the kickers' pushes on the ball (local memory; written only when somebody kicks)
   float moved2 = 0.0f;
+  const uint32_t tk0_in = m.tk0, tk1_in = m.tk1, tk2_in = m.tk2, ban_in = m.ban;
   {
-    float4* gpa = g.pa;
-    float4* gpb = g.pb;
-    float* gpc = g.pc;
-    // software pipeline: player j + 1's plane entries are in flight while player j computes; the commands come two
-    // players (one 32-byte sector) at a time, so the loop walks the players in pairs (np is even)
-    float4 n_a = ld_stream(gpa), n_b = ld_stream(gpb), n_cmd0, n_cmd1;
-    float n_c = ld_stream(gpc);
-    ld_nc_256(act, n_cmd0, n_cmd1);
-    constexpr int kAhead = S2D_FG_AHEAD;  // rows the L2 is asked for ahead of the register prefetch (no registers held)
+    // software pipeline: the plane entries of this sub-lane's next player are in flight while the current one
+    // computes; the commands come two players (one 32-byte sector) at a time, so the loop walks the players in pairs
+    // (np is even, and pairs do not straddle the groups of four the sub-lanes take turns with)
+    const int j_first = player_at(0);
+    float4 n_a = make_float4(0.f, 0.f, 0.f, 0.f), n_b = make_float4(0.f, 0.f, 0.f, 1.f), n_cmd0 = n_a, n_cmd1 = n_a;
+    float n_c = 0.0f;
+    if (j_first < np) {
+      n_a = ld_stream(g.pa + static_cast<size_t>(j_first) * g.row);
+      n_b = ld_stream(g.pb + static_cast<size_t>(j_first) * g.row);
+      n_c = ld_stream(g.pc + static_cast<size_t>(j_first) * g.rowc);
+      ld_nc_256(act + j_first, n_cmd0, n_cmd1);
+    }
+    constexpr int kAhead = LPM == 1 ? S2D_FG_AHEAD : 0;  // rows the L2 is asked for ahead of the register prefetch
 #pragma unroll
     for (int a = 1; a <= kAhead; ++a) {
       if (a < np) {
-        prefetch_l2(gpa + a * g.row);
-        prefetch_l2(gpb + a * g.row);
-        prefetch_l2(gpc + a * g.rowc);
+        prefetch_l2(g.pa + a * g.row);
+        prefetch_l2(g.pb + a * g.row);
+        prefetch_l2(g.pc + a * g.rowc);
       }
     }
 
-    auto one_player = [&](const int j, const float4 a) {
-      if constexpr (SP::kHetero) sp.row = sp.table + PT_ROW * P.type_of[j];
+    // `on`: the sub-lane has a player in this slot (with LPM > 1 the sub-lanes own 8 / 6 / 4 / 4 or 12 / 10 players and all
+    // walk the longest list, so that the warp votes of fg_commands stay whole); j_next: the player it handles after this one
+    auto one_player = [&](const int j, float4 a, const bool on, const int j_next) {
+      if constexpr (SP::kHetero) sp.row = sp.table + PT_ROW * P.type_of[on ? j : 0];
       const float4 pa = n_a, b = n_b;
       const float cap = n_c;
-      float4* const wpa = gpa;
-      float4* const wpb = gpb;
-      float* const wpc = gpc;
-      gpa += g.row;
-      gpb += g.row;
-      gpc += g.rowc;
-      if (j + 1 < np) {
-        n_a = ld_stream(gpa);
-        n_b = ld_stream(gpb);
-        n_c = ld_stream(gpc);
+      float4* const wpa = g.pa + static_cast<size_t>(j) * g.row;
+      float4* const wpb = g.pb + static_cast<size_t>(j) * g.row;
+      float* const wpc = g.pc + static_cast<size_t>(j) * g.rowc;
+      if (j_next < np) {
+        n_a = ld_stream(g.pa + static_cast<size_t>(j_next) * g.row);
+        n_b = ld_stream(g.pb + static_cast<size_t>(j_next) * g.row);
+        n_c = ld_stream(g.pc + static_cast<size_t>(j_next) * g.rowc);
       }
       if (kAhead > 0 && j + 1 + kAhead < np) {
-        prefetch_l2(gpa + kAhead * g.row);
-        prefetch_l2(gpb + kAhead * g.row);
-        prefetch_l2(gpc + kAhead * g.rowc);
+        prefetch_l2(wpa + (1 + kAhead) * g.row);
+        prefetch_l2(wpb + (1 + kAhead) * g.row);
+        prefetch_l2(wpc + (1 + kAhead) * g.rowc);
       }
+      if (!on) a.x = static_cast<float>(S2D_CMD_NONE);
       const bool left = j < pps;
       const int my_side = left ? S2D_SIDE_LEFT : S2D_SIDE_RIGHT;
       Episode p;
@@ -611,7 +629,7 @@ __device__ __forceinline__ bool fg_cycle(FgShared& S, const int t, const FgPlane
       p.body = b.x; p.stamina = b.y; p.effort = b.z; p.recovery = b.w;
       p.capacity = cap;
       p.bx = m.bx; p.by = m.by; p.bvx = m.bvx; p.bvy = m.bvy;
-      S.oldx[j][t] = p.px;
+      if (on) S.oldx[j][t] = p.px;
       float ax = 0.0f, ay = 0.0f, kax = 0.0f, kay = 0.0f;
       // tackle / catch and their after-effects (Player::tackle, Player::goalieCatch; spec: include/soccer2d.h).  One
       // vote skips all of it while nobody in the warp tackles, catches, lies on the ground or waits for its next catch.
@@ -619,7 +637,7 @@ __device__ __forceinline__ bool fg_cycle(FgShared& S, const int t, const FgPlane
       bool tackled = false;
       float tkx = 0.0f, tky = 0.0f;  // a tackle's push on the ball
       const int raw = static_cast<int>(a.x);
-      if (__any_sync(full, (m.tk0 | m.tk1 | m.tk2 | m.ban) != 0u || raw == S2D_CMD_TACKLE || raw == S2D_CMD_CATCH)) {
+      if (__any_sync(full, on && ((m.tk0 | m.tk1 | m.tk2 | m.ban) != 0u || raw == S2D_CMD_TACKLE || raw == S2D_CMD_CATCH)) && on) {
         const int word = j >> 3, shift = (j & 7) * 4;
         const uint32_t w = word == 0 ? m.tk0 : word == 1 ? m.tk1 : m.tk2;
         uint32_t count = (w >> shift) & 15u;
@@ -690,7 +708,7 @@ __device__ __forceinline__ bool fg_cycle(FgShared& S, const int t, const FgPlane
         p.vx = 0.0f;
         p.vy = 0.0f;
       }
-      if (kicked) {
+      if (kicked && on) {
         kick_mask |= 1u << j;
         kx[j] = kax;
         ky[j] = kay;
@@ -698,6 +716,7 @@ __device__ __forceinline__ bool fg_cycle(FgShared& S, const int t, const FgPlane
       move_object<SP::kNoise>(p.px, p.py, p.vx, p.vy, ax, ay, sp.player_accel_max(), sp.player_accel_max2(),
                               sp.player_speed_max(), sp.player_speed_max2(), sp.player_decay(), sp.player_rand(), &nz,
                               static_cast<uint32_t>(j));
+      if (!on) return;
       const float stepx = p.px - pa.x, stepy = p.py - pa.y;
       moved2 = fmaxf(moved2, stepx * stepx + stepy * stepy);
       if (!stopped) update_stamina(p, sp);
@@ -708,31 +727,61 @@ __device__ __forceinline__ bool fg_cycle(FgShared& S, const int t, const FgPlane
       if (obs_row) {  // (uniform) four players = 20 floats = five float4 of the row, starting at float4 1 + 5 (j / 4)
         const int q = j & 3;
         float(*stg)[kFgBlock] = S.obs + 5 * q;
-        stg[0][t] = p.px * static_cast<float>(1.0 / 52.5);
-        stg[1][t] = p.py * static_cast<float>(1.0 / 34.0);
-        stg[2][t] = p.vx;
-        stg[3][t] = p.vy;
-        stg[4][t] = p.body * static_cast<float>(1.0 / 180.0);
+        stg[0][tid] = p.px * static_cast<float>(1.0 / 52.5);
+        stg[1][tid] = p.py * static_cast<float>(1.0 / 34.0);
+        stg[2][tid] = p.vx;
+        stg[3][tid] = p.vy;
+        stg[4][tid] = p.body * static_cast<float>(1.0 / 180.0);
         if (valid && (q == 3 || j == np - 1)) {
           float4* o = reinterpret_cast<float4*>(obs_row) + 1 + 5 * (j >> 2);
-          st_stream(o, make_float4(S.obs[0][t], S.obs[1][t], S.obs[2][t], S.obs[3][t]));
-          st_stream(o + 1, make_float4(S.obs[4][t], S.obs[5][t], S.obs[6][t], S.obs[7][t]));
+          st_stream(o, make_float4(S.obs[0][tid], S.obs[1][tid], S.obs[2][tid], S.obs[3][tid]));
+          st_stream(o + 1, make_float4(S.obs[4][tid], S.obs[5][tid], S.obs[6][tid], S.obs[7][tid]));
           if (q == 3) {
-            st_stream(o + 2, make_float4(S.obs[8][t], S.obs[9][t], S.obs[10][t], S.obs[11][t]));
-            st_stream(o + 3, make_float4(S.obs[12][t], S.obs[13][t], S.obs[14][t], S.obs[15][t]));
-            st_stream(o + 4, make_float4(S.obs[16][t], S.obs[17][t], S.obs[18][t], S.obs[19][t]));
+            st_stream(o + 2, make_float4(S.obs[8][tid], S.obs[9][tid], S.obs[10][tid], S.obs[11][tid]));
+            st_stream(o + 3, make_float4(S.obs[12][tid], S.obs[13][tid], S.obs[14][tid], S.obs[15][tid]));
+            st_stream(o + 4, make_float4(S.obs[16][tid], S.obs[17][tid], S.obs[18][tid], S.obs[19][tid]));
           } else {  // players 20 and 21: floats 104..113; 114..119 are the referee's, written at the end of the launch
-            reinterpret_cast<float2*>(o + 2)[0] = make_float2(S.obs[8][t], S.obs[9][t]);
+            reinterpret_cast<float2*>(o + 2)[0] = make_float2(S.obs[8][tid], S.obs[9][tid]);
           }
         }
       }
     };
 #pragma unroll 1
-    for (int j = 0; j < np; j += 2) {
+    for (int it = 0; it < iters; it += 2) {
+      const int j = player_at(it), j_after = it + 2 < iters ? player_at(it + 2) : np;  // (j is even)
+      const bool on = j < np;
       const float4 c0 = n_cmd0, c1 = n_cmd1;
-      if (j + 2 < np) ld_nc_256(act + j + 2, n_cmd0, n_cmd1);
-      one_player(j, c0);
-      one_player(j + 1, c1);
+      if (j_after < np) ld_nc_256(act + j_after, n_cmd0, n_cmd1);
+      one_player(j, c0, on, on ? j + 1 : np);
+      one_player(j + 1, c1, on, j_after);
+    }
+  }
+  if (LPM > 1) {  // what the sub-lanes of a match found, merged: every one of them goes on with the whole picture
+    __syncwarp();
+    uint32_t d0 = m.tk0 ^ tk0_in, d1 = m.tk1 ^ tk1_in, d2 = m.tk2 ^ tk2_in, db = m.ban ^ ban_in;  // (disjoint nibbles)
+#pragma unroll
+    for (int sft = 1; sft < LPM; sft <<= 1) {
+      kick_mask |= __shfl_xor_sync(full, kick_mask, sft);
+      moved2 = fmaxf(moved2, __shfl_xor_sync(full, moved2, sft));
+      caught = max(caught, __shfl_xor_sync(full, caught, sft));
+      d0 |= __shfl_xor_sync(full, d0, sft);
+      d1 |= __shfl_xor_sync(full, d1, sft);
+      d2 |= __shfl_xor_sync(full, d2, sft);
+      db |= __shfl_xor_sync(full, db, sft);
+    }
+    m.tk0 = tk0_in ^ d0;
+    m.tk1 = tk1_in ^ d1;
+    m.tk2 = tk2_in ^ d2;
+    m.ban = ban_in ^ db;
+    if (kick_mask) {  // the pushes of the kickers the other sub-lanes handled (cold; the lanes of a match are converged)
+      const unsigned group = ((1u << LPM) - 1u) << (lane & ~(LPM - 1));
+#pragma unroll 1
+      for (uint32_t rest = kick_mask; rest; rest &= rest - 1u) {
+        const int j = __ffs(rest) - 1, owner = (j >> 2) & (LPM - 1);
+        const float vx = h == owner ? kx[j] : 0.0f, vy = h == owner ? ky[j] : 0.0f;
+        kx[j] = __shfl_sync(group, vx, owner, LPM);
+        ky[j] = __shfl_sync(group, vy, owner, LPM);
+      }
     }
   }
 
@@ -787,7 +836,9 @@ __device__ __forceinline__ bool fg_cycle(FgShared& S, const int t, const FgPlane
   uint32_t ball_mask = 0;  // players the live ball overlaps
   float cleared2 = 0.0f;
 #pragma unroll 1
-  for (int j = 0; j < np; ++j) {
+  for (int it = 0; it < iters; ++it) {
+    const int j = player_at(it);
+    if (j >= np) continue;
     float2 xy = S.xy[j][t];
     const bool left = j < pps;
     const int my_side = left ? S2D_SIDE_LEFT : S2D_SIDE_RIGHT;
@@ -828,6 +879,14 @@ __device__ __forceinline__ bool fg_cycle(FgShared& S, const int t, const FgPlane
     }
     if (!dead && c2 < r * r) ball_mask |= 1u << j;
   }
+  if (LPM > 1) {
+#pragma unroll
+    for (int sft = 1; sft < LPM; sft <<= 1) {
+      ball_mask |= __shfl_xor_sync(full, ball_mask, sft);
+      cleared2 = fmaxf(cleared2, __shfl_xor_sync(full, cleared2, sft));
+    }
+    __syncwarp();  // the referee's placements are in shared memory for the other sub-lanes
+  }
 
   // ---- collisions ----
   // `sep` (kept in the match state) is a LOWER BOUND on the smallest distance between two players.  Every cycle it
@@ -845,7 +904,7 @@ __device__ __forceinline__ bool fg_cycle(FgShared& S, const int t, const FgPlane
   if (__any_sync(full, m.sep < r2)) {
     float m2 = 3.0e38f;
 #pragma unroll 1
-    for (int i = 0; i + 1 < np; ++i) {
+    for (int i = h; i + 1 < np; i += LPM) {
       const float2 pi = S.xy[i][t];
 #pragma unroll 4
       for (int j = i + 1; j < np; ++j) {
@@ -854,6 +913,8 @@ __device__ __forceinline__ bool fg_cycle(FgShared& S, const int t, const FgPlane
         m2 = fminf(m2, ex * ex + ey * ey);
       }
     }
+#pragma unroll
+    for (int sft = 1; sft < LPM; sft <<= 1) m2 = fminf(m2, __shfl_xor_sync(full, m2, sft));
     pairs_close = m2 < r2 * r2;
     m.sep = sqrtf(m2) * 0.999f;
   }
@@ -861,10 +922,23 @@ __device__ __forceinline__ bool fg_cycle(FgShared& S, const int t, const FgPlane
   ball_collided = false;
   uint32_t touch = 0;
   {
-    const unsigned need = __ballot_sync(full, (pairs_close || ball_mask != 0u) && !stopped);  // (AfterGoal: nothing moves)
-    if (need)
-      fg_resolve_collisions(S, t, g, m, np, need, dead, r, r2, sp.collision_model(), obs_row ? P.obs : nullptr,
-                            static_cast<int64_t>(blockIdx.x) * kFgBlock + t, valid, collided_mask, touch, ball_collided);
+    constexpr unsigned kFirstSubLanes = LPM == 1 ? 0xffffffffu : LPM == 2 ? 0x55555555u : 0x11111111u;
+    const unsigned need = __ballot_sync(full, (pairs_close || ball_mask != 0u) && !stopped) & kFirstSubLanes;  // (AfterGoal: nothing moves)
+    if (need) {
+      fg_resolve_collisions(S, t, lane, LPM, g, m, np, need, dead, r, r2, sp.collision_model(), obs_row ? P.obs : nullptr,
+                            static_cast<int64_t>(blockIdx.x) * (kFgBlock / LPM) + t, valid, collided_mask, touch, ball_collided);
+      if (LPM > 1) {  // the first sub-lane received the outcome: hand it to the others
+        const int first = lane & ~(LPM - 1);
+        m.bx = __shfl_sync(full, m.bx, first);
+        m.by = __shfl_sync(full, m.by, first);
+        m.bvx = __shfl_sync(full, m.bvx, first);
+        m.bvy = __shfl_sync(full, m.bvy, first);
+        m.sep = __shfl_sync(full, m.sep, first);
+        collided_mask = __shfl_sync(full, collided_mask, first);
+        touch = __shfl_sync(full, touch, first);
+        ball_collided = __shfl_sync(full, static_cast<int>(ball_collided), first) != 0;
+      }
+    }
   }
   {
     const bool hit_l = (touch & left_set) != 0, hit_r = (touch & ~left_set) != 0;
@@ -976,6 +1050,7 @@ __device__ __forceinline__ bool fg_cycle(FgShared& S, const int t, const FgPlane
   const bool done = m.step_number >= 2 * half_time;
   result = !done ? S2D_RESULT_NONE : m.score_l > m.score_r ? 1 : m.score_r > m.score_l ? 2 : 3;
   if (done) m.mode = S2D_PM_TIME_OVER;
+  if (LPM > 1) __syncwarp();  // (kick-off placements: shared memory and planes, for the other sub-lanes' next cycle)
   return done;
 }
 
@@ -1027,21 +1102,25 @@ __device__ __forceinline__ void fg_bind_player_types(SP& sp, const KernelParams&
 
 // K lockstep cycles of every match; actions float4 [N][K][np].  NP = 22 is the 11 v 11 instantiation (player count and
 // team masks become immediates); NP = 0 takes the player count at run time.
-template <int VAR, int NP>
+template <int VAR, int NP, int LPM>
 __global__ void __launch_bounds__(kFgBlock, S2D_FG_MIN_BLOCKS) fullgame_step_kernel(const __grid_constant__ KernelParams P, const int K,
                                                                  const int np_runtime, const int half_time) {
+  static_assert(LPM == 1 || LPM == 2 || LPM == 4, "lanes per match");
   const int np = NP ? NP : np_runtime;
   using SP = typename VariantSP<VAR>::type;
   SP sp(P.cc);
   __shared__ FgShared S;
   fg_bind_player_types(sp, P);
-  const int t = threadIdx.x;
-  // Every thread owns a column of the state (rows are padded to the block size), so warps are whole: the columns past
-  // num_envs are scratch matches - they run the commands of the last real match and report nothing.
-  const int64_t env = static_cast<int64_t>(blockIdx.x) * kFgBlock + t;
+  const int tid = threadIdx.x;
+  const int t = tid / LPM;  // the match's column in the block's shared memory; the block holds kFgBlock / LPM matches
+  // Every thread owns (with LPM > 1: shares) a column of the state (rows are padded to 64), so warps are whole: the
+  // columns past num_envs are scratch matches - they run the commands of the last real match and report nothing.
+  const int64_t env = static_cast<int64_t>(blockIdx.x) * (kFgBlock / LPM) + t;
   const bool valid = env < P.num_envs;
+  const bool writer = valid && (tid & (LPM - 1)) == 0;  // the sub-lane that reports the match
   const int64_t env_in = valid ? env : P.num_envs - 1;
   const FgLayout L{P.num_envs, np};
+  if (env >= static_cast<int64_t>(L.nr())) return;  // (whole warps: nr is a multiple of 64)
   const FgPlanes g(P, L, env);
   const uint64_t gid = static_cast<uint64_t>(P.env_id_offset + env);
 
@@ -1059,33 +1138,35 @@ __global__ void __launch_bounds__(kFgBlock, S2D_FG_MIN_BLOCKS) fullgame_step_ker
     int rs;
     // in the last cycle of an 11 v 11 launch the player loop writes the observation row itself
     float* const obs_row = (NP == kFgMaxPlayers && k == 1) ? my_obs : nullptr;
-    const bool done = fg_cycle(S, t, g, m, P, sp, gid, np, half_time, act, obs_row, valid, obs_dirty, rw, rs, collided_mask,
-                               kicked_mask, ball_collided);
+    const bool done = fg_cycle<LPM>(S, t, tid, g, m, P, sp, gid, np, half_time, act, obs_row, valid, obs_dirty, rw, rs, collided_mask,
+                                    kicked_mask, ball_collided);
     reward_sum += rw;
     m.ep_return += rw;
     if (done) {
       any_done = 1;
       last_result = static_cast<uint32_t>(rs);
-      if (!m.done_flag && valid) {  // (a finished match stepped on with auto_reset off is tallied once)
+      if (!m.done_flag && writer) {  // (a finished match stepped on with auto_reset off is tallied once)
         unsigned long long* slot = P.stats + static_cast<size_t>(env % kStatSlots) * kStatWords;
         atomicAdd(slot + ST_EPISODES, 1ull);
         atomicAdd(slot + (rs == 1 ? ST_GOALS : rs == 2 ? ST_OUTS : ST_TIMEOUTS), 1ull);
         atomicAdd(slot + ST_EP_STEPS, static_cast<unsigned long long>(m.step_number));
         atomicAdd(reinterpret_cast<double*>(slot + ST_RETURN), static_cast<double>(m.ep_return));
       }
-      if (P.terminal_obs && valid) fg_write_obs(P.terminal_obs, env, g, m, np, half_time);
+      if (P.terminal_obs && writer) fg_write_obs(P.terminal_obs, env, g, m, np, half_time);
       if (P.auto_reset) {
+        if (LPM > 1) __syncwarp();  // (the terminal observation reads the planes the reset rewrites)
         fg_reset(S, t, g, m, P, sp, gid, np);
         collided_mask = kicked_mask = 0;
         ball_collided = false;
         obs_dirty = true;
+        if (LPM > 1) __syncwarp();
       } else {
         m.done_flag = true;
       }
     }
   }
+  if (!writer) return;
   fg_store(P, L, env, m, collided_mask, kicked_mask, ball_collided);
-  if (!valid) return;
   if (NP != kFgMaxPlayers || obs_dirty) {
     fg_write_obs(P.obs, env, g, m, np, half_time);  // the whole row from the planes
   } else {  // the players' part is written: the ball and the referee's six values

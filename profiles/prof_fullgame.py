@@ -24,7 +24,7 @@ def commands(shape):
 
 launches = int(sys.argv[1]) if len(sys.argv) > 1 else 5  # capture with ncu -s <launch index> -c 1
 for k in ((1, 16) if launches == 5 else (1,)):
-    n = 1 << 18
+    n = int(os.environ.get("FG_MATCHES", 1 << 18))
     env = Soccer2DVecEnv(n, scenario="fullgame", device="cuda:0", seed=0, substeps=k)
     pool = [commands((n, k, 22)) for _ in range(2)]
     env.reset_torch()

@@ -11,7 +11,7 @@ import torch  # noqa: E402
 import bench  # noqa: E402
 from soccer2d_b200 import Soccer2DVecEnv  # noqa: E402
 
-n, k = 1 << 18, int(sys.argv[1]) if len(sys.argv) > 1 else 1
+n, k = int(os.environ.get("FG_MATCHES", 1 << 18)), int(sys.argv[1]) if len(sys.argv) > 1 else 1
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 60
 dev = torch.device("cuda:0")
 gen = torch.Generator(device=dev).manual_seed(99)

@@ -424,7 +424,9 @@ typedef struct S2DMlpPolicy {
   const float* w2; const float* b2; /* [64][64], [64] */
   const float* w3; const float* b3; /* [n_actions][64], [n_actions] */
   int32_t hidden;                   /* 64 */
-  int32_t precision;                /* 0: TF32 operands (default); 1: bf16 operands (Q-networks only; ~1e-2 of Q's scale) */
+  int32_t precision;                /* 0: TF32 operands, warp-level mma.sync (default); 1: bf16 operands (Q-networks only;
+                                       ~1e-2 of Q's scale); 2: TF32 operands on tcgen05.mma, accumulators in tensor memory
+                                       (Q-networks only) */
 } S2DMlpPolicy;
 int s2d_rollout_mlp(S2DHandle h, const S2DMlpPolicy* policy, int k_substeps, float epsilon, void* actions_out,
                     void* q_out, void* stream);

@@ -101,11 +101,13 @@ def _layers(q):
     return [(l.weight.detach().contiguous(), l.bias.detach().contiguous()) for l in lin]
 
 
+@pytest.mark.parametrize("precision", ["tf32", "tf32_tcgen05"])
 @pytest.mark.parametrize("scenario,n_actions,n", [("reachball", 16, 4096 + 37), ("reachball", 12, 1000), ("shoot", 24, 2000 + 5)])
-def test_fused_policy_rollout_matches_policy_then_step(scenario, n_actions, n):
+def test_fused_policy_rollout_matches_policy_then_step(scenario, n_actions, n, precision):
     """K cycles of observe -> Q -> argmax -> step in one launch.  The env half is checked bit for bit (replaying the
     recorded actions through the ordinary step kernel gives the same state), the policy half against torch fp32:
-    Q-values within TF32 accuracy, and the greedy action equal except where fp32 itself sees a near-tie."""
+    Q-values within TF32 accuracy, and the greedy action equal except where fp32 itself sees a near-tie.
+    precision: "tf32" = warp-level mma.sync, "tf32_tcgen05" = tcgen05.mma with the accumulators in tensor memory."""
     from soccer2d_b200.rollout import QNetwork
     torch.manual_seed(0)
     k = 5
@@ -127,7 +129,7 @@ def test_fused_policy_rollout_matches_policy_then_step(scenario, n_actions, n):
     agree = total = 0
     worst_q = 0.0
     for launch in range(50):  # 250 cycles: episodes end and restart inside the launches
-        fused.rollout_mlp(layers, k, 0.0, actions, q_seen)
+        fused.rollout_mlp(layers, k, 0.0, actions, q_seen, precision=precision)
         for j in range(k):
             with torch.no_grad():
                 q32 = qnet(plain.obs)

@@ -597,9 +597,10 @@ def run_b200(args, rank, local_rank, world):
                         "envs_to_value": rollout,
                         "fused_policy_kernel": {
                             "envs_to_value": rollout_fused, "substeps": SUBSTEPS,
-                            "path": "Soccer2DVecEnv.rollout_mlp -> s2d_rollout_mlp: observe -> Q-network (mma.sync m16n8k8, TF32 "
-                                    "operands, fp32 accumulate, weights in shared memory) -> argmax -> step, K cycles per "
-                                    "launch; observation and action never leave the SM"}},
+                            "path": "Soccer2DVecEnv.rollout_mlp -> s2d_rollout_mlp: observe -> Q-network (tcgen05.mma kind::tf32, one "
+                                    "M=128 tile per block, accumulators and layer-2/3 activations in tensor memory, weights "
+                                    "in shared memory) -> argmax -> step, K cycles per launch; observation and action never "
+                                    "leave the SM"}},
         "single_env_gym_api": single,
         "clocks": clocks,
         "episode_stats": stats,

@@ -832,8 +832,9 @@ static int rollout_mlp(S2DHandle h, const S2DMlpPolicy* policy, int k_substeps, 
     else if (h->default_sp) rollout_mlp_kernel<SCN, kVarDefault, ACT><<<h->grid, kBlock, 0, s>>>(h->kp, k_substeps, w, epsilon, ao, qo, traj); \
     else rollout_mlp_kernel<SCN, kVarRuntime, ACT><<<h->grid, kBlock, 0, s>>>(h->kp, k_substeps, w, epsilon, ao, qo, traj); \
   } while (0)
-  if (policy->precision == 2) {  // the Q-network on tcgen05 (TF32 operands, accumulators in tensor memory)
-    if (actor) return fail(h, S2D_ERR_INVALID, "precision 2 (tcgen05): Q-networks (Discrete actions) only");
+  if (policy->precision < 0 || policy->precision > 2)
+    return fail(h, S2D_ERR_INVALID, "precision: 0 (TF32: tcgen05 for Q-networks, mma.sync for actors), 1 (bf16, mma.sync), 2 (TF32, mma.sync)");
+  if (policy->precision == 0 && !actor) {  // the Q-network on tcgen05 (TF32 operands, accumulators in tensor memory)
 #define S2D_TC5(SCN)                                                                                                   \
   do {                                                                                                                 \
     if (h->cfg.noise) rollout_mlp_tc5_kernel<SCN, kVarNoisy><<<h->grid, kBlock, 0, s>>>(h->kp, k_substeps, w, epsilon, ao, qo, traj); \
@@ -847,8 +848,8 @@ static int rollout_mlp(S2DHandle h, const S2DMlpPolicy* policy, int k_substeps, 
     h->env_steps += static_cast<uint64_t>(h->cfg.num_envs) * static_cast<uint64_t>(k_substeps);
     return after_user_op(h, s);
   }
-  if (policy->precision != 0 && (policy->precision != 1 || actor || h->cfg.noise))
-    return fail(h, S2D_ERR_INVALID, "precision: 0 (TF32, mma.sync), 2 (TF32, tcgen05), or 1 (bf16) for a Q-network on a handle without noise");
+  if (policy->precision == 1 && (actor || h->cfg.noise))
+    return fail(h, S2D_ERR_INVALID, "precision 1 (bf16): Q-networks on a handle without noise only");
   if (policy->precision == 1) {
     if (shoot) {
       if (h->default_sp) rollout_mlp_kernel<S2D_SCENARIO_SHOOT, kVarDefault, S2D_ACT_DISCRETE, true><<<h->grid, kBlock, 0, s>>>(h->kp, k_substeps, w, epsilon, ao, qo, traj);

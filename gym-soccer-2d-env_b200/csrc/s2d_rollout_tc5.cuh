@@ -81,6 +81,10 @@ __device__ __forceinline__ void tc5_wait(uint32_t mbar, uint32_t parity) {
 __device__ __forceinline__ void tc5_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc5_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+// Round-to-nearest (ties away) to TF32 for an operand the tensor core reads: the MMA ignores the low 13 mantissa bits, so
+// adding half a TF32 ulp to the bit pattern is the whole rounding (what cvt.rna.tf32.f32 takes three instructions for).
+__device__ __forceinline__ float tc5_round(float x) { return __uint_as_float(__float_as_uint(x) + 0x1000u); }
+
 // 16 consecutive columns of this thread's TMEM lane <-> registers
 __device__ __forceinline__ void tc5_ld16(uint32_t taddr, float (&v)[16]) {
   uint32_t r[16];
@@ -141,16 +145,16 @@ __device__ __forceinline__ void tc5_issue_layer(uint32_t d_tmem, uint32_t a_tmem
 // the hidden-layer epilogue of this thread's row: D (64 columns at d_tmem) -> + bias, ReLU, TF32 -> A (64 columns at a_tmem)
 __device__ __forceinline__ void tc5_hidden_epilogue(uint32_t d_tmem, uint32_t a_tmem, const float* bias) {
 #pragma unroll 1
-  for (int c = 0; c < kTc5Hidden; c += 16) {
+  for (int c = 0; c < kTc5Hidden; c += 16) {  // (32 columns at a time: measured, no gain, 25 more registers)
     float v[16];
     tc5_ld16(d_tmem + c, v);
 #pragma unroll
     for (int i = 0; i < 16; i += 4) {
       const float4 b = *reinterpret_cast<const float4*>(bias + c + i);
-      v[i] = to_tf32(fmaxf(v[i] + b.x, 0.0f));
-      v[i + 1] = to_tf32(fmaxf(v[i + 1] + b.y, 0.0f));
-      v[i + 2] = to_tf32(fmaxf(v[i + 2] + b.z, 0.0f));
-      v[i + 3] = to_tf32(fmaxf(v[i + 3] + b.w, 0.0f));
+      v[i] = tc5_round(fmaxf(v[i] + b.x, 0.0f));
+      v[i + 1] = tc5_round(fmaxf(v[i + 1] + b.y, 0.0f));
+      v[i + 2] = tc5_round(fmaxf(v[i + 2] + b.z, 0.0f));
+      v[i + 3] = tc5_round(fmaxf(v[i + 3] + b.w, 0.0f));
     }
     tc5_st16(a_tmem + c, v);
   }
@@ -211,7 +215,7 @@ __global__ void __launch_bounds__(kBlock, S2D_ROLLOUT_MIN_BLOCKS)
     {  // A1: the observation row, TF32, features 10..15 zero
       float v[16];
 #pragma unroll
-      for (int f = 0; f < 16; ++f) v[f] = f < kObsDim ? to_tf32(obs_row[f]) : 0.0f;
+      for (int f = 0; f < 16; ++f) v[f] = f < kObsDim ? tc5_round(obs_row[f]) : 0.0f;
       tc5_st16(ra, v);
       tc5_wait_st();
     }

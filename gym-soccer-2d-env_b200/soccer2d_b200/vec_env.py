@@ -631,8 +631,8 @@ class Soccer2DVecEnv(_VecEnvBase):
         [64, 10], [64], [64, 64], [64], [n, 64], [n]), e.g. `[(l.weight, l.bias) for l in qnet.linears]`.
         Outputs land in the env's obs / reward / done_u8 / result tensors as after `step_torch`; optional
         `actions_out` uint8 [N, k] receives the actions taken and `q_out` float32 [N, 16] (Shoot: [N, 24]) the Q-values of the last cycle.
-        `precision`: "tf32" (default: warp-level mma.sync), "tf32_tcgen05" (the same operands on tcgen05.mma with the
-        accumulators in tensor memory) or "bf16" (half the tensor-core work; Q-values then agree with fp32 only to ~1e-2).
+        `precision`: "tf32" (default: TF32 operands on tcgen05.mma, accumulators in tensor memory), "tf32_mma_sync" (the
+        same operands on warp-level mma.sync: the round-1 kernel) or "bf16" (mma.sync; Q-values agree with fp32 only to ~1e-2).
         `traj` (s2d_rollout_mlp_collect): time-major tensors for every cycle's transition, any of obs float32
         [k + 1, N, 10], actions uint8 [k, N], reward float32 [k, N], done uint8 [k, N] - what a replay buffer takes."""
         k = self.substeps if k is None else int(k)
@@ -650,7 +650,7 @@ class Soccer2DVecEnv(_VecEnvBase):
         if q_out is not None:
             width = 24 if self.scenario == "shoot" else 16
             assert q_out.dtype == torch.float32 and tuple(q_out.shape) == (self.num_envs, width) and q_out.is_contiguous()
-        pol = _abi.MlpPolicy(*ptrs, 64, {"tf32": 0, "bf16": 1, "tf32_tcgen05": 2}[precision])
+        pol = _abi.MlpPolicy(*ptrs, 64, {"tf32": 0, "tf32_tcgen05": 0, "bf16": 1, "tf32_mma_sync": 2}[precision])
         if traj is not None:
             assert actions_out is None and q_out is None, "traj replaces actions_out / q_out"
             want = {"obs": ((k + 1, self.num_envs, self.obs_dim), torch.float32), "actions": ((k, self.num_envs), torch.uint8),

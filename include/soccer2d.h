@@ -410,7 +410,7 @@ int s2d_set_player_types(S2DHandle h, const S2DPlayerType* types, int n, const u
  * with at most 24).
  * The reference's caller is SB3 DQN (dqn_stable_baselines3.py:33-55): MlpPolicy = obs -> 64 -> 64 -> n_actions with
  * ReLU, `action = argmax Q(obs)`, `env.step(action)`.  s2d_rollout_mlp runs k_substeps cycles of
- *     observe -> Q-network (warp-level tensor-core MMAs, TF32 operands, fp32 accumulate) -> action -> step
+ *     observe -> Q-network (tensor cores: tcgen05.mma, TF32 operands, fp32 accumulate in tensor memory) -> action -> step
  * per launch without the observation or the action leaving the SM; with probability `epsilon` the action is uniform
  * random instead (counter RNG keyed on (seed, global env id, cycle)).  Outputs as s2d_step (obs after the last cycle,
  * reward summed, done / result, statistics); `actions_out` (device, uint8 [num_envs][k_substeps]) and `q_out` (device,
@@ -424,9 +424,10 @@ typedef struct S2DMlpPolicy {
   const float* w2; const float* b2; /* [64][64], [64] */
   const float* w3; const float* b3; /* [n_actions][64], [n_actions] */
   int32_t hidden;                   /* 64 */
-  int32_t precision;                /* 0: TF32 operands, warp-level mma.sync (default); 1: bf16 operands (Q-networks only;
-                                       ~1e-2 of Q's scale); 2: TF32 operands on tcgen05.mma, accumulators in tensor memory
-                                       (Q-networks only) */
+  int32_t precision;                /* 0 (default): TF32 operands - Q-networks on tcgen05.mma with the accumulators in
+                                       tensor memory, actors on warp-level mma.sync; 1: bf16 operands, mma.sync
+                                       (Q-networks only; ~1e-2 of Q's scale); 2: TF32 operands on mma.sync for
+                                       Q-networks too (the round-1 kernel, kept for comparison) */
 } S2DMlpPolicy;
 int s2d_rollout_mlp(S2DHandle h, const S2DMlpPolicy* policy, int k_substeps, float epsilon, void* actions_out,
                     void* q_out, void* stream);

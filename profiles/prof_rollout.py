@@ -16,5 +16,5 @@ env = Soccer2DVecEnv(1 << 20, device="cuda:0", seed=0, substeps=16, use_continuo
                      change_ball_position=True, change_ball_velocity=True)
 env.reset_torch()
 for _ in range(4):
-    env.rollout_mlp(layers, 16)
+    env.rollout_mlp(layers, 16, precision=sys.argv[1] if len(sys.argv) > 1 else "tf32")
 torch.cuda.synchronize()

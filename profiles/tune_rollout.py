@@ -15,8 +15,8 @@ torch.manual_seed(0)
 qnet = QNetwork(10, 16).cuda()
 layers = [(m.weight.detach().contiguous(), m.bias.detach().contiguous()) for m in qnet.net if isinstance(m, torch.nn.Linear)]
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-for n, k, prec in ((1 << 20, 16, "tf32"), (1 << 20, 16, "tf32_tcgen05"), (1 << 20, 1, "tf32"), (1 << 20, 1, "tf32_tcgen05"),
-                   (1 << 16, 16, "tf32"), (1 << 16, 16, "tf32_tcgen05"), (1 << 20, 16, "bf16")):
+for n, k, prec in ((1 << 20, 16, "tf32"), (1 << 20, 16, "tf32_mma_sync"), (1 << 20, 1, "tf32"), (1 << 20, 1, "tf32_mma_sync"),
+                   (1 << 16, 16, "tf32"), (1 << 16, 16, "tf32_mma_sync"), (1 << 20, 16, "bf16")):
     env = Soccer2DVecEnv(n, device="cuda:0", seed=0, substeps=k, **KW)
     env.reset_torch()
     for _ in range(14 if k > 1 else 5):

@@ -101,13 +101,13 @@ def _layers(q):
     return [(l.weight.detach().contiguous(), l.bias.detach().contiguous()) for l in lin]
 
 
-@pytest.mark.parametrize("precision", ["tf32", "tf32_tcgen05"])
+@pytest.mark.parametrize("precision", ["tf32", "tf32_mma_sync"])
 @pytest.mark.parametrize("scenario,n_actions,n", [("reachball", 16, 4096 + 37), ("reachball", 12, 1000), ("shoot", 24, 2000 + 5)])
 def test_fused_policy_rollout_matches_policy_then_step(scenario, n_actions, n, precision):
     """K cycles of observe -> Q -> argmax -> step in one launch.  The env half is checked bit for bit (replaying the
     recorded actions through the ordinary step kernel gives the same state), the policy half against torch fp32:
     Q-values within TF32 accuracy, and the greedy action equal except where fp32 itself sees a near-tie.
-    precision: "tf32" = warp-level mma.sync, "tf32_tcgen05" = tcgen05.mma with the accumulators in tensor memory."""
+    precision: "tf32" = tcgen05.mma with the accumulators in tensor memory (default), "tf32_mma_sync" = warp-level mma.sync."""
     from soccer2d_b200.rollout import QNetwork
     torch.manual_seed(0)
     k = 5

@@ -597,6 +597,12 @@ int s2d_stats(S2DHandle h, S2DStats* out, void* stream) {
   return S2D_OK;
 }
 
+int s2d_env_steps(S2DHandle h, uint64_t* out) {
+  if (!h || !out) return S2D_ERR_INVALID;
+  *out = h->env_steps;
+  return S2D_OK;
+}
+
 int s2d_stats_reset(S2DHandle h, void* stream) {
   if (!h) return S2D_ERR_INVALID;
   if (!h->bound) return fail(h, S2D_ERR_UNBOUND, "s2d_bind has not been called");

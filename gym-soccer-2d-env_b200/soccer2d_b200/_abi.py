@@ -149,6 +149,7 @@ SIGNATURES = {
     "s2d_wait_host": (C.c_int, [_H, C.c_int]),
     "s2d_stats": (C.c_int, [_H, C.POINTER(Stats), C.c_void_p]),
     "s2d_stats_reset": (C.c_int, [_H, C.c_void_p]),
+    "s2d_env_steps": (C.c_int, [_H, C.POINTER(C.c_uint64)]),
     "s2d_export_env": (C.c_int, [_H, C.c_int64, C.POINTER(EnvSnapshot), C.c_void_p]),
     "s2d_pipeline_info": (C.c_int, [_H, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "s2d_launch_info": (C.c_int, [_H, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),

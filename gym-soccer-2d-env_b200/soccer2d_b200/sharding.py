@@ -39,3 +39,50 @@ def allreduce_stats(stats: dict, device=None, group=None) -> dict:
     out = {k: int(v) for k, v in zip(int_keys, counts.cpu().tolist())}
     out["return_sum"] = float(ret.item())
     return out
+
+
+class StatsFuture:
+    """Result of an asynchronous statistics all-reduce: `.result()` waits (for the side stream / the collective) and
+    returns the summed dict; until then neither the host nor the stepping stream is held up."""
+
+    def __init__(self, counts, ret, works=(), event=None):
+        self._counts, self._ret, self._works, self._event, self._out = counts, ret, list(works), event, None
+
+    def done(self) -> bool:
+        if self._out is not None:
+            return True
+        if any(not w.is_completed() for w in self._works):
+            return False
+        return self._event is None or self._event.query()
+
+    def result(self) -> dict:
+        if self._out is None:
+            for w in self._works:
+                w.wait()
+            if self._event is not None:
+                self._event.synchronize()
+            int_keys = [k for k in STAT_KEYS if k != "return_sum"]
+            self._out = {k: int(v) for k, v in zip(int_keys, self._counts.cpu().tolist())}
+            self._out["return_sum"] = float(self._ret.cpu().item())
+        return self._out
+
+
+def allreduce_stats_async(counts: torch.Tensor, ret: torch.Tensor, group=None, stream=None) -> StatsFuture:
+    """Sum over the ranks of `counts` (int64 [6]: episodes, goals, outs, timeouts, episode_steps, env_steps) and `ret`
+    (float64 [1]: return sum), in place, without blocking: with NCCL the collective is enqueued behind `stream` (a side
+    stream: the stepping stream is not involved) and the call returns at once; with gloo it runs on a background thread."""
+    import torch.distributed as dist
+
+    works, event = [], None
+    if dist.is_available() and dist.is_initialized():
+        if counts.is_cuda and stream is not None:
+            with torch.cuda.stream(stream):
+                works = [dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group, async_op=True),
+                         dist.all_reduce(ret, op=dist.ReduceOp.SUM, group=group, async_op=True)]
+        else:
+            works = [dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group, async_op=True),
+                     dist.all_reduce(ret, op=dist.ReduceOp.SUM, group=group, async_op=True)]
+    if counts.is_cuda:
+        event = torch.cuda.Event()
+        event.record(stream if stream is not None else torch.cuda.current_stream(counts.device))
+    return StatsFuture(counts, ret, works, event)

@@ -580,6 +580,32 @@ class Soccer2DVecEnv(_VecEnvBase):
         from .sharding import allreduce_stats
         return allreduce_stats(self.stats(), device=self.device, group=group)
 
+    def allreduce_stats_async(self, group=None):
+        """The same sum without a host synchronisation and without touching the stepping stream: the 256 partial
+        accumulators are reduced on the device on a SIDE stream (ordered after the launches enqueued so far), the
+        NCCL all-reduce follows on that stream, and a StatsFuture is returned at once - call `.result()` when the
+        numbers are needed (a training loop that reports every M launches: SURVEY.md section 8e)."""
+        from .sharding import allreduce_stats_async
+        dev = self.device
+        if getattr(self, "_stats_stream", None) is None:
+            self._stats_stream = torch.cuda.Stream(dev)
+        side = self._stats_stream
+        self._fence()  # (launches of the host-buffer pipeline count too)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        steps = C.c_uint64(0)
+        _abi.check(self.lib.s2d_env_steps(self.handle, C.byref(steps)), self.handle)
+        with torch.cuda.stream(side):
+            slots = self.stats_buf.view(torch.int64).view(-1, 8)
+            counts = torch.cat([slots[:, :5].sum(0), torch.tensor([steps.value], dtype=torch.int64, device=dev)])
+            ret = self.stats_buf.view(torch.float64).view(-1, 8)[:, 5].sum().reshape(1)
+            snapshot = torch.cuda.Event()
+            snapshot.record(side)
+        # later launches wait for this snapshot (two tiny reductions), not for the collective that follows it
+        torch.cuda.current_stream(dev).wait_event(snapshot)
+        counts.record_stream(side)
+        ret.record_stream(side)
+        return allreduce_stats_async(counts, ret, group=group, stream=side)
+
     def export_env(self, i: int) -> _abi.EnvSnapshot:
         """Host snapshot of env `i`: the WorldModel fields the reference path reads (idl/service.proto:306-349)."""
         snap = _abi.EnvSnapshot()

@@ -371,6 +371,9 @@ int s2d_clear(S2DHandle h, void* stream);
 
 int s2d_stats(S2DHandle h, S2DStats* host_out, void* stream);   /* reduces the partials; synchronises */
 int s2d_stats_reset(S2DHandle h, void* stream);
+/* env-steps simulated so far (S2DStats.env_steps) without touching the device: for callers that reduce the statistics
+ * buffer on the device themselves (Soccer2DVecEnv.allreduce_stats_async) */
+int s2d_env_steps(S2DHandle h, uint64_t* out);
 int s2d_export_env(S2DHandle h, int64_t local_env, S2DEnvSnapshot* host_out, void* stream); /* synchronises */
 
 /* Heterogeneous players (FULLGAME; proto PlayerType, idl/service.proto:1697-1732).  rcssserver draws 18 player types

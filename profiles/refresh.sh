@@ -2,17 +2,20 @@
 # Everything profiles/ quotes, in one call on the GPU box (1 GPU):  gpurun -- 'bash profiles/refresh.sh TAG'
 # Each ncu pass runs only after the same command has exited 0 without ncu.
 set -u
-TAG=${1:-r1}
+TAG=${1:-r2}
 O=gpurun_out
 mkdir -p $O
 python bench.py > $O/${TAG}_bench_n1.json 2> $O/${TAG}_bench_n1.err || { echo "bench failed"; tail -5 $O/${TAG}_bench_n1.err; exit 1; }
-python bench.py --impl reference --steps 3 --warmup 1 > $O/${TAG}_bench_reference.json 2>> $O/${TAG}_bench_n1.err || echo "reference arm failed"
+python bench.py --impl reference --steps 20 --warmup 5 > $O/${TAG}_bench_reference.json 2>> $O/${TAG}_bench_n1.err || echo "reference arm failed"
 python bench.py --steps 20 --warmup 3 > /dev/null 2>&1 && \
   ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file $O/${TAG}_launches_bench.csv \
       python bench.py --steps 20 --warmup 3 > $O/ncu_launches.log 2>&1
 python profiles/tune_scenarios.py > $O/${TAG}_scenarios.txt 2>&1
 python profiles/tune.py >> $O/${TAG}_scenarios.txt 2>&1
-python profiles/tune_variants.py >> $O/${TAG}_scenarios.txt 2>&1
+python profiles/time_fullgame.py 1 60 >> $O/${TAG}_scenarios.txt 2>&1
+python profiles/time_fullgame.py 16 6 >> $O/${TAG}_scenarios.txt 2>&1
+FG_MATCHES=32768 python profiles/time_fullgame.py 1 30 >> $O/${TAG}_scenarios.txt 2>&1
+python profiles/tune_rollout.py >> $O/${TAG}_scenarios.txt 2>&1
 python profiles/prof_step.py both 2 > /dev/null 2>&1 && {
   ncu --set full --clock-control none --import-source on -k regex:step_kernel -s 14 -c 1 -o $O/prof_${TAG}_k16 -f python profiles/prof_step.py k16 2 > $O/ncu_full.log 2>&1
   ncu --set full --clock-control none --import-source on -k regex:step_kernel -s 6 -c 1 -o $O/prof_${TAG}_k1 -f python profiles/prof_step.py k1 2 >> $O/ncu_full.log 2>&1
@@ -20,8 +23,10 @@ python profiles/prof_step.py both 2 > /dev/null 2>&1 && {
 python profiles/prof_fullgame.py > /dev/null 2>&1 && {
   ncu --set full --clock-control none --import-source on -k regex:fullgame_step -s 3 -c 1 -o $O/prof_${TAG}_fg_k1 -f python profiles/prof_fullgame.py >> $O/ncu_full.log 2>&1
   ncu --set full --clock-control none --import-source on -k regex:fullgame_step -s 8 -c 1 -o $O/prof_${TAG}_fg_k16 -f python profiles/prof_fullgame.py >> $O/ncu_full.log 2>&1
+  ncu --set full --clock-control none --import-source on -k regex:fullgame_step -s 45 -c 1 -o $O/prof_${TAG}_fg_k1_late -f python profiles/prof_fullgame.py 48 >> $O/ncu_full.log 2>&1
 }
-python profiles/tune_rollout.py >> $O/${TAG}_scenarios.txt 2>&1
-python profiles/prof_rollout.py > /dev/null 2>&1 && \
-  ncu --set full --clock-control none --import-source on -k regex:rollout_mlp -s 2 -c 1 -o $O/prof_${TAG}_rollout -f python profiles/prof_rollout.py >> $O/ncu_full.log 2>&1
+python profiles/prof_rollout.py tf32 > /dev/null 2>&1 && {
+  ncu --set full --clock-control none --import-source on -k regex:rollout_mlp -s 2 -c 1 -o $O/prof_${TAG}_rollout_tc5 -f python profiles/prof_rollout.py tf32 >> $O/ncu_full.log 2>&1
+  ncu --set full --clock-control none --import-source on -k regex:rollout_mlp -s 2 -c 1 -o $O/prof_${TAG}_rollout_mma -f python profiles/prof_rollout.py tf32_mma_sync >> $O/ncu_full.log 2>&1
+}
 ls -la $O | tail -20

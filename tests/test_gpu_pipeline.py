@@ -191,3 +191,30 @@ def test_output_layout_contract():
         assert all(x % 256 == 0 for x in (lay.reward, lay.done, lay.result, lay.terminal_obs, lay.bytes))
         assert lay.step_bytes == lay.result + n <= lay.bytes <= n * (env_dim * 4 + 6) + 4 * 256
         assert lay.bytes_with_terminal_obs >= lay.terminal_obs + n * env_dim * 4
+
+
+def test_async_statistics_do_not_block_and_equal_the_synchronous_ones():
+    """allreduce_stats_async: device-side reduction of the 256 partial accumulators on a side stream (+ the NCCL sum when
+    a process group exists), returned as a future; launches enqueued AFTER the call are not in the snapshot."""
+    n, k = 50000, 8
+    env = Soccer2DVecEnv(n, substeps=k, **KW)
+    env.reset_torch()
+    rng = np.random.default_rng(5)
+    acts = [torch.from_numpy(H.random_actions(rng, "discrete", n, k)).cuda() for _ in range(6)]
+    for a in acts[:3]:
+        env.step_torch(a)
+    fut = env.allreduce_stats_async()
+    for a in acts[3:]:          # keep stepping: none of this may leak into the snapshot
+        env.step_torch(a)
+    snap = fut.result()
+    after = env.stats()
+    ref = Soccer2DVecEnv(n, substeps=k, **KW)
+    ref.reset_torch()
+    for a in acts[:3]:
+        ref.step_torch(a)
+    want = ref.stats()
+    assert {x: snap[x] for x in want if x != "return_sum"} == {x: want[x] for x in want if x != "return_sum"}
+    assert abs(snap["return_sum"] - want["return_sum"]) <= 1e-9 * max(1.0, abs(want["return_sum"]))
+    assert after["episodes"] > snap["episodes"] > 0 and after["env_steps"] == 2 * snap["env_steps"]
+    env.close()
+    ref.close()

@@ -45,6 +45,13 @@ def _worker(rank, world, port, total, k, launches, q):
     st = sim.stats(_abi.Stats())
     local = {key: getattr(st, key) for key in ("episodes", "goals", "outs", "timeouts", "episode_steps", "env_steps", "return_sum")}
     total_stats = allreduce_stats(local)
+    # the asynchronous form (what a training loop uses between launches): same sum, returned as a future
+    import torch
+    from soccer2d_b200 import allreduce_stats_async
+    keys = ("episodes", "goals", "outs", "timeouts", "episode_steps", "env_steps")
+    fut = allreduce_stats_async(torch.tensor([int(local[k_]) for k_ in keys], dtype=torch.int64),
+                                torch.tensor([float(local["return_sum"])], dtype=torch.float64))
+    assert fut.result() == total_stats and fut.done()
     q.put((rank, off, n, sim.obs.copy(), local, total_stats))
     dist.barrier()
     dist.destroy_process_group()

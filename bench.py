@@ -46,7 +46,7 @@ SUBSTEPS = 16
 SCENARIO_KW = dict(use_continuous_action=False, action_space_size=16, change_ball_position=True,
                    change_ball_velocity=True, min_distance_to_ball=5.0, max_steps=200)
 STATE_BYTES, OBS_BYTES, OUT_BYTES = 80, 40, 6  # per env: state planes; obs row; reward + done + result
-FG_STATE_BYTES, FG_OBS_BYTES = 22 * 36 + 64, 480  # per 11v11 match
+FG_STATE_BYTES, FG_OBS_BYTES = 22 * 36 + 80, 480  # per 11v11 match: 22 players x 9 words + 16 match words + 16 B of tackle / catch counters
 
 
 def algorithmic_bytes_per_env(k):

@@ -78,7 +78,7 @@ struct Match {
 #define S2D_FG_AHEAD 2  // player rows the L2 is asked for ahead of the register prefetch (measured: 0 -> 201 us, 1..3 -> 190 us)
 #endif
 #ifndef S2D_FG_MIN_BLOCKS
-#define S2D_FG_MIN_BLOCKS 10  // 92 registers per thread (no spills), 20 warps per SM, 10 x 22 KB of shared memory
+#define S2D_FG_MIN_BLOCKS 10  // 96 registers per thread (spills only around the cold calls), 20 warps per SM, 10 x 22 KB of shared memory
 #endif
 
 // The block's shared memory: per player a row of kFgBlock entries (lane-minor: conflict-free).
@@ -925,8 +925,17 @@ __device__ __forceinline__ bool fg_cycle(FgShared& S, const int t, const int tid
     constexpr unsigned kFirstSubLanes = LPM == 1 ? 0xffffffffu : LPM == 2 ? 0x55555555u : 0x11111111u;
     const unsigned need = __ballot_sync(full, (pairs_close || ball_mask != 0u) && !stopped) & kFirstSubLanes;  // (AfterGoal: nothing moves)
     if (need) {
-      fg_resolve_collisions(S, t, lane, LPM, g, m, np, need, dead, r, r2, sp.collision_model(), obs_row ? P.obs : nullptr,
-                            static_cast<int64_t>(blockIdx.x) * (kFgBlock / LPM) + t, valid, collided_mask, touch, ball_collided);
+      // (copies in and out: a variable whose address a non-inlined function has seen lives on the stack for good, and with
+      // 220 KB of the SM's 256 KB taken as shared memory the stack is an L2 access)
+      Match mc = m;
+      uint32_t cm = 0, tc = 0;
+      bool bc = false;
+      fg_resolve_collisions(S, t, lane, LPM, g, mc, np, need, dead, r, r2, sp.collision_model(), obs_row ? P.obs : nullptr,
+                            static_cast<int64_t>(blockIdx.x) * (kFgBlock / LPM) + t, valid, cm, tc, bc);
+      m = mc;
+      collided_mask = cm;
+      touch = tc;
+      ball_collided = bc;
       if (LPM > 1) {  // the first sub-lane received the outcome: hand it to the others
         const int first = lane & ~(LPM - 1);
         m.bx = __shfl_sync(full, m.bx, first);
@@ -1155,7 +1164,9 @@ __global__ void __launch_bounds__(kFgBlock, S2D_FG_MIN_BLOCKS) fullgame_step_ker
       if (P.terminal_obs && writer) fg_write_obs(P.terminal_obs, env, g, m, np, half_time);
       if (P.auto_reset) {
         if (LPM > 1) __syncwarp();  // (the terminal observation reads the planes the reset rewrites)
-        fg_reset(S, t, g, m, P, sp, gid, np);
+        Match mc = m;  // (see fg_resolve_collisions' call)
+        fg_reset(S, t, g, mc, P, sp, gid, np);
+        m = mc;
         collided_mask = kicked_mask = 0;
         ball_collided = false;
         obs_dirty = true;

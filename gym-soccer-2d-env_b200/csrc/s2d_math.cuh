@@ -192,19 +192,6 @@ __device__ __forceinline__ void st_stream(float* p, float v) {
   asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
 #else
-// 256-bit accesses (sm_100): one full 32-byte sector per lane
-__device__ __forceinline__ void ld_nc_256(const float4* p, float4& a, float4& b) {
-  asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
-               : "l"(p));
-}
-__device__ __forceinline__ void st_stream_256(float4* p, const float4& a, const float4& b) {
-  asm volatile("st.global.L1::no_allocate.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(a.x), "f"(a.y), "f"(a.z),
-               "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w)
-               : "memory");
-}
-// asks the L2 for the line of p: one instruction per lane, no registers held while the data travels
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ float ld_stream(const float* p) { return *p; }
 __device__ __forceinline__ void st_stream(float* p, float v) { *p = v; }
 __device__ __forceinline__ float4 ld_stream(const float4* p) { return *p; }

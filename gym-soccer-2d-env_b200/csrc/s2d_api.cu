@@ -23,6 +23,7 @@ struct S2DSim {
   KernelParams kp;
   float4* d_table = nullptr;
   float* d_types = nullptr;  // heterogeneous players: [S2D_MAX_PLAYER_TYPES][PT_ROW]
+  uint8_t* d_type_of = nullptr;  // per-match assignment: [np][Nr]
   bool hetero = false;
   bool default_sp = false;  // cfg.sp == rcssserver defaults: use the constant-folded kernels
   bool bound = false;
@@ -233,6 +234,7 @@ int s2d_destroy(S2DHandle h) {
     DeviceGuard guard(h->cfg.device);
     if (h->d_table) cudaFree(h->d_table);
     if (h->d_types) cudaFree(h->d_types);
+    if (h->d_type_of) cudaFree(h->d_type_of);
     if (h->st_in) {
       cudaStreamSynchronize(h->st_in);
       cudaStreamSynchronize(h->st_compute);
@@ -765,7 +767,7 @@ int s2d_generate_player_types(uint64_t seed, const S2DServerParam* sp, S2DPlayer
   return S2D_OK;
 }
 
-int s2d_set_player_types(S2DHandle h, const S2DPlayerType* types, int n, const uint8_t* type_of_player) {
+static int set_player_types(S2DHandle h, const S2DPlayerType* types, int n, const uint8_t* type_of_player, bool per_match) {
   if (!h) return S2D_ERR_INVALID;
   if (h->cfg.scenario != S2D_SCENARIO_FULLGAME) return fail(h, S2D_ERR_INVALID, "player types exist in the FULLGAME scenario only");
   if (n == 0) {
@@ -794,19 +796,43 @@ int s2d_set_player_types(S2DHandle h, const S2DPlayerType* types, int n, const u
     r[PT_KICKABLE_AREA] = h->cfg.sp.player_size + h->cfg.sp.ball_size + t.kickable_margin;  // as S2D_DERIVED_PARAMS
   }
   uint8_t type_of[32] = {};
-  for (int j = 0; j < np; ++j) {
-    if (type_of_player[j] >= n) return fail(h, S2D_ERR_INVALID, "player %d has type %d, but there are %d types", j, type_of_player[j], n);
-    type_of[j] = type_of_player[j];
+  std::vector<uint8_t> planes;  // per match: transposed to the state's match-minor order, padding columns = type 0
+  const FgLayout L{h->cfg.num_envs, np};
+  if (per_match) {
+    planes.assign(L.nr() * np, 0);
+    for (int64_t e = 0; e < h->cfg.num_envs; ++e)
+      for (int j = 0; j < np; ++j) {
+        const uint8_t t = type_of_player[e * np + j];
+        if (t >= n) return fail(h, S2D_ERR_INVALID, "player %d of match %lld has type %d, but there are %d types", j, static_cast<long long>(e), t, n);
+        planes[static_cast<size_t>(j) * L.nr() + e] = t;
+      }
+  } else {
+    for (int j = 0; j < np; ++j) {
+      if (type_of_player[j] >= n) return fail(h, S2D_ERR_INVALID, "player %d has type %d, but there are %d types", j, type_of_player[j], n);
+      type_of[j] = type_of_player[j];
+    }
   }
   DeviceGuard guard(h->cfg.device);
   if (!h->d_types) S2D_CUDA(h, cudaMalloc(&h->d_types, sizeof(rows)));
   S2D_CUDA(h, cudaMemcpy(h->d_types, rows, sizeof(rows), cudaMemcpyHostToDevice));  // synchronous: later launches see it
+  if (per_match) {
+    if (!h->d_type_of) S2D_CUDA(h, cudaMalloc(&h->d_type_of, planes.size()));
+    S2D_CUDA(h, cudaMemcpy(h->d_type_of, planes.data(), planes.size(), cudaMemcpyHostToDevice));
+  }
   h->kp.player_types = h->d_types;
+  h->kp.type_of_match = per_match ? h->d_type_of : nullptr;
   memcpy(h->kp.type_of, type_of, sizeof(type_of));
   for (int k = 0; k < S2D_MAX_PIPELINE_SLOTS; ++k)
     if (h->slot_bound[k]) slot_params(h, k);
   h->hetero = true;
   return S2D_OK;
+}
+
+int s2d_set_player_types(S2DHandle h, const S2DPlayerType* types, int n, const uint8_t* type_of_player) {
+  return set_player_types(h, types, n, type_of_player, false);
+}
+int s2d_set_player_types_per_match(S2DHandle h, const S2DPlayerType* types, int n, const uint8_t* type_of_player) {
+  return set_player_types(h, types, n, type_of_player, true);
 }
 
 static int rollout_mlp(S2DHandle h, const S2DMlpPolicy* policy, int k_substeps, float epsilon, void* actions_out,

@@ -93,16 +93,26 @@ struct FgPlanes {
   float4* pa;
   float4* pb;
   float* pc;
+  const uint8_t* types;  // this match's column of the per-match player types ([np][Nr], s2d_set_player_types_per_match), else nullptr
   size_t row, rowc;  // elements per row
   __device__ __forceinline__ FgPlanes(const KernelParams& P, const FgLayout& L, int64_t env) {
     char* base = static_cast<char*>(P.state);
     pa = reinterpret_cast<float4*>(base + L.pa()) + env;
     pb = reinterpret_cast<float4*>(base + L.pb()) + env;
     pc = reinterpret_cast<float*>(base + L.pc()) + env;
+    types = P.type_of_match ? P.type_of_match + env : nullptr;
     row = L.nr();
     rowc = L.nr();
   }
 };
+
+// heterogeneous players: points sp at the constants of player j of this match (its own assignment if the handle has
+// one per match, else the handle's)
+template <class SP>
+__device__ __forceinline__ void fg_point_at_type(SP& sp, const KernelParams& P, const FgPlanes& g, const int j) {
+  if constexpr (SP::kHetero)
+    sp.row = sp.table + PT_ROW * (g.types ? static_cast<int>(__ldg(g.types + static_cast<size_t>(j) * g.row)) : static_cast<int>(P.type_of[j]));
+}
 
 // 4-4-2 kick-off formation of the left team (own half); the right team is the mirror image
 __device__ __constant__ float kFgFormX[11] = {-50, -36, -36, -36, -36, -20, -20, -20, -20, -9, -9};
@@ -161,7 +171,7 @@ __device__ __noinline__ void fg_reset(FgShared& S, int t, FgPlanes g, Match& m, 
   m.score_r = 0;
 #pragma unroll 1
   for (int j = 0; j < np; ++j) {
-    if constexpr (SP::kHetero) sp.row = sp.table + PT_ROW * P.type_of[j];
+    fg_point_at_type(sp, P, g, j);
     float2 xy;
     Episode p;
     fg_place_player(xy, p.body, P, gid, m.episode, j, np >> 1, 0);
@@ -605,7 +615,7 @@ __device__ __forceinline__ bool fg_cycle(FgShared& S, const int t, const int tid
     // `on`: the sub-lane has a player in this slot (with LPM > 1 the sub-lanes own 8 / 6 / 4 / 4 or 12 / 10 players and all
     // walk the longest list, so that the warp votes of fg_commands stay whole); j_next: the player it handles after this one
     auto one_player = [&](const int j, float4 a, const bool on, const int j_next) {
-      if constexpr (SP::kHetero) sp.row = sp.table + PT_ROW * P.type_of[on ? j : 0];
+      fg_point_at_type(sp, P, g, on ? j : 0);
       const float4 pa = n_a, b = n_b;
       const float cap = n_c;
       float4* const wpa = g.pa + static_cast<size_t>(j) * g.row;

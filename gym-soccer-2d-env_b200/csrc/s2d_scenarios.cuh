@@ -42,7 +42,8 @@ struct KernelParams {
   unsigned long long* stats;  // [kStatSlots][kStatWords]
   int32_t kick_actions;       // SHOOT Discrete(n): the last kick_actions actions are kicks
   const float* player_types;  // FULLGAME, heterogeneous players: [S2D_MAX_PLAYER_TYPES][PT_ROW] (device), else nullptr
-  uint8_t type_of[32];        // lane -> row of player_types
+  uint8_t type_of[32];        // player -> row of player_types (one assignment for every match of the handle)
+  const uint8_t* type_of_match;  // or one assignment per match: [np][Nr] (device, match-minor like the state), else nullptr
   const float4* action_table; // [256] Discrete(n) -> {cmd, power, lowered direction, dash direction rate}, built on the host
 };
 

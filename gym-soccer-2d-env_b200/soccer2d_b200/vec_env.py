@@ -70,6 +70,26 @@ class _SharedInfo(dict):
 _RUNNING = _SharedInfo(result=None)
 
 
+def per_match_type_assignment(seed: int, first_match: int, num_matches: int, players_per_side: int, num_types: int):
+    """uint8 [num_matches][2 * players_per_side]: the goalkeepers keep type 0, the field players of a team get different
+    non-default types (rcssserver's pt_max = 1) in an order that depends on (seed, GLOBAL match id, team) only."""
+    with np.errstate(over="ignore"):
+        gid = np.arange(first_match, first_match + num_matches, dtype=np.uint64)
+        x = (gid[:, None, None] * np.uint64(2) + np.arange(2, dtype=np.uint64)[None, :, None]) * np.uint64(64) \
+            + np.arange(num_types - 1, dtype=np.uint64)[None, None, :] + np.uint64(seed & 0xFFFFFFFF) * np.uint64(0x9E3779B97F4A7C15)
+        x = x + np.uint64(0x9E3779B97F4A7C15)  # splitmix64
+        x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        x = x ^ (x >> np.uint64(31))
+    order = np.argsort(x, axis=2, kind="stable").astype(np.uint8) + 1  # a permutation of the non-default types per team
+    field = players_per_side - 1
+    reps = -(-field // (num_types - 1))  # (more field players than non-default types: go round again)
+    order = np.tile(order, (1, 1, reps))[:, :, :field]
+    out = np.zeros((num_matches, 2, players_per_side), dtype=np.uint8)
+    out[:, :, 1:] = order
+    return out.reshape(num_matches, 2 * players_per_side)
+
+
 class LazyInfos(Sequence):
     """`infos` of Soccer2DVecEnv.step_wait: behaves like the list of per-env info dicts SB3 expects, but nothing is built
     until somebody looks.  Every running env answers with one shared read-only {'result': None}; an env whose episode
@@ -139,6 +159,9 @@ class Soccer2DVecEnv(_VecEnvBase):
     goto_dist_thr  Body_GoToPoint.distance_threshold for CMD_GOTO
     hetero_seed    fullgame: draw rcssserver's 18 heterogeneous player types from this seed and give every player but
                    the two goalkeepers a random one of them (see `set_player_types` for an explicit assignment)
+    hetero_per_match   with hetero_seed: every match gets an assignment of its own (rcssserver hands its types out match
+                   by match): per team ten different non-default types (pt_max = 1), drawn from a hash of (hetero_seed,
+                   global match id, team), so shards reproduce the global run
     noise          rcssserver's player_rand / ball_rand / kick_rand noise from the counter-based RNG, keyed on
                    (seed, global env id, server cycle, agent): reproducible, independent of sharding and of
                    `substeps`.  Off by default (the mode in which runs are compared with the double-precision CPU truth)
@@ -161,7 +184,7 @@ class Soccer2DVecEnv(_VecEnvBase):
     def __init__(self, num_envs: int, scenario: str = "reachball", device="cuda", seed: int = 0, substeps: int = 1,
                  env_id_offset: int = 0, auto_reset: bool = True, terminal_obs: bool = False,
                  server_param: dict | None = None, use_command_action: bool = False, goto_dist_thr: float = 0.5,
-                 noise: bool = False, host_mapped_io: bool = False, hetero_seed: int | None = None,
+                 noise: bool = False, host_mapped_io: bool = False, hetero_seed: int | None = None, hetero_per_match: bool = False,
                  host_numa_node: int | None = None, host_ring: int = 4, collision_model: str = "midpoint", **kwargs):
         if scenario.lower() not in _SCENARIOS:
             raise ValueError(f"Environment {scenario} not found.")  # environment_factory.py:28
@@ -293,9 +316,12 @@ class Soccer2DVecEnv(_VecEnvBase):
         self.type_of_player = None
         if hetero_seed is not None:
             types = self.generate_player_types(int(hetero_seed))
-            pick = np.random.default_rng(int(hetero_seed)).integers(1, len(types), size=self.num_players)
             pps = self.num_players // 2
-            pick[0] = pick[pps] = 0  # goalkeepers keep the default type, as rcssserver requires
+            if hetero_per_match:
+                pick = per_match_type_assignment(int(hetero_seed), self.env_id_offset, self.num_envs, pps, len(types))
+            else:
+                pick = np.random.default_rng(int(hetero_seed)).integers(1, len(types), size=self.num_players)
+                pick[0] = pick[pps] = 0  # goalkeepers keep the default type, as rcssserver requires
             self.set_player_types(types, pick)
         if _VecEnvBase is not object:
             _VecEnvBase.__init__(self, self.num_envs, self.observation_space, self.action_space)
@@ -733,17 +759,22 @@ class Soccer2DVecEnv(_VecEnvBase):
 
     def set_player_types(self, types, type_of_player) -> None:
         """`types`: list of _abi.PlayerType (or dicts of its fields); `type_of_player[j]`: the type of player j (left
-        team first), the same in every match.  Call before reset(): effort starts at the type's effort_max."""
+        team first), the same in every match - or `type_of_player[e][j]` ([num_envs][num_players]): an assignment of its
+        own for every match, as rcssserver hands out its types match by match.  Call before reset(): effort starts at
+        the type's effort_max."""
         arr = (_abi.PlayerType * len(types))()
         for k, t in enumerate(types):
             d = t if isinstance(t, dict) else t.as_dict()
             for name, v in d.items():
                 setattr(arr[k], name, float(v))
         tof = np.ascontiguousarray(np.asarray(type_of_player, dtype=np.uint8))
-        if tof.shape != (self.num_players,):
-            raise ValueError(f"type_of_player needs {self.num_players} entries")
-        _abi.check(self.lib.s2d_set_player_types(self.handle, arr, len(types), tof.ctypes.data_as(C.POINTER(C.c_uint8))),
-                   self.handle)
+        if tof.shape == (self.num_envs, self.num_players):
+            setter = self.lib.s2d_set_player_types_per_match
+        elif tof.shape == (self.num_players,):
+            setter = self.lib.s2d_set_player_types
+        else:
+            raise ValueError(f"type_of_player needs {self.num_players} entries, or [{self.num_envs}][{self.num_players}]")
+        _abi.check(setter(self.handle, arr, len(types), tof.ctypes.data_as(C.POINTER(C.c_uint8))), self.handle)
         self.player_types = [arr[k].as_dict() for k in range(len(types))]
         self.type_of_player = tof.copy()
 

@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define S2D_ABI_VERSION 11
+#define S2D_ABI_VERSION 12
 
 /* error codes */
 #define S2D_OK 0
@@ -408,6 +408,11 @@ int s2d_generate_player_types(uint64_t seed, const S2DServerParam* sp, S2DPlayer
  * type's effort_max).  From then on the step / reset kernels read the per-player values; n = 0 returns the handle to
  * homogeneous players.  FULLGAME only. */
 int s2d_set_player_types(S2DHandle h, const S2DPlayerType* types, int n, const uint8_t* type_of_player);
+/* The same with an assignment of its own for every match, as rcssserver hands out its types match by match:
+ * type_of_player is a HOST array [num_envs][s2d_num_players] (row e = the players of local match e).  The handle keeps a
+ * device copy (num_players bytes per match, read once per player and cycle).  The type TABLE stays one per handle: the
+ * matches differ in who plays with which of the n types, not in the types themselves. */
+int s2d_set_player_types_per_match(S2DHandle h, const S2DPlayerType* types, int n, const uint8_t* type_of_player);
 
 /* Closed-loop rollout with the policy inside the kernel (S2D_ACT_DISCRETE; REACHBALL with at most 16 actions, SHOOT
  * with at most 24).

@@ -92,6 +92,8 @@ def lib(kind: str):
         L.s2do_generate_player_types.argtypes = [C.c_uint64, C.c_void_p, C.c_void_p, C.c_int]
         L.s2do_set_player_types.restype = C.c_int
         L.s2do_set_player_types.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.s2do_set_player_types_per_match.restype = C.c_int
+        L.s2do_set_player_types_per_match.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.s2do_probe_sincos_deg.argtypes = [C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.s2do_probe_atan2_deg.restype = C.c_double
         L.s2do_probe_atan2_deg.argtypes = [C.c_double, C.c_double]
@@ -154,9 +156,11 @@ class OracleSim:
         return self.obs, self.reward, self.done, self.result
 
     def set_player_types(self, types_array, n, type_of_player):
-        """types_array: ctypes array of the product's PlayerType struct (same layout as S2DPlayerType)"""
+        """types_array: ctypes array of the product's PlayerType struct (same layout as S2DPlayerType); type_of_player:
+        [num_players], or [num_envs][num_players] for an assignment per match"""
         tof = np.ascontiguousarray(np.asarray(type_of_player, dtype=np.uint8))
-        assert self.L.s2do_set_player_types(self.h, C.byref(types_array), int(n), _ptr(tof)) == 0
+        setter = self.L.s2do_set_player_types_per_match if tof.ndim == 2 else self.L.s2do_set_player_types
+        assert setter(self.h, C.byref(types_array), int(n), _ptr(tof)) == 0
 
     def stats(self, stats_struct):
         self.L.s2do_stats(self.h, C.byref(stats_struct))

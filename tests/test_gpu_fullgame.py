@@ -195,6 +195,47 @@ def test_fullgame_tackles_catches_smart_kicks_and_the_goal_pause_bit_exact(k):
     env.close()
 
 
+@pytest.mark.parametrize("pps, k", [(11, 1), (11, 3), (4, 2)])
+def test_fullgame_player_types_per_match_bit_exact(pps, k):
+    """s2d_set_player_types_per_match: every match has its own assignment of the 18 types (rcssserver hands its types out
+    match by match).  Bit-exact against the oracle; a shard with env_id_offset reproduces its part of the global run; a
+    match whose row equals the per-handle assignment plays exactly like a handle that has that assignment."""
+    n = 150  # (ragged: three blocks of 64 columns, the last one mostly scratch)
+    kw = dict(scenario="fullgame", device="cuda:0", seed=5, substeps=k, terminal_obs=True, half_time_cycles=80,
+              players_per_side=pps)
+    env = Soccer2DVecEnv(n, hetero_seed=7, hetero_per_match=True, **kw)
+    np_ = 2 * pps
+    assert env.type_of_player.shape == (n, np_) and (env.type_of_player[:, 0] == 0).all() and (env.type_of_player[:, pps] == 0).all()
+    assert len({tuple(r) for r in env.type_of_player.tolist()}) == n  # all different
+    types = (_abi.PlayerType * 18)()
+    for j, t in enumerate(env.player_types):
+        for name, v in t.items():
+            setattr(types[j], name, v)
+    sim = OL.OracleSim(env.cfg, "f32")
+    sim.set_player_types(types, 18, env.type_of_player)
+    shard = Soccer2DVecEnv(50, env_id_offset=70, hetero_seed=7, hetero_per_match=True, **kw)
+    assert np.array_equal(shard.type_of_player, env.type_of_player[70:120])
+    one = Soccer2DVecEnv(n, **kw)
+    one.set_player_types(env.player_types, env.type_of_player[33])
+    assert np.array_equal(env.reset(), sim.reset())
+    shard.reset(), one.reset()
+    assert np.array_equal(gpu_state_fg(env), sim.get_state_fg())
+    rng = np.random.default_rng(2)
+    for t in range(-(-170 // k) + 3):  # (past the end of the first match: 2 x 80 cycles)
+        act = np.repeat(swarm_policy(sim.obs, np_, rng, random_frac=0.15), k, axis=1)
+        env.step_torch(torch.from_numpy(act))
+        shard.step_torch(torch.from_numpy(np.ascontiguousarray(act[70:120])))
+        one.step_torch(torch.from_numpy(act))
+        sim.step(act.reshape(n, -1), k)
+        same_step(env, sim)
+        assert np.array_equal(shard.obs.cpu().numpy(), env.obs.cpu().numpy()[70:120])
+        assert np.array_equal(one.obs.cpu().numpy()[33], env.obs.cpu().numpy()[33])
+    assert np.array_equal(gpu_state_fg(env), sim.get_state_fg())
+    assert env.stats()["episodes"] == sim.stats(_abi.Stats()).episodes > 0
+    for e in (env, shard, one):
+        e.close()
+
+
 @pytest.mark.parametrize("noise", [False, True])
 def test_fullgame_heterogeneous_players_bit_exact(noise):
     """rcssserver player types (PlayerType): every player but the goalkeepers plays with one of 17 drawn types; the

@@ -275,6 +275,49 @@ def test_intercept_meets_a_rolling_ball_sooner_than_chasing_it():
     assert reached[0] is not None and (reached[1] is None or reached[0] < reached[1]), reached
 
 
+def test_player_types_per_match_equal_one_handle_per_match():
+    """s2do_set_player_types_per_match (one assignment per match) against what it must mean: match e plays exactly like a
+    one-match handle with env_id_offset = e that was given row e as its per-handle assignment."""
+    import ctypes as C
+    from test_gpu_fullgame import swarm_policy
+    from soccer2d_b200.vec_env import per_match_type_assignment
+    n, pps = 5, 11
+    p = 2 * pps
+    lib = _abi.load()
+    cfg = H.make_config(n, "command", scenario=_abi.SCENARIO_FULLGAME, seed=21, half_time_cycles=60)
+    types = (_abi.PlayerType * 18)()
+    assert lib.s2d_generate_player_types(4, C.byref(cfg.sp), types, 18) == 0
+    assign = per_match_type_assignment(4, 0, n, pps, 18)
+    assert assign.shape == (n, p) and (assign[:, [0, pps]] == 0).all()
+    assert all(len(set(r[1:pps])) == pps - 1 and len(set(r[pps + 1:])) == pps - 1 for r in assign.tolist())  # pt_max = 1
+    assert np.array_equal(per_match_type_assignment(4, 2, 3, pps, 18), assign[2:])  # keyed on the global match id
+    for build in ("f64", "f32"):
+        whole = OL.OracleSim(cfg, build)
+        whole.set_player_types(types, 18, assign)
+        singles = []
+        for e in range(n):
+            c1 = H.make_config(1, "command", scenario=_abi.SCENARIO_FULLGAME, seed=21, half_time_cycles=60, env_id_offset=e)
+            s1 = OL.OracleSim(c1, build)
+            s1.set_player_types(types, 18, assign[e])
+            s1.reset()
+            singles.append(s1)
+        obs = whole.reset().copy()
+        assert all(np.array_equal(obs[e], singles[e].obs[0]) for e in range(n))
+        rng = np.random.default_rng(8)
+        for t in range(150):
+            act = swarm_policy(whole.obs, p, rng, random_frac=0.2)
+            whole.step(act.reshape(n, -1))
+            for e in range(n):
+                singles[e].step(act[e].reshape(1, -1))
+                assert np.array_equal(whole.obs[e], singles[e].obs[0]) and whole.done[e] == singles[e].done[0]
+        assert whole.done.any() or t > 100
+    # a row with an unknown type is refused
+    bad = assign.copy()
+    bad[3, 5] = 18
+    with pytest.raises(AssertionError):
+        OL.OracleSim(cfg, "f64").set_player_types(types, 18, bad)
+
+
 def test_fullgame_invariants_with_player_types_and_referee():
     """11 v 11 in the f64 build with rcssserver's heterogeneous player types, swarm play for 400 cycles: the physical
     limits of every player's own type hold, the referee's state stays consistent (dead ball inside the pitch, offside

@@ -86,6 +86,12 @@ struct FgShared {
   float2 xy[kFgMaxPlayers][kFgBlock];  // position (the same values as plane PA holds)
   float oldx[kFgMaxPlayers][kFgBlock]; // x before this cycle's move (the offside line is drawn at the moment of the pass)
   float obs[20][kFgBlock];             // four players' worth of the observation row on its way out (five float4)
+#ifdef S2D_FG_PAD
+  char pad[S2D_FG_PAD];                // (tuning aid: lowers the number of resident blocks)
+#endif
+  uint32_t kicked[kFgBlock];           // per thread: the players (bits) that kicked this cycle.  Kicks are rare; as a register
+                                       // variable the mask was spilled, and its reload (an L2 round trip: the SM's L1 is
+                                       // given to shared memory) sat in front of every player: 10 % of the kernel's time
 };
 
 // Plane pointers of one match (column t of every row), advanced by a row to go from player j to player j + 1.
@@ -248,7 +254,7 @@ __device__ __forceinline__ bool fg_commands(Episode& p, float4 a, float goto_dis
   // turn
   const bool do_turn = user_turn || goto_turn;
   if (__any_sync(full, do_turn)) {
-    const float speed = hypot2(do_turn ? p.vx : 1.0f, do_turn ? p.vy : 0.0f);
+    const float speed = hypot2_or_zero(do_turn ? p.vx : 1.0f, do_turn ? p.vy : 0.0f);  // (a standing player: often)
     const float inertia = 1.0f + sp.inertia_moment() * speed;
     float moment = goto_turn ? clampf(sp.min_moment(), rel * inertia, sp.max_moment()) : user_turn ? a.y : 1.0f;
     moment = clampf(sp.min_moment(), moment, sp.max_moment());
@@ -585,7 +591,7 @@ __device__ __forceinline__ bool fg_cycle(FgShared& S, const int t, const int tid
   }
 
   // ---- every player: command, move, stamina (the private part of the player streams through registers) ----
-  uint32_t kick_mask = 0;
+  S.kicked[tid] = 0u;
   float kx[32], ky[32];  // the kickers' pushes on the ball (local memory; written only when somebody kicks)
   float moved2 = 0.0f;
   const uint32_t tk0_in = m.tk0, tk1_in = m.tk1, tk2_in = m.tk2, ban_in = m.ban;
@@ -719,7 +725,7 @@ __device__ __forceinline__ bool fg_cycle(FgShared& S, const int t, const int tid
         p.vy = 0.0f;
       }
       if (kicked && on) {
-        kick_mask |= 1u << j;
+        S.kicked[tid] |= 1u << j;
         kx[j] = kax;
         ky[j] = kay;
       }
@@ -735,23 +741,43 @@ __device__ __forceinline__ bool fg_cycle(FgShared& S, const int t, const int tid
       st_stream(wpb, make_float4(p.body, p.stamina, p.effort, p.recovery));
       st_stream(wpc, p.capacity);
       if (obs_row) {  // (uniform) four players = 20 floats = five float4 of the row, starting at float4 1 + 5 (j / 4)
-        const int q = j & 3;
+        const int q = j & 3, grp = j >> 2;
         float(*stg)[kFgBlock] = S.obs + 5 * q;
         stg[0][tid] = p.px * static_cast<float>(1.0 / 52.5);
         stg[1][tid] = p.py * static_cast<float>(1.0 / 34.0);
         stg[2][tid] = p.vx;
         stg[3][tid] = p.vy;
         stg[4][tid] = p.body * static_cast<float>(1.0 / 180.0);
-        if (valid && (q == 3 || j == np - 1)) {
-          float4* o = reinterpret_cast<float4*>(obs_row) + 1 + 5 * (j >> 2);
-          st_stream(o, make_float4(S.obs[0][tid], S.obs[1][tid], S.obs[2][tid], S.obs[3][tid]));
-          st_stream(o + 1, make_float4(S.obs[4][tid], S.obs[5][tid], S.obs[6][tid], S.obs[7][tid]));
+        auto f4 = [&](int r) { return make_float4(S.obs[r][tid], S.obs[r + 1][tid], S.obs[r + 2][tid], S.obs[r + 3][tid]); };
+        if (LPM == 1) {
+          // Whole 32-byte sectors only (a half-written sector costs the L2 about as much as two whole ones: measured,
+          // profiles/micro/fg_layout.cu).  A group's five float4 start at an odd float4 of the row in the even groups and
+          // at an even one in the odd groups, so an odd group leaves its last float4 (rows 16-19) behind for the first
+          // float4 of the next one.  The first float4 of group 0 shares its sector with the ball and the last two floats
+          // of player 21 share theirs with the referee's values: those two sectors are written at the end of the launch.
+          if (valid) {
+            float4* o = reinterpret_cast<float4*>(obs_row) + 5 * grp;  // the group's values are o[1] .. o[5]
+            if ((grp & 1) == 0) {
+              if (q == 0 && grp > 0) st_stream_256(o, f4(16), f4(0));
+              if (q == 3) {
+                st_stream_256(o + 2, f4(4), f4(8));
+                st_stream_256(o + 4, f4(12), f4(16));
+              }
+            } else if (q == 3) {
+              st_stream_256(o + 1, f4(0), f4(4));
+              st_stream_256(o + 3, f4(8), f4(12));
+            } else if (j == np - 1) {  // players 20 and 21: floats 104..111
+              st_stream_256(o + 1, f4(0), f4(4));
+            }
+          }
+        } else if (valid && (q == 3 || j == np - 1)) {
+          float4* o = reinterpret_cast<float4*>(obs_row) + 1 + 5 * grp;
+          st_stream(o, f4(0));
+          st_stream(o + 1, f4(4));
           if (q == 3) {
-            st_stream(o + 2, make_float4(S.obs[8][tid], S.obs[9][tid], S.obs[10][tid], S.obs[11][tid]));
-            st_stream(o + 3, make_float4(S.obs[12][tid], S.obs[13][tid], S.obs[14][tid], S.obs[15][tid]));
-            st_stream(o + 4, make_float4(S.obs[16][tid], S.obs[17][tid], S.obs[18][tid], S.obs[19][tid]));
-          } else {  // players 20 and 21: floats 104..113; 114..119 are the referee's, written at the end of the launch
-            reinterpret_cast<float2*>(o + 2)[0] = make_float2(S.obs[8][tid], S.obs[9][tid]);
+            st_stream(o + 2, f4(8));
+            st_stream(o + 3, f4(12));
+            st_stream(o + 4, f4(16));
           }
         }
       }
@@ -766,6 +792,7 @@ __device__ __forceinline__ bool fg_cycle(FgShared& S, const int t, const int tid
       one_player(j + 1, c1, on, j_after);
     }
   }
+  uint32_t kick_mask = S.kicked[tid];
   if (LPM > 1) {  // what the sub-lanes of a match found, merged: every one of them goes on with the whole picture
     __syncwarp();
     uint32_t d0 = m.tk0 ^ tk0_in, d1 = m.tk1 ^ tk1_in, d2 = m.tk2 ^ tk2_in, db = m.ban ^ ban_in;  // (disjoint nibbles)
@@ -1190,13 +1217,21 @@ __global__ void __launch_bounds__(kFgBlock, S2D_FG_MIN_BLOCKS) fullgame_step_ker
   fg_store(P, L, env, m, collided_mask, kicked_mask, ball_collided);
   if (NP != kFgMaxPlayers || obs_dirty) {
     fg_write_obs(P.obs, env, g, m, np, half_time);  // the whole row from the planes
-  } else {  // the players' part is written: the ball and the referee's six values
+  } else {
+    // the players' part is written, up to the two sectors they share with the ball (floats 0..7) and with the referee's
+    // six values (floats 112..119): both are written whole, the players' halves from the planes (as the player loop
+    // wrote them, or as the referee / the collisions left them since)
     float4* row = reinterpret_cast<float4*>(my_obs);
-    st_stream(row, make_float4(m.bx * static_cast<float>(1.0 / 52.5), m.by * static_cast<float>(1.0 / 34.0),
-                               m.bvx * static_cast<float>(1.0 / 3.0), m.bvy * static_cast<float>(1.0 / 3.0)));
-    reinterpret_cast<float2*>(my_obs)[57] = make_float2(static_cast<float>(m.mode), static_cast<float>(m.side));
-    st_stream(row + 29, make_float4(static_cast<float>(m.score_l), static_cast<float>(m.score_r),
-                                    static_cast<float>(m.step_number) / static_cast<float>(2 * half_time), 0.0f));
+    const float4 a0 = ld_stream(g.pa), a21 = ld_stream(g.pa + static_cast<size_t>(kFgMaxPlayers - 1) * g.row);
+    const float body21 = ld_stream(reinterpret_cast<const float*>(g.pb + static_cast<size_t>(kFgMaxPlayers - 1) * g.row));
+    st_stream_256(row,
+                  make_float4(m.bx * static_cast<float>(1.0 / 52.5), m.by * static_cast<float>(1.0 / 34.0),
+                              m.bvx * static_cast<float>(1.0 / 3.0), m.bvy * static_cast<float>(1.0 / 3.0)),
+                  make_float4(a0.x * static_cast<float>(1.0 / 52.5), a0.y * static_cast<float>(1.0 / 34.0), a0.z, a0.w));
+    st_stream_256(row + 28,
+                  make_float4(a21.w, body21 * static_cast<float>(1.0 / 180.0), static_cast<float>(m.mode), static_cast<float>(m.side)),
+                  make_float4(static_cast<float>(m.score_l), static_cast<float>(m.score_r),
+                              static_cast<float>(m.step_number) / static_cast<float>(2 * half_time), 0.0f));
   }
   P.reward[env] = reward_sum;
   P.done[env] = static_cast<uint8_t>(any_done);

@@ -26,6 +26,13 @@ __device__ __forceinline__ float fmax_(float a, float b) { return fmaxf(a, b); }
 __device__ __forceinline__ float clampf(float lo, float x, float hi) { return fmaxf(lo, fminf(x, hi)); }
 
 __device__ __forceinline__ float hypot2(float x, float y) { return sqrtf(x * x + y * y); }
+// The same value for an operand that is often the zero vector (the velocity of a player at rest): sqrt(0) is answered
+// by the IEEE square root's out-of-line slow path, and a call makes the warp wait for every load in flight first.
+__device__ __forceinline__ float hypot2_or_zero(float x, float y) {
+  const bool zero = x == 0.0f && y == 0.0f;
+  const float h = hypot2(zero ? 1.0f : x, y);
+  return zero ? 0.0f : h;
+}
 
 // cold paths kept out of line: they are (almost) never taken, and inlining them costs registers and I-cache
 __device__ __noinline__ float cold_fmod360(float d) { return fmodf(d, 360.0f); }

@@ -125,7 +125,7 @@ template <class SP>
 __device__ __forceinline__ void turn(Episode& e, float moment, const SP& sp, const NoiseCtx& nz, uint32_t agent = 0) {
   moment = clampf(sp.min_moment(), moment, sp.max_moment());
   if (SP::kNoise) moment = moment * (1.0f + sp.player_rand() * u11(noise_block(nz, agent).z));
-  const float speed = hypot2(e.vx, e.vy);
+  const float speed = hypot2_or_zero(e.vx, e.vy);
   e.body = norm_deg(e.body + moment / (1.0f + sp.inertia_moment() * speed));
 }
 
@@ -178,7 +178,7 @@ __device__ __forceinline__ void lower_goto(const Episode& e, float tx, float ty,
   // asin(ratio) exceeds 15 degrees only for ratio > sin(15 deg) = 0.2588: below 0.25 the threshold is exactly 15
   const float athr = ratio > 0.25f ? fmax_(15.0f, atan2_deg(ratio, sqrtf(fmax_(0.0f, 1.0f - ratio * ratio)))) : 15.0f;
   if (fabsf(ang) > athr) {
-    const float speed = hypot2(e.vx, e.vy);
+    const float speed = hypot2_or_zero(e.vx, e.vy);
     cmd = S2D_CMD_TURN;
     dir = clampf(sp.min_moment(), ang * (1.0f + sp.inertia_moment() * speed), sp.max_moment());
     return;

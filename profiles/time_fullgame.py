@@ -16,7 +16,10 @@ steps = int(sys.argv[2]) if len(sys.argv) > 2 else 60
 dev = torch.device("cuda:0")
 gen = torch.Generator(device=dev).manual_seed(99)
 env = Soccer2DVecEnv(n, scenario="fullgame", device=dev, seed=0, substeps=k)
-pool = [bench.commands(torch, gen, dev, (n, k, 22)) for _ in range(2)]
+pool = [bench.commands(torch, gen, dev, (n, k, 22)) for _ in range(int(os.environ.get("FG_POOL", 2)))]
+if os.environ.get("FG_CMD"):  # every player the same kind of command (0 none, 1 dash, 2 turn, 3 kick, 4 go-to-point): no mixed warps
+    for p in pool:
+        p[..., 0] = float(os.environ["FG_CMD"])
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 for name, fl in (("flush", flush), ("noflush", None)):
     env.reset_torch()

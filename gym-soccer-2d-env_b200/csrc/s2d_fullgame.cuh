@@ -340,14 +340,15 @@ __device__ __forceinline__ float butterfly_sum(float v) {
 // matches of the warp: so the WARP resolves each such match together, lane l = player l of that match - positions come
 // from shared memory, partner positions are shuffle broadcasts, the ball's proposals are summed with an xor butterfly.
 // In a round every object collects the positions proposed for it and moves to their average; afterwards whatever
-// collided gets vel *= -0.1 once.  The lane that owns the match receives the masks (players that collided, players that
-// touched the ball) and the ball; the player lanes write positions and velocities back (shared memory, plane PA and,
+// collided gets vel *= -0.1 once.  The lane that owns the match finds the masks (players that collided, players that touched the
+// ball) and the ball in rows 0-4 of its observation staging column (nothing is passed by reference: a variable whose
+// address a non-inlined function has seen lives in local memory for good); the player lanes write positions and velocities back (shared memory, plane PA and,
 // when `obs_rows` (the observation tensor) is set - last cycle of a launch -, the row the player loop has already written).
-__device__ __noinline__ void fg_resolve_collisions(FgShared& S, const int t, const int lane, const int lpm, const FgPlanes g, Match& m,
+__device__ __noinline__ void fg_resolve_collisions(FgShared& S, const int t, const int tid, const int lane, const int lpm, const FgPlanes g,
+                                                   const float mbx, const float mby, const float mbvx, const float mbvy,
                                                    const int np, unsigned need,
                                                    const bool dead, const float r, const float r2, const int model, float* obs_rows,
-                                                   const int64_t env, const bool valid,
-                                                   uint32_t& collided_mask, uint32_t& touch, bool& ball_collided) {
+                                                   const int64_t env, const bool valid) {
   // (t = this thread's match column in shared memory; with lpm lanes per match, lane l holds column t - l / lpm + ..)
   const unsigned full = 0xffffffffu;
   const bool active = lane < np;
@@ -358,8 +359,8 @@ __device__ __noinline__ void fg_resolve_collisions(FgShared& S, const int t, con
     need &= need - 1u;
     const int dcol = src / lpm - lane / lpm;  // from this thread's match to the match being resolved
     const int ts = t + dcol;                  // its column in shared memory
-    float bx = __shfl_sync(full, m.bx, src), by = __shfl_sync(full, m.by, src);
-    const float bvx = __shfl_sync(full, m.bvx, src), bvy = __shfl_sync(full, m.bvy, src);
+    float bx = __shfl_sync(full, mbx, src), by = __shfl_sync(full, mby, src);
+    const float bvx = __shfl_sync(full, mbvx, src), bvy = __shfl_sync(full, mbvy, src);
     const bool ball_fixed = __shfl_sync(full, static_cast<int>(dead), src) != 0;
     const bool report = __shfl_sync(full, static_cast<int>(valid), src) != 0;
     float2 pos = active ? S.xy[lane][ts] : make_float2(0.0f, 0.0f);
@@ -447,17 +448,12 @@ __device__ __noinline__ void fg_resolve_collisions(FgShared& S, const int t, con
         o[3] = vy;
       }
     }
-    if (lane == src) {
-      m.bx = bx;
-      m.by = by;
-      if (ball_any) {
-        m.bvx *= -0.1f;
-        m.bvy *= -0.1f;
-      }
-      m.sep = 0.0f;  // players were pushed around: measure again next cycle
-      collided_mask = cm;
-      touch = tm;
-      ball_collided = ball_any;
+    if (lane == src) {  // the outcome, left in the owner's (free by now) observation staging column
+      S.obs[0][tid] = bx;
+      S.obs[1][tid] = by;
+      S.obs[2][tid] = __uint_as_float(ball_any ? 1u : 0u);
+      S.obs[3][tid] = __uint_as_float(cm);
+      S.obs[4][tid] = __uint_as_float(tm);
     }
   }
   __syncwarp();  // what the player lanes wrote (shared memory, plane PA) is read by the matches' own threads next
@@ -939,20 +935,27 @@ __device__ __forceinline__ bool fg_cycle(FgShared& S, const int t, const int tid
   }
   bool pairs_close = false;
   if (__any_sync(full, m.sep < r2)) {
+    // (the smallest squared distance, with sm_100's packed fp32 instructions: {dx, dy} and their squares take one issue
+    // slot each.  The value only feeds the bound and the conservative test below - the resolver makes the exact tests in
+    // the fp32 spec's own arithmetic - so it does not matter that the assembler may fuse packed operations.)
     float m2 = 3.0e38f;
 #pragma unroll 1
     for (int i = h; i + 1 < np; i += LPM) {
-      const float2 pi = S.xy[i][t];
+      const unsigned long long pi = *reinterpret_cast<const unsigned long long*>(&S.xy[i][t]);
 #pragma unroll 4
       for (int j = i + 1; j < np; ++j) {
-        const float2 pj = S.xy[j][t];
-        const float ex = pi.x - pj.x, ey = pi.y - pj.y;
-        m2 = fminf(m2, ex * ex + ey * ey);
+        const unsigned long long pj = *reinterpret_cast<const unsigned long long*>(&S.xy[j][t]);
+        unsigned long long d;
+        float sx, sy;
+        asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pi), "l"(pj));
+        asm("mul.rn.f32x2 %0, %0, %0;" : "+l"(d));
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(sx), "=f"(sy) : "l"(d));
+        m2 = fminf(m2, sx + sy);
       }
     }
 #pragma unroll
     for (int sft = 1; sft < LPM; sft <<= 1) m2 = fminf(m2, __shfl_xor_sync(full, m2, sft));
-    pairs_close = m2 < r2 * r2;
+    pairs_close = m2 < r2 * r2 * 1.000001f;  // (a last-bit difference from the resolver's own sums must not hide a pair)
     m.sep = sqrtf(m2) * 0.999f;
   }
   collided_mask = 0;
@@ -962,27 +965,21 @@ __device__ __forceinline__ bool fg_cycle(FgShared& S, const int t, const int tid
     constexpr unsigned kFirstSubLanes = LPM == 1 ? 0xffffffffu : LPM == 2 ? 0x55555555u : 0x11111111u;
     const unsigned need = __ballot_sync(full, (pairs_close || ball_mask != 0u) && !stopped) & kFirstSubLanes;  // (AfterGoal: nothing moves)
     if (need) {
-      // (copies in and out: a variable whose address a non-inlined function has seen lives on the stack for good, and with
-      // 220 KB of the SM's 256 KB taken as shared memory the stack is an L2 access)
-      Match mc = m;
-      uint32_t cm = 0, tc = 0;
-      bool bc = false;
-      fg_resolve_collisions(S, t, lane, LPM, g, mc, np, need, dead, r, r2, sp.collision_model(), obs_row ? P.obs : nullptr,
-                            static_cast<int64_t>(blockIdx.x) * (kFgBlock / LPM) + t, valid, cm, tc, bc);
-      m = mc;
-      collided_mask = cm;
-      touch = tc;
-      ball_collided = bc;
-      if (LPM > 1) {  // the first sub-lane received the outcome: hand it to the others
-        const int first = lane & ~(LPM - 1);
-        m.bx = __shfl_sync(full, m.bx, first);
-        m.by = __shfl_sync(full, m.by, first);
-        m.bvx = __shfl_sync(full, m.bvx, first);
-        m.bvy = __shfl_sync(full, m.bvy, first);
-        m.sep = __shfl_sync(full, m.sep, first);
-        collided_mask = __shfl_sync(full, collided_mask, first);
-        touch = __shfl_sync(full, touch, first);
-        ball_collided = __shfl_sync(full, static_cast<int>(ball_collided), first) != 0;
+      fg_resolve_collisions(S, t, tid, lane, LPM, g, m.bx, m.by, m.bvx, m.bvy, np, need, dead, r, r2, sp.collision_model(),
+                            obs_row ? P.obs : nullptr, static_cast<int64_t>(blockIdx.x) * (kFgBlock / LPM) + t, valid);
+      const int first = lane & ~(LPM - 1);  // the sub-lane that stood for the match
+      if ((need >> first) & 1u) {
+        const int col = tid & ~(LPM - 1);
+        m.bx = S.obs[0][col];
+        m.by = S.obs[1][col];
+        ball_collided = __float_as_uint(S.obs[2][col]) != 0u;
+        collided_mask = __float_as_uint(S.obs[3][col]);
+        touch = __float_as_uint(S.obs[4][col]);
+        if (ball_collided) {
+          m.bvx *= -0.1f;
+          m.bvy *= -0.1f;
+        }
+        m.sep = 0.0f;  // players were pushed around: measure again next cycle
       }
     }
   }

@@ -207,10 +207,14 @@ __global__ void __launch_bounds__(kBlock, S2D_ROLLOUT_MIN_BLOCKS)
 #pragma unroll 1
   for (int k = 0; k < K; ++k) {
     scenario_obs<SCN>(e, obs_row);
-    if (T.obs && valid) {
-      float* dst = T.obs + (static_cast<int64_t>(k) * n + i) * kObsDim;
+    if (T.obs && warp_first < n) {
+      if ((n & 1) == 0) {  // whole sectors: the warp's 32 rows go out as 512-byte stores (slices of n rows stay 16-byte aligned)
+        warp_store_obs(T.obs + static_cast<int64_t>(k) * n * kObsDim, warp_first, n, obs_row, valid, s_stage[warp]);
+      } else if (valid) {
+        float* dst = T.obs + (static_cast<int64_t>(k) * n + i) * kObsDim;
 #pragma unroll
-      for (int f = 0; f < kObsDim; f += 2) *reinterpret_cast<float2*>(dst + f) = make_float2(obs_row[f], obs_row[f + 1]);
+        for (int f = 0; f < kObsDim; f += 2) *reinterpret_cast<float2*>(dst + f) = make_float2(obs_row[f], obs_row[f + 1]);
+      }
     }
     {  // A1: the observation row, TF32, features 10..15 zero
       float v[16];
@@ -293,18 +297,22 @@ __global__ void __launch_bounds__(kBlock, S2D_ROLLOUT_MIN_BLOCKS)
   if (valid) {
     store_episode(P.state, n, i, e);
     scenario_obs<SCN>(e, obs_row);
-    if (T.obs) {
-      float* dst = T.obs + (static_cast<int64_t>(K) * n + i) * kObsDim;
-#pragma unroll
-      for (int f = 0; f < kObsDim; ++f) dst[f] = obs_row[f];
-    }
     P.reward[i] = out.reward_sum;
     P.done[i] = static_cast<uint8_t>(out.ended != 0);
     P.result[i] = static_cast<uint8_t>(out.last_result());
   } else {
     out = LaunchOut();
   }
-  if (warp_first < n) warp_store_obs(P.obs, warp_first, n, obs_row, valid, s_stage[warp]);
+  if (warp_first < n) {
+    if (T.obs && (n & 1) == 0) {
+      warp_store_obs(T.obs + static_cast<int64_t>(K) * n * kObsDim, warp_first, n, obs_row, valid, s_stage[warp]);
+    } else if (T.obs && valid) {
+      float* dst = T.obs + (static_cast<int64_t>(K) * n + i) * kObsDim;
+#pragma unroll
+      for (int f = 0; f < kObsDim; ++f) dst[f] = obs_row[f];
+    }
+    warp_store_obs(P.obs, warp_first, n, obs_row, valid, s_stage[warp]);
+  }
   flush_tally(out, P.stats);
   tc5_fence_before();
   __syncthreads();

@@ -373,53 +373,60 @@ __device__ __noinline__ void fg_resolve_collisions(FgShared& S, const int t, con
     bool collided = false, ballhit = false, ball_any = false;
 #pragma unroll 1
     for (int round = 0; round < 10; ++round) {
-      bool col = false;
-      int cnt = 0;
-      float sx = 0.0f, sy = 0.0f, bpx = 0.0f, bpy = 0.0f;
-      bool bc = false;
-#pragma unroll 1
+      // Pass 1, without a branch: which players overlap this lane's player (bit j), and does the ball.  The tests are the
+      // specification's own (ex * ex + ey * ey < r2 * r2, ...).  Almost every pair says no, so finding the few that say
+      // yes first keeps the expensive part below out of the 22-iteration loop.
+      uint32_t hits = 0;
+#pragma unroll 2
       for (int j = 0; j < np; ++j) {
         const float xj = __shfl_sync(full, pos.x, j), yj = __shfl_sync(full, pos.y, j);
-        if (!active) continue;
+        const float ex = pos.x - xj, ey = pos.y - yj;
+        hits |= (ex * ex + ey * ey < r2 * r2) ? 1u << j : 0u;
+      }
+      hits &= active ? ~(1u << lane) : 0u;
+      const float dx = bx - pos.x, dy = by - pos.y;
+      const bool bc = active && !ball_fixed && dx * dx + dy * dy < r * r;
+      hits |= bc ? 1u << lane : 0u;
+      const bool col = hits != 0u;
+      collided |= col;
+      ballhit |= bc;
+      // Pass 2: the proposals, partner by partner in increasing player index (the order of these sums is part of the
+      // fp32 spec); bit `lane` stands for the ball.  Lanes take as many turns as the busiest of them has partners.
+      int cnt = 0;
+      float sx = 0.0f, sy = 0.0f, bpx = 0.0f, bpy = 0.0f;
+#pragma unroll 1
+      for (uint32_t rest = hits; __any_sync(full, rest != 0u); rest &= rest - 1u) {
+        const int j = rest ? __ffs(rest) - 1 : lane;
+        const float xj = __shfl_sync(full, pos.x, j), yj = __shfl_sync(full, pos.y, j);
+        if (rest == 0u) continue;
         if (j == lane) {
-          if (ball_fixed) continue;
-          const float dx = bx - pos.x, dy = by - pos.y;
-          if (dx * dx + dy * dy < r * r) {
-            col = collided = ballhit = bc = true;
-            const float2 b = ball_back_trace(pos.x, pos.y, bx, by, bvx, bvy, r + kCollideEps);
-            bpx = b.x;
-            bpy = b.y;
-            float2 own = pos;
-            if (model == S2D_COLLISION_BACKTRACE) own = ball_back_trace(bx, by, pos.x, pos.y, vel.x, vel.y, r + kCollideEps, -1.0f);
-            sx += own.x;
-            sy += own.y;
-            cnt += 1;
-          }
+          const float2 b = ball_back_trace(pos.x, pos.y, bx, by, bvx, bvy, r + kCollideEps);
+          bpx = b.x;
+          bpy = b.y;
+          float2 own = pos;
+          if (model == S2D_COLLISION_BACKTRACE) own = ball_back_trace(bx, by, pos.x, pos.y, vel.x, vel.y, r + kCollideEps, -1.0f);
+          sx += own.x;
+          sy += own.y;
+        } else if (model == S2D_COLLISION_BACKTRACE) {
+          const float2 own = ball_back_trace(xj, yj, pos.x, pos.y, vel.x, vel.y, r2 + kCollideEps, lane < j ? 1.0f : -1.0f);
+          sx += own.x;
+          sy += own.y;
         } else {
           const float ex = pos.x - xj, ey = pos.y - yj;
-          if (ex * ex + ey * ey < r2 * r2) {
-            col = collided = true;
-            if (model == S2D_COLLISION_BACKTRACE) {
-              const float2 own = ball_back_trace(xj, yj, pos.x, pos.y, vel.x, vel.y, r2 + kCollideEps, lane < j ? 1.0f : -1.0f);
-              sx += own.x;
-              sy += own.y;
-            } else {
-              const float mx = (pos.x + xj) / 2.0f, my = (pos.y + yj) / 2.0f;
-              const float d = hypot2(ex, ey);
-              float ux, uy;
-              if (d < 1.0e-10f) {
-                ux = lane < j ? 1.0f : -1.0f;
-                uy = 0.0f;
-              } else {
-                ux = ex / d;
-                uy = ey / d;
-              }
-              sx += mx + ux * h;
-              sy += my + uy * h;
-            }
-            cnt += 1;
+          const float mx = (pos.x + xj) / 2.0f, my = (pos.y + yj) / 2.0f;
+          const float d = hypot2(ex, ey);
+          float ux, uy;
+          if (d < 1.0e-10f) {
+            ux = lane < j ? 1.0f : -1.0f;
+            uy = 0.0f;
+          } else {
+            ux = ex / d;
+            uy = ey / d;
           }
+          sx += mx + ux * h;
+          sy += my + uy * h;
         }
+        cnt += 1;
       }
       const int bcnt = __popc(__ballot_sync(full, bc));
       const float bsx = butterfly_sum(bpx), bsy = butterfly_sum(bpy);

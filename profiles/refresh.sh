@@ -13,11 +13,17 @@ python bench.py --steps 20 --warmup 3 > /dev/null 2>&1 && \
 python profiles/tune_scenarios.py > $O/${TAG}_scenarios.txt 2>&1
 python profiles/tune.py >> $O/${TAG}_scenarios.txt 2>&1
 python profiles/time_fullgame.py 1 60 >> $O/${TAG}_scenarios.txt 2>&1
+echo "--- fresh commands every cycle (8 command tensors in turn: the bench workload)" >> $O/${TAG}_scenarios.txt
+FG_POOL=8 python profiles/time_fullgame.py 1 30 >> $O/${TAG}_scenarios.txt 2>&1
+echo "--- every player the same kind of command: 0 none, 1 dash, 4 go-to-point" >> $O/${TAG}_scenarios.txt
+for c in 0 1 4; do FG_CMD=$c python profiles/time_fullgame.py 1 10 2>&1 | grep "^flush" >> $O/${TAG}_scenarios.txt; done
+python profiles/time_step_phases.py >> $O/${TAG}_scenarios.txt 2>&1
+nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o /tmp/fg_layout profiles/micro/fg_layout.cu && /tmp/fg_layout > $O/${TAG}_fg_layout_probe.txt 2>&1
 python profiles/time_fullgame.py 16 6 >> $O/${TAG}_scenarios.txt 2>&1
 FG_MATCHES=32768 python profiles/time_fullgame.py 1 30 >> $O/${TAG}_scenarios.txt 2>&1
 python profiles/tune_rollout.py >> $O/${TAG}_scenarios.txt 2>&1
 python profiles/prof_step.py both 2 > /dev/null 2>&1 && {
-  ncu --set full --clock-control none --import-source on -k regex:step_kernel -s 14 -c 1 -o $O/prof_${TAG}_k16 -f python profiles/prof_step.py k16 2 > $O/ncu_full.log 2>&1
+  ncu --set full --clock-control none --import-source on -k regex:step_kernel -s 150 -c 1 -o $O/prof_${TAG}_k16 -f python profiles/prof_step.py k16 2 150 > $O/ncu_full.log 2>&1
   ncu --set full --clock-control none --import-source on -k regex:step_kernel -s 6 -c 1 -o $O/prof_${TAG}_k1 -f python profiles/prof_step.py k1 2 >> $O/ncu_full.log 2>&1
 }
 python profiles/prof_fullgame.py > /dev/null 2>&1 && {

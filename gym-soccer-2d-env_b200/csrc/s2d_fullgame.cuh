@@ -624,6 +624,7 @@ __device__ __forceinline__ bool fg_cycle(FgShared& S, const int t, const int tid
     // `on`: the sub-lane has a player in this slot (with LPM > 1 the sub-lanes own 8 / 6 / 4 / 4 or 12 / 10 players and all
     // walk the longest list, so that the warp votes of fg_commands stay whole); j_next: the player it handles after this one
     auto one_player = [&](const int j, float4 a, const bool on, const int j_next) {
+      if (LPM == 2 && obs_row) __syncwarp();  // (the observation staging columns are read across the two sub-lanes)
       fg_point_at_type(sp, P, g, on ? j : 0);
       const float4 pa = n_a, b = n_b;
       const float cap = n_c;
@@ -752,16 +753,21 @@ __device__ __forceinline__ bool fg_cycle(FgShared& S, const int t, const int tid
         stg[3][tid] = p.vy;
         stg[4][tid] = p.body * static_cast<float>(1.0 / 180.0);
         auto f4 = [&](int r) { return make_float4(S.obs[r][tid], S.obs[r + 1][tid], S.obs[r + 2][tid], S.obs[r + 3][tid]); };
-        if (LPM == 1) {
+        if (LPM <= 2) {
           // Whole 32-byte sectors only (a half-written sector costs the L2 about as much as two whole ones: measured,
           // profiles/micro/fg_layout.cu).  A group's five float4 start at an odd float4 of the row in the even groups and
           // at an even one in the odd groups, so an odd group leaves its last float4 (rows 16-19) behind for the first
           // float4 of the next one.  The first float4 of group 0 shares its sector with the ball and the last two floats
           // of player 21 share theirs with the referee's values: those two sectors are written at the end of the launch.
+          // With two lanes per match the even groups are the first sub-lane's and the odd ones the second's: the float4
+          // left behind sits in the neighbour's column (written a whole group of players ago; the __syncwarp at the top
+          // of every player slot orders it).
+          const int left_behind = LPM == 1 ? tid : tid | 1;
           if (valid) {
             float4* o = reinterpret_cast<float4*>(obs_row) + 5 * grp;  // the group's values are o[1] .. o[5]
             if ((grp & 1) == 0) {
-              if (q == 0 && grp > 0) st_stream_256(o, f4(16), f4(0));
+              if (q == 0 && grp > 0)
+                st_stream_256(o, make_float4(S.obs[16][left_behind], S.obs[17][left_behind], S.obs[18][left_behind], S.obs[19][left_behind]), f4(0));
               if (q == 3) {
                 st_stream_256(o + 2, f4(4), f4(8));
                 st_stream_256(o + 4, f4(12), f4(16));

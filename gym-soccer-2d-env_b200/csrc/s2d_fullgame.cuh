@@ -78,7 +78,11 @@ struct Match {
 #define S2D_FG_AHEAD 2  // player rows the L2 is asked for ahead of the register prefetch (measured: 0 -> 201 us, 1..3 -> 190 us)
 #endif
 #ifndef S2D_FG_MIN_BLOCKS
-#define S2D_FG_MIN_BLOCKS 10  // 96 registers per thread (spills only around the cold calls), 20 warps per SM, 10 x 22 KB of shared memory
+// Register budget of the step kernel.  Measured after the store pattern stopped being the bound (profiles/README.md):
+// 10 blocks (96 registers, spills and rebuilt pointers in the player loop) 172 us per 2^18-match cycle, 7 or 8 blocks
+// (124 registers, nothing spilled, 8 blocks = 16 warps resident) 160-164 us, 6 blocks (144 registers, 12 warps) 176 us;
+// a 32 K-match shard 39 -> 34 us.
+#define S2D_FG_MIN_BLOCKS 7
 #endif
 
 // The block's shared memory: per player a row of kFgBlock entries (lane-minor: conflict-free).

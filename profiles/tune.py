@@ -13,7 +13,7 @@ KW = dict(use_continuous_action=False, action_space_size=16, change_ball_positio
           change_ball_velocity=os.environ.get("S2D_TUNE_STILL", "0") != "1")  # S2D_TUNE_STILL=1: the ball rests (reference default)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 out = []
-for name, n, k, warm, steps in (("k16", 1 << 20, 16, 14, 30), ("k1", 1 << 23, 1, 10, 30)):
+for name, n, k, warm, steps in (("k16", 1 << 20, 16, int(os.environ.get("S2D_TUNE_WARM", 14)), 30), ("k1", 1 << 23, 1, 10, 30)):  # S2D_TUNE_WARM=150: steady state of the episode ends
     env = Soccer2DVecEnv(n, device="cuda:0", seed=0, substeps=k, **KW)
     g = torch.Generator(device="cuda").manual_seed(0)
     pool = [torch.randint(0, 16, (n, k), dtype=torch.uint8, device="cuda", generator=g) for _ in range(2)]

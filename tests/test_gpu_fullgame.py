@@ -105,7 +105,9 @@ def same_step(env, sim):
 @pytest.mark.parametrize("pps,k,default_sp,collision_model", [(11, 1, True, "midpoint"), (11, 4, True, "midpoint"),
                                                              (3, 1, True, "midpoint"), (11, 1, False, "midpoint"),
                                                              (11, 1, True, "backtrace"), (5, 3, False, "backtrace")])
-def test_fullgame_bit_exact_against_fp32_oracle(pps, k, default_sp, collision_model):
+@pytest.mark.parametrize("lanes", ["1", "2"])
+def test_fullgame_bit_exact_against_fp32_oracle(pps, k, default_sp, collision_model, lanes, monkeypatch):
+    monkeypatch.setenv("S2D_FG_LANES", lanes)  # thread per match / two lanes per match (read when the handle is created)
     n = 131
     sp = None if default_sp else dict(player_decay=0.45, kickable_margin=0.8, slowness_on_top_for_right_team=1.1,
                                      ball_decay=0.95, kick_power_rate=0.03)
@@ -532,10 +534,13 @@ def set_gpu_state_fg(env, vec):
     pl["ej"].copy_(torch.from_numpy(ej.astype(np.uint32).view(np.int32)))
 
 
+@pytest.mark.parametrize("lanes", ["1", "2"])
 @pytest.mark.parametrize("collision_model", ["midpoint", "backtrace"])
-def test_fullgame_random_states_bit_exact(collision_model):
+def test_fullgame_random_states_bit_exact(collision_model, lanes, monkeypatch):
     """One cycle from hand-made states (players piled on the ball, the ball near or beyond every line, every play mode,
-    stale offside marks) with random commands: reaches the referee branches a trajectory rarely visits."""
+    stale offside marks) with random commands: reaches the referee branches a trajectory rarely visits.  Both mappings of
+    the 11 v 11 kernel: one thread per match (what a full-size shard runs) and two lanes per match (small shards)."""
+    monkeypatch.setenv("S2D_FG_LANES", lanes)  # (read when the handle is created)
     n, p = 512, 22
     env = Soccer2DVecEnv(n, scenario="fullgame", device="cuda:0", seed=2, half_time_cycles=10 ** 6, auto_reset=False,
                          collision_model=collision_model)

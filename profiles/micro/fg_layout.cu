@@ -35,7 +35,26 @@ __global__ void __launch_bounds__(BLK, 10) probe(char* state, const float4* cmd,
       float* o = obs + i * 120 + 4 + 5 * j;
       o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x;
     }
-    if (OBS >= 2) {  // four players staged in shared memory, then written as ...
+    if (OBS == 5) {  // eight players staged (40 floats = 5 sectors, starting half a sector into the row: floats 4 + 40 p),
+                     // written by the warp together as whole sectors: 160 sectors = 5 stores, consecutive lanes = consecutive sectors
+      __shared__ float stage8[BLK][41];
+      float* sr = stage8[threadIdx.x] + 5 * (j & 7);
+      sr[0] = a.x; sr[1] = a.y; sr[2] = a.z; sr[3] = a.w; sr[4] = b.x;
+      if ((j & 7) == 7) {
+        __syncwarp();
+        const int lane = threadIdx.x & 31, w0 = threadIdx.x & ~31;
+        const int64_t first = i - lane;
+        const int p = j >> 3;
+        for (int s5 = 0; s5 < 5; ++s5) {
+          const int piece = lane + 32 * s5, mt = piece / 5, sec = piece % 5;
+          const float* rr = stage8[w0 + mt] + 8 * sec;  // (the probe ignores the half-sector offset: same traffic)
+          asm volatile("st.global.L1::no_allocate.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(reinterpret_cast<float4*>(obs + (first + mt) * 120) + 10 * p + 2 * sec),
+                       "f"(rr[0]), "f"(rr[1]), "f"(rr[2]), "f"(rr[3]), "f"(rr[4]), "f"(rr[5]), "f"(rr[6]), "f"(rr[7]) : "memory");
+        }
+        __syncwarp();
+      }
+    }
+    if (OBS >= 2 && OBS <= 4) {  // four players staged in shared memory, then written as ...
       __shared__ float stage[BLK][21];
       float* sr = stage[threadIdx.x] + 5 * (j & 3);
       sr[0] = a.x; sr[1] = a.y; sr[2] = a.z; sr[3] = a.w; sr[4] = b.x;
@@ -70,17 +89,21 @@ int main() {
   const int64_t n = 1 << 18;
   const size_t sbytes = (size_t)n * (NP * 36 + 80);
   char* state; float4* cmd; float* obs; char* flush;
-  cudaMalloc(&state, sbytes); cudaMalloc(&cmd, n * NP * 16); cudaMalloc(&obs, n * 480 + 4096);  // (slack: the probe writes whole groups past the last row) cudaMalloc(&flush, 256 << 20);
+  cudaMalloc(&state, sbytes); cudaMalloc(&cmd, n * NP * 16); cudaMalloc(&obs, n * 480 + 4096);  // (slack: the probe writes whole groups past the last row)
+  cudaMalloc(&flush, 256 << 20);
   cudaMemset(state, 0, sbytes); cudaMemset(cmd, 0, n * NP * 16);
+  if (cudaError_t e = cudaGetLastError()) { printf("setup: %s\n", cudaGetErrorString(e)); return 1; }
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   auto run = [&](auto kern, const char* name, double bytes) {
     float best = 1e9, sum = 0;
     for (int r = 0; r < 8; ++r) {
-      cudaMemset(flush, r, 256 << 20);
-      cudaEventRecord(e0); kern<<<n / BLK, BLK>>>(state, cmd, obs, n); cudaEventRecord(e1); cudaEventSynchronize(e1);
-      float ms; cudaEventElapsedTime(&ms, e0, e1); if (r >= 2) { sum += ms; best = ms < best ? ms : best; }
+      cudaError_t c0 = cudaMemset(flush, r, 256 << 20);
+      cudaError_t c1 = cudaEventRecord(e0); kern<<<n / BLK, BLK>>>(state, cmd, obs, n); cudaError_t c2 = cudaGetLastError(); cudaError_t c3 = cudaEventRecord(e1); cudaError_t c4 = cudaEventSynchronize(e1);
+      float ms; cudaError_t c5 = cudaEventElapsedTime(&ms, e0, e1);
+      if (r == 7 && (c0 || c1 || c2 || c3 || c4 || c5)) printf("  errors: memset %d record %d launch %d record %d sync %d elapsed %d\n", c0, c1, c2, c3, c4, c5); if (r >= 2) { sum += ms; best = ms < best ? ms : best; }
     }
     printf("%-28s mean %.1f us  best %.1f us  -> %.0f GB/s\n", name, sum / 6 * 1e3, best * 1e3, bytes / (sum / 6 * 1e-3) / 1e9);
+    if (cudaError_t e = cudaGetLastError()) printf("  (%s: %s)\n", name, cudaGetErrorString(e));
   };
   const double st = 2.0 * n * NP * 36, cm = (double)n * NP * 16, ob = (double)n * 480;
   run(probe<0, 0>, "plane-major, no obs", st + cm);
@@ -89,6 +112,6 @@ int main() {
   run(probe<0, 2>, "obs: 16 B pieces per thread", st + cm + ob);
   run(probe<0, 3>, "obs: 32 B sectors per thread", st + cm + ob);
   run(probe<0, 4>, "obs: warp-cooperative rows", st + cm + ob);
-  printf("%s\n", cudaGetErrorString(cudaGetLastError()));
+  run(probe<0, 5>, "obs: warp-cooperative sectors", st + cm + ob * 80.0 / 120.0);  // (players 0..15 only: 2 x 8)
   return 0;
 }

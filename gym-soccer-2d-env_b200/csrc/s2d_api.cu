@@ -865,16 +865,18 @@ static int rollout_mlp(S2DHandle h, const S2DMlpPolicy* policy, int k_substeps, 
     else rollout_mlp_kernel<SCN, kVarRuntime, ACT><<<h->grid, kBlock, 0, s>>>(h->kp, k_substeps, w, epsilon, ao, qo, traj); \
   } while (0)
   if (policy->precision < 0 || policy->precision > 2)
-    return fail(h, S2D_ERR_INVALID, "precision: 0 (TF32: tcgen05 for Q-networks, mma.sync for actors), 1 (bf16, mma.sync), 2 (TF32, mma.sync)");
-  if (policy->precision == 0 && !actor) {  // the Q-network on tcgen05 (TF32 operands, accumulators in tensor memory)
-#define S2D_TC5(SCN)                                                                                                   \
+    return fail(h, S2D_ERR_INVALID, "precision: 0 (TF32, tcgen05), 1 (bf16, mma.sync), 2 (TF32, mma.sync)");
+  if (policy->precision == 0) {  // the network on tcgen05 (TF32 operands, accumulators in tensor memory)
+#define S2D_TC5(SCN, ACT)                                                                                              \
   do {                                                                                                                 \
-    if (h->cfg.noise) rollout_mlp_tc5_kernel<SCN, kVarNoisy><<<h->grid, kBlock, 0, s>>>(h->kp, k_substeps, w, epsilon, ao, qo, traj); \
-    else if (h->default_sp) rollout_mlp_tc5_kernel<SCN, kVarDefault><<<h->grid, kBlock, 0, s>>>(h->kp, k_substeps, w, epsilon, ao, qo, traj); \
-    else rollout_mlp_tc5_kernel<SCN, kVarRuntime><<<h->grid, kBlock, 0, s>>>(h->kp, k_substeps, w, epsilon, ao, qo, traj); \
+    if (h->cfg.noise) rollout_mlp_tc5_kernel<SCN, kVarNoisy, ACT><<<h->grid, kBlock, 0, s>>>(h->kp, k_substeps, w, epsilon, ao, qo, traj); \
+    else if (h->default_sp) rollout_mlp_tc5_kernel<SCN, kVarDefault, ACT><<<h->grid, kBlock, 0, s>>>(h->kp, k_substeps, w, epsilon, ao, qo, traj); \
+    else rollout_mlp_tc5_kernel<SCN, kVarRuntime, ACT><<<h->grid, kBlock, 0, s>>>(h->kp, k_substeps, w, epsilon, ao, qo, traj); \
   } while (0)
-    if (shoot) S2D_TC5(S2D_SCENARIO_SHOOT);
-    else S2D_TC5(S2D_SCENARIO_REACHBALL);
+    if (actor && mode == S2D_ACT_TURNING) S2D_TC5(S2D_SCENARIO_REACHBALL, S2D_ACT_TURNING);
+    else if (actor) S2D_TC5(S2D_SCENARIO_REACHBALL, S2D_ACT_CONTINUOUS);
+    else if (shoot) S2D_TC5(S2D_SCENARIO_SHOOT, S2D_ACT_DISCRETE);
+    else S2D_TC5(S2D_SCENARIO_REACHBALL, S2D_ACT_DISCRETE);
 #undef S2D_TC5
     S2D_CUDA(h, cudaGetLastError());
     h->env_steps += static_cast<uint64_t>(h->cfg.num_envs) * static_cast<uint64_t>(k_substeps);

@@ -161,13 +161,17 @@ __device__ __forceinline__ void tc5_hidden_epilogue(uint32_t d_tmem, uint32_t a_
   tc5_wait_st();
 }
 
-// K closed-loop cycles (observe, Q-network on tcgen05, (epsilon-)greedy action, step) of a one-player scenario with
-// Discrete actions: the same contract as rollout_mlp_kernel<SCN, VAR, S2D_ACT_DISCRETE>.
-template <int SCN, int VAR>
+// K closed-loop cycles (observe, network on tcgen05, action, step) of a one-player scenario: the same contract as
+// rollout_mlp_kernel<SCN, VAR, ACT>.  ACT = S2D_ACT_DISCRETE: W is a Q-network, (epsilon-)greedy action.
+// ACT = S2D_ACT_CONTINUOUS / S2D_ACT_TURNING (ReachBall): W is a DDPG actor - tanh of the last layer's first 1 / 4 outputs is
+// the Box(1) / Box(4) action, `epsilon` the half-width of the uniform exploration noise.
+template <int SCN, int VAR, int ACT = S2D_ACT_DISCRETE>
 __global__ void __launch_bounds__(kBlock, S2D_ROLLOUT_MIN_BLOCKS)
     rollout_mlp_tc5_kernel(const __grid_constant__ KernelParams P, const int K, const MlpWeights W, const float epsilon,
                            uint8_t* __restrict__ actions_out, float* __restrict__ q_out, const TrajOut T) {
   static_assert(kBlock == 128, "one block = one M = 128 tile");
+  constexpr bool kActor = ACT != S2D_ACT_DISCRETE;
+  constexpr int kActDim = ACT == S2D_ACT_TURNING ? 4 : 1;
   constexpr int N3 = SCN == S2D_SCENARIO_SHOOT ? 32 : 16;  // layer 3's N (a multiple of 16); q_out rows hold 8 NT values
   constexpr int NQ = SCN == S2D_SCENARIO_SHOOT ? 24 : 16;
   using SP = typename VariantSP<VAR>::type;
@@ -243,9 +247,19 @@ __global__ void __launch_bounds__(kBlock, S2D_ROLLOUT_MIN_BLOCKS)
     tc5_wait(mbar, parity);
     parity ^= 1u;
     tc5_fence_after();
-    // the thread's own Q row: + bias, first maximum wins (as torch.argmax)
+    // the thread's own output row.  Q-network: + bias, first maximum wins (as torch.argmax); actor: tanh(. + bias)
     int a = 0;
-    {
+    float4 av = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    if (kActor) {
+      float v[16];
+      tc5_ld16(rd, v);
+      av.x = tanh_poly(v[0] + s.b3[0]);
+      if (kActDim == 4) {
+        av.y = tanh_poly(v[1] + s.b3[1]);
+        av.z = tanh_poly(v[2] + s.b3[2]);
+        av.w = tanh_poly(v[3] + s.b3[3]);
+      }
+    } else {
       float best = -3.4e38f;
 #pragma unroll
       for (int c = 0; c < N3; c += 16) {
@@ -271,6 +285,23 @@ __global__ void __launch_bounds__(kBlock, S2D_ROLLOUT_MIN_BLOCKS)
     tc5_fence_before();  // (the next cycle's A1 store and MMA re-use the regions this cycle read)
     int rs;
     const float reward_before = out.reward_sum;
+    if (kActor) {  // (exploration noise and action stores as in rollout_mlp_kernel: the same counter streams)
+      if (epsilon > 0.0f) {
+        const uint4 w = philox4x32_10(P.seed, gid, e.cycle, RNG_ACTION, 2);
+        av.x = clampf(-1.0f, av.x + epsilon * u11(w.x), 1.0f);
+        av.y = clampf(-1.0f, av.y + epsilon * u11(w.y), 1.0f);
+        av.z = clampf(-1.0f, av.z + epsilon * u11(w.z), 1.0f);
+        av.w = clampf(-1.0f, av.w + epsilon * u11(w.w), 1.0f);
+      }
+      if (T.actions_f && valid) {
+        float* dst = T.actions_f + (static_cast<int64_t>(k) * n + i) * kActDim;
+        dst[0] = av.x;
+        if (kActDim == 4) { dst[1] = av.y; dst[2] = av.z; dst[3] = av.w; }
+      }
+      out.reward_sum = 0.0f;
+      rs = substep<SCN, ACT, SP, true>(e, P, sp, gid, i, av.x, kActDim == 4 ? av.y : 0.f, kActDim == 4 ? av.z : 0.f,
+                                       kActDim == 4 ? av.w : 0.f, out);
+    } else {
     if (epsilon > 0.0f) {  // exploration: the same counter stream as the mma.sync kernel
       const uint4 w = philox4x32_10(P.seed, gid, e.cycle, RNG_ACTION, 1);
       if (u32_to_unit(w.x) < epsilon) a = u32_to_int(w.y, 0, W.n_actions - 1);
@@ -283,6 +314,7 @@ __global__ void __launch_bounds__(kBlock, S2D_ROLLOUT_MIN_BLOCKS)
     } else {
       const float2 tab = __ldg(reinterpret_cast<const float2*>(P.action_table + a) + 1);
       rs = substep<SCN, S2D_ACT_DISCRETE, SP, true>(e, P, sp, gid, i, 0.f, 0.f, tab.x, tab.y, out);
+    }
     }
     const float rw = out.reward_sum;
     out.reward_sum = reward_before + rw;

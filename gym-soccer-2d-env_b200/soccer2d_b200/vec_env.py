@@ -720,12 +720,14 @@ class Soccer2DVecEnv(_VecEnvBase):
                                             q_out.data_ptr() if q_out is not None else None, _stream_ptr(self.device)),
                    self.handle)
 
-    def rollout_actor(self, layers, k: int | None = None, noise: float = 0.0, traj: dict | None = None) -> None:
+    def rollout_actor(self, layers, k: int | None = None, noise: float = 0.0, traj: dict | None = None,
+                      precision: str = "tf32") -> None:
         """`k` cycles of observe -> actor(obs) -> Box action -> step in ONE launch (ReachBall with the Box(1) or the Box(4)
         turning action space): the DDPG counterpart of `rollout_mlp` (s2d_rollout_actor_collect).  `layers` = [(weight,
         bias)] * 3 of a 64-64 ReLU MLP whose last layer has action_dim rows; tanh is applied in the kernel.  `noise`: the
         half-width of a uniform exploration noise.  `traj`: time-major tensors, any of obs float32 [k + 1, N, 10],
-        actions float32 [k, N, action_dim], reward float32 [k, N], done uint8 [k, N]."""
+        actions float32 [k, N, action_dim], reward float32 [k, N], done uint8 [k, N].  `precision`: "tf32" (default:
+        tcgen05.mma, accumulators in tensor memory) or "tf32_mma_sync" (the warp-level kernel of round 1)."""
         k = self.substeps if k is None else int(k)
         self._user_dirty = True
         ad = 4 if self.action_mode == _abi.ACT_TURNING else 1
@@ -737,7 +739,7 @@ class Soccer2DVecEnv(_VecEnvBase):
                 if t.dtype != torch.float32 or not t.is_cuda or not t.is_contiguous() or t.device != self.device:
                     raise ValueError("rollout_actor: weights must be contiguous float32 tensors on the env's device")
             ptrs += [w.data_ptr(), b.data_ptr()]
-        pol = _abi.MlpPolicy(*ptrs, 64, 0)
+        pol = _abi.MlpPolicy(*ptrs, 64, {"tf32": 0, "tf32_tcgen05": 0, "tf32_mma_sync": 2}[precision])
         t = _abi.Trajectory()
         want = {"obs": ((k + 1, self.num_envs, self.obs_dim), torch.float32, "obs"),
                 "actions": ((k, self.num_envs, ad), torch.float32, "actions_f"),

@@ -432,10 +432,10 @@ typedef struct S2DMlpPolicy {
   const float* w2; const float* b2; /* [64][64], [64] */
   const float* w3; const float* b3; /* [n_actions][64], [n_actions] */
   int32_t hidden;                   /* 64 */
-  int32_t precision;                /* 0 (default): TF32 operands - Q-networks on tcgen05.mma with the accumulators in
-                                       tensor memory, actors on warp-level mma.sync; 1: bf16 operands, mma.sync
-                                       (Q-networks only; ~1e-2 of Q's scale); 2: TF32 operands on mma.sync for
-                                       Q-networks too (the round-1 kernel, kept for comparison) */
+  int32_t precision;                /* 0 (default): TF32 operands on tcgen05.mma with the accumulators in tensor memory
+                                       (Q-networks and actors); 1: bf16 operands, mma.sync (Q-networks only; ~1e-2 of
+                                       Q's scale); 2: TF32 operands on warp-level mma.sync (the round-1 kernels, kept
+                                       for comparison) */
 } S2DMlpPolicy;
 int s2d_rollout_mlp(S2DHandle h, const S2DMlpPolicy* policy, int k_substeps, float epsilon, void* actions_out,
                     void* q_out, void* stream);

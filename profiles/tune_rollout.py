@@ -33,23 +33,23 @@ for n, k, prec in ((1 << 20, 16, "tf32"), (1 << 20, 16, "tf32_mma_sync"), (1 << 
     print(f"fused policy+step ({prec}): {n} envs K={k}: median {med:.4f} ms  min {ms[0]:.4f}  {n * k / med / 1e6:.2f} G env-steps/s  stats {env.stats()['episodes']}")
     env.close()
 from soccer2d_b200.rollout import Actor, mlp_layers  # noqa: E402
-for turning in (False, True):
+for turning, aprec in ((False, "tf32"), (True, "tf32"), (False, "tf32_mma_sync"), (True, "tf32_mma_sync")):
     n, k = 1 << 20, 16
     env = Soccer2DVecEnv(n, device="cuda:0", seed=0, substeps=k, use_continuous_action=True, use_turning=turning,
                          change_ball_position=True, change_ball_velocity=True)
     actor = Actor(10, 4 if turning else 1).cuda()
     env.reset_torch()
     for _ in range(14):
-        env.rollout_actor(mlp_layers(actor), k)
+        env.rollout_actor(mlp_layers(actor), k, precision=aprec)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(20)]
     for a, b in ev:
         flush.zero_()
         a.record()
-        env.rollout_actor(mlp_layers(actor), k)
+        env.rollout_actor(mlp_layers(actor), k, precision=aprec)
         b.record()
     torch.cuda.synchronize()
     ms = sorted(a.elapsed_time(b) for a, b in ev)
-    print(f"fused actor+step ({'Box(4) turning' if turning else 'Box(1)'}): {n} envs K={k}: median {ms[len(ms) // 2]:.4f} ms  "
+    print(f"fused actor+step ({'Box(4) turning' if turning else 'Box(1)'}, {aprec}): {n} envs K={k}: median {ms[len(ms) // 2]:.4f} ms  "
           f"{n * k / ms[len(ms) // 2] / 1e6:.2f} G env-steps/s")
     env.close()
 env = Soccer2DVecEnv(1 << 20, device="cuda:0", seed=0, substeps=1, **KW)

@@ -243,9 +243,11 @@ def test_dqn_learns_from_fused_collection():
     env.close()
 
 
+@pytest.mark.parametrize("precision", ["tf32", "tf32_mma_sync"])
 @pytest.mark.parametrize("turning", [False, True])
-def test_fused_actor_rollout_matches_actor_then_step(turning):
-    """s2d_rollout_actor_collect: the DDPG actor inside the step kernel, Box(1) and Box(4) action spaces.  The recorded
+def test_fused_actor_rollout_matches_actor_then_step(turning, precision):
+    """s2d_rollout_actor_collect: the DDPG actor inside the step kernel (tcgen05, and the warp-level mma.sync kernel),
+    Box(1) and Box(4) action spaces.  The recorded
     actions equal torch's fp32 actor on the recorded observations to TF32 accuracy; replaying them through the ordinary
     step kernel reproduces every recorded observation, reward and done flag bit for bit."""
     from soccer2d_b200.rollout import Actor, mlp_layers
@@ -265,7 +267,7 @@ def test_fused_actor_rollout_matches_actor_then_step(turning):
             "reward": torch.zeros((k, n), device="cuda"), "done": torch.zeros((k, n), dtype=torch.uint8, device="cuda")}
     worst = 0.0
     for launch in range(20):
-        fused.rollout_actor(mlp_layers(actor), k, 0.0, traj=traj)
+        fused.rollout_actor(mlp_layers(actor), k, 0.0, traj=traj, precision=precision)
         assert torch.equal(traj["obs"][0], plain.obs)
         for j in range(k):
             with torch.no_grad():
@@ -281,9 +283,9 @@ def test_fused_actor_rollout_matches_actor_then_step(turning):
     det = torch.zeros((k, n, ad), device="cuda")
     noisy = torch.zeros((k, n, ad), device="cuda")
     state = fused.state.clone()
-    fused.rollout_actor(mlp_layers(actor), k, 0.0, traj={"actions": det})
+    fused.rollout_actor(mlp_layers(actor), k, 0.0, traj={"actions": det}, precision=precision)
     fused.state.copy_(state)
-    fused.rollout_actor(mlp_layers(actor), k, 0.25, traj={"actions": noisy})
+    fused.rollout_actor(mlp_layers(actor), k, 0.25, traj={"actions": noisy}, precision=precision)
     d = (noisy[0] - det[0])  # first cycle: the same state, so the same deterministic action
     inside = det[0].abs() < 0.7
     assert float(d[inside].abs().max()) <= 0.25 + 1e-6 and float(d[inside].std()) == pytest.approx(0.25 / 3 ** 0.5, rel=0.05)

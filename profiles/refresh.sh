@@ -34,17 +34,18 @@ python profiles/prof_fullgame.py > /dev/null 2>&1 && {
 python profiles/prof_rollout.py tf32 > /dev/null 2>&1 && {
   ncu --set full --clock-control none --import-source on -k regex:rollout_mlp -s 2 -c 1 -o $O/prof_${TAG}_rollout_tc5 -f python profiles/prof_rollout.py tf32 >> $O/ncu_full.log 2>&1
   ncu --set full --clock-control none --import-source on -k regex:rollout_mlp -s 2 -c 1 -o $O/prof_${TAG}_rollout_mma -f python profiles/prof_rollout.py tf32_mma_sync >> $O/ncu_full.log 2>&1
+  ncu --set full --clock-control none --import-source on -k regex:rollout_mlp -s 2 -c 1 -o $O/prof_${TAG}_actor_tc5 -f python profiles/prof_rollout.py actor >> $O/ncu_full.log 2>&1
 }
 # summaries here (the captures are ~18 MB each; gpurun brings back at most 64 MiB): CSV + traffic.json + source profiles
 python profiles/summarize_ncu.py $O/${TAG}_kernels_ncu_full.csv $O/${TAG}_traffic.json \
   k16_envs_1048576:16777216=$O/prof_${TAG}_k16.ncu-rep k1_envs_8388608:8388608=$O/prof_${TAG}_k1.ncu-rep \
   fullgame_k1_envs_262144:262144=$O/prof_${TAG}_fg_k1.ncu-rep fullgame_k16_envs_262144:4194304=$O/prof_${TAG}_fg_k16.ncu-rep \
   fullgame_k1_late_envs_262144:262144=$O/prof_${TAG}_fg_k1_late.ncu-rep \
-  rollout_tc5_k16_envs_1048576:16777216=$O/prof_${TAG}_rollout_tc5.ncu-rep rollout_mma_k16_envs_1048576:16777216=$O/prof_${TAG}_rollout_mma.ncu-rep \
+  rollout_tc5_k16_envs_1048576:16777216=$O/prof_${TAG}_rollout_tc5.ncu-rep rollout_mma_k16_envs_1048576:16777216=$O/prof_${TAG}_rollout_mma.ncu-rep actor_tc5_k16_envs_1048576:16777216=$O/prof_${TAG}_actor_tc5.ncu-rep \
   > $O/summarize.log 2>&1
 for c in fg_k1:262144 fg_k1_late:262144 rollout_tc5:524288 rollout_mma:524288 k16:524288; do
   n=${c%%:*}; u=${c##*:}
   python profiles/source_profile.py $O/prof_${TAG}_$n.ncu-rep $u 40 > $O/${TAG}_source_profile_$n.txt 2>&1
 done
-rm -f $O/prof_${TAG}_k16.ncu-rep $O/prof_${TAG}_k1.ncu-rep $O/prof_${TAG}_fg_k16.ncu-rep $O/prof_${TAG}_fg_k1_late.ncu-rep $O/prof_${TAG}_rollout_mma.ncu-rep
+rm -f $O/prof_${TAG}_actor_tc5.ncu-rep $O/prof_${TAG}_k16.ncu-rep $O/prof_${TAG}_k1.ncu-rep $O/prof_${TAG}_fg_k16.ncu-rep $O/prof_${TAG}_fg_k1_late.ncu-rep $O/prof_${TAG}_rollout_mma.ncu-rep
 ls -la $O | tail -24

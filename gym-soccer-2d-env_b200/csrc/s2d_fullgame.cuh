@@ -89,7 +89,8 @@ struct Match {
 struct FgShared {
   float2 xy[kFgMaxPlayers][kFgBlock];  // position (the same values as plane PA holds)
   float oldx[kFgMaxPlayers][kFgBlock]; // x before this cycle's move (the offside line is drawn at the moment of the pass)
-  float obs[20][kFgBlock];             // four players' worth of the observation row on its way out (five float4)
+  float obs[20][kFgBlock];             // four players' worth of the observation row on its way out (five float4); after the
+                                       // player loop rows 0-4 of a column bring the collision resolver's outcome back
 #ifdef S2D_FG_PAD
   char pad[S2D_FG_PAD];                // (tuning aid: lowers the number of resident blocks)
 #endif

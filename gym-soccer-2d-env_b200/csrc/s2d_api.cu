@@ -76,6 +76,13 @@ struct DeviceGuard {
   }
 };
 
+namespace {
+__global__ void fill_sincos_memo(float2* memo) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < kSinCosMemoSize) sincos_deg(static_cast<float>(j - kSinCosMemoHalf), memo[j].x, memo[j].y);
+}
+}  // namespace
+
 extern "C" {
 
 int s2d_abi_version(void) { return S2D_ABI_VERSION; }
@@ -209,8 +216,16 @@ int s2d_create(const S2DConfig* cfg, S2DHandle* out) {
   float4 table[256];
   make_kernel_params(*cfg, kp, table);
   h->default_sp = is_default_server_param(cfg->sp) && cfg->collision_model == S2D_COLLISION_MIDPOINT;
-  cudaError_t e = cudaMalloc(&h->d_table, sizeof(table));
+  // one allocation: the action table, then the memo of sincos_deg over whole degrees (written by sincos_deg itself)
+  cudaError_t e = cudaMalloc(&h->d_table, sizeof(table) + sizeof(float2) * kSinCosMemoSize);
   if (e == cudaSuccess) e = cudaMemcpy(h->d_table, table, sizeof(table), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    float2* memo = reinterpret_cast<float2*>(h->d_table + 256);
+    fill_sincos_memo<<<(kSinCosMemoSize + 255) / 256, 256>>>(memo);
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    kp.sincos_memo = memo;
+  }
   if (e != cudaSuccess) {
     fail(nullptr, S2D_ERR_CUDA, "allocating the action table failed: %s", cudaGetErrorString(e));
     if (h->d_table) cudaFree(h->d_table);

@@ -75,6 +75,31 @@ __device__ __forceinline__ void sincos_deg(float x, float& s, float& c) {
   c = cc;
 }
 
+// Memo of sincos_deg over the whole degrees in [-360, 360] ({sin, cos} per entry, 5.8 KB in global memory, read
+// through L1 by the ReachBall Discrete(n) step kernel).  A player placed at a whole-degree body angle that only
+// dashes in directions snapped to dash_angle_step = 1 asks for nothing else, and so do the ball-velocity draws of a
+// placement; a table read is a quarter of the polynomial's instructions.  The
+// entries are written by sincos_deg itself (fill_sincos_memo, s2d_api.cu), so a hit returns the very bits the
+// polynomial would; any other argument takes the polynomial, out of line.
+constexpr int kSinCosMemoHalf = 360, kSinCosMemoSize = 2 * kSinCosMemoHalf + 1;
+__device__ __noinline__ float2 cold_sincos_deg(float x) {
+  float2 r;
+  sincos_deg(x, r.x, r.y);
+  return r;
+}
+__device__ __forceinline__ void sincos_deg_memo(float x, const float2* __restrict__ memo, float& s, float& c) {
+  const float r = rintf(x);
+  if (r == x && fabsf(x) <= static_cast<float>(kSinCosMemoHalf)) {
+    const float2 t = __ldg(memo + (static_cast<int>(r) + kSinCosMemoHalf));
+    s = t.x;
+    c = t.y;
+  } else {
+    const float2 t = cold_sincos_deg(x);
+    s = t.x;
+    c = t.y;
+  }
+}
+
 // Vector2D::th() in degrees: octant reduction, ONE division, odd minimax polynomial; 0 for the zero vector.
 __device__ __forceinline__ float atan2_deg(float y, float x) {
   const float ax = fabsf(x), ay = fabsf(y);

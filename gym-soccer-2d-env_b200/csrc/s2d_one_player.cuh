@@ -103,7 +103,7 @@ S2D_HD void dash_direction(float dir, const SP& sp, float& snapped, float& rate)
 // dash_power_rate.  Gives the player's acceleration (it is the only contribution in a cycle).
 template <class SP>
 __device__ __forceinline__ void dash_apply(Episode& e, float power, float dir, float rate, const SP& sp, float& ax,
-                                           float& ay, bool left_team = true) {
+                                           float& ay, bool left_team = true, const float2* sincos_memo = nullptr) {
   power = clampf(sp.min_dash_power(), power, sp.max_dash_power());
   const bool back = power < 0.0f;
   float need = back ? power * -2.0f : power;
@@ -115,7 +115,8 @@ __device__ __forceinline__ void dash_apply(Episode& e, float power, float dir, f
   if (slow != 1.0f && e.py < 0.0f) eff = cold_div(eff, slow);
   dir = back ? dir + 180.0f : dir;
   float s, c;
-  sincos_deg(e.body + dir, s, c);
+  if (sincos_memo) sincos_deg_memo(e.body + dir, sincos_memo, s, c);  // the same bits, see s2d_math.cuh
+  else sincos_deg(e.body + dir, s, c);
   ax = eff * c;
   ay = eff * s;
 }
@@ -486,12 +487,13 @@ __device__ __forceinline__ void update_stamina(Episode& e, const SP& sp) {
 // Outputs (dx, dy) = ball - player after the cycle and d2 = dx*dx + dy*dy, which the scenario's scoring re-uses.
 template <bool TURNS, bool KICKS, class SP>
 __device__ __forceinline__ void simulate_cycle(Episode& e, int cmd, float power, float dir, float rate, const SP& sp,
-                                               float& dx, float& dy, float& d2, uint64_t seed, uint64_t gid) {
+                                               float& dx, float& dy, float& d2, uint64_t seed, uint64_t gid,
+                                               const float2* sincos_memo = nullptr) {
   float ax = 0.0f, ay = 0.0f, bax = 0.0f, bay = 0.0f;
   const NoiseCtx nz{seed, gid, e.cycle};
   if (KICKS) e.flags &= ~S2D_FLAG_KICKED;
   if (cmd == S2D_CMD_DASH) {
-    dash_apply(e, power, dir, rate, sp, ax, ay);
+    dash_apply(e, power, dir, rate, sp, ax, ay, true, sincos_memo);
   } else if (TURNS && cmd == S2D_CMD_TURN) {
     turn(e, dir, sp, nz);
   } else if (KICKS && cmd == S2D_CMD_KICK) {

@@ -355,7 +355,7 @@ __global__ void __launch_bounds__(kBlock, S2D_ROLLOUT_MIN_BLOCKS)
         rs = substep<SCN, S2D_ACT_DISCRETE, SP, true>(e, P, sp, gid, i, tab.x, tab.y, tab.z, tab.w, out);
       } else {
         const float2 tab = __ldg(reinterpret_cast<const float2*>(P.action_table + a) + 1);
-        rs = substep<SCN, S2D_ACT_DISCRETE, SP, true>(e, P, sp, gid, i, 0.f, 0.f, tab.x, tab.y, out);
+        rs = substep<SCN, S2D_ACT_DISCRETE, SP, true>(e, P, sp, gid, i, 0.f, 0.f, tab.x, tab.y, out, P.sincos_memo);
       }
     } else {
       mlp_actor(s, warp, lane);

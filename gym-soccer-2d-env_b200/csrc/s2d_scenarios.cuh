@@ -45,6 +45,7 @@ struct KernelParams {
   uint8_t type_of[32];        // player -> row of player_types (one assignment for every match of the handle)
   const uint8_t* type_of_match;  // or one assignment per match: [np][Nr] (device, match-minor like the state), else nullptr
   const float4* action_table; // [256] Discrete(n) -> {cmd, power, lowered direction, dash direction rate}, built on the host
+  const float2* sincos_memo;  // [kSinCosMemoSize] {sin, cos} of the whole degrees in [-360, 360] (device; s2d_math.cuh)
 };
 
 // Fills everything but the buffer pointers from a config.  `table` receives, per Discrete(n) action, the command
@@ -302,7 +303,8 @@ __device__ __forceinline__ Placement draw_placement_warp(const KernelParams& P, 
       const float s_try = u32_to_unit((t & 1) ? qz : qx) * 3.0f;
       const float d_try = static_cast<float>(u32_to_int((t & 1) ? qw : qy, 0, 360));
       float tsn, tcs;
-      sincos_deg(d_try, tsn, tcs);
+      if (P.sincos_memo) sincos_deg_memo(d_try, P.sincos_memo, tsn, tcs);  // whole degrees in [0, 360]: always a hit
+      else sincos_deg(d_try, tsn, tcs);
       const unsigned ok = __ballot_sync(full, have && ball_stays_inside(P, pl.bx, pl.by, s_try, tsn, tcs));
       if (ok) {
         const int first = __ffs(ok) - 1;
@@ -380,7 +382,8 @@ __device__ __forceinline__ void reset_episode(Episode& e, const KernelParams& P,
 // episode's result, S2D_RESULT_NONE while it goes on (step_kernel: the warp handles endings together, end_of_episode).
 template <int SCN, int ACT, class SP, bool DEFER_END = false>
 __device__ __forceinline__ int substep(Episode& e, const KernelParams& P, const SP& sp, uint64_t gid, int64_t i, float a0,
-                                        float a1, float a2, float a3, LaunchOut& out) {
+                                        float a1, float a2, float a3, LaunchOut& out,
+                                        const float2* sincos_memo = nullptr) {
   constexpr bool kTurns = ACT == S2D_ACT_TURNING || ACT == S2D_ACT_COMMAND;
   constexpr bool kKicks = ACT == S2D_ACT_COMMAND || SCN == S2D_SCENARIO_SHOOT;
   e.step_number += 1;  // reach_ball_env.py:55
@@ -410,7 +413,7 @@ __device__ __forceinline__ int substep(Episode& e, const KernelParams& P, const 
   float dx, dy, d2, rw;
   int rs;
   const float pbx = e.bx, pby = e.by;
-  simulate_cycle<kTurns, kKicks>(e, cmd, power, dir, rate, sp, dx, dy, d2, P.seed, gid);
+  simulate_cycle<kTurns, kKicks>(e, cmd, power, dir, rate, sp, dx, dy, d2, P.seed, gid, sincos_memo);
   const bool done = scenario_check<SCN>(e, P, sp, dx, dy, d2, pbx, pby, rw, rs);
   out.reward_sum += rw;
   e.ep_return += rw;
@@ -511,6 +514,10 @@ struct VariantSP {
 // alone would hold its 31 neighbours for ~560 instructions; so with up to kWarpDrawMax lanes due the warp makes each
 // lane's draws together (draw_placement_warp), with more (synchronised time-outs) every due lane draws for itself in
 // parallel.  Both orders consume the same Philox words: the results are identical.
+#ifndef S2D_SINCOS_MEMO_MIN_K
+#define S2D_SINCOS_MEMO_MIN_K 4  // launches of fewer cycles are bound by HBM: they leave the L1 to the streams
+#endif
+constexpr int kSinCosMemoMinK = S2D_SINCOS_MEMO_MIN_K;
 #ifndef S2D_WARP_DRAW_MAX
 #define S2D_WARP_DRAW_MAX 3
 #endif
@@ -577,6 +584,10 @@ __global__ void __launch_bounds__(kBlock, S2D_MIN_BLOCKS) step_kernel(const __gr
   const int64_t il = valid ? i : n - 1;
   load_episode(P.state, n, il, e);
   if (ACT == S2D_ACT_DISCRETE) {
+    // ReachBall: bodies are whole degrees (placement) and never turn, dash directions are snapped to whole degrees:
+    // the dash's sin / cos come from the memo (s2d_math.cuh; 5.8 KB, it stays in L1 next to the action table) when
+    // the launch is long enough for that to matter.
+    const float2* memo = (SCN != S2D_SCENARIO_SHOOT && K >= kSinCosMemoMinK) ? P.sincos_memo : nullptr;
     // the 4 KB action table stays in L1 (read-only path); `act` walks the lane's K action bytes
     const uint8_t* act = static_cast<const uint8_t*>(P.actions) + il * K;
 #pragma unroll 1
@@ -587,7 +598,7 @@ __global__ void __launch_bounds__(kBlock, S2D_MIN_BLOCKS) step_kernel(const __gr
         rs = substep<SCN, ACT, SP, true>(e, P, sp, gid, i, t.x, t.y, t.z, t.w, out);
       } else {  // ReachBall: always Dash(100, .): only the lowered direction and its rate are needed
         const float2 t = __ldg(reinterpret_cast<const float2*>(P.action_table + __ldg(act)) + 1);
-        rs = substep<SCN, ACT, SP, true>(e, P, sp, gid, i, 0.f, 0.f, t.x, t.y, out);
+        rs = substep<SCN, ACT, SP, true>(e, P, sp, gid, i, 0.f, 0.f, t.x, t.y, out, memo);
       }
       end_of_episode<SCN>(e, P, sp, gid, i, valid, rs, out);
     }

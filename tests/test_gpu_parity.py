@@ -185,6 +185,45 @@ def test_fused_substeps_equal_oracle_and_single_steps(mode, k):
     one.close()
 
 
+@pytest.mark.parametrize("step", [22.5, 0.0, 1.0])
+def test_sincos_memo_hits_and_misses_bit_exact(step):
+    """Launches of K >= 4 ReachBall Discrete(n) cycles read the dash's sin / cos from the whole-degree memo
+    (s2d_math.cuh: sincos_deg_memo) and fall back to the polynomial for any other angle.  dash_angle_step = 22.5 or 0
+    (no snapping) makes half of the 16 directions fractional, so warps mix hits and misses; step 1 with a few bodies
+    pushed off the whole degrees does the same from the state's side.  All of it must equal the oracle (which only
+    knows the polynomial) and the K = 1 launches (which never read the memo) bit for bit."""
+    n, k = 640, 8
+    kw = dict(seed=17, change_ball_velocity=True, max_steps=60, terminal_obs=True)
+    if step != 1.0:
+        kw["server_param"] = dict(dash_angle_step=step)
+    env = make_env(n, "discrete", substeps=k, **kw)
+    one = make_env(n, "discrete", substeps=1, **kw)
+    sim = OL.OracleSim(env.cfg, "f32")
+    env.reset_torch()
+    one.reset_torch()
+    sim.reset()
+    if step == 1.0:
+        st = sim.get_state()
+        for i in range(0, n, 3):
+            v = st[i].copy()
+            v[4] = float(np.float32(v[4] * 0.5 + 0.37))  # body: off the whole degrees
+            set_gpu_state(env, i, v)
+            set_gpu_state(one, i, v)
+            sim.set_state(i, v)
+    rng = np.random.default_rng(4)
+    for _ in range(20):
+        act = H.random_actions(rng, "discrete", n, k)
+        env.step_torch(torch.from_numpy(act))
+        sim.step(act, k)
+        assert_same_step(env, sim)
+        for j in range(k):
+            one.step_torch(torch.from_numpy(np.ascontiguousarray(act[:, j:j + 1])))
+        assert torch.equal(env.obs, one.obs) and torch.equal(env.state, one.state)
+    assert np.array_equal(gpu_state(env), sim.get_state())
+    env.close()
+    one.close()
+
+
 def test_shards_reproduce_the_global_run():
     """RNG is keyed on the GLOBAL env id: 3 shards (as 3 ranks would hold) == one big env."""
     n, k = 3000, 4

@@ -546,7 +546,19 @@ __device__ __forceinline__ void end_of_episode(Episode& e, const KernelParams& P
     if (!P.auto_reset) e.flags |= S2D_FLAG_DONE;
   }
   if (!P.auto_reset) return;
-  if (__popc(pending) <= kWarpDrawMax) {
+  if ((pending & (pending - 1u)) == 0u) {
+    // the usual case, ONE lane due: it places its new episode and runs the idle cycle in one piece, so that the
+    // compiler sees a player at rest with full stamina there (most of that cycle folds away)
+    const int lane = threadIdx.x & 31, src = __ffs(pending) - 1;
+    const uint32_t g_lo = __shfl_sync(full, static_cast<uint32_t>(gid), src);
+    const uint32_t g_hi = __shfl_sync(full, static_cast<uint32_t>(gid >> 32), src);
+    const uint32_t episode = __shfl_sync(full, e.episode, src);
+    const Placement pl = draw_placement_warp(P, (static_cast<uint64_t>(g_hi) << 32) | g_lo, episode, lane);
+    if (done) {
+      apply_placement(e, pl, sp);
+      finish_reset<SCN>(e, P, sp, gid);
+    }
+  } else if (__popc(pending) <= kWarpDrawMax) {
     const int lane = threadIdx.x & 31;
     do {
       const int src = __ffs(pending) - 1;

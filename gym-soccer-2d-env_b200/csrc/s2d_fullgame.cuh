@@ -231,15 +231,34 @@ __device__ __forceinline__ bool fg_commands(Episode& p, float4 a, float goto_dis
   const bool is_kick = c == S2D_CMD_KICK && may_kick;
   const bool user_dash = c == S2D_CMD_DASH, user_turn = c == S2D_CMD_TURN;
 
-  // geometry: player -> reference point
-  float dist = 0.0f, rel = 0.0f;
-  if (__any_sync(full, is_goto || is_kick)) {
+  // The operands of the three long chains of a command - geometry to the reference point (square root, atan2), the
+  // player's speed (square root; a turn's inertia), sin / cos of body + direction (dash, kick) - are all known once
+  // the command is decoded, before go-to-point has decided anything.  They are evaluated up front in ONE block, side by
+  // side, for every lane whose command MAY need them: this kernel is bound by the length of the thread's dependency
+  // chain, not by issue slots, and three independent chains overlap where three voted blocks in a row did not.
+  const bool may_turn = user_turn || is_goto;                  // superset of do_turn
+  const bool may_dsh = (user_dash || is_goto) && may_dash;     // superset of do_dash
+  float dist = 0.0f, rel = 0.0f, speed = 0.0f;
+  float dir = 0.0f, rate = 1.0f, sn = 0.0f, cs = 1.0f;
+  const float user_power = clampf(sp.min_dash_power(), a.y, sp.max_dash_power());
+  const bool back = user_dash && user_power < 0.0f;
+  auto dash_kick_direction = [&]() {  // dash direction (go-to-point dashes straight: direction 0) and the one sincos
+    dash_direction(user_dash ? a.z : 0.0f, sp, dir, rate);
+    const float kick_dir = clampf(sp.min_moment(), a.z, sp.max_moment());
+    const float d = is_kick ? kick_dir : back ? dir + 180.0f : dir;
+    sincos_deg(p.body + d, sn, cs);  // (of the body angle before this cycle's turn: who turns neither dashes nor kicks)
+  };
+  if (__any_sync(full, is_goto || is_kick || user_turn)) {
     // (lanes that are not concerned get harmless operands: a zero numerator or denominator, or sqrt(0), would send
     // the whole warp through the slow paths of the IEEE division and square root)
     const float dx = is_goto ? a.y - p.px : is_kick ? p.bx - p.px : 1.0f;
     const float dy = is_goto ? a.z - p.py : is_kick ? p.by - p.py : 0.5f;
     dist = hypot2(dx, dy);
     rel = norm_deg_360(atan2_deg(dy, dx) - p.body);
+    speed = hypot2_or_zero(may_turn ? p.vx : 1.0f, may_turn ? p.vy : 0.0f);  // (a standing player: often)
+    dash_kick_direction();
+  } else if (__any_sync(full, may_dsh)) {  // nobody but dashers in the warp
+    dash_kick_direction();
   }
 
   // go-to-point decides: nothing (arrived) | turn towards the target | dash straight at it
@@ -259,8 +278,7 @@ __device__ __forceinline__ bool fg_commands(Episode& p, float4 a, float goto_dis
   // turn
   const bool do_turn = user_turn || goto_turn;
   if (__any_sync(full, do_turn)) {
-    const float speed = hypot2_or_zero(do_turn ? p.vx : 1.0f, do_turn ? p.vy : 0.0f);  // (a standing player: often)
-    const float inertia = 1.0f + sp.inertia_moment() * speed;
+    const float inertia = 1.0f + sp.inertia_moment() * (do_turn ? speed : 0.2f);
     float moment = goto_turn ? clampf(sp.min_moment(), rel * inertia, sp.max_moment()) : user_turn ? a.y : 1.0f;
     moment = clampf(sp.min_moment(), moment, sp.max_moment());
     if (SP::kNoise) moment = moment * (1.0f + sp.player_rand() * u11(noise_block(nz, static_cast<uint32_t>(agent)).z));
@@ -268,18 +286,7 @@ __device__ __forceinline__ bool fg_commands(Episode& p, float4 a, float goto_dis
     p.body = do_turn ? body : p.body;
   }
 
-  // dash direction (go-to-point dashes straight: direction 0) and the one sincos
   const bool do_dash = (user_dash || goto_dash) && may_dash;  // (AfterGoal: the clock stands still, only turns work)
-  float dir = 0.0f, rate = 1.0f;
-  if (__any_sync(full, do_dash)) dash_direction(user_dash ? a.z : 0.0f, sp, dir, rate);
-  const float user_power = clampf(sp.min_dash_power(), a.y, sp.max_dash_power());
-  const bool back = user_dash && user_power < 0.0f;
-  float sn = 0.0f, cs = 1.0f;
-  if (__any_sync(full, do_dash || is_kick)) {
-    const float kick_dir = clampf(sp.min_moment(), a.z, sp.max_moment());
-    const float d = is_kick ? kick_dir : back ? dir + 180.0f : dir;
-    sincos_deg(p.body + d, sn, cs);
-  }
 
   // dash
   if (__any_sync(full, do_dash)) {

@@ -12,6 +12,7 @@ using namespace s2d;
 struct Emu {
   KernelParams kp;
   float4 table[256];
+  float2 memo[kSinCosMemoSize];  // sincos_deg over the whole degrees, as fill_sincos_memo (s2d_api.cu) writes it
   bool default_sp;  // same dispatch as s2d_create: constant-folded accessors for the default ServerParam
   std::vector<unsigned char> state;
 };
@@ -27,10 +28,12 @@ static void step_all(Emu* h, const void* actions, int K, float* obs, float* rewa
     LaunchOut out;
     load_episode(P.state, n, i, e);
     const uint64_t gid = (uint64_t)(P.env_id_offset + i);
+    // step_kernel's rule: ReachBall Discrete(n) launches of K >= S2D_SINCOS_MEMO_MIN_K (4) cycles read the memo
+    const float2* memo = (ACT == S2D_ACT_DISCRETE && SCN != S2D_SCENARIO_SHOOT && K >= 4) ? h->memo : nullptr;
     for (int k = 0; k < K; ++k) {
       if (ACT == S2D_ACT_DISCRETE) {
         const float4 t = h->table[((const uint8_t*)actions)[i * K + k]];
-        substep<SCN, ACT>(e, P, sp, gid, i, t.x, t.y, t.z, t.w, out);
+        substep<SCN, ACT>(e, P, sp, gid, i, t.x, t.y, t.z, t.w, out, memo);
       } else if (ACT == S2D_ACT_CONTINUOUS) {
         substep<SCN, ACT>(e, P, sp, gid, i, ((const float*)actions)[i * K + k], 0.f, 0.f, 0.f, out);
       } else {
@@ -57,6 +60,8 @@ void* emu_create(const S2DConfig* cfg) {
   h->state.assign((size_t)cfg->num_envs * kStateBytesPerEnv, 0);
   h->kp.state = h->state.data();
   h->kp.action_table = h->table;
+  for (int j = 0; j < kSinCosMemoSize; ++j) sincos_deg((float)(j - kSinCosMemoHalf), h->memo[j].x, h->memo[j].y);
+  h->kp.sincos_memo = h->memo;
   return h;
 }
 void emu_destroy(void* p) { delete (Emu*)p; }

@@ -62,6 +62,27 @@ def test_kernel_source_runtime_params_path(mode):
     assert np.array_equal(emu.get_state(), sim.get_state())
 
 
+@pytest.mark.parametrize("step", [1.0, 22.5, 0.0])
+def test_kernel_source_sincos_memo_hits_and_misses(step):
+    """ReachBall Discrete(n) launches of K >= 4 cycles take the dash's sin / cos from the whole-degree memo
+    (s2d_math.cuh: sincos_deg_memo; the emulation applies step_kernel's rule).  dash_angle_step = 1 only hits;
+    22.5 and 0 (no snapping) make half of the 16 directions fractional, those miss and take the polynomial.  The
+    oracle only knows the polynomial: equal bits either way."""
+    n, k = 131, 8
+    kw = dict(sp=dict(dash_angle_step=step)) if step != 1.0 else {}
+    cfg = H.make_config(n, "discrete", seed=5, change_ball_velocity=1, max_steps=50, **kw)
+    emu, sim = EL.EmuSim(cfg), OL.OracleSim(cfg, "f32")
+    assert np.array_equal(emu.reset(), sim.reset())
+    rng = np.random.default_rng(1)
+    for t in range(40):
+        act = H.random_actions(rng, "discrete", n, k)
+        emu.step(act, k)
+        sim.step(act, k)
+        assert np.array_equal(emu.done, sim.done) and np.array_equal(emu.result, sim.result)
+        assert np.array_equal(emu.obs, sim.obs) and np.array_equal(emu.reward, sim.reward)
+    assert np.array_equal(emu.get_state(), sim.get_state())
+
+
 @pytest.mark.parametrize("collision_model", [0, 1])
 def test_kernel_source_hand_placed_states(collision_model):
     cases = HAND_PLACED_STATES + [[0, 0, 0.2, 0, 0, 8000, 1, 1, 130600, 1.0, 0, -0.5, 0, 1, 5, 0, 3, 3, 1],

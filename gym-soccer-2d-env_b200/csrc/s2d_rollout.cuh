@@ -19,6 +19,9 @@
 #pragma once
 #include "s2d_scenarios.cuh"
 
+#ifndef S2D_ROLLOUT_DRAW_MEMO
+#define S2D_ROLLOUT_DRAW_MEMO true
+#endif
 namespace s2d {
 
 constexpr int kMlpHidden = 64;
@@ -375,7 +378,7 @@ __global__ void __launch_bounds__(kBlock, S2D_ROLLOUT_MIN_BLOCKS)
       }
       out.reward_sum = 0.0f;
       rs = substep<SCN, ACT, SP, true>(e, P, sp, gid, i, av.x, kActDim == 4 ? av.y : 0.f, kActDim == 4 ? av.z : 0.f,
-                                       kActDim == 4 ? av.w : 0.f, out);
+                                       kActDim == 4 ? av.w : 0.f, out, kActDim == 1 ? P.sincos_memo : nullptr);
     }
     const float rw = out.reward_sum;
     out.reward_sum = reward_before + rw;  // ... and is put back together in the order the step kernel adds it up)
@@ -385,7 +388,7 @@ __global__ void __launch_bounds__(kBlock, S2D_ROLLOUT_MIN_BLOCKS)
       if (T.reward) T.reward[at] = rw;
       if (T.done) T.done[at] = static_cast<uint8_t>(rs != S2D_RESULT_NONE);
     }
-    end_of_episode<SCN>(e, P, sp, gid, i, valid, rs, out);
+    end_of_episode<SCN, SP, false, S2D_ROLLOUT_DRAW_MEMO>(e, P, sp, gid, i, valid, rs, out);
   }
   if (valid) {
     store_episode(P.state, n, i, e);

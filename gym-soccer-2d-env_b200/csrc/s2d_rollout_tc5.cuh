@@ -21,6 +21,9 @@
 #pragma once
 #include "s2d_rollout.cuh"
 
+#ifndef S2D_ROLLOUT_DRAW_MEMO
+#define S2D_ROLLOUT_DRAW_MEMO true
+#endif
 namespace s2d {
 
 #ifndef S2D_HOST_EMU
@@ -300,7 +303,7 @@ __global__ void __launch_bounds__(kBlock, S2D_ROLLOUT_MIN_BLOCKS)
       }
       out.reward_sum = 0.0f;
       rs = substep<SCN, ACT, SP, true>(e, P, sp, gid, i, av.x, kActDim == 4 ? av.y : 0.f, kActDim == 4 ? av.z : 0.f,
-                                       kActDim == 4 ? av.w : 0.f, out);
+                                       kActDim == 4 ? av.w : 0.f, out, kActDim == 1 ? P.sincos_memo : nullptr);
     } else {
     if (epsilon > 0.0f) {  // exploration: the same counter stream as the mma.sync kernel
       const uint4 w = philox4x32_10(P.seed, gid, e.cycle, RNG_ACTION, 1);
@@ -324,7 +327,7 @@ __global__ void __launch_bounds__(kBlock, S2D_ROLLOUT_MIN_BLOCKS)
       if (T.reward) T.reward[at] = rw;
       if (T.done) T.done[at] = static_cast<uint8_t>(rs != S2D_RESULT_NONE);
     }
-    end_of_episode<SCN>(e, P, sp, gid, i, valid, rs, out);
+    end_of_episode<SCN, SP, false, S2D_ROLLOUT_DRAW_MEMO>(e, P, sp, gid, i, valid, rs, out);
   }
   if (valid) {
     store_episode(P.state, n, i, e);

@@ -277,6 +277,7 @@ __device__ __forceinline__ Placement draw_placement(const KernelParams& P, uint6
 // lanes 0-1 compute the two placement blocks, lanes 2-31 thirty ball-velocity blocks (tries 0..59), every lane
 // evaluates one try per round, and a ballot picks the first accepted one - exactly the try the sequential loop of
 // draw_placement stops at.  Returns the placement in every lane.
+template <bool MEMO = true>
 __device__ __forceinline__ Placement draw_placement_warp(const KernelParams& P, uint64_t gid, uint32_t episode, int lane) {
   const unsigned full = 0xffffffffu;
   const bool placement_lane = lane < 2;
@@ -303,7 +304,7 @@ __device__ __forceinline__ Placement draw_placement_warp(const KernelParams& P, 
       const float s_try = u32_to_unit((t & 1) ? qz : qx) * 3.0f;
       const float d_try = static_cast<float>(u32_to_int((t & 1) ? qw : qy, 0, 360));
       float tsn, tcs;
-      if (P.sincos_memo) sincos_deg_memo(d_try, P.sincos_memo, tsn, tcs);  // whole degrees in [0, 360]: always a hit
+      if (MEMO && P.sincos_memo) sincos_deg_memo(d_try, P.sincos_memo, tsn, tcs);  // whole degrees in [0, 360]: always a hit
       else sincos_deg(d_try, tsn, tcs);
       const unsigned ok = __ballot_sync(full, have && ball_stays_inside(P, pl.bx, pl.by, s_try, tsn, tcs));
       if (ok) {
@@ -523,7 +524,9 @@ constexpr int kSinCosMemoMinK = S2D_SINCOS_MEMO_MIN_K;
 #endif
 constexpr int kWarpDrawMax = S2D_WARP_DRAW_MAX;
 
-template <int SCN, class SP>
+// ONE_PIECE / MEMO: the step kernels' refinements (one lane due: placement and idle cycle in one piece; the draws'
+// sin / cos from the whole-degree memo); the fused-policy kernels, at their register limit, are faster without them.
+template <int SCN, class SP, bool ONE_PIECE = true, bool MEMO = true>
 __device__ __forceinline__ void end_of_episode(Episode& e, const KernelParams& P, const SP& sp, uint64_t gid, int64_t i,
                                                bool valid, int rs, LaunchOut& out) {
   const unsigned full = 0xffffffffu;
@@ -546,14 +549,14 @@ __device__ __forceinline__ void end_of_episode(Episode& e, const KernelParams& P
     if (!P.auto_reset) e.flags |= S2D_FLAG_DONE;
   }
   if (!P.auto_reset) return;
-  if ((pending & (pending - 1u)) == 0u) {
+  if (ONE_PIECE && (pending & (pending - 1u)) == 0u) {
     // the usual case, ONE lane due: it places its new episode and runs the idle cycle in one piece, so that the
     // compiler sees a player at rest with full stamina there (most of that cycle folds away)
     const int lane = threadIdx.x & 31, src = __ffs(pending) - 1;
     const uint32_t g_lo = __shfl_sync(full, static_cast<uint32_t>(gid), src);
     const uint32_t g_hi = __shfl_sync(full, static_cast<uint32_t>(gid >> 32), src);
     const uint32_t episode = __shfl_sync(full, e.episode, src);
-    const Placement pl = draw_placement_warp(P, (static_cast<uint64_t>(g_hi) << 32) | g_lo, episode, lane);
+    const Placement pl = draw_placement_warp<MEMO>(P, (static_cast<uint64_t>(g_hi) << 32) | g_lo, episode, lane);
     if (done) {
       apply_placement(e, pl, sp);
       finish_reset<SCN>(e, P, sp, gid);
@@ -566,7 +569,7 @@ __device__ __forceinline__ void end_of_episode(Episode& e, const KernelParams& P
       const uint32_t g_lo = __shfl_sync(full, static_cast<uint32_t>(gid), src);
       const uint32_t g_hi = __shfl_sync(full, static_cast<uint32_t>(gid >> 32), src);
       const uint32_t episode = __shfl_sync(full, e.episode, src);
-      const Placement pl = draw_placement_warp(P, (static_cast<uint64_t>(g_hi) << 32) | g_lo, episode, lane);
+      const Placement pl = draw_placement_warp<MEMO>(P, (static_cast<uint64_t>(g_hi) << 32) | g_lo, episode, lane);
       if (lane == src) apply_placement(e, pl, sp);
     } while (pending);
     if (done) finish_reset<SCN>(e, P, sp, gid);
@@ -615,10 +618,12 @@ __global__ void __launch_bounds__(kBlock, S2D_MIN_BLOCKS) step_kernel(const __gr
       end_of_episode<SCN>(e, P, sp, gid, i, valid, rs, out);
     }
   } else if (ACT == S2D_ACT_CONTINUOUS) {
+    // Box(1): the direction a * 180 is snapped to dash_angle_step = 1 as well and nobody turns - whole degrees again
+    const float2* memo = K >= kSinCosMemoMinK ? P.sincos_memo : nullptr;
     const float* act = static_cast<const float*>(P.actions) + il * K;
 #pragma unroll 1
     for (int k = 0; k < K; ++k) {
-      const int rs = substep<SCN, ACT, SP, true>(e, P, sp, gid, i, __ldg(act + k), 0.f, 0.f, 0.f, out);
+      const int rs = substep<SCN, ACT, SP, true>(e, P, sp, gid, i, __ldg(act + k), 0.f, 0.f, 0.f, out, memo);
       end_of_episode<SCN>(e, P, sp, gid, i, valid, rs, out);
     }
   } else {

@@ -9,14 +9,18 @@ import torch  # noqa: E402
 
 from soccer2d_b200 import Soccer2DVecEnv  # noqa: E402
 
-KW = dict(use_continuous_action=False, action_space_size=16, change_ball_position=True,
+CONT = os.environ.get("S2D_TUNE_CONTINUOUS", "0") == "1"  # Box(1) actions (the dash direction) instead of Discrete(16)
+KW = dict(use_continuous_action=CONT, action_space_size=16, change_ball_position=True,
           change_ball_velocity=os.environ.get("S2D_TUNE_STILL", "0") != "1")  # S2D_TUNE_STILL=1: the ball rests (reference default)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 out = []
 for name, n, k, warm, steps in (("k16", 1 << 20, 16, int(os.environ.get("S2D_TUNE_WARM", 14)), 30), ("k1", 1 << 23, 1, 10, 30)):  # S2D_TUNE_WARM=150: steady state of the episode ends
     env = Soccer2DVecEnv(n, device="cuda:0", seed=0, substeps=k, **KW)
     g = torch.Generator(device="cuda").manual_seed(0)
-    pool = [torch.randint(0, 16, (n, k), dtype=torch.uint8, device="cuda", generator=g) for _ in range(2)]
+    if CONT:
+        pool = [torch.rand((n, k), dtype=torch.float32, device="cuda", generator=g) * 2 - 1 for _ in range(2)]
+    else:
+        pool = [torch.randint(0, 16, (n, k), dtype=torch.uint8, device="cuda", generator=g) for _ in range(2)]
     env.reset_torch()
     for i in range(warm):
         env.bind_actions(pool[i % 2])
